@@ -1,0 +1,169 @@
+/*
+ * vpbs_commit.h — C ABI of libvpbs_commit.so: the B200 (sm_100a) polynomial-commitment path of
+ * vPBS (zama-ai/verifiable-fhe-paper), i.e. what plonky2 0.2.0 does inside
+ * PolynomialBatch::from_values / from_coeffs and MerkleTree::new for
+ * F = GoldilocksField, C = PoseidonGoldilocksConfig.
+ *
+ * The reference reaches this path only through plonky2 (crates.io dependency,
+ * /root/reference/Cargo.toml:7): `prove()` at /root/reference/src/vtfhe/ivc_based_vpbs.rs:302,
+ * :333, :364 and `builder.build::<C>()` at :40, :46, :61, :275.  Each entry point below names the
+ * plonky2 0.2.0 item ("[P2] file::item") whose FFI replacement it is; INTEGRATION.md shows the
+ * Rust `extern "C"` block and the plonky2 patch that bind them.
+ *
+ * Conventions
+ *  - every field element is a uint64_t (GoldilocksField is #[repr(transparent)] over u64);
+ *    inputs may be non-canonical (any u64), outputs are canonical (< p = 2^64 - 2^32 + 1);
+ *  - a hash (HashOut) is 4 consecutive uint64_t;
+ *  - all functions return VPBS_OK (0) or a negative vpbs_status; nothing throws or aborts across
+ *    the boundary; vpbs_last_error() gives the message of the last failure on that context;
+ *  - there is NO CPU fallback: without a usable CUDA device every call fails with VPBS_ERR_CUDA;
+ *  - a context is bound to one device and one stream and is not re-entrant (one call in flight
+ *    per context); distinct contexts are independent and may be used from different threads;
+ *  - host entry points take caller-owned host memory and never retain it past return;
+ *    `*_dev` entry points take device pointers on the context's device and are asynchronous on
+ *    the context's stream (see vpbs_ctx_set_stream / vpbs_ctx_sync).
+ */
+#ifndef VPBS_COMMIT_H
+#define VPBS_COMMIT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPBS_ABI_VERSION 1
+#define VPBS_SALT_SIZE 4 /* [P2] fri/oracle.rs SALT_SIZE */
+
+typedef enum vpbs_status {
+  VPBS_OK = 0,
+  VPBS_ERR_ARG = -1,   /* what plonky2 assert!s on: non power of two, cap_height > log2(leaves), ... */
+  VPBS_ERR_CUDA = -2,  /* no device / kernel or copy failure */
+  VPBS_ERR_OOM = -3,   /* device or pinned-host allocation failed */
+  VPBS_ERR_STATE = -4  /* context unusable (destroyed / wrong device) */
+} vpbs_status;
+
+typedef struct vpbs_ctx vpbs_ctx;
+
+/* Per-call timings in milliseconds, named after the TimingTree scopes plonky2 prints for the same
+ * work ([P2] fri/oracle.rs timed!(..) labels; the reference prints them per step,
+ * /root/reference/src/vtfhe/ivc_based_vpbs.rs:301-309).  "transpose LDEs" is fused into the last
+ * NTT pass here, so it is reported inside fft_ms. */
+typedef struct vpbs_stats {
+  float h2d_ms;    /* host -> device copies of the inputs (0 for *_dev calls)      */
+  float ifft_ms;   /* "IFFT"                                                       */
+  float fft_ms;    /* "FFT + blinding" + "transpose LDEs"                          */
+  float merkle_ms; /* "build Merkle tree"                                          */
+  float d2h_ms;    /* device -> host copies of the outputs (0 for *_dev calls)     */
+  float total_ms;  /* first event to last event of the call                        */
+  uint64_t kernel_launches; /* kernels of this library launched by the call        */
+} vpbs_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int vpbs_abi_version(void);
+int vpbs_device_count(void); /* >= 0, or a negative vpbs_status */
+int vpbs_ctx_create(int device, vpbs_ctx** out);
+void vpbs_ctx_destroy(vpbs_ctx* ctx);
+/* Use an existing CUDA stream (a cudaStream_t passed as void*; NULL = the context's own). */
+int vpbs_ctx_set_stream(vpbs_ctx* ctx, void* cuda_stream);
+int vpbs_ctx_sync(vpbs_ctx* ctx);
+const char* vpbs_last_error(vpbs_ctx* ctx); /* ctx may be NULL: last create/global error */
+/* Total kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t vpbs_ctx_kernel_launches(vpbs_ctx* ctx);
+
+/* Pinned host memory for callers that want full-speed PCIe copies. */
+void* vpbs_host_alloc(size_t bytes);
+void vpbs_host_free(void* p);
+
+/* ---- single-polynomial transforms (host memory, in place, natural order in and out) -------- */
+/* [P2] plonky2_field/src/fft.rs fft_with_options(poly, None, None): out[i] = sum_j c_j w^(ij). */
+int vpbs_fft(vpbs_ctx* ctx, uint64_t* inout, uint32_t log_n);
+/* [P2] plonky2_field/src/fft.rs ifft_with_options: c_j = n^-1 sum_i v_i w^(-ij). */
+int vpbs_ifft(vpbs_ctx* ctx, uint64_t* inout, uint32_t log_n);
+/* [P2] plonky2_field/src/polynomial/mod.rs PolynomialCoeffs::coset_fft_with_options(shift, ..). */
+int vpbs_coset_fft(vpbs_ctx* ctx, uint64_t* inout, uint32_t log_n, uint64_t shift);
+
+/* ---- hashing (host memory) ------------------------------------------------------------------ */
+/* [P2] plonky2/src/hash/poseidon.rs Poseidon::poseidon on `count` independent 12-word states. */
+int vpbs_poseidon_permute(vpbs_ctx* ctx, uint64_t* states_inout, uint64_t count);
+/* [P2] plonk/config.rs Hasher::hash_or_noop over `count` rows of `len` elements (row-major):
+ * len <= 4 copies (canonical, zero padded), otherwise hash_n_to_m_no_pad (overwrite-mode sponge). */
+int vpbs_hash_or_noop_batch(vpbs_ctx* ctx, const uint64_t* rows, uint64_t count, uint32_t len,
+                            uint64_t* hashes_out /* count x 4 */);
+/* [P2] hash/hashing.rs compress == PoseidonHash::two_to_one on `count` pairs. */
+int vpbs_two_to_one_batch(vpbs_ctx* ctx, const uint64_t* left /* count x 4 */,
+                          const uint64_t* right /* count x 4 */, uint64_t count,
+                          uint64_t* hashes_out /* count x 4 */);
+
+/* ---- [P2] plonky2/src/hash/merkle_tree.rs MerkleTree::new(leaves, cap_height) ----------------
+ * leaves_rowmajor: nleaves x leaf_len.  digests_out: 2*(nleaves - 2^cap_height) hashes in
+ * plonky2's layout (per cap subtree: left subtree digests || left child || right child || right
+ * subtree digests, so MerkleTree::prove's index formula applies unchanged); may be NULL when that
+ * count is 0 (tree is all cap).  cap_out: 2^cap_height hashes.
+ * VPBS_ERR_ARG if nleaves is not a power of two or cap_height > log2(nleaves) (plonky2 panics). */
+int vpbs_merkle_new(vpbs_ctx* ctx, const uint64_t* leaves_rowmajor, uint64_t nleaves,
+                    uint32_t leaf_len, uint32_t cap_height, uint64_t* digests_out,
+                    uint64_t* cap_out);
+
+/* ---- [P2] plonky2/src/fri/oracle.rs PolynomialBatch::lde_values --------------------------------
+ * cols: ncols pointers to n = 2^log_n elements each (a Vec<PolynomialValues<F>> is ncols separately
+ * allocated Vec<F>).  inputs_are_coeffs = 0: values (ifft first, as from_values), 1: coefficients.
+ * coeffs_out: NULL or ncols pointers receiving the n coefficients of each polynomial.
+ * lde_cols_out: ncols * (n << rate_bits), column-major, NATURAL order: column c, index i holds
+ * poly_c(7 * w_m^i) — exactly lde_values()[c][i]. */
+int vpbs_lde_batch(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                   uint32_t rate_bits, int inputs_are_coeffs, uint64_t* const* coeffs_out,
+                   uint64_t* lde_cols_out);
+
+/* ---- [P2] plonky2/src/fri/oracle.rs PolynomialBatch::from_values / from_coeffs ------------------
+ * The whole commit: (ifft) -> lde + coset fft (shift 7) -> transpose + reverse_index_bits ->
+ * MerkleTree::new.  m = n << rate_bits leaves of width ncols (+4 if salt_cols).
+ *  salt_cols   NULL (blinding = false, the only case the reference uses:
+ *              CircuitConfig::standard_recursion_config(), ivc_based_vpbs.rs:38,41,48,190), or
+ *              VPBS_SALT_SIZE pointers to m random elements each, drawn by the caller (the RNG stays
+ *              on the host so the device path is deterministic); they are appended to every leaf
+ *              the way lde_values() chains them.
+ *  coeffs_out  NULL or ncols pointers (n each): PolynomialBatch.polynomials.
+ *  leaves_out  m x width row-major, leaf k = natural LDE row bitrev(k): MerkleTree.leaves.
+ *              May be NULL (cap/digests only).
+ *  digests_out 2*(m - 2^cap_height) hashes, plonky2 layout; NULL allowed only if that is 0 or the
+ *              caller does not want them.
+ *  cap_out     2^cap_height hashes (required).
+ *  stats       NULL or timing breakdown. */
+int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                const uint64_t* const* salt_cols, uint64_t* const* coeffs_out, uint64_t* leaves_out,
+                uint64_t* digests_out, uint64_t* cap_out, vpbs_stats* stats);
+
+/* Same computation on device-resident data (the prover keeps its batches in HBM; also what
+ * bench.py times as the kernel-only number).  d_cols: ncols x n column-major, contiguous.
+ * d_salt: NULL or 4 x m.  d_coeffs_out: NULL or ncols x n.  d_leaves_out: m x width (required).
+ * d_digests_out: required unless the tree is all cap.  d_cap_out: required.
+ * Asynchronous on the context's stream; stats (if non-NULL) forces a sync. */
+int vpbs_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
+                    uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                    const uint64_t* d_salt, uint64_t* d_coeffs_out, uint64_t* d_leaves_out,
+                    uint64_t* d_digests_out, uint64_t* d_cap_out, vpbs_stats* stats);
+
+/* Row-range shard of one commit for multi-GPU proving (SURVEY.md §8(e) partitioning B): computes
+ * only leaves [first_leaf, first_leaf + nleaves_shard) of the m-leaf tree, where the shard is a
+ * whole number of cap subtrees (or, if smaller than a cap subtree, a power-of-two aligned piece of
+ * one) — already in leaf order — and the digests and subtree roots under it.
+ *  d_cols            all ncols x n inputs (every shard needs every coefficient column)
+ *  d_leaves_out      nleaves_shard x width
+ *  d_digests_out     the plonky2-layout digests of the cap subtrees this shard owns
+ *                    (2*(nleaves_shard - nroots) hashes)
+ *  d_roots_out       nroots = max(1, nleaves_shard >> (log2 m - cap_height)) hashes: the cap
+ *                    entries first_leaf >> (log2 m - cap_height) ... owned by this shard.
+ * The only cross-GPU traffic of a sharded commit is the gather of d_roots_out (32 B per entry). */
+int vpbs_commit_shard_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
+                          uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                          uint64_t first_leaf, uint64_t nleaves_shard, uint64_t* d_coeffs_out,
+                          uint64_t* d_leaves_out, uint64_t* d_digests_out, uint64_t* d_roots_out,
+                          vpbs_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPBS_COMMIT_H */

@@ -1,0 +1,189 @@
+"""ctypes binding for oracle/liboracle.so (CPU restatement of plonky2 0.2.0's commit path).
+
+TEST INFRASTRUCTURE ONLY: import this from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never from the product package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+P = 0xFFFFFFFF00000001
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u64pp = ctypes.POINTER(_u64p)
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle.c -> liboracle.so with the recipe in oracle/Makefile."""
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "Makefile")]
+    if force or not os.path.exists(_SO) or any(
+            os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = ctypes.CDLL(_SO)
+        u64, u32, sz = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_size_t
+        for name in ("orc_gl_add", "orc_gl_sub", "orc_gl_mul", "orc_gl_pow"):
+            getattr(L, name).restype = u64
+            getattr(L, name).argtypes = [u64, u64]
+        L.orc_gl_inv.restype = u64
+        L.orc_gl_inv.argtypes = [u64]
+        L.orc_primitive_root_of_unity.restype = u64
+        L.orc_primitive_root_of_unity.argtypes = [ctypes.c_uint]
+        for name in ("orc_fft", "orc_ifft"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [_u64p, ctypes.c_uint]
+        L.orc_coset_fft.restype = None
+        L.orc_coset_fft.argtypes = [_u64p, ctypes.c_uint, u64]
+        L.orc_lde.restype = None
+        L.orc_lde.argtypes = [_u64p, ctypes.c_uint, ctypes.c_uint, _u64p]
+        L.orc_poseidon_round_constants.argtypes = [_u64p]
+        L.orc_poseidon.argtypes = [_u64p]
+        L.orc_hash_no_pad.argtypes = [_u64p, sz, _u64p]
+        L.orc_hash_or_noop.argtypes = [_u64p, sz, _u64p]
+        L.orc_two_to_one.argtypes = [_u64p, _u64p, _u64p]
+        L.orc_merkle_new.restype = ctypes.c_int
+        L.orc_merkle_new.argtypes = [_u64p, u64, u32, u32, _u64p, _u64p]
+        L.orc_merkle_prove.restype = ctypes.c_int
+        L.orc_merkle_prove.argtypes = [_u64p, u64, u32, u64, _u64p]
+        L.orc_merkle_verify.restype = ctypes.c_int
+        L.orc_merkle_verify.argtypes = [_u64p, u32, u64, _u64p, u32, _u64p, u32]
+        L.orc_commit.restype = ctypes.c_int
+        L.orc_commit.argtypes = [_u64pp, u32, u32, u32, u32, ctypes.c_int, _u64pp,
+                                 _u64p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_set_threads.argtypes = [ctypes.c_int]
+        L.orc_get_threads.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u64p)
+
+
+def _arr(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+def gl_mul(a, b): return lib().orc_gl_mul(int(a), int(b))
+def gl_add(a, b): return lib().orc_gl_add(int(a), int(b))
+def gl_sub(a, b): return lib().orc_gl_sub(int(a), int(b))
+def gl_pow(a, e): return lib().orc_gl_pow(int(a), int(e))
+def gl_inv(a): return lib().orc_gl_inv(int(a))
+def primitive_root_of_unity(k): return lib().orc_primitive_root_of_unity(int(k))
+def set_threads(n): lib().orc_set_threads(int(n))
+def get_threads(): return lib().orc_get_threads()
+
+
+def _log2(n):
+    assert n > 0 and n & (n - 1) == 0, "length must be a power of two"
+    return n.bit_length() - 1
+
+
+def fft(v):
+    a = _arr(v).copy(); lib().orc_fft(_p(a), _log2(a.size)); return a
+
+
+def ifft(v):
+    a = _arr(v).copy(); lib().orc_ifft(_p(a), _log2(a.size)); return a
+
+
+def coset_fft(v, shift):
+    a = _arr(v).copy(); lib().orc_coset_fft(_p(a), _log2(a.size), int(shift)); return a
+
+
+def lde(coeffs, rate_bits):
+    a = _arr(coeffs); out = np.empty(a.size << rate_bits, dtype=np.uint64)
+    lib().orc_lde(_p(a), _log2(a.size), rate_bits, _p(out)); return out
+
+
+def round_constants():
+    out = np.empty(360, dtype=np.uint64); lib().orc_poseidon_round_constants(_p(out)); return out
+
+
+def poseidon(state):
+    a = _arr(state).copy(); assert a.size == 12; lib().orc_poseidon(_p(a)); return a
+
+
+def hash_no_pad(x):
+    a = _arr(x); out = np.empty(4, dtype=np.uint64)
+    lib().orc_hash_no_pad(_p(a) if a.size else None, a.size, _p(out)); return out
+
+
+def hash_or_noop(x):
+    a = _arr(x); out = np.empty(4, dtype=np.uint64)
+    lib().orc_hash_or_noop(_p(a) if a.size else None, a.size, _p(out)); return out
+
+
+def two_to_one(l, r):
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_two_to_one(_p(_arr(l)), _p(_arr(r)), _p(out)); return out
+
+
+def merkle_new(leaves, cap_height):
+    """leaves: (nleaves, leaf_len) uint64 -> (digests (2(n-2^h),4), cap (2^h,4))."""
+    a = _arr(leaves); n, w = a.shape
+    digests = np.empty((2 * (n - (1 << cap_height)) if n >= (1 << cap_height) else 0, 4), np.uint64)
+    cap = np.empty((1 << cap_height, 4), np.uint64)
+    rc = lib().orc_merkle_new(_p(a) if a.size else None, n, w, cap_height,
+                              _p(digests) if digests.size else None, _p(cap))
+    if rc != 0:
+        raise ValueError("orc_merkle_new: bad arguments")
+    return digests, cap
+
+
+def merkle_prove(digests, nleaves, cap_height, leaf_index):
+    d = _arr(digests)
+    sib = np.empty((_log2(nleaves) - cap_height, 4), np.uint64)
+    rc = lib().orc_merkle_prove(_p(d) if d.size else None, nleaves, cap_height, leaf_index,
+                                _p(sib) if sib.size else None)
+    if rc != 0:
+        raise ValueError("orc_merkle_prove: bad arguments")
+    return sib
+
+
+def merkle_verify(leaf, leaf_index, siblings, cap):
+    l, s, c = _arr(leaf), _arr(siblings), _arr(cap)
+    return lib().orc_merkle_verify(_p(l) if l.size else None, l.size, leaf_index,
+                                   _p(s) if s.size else None, s.shape[0] if s.size else 0,
+                                   _p(c), _log2(c.shape[0])) == 0
+
+
+def commit(cols, rate_bits, cap_height, inputs_are_coeffs=False, salt_cols=None, want_lde=False):
+    """cols: (ncols, n) uint64.  Returns dict(coeffs, lde|None, leaves, digests, cap)."""
+    a = _arr(cols); ncols, n = a.shape; log_n = _log2(n); m = n << rate_bits
+    width = ncols + (4 if salt_cols is not None else 0)
+    colp = (_u64p * ncols)(*[_p(a[c]) for c in range(ncols)])
+    saltp = None
+    if salt_cols is not None:
+        s = _arr(salt_cols); assert s.shape == (4, m)
+        saltp = (_u64p * 4)(*[_p(s[i]) for i in range(4)])
+    coeffs = np.empty((ncols, n), np.uint64)
+    ldec = np.empty((ncols, m), np.uint64) if want_lde else None
+    leaves = np.empty((m, width), np.uint64)
+    ncap = 1 << cap_height
+    digests = np.empty((2 * (m - ncap) if m >= ncap else 0, 4), np.uint64)
+    cap = np.empty((ncap, 4), np.uint64)
+    rc = lib().orc_commit(colp, ncols, log_n, rate_bits, cap_height, int(inputs_are_coeffs), saltp,
+                          _p(coeffs), _p(ldec) if want_lde else None, _p(leaves),
+                          _p(digests) if digests.size else None, _p(cap))
+    if rc != 0:
+        raise ValueError("orc_commit: bad arguments (rc=%d)" % rc)
+    return dict(coeffs=coeffs, lde=ldec, leaves=leaves, digests=digests, cap=cap)

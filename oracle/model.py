@@ -1,0 +1,218 @@
+"""model.py — independent big-integer Python model of plonky2 0.2.0's commitment path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/oracle.h).  It exists as a second opinion on oracle.c: it is
+written from the *mathematical definitions* (direct O(n^2) polynomial evaluation instead of an FFT,
+Python `%` instead of reduce128, recursion by definition for the Merkle tree) so that a shared bug
+between the two is unlikely.  Pure-Python loops: use only for small cases.
+
+Upstream items restated ([P2] = plonky2 0.2.0 family, absent from /root/reference; reached from
+/root/reference/src/vtfhe/ivc_based_vpbs.rs:275,302,333,364):
+  [P2] plonky2_field/src/goldilocks_field.rs   p, generator 7, POWER_OF_TWO_GENERATOR
+  [P2] plonky2_field/src/fft.rs, polynomial/mod.rs   fft / ifft / lde / coset_fft
+  [P2] plonky2/src/hash/poseidon{,_goldilocks}.rs    permutation
+  [P2] plonky2/src/hash/hashing.rs, plonk/config.rs  hash_n_to_m_no_pad / hash_or_noop / compress
+  [P2] plonky2/src/hash/merkle_tree.rs               MerkleTree::new / prove
+  [P2] plonky2/src/fri/oracle.rs                     PolynomialBatch::from_values / from_coeffs
+"""
+from __future__ import annotations
+
+P = 2**64 - 2**32 + 1
+GENERATOR = 7
+POWER_OF_TWO_GENERATOR = pow(GENERATOR, (P - 1) >> 32, P)  # == 1753635133440165772
+COSET_SHIFT = GENERATOR
+SALT_SIZE = 4
+
+
+def primitive_root_of_unity(n_log: int) -> int:
+    assert n_log <= 32
+    return pow(POWER_OF_TWO_GENERATOR, 1 << (32 - n_log), P)
+
+
+def bitrev(x: int, bits: int) -> int:
+    return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+
+
+# --------------------------------------------------------------------------- polynomials
+def evaluate(coeffs, x):
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + c) % P
+    return acc
+
+
+def fft(coeffs):
+    """[P2] fft.rs fft: out[i] = poly(w_n^i), natural order."""
+    n = len(coeffs)
+    w = primitive_root_of_unity(n.bit_length() - 1)
+    return [evaluate(coeffs, pow(w, i, P)) for i in range(n)]
+
+
+def ifft(values):
+    """[P2] fft.rs ifft: c_j = n^-1 sum_i v_i w^(-ij)."""
+    n = len(values)
+    w_inv = pow(primitive_root_of_unity(n.bit_length() - 1), P - 2, P)
+    n_inv = pow(n, P - 2, P)
+    return [evaluate(values, pow(w_inv, j, P)) * n_inv % P for j in range(n)]
+
+
+def coset_fft(coeffs, shift):
+    """[P2] polynomial/mod.rs coset_fft: out[i] = poly(shift * w_n^i)."""
+    n = len(coeffs)
+    w = primitive_root_of_unity(n.bit_length() - 1)
+    return [evaluate(coeffs, shift * pow(w, i, P) % P) for i in range(n)]
+
+
+def lde(coeffs, rate_bits):
+    """[P2] lde(rate_bits) + coset_fft(coset_shift): evaluations on 7*<w_m>, natural order."""
+    padded = list(coeffs) + [0] * (len(coeffs) * ((1 << rate_bits) - 1))
+    return coset_fft(padded, COSET_SHIFT)
+
+
+# --------------------------------------------------------------------------- Poseidon
+MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+MDS_DIAG = [8] + [0] * 11
+HALF_N_FULL_ROUNDS = 4
+N_PARTIAL_ROUNDS = 22
+WIDTH = 12
+RATE = 8
+
+
+def _chacha8_stream(key):
+    def rotl(x, r):
+        return ((x << r) | (x >> (32 - r))) & 0xFFFFFFFF
+
+    def qr(x, a, b, c, d):
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] = rotl(x[b] ^ x[c], 7)
+
+    counter = 0
+    while True:
+        s = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(key) + [
+            counter & 0xFFFFFFFF, counter >> 32, 0, 0]
+        x = list(s)
+        for _ in range(4):
+            qr(x, 0, 4, 8, 12); qr(x, 1, 5, 9, 13); qr(x, 2, 6, 10, 14); qr(x, 3, 7, 11, 15)
+            qr(x, 0, 5, 10, 15); qr(x, 1, 6, 11, 12); qr(x, 2, 7, 8, 13); qr(x, 3, 4, 9, 14)
+        for a, b in zip(x, s):
+            yield (a + b) & 0xFFFFFFFF
+        counter += 1
+
+
+def round_constants():
+    """ALL_ROUND_CONSTANTS regenerated as ChaCha8Rng::seed_from_u64(0) draws."""
+    state, key = 0, []
+    for _ in range(8):
+        state = (state * 6364136223846793005 + 11634580027462260723) % 2**64
+        xs = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+        rot = state >> 59
+        key.append(((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF)
+    words = _chacha8_stream(key)
+    out = []
+    while len(out) < 360:
+        v = next(words) | (next(words) << 32)
+        wide = v * P
+        if wide % 2**64 <= P - 1:
+            out.append(wide >> 64)
+    return out
+
+
+RC = round_constants()
+
+
+def poseidon(state):
+    """[P2] Poseidon::poseidon, naive rounds: constants, S-box (x^7; lane 0 only in partial
+    rounds), MDS (out[r] = sum_i CIRC[i]*s[(i+r)%12] + DIAG[r]*s[r])."""
+    s = [x % P for x in state]
+    assert len(s) == WIDTH
+    for r in range(2 * HALF_N_FULL_ROUNDS + N_PARTIAL_ROUNDS):
+        s = [(x + RC[12 * r + i]) % P for i, x in enumerate(s)]
+        if r < HALF_N_FULL_ROUNDS or r >= HALF_N_FULL_ROUNDS + N_PARTIAL_ROUNDS:
+            s = [pow(x, 7, P) for x in s]
+        else:
+            s[0] = pow(s[0], 7, P)
+        s = [(sum(MDS_CIRC[i] * s[(i + r2) % 12] for i in range(12)) + MDS_DIAG[r2] * s[r2]) % P
+             for r2 in range(12)]
+    return s
+
+
+def hash_no_pad(inputs):
+    state = [0] * WIDTH
+    for off in range(0, len(inputs), RATE):
+        chunk = inputs[off:off + RATE]
+        state[:len(chunk)] = [x % P for x in chunk]   # overwrite mode
+        state = poseidon(state)
+    return state[:4]
+
+
+def hash_or_noop(inputs):
+    if len(inputs) <= 4:
+        return [x % P for x in inputs] + [0] * (4 - len(inputs))
+    return hash_no_pad(inputs)
+
+
+def two_to_one(left, right):
+    return poseidon(list(left) + list(right) + [0] * 4)[:4]
+
+
+# --------------------------------------------------------------------------- Merkle tree
+def _fill_subtree(leaves):
+    """Returns (digests_buf as list of hashes, root) following [P2] fill_subtree's layout:
+    left recursive output || left child digest || right child digest || right recursive output."""
+    if len(leaves) == 1:
+        return [], hash_or_noop(leaves[0])
+    half = len(leaves) // 2
+    lbuf, ld = _fill_subtree(leaves[:half])
+    rbuf, rd = _fill_subtree(leaves[half:])
+    return lbuf + [ld, rd] + rbuf, two_to_one(ld, rd)
+
+
+def merkle_new(leaves, cap_height):
+    """[P2] MerkleTree::new -> (digests, cap), each a list of 4-element hashes."""
+    n = len(leaves)
+    assert n & (n - 1) == 0 and cap_height <= n.bit_length() - 1
+    sub = n >> cap_height
+    digests, cap = [], []
+    for s in range(1 << cap_height):
+        buf, root = _fill_subtree(leaves[s * sub:(s + 1) * sub])
+        digests += buf
+        cap.append(root)
+    assert len(digests) == 2 * (n - (1 << cap_height))
+    return digests, cap
+
+
+def merkle_prove(digests, nleaves, cap_height, leaf_index):
+    num_layers = nleaves.bit_length() - 1 - cap_height
+    tree_len = len(digests) >> cap_height
+    tree = digests[tree_len * (leaf_index >> num_layers):][:tree_len]
+    pair_index = leaf_index & ((1 << num_layers) - 1)
+    sibs = []
+    for i in range(num_layers):
+        parity = pair_index & 1
+        pair_index >>= 1
+        sibs.append(tree[2 * ((pair_index << (i + 1)) + (1 << i) - 1) + (1 - parity)])
+    return sibs
+
+
+def merkle_verify(leaf, leaf_index, siblings, cap):
+    cur = hash_or_noop(leaf)
+    idx = leaf_index
+    for sib in siblings:
+        cur = two_to_one(sib, cur) if idx & 1 else two_to_one(cur, sib)
+        idx >>= 1
+    return cur == cap[idx]
+
+
+# --------------------------------------------------------------------------- PolynomialBatch
+def commit(cols, rate_bits, cap_height, inputs_are_coeffs=False, salt_cols=None):
+    """[P2] PolynomialBatch::from_values / from_coeffs.
+    Returns dict(coeffs, lde (natural order, per column), leaves (bit-reversed rows), digests, cap)."""
+    n = len(cols[0])
+    log_m = n.bit_length() - 1 + rate_bits
+    coeffs = [[x % P for x in c] if inputs_are_coeffs else ifft(c) for c in cols]
+    lde_cols = [lde(c, rate_bits) for c in coeffs]
+    all_cols = lde_cols + ([[x % P for x in s] for s in salt_cols] if salt_cols else [])
+    leaves = [[col[bitrev(k, log_m)] for col in all_cols] for k in range(n << rate_bits)]
+    digests, cap = merkle_new(leaves, cap_height)
+    return dict(coeffs=coeffs, lde=lde_cols, leaves=leaves, digests=digests, cap=cap)

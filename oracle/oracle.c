@@ -1,0 +1,483 @@
+/*
+ * oracle.c — CPU restatement of plonky2 0.2.0's commitment path (see oracle.h header).
+ * TEST INFRASTRUCTURE ONLY — never linked into or called from the product library.
+ *
+ * Plain C11 + OpenMP.  Parallel regions mirror where plonky2 uses rayon: over columns for the
+ * FFTs ([P2] fri/oracle.rs from_values / lde_values), over rows for transpose, over leaves and
+ * sibling pairs for the Merkle tree ([P2] hash/merkle_tree.rs fill_digests_buf / fill_subtree).
+ */
+#include "oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+#define P ORC_P
+#define EPS 0xFFFFFFFFULL
+
+/* ------------------------------------------------------------------------------------------
+ * Goldilocks field.  [P2] plonky2_field/src/goldilocks_field.rs
+ * ---------------------------------------------------------------------------------------- */
+static inline uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
+
+/* [P2] goldilocks_field.rs reduce128: x = lo + 2^64*hi, 2^64 = EPS, 2^96 = -1 (mod p). */
+static inline uint64_t reduce128(u128 x) {
+  uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+  uint64_t hi_hi = hi >> 32, hi_lo = hi & EPS;
+  uint64_t t0 = lo - hi_hi;
+  if (lo < hi_hi) t0 -= EPS; /* borrow: add p */
+  uint64_t t1 = hi_lo * EPS;
+  uint64_t r = t0 + t1;
+  if (r < t1) r += EPS; /* carry: subtract p */
+  return r;             /* < 2^64, not necessarily canonical */
+}
+static inline uint64_t add_(uint64_t a, uint64_t b) { /* a,b canonical */
+  uint64_t s = a + b;
+  if (s < a || s >= P) s -= P;
+  return s;
+}
+static inline uint64_t sub_(uint64_t a, uint64_t b) { return a >= b ? a - b : a + (P - b); }
+static inline uint64_t mul_(uint64_t a, uint64_t b) { return canon(reduce128((u128)a * b)); }
+
+uint64_t orc_gl_add(uint64_t a, uint64_t b) { return add_(canon(a), canon(b)); }
+uint64_t orc_gl_sub(uint64_t a, uint64_t b) { return sub_(canon(a), canon(b)); }
+uint64_t orc_gl_mul(uint64_t a, uint64_t b) { return mul_(a, b); }
+uint64_t orc_gl_pow(uint64_t a, uint64_t e) {
+  uint64_t r = 1, b = canon(a);
+  while (e) {
+    if (e & 1) r = mul_(r, b);
+    b = mul_(b, b);
+    e >>= 1;
+  }
+  return r;
+}
+uint64_t orc_gl_inv(uint64_t a) { return orc_gl_pow(a, P - 2); }
+
+/* [P2] GoldilocksField::POWER_OF_TWO_GENERATOR = 7^((p-1)/2^32); two-adicity 32; generator 7. */
+#define POWER_OF_TWO_GENERATOR 1753635133440165772ULL
+#define COSET_SHIFT 7ULL
+uint64_t orc_primitive_root_of_unity(unsigned n_log) {
+  uint64_t b = POWER_OF_TWO_GENERATOR;
+  for (unsigned i = n_log; i < 32; i++) b = mul_(b, b);
+  return b;
+}
+
+static int g_threads = 0;
+void orc_set_threads(int n) { g_threads = n; }
+int orc_get_threads(void) {
+#ifdef _OPENMP
+  return g_threads > 0 ? g_threads : omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FFT.  [P2] plonky2_field/src/fft.rs fft_dispatch -> fft_classic: reverse_index_bits_in_place,
+ * then lg n radix-2 decimation-in-time layers reading root_table[lg_m-1][j] = w_{2^lg_m}^j.
+ * (zero_factor only skips butterflies whose inputs are known zeros: same values.)
+ * ---------------------------------------------------------------------------------------- */
+static inline uint64_t bitrev(uint64_t x, unsigned bits) {
+  uint64_t r = 0;
+  for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1ULL) << (bits - 1 - i);
+  return r;
+}
+static void reverse_index_bits_in_place_u64(uint64_t* v, unsigned log_n) {
+  uint64_t n = 1ULL << log_n;
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t j = bitrev(i, log_n);
+    if (i < j) {
+      uint64_t t = v[i];
+      v[i] = v[j];
+      v[j] = t;
+    }
+  }
+}
+/* roots[j] = w_n^j for j < n/2 (the last row of plonky2's fft_root_table; row lg_m-1 is this
+ * one read with stride n/2^lg_m). */
+static uint64_t* make_roots(unsigned log_n) {
+  uint64_t half = log_n ? (1ULL << (log_n - 1)) : 1;
+  uint64_t* r = (uint64_t*)malloc(sizeof(uint64_t) * half);
+  uint64_t w = orc_primitive_root_of_unity(log_n), acc = 1;
+  for (uint64_t j = 0; j < half; j++) {
+    r[j] = acc;
+    acc = mul_(acc, w);
+  }
+  return r;
+}
+static void fft_classic(uint64_t* v, unsigned log_n, const uint64_t* roots) {
+  uint64_t n = 1ULL << log_n;
+  for (uint64_t i = 0; i < n; i++) v[i] = canon(v[i]);
+  reverse_index_bits_in_place_u64(v, log_n);
+  for (unsigned lg_half_m = 0; lg_half_m < log_n; lg_half_m++) {
+    uint64_t half_m = 1ULL << lg_half_m, m = half_m << 1;
+    uint64_t stride = n / m; /* w_m^j = w_n^(j*n/m) */
+    for (uint64_t k = 0; k < n; k += m)
+      for (uint64_t j = 0; j < half_m; j++) {
+        uint64_t t = mul_(roots[j * stride], v[k + half_m + j]);
+        uint64_t u = v[k + j];
+        v[k + j] = add_(u, t);
+        v[k + half_m + j] = sub_(u, t);
+      }
+  }
+}
+void orc_fft(uint64_t* v, unsigned log_n) {
+  uint64_t* roots = make_roots(log_n);
+  fft_classic(v, log_n, roots);
+  free(roots);
+}
+/* [P2] fft.rs ifft_with_options: forward FFT, then reverse all values except the first and
+ * scale by n^-1 (= F::inverse_2exp(lg n)). */
+static void ifft_with_roots(uint64_t* v, unsigned log_n, const uint64_t* roots) {
+  uint64_t n = 1ULL << log_n;
+  fft_classic(v, log_n, roots);
+  uint64_t n_inv = orc_gl_inv(n % P);
+  v[0] = mul_(v[0], n_inv);
+  if (n > 1) v[n / 2] = mul_(v[n / 2], n_inv);
+  for (uint64_t i = 1; i < n / 2; i++) {
+    uint64_t j = n - i;
+    uint64_t ci = mul_(v[j], n_inv), cj = mul_(v[i], n_inv);
+    v[i] = ci;
+    v[j] = cj;
+  }
+}
+void orc_ifft(uint64_t* v, unsigned log_n) {
+  uint64_t* roots = make_roots(log_n);
+  ifft_with_roots(v, log_n, roots);
+  free(roots);
+}
+/* [P2] polynomial/mod.rs coset_fft_with_options: c_j *= shift^j, then fft. */
+static void coset_fft_with_roots(uint64_t* v, unsigned log_n, uint64_t shift,
+                                 const uint64_t* roots) {
+  uint64_t n = 1ULL << log_n, s = 1;
+  shift = canon(shift);
+  for (uint64_t j = 0; j < n; j++) {
+    v[j] = mul_(v[j], s);
+    s = mul_(s, shift);
+  }
+  fft_classic(v, log_n, roots);
+}
+void orc_coset_fft(uint64_t* v, unsigned log_n, uint64_t shift) {
+  uint64_t* roots = make_roots(log_n);
+  coset_fft_with_roots(v, log_n, shift, roots);
+  free(roots);
+}
+/* [P2] PolynomialCoeffs::lde = zero-pad to n<<rate_bits; lde_values() then takes
+ * coset_fft_with_options(F::coset_shift(), Some(rate_bits), fft_root_table). */
+void orc_lde(const uint64_t* coeffs, unsigned log_n, unsigned rate_bits, uint64_t* out) {
+  uint64_t n = 1ULL << log_n, m = n << rate_bits;
+  memcpy(out, coeffs, n * sizeof(uint64_t));
+  memset(out + n, 0, (m - n) * sizeof(uint64_t));
+  orc_coset_fft(out, log_n + rate_bits, COSET_SHIFT);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Poseidon.  [P2] plonky2/src/hash/poseidon.rs (Poseidon trait: SPONGE_WIDTH 12, x^7,
+ * HALF_N_FULL_ROUNDS 4, N_PARTIAL_ROUNDS 22) and hash/poseidon_goldilocks.rs (MDS_MATRIX_CIRC,
+ * MDS_MATRIX_DIAG, ALL_ROUND_CONSTANTS).  Naive round form (constant layer, S-box layer, MDS
+ * layer), which upstream's tests assert equal to its fast-partial-round form.
+ *
+ * ALL_ROUND_CONSTANTS is regenerated instead of transcribed: upstream documents it as 360 draws
+ * of F::rand() from ChaCha8Rng::seed_from_u64(0) (rand 0.8 / rand_chacha 0.3).  SURVEY.md App. D.
+ * The three plonky2 known-answer vectors in tests/golden/poseidon_kat.json check the result.
+ * ---------------------------------------------------------------------------------------- */
+static const uint64_t MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+static const uint64_t MDS_DIAG[12] = {8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static uint64_t RC[360];
+static int rc_ready = 0;
+
+static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+#define QR(a, b, c, d)                  \
+  a += b; d ^= a; d = rotl32(d, 16);    \
+  c += d; b ^= c; b = rotl32(b, 12);    \
+  a += b; d ^= a; d = rotl32(d, 8);     \
+  c += d; b ^= c; b = rotl32(b, 7);
+static void chacha8_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+  uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u,
+                    key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                    (uint32_t)counter, (uint32_t)(counter >> 32), 0, 0};
+  uint32_t x[16];
+  memcpy(x, s, sizeof x);
+  for (int dr = 0; dr < 4; dr++) { /* 4 double rounds = ChaCha8 */
+    QR(x[0], x[4], x[8], x[12]) QR(x[1], x[5], x[9], x[13])
+    QR(x[2], x[6], x[10], x[14]) QR(x[3], x[7], x[11], x[15])
+    QR(x[0], x[5], x[10], x[15]) QR(x[1], x[6], x[11], x[12])
+    QR(x[2], x[7], x[8], x[13]) QR(x[3], x[4], x[9], x[14])
+  }
+  for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
+}
+static void gen_round_constants(void) {
+  /* rand_core SeedableRng::seed_from_u64(0): PCG32 expansion of the seed into the key. */
+  uint32_t key[8];
+  uint64_t state = 0;
+  for (int i = 0; i < 8; i++) {
+    state = state * 6364136223846793005ULL + 11634580027462260723ULL;
+    uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
+    uint32_t rot = (uint32_t)(state >> 59);
+    key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+  }
+  uint32_t blk[16];
+  uint64_t counter = 0;
+  int pos = 16, k = 0;
+  while (k < 360) {
+    uint32_t w[2];
+    for (int h = 0; h < 2; h++) {
+      if (pos == 16) {
+        chacha8_block(key, counter++, blk);
+        pos = 0;
+      }
+      w[h] = blk[pos++];
+    }
+    uint64_t v = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    /* rand 0.8 UniformInt<u64>::sample_single(0, p): zone = (p << lz(p)) - 1 = p - 1. */
+    u128 wide = (u128)v * P;
+    if ((uint64_t)wide <= P - 1) RC[k++] = (uint64_t)(wide >> 64);
+  }
+  rc_ready = 1;
+}
+static void ensure_rc(void) {
+  if (!rc_ready) {
+#pragma omp critical(orc_rc)
+    if (!rc_ready) gen_round_constants();
+  }
+}
+void orc_poseidon_round_constants(uint64_t out[360]) {
+  ensure_rc();
+  memcpy(out, RC, sizeof RC);
+}
+
+static inline uint64_t sbox7(uint64_t x) {
+  uint64_t x2 = mul_(x, x), x4 = mul_(x2, x2), x3 = mul_(x, x2);
+  return mul_(x3, x4);
+}
+/* [P2] Poseidon::mds_layer / mds_row_shf: out[r] = sum_i state[(i+r)%12]*CIRC[i] + state[r]*DIAG[r] */
+static inline void mds_layer(uint64_t s[12]) {
+  uint64_t o[12];
+  for (int r = 0; r < 12; r++) {
+    u128 acc = 0;
+    for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * MDS_CIRC[i];
+    acc += (u128)s[r] * MDS_DIAG[r];
+    o[r] = canon(reduce128(acc));
+  }
+  memcpy(s, o, sizeof o);
+}
+static void poseidon_(uint64_t s[12]) {
+  int rc = 0;
+  for (int r = 0; r < 30; r++) {
+    for (int i = 0; i < 12; i++) s[i] = add_(s[i], RC[rc++]);
+    if (r < 4 || r >= 26) {
+      for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+    } else {
+      s[0] = sbox7(s[0]);
+    }
+    mds_layer(s);
+  }
+}
+void orc_poseidon(uint64_t state[12]) {
+  ensure_rc();
+  for (int i = 0; i < 12; i++) state[i] = canon(state[i]);
+  poseidon_(state);
+}
+/* [P2] hash/hashing.rs hash_n_to_m_no_pad with PoseidonPermutation (RATE 8): state starts at 0;
+ * each chunk of <=8 inputs OVERWRITES state[0..len) (set_from_slice), then permute; squeeze
+ * state[0..4). */
+static void hash_no_pad_(const uint64_t* in, size_t len, uint64_t out[4]) {
+  uint64_t s[12] = {0};
+  for (size_t off = 0; off < len; off += 8) {
+    size_t c = len - off < 8 ? len - off : 8;
+    for (size_t i = 0; i < c; i++) s[i] = canon(in[off + i]);
+    poseidon_(s);
+  }
+  memcpy(out, s, 4 * sizeof(uint64_t));
+}
+void orc_hash_no_pad(const uint64_t* in, size_t len, uint64_t out[4]) {
+  ensure_rc();
+  hash_no_pad_(in, len, out);
+}
+/* [P2] plonk/config.rs Hasher::hash_or_noop: inputs that fit in a hash (<= 4 elements) are
+ * copied (canonical, zero padded) instead of hashed. */
+static void hash_or_noop_(const uint64_t* in, size_t len, uint64_t out[4]) {
+  if (len <= 4) {
+    for (size_t i = 0; i < 4; i++) out[i] = i < len ? canon(in[i]) : 0;
+  } else {
+    hash_no_pad_(in, len, out);
+  }
+}
+void orc_hash_or_noop(const uint64_t* in, size_t len, uint64_t out[4]) {
+  ensure_rc();
+  hash_or_noop_(in, len, out);
+}
+/* [P2] hash/hashing.rs compress (= PoseidonHash::two_to_one): perm(l || r || 0^4)[0..4). */
+static void two_to_one_(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+  uint64_t s[12] = {0};
+  for (int i = 0; i < 4; i++) {
+    s[i] = canon(l[i]);
+    s[4 + i] = canon(r[i]);
+  }
+  poseidon_(s);
+  memcpy(out, s, 4 * sizeof(uint64_t));
+}
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+  ensure_rc();
+  two_to_one_(l, r, out);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Merkle tree.  [P2] plonky2/src/hash/merkle_tree.rs
+ * ---------------------------------------------------------------------------------------- */
+static int log2_strict(uint64_t n) {
+  if (n == 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while ((1ULL << l) < n) l++;
+  return l;
+}
+/* [P2] fill_subtree, literally: digests_buf layout is
+ *   left recursive output || left child digest || right child digest || right recursive output */
+static void fill_subtree(uint64_t* digests_buf, uint64_t buf_len, const uint64_t* leaves,
+                         uint64_t nleaves, uint32_t leaf_len, uint64_t out[4]) {
+  if (buf_len == 0) {
+    hash_or_noop_(leaves, leaf_len, out);
+    return;
+  }
+  uint64_t half = buf_len / 2;
+  uint64_t* left_buf = digests_buf;               /* [0, half-1) */
+  uint64_t* left_mem = digests_buf + 4 * (half - 1);
+  uint64_t* right_mem = digests_buf + 4 * half;
+  uint64_t* right_buf = digests_buf + 4 * (half + 1); /* (half, buf_len) */
+  uint64_t l[4], r[4];
+  if (nleaves >= 4096) {
+#pragma omp task shared(l)
+    fill_subtree(left_buf, half - 1, leaves, nleaves / 2, leaf_len, l);
+#pragma omp task shared(r)
+    fill_subtree(right_buf, half - 1, leaves + (nleaves / 2) * leaf_len, nleaves / 2, leaf_len, r);
+#pragma omp taskwait
+  } else {
+    fill_subtree(left_buf, half - 1, leaves, nleaves / 2, leaf_len, l);
+    fill_subtree(right_buf, half - 1, leaves + (nleaves / 2) * leaf_len, nleaves / 2, leaf_len, r);
+  }
+  memcpy(left_mem, l, sizeof l);
+  memcpy(right_mem, r, sizeof r);
+  two_to_one_(l, r, out);
+}
+/* [P2] MerkleTree::new + fill_digests_buf. */
+int orc_merkle_new(const uint64_t* leaves, uint64_t nleaves, uint32_t leaf_len, uint32_t cap_height,
+                   uint64_t* digests, uint64_t* cap) {
+  ensure_rc();
+  int lg = log2_strict(nleaves);
+  if (lg < 0 || (int)cap_height > lg) return -1;
+  uint64_t ncap = 1ULL << cap_height;
+  uint64_t num_digests = 2 * (nleaves - ncap);
+  if (num_digests == 0) { /* tree is all cap */
+#pragma omp parallel for num_threads(orc_get_threads()) schedule(static)
+    for (uint64_t k = 0; k < nleaves; k++) hash_or_noop_(leaves + k * leaf_len, leaf_len, cap + 4 * k);
+    return 0;
+  }
+  uint64_t sub_digests = num_digests >> cap_height, sub_leaves = nleaves >> cap_height;
+#pragma omp parallel num_threads(orc_get_threads())
+#pragma omp single
+  for (uint64_t s = 0; s < ncap; s++) {
+#pragma omp task firstprivate(s)
+    fill_subtree(digests + 4 * s * sub_digests, sub_digests, leaves + s * sub_leaves * leaf_len,
+                 sub_leaves, leaf_len, cap + 4 * s);
+  }
+  return 0;
+}
+/* [P2] MerkleTree::prove. */
+int orc_merkle_prove(const uint64_t* digests, uint64_t nleaves, uint32_t cap_height,
+                     uint64_t leaf_index, uint64_t* siblings_out) {
+  int lg = log2_strict(nleaves);
+  if (lg < 0 || (int)cap_height > lg || leaf_index >= nleaves) return -1;
+  uint32_t num_layers = (uint32_t)lg - cap_height;
+  uint64_t num_digests = 2 * (nleaves - (1ULL << cap_height));
+  uint64_t tree_index = leaf_index >> num_layers;
+  uint64_t tree_len = num_digests >> cap_height;
+  const uint64_t* digest_tree = digests + 4 * tree_len * tree_index;
+  uint64_t pair_index = leaf_index & ((1ULL << num_layers) - 1);
+  for (uint32_t i = 0; i < num_layers; i++) {
+    uint64_t parity = pair_index & 1;
+    pair_index >>= 1;
+    uint64_t siblings_index = (pair_index << (i + 1)) + (1ULL << i) - 1;
+    uint64_t sibling_index = 2 * siblings_index + (1 - parity);
+    memcpy(siblings_out + 4 * i, digest_tree + 4 * sibling_index, 32);
+  }
+  return 0;
+}
+/* [P2] hash/merkle_proofs.rs verify_merkle_proof_to_cap. */
+int orc_merkle_verify(const uint64_t* leaf, uint32_t leaf_len, uint64_t leaf_index,
+                      const uint64_t* siblings, uint32_t nsiblings, const uint64_t* cap,
+                      uint32_t cap_height) {
+  ensure_rc();
+  (void)cap_height;
+  uint64_t cur[4], nxt[4];
+  uint64_t index = leaf_index;
+  hash_or_noop_(leaf, leaf_len, cur);
+  for (uint32_t i = 0; i < nsiblings; i++) {
+    uint64_t bit = index & 1;
+    index >>= 1;
+    if (bit) two_to_one_(siblings + 4 * i, cur, nxt);
+    else two_to_one_(cur, siblings + 4 * i, nxt);
+    memcpy(cur, nxt, sizeof cur);
+  }
+  return memcmp(cur, cap + 4 * index, 32) == 0 ? 0 : 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PolynomialBatch.  [P2] plonky2/src/fri/oracle.rs from_values / from_coeffs / lde_values;
+ * plonky2_util transpose + reverse_index_bits_in_place.  Reached from the reference at
+ * /root/reference/src/vtfhe/ivc_based_vpbs.rs:275 (build) and :302/:333/:364 (prove).
+ * ---------------------------------------------------------------------------------------- */
+int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+               uint32_t cap_height, int inputs_are_coeffs, const uint64_t* const* salt_cols,
+               uint64_t* coeffs_out, uint64_t* lde_cols_out, uint64_t* leaves_out,
+               uint64_t* digests_out, uint64_t* cap_out) {
+  ensure_rc();
+  if (!cols || ncols == 0 || log_n + rate_bits > 32 || cap_height > log_n + rate_bits) return -1;
+  const uint64_t n = 1ULL << log_n, m = n << rate_bits;
+  const unsigned log_m = log_n + rate_bits;
+  const uint32_t salt = salt_cols ? 4 : 0, width = ncols + salt;
+  int nt = orc_get_threads();
+  uint64_t* roots_n = make_roots(log_n);
+  uint64_t* roots_m = make_roots(log_m);
+  uint64_t* coeffs = coeffs_out ? coeffs_out : (uint64_t*)malloc(sizeof(uint64_t) * ncols * n);
+  uint64_t* lde = lde_cols_out ? lde_cols_out : (uint64_t*)malloc(sizeof(uint64_t) * (uint64_t)ncols * m);
+  if (!coeffs || !lde) return -2;
+
+  /* "IFFT": values.into_par_iter().map(|v| v.ifft()) */
+#pragma omp parallel for num_threads(nt) schedule(dynamic)
+  for (uint32_t c = 0; c < ncols; c++) {
+    uint64_t* dst = coeffs + (uint64_t)c * n;
+    for (uint64_t i = 0; i < n; i++) dst[i] = canon(cols[c][i]);
+    if (!inputs_are_coeffs) ifft_with_roots(dst, log_n, roots_n);
+  }
+  /* "FFT + blinding": polynomials.par_iter().map(|p| p.lde(r).coset_fft_with_options(7, ..)) */
+#pragma omp parallel for num_threads(nt) schedule(dynamic)
+  for (uint32_t c = 0; c < ncols; c++) {
+    uint64_t* dst = lde + (uint64_t)c * m;
+    memcpy(dst, coeffs + (uint64_t)c * n, n * sizeof(uint64_t));
+    memset(dst + n, 0, (m - n) * sizeof(uint64_t));
+    coset_fft_with_roots(dst, log_m, COSET_SHIFT, roots_m);
+  }
+  /* "transpose LDEs" + reverse_index_bits_in_place: leaf k = natural row bitrev(k); the salt
+   * columns are further entries of lde_values and are transposed/reordered with the rest. */
+  if (leaves_out) {
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (uint64_t k = 0; k < m; k++) {
+      uint64_t i = bitrev(k, log_m);
+      uint64_t* row = leaves_out + k * width;
+      for (uint32_t c = 0; c < ncols; c++) row[c] = lde[(uint64_t)c * m + i];
+      for (uint32_t s = 0; s < salt; s++) row[ncols + s] = canon(salt_cols[s][i]);
+    }
+  }
+  int rc = 0;
+  /* "build Merkle tree" */
+  if (leaves_out && cap_out)
+    rc = orc_merkle_new(leaves_out, m, width, cap_height, digests_out, cap_out);
+  if (!coeffs_out) free(coeffs);
+  if (!lde_cols_out) free(lde);
+  free(roots_n);
+  free(roots_m);
+  return rc;
+}

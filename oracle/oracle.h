@@ -1,0 +1,90 @@
+/*
+ * oracle.h — CPU restatement of plonky2 0.2.0's polynomial-commitment path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * The product (libvpbs_commit.so) never links, loads or calls this file.
+ *
+ * What it restates: the algorithm lives in crates that are NOT under /root/reference
+ * (plonky2 0.2.0, plonky2_field 0.2.0, plonky2_util 0.2.0 — /root/reference/Cargo.toml:7,
+ * Cargo.lock:371-374, 396-399, 421-424).  Each function below names the upstream item it
+ * follows ("[P2] path::item") and the reference call site that reaches it.
+ *
+ * Parity status: the plonky2 crates cannot be built here (no Rust toolchain), so this oracle is
+ * pinned by (1) plonky2's published Poseidon known-answer vectors, (2) the reference's own
+ * Goldilocks NTT golden vectors /root/reference/src/ntt/params_{8..2048}.rs (TESTG/TESTGHAT,
+ * ROOTS, INVROOTS, NINV) and (3) an independent big-integer Python model (oracle/model.py).
+ * No reference test pins an LDE value, digest or cap, so at the commit boundary itself the
+ * reference is "parity unpinned" (SURVEY.md §8(c)); the conventions (overwrite sponge,
+ * hash_or_noop threshold, digests layout, bit-reversed leaves, coset shift 7) follow upstream's
+ * definitions as restated in SURVEY.md §8(a).
+ */
+#ifndef VPBS_ORACLE_H
+#define VPBS_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_P 0xFFFFFFFF00000001ULL
+
+/* [P2] plonky2_field/src/goldilocks_field.rs — GoldilocksField arithmetic (canonical results). */
+uint64_t orc_gl_add(uint64_t a, uint64_t b);
+uint64_t orc_gl_sub(uint64_t a, uint64_t b);
+uint64_t orc_gl_mul(uint64_t a, uint64_t b);
+uint64_t orc_gl_pow(uint64_t a, uint64_t e);
+uint64_t orc_gl_inv(uint64_t a);
+/* [P2] Field::primitive_root_of_unity(n_log) = POWER_OF_TWO_GENERATOR^(2^(32-n_log)). */
+uint64_t orc_primitive_root_of_unity(unsigned n_log);
+
+/* [P2] plonky2_field/src/fft.rs — fft_with_options / ifft_with_options, natural order in & out. */
+void orc_fft(uint64_t* v, unsigned log_n);
+void orc_ifft(uint64_t* v, unsigned log_n);
+/* [P2] polynomial/mod.rs — PolynomialCoeffs::coset_fft_with_options(shift, ..). */
+void orc_coset_fft(uint64_t* v, unsigned log_n, uint64_t shift);
+/* [P2] PolynomialCoeffs::lde(rate_bits) then coset_fft(F::coset_shift()=7): out has n<<rate_bits. */
+void orc_lde(const uint64_t* coeffs, unsigned log_n, unsigned rate_bits, uint64_t* out);
+
+/* [P2] plonky2/src/hash/poseidon.rs + poseidon_goldilocks.rs — width-12 permutation. */
+void orc_poseidon_round_constants(uint64_t out[360]);
+void orc_poseidon(uint64_t state[12]);
+/* [P2] hash/hashing.rs hash_n_to_m_no_pad (m=4), plonk/config.rs Hasher::hash_or_noop, compress. */
+void orc_hash_no_pad(const uint64_t* in, size_t len, uint64_t out[4]);
+void orc_hash_or_noop(const uint64_t* in, size_t len, uint64_t out[4]);
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+
+/* [P2] hash/merkle_tree.rs MerkleTree::new: leaves row-major nleaves x leaf_len.
+ * digests: 2*(nleaves - 2^cap_height) x 4 in plonky2's layout; cap: 2^cap_height x 4.
+ * Returns 0, or -1 on bad arguments (the conditions plonky2 asserts on). */
+int orc_merkle_new(const uint64_t* leaves, uint64_t nleaves, uint32_t leaf_len, uint32_t cap_height,
+                   uint64_t* digests, uint64_t* cap);
+/* [P2] MerkleTree::prove(leaf_index): siblings_out gets (log2 nleaves - cap_height) x 4. */
+int orc_merkle_prove(const uint64_t* digests, uint64_t nleaves, uint32_t cap_height,
+                     uint64_t leaf_index, uint64_t* siblings_out);
+/* [P2] merkle_proofs.rs verify_merkle_proof_to_cap: returns 0 iff the path hashes to cap. */
+int orc_merkle_verify(const uint64_t* leaf, uint32_t leaf_len, uint64_t leaf_index,
+                      const uint64_t* siblings, uint32_t nsiblings, const uint64_t* cap,
+                      uint32_t cap_height);
+
+/* [P2] fri/oracle.rs PolynomialBatch::from_values / from_coeffs.
+ * cols: ncols pointers to n=2^log_n values (or coefficients).  salt_cols: NULL or 4 pointers of
+ * n<<rate_bits elements (the blinding columns, natural LDE order, as lde_values() chains them).
+ * coeffs_out: ncols*n (column-major) or NULL; lde_cols_out: ncols*(n<<r) natural order,
+ * column-major, or NULL; leaves_out: m x (ncols+salt) row-major in leaf (bit-reversed) order;
+ * digests_out / cap_out as orc_merkle_new. */
+int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+               uint32_t cap_height, int inputs_are_coeffs, const uint64_t* const* salt_cols,
+               uint64_t* coeffs_out, uint64_t* lde_cols_out, uint64_t* leaves_out,
+               uint64_t* digests_out, uint64_t* cap_out);
+
+/* Threads used by the parallel regions (mirrors rayon's pool). */
+void orc_set_threads(int n);
+int orc_get_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

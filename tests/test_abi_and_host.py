@@ -1,0 +1,94 @@
+"""CPU suite, part 2: the C-ABI library loads and exports what include/vpbs_commit.h declares,
+fails loudly without a GPU (no CPU fallback), and the host-side logic of the plonky2 mirror."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "vpbs_commit.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vpbs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol(V):
+    V.build.build()
+    lib = V._lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libvpbs_commit.so does not export %s" % s
+    assert sorted(V._lib.SIGNATURES) == syms, "binding and header disagree"
+    assert lib.vpbs_abi_version() == 1
+
+
+def test_library_contains_sm100a_code_only(V):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", V._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under the package may import, link or execute oracle/ (it is test infrastructure)."""
+    pkg = os.path.join(ROOT, "verifiable-fhe-paper_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".inc")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "orc_" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_no_gpu_means_loud_failure(V):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(V.VpbsError):
+        V.Context(0)
+
+
+def test_generated_round_constants_match_oracle(oracle):
+    inc = open(os.path.join(ROOT, "verifiable-fhe-paper_b200", "csrc", "poseidon_rc.inc")).read()
+    vals = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{16})ULL", inc)]
+    assert vals == [int(x) for x in oracle.round_constants()]
+
+
+def test_merkle_prove_index_arithmetic(V, oracle):
+    rng = np.random.default_rng(3)
+    for (lg, h, w) in [(5, 0, 7), (5, 2, 3), (4, 4, 9), (3, 1, 135)]:
+        leaves = rng.integers(0, 2**64, size=(1 << lg, w), dtype=np.uint64)
+        digests, cap = oracle.merkle_new(leaves, h)
+        tree = V.MerkleTree(leaves, digests, cap)
+        for i in range(1 << lg):
+            got = tree.prove(i).siblings
+            assert np.array_equal(got, oracle.merkle_prove(digests, 1 << lg, h, i))
+            assert oracle.merkle_verify(tree.get(i), i, got, cap)
+
+
+def test_argument_errors_match_plonky2_asserts(V):
+    with pytest.raises(ValueError):
+        V.log2_strict(6)
+    with pytest.raises(ValueError):
+        V.MerkleTree.new(np.zeros((6, 3), np.uint64), 1, ctx=object())
+    with pytest.raises(ValueError):
+        V.MerkleTree.new(np.zeros((8, 3), np.uint64), 4, ctx=object())
+    with pytest.raises(ValueError):
+        V.PolynomialBatch.from_values(np.zeros((2, 8), np.uint64), 1, False, 5, ctx=object())
+    with pytest.raises(ValueError):
+        V.PolynomialBatch.from_values(np.zeros((2, 6), np.uint64), 1, False, 1, ctx=object())
+
+
+def test_reverse_bits_and_synthetic_inputs(V):
+    assert V.reverse_bits(0b0011, 4) == 0b1100
+    assert V.reverse_bits(1, 19) == 1 << 18
+    a = V.synthetic_columns(3, 16)
+    b = V.synthetic_columns(3, 16)
+    assert np.array_equal(a, b) and a.shape == (3, 16) and (a < np.uint64(V.P)).all()
+    assert not np.array_equal(a[0], a[1])
+    raw = V.synthetic_columns(3, 16, canonical=False)
+    assert np.array_equal(raw % np.uint64(V.P), a)

@@ -1,0 +1,288 @@
+"""GPU suite: bit-exact parity of the CUDA path (through the C ABI) against the oracle, the
+committed golden fixtures and — at BASELINE.json's full sizes — size-independent properties.
+All integer work: the bar is exact equality everywhere."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from conftest import unhex
+
+pytestmark = pytest.mark.gpu
+P = 2**64 - 2**32 + 1
+EDGE = [0, 1, 2, P - 1, P, P + 1, 2**64 - 1, 2**32 - 1, 2**32, 2**32 + 1, P - 2**32, 2**63]
+
+
+def rand_u64(rng, shape, edge_frac=0.15):
+    a = rng.integers(0, 2**64, size=shape, dtype=np.uint64)
+    mask = rng.random(shape) < edge_frac
+    a[mask] = rng.choice(np.array(EDGE, dtype=np.uint64), size=int(mask.sum()))
+    return a
+
+
+# ------------------------------------------------------------------------------ poseidon / hashes
+def test_poseidon_known_answers(V, ctx, poseidon_kat):
+    inp = unhex([v["input"] for v in poseidon_kat["vectors"]])
+    want = unhex([v["output"] for v in poseidon_kat["vectors"]])
+    assert np.array_equal(V.poseidon(inp, ctx), want)
+
+
+def test_poseidon_random_and_noncanonical(V, ctx, oracle):
+    rng = np.random.default_rng(1)
+    states = rand_u64(rng, (4096, 12), 0.3)
+    got = V.poseidon(states, ctx)
+    for k in range(0, 4096, 7):
+        assert np.array_equal(got[k], oracle.poseidon(states[k])), k
+    assert (got < np.uint64(P)).all()
+
+
+@pytest.mark.parametrize("width", [0, 1, 3, 4, 5, 7, 8, 9, 15, 16, 17, 20, 128, 135, 139])
+def test_hash_or_noop_widths(V, ctx, oracle, width):
+    rng = np.random.default_rng(width)
+    rows = rand_u64(rng, (257, width), 0.2)
+    got = V.hash_or_noop(rows, ctx)
+    for k in range(0, 257, 16):
+        assert np.array_equal(got[k], oracle.hash_or_noop(rows[k])), (width, k)
+
+
+def test_two_to_one(V, ctx, oracle, model_anchors):
+    assert ["%016x" % int(x) for x in V.two_to_one([1, 2, 3, 4], [5, 6, 7, 8], ctx)[0]] == \
+        model_anchors["two_to_one_1234_5678"]
+    rng = np.random.default_rng(5)
+    l, r = rand_u64(rng, (300, 4)), rand_u64(rng, (300, 4))
+    got = V.two_to_one(l, r, ctx)
+    for k in range(0, 300, 11):
+        assert np.array_equal(got[k], oracle.two_to_one(l[k], r[k]))
+
+
+# ------------------------------------------------------------------------------ transforms
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024, 2048])
+def test_reference_ntt_vectors(V, ctx, ntt_params, oracle, n):
+    """The reference's own golden vectors (src/ntt/params_N.rs) through the CUDA transforms."""
+    lg = n.bit_length() - 1
+    w = oracle.primitive_root_of_unity(lg + 1)
+    rev = lambda i: int(format(i, "0%db" % lg)[::-1], 2)
+    g, ghat = ntt_params["TESTG_%d" % n], ntt_params["TESTGHAT_%d" % n]
+    ev = V.coset_fft(g, w, ctx)
+    assert [int(ev[rev(k)]) for k in range(n)] == [int(x) for x in ghat]
+    full = V.fft(np.concatenate([g, np.zeros(n, np.uint64)]), ctx)
+    assert [int(full[2 * rev(k) + 1]) for k in range(n)] == [int(x) for x in ghat]
+    assert np.array_equal(V.ifft(full, ctx)[:n], g)
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 21)))
+def test_fft_ifft_coset_against_oracle(V, ctx, oracle, log_n):
+    rng = np.random.default_rng(100 + log_n)
+    v = rand_u64(rng, (1 << log_n,))
+    assert np.array_equal(V.fft(v, ctx), oracle.fft(v))
+    assert np.array_equal(V.ifft(v, ctx), oracle.ifft(v))
+    shift = int(rng.integers(1, 2**64, dtype=np.uint64))
+    assert np.array_equal(V.coset_fft(v, shift, ctx), oracle.coset_fft(v, shift))
+    assert np.array_equal(V.ifft(V.fft(v, ctx), ctx), v % np.uint64(P))
+
+
+@pytest.mark.parametrize("log_n,ncols,rate_bits,coeffs", [(0, 3, 3, False), (3, 5, 0, False),
+                                                          (5, 9, 3, True), (9, 4, 2, False),
+                                                          (12, 3, 3, False)])
+def test_lde_values_natural_order(V, ctx, oracle, log_n, ncols, rate_bits, coeffs):
+    rng = np.random.default_rng(7 * log_n + ncols)
+    cols = rand_u64(rng, (ncols, 1 << log_n))
+    co, lde = V.lde_values(cols, rate_bits, coeffs, ctx)
+    ref = oracle.commit(cols, rate_bits, 0, coeffs, want_lde=True)
+    assert np.array_equal(lde, ref["lde"])
+    if not coeffs:
+        assert np.array_equal(co, ref["coeffs"])
+
+
+# ------------------------------------------------------------------------------ Merkle tree
+@pytest.mark.parametrize("log_leaves,width,cap_height", [
+    (0, 5, 0), (1, 5, 0), (1, 5, 1), (3, 4, 0), (3, 3, 3), (4, 9, 2), (6, 135, 4), (6, 20, 6),
+    (10, 16, 4), (10, 128, 0), (12, 8, 5), (13, 33, 4)])
+def test_merkle_new_against_oracle(V, ctx, oracle, log_leaves, width, cap_height):
+    rng = np.random.default_rng(log_leaves * 100 + width)
+    leaves = rand_u64(rng, (1 << log_leaves, width))
+    tree = V.MerkleTree.new(leaves, cap_height, ctx)
+    digests, cap = oracle.merkle_new(leaves, cap_height)
+    assert np.array_equal(tree.cap, cap)
+    assert np.array_equal(tree.digests, digests)
+    for i in {0, (1 << log_leaves) - 1, (1 << log_leaves) // 3}:
+        proof = tree.prove(i)
+        assert oracle.merkle_verify(leaves[i], i, proof.siblings, cap)
+        assert V.verify_merkle_proof_to_cap(leaves[i], i, tree.cap, proof, ctx)
+
+
+def test_merkle_new_rejects_bad_arguments(V, ctx):
+    with pytest.raises(ValueError):
+        V.MerkleTree.new(np.zeros((6, 3), np.uint64), 1, ctx)
+    with pytest.raises(ValueError):
+        V.MerkleTree.new(np.zeros((8, 3), np.uint64), 4, ctx)
+    # and at the C ABI itself
+    a = np.zeros((8, 3), np.uint64)
+    cap = np.zeros((16, 4), np.uint64)
+    rc = ctx.lib.vpbs_merkle_new(ctx.handle, a.ctypes.data_as(V._lib.u64p), 8, 3, 4, None,
+                                 cap.ctypes.data_as(V._lib.u64p))
+    assert rc == V._lib.VPBS_ERR_ARG and b"cap_height" in ctx.lib.vpbs_last_error(ctx.handle)
+    rc = ctx.lib.vpbs_merkle_new(ctx.handle, a.ctypes.data_as(V._lib.u64p), 6, 3, 0, None,
+                                 cap.ctypes.data_as(V._lib.u64p))
+    assert rc == V._lib.VPBS_ERR_ARG
+
+
+# ------------------------------------------------------------------------------ PolynomialBatch
+def check_batch(V, oracle, batch, cols, rate_bits, cap_height, coeffs, salt=None):
+    ref = oracle.commit(cols, rate_bits, cap_height, coeffs, salt)
+    assert np.array_equal(batch.merkle_tree.cap, ref["cap"])
+    assert np.array_equal(batch.merkle_tree.digests, ref["digests"])
+    assert np.array_equal(batch.merkle_tree.leaves, ref["leaves"])
+    assert np.array_equal(batch.polynomials, ref["coeffs"])
+    return ref
+
+
+def test_model_anchor_commits(V, ctx, model_anchors):
+    """Golden fixtures from the independent model (incl. SURVEY.md §8(c) anchors)."""
+    for c in model_anchors["commits"]:
+        cols = unhex(c["cols"])
+        salt = unhex(c["salt"]) if c["salt"] else None
+        f = V.PolynomialBatch.from_coeffs if c["inputs_are_coeffs"] else V.PolynomialBatch.from_values
+        b = f(cols, c["rate_bits"], salt is not None, c["cap_height"], ctx=ctx, salt=salt)
+        assert np.array_equal(b.polynomials, unhex(c["coeffs"])), c["name"]
+        assert np.array_equal(b.merkle_tree.leaves, unhex(c["leaves"])), c["name"]
+        want_d = unhex(c["digests"]) if c["digests"] else np.empty((0, 4), np.uint64)
+        assert np.array_equal(b.merkle_tree.digests, want_d), c["name"]
+        assert np.array_equal(b.merkle_tree.cap, unhex(c["cap"])), c["name"]
+        # get_lde_values(i) = natural-order LDE row i without the salt
+        lde = unhex(c["lde"])
+        for i in {0, min(1, lde.shape[1] - 1), lde.shape[1] - 1}:
+            assert np.array_equal(b.get_lde_values(i), lde[:, i]), c["name"]
+
+
+SHAPES = [(lg, C, r, h) for lg in (0, 1, 2, 3, 5, 8, 9, 11) for C in (1, 3, 4, 5, 8, 9, 16, 20)
+          for (r, h) in ((0, 0), (1, 1), (3, 4), (2, 0))]
+
+
+@pytest.mark.parametrize("log_n,ncols,rate_bits,cap_height",
+                         [s for i, s in enumerate(SHAPES) if i % 5 == 0 and s[3] <= s[0] + s[2]])
+def test_commit_shapes_from_values(V, ctx, oracle, log_n, ncols, rate_bits, cap_height):
+    rng = np.random.default_rng(hash((log_n, ncols, rate_bits, cap_height)) % 2**32)
+    cols = rand_u64(rng, (ncols, 1 << log_n))
+    b = V.PolynomialBatch.from_values(cols, rate_bits, False, cap_height, ctx=ctx)
+    check_batch(V, oracle, b, cols, rate_bits, cap_height, False)
+
+
+@pytest.mark.parametrize("log_n,ncols,rate_bits,cap_height", [
+    (4, 135, 3, 4), (7, 128, 3, 7), (10, 135, 3, 4), (12, 20, 3, 4), (13, 16, 3, 4), (6, 7, 3, 9),
+    (14, 2, 1, 15), (16, 3, 3, 4), (17, 2, 2, 0)])
+def test_commit_more_shapes(V, ctx, oracle, log_n, ncols, rate_bits, cap_height):
+    rng = np.random.default_rng(log_n * 1000 + ncols)
+    cols = rand_u64(rng, (ncols, 1 << log_n))
+    for coeffs in (False, True):
+        f = V.PolynomialBatch.from_coeffs if coeffs else V.PolynomialBatch.from_values
+        b = f(cols, rate_bits, False, cap_height, ctx=ctx)
+        check_batch(V, oracle, b, cols, rate_bits, cap_height, coeffs)
+
+
+def test_commit_with_blinding_salt(V, ctx, oracle):
+    rng = np.random.default_rng(99)
+    cols = rand_u64(rng, (20, 256))
+    salt = rand_u64(rng, (4, 256 << 3))
+    b = V.PolynomialBatch.from_values(cols, 3, True, 4, ctx=ctx, salt=salt)
+    ref = check_batch(V, oracle, b, cols, 3, 4, False, salt)
+    assert b.merkle_tree.leaves.shape[1] == 24
+    assert np.array_equal(b.get_lde_values(5), ref["leaves"][V.reverse_bits(5, 11)][:20])
+    # a fresh random salt is drawn on the host when none is given
+    b2 = V.PolynomialBatch.from_values(cols, 3, True, 4, ctx=ctx, rng=np.random.default_rng(1))
+    assert not np.array_equal(b2.merkle_tree.cap, b.merkle_tree.cap)
+    assert np.array_equal(b2.merkle_tree.leaves[:, :20], b.merkle_tree.leaves[:, :20])
+
+
+def test_adversarial_columns(V, ctx, oracle):
+    """All-zero, all-(p-1), non-canonical and 2^64-1 columns."""
+    n = 1 << 10
+    rng = np.random.default_rng(4)
+    cols = np.stack([np.zeros(n, np.uint64), np.full(n, P - 1, np.uint64),
+                     np.full(n, 2**64 - 1, np.uint64), np.full(n, P, np.uint64),
+                     rng.integers(P, 2**64, size=n, dtype=np.uint64),
+                     np.arange(n, dtype=np.uint64)])
+    for coeffs in (False, True):
+        f = V.PolynomialBatch.from_coeffs if coeffs else V.PolynomialBatch.from_values
+        b = f(cols, 3, False, 4, ctx=ctx)
+        check_batch(V, oracle, b, cols, 3, 4, coeffs)
+    assert (b.merkle_tree.leaves < np.uint64(P)).all()
+
+
+def test_commit_rejects_bad_arguments(V, ctx):
+    with pytest.raises(ValueError):
+        V.PolynomialBatch.from_values(np.zeros((2, 8), np.uint64), 1, False, 5, ctx=ctx)
+    cols = np.zeros((1, 8), np.uint64)
+    colp = (V._lib.u64p * 1)(cols[0].ctypes.data_as(V._lib.u64p))
+    cap = np.zeros((64, 4), np.uint64)
+    rc = ctx.lib.vpbs_commit(ctx.handle, colp, 1, 3, 1, 5, 0, None, None, None, None,
+                             cap.ctypes.data_as(V._lib.u64p), None)
+    assert rc == V._lib.VPBS_ERR_ARG
+    rc = ctx.lib.vpbs_commit(ctx.handle, colp, 0, 3, 1, 1, 0, None, None, None, None,
+                             cap.ctypes.data_as(V._lib.u64p), None)
+    assert rc == V._lib.VPBS_ERR_ARG
+
+
+def test_oracle_regression_pins_on_gpu(V, ctx, oracle_commits):
+    """Committed fixtures (caps + sha256 of every output) incl. the N=8 step shapes and 2^16 rows."""
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for c in oracle_commits["cases"]:
+        cols = V.synthetic_columns(c["ncols"], 1 << c["log_n"], c["seed"], c["canonical"])
+        f = V.PolynomialBatch.from_coeffs if c["inputs_are_coeffs"] else V.PolynomialBatch.from_values
+        b = f(cols, c["rate_bits"], False, c["cap_height"], ctx=ctx)
+        assert ["%016x" % int(x) for x in b.merkle_tree.cap.reshape(-1)] == sum(c["cap"], [])
+        assert sha(b.polynomials) == c["sha256_coeffs"]
+        assert sha(b.merkle_tree.leaves) == c["sha256_leaves"]
+        assert sha(b.merkle_tree.digests) == c["sha256_digests"]
+
+
+# ------------------------------------------------------------------------------ full-size configs
+def test_microbench_config_full_size(V, ctx, oracle):
+    """BASELINE.json configs[1]: 2^16 rows x 128 columns, rate_bits 3, cap_height 4 — compared
+    bit-for-bit with the (multi-threaded) oracle, plus size-independent properties."""
+    cols = V.synthetic_columns(128, 1 << 16)
+    b = V.PolynomialBatch.from_values(cols, 3, False, 4, ctx=ctx)
+    ref = oracle.commit(cols, 3, 4, False)
+    assert np.array_equal(b.merkle_tree.cap, ref["cap"])
+    assert np.array_equal(b.polynomials, ref["coeffs"])
+    assert np.array_equal(b.merkle_tree.digests, ref["digests"])
+    assert np.array_equal(b.merkle_tree.leaves, ref["leaves"])
+    # properties: round trip, linearity of the LDE, Merkle openings verify
+    assert np.array_equal(V.fft(b.polynomials[5], ctx), cols[5])
+    rnd = random.Random(3)
+    for _ in range(4):
+        i = rnd.randrange(1 << 19)
+        assert oracle.merkle_verify(b.merkle_tree.get(i), i, b.merkle_tree.prove(i).siblings,
+                                    b.merkle_tree.cap)
+    # leaf k = natural LDE row bitrev(k): evaluate column 3 directly at 7 * w^bitrev(k)
+    w = oracle.primitive_root_of_unity(19)
+    for k in (0, 1, 12345, (1 << 19) - 1):
+        x = oracle.gl_mul(7, oracle.gl_pow(w, V.reverse_bits(k, 19)))
+        acc = 0
+        for c in b.polynomials[3][::-1]:
+            acc = (acc * x + int(c)) % P
+        assert int(b.merkle_tree.leaves[k, 3]) == acc
+
+
+def test_step_shapes_full_size(V, ctx, oracle):
+    """BASELINE.json configs[2] stand-in: the three commits of one N=1024 IVC step."""
+    for (ncols, coeffs, seed) in ((135, False, 0x5EED0000), (20, False, 0x5EED1000), (16, True, 0x5EED2000)):
+        cols = V.synthetic_columns(ncols, 1 << 16, seed)
+        f = V.PolynomialBatch.from_coeffs if coeffs else V.PolynomialBatch.from_values
+        b = f(cols, 3, False, 4, ctx=ctx)
+        ref = oracle.commit(cols, 3, 4, coeffs)
+        assert np.array_equal(b.merkle_tree.cap, ref["cap"])
+        assert np.array_equal(b.merkle_tree.digests, ref["digests"])
+        assert np.array_equal(b.merkle_tree.leaves, ref["leaves"])
+
+
+def test_linearity_of_lde(V, ctx):
+    """LDE(a + b) = LDE(a) + LDE(b) on full-size columns (size-independent property)."""
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, P, size=(2, 1 << 16), dtype=np.uint64)
+    s = ((a[0].astype(object) + a[1].astype(object)) % P).astype(np.uint64).reshape(1, -1)
+    la = V.PolynomialBatch.from_values(a, 3, False, 4, ctx=ctx).merkle_tree.leaves
+    ls = V.PolynomialBatch.from_values(s, 3, False, 4, ctx=ctx).merkle_tree.leaves
+    want = (la[:, 0].astype(object) + la[:, 1].astype(object)) % P
+    assert np.array_equal(ls[:, 0].astype(object), want)

@@ -1,0 +1,150 @@
+"""CPU suite, part 1: pin the oracle (oracle/oracle.c) before anything is compared against it.
+
+Pins: plonky2's Poseidon known-answer vectors; the reference's Goldilocks NTT vectors
+(/root/reference/src/ntt/params_*.rs, committed as tests/golden/ntt_params.npz); the independent
+Python model (oracle/model.py) incl. the SURVEY.md §8(c) anchors; regression pins for mid-size
+commits.  No reference test pins an LDE value / digest / cap, so the commit boundary itself stays
+"parity unpinned" against plonky2 proper (see oracle/oracle.h).
+"""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from conftest import unhex
+
+P = 2**64 - 2**32 + 1
+
+
+def test_round_constants_match_published_prefix(oracle, poseidon_kat):
+    rc = oracle.round_constants()
+    assert ["%016x" % int(x) for x in rc[:12]] == poseidon_kat["round_constants_first12"]
+    assert ["%016x" % int(x) for x in rc[-4:]] == poseidon_kat["round_constants_last4"]
+    assert all(int(x) < P for x in rc)
+
+
+def test_poseidon_known_answers(oracle, poseidon_kat):
+    from oracle import model
+    for v in poseidon_kat["vectors"]:
+        inp = [int(x, 16) for x in v["input"]]
+        want = [int(x, 16) for x in v["output"]]
+        assert [int(x) for x in oracle.poseidon(inp)] == want
+        assert model.poseidon(inp) == want
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024, 2048])
+def test_reference_ntt_vectors(oracle, ntt_params, n):
+    """ROOTS[i] = w^bitrev(i) with w = primitive_root_of_unity(log2 2N); NINV = N^-1;
+    TESTGHAT[k] = TESTG(w^(2*bitrev(k)+1)) = coset_fft(TESTG, shift = w)[bitrev(k)]."""
+    lg = n.bit_length() - 1
+    w = oracle.primitive_root_of_unity(lg + 1)
+    rev = lambda i: int(format(i, "0%db" % lg)[::-1], 2)
+    roots, invroots = ntt_params["ROOTS_%d" % n], ntt_params["INVROOTS_%d" % n]
+    for i in range(n):
+        assert int(roots[i]) == oracle.gl_pow(w, rev(i))
+        assert oracle.gl_mul(int(roots[i]), int(invroots[i])) == 1
+    assert oracle.gl_mul(int(ntt_params["NINV_%d" % n][0]), n) == 1
+    g, ghat = ntt_params["TESTG_%d" % n], ntt_params["TESTGHAT_%d" % n]
+    ev = oracle.coset_fft(g, w)
+    assert [int(ev[rev(k)]) for k in range(n)] == [int(x) for x in ghat]
+    # the same numbers through the zero-padded size-2N transform (the LDE structure, shift 1)
+    padded = np.concatenate([g, np.zeros(n, np.uint64)])
+    full = oracle.fft(padded)
+    assert [int(full[2 * rev(k) + 1]) for k in range(n)] == [int(x) for x in ghat]
+    # and back
+    assert [int(x) for x in oracle.ifft(full)[:n]] == [int(x) for x in g]
+
+
+def test_field_ops_against_bigint(oracle):
+    rnd = random.Random(7)
+    edge = [0, 1, 2, P - 1, P, P + 1, 2**64 - 1, 2**32 - 1, 2**32, 2**32 + 1, P - 2**32, 2**63]
+    for _ in range(20000):
+        a = rnd.choice(edge) if rnd.random() < 0.3 else rnd.getrandbits(64)
+        b = rnd.choice(edge) if rnd.random() < 0.3 else rnd.getrandbits(64)
+        assert oracle.gl_mul(a, b) == a * b % P
+        assert oracle.gl_add(a, b) == (a + b) % P
+        assert oracle.gl_sub(a, b) == (a - b) % P
+    assert oracle.primitive_root_of_unity(32) == 1753635133440165772
+    assert oracle.gl_pow(7, (P - 1) >> 32) == 1753635133440165772
+
+
+def test_model_anchor_hashes(oracle, model_anchors):
+    assert ["%016x" % int(x) for x in oracle.hash_no_pad(list(range(1, 10)))] == model_anchors["hash_no_pad_1_9"]
+    assert ["%016x" % int(x) for x in oracle.hash_no_pad(list(range(8)))] == model_anchors["hash_no_pad_0_7"]
+    assert ["%016x" % int(x) for x in oracle.two_to_one([1, 2, 3, 4], [5, 6, 7, 8])] == \
+        model_anchors["two_to_one_1234_5678"]
+    assert [int(x) for x in oracle.hash_or_noop([])] == [0, 0, 0, 0]
+    assert [int(x) for x in oracle.hash_or_noop([5, P + 3])] == [5, 3, 0, 0]
+
+
+def test_model_anchor_commits(oracle, model_anchors):
+    for c in model_anchors["commits"]:
+        cols = unhex(c["cols"])
+        salt = unhex(c["salt"]) if c["salt"] else None
+        res = oracle.commit(cols, c["rate_bits"], c["cap_height"], c["inputs_are_coeffs"], salt,
+                            want_lde=True)
+        assert np.array_equal(res["coeffs"], unhex(c["coeffs"])), c["name"]
+        assert np.array_equal(res["lde"], unhex(c["lde"])), c["name"]
+        assert np.array_equal(res["leaves"], unhex(c["leaves"])), c["name"]
+        want_d = unhex(c["digests"]) if c["digests"] else np.empty((0, 4), np.uint64)
+        assert np.array_equal(res["digests"], want_d), c["name"]
+        assert np.array_equal(res["cap"], unhex(c["cap"])), c["name"]
+
+
+def test_survey_anchor_values(model_anchors):
+    """The anchors SURVEY.md §8(c) records for the 8-row x 9-column commit."""
+    c = next(x for x in model_anchors["commits"] if x["name"] == "survey_8x9")
+    assert c["coeffs"][0][:3] == ["7fffffff80000005", "80007f7f7f800080", "80007fff80000000"]
+    assert c["lde"][0][:3] == ["f868a66099900b7d", "770b6c1aa730220e", "b7390621061fb4dc"]
+    assert c["leaves"][1][:3] == ["3c37599c666e1f6c", "3c37599c666e1f74", "3c37599c666e1f7c"]
+    assert c["cap"][0] == ["eb316d0b1882f2bc", "cb2b3eae135bbfe0", "48e51bf3ded5e389", "7f2d103884aed82f"]
+    assert c["cap"][1] == ["66f4c4c80b305b4b", "db102bfea741c68a", "2cbdd859051f223e", "0a7bbc3e907a28b2"]
+
+
+def test_model_vs_oracle_random_small(oracle):
+    from oracle import model
+    rnd = random.Random(11)
+    for _ in range(40):
+        lg = rnd.randint(0, 4)
+        C = rnd.choice([1, 2, 3, 4, 5, 8, 9, 16, 20])
+        r = rnd.randint(0, 3)
+        h = rnd.randint(0, lg + r)
+        co, sa = rnd.random() < 0.3, rnd.random() < 0.3
+        n, m = 1 << lg, (1 << lg) << r
+        cols = [[rnd.getrandbits(64) for _ in range(n)] for _ in range(C)]
+        sc = [[rnd.getrandbits(64) for _ in range(m)] for _ in range(4)] if sa else None
+        a = oracle.commit(np.array(cols, dtype=np.uint64), r, h, co,
+                          np.array(sc, dtype=np.uint64) if sa else None, want_lde=True)
+        b = model.commit(cols, r, h, co, sc)
+        for k in ("coeffs", "lde", "leaves", "cap"):
+            assert a[k].tolist() == b[k], (lg, C, r, h, co, sa, k)
+        assert a["digests"].tolist() == b["digests"]
+        i = rnd.randrange(m)
+        sib = oracle.merkle_prove(a["digests"], m, h, i)
+        assert sib.tolist() == model.merkle_prove(b["digests"], m, h, i)
+        assert oracle.merkle_verify(a["leaves"][i], i, sib, a["cap"])
+        bad = a["leaves"][i].copy()
+        bad[0] ^= np.uint64(1)
+        assert not oracle.merkle_verify(bad, i, sib, a["cap"])
+
+
+def test_oracle_rejects_what_plonky2_asserts(oracle):
+    leaves = np.zeros((6, 3), np.uint64)
+    with pytest.raises(ValueError):
+        oracle.merkle_new(leaves, 1)            # not a power of two
+    with pytest.raises(ValueError):
+        oracle.merkle_new(np.zeros((8, 3), np.uint64), 4)  # cap_height > log2(leaves)
+
+
+def test_oracle_regression_pins(oracle, oracle_commits, V):
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for c in oracle_commits["cases"]:
+        if c["log_n"] > 13:
+            continue  # the 2^16 case is checked on the GPU box (keeps the CPU suite short)
+        cols = V.synthetic_columns(c["ncols"], 1 << c["log_n"], c["seed"], c["canonical"])
+        res = oracle.commit(cols, c["rate_bits"], c["cap_height"], c["inputs_are_coeffs"])
+        assert ["%016x" % int(x) for x in res["cap"].reshape(-1)] == sum(c["cap"], [])
+        assert sha(res["coeffs"]) == c["sha256_coeffs"]
+        assert sha(res["leaves"]) == c["sha256_leaves"]
+        assert sha(res["digests"]) == c["sha256_digests"]

@@ -1,0 +1,139 @@
+// merkle.cuh — Poseidon leaf hashing and level-by-level Merkle reduction (sm_100a).
+//
+// Replaces, for H = PoseidonHash over GoldilocksField:
+//   [P2] plonky2 0.2.0 src/hash/hashing.rs      hash_n_to_m_no_pad (overwrite-mode sponge), compress
+//   [P2] plonky2 0.2.0 src/plonk/config.rs      Hasher::hash_or_noop / two_to_one
+//   [P2] plonky2 0.2.0 src/hash/merkle_tree.rs  MerkleTree::new / fill_digests_buf / fill_subtree
+// reached from PolynomialBatch::from_coeffs ("build Merkle tree" scope) in every prove()/build() of
+// the reference (/root/reference/src/vtfhe/ivc_based_vpbs.rs:275,302,333,364).
+//
+// The digests buffer uses plonky2's layout so MerkleTree::prove's index arithmetic is unchanged:
+// inside one cap subtree, the sibling pair q of layer i (layer 0 = leaf digests) lives at hash
+// indices 2*((q << (i+1)) + (1 << i) - 1) and +1.
+#pragma once
+#include "poseidon.cuh"
+
+namespace merkle {
+
+using gl::u32;
+using gl::u64;
+
+struct Hash4 {
+  u64 e[4];
+};
+
+__device__ __forceinline__ void store_hash(u64* dst, const u64 (&s)[poseidon::WIDTH]) {
+  // hashes are 32-byte aligned (cudaMalloc base + 32 * index)
+  ulonglong2* d = reinterpret_cast<ulonglong2*>(dst);
+  d[0] = make_ulonglong2(gl::canon(s[0]), gl::canon(s[1]));
+  d[1] = make_ulonglong2(gl::canon(s[2]), gl::canon(s[3]));
+}
+
+// hash_or_noop of one row of `width` elements (any u64 values).
+__device__ __forceinline__ void hash_row(const u64* __restrict__ row, u32 width, u64* out) {
+  u64 s[poseidon::WIDTH];
+#pragma unroll
+  for (int i = 0; i < poseidon::WIDTH; i++) s[i] = 0;
+  if (width <= 4) {  // [P2] hash_or_noop: inputs that fit in a hash are copied, not hashed
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if ((u32)i < width) s[i] = __ldg(row + i);
+    store_hash(out, s);
+    return;
+  }
+  u32 off = 0;
+  for (; off + poseidon::RATE <= width; off += poseidon::RATE) {
+#pragma unroll
+    for (int i = 0; i < poseidon::RATE; i++) s[i] = __ldg(row + off + i);
+    poseidon::permute_lazy(s);
+  }
+  if (off < width) {  // short last chunk overwrites only the first lanes
+#pragma unroll
+    for (int i = 0; i < poseidon::RATE; i++)
+      if (off + i < width) s[i] = __ldg(row + off + i);
+    poseidon::permute_lazy(s);
+  }
+  store_hash(out, s);
+}
+
+// Position (in hashes) of leaf digest `l` of a cap subtree inside that subtree's digest buffer.
+__device__ __forceinline__ u64 leaf_digest_pos(u64 l) { return 4 * (l >> 1) + (l & 1); }
+
+// One thread per leaf.  all_cap: the tree has no digests, leaf hashes are the cap.
+__global__ void __launch_bounds__(128)
+hash_leaves(const u64* __restrict__ leaves, u64 nleaves, u32 width, u64* __restrict__ out,
+            unsigned log_sub, u64 sub_digests, int all_cap) {
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nleaves) return;
+  u64 pos = k;
+  if (!all_cap) {
+    const u64 sub = k >> log_sub, l = k & ((1ULL << log_sub) - 1);
+    pos = sub * sub_digests + leaf_digest_pos(l);
+  }
+  hash_row(leaves + k * width, width, out + 4 * pos);
+}
+
+// Layer `level` (>= 1) of every cap subtree: node jj = two_to_one(children pair jj of level-1).
+// level == log_sub writes the subtree roots into `cap`.
+__global__ void __launch_bounds__(128)
+reduce_level(u64* __restrict__ digests, u64* __restrict__ cap, unsigned level, unsigned log_sub,
+             u64 sub_digests, u64 nnodes) {
+  const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnodes) return;
+  const unsigned log_nodes = log_sub - level;
+  const u64 sub = j >> log_nodes, jj = j & ((1ULL << log_nodes) - 1);
+  u64* base = digests + 4 * sub * sub_digests;
+  const ulonglong2* ch = reinterpret_cast<const ulonglong2*>(
+      base + 4 * (2 * ((jj << level) + (1ULL << (level - 1)) - 1)));
+  u64 s[poseidon::WIDTH];
+  const ulonglong2 a = ch[0], b = ch[1], c = ch[2], d = ch[3];
+  s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
+  s[4] = c.x; s[5] = c.y; s[6] = d.x; s[7] = d.y;
+  s[8] = s[9] = s[10] = s[11] = 0;
+  poseidon::permute_lazy(s);
+  u64* out = (level == log_sub)
+                 ? cap + 4 * sub
+                 : base + 4 * (2 * (((jj >> 1) << (level + 1)) + (1ULL << level) - 1) + (jj & 1));
+  store_hash(out, s);
+}
+
+// Blinding columns: leaves[k][first_col + s] = salt[s][bitrev(first_leaf + k)] (salt vectors are
+// extra lde_values() columns in natural order; they get transposed/bit-reversed like the rest).
+__global__ void scatter_salt(const u64* __restrict__ salt, u64 m, unsigned log_m, u64 first_leaf,
+                             u64 nleaves, u64* __restrict__ leaves, u32 width, u32 first_col) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nleaves * 4) return;
+  const u64 k = i >> 2;
+  const u32 s = (u32)(i & 3);
+  const u64 g = first_leaf + k;
+  const u64 nat = log_m ? (__brevll(g) >> (64 - log_m)) : 0;
+  leaves[k * width + first_col + s] = gl::canon(__ldg(salt + (u64)s * m + nat));
+}
+
+// ---- small batch entry points (tests / callers that hash outside a tree) -----------------------
+__global__ void permute_batch(u64* states, u64 count) {
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  u64 s[poseidon::WIDTH];
+#pragma unroll
+  for (int i = 0; i < poseidon::WIDTH; i++) s[i] = states[k * poseidon::WIDTH + i];
+  poseidon::permute_lazy(s);
+#pragma unroll
+  for (int i = 0; i < poseidon::WIDTH; i++) states[k * poseidon::WIDTH + i] = gl::canon(s[i]);
+}
+__global__ void two_to_one_batch(const u64* __restrict__ l, const u64* __restrict__ r, u64 count,
+                                 u64* __restrict__ out) {
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  u64 s[poseidon::WIDTH];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    s[i] = l[4 * k + i];
+    s[4 + i] = r[4 * k + i];
+    s[8 + i] = 0;
+  }
+  poseidon::permute_lazy(s);
+  store_hash(out + 4 * k, s);
+}
+
+}  // namespace merkle

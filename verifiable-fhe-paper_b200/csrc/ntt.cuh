@@ -1,0 +1,180 @@
+// ntt.cuh — batched Goldilocks NTT passes for the commit path (sm_100a).
+//
+// Replaces, for F = GoldilocksField:
+//   [P2] plonky2_field 0.2.0 src/fft.rs            fft_dispatch / fft_classic / ifft_with_options
+//   [P2] plonky2_field 0.2.0 src/polynomial/mod.rs PolynomialCoeffs::{lde, coset_fft_with_options}
+//   [P2] plonky2_util 0.2.0  src/lib.rs            transpose + reverse_index_bits_in_place
+// as reached from PolynomialBatch::from_values / from_coeffs ([P2] plonky2/src/fri/oracle.rs),
+// i.e. from prove()/build() at /root/reference/src/vtfhe/ivc_based_vpbs.rs:275,302,333,364.
+//
+// Algorithm: decimation-in-frequency, split into passes of up to 8 layers.  A pass of s layers
+// on blocks of size B is a batch of 2^s-point DFTs over stride B/2^s done in shared memory
+// (bit-reversed in-place output), followed by one twiddle w_B^(low*k) per element (four-step
+// form), so global memory is touched once per pass and the only global twiddle traffic is one
+// table read per element.  After all passes position `pos` holds X[bitrev(pos)]:
+//   * the forward LDE wants exactly that order (plonky2 bit-reverses the leaves), so its last pass
+//     writes rows of the row-major leaf matrix directly (transpose fused, 128-byte row segments);
+//   * the inverse transform / plain fft undo it in the last pass's store (natural order out).
+// The LDE never materialises the zero padding: leaf block b (n rows) is the size-n transform of
+// c_j * (7 w_m^bitrev(b))^j (what fft_classic's zero_factor skipping amounts to).
+#pragma once
+#include "gl64.cuh"
+
+namespace ntt {
+
+using gl::u32;
+using gl::u64;
+
+constexpr int THREADS = 256;
+constexpr unsigned LOG_TILE = 12;  // 4096 elements (32 KB) per CTA
+constexpr unsigned MAX_PASS_BITS = 8;
+
+struct Roots {
+  const u64* w;    // w[t] = omega_N^t, t < N/2
+  unsigned log_N;  // >= 1
+};
+
+__device__ __forceinline__ unsigned brev(unsigned x, unsigned bits) {
+  return bits ? (__brev(x) >> (32 - bits)) : 0u;
+}
+// omega_{2^lg}^(+-e), 0 <= e < 2^lg, lg <= log_N.
+template <bool INVERSE>
+__device__ __forceinline__ u64 root_of(const Roots& R, unsigned lg, u64 e) {
+  u64 idx = e << (R.log_N - lg);
+  const u64 N = 1ULL << R.log_N, half = N >> 1;
+  if (INVERSE && idx) idx = N - idx;
+  return idx < half ? __ldg(R.w + idx) : gl::P - __ldg(R.w + (idx - half));  // roots are never 0
+}
+
+// s radix-2 DIF layers over sm[q * pitch + t], q < 2^s, t < 2^log_T; tw[e] = omega_{2^s}^(+-e).
+__device__ __forceinline__ void dif_layers(u64* sm, const u64* tw, unsigned s, unsigned log_T,
+                                           unsigned pitch) {
+  const unsigned half_elems = (1u << s >> 1) << log_T;
+  for (unsigned l = 0; l < s; l++) {
+    const unsigned log_dd = s - 1 - l, dd = 1u << log_dd;
+    for (unsigned b = threadIdx.x; b < half_elems; b += THREADS) {
+      const unsigned t = b & ((1u << log_T) - 1), pi = b >> log_T;
+      const unsigned j = pi & (dd - 1);
+      const unsigned q_lo = ((pi >> log_dd) << (log_dd + 1)) + j;
+      u64* pa = sm + q_lo * pitch + t;
+      u64* pb = pa + dd * pitch;
+      const u64 a = *pa, c = *pb;
+      *pa = gl::add(a, c);
+      *pb = gl::mul(gl::sub(a, c), tw[j << l]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- pass over a strided sub-transform (every pass but the last) ------------------------------
+// Column-major data; blocks of size 2^log_B; 2^s-point DFT over stride sigma = 2^(log_B - s);
+// a CTA takes 2^log_T consecutive `low` offsets (contiguous in memory).  blockIdx.y = column.
+template <bool INVERSE>
+__global__ void __launch_bounds__(THREADS)
+pass_strided(const u64* __restrict__ src, u64 src_col_stride, u64* __restrict__ dst,
+             u64 dst_col_stride, unsigned log_B, unsigned s, unsigned log_T,
+             const u64* __restrict__ in_scale, Roots R) {
+  extern __shared__ u64 sm[];
+  const unsigned S = 1u << s, T = 1u << log_T;
+  const unsigned log_sigma = log_B - s;
+  u64* tw = sm + (S << log_T);
+  const unsigned tiles_per_block_log = log_sigma - log_T;
+  const u64 blk = blockIdx.x >> tiles_per_block_log;
+  const u64 low0 = (u64)(blockIdx.x & ((1u << tiles_per_block_log) - 1)) << log_T;
+  const u64 base = blk << log_B;
+  src += (u64)blockIdx.y * src_col_stride;
+  dst += (u64)blockIdx.y * dst_col_stride;
+
+  for (unsigned e = threadIdx.x; e < S / 2; e += THREADS) tw[e] = root_of<INVERSE>(R, s, e);
+  for (unsigned idx = threadIdx.x; idx < (S << log_T); idx += THREADS) {
+    const unsigned t = idx & (T - 1), q = idx >> log_T;
+    const u64 pos = base + ((u64)q << log_sigma) + low0 + t;
+    u64 x = gl::canon(__ldg(src + pos));
+    if (in_scale) x = gl::mul(x, __ldg(in_scale + pos));
+    sm[idx] = x;
+  }
+  __syncthreads();
+  dif_layers(sm, tw, s, log_T, T);
+  for (unsigned idx = threadIdx.x; idx < (S << log_T); idx += THREADS) {
+    const unsigned t = idx & (T - 1), q = idx >> log_T;
+    const u64 pos = base + ((u64)q << log_sigma) + low0 + t;
+    const u64 e = (low0 + t) * (u64)brev(q, s);  // < 2^log_B
+    u64 x = sm[idx];
+    if (e) x = gl::mul(x, root_of<INVERSE>(R, log_B, e));
+    dst[pos] = x;
+  }
+}
+
+// ---- last pass: contiguous 2^s-point blocks ------------------------------------------------------
+enum StoreMode { STORE_LEAF = 0, STORE_NATURAL = 1 };
+// STORE_LEAF   : lanes = 2^log_T consecutive columns (blockIdx.y), block = blockIdx.x;
+//                dst[(row0 + pos) * dst_stride + col]  (row-major leaf matrix; pos = leaf index
+//                inside this LDE block: transpose + reverse_index_bits fused).
+// STORE_NATURAL: lanes = 2^log_T blocks whose bit-reversed ids are consecutive, column =
+//                blockIdx.y; dst[col * dst_stride + bitrev(pos)]  (natural order, column-major).
+template <bool INVERSE, int MODE>
+__global__ void __launch_bounds__(THREADS)
+pass_final(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
+           u64* __restrict__ dst, u64 dst_stride, u64 row0, unsigned log_n, unsigned s,
+           unsigned log_T, const u64* __restrict__ in_scale, u64 out_scale, Roots R) {
+  extern __shared__ u64 sm[];
+  const unsigned S = 1u << s, T = 1u << log_T, pitch = T + 1;
+  u64* tw = sm + S * pitch;
+  const unsigned log_nb = log_n - s;  // blocks per column
+  for (unsigned e = threadIdx.x; e < S / 2; e += THREADS) tw[e] = root_of<INVERSE>(R, s, e);
+
+  for (unsigned idx = threadIdx.x; idx < (S << log_T); idx += THREADS) {
+    const unsigned q = idx & (S - 1), lane = idx >> s;
+    u64 x = 0;
+    if (MODE == STORE_LEAF) {
+      const unsigned col = blockIdx.y * T + lane;
+      if (col < ncols) {
+        const u64 pos = ((u64)blockIdx.x << s) + q;
+        x = gl::canon(__ldg(src + (u64)col * src_col_stride + pos));
+        if (in_scale) x = gl::mul(x, __ldg(in_scale + pos));
+      }
+    } else {
+      const u64 blk = brev(blockIdx.x * T + lane, log_nb);
+      const u64 pos = (blk << s) + q;
+      x = gl::canon(__ldg(src + (u64)blockIdx.y * src_col_stride + pos));
+      if (in_scale) x = gl::mul(x, __ldg(in_scale + pos));
+    }
+    sm[q * pitch + lane] = x;
+  }
+  __syncthreads();
+  dif_layers(sm, tw, s, log_T, pitch);
+  for (unsigned idx = threadIdx.x; idx < (S << log_T); idx += THREADS) {
+    const unsigned lane = idx & (T - 1), q = idx >> log_T;
+    u64 x = sm[q * pitch + lane];
+    if (out_scale != 1) x = gl::mul(x, out_scale);
+    if (MODE == STORE_LEAF) {
+      const unsigned col = blockIdx.y * T + lane;
+      const u64 pos = ((u64)blockIdx.x << s) + q;
+      if (col < ncols) dst[(row0 + pos) * dst_stride + col] = x;
+    } else {
+      const u64 nat = ((u64)brev(q, s) << log_nb) + (u64)blockIdx.x * T + lane;
+      dst[(u64)blockIdx.y * dst_stride + nat] = x;
+    }
+  }
+}
+
+// ---- tables ------------------------------------------------------------------------------------
+// w[t] = omega_N^t for t < N/2.
+__global__ void fill_roots(u64* w, unsigned log_N) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (1ULL << (log_N - 1))) return;
+  w[t] = gl::pow(gl::primitive_root_of_unity(log_N), t);
+}
+// out[b * n + j] = (shift * omega_m^bitrev_r(b))^j  for b < 2^rate_bits, j < n = 2^log_n,
+// m = n << rate_bits: the per-block coset factors of the LDE (rate_bits = 0: plain shift^j).
+__global__ void fill_coset_powers(u64* out, unsigned log_n, unsigned rate_bits, u64 shift) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1ULL << (log_n + rate_bits))) return;
+  const u64 j = i & ((1ULL << log_n) - 1);
+  const unsigned b = (unsigned)(i >> log_n);
+  const u64 g = gl::mul(gl::canon(shift),
+                        gl::pow(gl::primitive_root_of_unity(log_n + rate_bits), brev(b, rate_bits)));
+  out[i] = gl::pow(g, j);
+}
+
+}  // namespace ntt

@@ -1,0 +1,697 @@
+// vpbs_commit.cu — context, launch orchestration and the C ABI of libvpbs_commit.so.
+// See include/vpbs_commit.h for the contract and the plonky2 0.2.0 items each entry replaces.
+//
+// HBM layout of one commit (n = 2^log_n rows, C columns, r = rate_bits, m = n << r):
+//   values   C x n   column-major   (caller / arena "in")
+//   coeffs   C x n   column-major   (PolynomialBatch.polynomials)
+//   work     C x n   column-major   scratch of the multi-pass NTT (stays L2-resident per block)
+//   leaves   m x W   row-major      W = C (+4 salt); leaf k = natural LDE row bitrev(k)
+//   digests  2(m - 2^h) x 4, plonky2 layout;  cap 2^h x 4
+// There is no CPU fallback anywhere in this file: every path ends in a kernel launch or an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vpbs_commit.h"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+using gl::u32;
+using gl::u64;
+
+namespace {
+
+std::mutex g_err_mu;
+std::string g_global_err;
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct vpbs_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  // twiddles
+  u64* roots = nullptr;
+  unsigned roots_log = 0;
+  std::map<std::pair<unsigned, std::pair<unsigned, u64>>, u64*> coset_tables;  // (log_n,(r,shift))
+  // grow-only arena
+  std::map<std::string, Buf> arena;
+  cudaEvent_t ev[8] = {};
+};
+
+namespace {
+
+int fail(vpbs_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  else {
+    std::lock_guard<std::mutex> g(g_err_mu);
+    g_global_err = msg;
+  }
+  return code;
+}
+#define CU(ctx, call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? VPBS_ERR_OOM : VPBS_ERR_CUDA,     \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                     \
+  } while (0)
+
+int arena_get(vpbs_ctx* ctx, const char* name, size_t bytes, void** out) {
+  Buf& b = ctx->arena[name];
+  if (b.bytes < bytes) {
+    if (b.p) {
+      CU(ctx, cudaStreamSynchronize(ctx->stream));
+      CU(ctx, cudaFree(b.p));
+      b.p = nullptr;
+      b.bytes = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    CU(ctx, cudaMalloc(&b.p, want));
+    b.bytes = want;
+  }
+  *out = b.p;
+  return VPBS_OK;
+}
+
+int ensure_roots(vpbs_ctx* ctx, unsigned log_N) {
+  if (log_N < 1) log_N = 1;
+  if (ctx->roots && ctx->roots_log >= log_N) return VPBS_OK;
+  if (ctx->roots) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaFree(ctx->roots));
+    ctx->roots = nullptr;
+  }
+  const u64 half = 1ULL << (log_N - 1);
+  CU(ctx, cudaMalloc(&ctx->roots, half * sizeof(u64)));
+  ntt::fill_roots<<<(unsigned)((half + 255) / 256), 256, 0, ctx->stream>>>(ctx->roots, log_N);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  ctx->roots_log = log_N;
+  return VPBS_OK;
+}
+
+int get_coset_table(vpbs_ctx* ctx, unsigned log_n, unsigned rate_bits, u64 shift, const u64** out) {
+  auto key = std::make_pair(log_n, std::make_pair(rate_bits, shift));
+  auto it = ctx->coset_tables.find(key);
+  if (it != ctx->coset_tables.end()) {
+    *out = it->second;
+    return VPBS_OK;
+  }
+  if (ctx->coset_tables.size() >= 16) {  // bounded cache
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& kv : ctx->coset_tables) cudaFree(kv.second);
+    ctx->coset_tables.clear();
+  }
+  const u64 total = 1ULL << (log_n + rate_bits);
+  u64* t = nullptr;
+  CU(ctx, cudaMalloc(&t, total * sizeof(u64)));
+  ntt::fill_coset_powers<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(t, log_n,
+                                                                                 rate_bits, shift);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  ctx->coset_tables[key] = t;
+  *out = t;
+  return VPBS_OK;
+}
+
+// Pass plan: the last pass takes min(L, 8) layers, the rest is split evenly (<= 8 each).
+struct Plan {
+  unsigned npass = 0;
+  unsigned s[8];
+};
+Plan make_plan(unsigned L) {
+  Plan p;
+  const unsigned last = L < ntt::MAX_PASS_BITS ? L : ntt::MAX_PASS_BITS;
+  unsigned rest = L - last;
+  const unsigned k = (rest + ntt::MAX_PASS_BITS - 1) / ntt::MAX_PASS_BITS;
+  for (unsigned i = 0; i < k; i++) {
+    unsigned si = rest / (k - i);
+    if (rest % (k - i)) si++;
+    p.s[p.npass++] = si;
+    rest -= si;
+  }
+  p.s[p.npass++] = last;
+  return p;
+}
+
+enum class Out { Leaf, Natural };
+
+// One size-2^log_n transform of `ncols` columns.
+//   src (column-major, stride src_stride) -> dst.  work: scratch ncols x n (needed if npass > 1).
+//   Out::Leaf   : dst = row-major matrix, row stride dst_stride, rows row0.. in bit-reversed order
+//   Out::Natural: dst = column-major, column stride dst_stride, natural order
+template <bool INVERSE>
+int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols, unsigned log_n,
+                  u64* work, Out mode, u64* dst, u64 dst_stride, u64 row0, const u64* in_scale,
+                  u64 out_scale) {
+  const ntt::Roots R{ctx->roots, ctx->roots_log};
+  const Plan plan = make_plan(log_n);
+  const u64 n = 1ULL << log_n;
+  unsigned log_B = log_n;
+  const u64* cur = src;
+  u64 cur_stride = src_stride;
+  for (unsigned p = 0; p + 1 < plan.npass; p++) {
+    const unsigned s = plan.s[p];
+    const unsigned log_sigma = log_B - s;
+    unsigned log_T = ntt::LOG_TILE - s;
+    if (log_T > log_sigma) log_T = log_sigma;
+    const size_t smem = ((size_t)(1u << s << log_T) + (1u << s) / 2) * sizeof(u64);
+    dim3 grid((unsigned)(n >> (s + log_T)), ncols);
+    ntt::pass_strided<INVERSE><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+        cur, cur_stride, work, n, log_B, s, log_T, p == 0 ? in_scale : nullptr, R);
+    ctx->launches++;
+    cur = work;
+    cur_stride = n;
+    log_B -= s;
+  }
+  {
+    const unsigned s = plan.s[plan.npass - 1];
+    const u64* scale = plan.npass == 1 ? in_scale : nullptr;
+    if (mode == Out::Leaf) {
+      const unsigned log_T = 4;
+      const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
+      dim3 grid((unsigned)(n >> s), (ncols + (1u << log_T) - 1) >> log_T);
+      ntt::pass_final<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+          cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
+    } else {
+      unsigned log_T = 4;
+      if (log_T > log_n - s) log_T = log_n - s;
+      const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
+      dim3 grid((unsigned)(n >> (s + log_T)), ncols);
+      ntt::pass_final<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+          cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
+    }
+    ctx->launches++;
+  }
+  CU(ctx, cudaGetLastError());
+  return VPBS_OK;
+}
+
+int log2_strict(u64 n) {
+  if (n == 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while ((1ULL << l) < n) l++;
+  return l;
+}
+
+// MerkleTree::new over device leaves.  nleaves leaves of `width`, split into `nsub` subtrees whose
+// roots go to d_roots; digests in plonky2 layout per subtree.
+int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, unsigned log_sub,
+                 u64* d_digests, u64* d_roots) {
+  const u64 sub_leaves = 1ULL << log_sub;
+  const u64 nsub = nleaves >> log_sub;
+  const u64 sub_digests = 2 * sub_leaves - 2;
+  const int all_cap = log_sub == 0;
+  if (nleaves == 0) return VPBS_OK;
+  merkle::hash_leaves<<<(unsigned)((nleaves + 127) / 128), 128, 0, ctx->stream>>>(
+      d_leaves, nleaves, width, all_cap ? d_roots : d_digests, log_sub, sub_digests, all_cap);
+  ctx->launches++;
+  for (unsigned level = 1; level <= log_sub; level++) {
+    const u64 nnodes = nsub << (log_sub - level);
+    merkle::reduce_level<<<(unsigned)((nnodes + 127) / 128), 128, 0, ctx->stream>>>(
+        d_digests, d_roots, level, log_sub, sub_digests, nnodes);
+    ctx->launches++;
+  }
+  CU(ctx, cudaGetLastError());
+  return VPBS_OK;
+}
+
+struct Timer {
+  vpbs_ctx* ctx;
+  bool on;
+  int n = 0;
+  void mark() {
+    if (on && n < 8) cudaEventRecord(ctx->ev[n++], ctx->stream);
+  }
+  float ms(int a, int b) {
+    float t = 0;
+    if (on && a < n && b < n) cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
+    return t;
+  }
+};
+
+// The commit on device data; shard = LDE blocks [first_leaf/n, +nleaves_shard/n).
+int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate_bits,
+                u32 cap_height, int inputs_are_coeffs, const u64* d_salt, u64 first_leaf,
+                u64 nleaves_shard, u64* d_coeffs_out, u64* d_leaves, u64* d_digests, u64* d_roots,
+                Timer* tm) {
+  if (!d_cols || !d_roots || ncols == 0) return fail(ctx, VPBS_ERR_ARG, "null pointer or ncols == 0");
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  const unsigned log_m = log_n + rate_bits;
+  if (cap_height > log_m)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  const u64 n = 1ULL << log_n, m = n << rate_bits;
+  const u32 width = ncols + (d_salt ? VPBS_SALT_SIZE : 0);
+  if (nleaves_shard == 0 || (nleaves_shard & (n - 1)) || (first_leaf & (n - 1)) ||
+      first_leaf + nleaves_shard > m)
+    return fail(ctx, VPBS_ERR_ARG, "shard must be a whole number of n-row LDE blocks");
+  const unsigned log_sub = log_m - cap_height;  // leaves per cap subtree
+  const bool whole = nleaves_shard == m;
+  if (!whole) {
+    const int lg = log2_strict(nleaves_shard);
+    if (lg < 0 || (first_leaf & (nleaves_shard - 1)) || (unsigned)lg < log_sub)
+      return fail(ctx, VPBS_ERR_ARG,
+                  "shard must be an aligned power of two covering whole cap subtrees");
+  }
+  if (!d_leaves) return fail(ctx, VPBS_ERR_ARG, "leaves buffer required");
+  if (log_sub > 0 && !d_digests) return fail(ctx, VPBS_ERR_ARG, "digests buffer required");
+
+  int rc;
+  if ((rc = ensure_roots(ctx, log_m)) != VPBS_OK) return rc;
+  const u64* coset = nullptr;
+  if ((rc = get_coset_table(ctx, log_n, rate_bits, gl::COSET_SHIFT, &coset)) != VPBS_OK) return rc;
+  u64* work = nullptr;
+  if ((rc = arena_get(ctx, "work", (size_t)ncols * n * sizeof(u64), (void**)&work)) != VPBS_OK)
+    return rc;
+
+  tm->mark();  // 0
+  // "IFFT": values -> coefficients (natural order), scaled by n^-1.
+  const u64* coeffs = d_cols;
+  if (!inputs_are_coeffs) {
+    u64* cbuf = d_coeffs_out;
+    if (!cbuf && (rc = arena_get(ctx, "coeffs", (size_t)ncols * n * sizeof(u64), (void**)&cbuf)))
+      return rc;
+    const u64 n_inv = gl::inv(n % gl::P);
+    if ((rc = run_transform<true>(ctx, d_cols, n, ncols, log_n, work, Out::Natural, cbuf, n, 0,
+                                  nullptr, n_inv)) != VPBS_OK)
+      return rc;
+    coeffs = cbuf;
+  } else if (d_coeffs_out && d_coeffs_out != d_cols) {
+    CU(ctx, cudaMemcpyAsync(d_coeffs_out, d_cols, (size_t)ncols * n * sizeof(u64),
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  tm->mark();  // 1
+  // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
+  // leaf rows.
+  const u64 b0 = first_leaf >> log_n, nb = nleaves_shard >> log_n;
+  for (u64 b = 0; b < nb; b++) {
+    if ((rc = run_transform<false>(ctx, coeffs, n, ncols, log_n, work, Out::Leaf, d_leaves, width,
+                                   b << log_n, coset + ((b0 + b) << log_n), 1)) != VPBS_OK)
+      return rc;
+  }
+  if (d_salt) {
+    const u64 cnt = nleaves_shard * 4;
+    merkle::scatter_salt<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(
+        d_salt, m, log_m, first_leaf, nleaves_shard, d_leaves, width, ncols);
+    ctx->launches++;
+  }
+  tm->mark();  // 2
+  // "build Merkle tree"
+  if ((rc = merkle_build(ctx, d_leaves, nleaves_shard, width, log_sub, d_digests, d_roots)) != VPBS_OK)
+    return rc;
+  tm->mark();  // 3
+  CU(ctx, cudaGetLastError());
+  return VPBS_OK;
+}
+
+void fill_stats(vpbs_stats* st, Timer& tm, uint64_t launches) {
+  // events: 0 start | 1 after ifft | 2 after fft | 3 after merkle  (host variants add h2d/d2h)
+  st->ifft_ms = tm.ms(0, 1);
+  st->fft_ms = tm.ms(1, 2);
+  st->merkle_ms = tm.ms(2, 3);
+  st->kernel_launches = launches;
+}
+
+bool usable(vpbs_ctx* ctx) { return ctx != nullptr; }
+
+int bind(vpbs_ctx* ctx) {
+  if (!usable(ctx)) return VPBS_ERR_STATE;
+  CU(ctx, cudaSetDevice(ctx->device));
+  return VPBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vpbs_abi_version(void) { return VPBS_ABI_VERSION; }
+
+int vpbs_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail(nullptr, VPBS_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return VPBS_ERR_CUDA;
+  }
+  return n;
+}
+
+int vpbs_ctx_create(int device, vpbs_ctx** out) {
+  if (!out) return fail(nullptr, VPBS_ERR_ARG, "out == NULL");
+  *out = nullptr;
+  int n = vpbs_device_count();
+  if (n < 0) return n;
+  if (n == 0) return fail(nullptr, VPBS_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(nullptr, VPBS_ERR_ARG, "device index out of range");
+  vpbs_ctx* ctx = new (std::nothrow) vpbs_ctx();
+  if (!ctx) return fail(nullptr, VPBS_ERR_OOM, "host allocation failed");
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  for (int i = 0; e == cudaSuccess && i < 8; i++) e = cudaEventCreate(&ctx->ev[i]);
+  if (e != cudaSuccess) {
+    fail(nullptr, VPBS_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
+    delete ctx;
+    return VPBS_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return VPBS_OK;
+}
+
+void vpbs_ctx_destroy(vpbs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->arena)
+    if (kv.second.p) cudaFree(kv.second.p);
+  for (auto& kv : ctx->coset_tables) cudaFree(kv.second);
+  if (ctx->roots) cudaFree(ctx->roots);
+  for (int i = 0; i < 8; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int vpbs_ctx_set_stream(vpbs_ctx* ctx, void* cuda_stream) {
+  if (!usable(ctx)) return VPBS_ERR_STATE;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return VPBS_OK;
+}
+
+int vpbs_ctx_sync(vpbs_ctx* ctx) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+const char* vpbs_last_error(vpbs_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> g(g_err_mu);
+  static thread_local std::string copy;
+  copy = g_global_err;
+  return copy.c_str();
+}
+
+uint64_t vpbs_ctx_kernel_launches(vpbs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* vpbs_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void vpbs_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- single-vector transforms --------------------------------------------------------------------
+static int transform_host(vpbs_ctx* ctx, uint64_t* inout, uint32_t log_n, bool inverse, bool coset,
+                          uint64_t shift) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!inout) return fail(ctx, VPBS_ERR_ARG, "inout == NULL");
+  if (log_n > 30) return fail(ctx, VPBS_ERR_ARG, "log_n > 30");
+  const u64 n = 1ULL << log_n;
+  u64 *a = nullptr, *b = nullptr, *w = nullptr;
+  if ((rc = arena_get(ctx, "in", n * sizeof(u64), (void**)&a))) return rc;
+  if ((rc = arena_get(ctx, "coeffs", n * sizeof(u64), (void**)&b))) return rc;
+  if ((rc = arena_get(ctx, "work", n * sizeof(u64), (void**)&w))) return rc;
+  if ((rc = ensure_roots(ctx, log_n))) return rc;
+  const u64* scale = nullptr;
+  if (coset && (rc = get_coset_table(ctx, log_n, 0, shift, &scale))) return rc;
+  CU(ctx, cudaMemcpyAsync(a, inout, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+  if (inverse)
+    rc = run_transform<true>(ctx, a, n, 1, log_n, w, Out::Natural, b, n, 0, nullptr, gl::inv(n % gl::P));
+  else
+    rc = run_transform<false>(ctx, a, n, 1, log_n, w, Out::Natural, b, n, 0, scale, 1);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(inout, b, n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+int vpbs_fft(vpbs_ctx* ctx, uint64_t* inout, uint32_t log_n) {
+  return transform_host(ctx, inout, log_n, false, false, 1);
+}
+int vpbs_ifft(vpbs_ctx* ctx, uint64_t* inout, uint32_t log_n) {
+  return transform_host(ctx, inout, log_n, true, false, 1);
+}
+int vpbs_coset_fft(vpbs_ctx* ctx, uint64_t* inout, uint32_t log_n, uint64_t shift) {
+  return transform_host(ctx, inout, log_n, false, true, shift);
+}
+
+// ---- hashing -------------------------------------------------------------------------------------
+int vpbs_poseidon_permute(vpbs_ctx* ctx, uint64_t* states, uint64_t count) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (count == 0) return VPBS_OK;
+  if (!states) return fail(ctx, VPBS_ERR_ARG, "states == NULL");
+  u64* d = nullptr;
+  const size_t bytes = count * 12 * sizeof(u64);
+  if ((rc = arena_get(ctx, "in", bytes, (void**)&d))) return rc;
+  CU(ctx, cudaMemcpyAsync(d, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  merkle::permute_batch<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d, count);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(states, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_hash_or_noop_batch(vpbs_ctx* ctx, const uint64_t* rows, uint64_t count, uint32_t len,
+                            uint64_t* hashes_out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (count == 0) return VPBS_OK;
+  if (!hashes_out || (len && !rows)) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  u64 *d = nullptr, *h = nullptr;
+  const size_t bytes = count * (size_t)len * sizeof(u64);
+  if ((rc = arena_get(ctx, "leaves", bytes, (void**)&d))) return rc;
+  if ((rc = arena_get(ctx, "cap", count * 32, (void**)&h))) return rc;
+  if (bytes) CU(ctx, cudaMemcpyAsync(d, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  merkle::hash_leaves<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(d, count, len, h, 0,
+                                                                               0, 1);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(hashes_out, h, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_two_to_one_batch(vpbs_ctx* ctx, const uint64_t* left, const uint64_t* right,
+                          uint64_t count, uint64_t* hashes_out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (count == 0) return VPBS_OK;
+  if (!left || !right || !hashes_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  u64 *l = nullptr, *r = nullptr, *h = nullptr;
+  if ((rc = arena_get(ctx, "in", count * 32, (void**)&l))) return rc;
+  if ((rc = arena_get(ctx, "coeffs", count * 32, (void**)&r))) return rc;
+  if ((rc = arena_get(ctx, "cap", count * 32, (void**)&h))) return rc;
+  CU(ctx, cudaMemcpyAsync(l, left, count * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(r, right, count * 32, cudaMemcpyHostToDevice, ctx->stream));
+  merkle::two_to_one_batch<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(l, r, count, h);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(hashes_out, h, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+// ---- MerkleTree::new -----------------------------------------------------------------------------
+int vpbs_merkle_new(vpbs_ctx* ctx, const uint64_t* leaves, uint64_t nleaves, uint32_t leaf_len,
+                    uint32_t cap_height, uint64_t* digests_out, uint64_t* cap_out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  const int lg = log2_strict(nleaves);
+  if (lg < 0) return fail(ctx, VPBS_ERR_ARG, "leaves.len() must be a power of two");
+  if ((int)cap_height > lg)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  if (!cap_out || (leaf_len && !leaves)) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  const u64 ncap = 1ULL << cap_height, ndig = 2 * (nleaves - ncap);
+  if (ndig && !digests_out) return fail(ctx, VPBS_ERR_ARG, "digests_out == NULL");
+  u64 *dl = nullptr, *dd = nullptr, *dc = nullptr;
+  const size_t lbytes = nleaves * (size_t)leaf_len * sizeof(u64);
+  if ((rc = arena_get(ctx, "leaves", lbytes, (void**)&dl))) return rc;
+  if ((rc = arena_get(ctx, "digests", ndig * 32, (void**)&dd))) return rc;
+  if ((rc = arena_get(ctx, "cap", ncap * 32, (void**)&dc))) return rc;
+  if (lbytes) CU(ctx, cudaMemcpyAsync(dl, leaves, lbytes, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = merkle_build(ctx, dl, nleaves, leaf_len, (unsigned)lg - cap_height, dd, dc))) return rc;
+  if (ndig) CU(ctx, cudaMemcpyAsync(digests_out, dd, ndig * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(cap_out, dc, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+// ---- PolynomialBatch::lde_values -------------------------------------------------------------------
+int vpbs_lde_batch(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                   uint32_t rate_bits, int inputs_are_coeffs, uint64_t* const* coeffs_out,
+                   uint64_t* lde_cols_out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!cols || ncols == 0 || !lde_cols_out) return fail(ctx, VPBS_ERR_ARG, "null pointer or ncols == 0");
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  const unsigned log_m = log_n + rate_bits;
+  const u64 n = 1ULL << log_n, m = n << rate_bits;
+  u64 *din = nullptr, *dco = nullptr, *dw = nullptr, *dpad = nullptr, *dout = nullptr;
+  if ((rc = arena_get(ctx, "in", (size_t)ncols * n * 8, (void**)&din))) return rc;
+  if ((rc = arena_get(ctx, "coeffs", (size_t)ncols * n * 8, (void**)&dco))) return rc;
+  if ((rc = arena_get(ctx, "work", (size_t)ncols * m * 8, (void**)&dw))) return rc;
+  if ((rc = arena_get(ctx, "pad", (size_t)ncols * m * 8, (void**)&dpad))) return rc;
+  if ((rc = arena_get(ctx, "leaves", (size_t)ncols * m * 8, (void**)&dout))) return rc;
+  if ((rc = ensure_roots(ctx, log_m))) return rc;
+  const u64* scale = nullptr;
+  if ((rc = get_coset_table(ctx, log_m, 0, gl::COSET_SHIFT, &scale))) return rc;
+  for (u32 c = 0; c < ncols; c++) {
+    if (!cols[c]) return fail(ctx, VPBS_ERR_ARG, "cols[c] == NULL");
+    CU(ctx, cudaMemcpyAsync(din + (u64)c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const u64* coeffs = din;
+  if (!inputs_are_coeffs) {
+    if ((rc = run_transform<true>(ctx, din, n, ncols, log_n, dw, Out::Natural, dco, n, 0, nullptr,
+                                  gl::inv(n % gl::P))))
+      return rc;
+    coeffs = dco;
+  }
+  // PolynomialCoeffs::lde: zero padding made explicit, then one natural-order size-m coset fft.
+  CU(ctx, cudaMemsetAsync(dpad, 0, (size_t)ncols * m * 8, ctx->stream));
+  CU(ctx, cudaMemcpy2DAsync(dpad, m * 8, coeffs, n * 8, n * 8, ncols, cudaMemcpyDeviceToDevice,
+                            ctx->stream));
+  if ((rc = run_transform<false>(ctx, dpad, m, ncols, log_m, dw, Out::Natural, dout, m, 0, scale, 1)))
+    return rc;
+  if (coeffs_out)
+    for (u32 c = 0; c < ncols; c++)
+      if (coeffs_out[c])
+        CU(ctx, cudaMemcpyAsync(coeffs_out[c], coeffs + (u64)c * n, n * 8, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  CU(ctx, cudaMemcpyAsync(lde_cols_out, dout, (size_t)ncols * m * 8, cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+// ---- PolynomialBatch::from_values / from_coeffs ------------------------------------------------------
+int vpbs_commit_shard_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
+                          uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                          uint64_t first_leaf, uint64_t nleaves_shard, uint64_t* d_coeffs_out,
+                          uint64_t* d_leaves_out, uint64_t* d_digests_out, uint64_t* d_roots_out,
+                          vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  const uint64_t l0 = ctx->launches;
+  Timer tm{ctx, stats != nullptr};
+  rc = commit_core(ctx, d_cols, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, nullptr,
+                   first_leaf, nleaves_shard, d_coeffs_out, d_leaves_out, d_digests_out,
+                   d_roots_out, &tm);
+  if (rc) return rc;
+  if (stats) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(stats, 0, sizeof *stats);
+    fill_stats(stats, tm, ctx->launches - l0);
+    stats->total_ms = tm.ms(0, 3);
+  }
+  return VPBS_OK;
+}
+
+int vpbs_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
+                    uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                    const uint64_t* d_salt, uint64_t* d_coeffs_out, uint64_t* d_leaves_out,
+                    uint64_t* d_digests_out, uint64_t* d_cap_out, vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  const uint64_t l0 = ctx->launches;
+  Timer tm{ctx, stats != nullptr};
+  rc = commit_core(ctx, d_cols, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, d_salt, 0,
+                   1ULL << (log_n + rate_bits), d_coeffs_out, d_leaves_out, d_digests_out,
+                   d_cap_out, &tm);
+  if (rc) return rc;
+  if (stats) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(stats, 0, sizeof *stats);
+    fill_stats(stats, tm, ctx->launches - l0);
+    stats->total_ms = tm.ms(0, 3);
+  }
+  return VPBS_OK;
+}
+
+int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                const uint64_t* const* salt_cols, uint64_t* const* coeffs_out, uint64_t* leaves_out,
+                uint64_t* digests_out, uint64_t* cap_out, vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!cols || ncols == 0 || !cap_out) return fail(ctx, VPBS_ERR_ARG, "null pointer or ncols == 0");
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  const unsigned log_m = log_n + rate_bits;
+  if (cap_height > log_m)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  const u64 n = 1ULL << log_n, m = n << rate_bits;
+  const u32 width = ncols + (salt_cols ? VPBS_SALT_SIZE : 0);
+  const u64 ncap = 1ULL << cap_height, ndig = 2 * (m - ncap);
+  u64 *din = nullptr, *dco = nullptr, *dle = nullptr, *ddi = nullptr, *dca = nullptr, *dsa = nullptr;
+  if ((rc = arena_get(ctx, "in", (size_t)ncols * n * 8, (void**)&din))) return rc;
+  if ((rc = arena_get(ctx, "coeffs", (size_t)ncols * n * 8, (void**)&dco))) return rc;
+  if ((rc = arena_get(ctx, "leaves", (size_t)m * width * 8, (void**)&dle))) return rc;
+  if ((rc = arena_get(ctx, "digests", ndig * 32, (void**)&ddi))) return rc;
+  if ((rc = arena_get(ctx, "cap", ncap * 32, (void**)&dca))) return rc;
+  if (salt_cols && (rc = arena_get(ctx, "salt", (size_t)4 * m * 8, (void**)&dsa))) return rc;
+
+  const uint64_t l0 = ctx->launches;
+  cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
+  if (stats) cudaEventRecord(e0, ctx->stream);
+  for (u32 c = 0; c < ncols; c++) {
+    if (!cols[c]) return fail(ctx, VPBS_ERR_ARG, "cols[c] == NULL");
+    CU(ctx, cudaMemcpyAsync(din + (u64)c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (salt_cols)
+    for (int s = 0; s < VPBS_SALT_SIZE; s++) {
+      if (!salt_cols[s]) return fail(ctx, VPBS_ERR_ARG, "salt_cols[s] == NULL");
+      CU(ctx, cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice,
+                              ctx->stream));
+    }
+  if (stats) cudaEventRecord(e1, ctx->stream);
+  Timer tm{ctx, stats != nullptr};
+  rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
+                   inputs_are_coeffs ? nullptr : dco, dle, ddi, dca, &tm);
+  if (rc) return rc;
+  if (stats) cudaEventRecord(e2, ctx->stream);
+  if (coeffs_out) {
+    const u64* csrc = inputs_are_coeffs ? din : dco;
+    for (u32 c = 0; c < ncols; c++)
+      if (coeffs_out[c])
+        CU(ctx, cudaMemcpyAsync(coeffs_out[c], csrc + (u64)c * n, n * 8, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  }
+  if (leaves_out)
+    CU(ctx, cudaMemcpyAsync(leaves_out, dle, (size_t)m * width * 8, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  if (digests_out && ndig)
+    CU(ctx, cudaMemcpyAsync(digests_out, ddi, ndig * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(cap_out, dca, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (stats) cudaEventRecord(e3, ctx->stream);
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    fill_stats(stats, tm, ctx->launches - l0);
+    cudaEventElapsedTime(&stats->h2d_ms, e0, e1);
+    cudaEventElapsedTime(&stats->d2h_ms, e2, e3);
+    cudaEventElapsedTime(&stats->total_ms, e0, e3);
+  }
+  return VPBS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+"""Host-side mirror of the plonky2 0.2.0 interface for the commitment path, over the C ABI.
+
+Names, argument meaning and failure behaviour follow upstream so the parity tests read like
+plonky2 call sites (the reference reaches them through prove()/build(),
+/root/reference/src/vtfhe/ivc_based_vpbs.rs:275,302,333,364):
+
+  [P2] plonky2_field/src/fft.rs            fft, ifft, FftRootTable (kept on the device here)
+  [P2] plonky2_field/src/polynomial/mod.rs PolynomialCoeffs::coset_fft / lde
+  [P2] plonky2/src/hash/merkle_tree.rs     MerkleTree::{new, get, prove}, MerkleCap
+  [P2] plonky2/src/fri/oracle.rs           PolynomialBatch::{from_values, from_coeffs,
+                                           get_lde_values}, SALT_SIZE
+
+Everything numeric is a numpy uint64 array (GoldilocksField is a transparent u64).  Where plonky2
+`assert!`s/panics, these raise (ValueError for argument errors, VpbsError for device errors).
+There is no CPU implementation behind any of it: every call goes to libvpbs_commit.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import VpbsError, VpbsStats, u64p, u64pp
+
+P = 0xFFFFFFFF00000001
+SALT_SIZE = 4
+COSET_SHIFT = 7
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(u64p)
+
+
+def _as_u64(x) -> np.ndarray:
+    a = np.asarray(x)
+    if a.dtype != np.uint64:
+        a = a.astype(np.uint64)
+    return np.ascontiguousarray(a)
+
+
+def log2_strict(n: int) -> int:
+    """[P2] plonky2_util::log2_strict — panics (here: ValueError) unless n is a power of two."""
+    if n <= 0 or n & (n - 1):
+        raise ValueError("Not a power of two: %d" % n)
+    return n.bit_length() - 1
+
+
+def reverse_bits(x: int, bits: int) -> int:
+    """[P2] plonky2_util::reverse_bits."""
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (x & 1)
+        x >>= 1
+    return r
+
+
+class Context:
+    """One vpbs_ctx: a device, a stream and the grow-only device arena reused across commits."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._L.vpbs_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise VpbsError(rc, (self._L.vpbs_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vpbs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def check(self, rc: int):
+        if rc == 0:
+            return
+        msg = (self._L.vpbs_last_error(self._h) or b"").decode()
+        if rc == _lib.VPBS_ERR_ARG:
+            raise ValueError(msg)
+        raise VpbsError(rc, msg)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def lib(self):
+        return self._L
+
+    def set_stream(self, cuda_stream: int):
+        self.check(self._L.vpbs_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self.check(self._L.vpbs_ctx_sync(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.vpbs_ctx_kernel_launches(self._h))
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ----------------------------------------------------------------------------- fft.rs
+def fft(coeffs, ctx: Optional[Context] = None) -> np.ndarray:
+    """[P2] fft(poly): values[i] = poly(w^i), natural order."""
+    ctx = ctx or default_context()
+    a = _as_u64(coeffs).copy()
+    ctx.check(ctx.lib.vpbs_fft(ctx.handle, _ptr(a), log2_strict(a.size)))
+    return a
+
+
+def ifft(values, ctx: Optional[Context] = None) -> np.ndarray:
+    """[P2] ifft(poly): coefficients of the interpolant over <w>."""
+    ctx = ctx or default_context()
+    a = _as_u64(values).copy()
+    ctx.check(ctx.lib.vpbs_ifft(ctx.handle, _ptr(a), log2_strict(a.size)))
+    return a
+
+
+def coset_fft(coeffs, shift: int = COSET_SHIFT, ctx: Optional[Context] = None) -> np.ndarray:
+    """[P2] PolynomialCoeffs::coset_fft(shift): values[i] = poly(shift * w^i)."""
+    ctx = ctx or default_context()
+    a = _as_u64(coeffs).copy()
+    ctx.check(ctx.lib.vpbs_coset_fft(ctx.handle, _ptr(a), log2_strict(a.size), int(shift) % 2**64))
+    return a
+
+
+def lde_values(polys, rate_bits: int, inputs_are_coeffs: bool = True,
+               ctx: Optional[Context] = None):
+    """[P2] PolynomialBatch::lde_values without blinding: (ncols, n << rate_bits), natural order.
+    Returns (coeffs, lde)."""
+    ctx = ctx or default_context()
+    a = _as_u64(polys)
+    ncols, n = a.shape
+    log_n = log2_strict(n)
+    colp = (u64p * ncols)(*[_ptr(a[c]) for c in range(ncols)])
+    coeffs = np.empty((ncols, n), np.uint64)
+    cop = (u64p * ncols)(*[_ptr(coeffs[c]) for c in range(ncols)])
+    out = np.empty((ncols, n << rate_bits), np.uint64)
+    ctx.check(ctx.lib.vpbs_lde_batch(ctx.handle, colp, ncols, log_n, rate_bits,
+                                     int(inputs_are_coeffs), cop, _ptr(out)))
+    return coeffs, out
+
+
+# ----------------------------------------------------------------------------- hashing
+def poseidon(states, ctx: Optional[Context] = None) -> np.ndarray:
+    """[P2] Poseidon::poseidon on a (count, 12) batch of states."""
+    ctx = ctx or default_context()
+    a = _as_u64(states).reshape(-1, 12).copy()
+    ctx.check(ctx.lib.vpbs_poseidon_permute(ctx.handle, _ptr(a), a.shape[0]))
+    return a
+
+
+def hash_or_noop(rows, ctx: Optional[Context] = None) -> np.ndarray:
+    """[P2] Hasher::hash_or_noop on every row of a (count, len) matrix -> (count, 4)."""
+    ctx = ctx or default_context()
+    a = _as_u64(rows)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    out = np.empty((a.shape[0], 4), np.uint64)
+    ctx.check(ctx.lib.vpbs_hash_or_noop_batch(ctx.handle, _ptr(a) if a.size else None, a.shape[0],
+                                              a.shape[1], _ptr(out)))
+    return out
+
+
+def two_to_one(left, right, ctx: Optional[Context] = None) -> np.ndarray:
+    """[P2] PoseidonHash::two_to_one on (count, 4) batches."""
+    ctx = ctx or default_context()
+    l, r = _as_u64(left).reshape(-1, 4), _as_u64(right).reshape(-1, 4)
+    if l.shape != r.shape:
+        raise ValueError("left/right shape mismatch")
+    out = np.empty_like(l)
+    ctx.check(ctx.lib.vpbs_two_to_one_batch(ctx.handle, _ptr(l), _ptr(r), l.shape[0], _ptr(out)))
+    return out
+
+
+# ----------------------------------------------------------------------------- merkle_tree.rs
+@dataclass
+class MerkleProof:
+    """[P2] hash/merkle_proofs.rs MerkleProof { siblings }."""
+    siblings: np.ndarray  # (num_layers, 4)
+
+
+class MerkleTree:
+    """[P2] hash/merkle_tree.rs MerkleTree { leaves, digests, cap }."""
+
+    def __init__(self, leaves: np.ndarray, digests: np.ndarray, cap: np.ndarray):
+        self.leaves = leaves    # (nleaves, leaf_len), row k = leaf k
+        self.digests = digests  # (2 * (nleaves - 2^cap_height), 4), plonky2 layout
+        self.cap = cap          # (2^cap_height, 4)  == MerkleCap.0
+
+    @classmethod
+    def new(cls, leaves, cap_height: int, ctx: Optional[Context] = None) -> "MerkleTree":
+        ctx = ctx or default_context()
+        a = _as_u64(leaves)
+        if a.ndim != 2:
+            raise ValueError("leaves must be a (nleaves, leaf_len) matrix")
+        nleaves, leaf_len = a.shape
+        lg = log2_strict(nleaves)
+        if cap_height > lg:
+            # same condition plonky2 asserts on in MerkleTree::new
+            raise ValueError("cap_height=%d should be at most log2(leaves.len())=%d"
+                             % (cap_height, lg))
+        ndig = 2 * (nleaves - (1 << cap_height))
+        digests = np.empty((ndig, 4), np.uint64)
+        cap = np.empty((1 << cap_height, 4), np.uint64)
+        ctx.check(ctx.lib.vpbs_merkle_new(ctx.handle, _ptr(a) if a.size else None, nleaves,
+                                          leaf_len, cap_height, _ptr(digests) if ndig else None,
+                                          _ptr(cap)))
+        return cls(a, digests, cap)
+
+    def get(self, i: int) -> np.ndarray:
+        return self.leaves[i]
+
+    def prove(self, leaf_index: int) -> MerkleProof:
+        """[P2] MerkleTree::prove — pure index arithmetic over `digests` (unchanged layout)."""
+        cap_height = log2_strict(self.cap.shape[0])
+        num_layers = log2_strict(self.leaves.shape[0]) - cap_height
+        if leaf_index >> (cap_height + num_layers):
+            raise ValueError("leaf_index out of range")
+        tree_index = leaf_index >> num_layers
+        tree_len = self.digests.shape[0] >> cap_height
+        tree = self.digests[tree_len * tree_index: tree_len * (tree_index + 1)]
+        pair_index = leaf_index & ((1 << num_layers) - 1)
+        sibs = np.empty((num_layers, 4), np.uint64)
+        for i in range(num_layers):
+            parity = pair_index & 1
+            pair_index >>= 1
+            siblings_index = (pair_index << (i + 1)) + (1 << i) - 1
+            sibs[i] = tree[2 * siblings_index + (1 - parity)]
+        return MerkleProof(sibs)
+
+
+def verify_merkle_proof_to_cap(leaf, leaf_index: int, cap: np.ndarray, proof: MerkleProof,
+                               ctx: Optional[Context] = None) -> bool:
+    """[P2] hash/merkle_proofs.rs verify_merkle_proof_to_cap (hashing done on the device)."""
+    cur = hash_or_noop(np.asarray(leaf, dtype=np.uint64).reshape(1, -1), ctx)[0]
+    idx = leaf_index
+    for sib in proof.siblings:
+        cur = (two_to_one(sib, cur, ctx) if idx & 1 else two_to_one(cur, sib, ctx))[0]
+        idx >>= 1
+    return bool(np.array_equal(cur, cap[idx]))
+
+
+# ----------------------------------------------------------------------------- fri/oracle.rs
+class PolynomialBatch:
+    """[P2] fri/oracle.rs PolynomialBatch { polynomials, merkle_tree, degree_log, rate_bits,
+    blinding }."""
+
+    def __init__(self, polynomials, merkle_tree, degree_log, rate_bits, blinding, stats=None):
+        self.polynomials = polynomials  # (ncols, n) coefficients
+        self.merkle_tree = merkle_tree
+        self.degree_log = degree_log
+        self.rate_bits = rate_bits
+        self.blinding = blinding
+        self.stats = stats              # per-phase timings (plonky2's TimingTree scopes)
+
+    @classmethod
+    def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
+                    fft_root_table=None, *, ctx: Optional[Context] = None, salt=None,
+                    rng: Optional[np.random.Generator] = None) -> "PolynomialBatch":
+        """values: (ncols, n) evaluations over <w_n>.  `timing` / `fft_root_table` are accepted for
+        signature parity (timings come back in .stats; root tables are cached on the device)."""
+        return cls._commit(values, rate_bits, blinding, cap_height, False, ctx, salt, rng)
+
+    @classmethod
+    def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
+                    fft_root_table=None, *, ctx: Optional[Context] = None, salt=None,
+                    rng: Optional[np.random.Generator] = None) -> "PolynomialBatch":
+        return cls._commit(polynomials, rate_bits, blinding, cap_height, True, ctx, salt, rng)
+
+    @classmethod
+    def _commit(cls, cols, rate_bits, blinding, cap_height, are_coeffs, ctx, salt, rng):
+        ctx = ctx or default_context()
+        a = _as_u64(cols)
+        if a.ndim != 2 or a.shape[0] == 0:
+            raise ValueError("need a non-empty (ncols, n) matrix")
+        ncols, n = a.shape
+        log_n = log2_strict(n)
+        m = n << rate_bits
+        if cap_height > log_n + rate_bits:
+            raise ValueError("cap_height=%d should be at most log2(leaves.len())=%d"
+                             % (cap_height, log_n + rate_bits))
+        salt_arr, saltp = None, None
+        if blinding:
+            # [P2] lde_values: SALT_SIZE extra columns of F::rand_vec(m); RNG stays on the host
+            if salt is None:
+                rng = rng or np.random.default_rng()
+                salt = rng.integers(0, P, size=(SALT_SIZE, m), dtype=np.uint64)
+            salt_arr = _as_u64(salt)
+            if salt_arr.shape != (SALT_SIZE, m):
+                raise ValueError("salt must be (%d, %d)" % (SALT_SIZE, m))
+            saltp = (u64p * SALT_SIZE)(*[_ptr(salt_arr[s]) for s in range(SALT_SIZE)])
+        width = ncols + (SALT_SIZE if blinding else 0)
+        colp = (u64p * ncols)(*[_ptr(a[c]) for c in range(ncols)])
+        coeffs = np.empty((ncols, n), np.uint64)
+        cop = (u64p * ncols)(*[_ptr(coeffs[c]) for c in range(ncols)])
+        leaves = np.empty((m, width), np.uint64)
+        ndig = 2 * (m - (1 << cap_height))
+        digests = np.empty((ndig, 4), np.uint64)
+        cap = np.empty((1 << cap_height, 4), np.uint64)
+        st = VpbsStats()
+        ctx.check(ctx.lib.vpbs_commit(ctx.handle, colp, ncols, log_n, rate_bits, cap_height,
+                                      int(are_coeffs), saltp, cop, _ptr(leaves),
+                                      _ptr(digests) if ndig else None, _ptr(cap),
+                                      ctypes.byref(st)))
+        if are_coeffs:
+            coeffs = a % np.uint64(P) if (a >= np.uint64(P)).any() else a
+        return cls(coeffs, MerkleTree(leaves, digests, cap), log_n, rate_bits, blinding,
+                   st.as_dict())
+
+    def get_lde_values(self, index: int, step: int = 1) -> np.ndarray:
+        """[P2] PolynomialBatch::get_lde_values: leaf reverse_bits(index * step) minus the salt."""
+        index = index * step
+        index = reverse_bits(index, self.degree_log + self.rate_bits)
+        row = self.merkle_tree.get(index)
+        return row[: row.shape[0] - (SALT_SIZE if self.blinding else 0)]
+
+
+# ----------------------------------------------------------------------------- device-resident
+def commit_device(ctx: Context, d_cols: int, ncols: int, log_n: int, rate_bits: int,
+                  cap_height: int, inputs_are_coeffs: bool, d_coeffs: int, d_leaves: int,
+                  d_digests: int, d_cap: int, d_salt: int = 0, want_stats: bool = False):
+    """vpbs_commit_dev on raw device pointers (e.g. torch tensor .data_ptr())."""
+    st = VpbsStats() if want_stats else None
+    ctx.check(ctx.lib.vpbs_commit_dev(ctx.handle, d_cols, ncols, log_n, rate_bits, cap_height,
+                                      int(inputs_are_coeffs), d_salt or None, d_coeffs or None,
+                                      d_leaves, d_digests or None, d_cap,
+                                      ctypes.byref(st) if st is not None else None))
+    return st.as_dict() if st is not None else None
+
+
+def commit_shard_device(ctx: Context, d_cols: int, ncols: int, log_n: int, rate_bits: int,
+                        cap_height: int, inputs_are_coeffs: bool, first_leaf: int,
+                        nleaves_shard: int, d_coeffs: int, d_leaves: int, d_digests: int,
+                        d_roots: int, want_stats: bool = False):
+    """vpbs_commit_shard_dev: the row range [first_leaf, first_leaf + nleaves_shard) of a commit."""
+    st = VpbsStats() if want_stats else None
+    ctx.check(ctx.lib.vpbs_commit_shard_dev(ctx.handle, d_cols, ncols, log_n, rate_bits, cap_height,
+                                            int(inputs_are_coeffs), first_leaf, nleaves_shard,
+                                            d_coeffs or None, d_leaves, d_digests or None, d_roots,
+                                            ctypes.byref(st) if st is not None else None))
+    return st.as_dict() if st is not None else None
+
+
+# ----------------------------------------------------------------------------- synthetic inputs
+def synthetic_columns(ncols: int, n: int, seed: int = 0x5EED0000, canonical: bool = True) -> np.ndarray:
+    """SURVEY.md §8(d) workload: column c, row i = splitmix64(seed + c, counter i) (mod p)."""
+    i = np.arange(1, n + 1, dtype=np.uint64)
+    out = np.empty((ncols, n), np.uint64)
+    with np.errstate(over="ignore"):
+        for c in range(ncols):
+            z = np.uint64((seed + c) % 2**64) + i * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[c] = z
+    if canonical:
+        out = np.where(out >= np.uint64(P), out - np.uint64(P), out)
+    return out
