@@ -41,15 +41,6 @@ __device__ __forceinline__ u64 sbox7(u64 x) {
   return gl::mul_lazy(x3, x4);
 }
 
-// acc + x * c as one IMAD.WIDE.U32 (opaque to the optimiser, which otherwise rewrites the small
-// constant multiplies into shift/add chains that cost more issue slots).
-template <u32 C>
-__device__ __forceinline__ u64 mac32(u64 acc, u32 x) {
-  u64 r;
-  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(x), "n"(C), "l"(acc));
-  return r;
-}
-
 // value = lo + 2^32 * hi with lo, hi < 2^43  ->  arbitrary-u64 representative mod p.
 //   hi = hh * 2^32 + hl:  value = lo + hh * (2^32 - 1) + hl * 2^32   (2^64 = 2^32 - 1 mod p)
 __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
@@ -71,41 +62,58 @@ __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
   return ((u64)r1 << 32) | r0;
 }
 
+// ---- MDS layer on the FP64 pipe ---------------------------------------------------------------
+// On B200 a 64-bit integer multiply-accumulate costs three issue slots (IMAD.WIDE.U32 runs at half
+// rate on the fmaheavy pipe and ptxas splits its 64-bit addend into IADD3 + IADD3.X), while DFMA is
+// one full-rate slot on its own pipe with a 53-bit exact integer range (measured:
+// tools/microbench.cu, profiles/).  The MDS constants are <= 41 and each state word is split in
+// 32-bit halves, so every partial sum RC + sum_i c_i * half_i stays below 2^42: exact in doubles.
+//   * half -> double: bit pattern {half, 0x43300000} is 2^52 + half; subtract 2^52.
+//   * the accumulator starts at 2^52 + RC_half, so the final mantissa *is* the integer sum:
+//     no conversion back, just mask off the exponent bits.
+__device__ __forceinline__ double half_to_f64(u32 x) {
+  return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+}
+// Round constants pre-split for the accumulators: RCD[2*(12*r+i)] = 2^52 + lo32(RC),
+// RCD[2*(12*r+i)+1] = 2^52 + hi32(RC) (exact doubles; row 30 is the all-zero "no next round").
+__constant__ double RCD[2 * (ROUNDS + 1) * WIDTH] = {
+#include "poseidon_rcd.inc"
+};
+
 template <int R, int I>
 struct MdsRow {
   static constexpr u32 CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  __device__ __forceinline__ static void run(const u32 (&lo)[WIDTH], const u32 (&hi)[WIDTH],
-                                             u64& acc_lo, u64& acc_hi) {
-    acc_lo = mac32<CIRC[I]>(acc_lo, lo[(I + R) % WIDTH]);
-    acc_hi = mac32<CIRC[I]>(acc_hi, hi[(I + R) % WIDTH]);
-    if constexpr (I + 1 < WIDTH) MdsRow<R, I + 1>::run(lo, hi, acc_lo, acc_hi);
+  // MDS_MATRIX_DIAG = [8, 0, ..., 0] only touches (row 0, lane 0): fold it into that coefficient.
+  static constexpr double COEF = (double)(CIRC[I] + ((R == 0 && I == 0) ? 8u : 0u));
+  __device__ __forceinline__ static void run(const double (&dl)[WIDTH], const double (&dh)[WIDTH],
+                                             double& acc_lo, double& acc_hi) {
+    acc_lo = fma(dl[(I + R) % WIDTH], COEF, acc_lo);
+    acc_hi = fma(dh[(I + R) % WIDTH], COEF, acc_hi);
+    if constexpr (I + 1 < WIDTH) MdsRow<R, I + 1>::run(dl, dh, acc_lo, acc_hi);
   }
 };
 
 template <int R>
-__device__ __forceinline__ void mds_rows(u64 (&s)[WIDTH], const u32 (&lo)[WIDTH],
-                                         const u32 (&hi)[WIDTH], const u64* __restrict__ rc_next) {
-  const u64 c = rc_next[R];
-  u64 acc_lo = (u32)c, acc_hi = c >> 32;
-  MdsRow<R, 0>::run(lo, hi, acc_lo, acc_hi);
-  if constexpr (R == 0) {  // MDS_MATRIX_DIAG = [8, 0, ..., 0]
-    acc_lo = mac32<8>(acc_lo, lo[0]);
-    acc_hi = mac32<8>(acc_hi, hi[0]);
-  }
-  s[R] = reduce96(acc_lo, acc_hi);
-  if constexpr (R + 1 < WIDTH) mds_rows<R + 1>(s, lo, hi, rc_next);
+__device__ __forceinline__ void mds_rows(u64 (&s)[WIDTH], const double (&dl)[WIDTH],
+                                         const double (&dh)[WIDTH], const double* __restrict__ rcd) {
+  double acc_lo = rcd[2 * R], acc_hi = rcd[2 * R + 1];
+  MdsRow<R, 0>::run(dl, dh, acc_lo, acc_hi);
+  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
+  s[R] = reduce96((u64)__double_as_longlong(acc_lo) & MANT, (u64)__double_as_longlong(acc_hi) & MANT);
+  if constexpr (R + 1 < WIDTH) mds_rows<R + 1>(s, dl, dh, rcd);
 }
 
 // MDS layer fused with the following constant layer:
 //   s'_r = RC_next[r] + sum_i CIRC[i] * s_{(i+r) mod 12} + DIAG[r] * s_r
-__device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], const u64* __restrict__ rc_next) {
-  u32 lo[WIDTH], hi[WIDTH];
+// `next_round` indexes the constants added after the MDS (ROUNDS = none).
+__device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
+  double dl[WIDTH], dh[WIDTH];
 #pragma unroll
   for (int i = 0; i < WIDTH; i++) {
-    lo[i] = (u32)s[i];
-    hi[i] = (u32)(s[i] >> 32);
+    dl[i] = half_to_f64((u32)s[i]);
+    dh[i] = half_to_f64((u32)(s[i] >> 32));
   }
-  mds_rows<0>(s, lo, hi, rc_next);
+  mds_rows<0>(s, dl, dh, RCD + 2 * WIDTH * next_round);
 }
 
 // In-place permutation; input words arbitrary u64, output words arbitrary u64 (lazy).
@@ -119,13 +127,13 @@ __device__ __forceinline__ void permute_lazy(u64 (&s)[WIDTH]) {
     for (int k = 0; k < FULL_ROUNDS_HALF; k++, r++) {
 #pragma unroll
       for (int i = 0; i < WIDTH; i++) s[i] = sbox7(s[i]);
-      mds_add_rc(s, RC + (r + 1) * WIDTH);
+      mds_add_rc(s, r + 1);
     }
     if (half == 0) {
 #pragma unroll 1
       for (int k = 0; k < PARTIAL_ROUNDS; k++, r++) {
         s[0] = sbox7(s[0]);
-        mds_add_rc(s, RC + (r + 1) * WIDTH);
+        mds_add_rc(s, r + 1);
       }
     }
   }

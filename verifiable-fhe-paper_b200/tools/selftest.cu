@@ -29,7 +29,7 @@ __global__ void k_mds(const u64* a, u64* out, int n) {  // n states of 12; rc_ne
   if (i >= n) return;
   u64 s[12];
   for (int k = 0; k < 12; k++) s[k] = a[i * 12 + k];
-  poseidon::mds_add_rc(s, poseidon::RC + 30 * 12);
+  poseidon::mds_add_rc(s, 30);
   for (int k = 0; k < 12; k++) out[i * 12 + k] = s[k];
 }
 
