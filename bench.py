@@ -1,0 +1,413 @@
+#!/usr/bin/env python3
+"""bench.py — LDE + Poseidon-Merkle commit throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one PolynomialBatch::from_values commit of BASELINE.json configs[1]
+(2^16 rows x 128 Goldilocks columns, rate_bits = 3, Poseidon cap_height = 4) on synthetic values.
+N > 1: every rank commits its own independent batch (one proof per GPU, no data-path collective —
+north_star "independent PBS proofs shard one per GPU"), so scaling is weak and
+value = N * K * 2^16 trace rows / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel = Poseidon
+leaf hashing, integer-issue bound), roofline_hbm (the NTT/LDE kernels against HBM), cpu_baseline
+(the C restatement of plonky2's CPU path, oracle/, timed on this box's host cores), e2e (host
+buffers through the C ABI with H2D/D2H in the timed region), step_standin (the three commits of
+one N=1024 IVC step), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N, NCOLS, RATE_BITS, CAP_HEIGHT = 16, 128, 3, 4
+METRIC = "LDE+Merkle commit rows/s (2^16-row x 128-col Goldilocks batch, rate_bits=3, cap_height=4)"
+UNIT = "trace rows/s"
+# integer work per Poseidon permutation in 32x32->64 multiply-accumulates
+# (1,077 full modmuls x 4 + 2,304 + 44 small MACs), and the IMAD.WIDE issue rate it is held against.
+IMAD_PER_PERMUTATION = 6700
+IMAD_WIDE_LANES_PER_CLK_PER_SM = 64
+SM_COUNT = 148
+
+
+def algorithmic_bytes(ncols, n, r, h, from_values=True):
+    m = n << r
+    b = 8 * ncols * n + 8 * ncols * m + 64 * (m - (1 << h)) + 32 * (1 << h)
+    return b + (8 * ncols * n if from_values else 0)
+
+
+def permutations(ncols, n, r, h):
+    m = n << r
+    return (m * ((ncols + 7) // 8) if ncols > 4 else 0) + (m - (1 << h))
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clocks, reasons, power, mx = [], set(), [], None
+        for r in self.rows:
+            try:
+                clocks.append(float(r[1])); mx = float(r[2]); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load": samples in the upper half of the observed power range
+        if power:
+            thr = (max(power) + min(power)) / 2
+            loaded = [c for c, p in zip(clocks, power) if p >= thr] or clocks
+        else:
+            loaded = clocks
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": mx,
+                "power_w_max": max(power) if power else None, "samples": len(clocks),
+                "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores.
+    plonky2 itself cannot be built here (no Rust toolchain; crates not vendored), so this is the C
+    restatement in oracle/ ("port"), with all host threads."""
+    if rank != 0:
+        return
+    import numpy as np
+    import vfhe_b200 as V
+    from oracle import binding as B
+    B.build()
+    cores = os.cpu_count() or 1
+    B.set_threads(cores)
+    n = 1 << LOG_N
+    cols = V.synthetic_columns(NCOLS, n)
+    t0 = time.perf_counter()
+    B.commit(cols, RATE_BITS, CAP_HEIGHT)          # warm-up, also sizes the sample
+    t_est = time.perf_counter() - t0
+    budget = 150.0
+    timed = max(1, min(args.steps, int(budget / max(t_est, 1e-3))))
+    extra_warm = max(0, min(args.warmup - 1, int(30.0 / max(t_est, 1e-3))))
+    for _ in range(extra_warm):
+        B.commit(cols, RATE_BITS, CAP_HEIGHT)
+    t0 = time.perf_counter()
+    for _ in range(timed):
+        B.commit(cols, RATE_BITS, CAP_HEIGHT)
+    dt = (time.perf_counter() - t0) / timed
+    value = n / dt
+    sample = ("%d of %d steps timed (bounded to ~%ds); each step = one full 2^16x128 commit by the C "
+              "restatement of plonky2 0.2.0's CPU path (oracle/liboracle.so, OpenMP, %d threads)"
+              % (timed, args.steps, int(budget), cores))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(world):
+    return {"workload": "configs[1]: standalone commit microbench, 2^16 rows x 128 Goldilocks columns, "
+                        "rate_bits=3, Poseidon cap_height=4, from values, blinding off",
+            "log_n": LOG_N, "ncols": NCOLS, "rate_bits": RATE_BITS, "cap_height": CAP_HEIGHT,
+            "parallelism": "one independent commit per GPU x%d, no collective" % world,
+            "l2": "per-step working set ~0.7 GB (64 MiB in, 512 MiB leaves, 34 MB digests) exceeds "
+                  "the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import vfhe_b200 as V
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the commit path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    V.build.build()
+    ctx = V.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    n, m = 1 << LOG_N, (1 << LOG_N) << RATE_BITS
+    ncap = 1 << CAP_HEIGHT
+    host_cols = V.synthetic_columns(NCOLS, n, seed=0x5EED0000 + 1000 * rank)
+    dev = torch.device("cuda", local_rank)
+    d_cols = torch.from_numpy(host_cols.view(np.int64)).to(dev)
+    d_coeffs = torch.empty((NCOLS, n), dtype=torch.int64, device=dev)
+    d_leaves = torch.empty((m, NCOLS), dtype=torch.int64, device=dev)
+    d_digests = torch.empty((2 * (m - ncap), 4), dtype=torch.int64, device=dev)
+    d_cap = torch.empty((ncap, 4), dtype=torch.int64, device=dev)
+
+    def step(stats=True):
+        return V.commit_device(ctx, d_cols.data_ptr(), NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, False,
+                               d_coeffs.data_ptr(), d_leaves.data_ptr(), d_digests.data_ptr(),
+                               d_cap.data_ptr(), want_stats=stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_phase = []
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        per_phase.append(step())
+    ev1.record()
+    barrier()
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = ctx.kernel_launches - launches0
+    ms_per_step = elapsed_ms / args.steps
+    value = world * args.steps * n / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the host C ABI: pinned host buffers, H2D + D2H inside the timed region
+    lib = ctx.lib
+
+    def pinned(shape):
+        nbytes = int(np.prod(shape)) * 8
+        p = lib.vpbs_host_alloc(nbytes)
+        if not p:
+            raise SystemExit("vpbs_host_alloc failed")
+        buf = (ctypes.c_uint64 * (nbytes // 8)).from_address(p)
+        return np.ctypeslib.as_array(buf).reshape(shape), p
+
+    h_cols, p0 = pinned((NCOLS, n))
+    h_cols[:] = host_cols
+    h_coeffs, p1 = pinned((NCOLS, n))
+    h_leaves, p2 = pinned((m, NCOLS))
+    h_digests, p3 = pinned((2 * (m - ncap), 4))
+    h_cap, p4 = pinned((ncap, 4))
+    u64p = V._lib.u64p
+    colp = (u64p * NCOLS)(*[h_cols[c].ctypes.data_as(u64p) for c in range(NCOLS)])
+    cop = (u64p * NCOLS)(*[h_coeffs[c].ctypes.data_as(u64p) for c in range(NCOLS)])
+    e2e_stats = V.VpbsStats()
+
+    def e2e_step():
+        ctx.check(lib.vpbs_commit(ctx.handle, colp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None, cop,
+                                  h_leaves.ctypes.data_as(u64p), h_digests.ctypes.data_as(u64p),
+                                  h_cap.ctypes.data_as(u64p), ctypes.byref(e2e_stats)))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * args.e2e_steps * n / e2e_s
+    h2d_bytes = 8 * NCOLS * n
+    d2h_bytes = 8 * NCOLS * n + 8 * m * NCOLS + 32 * 2 * (m - ncap) + 32 * ncap
+    cap_matches = bool(np.array_equal(h_cap.view(np.int64), d_cap.cpu().numpy()))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the N=1024 step stand-in (BASELINE.json configs[2]): wires / Z / quotient commits
+    step_standin = None
+    if rank == 0:
+        tot = []
+        bufs = {}
+        for (c, coeffs) in ((135, False), (20, False), (16, True)):
+            bufs[c] = (torch.from_numpy(V.synthetic_columns(c, n, 0x5EED0000 + c).view(np.int64)).to(dev),
+                       torch.empty((c, n), dtype=torch.int64, device=dev),
+                       torch.empty((m, c), dtype=torch.int64, device=dev))
+        for it in range(4):
+            t = 0.0
+            for (c, coeffs) in ((135, False), (20, False), (16, True)):
+                a, b, l = bufs[c]
+                st = V.commit_device(ctx, a.data_ptr(), c, LOG_N, RATE_BITS, CAP_HEIGHT, coeffs,
+                                     b.data_ptr(), l.data_ptr(), d_digests.data_ptr(),
+                                     d_cap.data_ptr(), want_stats=True)
+                t += st["total_ms"]
+            tot.append(t)
+        step_standin = {"what": "three commits of one N=1024 IVC step (135 + 20 value columns, 16 "
+                                "coefficient columns, 2^16 rows), kernels only, inputs in HBM",
+                        "ms": min(tot[1:]), "permutations": sum(permutations(c, n, RATE_BITS, CAP_HEIGHT)
+                                                                 for c in (135, 20, 16))}
+        del bufs
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic = {}
+    peaks = measured_peaks()
+    hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    leaf_ms = statistics.mean(s["leaf_hash_ms"] for s in per_phase)
+    merkle_ms = statistics.mean(s["merkle_ms"] for s in per_phase)
+    ifft_ms = statistics.mean(s["ifft_ms"] for s in per_phase)
+    fft_ms = statistics.mean(s["fft_ms"] for s in per_phase)
+    sm_mhz = (clocks or {}).get("sm_mhz") or (peaks or {}).get("sm_max_mhz", 1965.0)
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    leaf_perms = m * ((NCOLS + 7) // 8)
+    int_peak = SM_COUNT * IMAD_WIDE_LANES_PER_CLK_PER_SM * sm_max * 1e6 / 1e9  # G IMAD.WIDE/s
+    int_ach = leaf_perms * IMAD_PER_PERMUTATION / (leaf_ms * 1e-3) / 1e9
+    leaf_bytes = 8 * m * NCOLS + 32 * m
+    lde_bytes = 8 * NCOLS * n * 2 + 8 * NCOLS * m  # values in, coeffs out, leaves out
+    roofline = {
+        "kernel": "merkle::hash_leaves (Poseidon sponge over 2^19 rows x 128, one leaf per thread)",
+        "bound": "int", "achieved": int_ach, "peak": int_peak, "unit": "G IMAD.WIDE.U32-equivalent/s",
+        "frac": int_ach / int_peak,
+        "how": "algorithmic 32x32->64 MACs (SURVEY.md §8(d): %d per permutation x %d permutations per "
+               "launch) / mean launch duration from CUDA events on the launching stream; peak = 148 SM"
+               " x 64 IMAD.WIDE lanes/clk (measured, profiles/microbench_r1.jsonl) x sm_max_mhz"
+               % (IMAD_PER_PERMUTATION, leaf_perms),
+        "launch_ms": leaf_ms, "permutations_per_launch": leaf_perms,
+        "hbm_frac": leaf_bytes / (leaf_ms * 1e-3) / 1e9 / hbm_peak,
+        "traffic": traffic.get("hash_leaves_dram_bytes"),
+    }
+    roofline_hbm = {
+        "kernels": "ntt::pass_strided / ntt::pass_final (IFFT + coset LDE + fused transpose)",
+        "bound": "hbm", "achieved": lde_bytes / ((ifft_ms + fft_ms) * 1e-3) / 1e9, "peak": hbm_peak,
+        "unit": "GB/s", "frac": lde_bytes / ((ifft_ms + fft_ms) * 1e-3) / 1e9 / hbm_peak,
+        "peak_source": hbm_src, "algorithmic_bytes": lde_bytes, "ms": ifft_ms + fft_ms,
+        "traffic": traffic.get("ntt_dram_bytes"),
+    }
+    whole = {"algorithmic_bytes": algorithmic_bytes(NCOLS, n, RATE_BITS, CAP_HEIGHT),
+             "permutations": permutations(NCOLS, n, RATE_BITS, CAP_HEIGHT),
+             "hbm_frac": algorithmic_bytes(NCOLS, n, RATE_BITS, CAP_HEIGHT) / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+             "int_frac": permutations(NCOLS, n, RATE_BITS, CAP_HEIGHT) * IMAD_PER_PERMUTATION
+             / (ms_per_step * 1e-3) / 1e9 / int_peak}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle, all host threads, one full commit
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as B
+        B.build()
+        cores = os.cpu_count() or 1
+        B.set_threads(cores)
+        t0 = time.perf_counter()
+        ref = B.commit(host_cols, RATE_BITS, CAP_HEIGHT)
+        dt = time.perf_counter() - t0
+        same = bool(np.array_equal(ref["cap"].view(np.int64), d_cap_check(ctx, V, host_cols, np)))
+        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "one full 2^16x128 commit (%.1f s) by the C restatement of plonky2 "
+                                  "0.2.0's CPU path (oracle/liboracle.so, OpenMP); plonky2 itself "
+                                  "cannot be built here (no Rust toolchain)" % dt,
+                        "cap_matches_gpu": same}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(world),
+        "lde_rows_per_s": value * (1 << RATE_BITS),
+        "phase_ms": {"ifft": ifft_ms, "fft_transpose": fft_ms, "merkle": merkle_ms,
+                     "leaf_hash": leaf_ms},
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_whole_commit": whole,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.e2e_steps * 1e3,
+                "steps": args.e2e_steps, "api": "vpbs_commit (host C ABI, pinned buffers)",
+                "phase_ms_last": e2e_stats.as_dict(), "cap_matches_device_path": cap_matches},
+        "step_standin": step_standin,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    for p in (p0, p1, p2, p3, p4):
+        lib.vpbs_host_free(p)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def d_cap_check(ctx, V, host_cols, np):
+    """cap of the same batch through the host API (for the cpu_baseline cross-check)."""
+    b = V.PolynomialBatch.from_values(host_cols, RATE_BITS, False, CAP_HEIGHT, ctx=ctx)
+    return b.merkle_tree.cap.view(np.int64)
+
+
+if __name__ == "__main__":
+    main()

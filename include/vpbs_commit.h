@@ -54,7 +54,8 @@ typedef struct vpbs_stats {
   float h2d_ms;    /* host -> device copies of the inputs (0 for *_dev calls)      */
   float ifft_ms;   /* "IFFT"                                                       */
   float fft_ms;    /* "FFT + blinding" + "transpose LDEs"                          */
-  float merkle_ms; /* "build Merkle tree"                                          */
+  float merkle_ms; /* "build Merkle tree" (leaf hashing + all levels)              */
+  float leaf_hash_ms; /* the leaf-hashing kernel alone (part of merkle_ms)        */
   float d2h_ms;    /* device -> host copies of the outputs (0 for *_dev calls)     */
   float total_ms;  /* first event to last event of the call                        */
   uint64_t kernel_launches; /* kernels of this library launched by the call        */

@@ -27,11 +27,13 @@ static inline uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
 static inline uint64_t reduce128(u128 x) {
   uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
   uint64_t hi_hi = hi >> 32, hi_lo = hi & EPS;
-  uint64_t t0 = lo - hi_hi;
-  if (lo < hi_hi) t0 -= EPS; /* borrow: add p */
+  uint64_t t0, r;
+  /* branch-free: the carry/borrow is taken ~half the time, so branches would mispredict */
+  uint64_t borrow = __builtin_sub_overflow(lo, hi_hi, &t0);
+  t0 -= EPS & (0 - borrow); /* borrow: add p */
   uint64_t t1 = hi_lo * EPS;
-  uint64_t r = t0 + t1;
-  if (r < t1) r += EPS; /* carry: subtract p */
+  uint64_t carry = __builtin_add_overflow(t0, t1, &r);
+  r += EPS & (0 - carry); /* carry: subtract p */
   return r;             /* < 2^64, not necessarily canonical */
 }
 static inline uint64_t add_(uint64_t a, uint64_t b) { /* a,b canonical */
@@ -184,7 +186,6 @@ void orc_lde(const uint64_t* coeffs, unsigned log_n, unsigned rate_bits, uint64_
  * of F::rand() from ChaCha8Rng::seed_from_u64(0) (rand 0.8 / rand_chacha 0.3).  SURVEY.md App. D.
  * The three plonky2 known-answer vectors in tests/golden/poseidon_kat.json check the result.
  * ---------------------------------------------------------------------------------------- */
-static const uint64_t MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 static const uint64_t MDS_DIAG[12] = {8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 static uint64_t RC[360];
 static int rc_ready = 0;
@@ -249,32 +250,49 @@ void orc_poseidon_round_constants(uint64_t out[360]) {
   memcpy(out, RC, sizeof RC);
 }
 
+/* Internally the state words are arbitrary u64 representatives (as upstream's GoldilocksField);
+ * they are canonicalised when the permutation returns. */
+static inline uint64_t mul_lazy(uint64_t a, uint64_t b) { return reduce128((u128)a * b); }
 static inline uint64_t sbox7(uint64_t x) {
-  uint64_t x2 = mul_(x, x), x4 = mul_(x2, x2), x3 = mul_(x, x2);
-  return mul_(x3, x4);
+  uint64_t x2 = mul_lazy(x, x), x4 = mul_lazy(x2, x2), x3 = mul_lazy(x, x2);
+  return mul_lazy(x3, x4);
 }
-/* [P2] Poseidon::mds_layer / mds_row_shf: out[r] = sum_i state[(i+r)%12]*CIRC[i] + state[r]*DIAG[r] */
-static inline void mds_layer(uint64_t s[12]) {
-  uint64_t o[12];
-  for (int r = 0; r < 12; r++) {
-    u128 acc = 0;
-    for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * MDS_CIRC[i];
-    acc += (u128)s[r] * MDS_DIAG[r];
-    o[r] = canon(reduce128(acc));
+/* [P2] Poseidon::mds_layer / mds_row_shf: out[r] = sum_i state[(i+r)%12]*CIRC[i] + state[r]*DIAG[r].
+ * Computed on the 32-bit halves of each word (sums stay below 2^42), like upstream's
+ * mds_row_shf does with u128 accumulators; `rc` = the next round's constants (or zeros). */
+static inline void mds_layer_add_rc(uint64_t s[12], const uint64_t* rc) {
+  static const uint32_t C32[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  uint32_t lo[24], hi[24];
+  uint64_t al[12], ah[12];
+  for (int i = 0; i < 12; i++) {
+    lo[i] = lo[i + 12] = (uint32_t)s[i];
+    hi[i] = hi[i + 12] = (uint32_t)(s[i] >> 32);
+    al[i] = ah[i] = 0;
   }
-  memcpy(s, o, sizeof o);
+  for (int i = 0; i < 12; i++) /* 32x32->64 products: vectorises to vpmuludq */
+    for (int r = 0; r < 12; r++) {
+      al[r] += (uint64_t)lo[i + r] * C32[i];
+      ah[r] += (uint64_t)hi[i + r] * C32[i];
+    }
+  al[0] += (uint64_t)lo[0] * (uint32_t)MDS_DIAG[0];
+  ah[0] += (uint64_t)hi[0] * (uint32_t)MDS_DIAG[0];
+  for (int r = 0; r < 12; r++) {
+    u128 v = (u128)al[r] + ((u128)ah[r] << 32) + rc[r]; /* value = al + 2^32 * ah (+ rc) */
+    s[r] = reduce128(v);
+  }
 }
+static const uint64_t ZERO12[12] = {0};
 static void poseidon_(uint64_t s[12]) {
-  int rc = 0;
+  for (int i = 0; i < 12; i++) s[i] = add_(canon(s[i]), RC[i]);
   for (int r = 0; r < 30; r++) {
-    for (int i = 0; i < 12; i++) s[i] = add_(s[i], RC[rc++]);
     if (r < 4 || r >= 26) {
       for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
     } else {
       s[0] = sbox7(s[0]);
     }
-    mds_layer(s);
+    mds_layer_add_rc(s, r < 29 ? RC + 12 * (r + 1) : ZERO12);
   }
+  for (int i = 0; i < 12; i++) s[i] = canon(s[i]);
 }
 void orc_poseidon(uint64_t state[12]) {
   ensure_rc();

@@ -19,6 +19,7 @@ u64pp = ctypes.POINTER(u64p)
 class VpbsStats(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_float), ("ifft_ms", ctypes.c_float),
                 ("fft_ms", ctypes.c_float), ("merkle_ms", ctypes.c_float),
+                ("leaf_hash_ms", ctypes.c_float),
                 ("d2h_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("kernel_launches", ctypes.c_uint64)]
 

@@ -41,13 +41,8 @@ __device__ __forceinline__ void hash_row(const u64* __restrict__ row, u32 width,
     store_hash(out, s);
     return;
   }
-  u32 off = 0;
-  for (; off + poseidon::RATE <= width; off += poseidon::RATE) {
-#pragma unroll
-    for (int i = 0; i < poseidon::RATE; i++) s[i] = __ldg(row + off + i);
-    poseidon::permute_lazy(s);
-  }
-  if (off < width) {  // short last chunk overwrites only the first lanes
+  // one permutation call site (code size); a short last chunk overwrites only the first lanes
+  for (u32 off = 0; off < width; off += poseidon::RATE) {
 #pragma unroll
     for (int i = 0; i < poseidon::RATE; i++)
       if (off + i < width) s[i] = __ldg(row + off + i);

@@ -48,7 +48,7 @@ struct vpbs_ctx {
   std::map<std::pair<unsigned, std::pair<unsigned, u64>>, u64*> coset_tables;  // (log_n,(r,shift))
   // grow-only arena
   std::map<std::string, Buf> arena;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};
 };
 
 namespace {
@@ -210,7 +210,7 @@ int log2_strict(u64 n) {
 // MerkleTree::new over device leaves.  nleaves leaves of `width`, split into `nsub` subtrees whose
 // roots go to d_roots; digests in plonky2 layout per subtree.
 int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, unsigned log_sub,
-                 u64* d_digests, u64* d_roots) {
+                 u64* d_digests, u64* d_roots, cudaEvent_t after_leaves = nullptr) {
   const u64 sub_leaves = 1ULL << log_sub;
   const u64 nsub = nleaves >> log_sub;
   const u64 sub_digests = 2 * sub_leaves - 2;
@@ -219,6 +219,7 @@ int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, uns
   merkle::hash_leaves<<<(unsigned)((nleaves + 127) / 128), 128, 0, ctx->stream>>>(
       d_leaves, nleaves, width, all_cap ? d_roots : d_digests, log_sub, sub_digests, all_cap);
   ctx->launches++;
+  if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
   for (unsigned level = 1; level <= log_sub; level++) {
     const u64 nnodes = nsub << (log_sub - level);
     merkle::reduce_level<<<(unsigned)((nnodes + 127) / 128), 128, 0, ctx->stream>>>(
@@ -233,8 +234,9 @@ struct Timer {
   vpbs_ctx* ctx;
   bool on;
   int n = 0;
+  bool leaf_event = false;
   void mark() {
-    if (on && n < 8) cudaEventRecord(ctx->ev[n++], ctx->stream);
+    if (on && n < 4) cudaEventRecord(ctx->ev[n++], ctx->stream);
   }
   float ms(int a, int b) {
     float t = 0;
@@ -310,8 +312,10 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   }
   tm->mark();  // 2
   // "build Merkle tree"
-  if ((rc = merkle_build(ctx, d_leaves, nleaves_shard, width, log_sub, d_digests, d_roots)) != VPBS_OK)
+  if ((rc = merkle_build(ctx, d_leaves, nleaves_shard, width, log_sub, d_digests, d_roots,
+                         tm->on ? ctx->ev[8] : nullptr)) != VPBS_OK)
     return rc;
+  tm->leaf_event = tm->on;
   tm->mark();  // 3
   CU(ctx, cudaGetLastError());
   return VPBS_OK;
@@ -322,6 +326,7 @@ void fill_stats(vpbs_stats* st, Timer& tm, uint64_t launches) {
   st->ifft_ms = tm.ms(0, 1);
   st->fft_ms = tm.ms(1, 2);
   st->merkle_ms = tm.ms(2, 3);
+  if (tm.leaf_event && tm.n > 2) cudaEventElapsedTime(&st->leaf_hash_ms, tm.ctx->ev[2], tm.ctx->ev[8]);
   st->kernel_launches = launches;
 }
 
@@ -361,7 +366,7 @@ int vpbs_ctx_create(int device, vpbs_ctx** out) {
   ctx->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-  for (int i = 0; e == cudaSuccess && i < 8; i++) e = cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; e == cudaSuccess && i < 10; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     fail(nullptr, VPBS_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
     delete ctx;
@@ -380,7 +385,7 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : ctx->coset_tables) cudaFree(kv.second);
   if (ctx->roots) cudaFree(ctx->roots);
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < 10; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
