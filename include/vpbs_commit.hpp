@@ -1,0 +1,224 @@
+// vpbs_commit.hpp — header-only C++ host mirror of plonky2 0.2.0's commitment API over the C ABI
+// (include/vpbs_commit.h).  The reference's host language is Rust, which this environment cannot
+// compile; this mirror keeps plonky2's names, argument meaning and failure behaviour so that a
+// call site reads like upstream:
+//
+//   [P2] plonky2_field/src/fft.rs            fft / ifft                      -> vpbs::fft, vpbs::ifft
+//   [P2] plonky2_field/src/polynomial/mod.rs PolynomialCoeffs::coset_fft     -> vpbs::coset_fft
+//   [P2] plonky2/src/hash/merkle_tree.rs     MerkleTree::{new,get,prove}     -> vpbs::MerkleTree
+//   [P2] plonky2/src/fri/oracle.rs           PolynomialBatch::{from_values,from_coeffs,
+//                                            get_lde_values}                 -> vpbs::PolynomialBatch
+//
+// reached in the reference from prove()/build(), /root/reference/src/vtfhe/ivc_based_vpbs.rs:275,
+// :302, :333, :364.  Where plonky2 panics (assert!/unwrap) these throw std::invalid_argument
+// (argument errors) or std::runtime_error (device errors).  No CPU fallback exists behind any call.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vpbs_commit.h"
+
+namespace vpbs {
+
+using F = uint64_t;  // GoldilocksField: #[repr(transparent)] u64
+constexpr std::size_t NUM_HASH_OUT_ELTS = 4;
+constexpr std::size_t SALT_SIZE = VPBS_SALT_SIZE;
+struct HashOut {
+  F elements[NUM_HASH_OUT_ELTS];
+  bool operator==(const HashOut& o) const {
+    for (std::size_t i = 0; i < NUM_HASH_OUT_ELTS; i++)
+      if (elements[i] != o.elements[i]) return false;
+    return true;
+  }
+};
+
+inline unsigned log2_strict(std::size_t n) {  // [P2] plonky2_util::log2_strict
+  if (n == 0 || (n & (n - 1))) throw std::invalid_argument("Not a power of two: " + std::to_string(n));
+  unsigned l = 0;
+  while ((std::size_t(1) << l) < n) l++;
+  return l;
+}
+inline std::size_t reverse_bits(std::size_t x, unsigned bits) {  // [P2] plonky2_util::reverse_bits
+  std::size_t r = 0;
+  for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    int rc = vpbs_ctx_create(device, &h_);
+    if (rc != VPBS_OK) throw std::runtime_error(std::string("vpbs_ctx_create: ") + vpbs_last_error(nullptr));
+  }
+  ~Context() { vpbs_ctx_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  vpbs_ctx* get() const { return h_; }
+  void check(int rc) const {
+    if (rc == VPBS_OK) return;
+    std::string msg = vpbs_last_error(h_);
+    if (rc == VPBS_ERR_ARG) throw std::invalid_argument(msg);
+    throw std::runtime_error("vpbs error " + std::to_string(rc) + ": " + msg);
+  }
+
+ private:
+  vpbs_ctx* h_ = nullptr;
+};
+
+// ---- fft.rs / polynomial/mod.rs ---------------------------------------------------------------
+inline std::vector<F> fft(const Context& ctx, std::vector<F> coeffs) {
+  ctx.check(vpbs_fft(ctx.get(), coeffs.data(), log2_strict(coeffs.size())));
+  return coeffs;
+}
+inline std::vector<F> ifft(const Context& ctx, std::vector<F> values) {
+  ctx.check(vpbs_ifft(ctx.get(), values.data(), log2_strict(values.size())));
+  return values;
+}
+inline std::vector<F> coset_fft(const Context& ctx, std::vector<F> coeffs, F shift = 7) {
+  ctx.check(vpbs_coset_fft(ctx.get(), coeffs.data(), log2_strict(coeffs.size()), shift));
+  return coeffs;
+}
+
+// ---- hash/merkle_tree.rs ------------------------------------------------------------------------
+struct MerkleProof {
+  std::vector<HashOut> siblings;
+};
+
+class MerkleTree {
+ public:
+  // Row-major leaves (leaf k = leaves[k*leaf_len .. (k+1)*leaf_len)): the flat form of plonky2's
+  // Vec<Vec<F>>.
+  std::vector<F> leaves;
+  std::size_t leaf_len = 0;
+  std::vector<HashOut> digests;
+  std::vector<HashOut> cap;  // MerkleCap.0
+
+  MerkleTree() = default;
+  // MerkleTree::new(leaves, cap_height)
+  MerkleTree(const Context& ctx, std::vector<F> leaves_rowmajor, std::size_t leaf_length,
+             unsigned cap_height)
+      : leaves(std::move(leaves_rowmajor)), leaf_len(leaf_length) {
+    const std::size_t nleaves = leaf_len ? leaves.size() / leaf_len : 0;
+    const unsigned lg = log2_strict(nleaves);
+    if (cap_height > lg)
+      throw std::invalid_argument("cap_height=" + std::to_string(cap_height) +
+                                  " should be at most log2(leaves.len())=" + std::to_string(lg));
+    digests.resize(2 * (nleaves - (std::size_t(1) << cap_height)));
+    cap.resize(std::size_t(1) << cap_height);
+    ctx.check(vpbs_merkle_new(ctx.get(), leaves.data(), nleaves, (uint32_t)leaf_len, cap_height,
+                              digests.empty() ? nullptr : digests[0].elements, cap[0].elements));
+  }
+  std::size_t num_leaves() const { return leaf_len ? leaves.size() / leaf_len : 0; }
+  const F* get(std::size_t i) const { return leaves.data() + i * leaf_len; }
+  // MerkleTree::prove: index arithmetic over the unchanged `digests` layout.
+  MerkleProof prove(std::size_t leaf_index) const {
+    const unsigned cap_height = log2_strict(cap.size());
+    const unsigned num_layers = log2_strict(num_leaves()) - cap_height;
+    if (leaf_index >> (cap_height + num_layers)) throw std::invalid_argument("leaf_index out of range");
+    const std::size_t tree_index = leaf_index >> num_layers;
+    const std::size_t tree_len = digests.size() >> cap_height;
+    const HashOut* tree = digests.data() + tree_len * tree_index;
+    std::size_t pair_index = leaf_index & ((std::size_t(1) << num_layers) - 1);
+    MerkleProof p;
+    for (unsigned i = 0; i < num_layers; i++) {
+      const std::size_t parity = pair_index & 1;
+      pair_index >>= 1;
+      const std::size_t siblings_index = (pair_index << (i + 1)) + (std::size_t(1) << i) - 1;
+      p.siblings.push_back(tree[2 * siblings_index + (1 - parity)]);
+    }
+    return p;
+  }
+};
+
+// [P2] hash/merkle_proofs.rs verify_merkle_proof_to_cap (hashing on the device).
+inline bool verify_merkle_proof_to_cap(const Context& ctx, const F* leaf, std::size_t leaf_len,
+                                       std::size_t leaf_index, const std::vector<HashOut>& cap,
+                                       const MerkleProof& proof) {
+  HashOut cur;
+  ctx.check(vpbs_hash_or_noop_batch(ctx.get(), leaf, 1, (uint32_t)leaf_len, cur.elements));
+  std::size_t idx = leaf_index;
+  for (const HashOut& sib : proof.siblings) {
+    HashOut nxt;
+    if (idx & 1) ctx.check(vpbs_two_to_one_batch(ctx.get(), sib.elements, cur.elements, 1, nxt.elements));
+    else ctx.check(vpbs_two_to_one_batch(ctx.get(), cur.elements, sib.elements, 1, nxt.elements));
+    cur = nxt;
+    idx >>= 1;
+  }
+  return cur == cap[idx];
+}
+
+// ---- fri/oracle.rs ------------------------------------------------------------------------------
+class PolynomialBatch {
+ public:
+  std::vector<std::vector<F>> polynomials;  // coefficient vectors
+  MerkleTree merkle_tree;
+  unsigned degree_log = 0;
+  unsigned rate_bits = 0;
+  bool blinding = false;
+  vpbs_stats stats{};  // plonky2's TimingTree scopes for this commit
+
+  // from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table): `salt` stands in
+  // for F::rand_vec (the RNG stays on the host); required iff blinding.
+  static PolynomialBatch from_values(const Context& ctx, const std::vector<std::vector<F>>& values,
+                                     unsigned rate_bits, bool blinding, unsigned cap_height,
+                                     const std::vector<std::vector<F>>* salt = nullptr) {
+    return commit(ctx, values, rate_bits, blinding, cap_height, false, salt);
+  }
+  static PolynomialBatch from_coeffs(const Context& ctx, const std::vector<std::vector<F>>& polys,
+                                     unsigned rate_bits, bool blinding, unsigned cap_height,
+                                     const std::vector<std::vector<F>>* salt = nullptr) {
+    return commit(ctx, polys, rate_bits, blinding, cap_height, true, salt);
+  }
+  // get_lde_values(index, step): leaf reverse_bits(index * step) without the salt.
+  std::vector<F> get_lde_values(std::size_t index, std::size_t step = 1) const {
+    const std::size_t k = reverse_bits(index * step, degree_log + rate_bits);
+    const F* row = merkle_tree.get(k);
+    return std::vector<F>(row, row + merkle_tree.leaf_len - (blinding ? SALT_SIZE : 0));
+  }
+
+ private:
+  static PolynomialBatch commit(const Context& ctx, const std::vector<std::vector<F>>& cols,
+                                unsigned rate_bits, bool blinding, unsigned cap_height,
+                                bool are_coeffs, const std::vector<std::vector<F>>* salt) {
+    if (cols.empty()) throw std::invalid_argument("empty batch");
+    const std::size_t n = cols[0].size();
+    const unsigned log_n = log2_strict(n);
+    for (auto& c : cols)
+      if (c.size() != n) throw std::invalid_argument("Polynomial degrees inconsistent");
+    const std::size_t m = n << rate_bits, ncols = cols.size();
+    if (blinding && (!salt || salt->size() != SALT_SIZE)) throw std::invalid_argument("blinding needs 4 salt columns");
+    PolynomialBatch b;
+    b.degree_log = log_n;
+    b.rate_bits = rate_bits;
+    b.blinding = blinding;
+    b.polynomials.assign(ncols, std::vector<F>(n));
+    std::vector<const F*> in(ncols), sp(SALT_SIZE);
+    std::vector<F*> co(ncols);
+    for (std::size_t c = 0; c < ncols; c++) {
+      in[c] = cols[c].data();
+      co[c] = b.polynomials[c].data();
+    }
+    if (blinding)
+      for (std::size_t s = 0; s < SALT_SIZE; s++) {
+        if ((*salt)[s].size() != m) throw std::invalid_argument("salt column length");
+        sp[s] = (*salt)[s].data();
+      }
+    if (cap_height > log_n + rate_bits)
+      throw std::invalid_argument("cap_height should be at most log2(leaves.len())");
+    MerkleTree& t = b.merkle_tree;
+    t.leaf_len = ncols + (blinding ? SALT_SIZE : 0);
+    t.leaves.resize(m * t.leaf_len);
+    t.digests.resize(2 * (m - (std::size_t(1) << cap_height)));
+    t.cap.resize(std::size_t(1) << cap_height);
+    ctx.check(vpbs_commit(ctx.get(), in.data(), (uint32_t)ncols, log_n, rate_bits, cap_height,
+                          are_coeffs ? 1 : 0, blinding ? sp.data() : nullptr, co.data(),
+                          t.leaves.data(), t.digests.empty() ? nullptr : t.digests[0].elements,
+                          t.cap[0].elements, &b.stats));
+    return b;
+  }
+};
+
+}  // namespace vpbs

@@ -286,3 +286,122 @@ def test_linearity_of_lde(V, ctx):
     ls = V.PolynomialBatch.from_values(s, 3, False, 4, ctx=ctx).merkle_tree.leaves
     want = (la[:, 0].astype(object) + la[:, 1].astype(object)) % P
     assert np.array_equal(ls[:, 0].astype(object), want)
+
+
+def test_cpp_host_mirror(V, ctx, oracle, tmp_path):
+    """include/vpbs_commit.hpp (C++ mirror of plonky2's API over the C ABI) vs the oracle."""
+    import os
+    import subprocess
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    exe = str(tmp_path / "test_api")
+    libdir = os.path.join(root, "verifiable-fhe-paper_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", os.path.join(root, "tests", "cpp", "test_api.cpp"),
+                    "-o", exe, "-L" + libdir, "-lvpbs_commit", "-L" + os.path.join(root, "oracle"),
+                    "-loracle", "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(root, "oracle")],
+                   check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp host mirror ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("log_n,ncols,rate_bits,cap_height,world", [
+    (10, 20, 3, 4, 8), (10, 135, 3, 4, 2), (12, 16, 3, 3, 4), (8, 5, 2, 6, 4), (13, 9, 1, 1, 2)])
+def test_row_range_shards_equal_full_commit(V, ctx, oracle, log_n, ncols, rate_bits, cap_height, world):
+    """vpbs_commit_shard_dev: every shard (run here one after the other on one GPU) reproduces its
+    rows, digests and subtree roots of the full commit bit-for-bit (multi-GPU parity rule)."""
+    import torch
+    cols = V.synthetic_columns(ncols, 1 << log_n, seed=31337)
+    ref = oracle.commit(cols, rate_bits, cap_height)
+    d_cols = torch.from_numpy(cols.view(np.int64)).cuda()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    caps = []
+    for rank in range(world):
+        plan, leaves, digests, cap, coeffs, _ = _one_shard(V, ctx, d_cols, ncols, log_n, rate_bits,
+                                                            cap_height, rank, world)
+        torch.cuda.synchronize()
+        assert np.array_equal(leaves.cpu().numpy().view(np.uint64),
+                              ref["leaves"][plan.first_leaf: plan.first_leaf + plan.nleaves])
+        assert np.array_equal(digests.cpu().numpy().view(np.uint64),
+                              ref["digests"][plan.digest_offset: plan.digest_offset + plan.ndigests])
+        assert np.array_equal(coeffs.cpu().numpy().view(np.uint64), ref["coeffs"])
+        caps.append(cap.cpu().numpy().view(np.uint64))
+    assert np.array_equal(np.concatenate(caps), ref["cap"])
+    ctx.set_stream(0)
+
+
+def _one_shard(V, ctx, d_cols, ncols, log_n, rate_bits, cap_height, rank, world):
+    import torch
+    plan = V.shard_plan(log_n, rate_bits, cap_height, rank, world)
+    n = 1 << log_n
+    dev = d_cols.device
+    coeffs = torch.empty((ncols, n), dtype=torch.int64, device=dev)
+    leaves = torch.empty((plan.nleaves, ncols), dtype=torch.int64, device=dev)
+    digests = torch.empty((max(plan.ndigests, 1), 4), dtype=torch.int64, device=dev)
+    roots = torch.empty((plan.ncap, 4), dtype=torch.int64, device=dev)
+    V.commit_shard_device(ctx, d_cols.data_ptr(), ncols, log_n, rate_bits, cap_height, False,
+                          plan.first_leaf, plan.nleaves, coeffs.data_ptr(), leaves.data_ptr(),
+                          digests.data_ptr() if plan.ndigests else 0, roots.data_ptr())
+    return plan, leaves, digests[:plan.ndigests], roots, coeffs, None
+
+
+def test_shard_rejects_bad_ranges(V, ctx):
+    import torch
+    cols = torch.zeros((2, 16), dtype=torch.int64, device="cuda")
+    out = torch.zeros((1024,), dtype=torch.int64, device="cuda")
+    with pytest.raises(ValueError):   # not a whole LDE block
+        V.commit_shard_device(ctx, cols.data_ptr(), 2, 4, 3, 2, False, 8, 8, 0, out.data_ptr(),
+                              out.data_ptr(), out.data_ptr())
+    with pytest.raises(ValueError):   # smaller than a cap subtree
+        V.commit_shard_device(ctx, cols.data_ptr(), 2, 4, 3, 0, False, 0, 16, 0, out.data_ptr(),
+                              out.data_ptr(), out.data_ptr())
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import vfhe_b200 as V
+    from oracle import binding as B
+    c = V.Context(rank)
+    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    log_n, ncols, r, h = 12, 20, 3, 4
+    cols = V.synthetic_columns(ncols, 1 << log_n, seed=5)
+    d_cols = torch.from_numpy(cols.view(np.int64)).cuda()
+    plan, leaves, digests, cap, coeffs, _ = V.commit_sharded(c, d_cols, ncols, log_n, r, h, False, rank, world)
+    torch.cuda.synchronize()
+    ref = B.commit(cols, r, h)
+    ok = (np.array_equal(cap.cpu().numpy().view(np.uint64), ref["cap"])
+          and np.array_equal(leaves.cpu().numpy().view(np.uint64),
+                             ref["leaves"][plan.first_leaf: plan.first_leaf + plan.nleaves])
+          and np.array_equal(digests.cpu().numpy().view(np.uint64),
+                             ref["digests"][plan.digest_offset: plan.digest_offset + plan.ndigests]))
+    res = [None] * world
+    dist.all_gather_object(res, bool(ok))
+    if rank == 0:
+        q.put(all(res))
+    dist.destroy_process_group()
+
+
+def test_sharded_commit_over_nccl(V):
+    """One commit split over all visible GPUs (needs >= 2): only the subtree roots cross NVLink."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 1 << (min(world, 8).bit_length() - 1)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    procs = [mpctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

@@ -4,10 +4,11 @@ Only what the hot path needs: csrc/ (CUDA kernels + C ABI, built into libvpbs_co
 the ctypes binding and a host-side mirror of plonky2's PolynomialBatch / MerkleTree / fft API.
 The directory name is not a Python identifier; import it through the root module `vfhe_b200`.
 """
-from . import _lib, build  # noqa: F401
+from . import _lib, build, sharding  # noqa: F401
 from ._lib import VpbsError, VpbsStats  # noqa: F401
 from .plonky2_api import (  # noqa: F401
     COSET_SHIFT, P, SALT_SIZE, Context, MerkleProof, MerkleTree, PolynomialBatch, coset_fft,
     commit_device, commit_shard_device, default_context, fft, hash_or_noop, ifft, lde_values,
     log2_strict, poseidon, reverse_bits, synthetic_columns, two_to_one,
     verify_merkle_proof_to_cap)
+from .sharding import ShardPlan, commit_sharded, gather_cap, shard_plan  # noqa: F401,E402
