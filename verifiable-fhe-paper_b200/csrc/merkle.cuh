@@ -54,8 +54,14 @@ __device__ __forceinline__ void hash_row(const u64* __restrict__ row, u32 width,
 // Position (in hashes) of leaf digest `l` of a cap subtree inside that subtree's digest buffer.
 __device__ __forceinline__ u64 leaf_digest_pos(u64 l) { return 4 * (l >> 1) + (l & 1); }
 
+#ifndef VPBS_HASH_THREADS
+#define VPBS_HASH_THREADS 128
+#endif
+#ifndef VPBS_HASH_MIN_BLOCKS
+#define VPBS_HASH_MIN_BLOCKS 1
+#endif
 // One thread per leaf.  all_cap: the tree has no digests, leaf hashes are the cap.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(VPBS_HASH_THREADS, VPBS_HASH_MIN_BLOCKS)
 hash_leaves(const u64* __restrict__ leaves, u64 nleaves, u32 width, u64* __restrict__ out,
             unsigned log_sub, u64 sub_digests, int all_cap) {
   const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;

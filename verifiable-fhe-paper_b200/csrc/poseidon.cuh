@@ -80,40 +80,48 @@ __constant__ double RCD[2 * (ROUNDS + 1) * WIDTH] = {
 #include "poseidon_rcd.inc"
 };
 
-template <int R, int I>
-struct MdsRow {
+// Input-stationary order: for each state word (converted to doubles on the fly) update all twelve
+// output accumulators.  Consecutive DFMAs then share their multiplicand, which the register reuse
+// cache serves without a second register-file read (a DFMA with three distinct 64-bit register
+// operands needs two dispatch cycles on this part), and only one converted pair is live at a time.
+template <int J, int R>
+struct MdsCol {
   static constexpr u32 CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  // MDS_MATRIX_DIAG = [8, 0, ..., 0] only touches (row 0, lane 0): fold it into that coefficient.
-  static constexpr double COEF = (double)(CIRC[I] + ((R == 0 && I == 0) ? 8u : 0u));
-  __device__ __forceinline__ static void run(const double (&dl)[WIDTH], const double (&dh)[WIDTH],
-                                             double& acc_lo, double& acc_hi) {
-    acc_lo = fma(dl[(I + R) % WIDTH], COEF, acc_lo);
-    acc_hi = fma(dh[(I + R) % WIDTH], COEF, acc_hi);
-    if constexpr (I + 1 < WIDTH) MdsRow<R, I + 1>::run(dl, dh, acc_lo, acc_hi);
+  // out[R] takes in[J] with coefficient CIRC[(J - R) mod 12]; MDS_MATRIX_DIAG = [8, 0, ..., 0]
+  // only touches (row 0, lane 0) and is folded into that coefficient.
+  static constexpr double COEF =
+      (double)(CIRC[(J - R + WIDTH) % WIDTH] + ((R == 0 && J == 0) ? 8u : 0u));
+  __device__ __forceinline__ static void run(double xl, double xh, double (&al)[WIDTH],
+                                             double (&ah)[WIDTH]) {
+    al[R] = fma(xl, COEF, al[R]);
+    ah[R] = fma(xh, COEF, ah[R]);
+    if constexpr (R + 1 < WIDTH) MdsCol<J, R + 1>::run(xl, xh, al, ah);
   }
 };
 
-template <int R>
-__device__ __forceinline__ void mds_rows(u64 (&s)[WIDTH], const double (&dl)[WIDTH],
-                                         const double (&dh)[WIDTH], const double* __restrict__ rcd) {
-  double acc_lo = rcd[2 * R], acc_hi = rcd[2 * R + 1];
-  MdsRow<R, 0>::run(dl, dh, acc_lo, acc_hi);
-  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
-  s[R] = reduce96((u64)__double_as_longlong(acc_lo) & MANT, (u64)__double_as_longlong(acc_hi) & MANT);
-  if constexpr (R + 1 < WIDTH) mds_rows<R + 1>(s, dl, dh, rcd);
+template <int J>
+__device__ __forceinline__ void mds_cols(const u64 (&s)[WIDTH], double (&al)[WIDTH],
+                                         double (&ah)[WIDTH]) {
+  MdsCol<J, 0>::run(half_to_f64((u32)s[J]), half_to_f64((u32)(s[J] >> 32)), al, ah);
+  if constexpr (J + 1 < WIDTH) mds_cols<J + 1>(s, al, ah);
 }
 
 // MDS layer fused with the following constant layer:
 //   s'_r = RC_next[r] + sum_i CIRC[i] * s_{(i+r) mod 12} + DIAG[r] * s_r
 // `next_round` indexes the constants added after the MDS (ROUNDS = none).
 __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
-  double dl[WIDTH], dh[WIDTH];
+  double al[WIDTH], ah[WIDTH];
+  const double* __restrict__ rcd = RCD + 2 * WIDTH * next_round;
 #pragma unroll
-  for (int i = 0; i < WIDTH; i++) {
-    dl[i] = half_to_f64((u32)s[i]);
-    dh[i] = half_to_f64((u32)(s[i] >> 32));
+  for (int r = 0; r < WIDTH; r++) {
+    al[r] = rcd[2 * r];
+    ah[r] = rcd[2 * r + 1];
   }
-  mds_rows<0>(s, dl, dh, RCD + 2 * WIDTH * next_round);
+  mds_cols<0>(s, al, ah);
+  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++)
+    s[r] = reduce96((u64)__double_as_longlong(al[r]) & MANT, (u64)__double_as_longlong(ah[r]) & MANT);
 }
 
 // In-place permutation; input words arbitrary u64, output words arbitrary u64 (lazy).
