@@ -56,7 +56,9 @@ typedef struct vpbs_stats {
   float fft_ms;    /* "FFT + blinding" + "transpose LDEs"                          */
   float merkle_ms; /* "build Merkle tree" (leaf hashing + all levels)              */
   float leaf_hash_ms; /* the leaf-hashing kernel alone (part of merkle_ms)        */
-  float d2h_ms;    /* device -> host copies of the outputs (0 for *_dev calls)     */
+  float d2h_ms;    /* output copies NOT hidden behind kernels: last kernel -> last copy
+                      (the host API streams coefficients / leaf blocks out on a second
+                      stream while later kernels run; 0 for *_dev calls)           */
   float total_ms;  /* first event to last event of the call                        */
   uint64_t kernel_launches; /* kernels of this library launched by the call        */
 } vpbs_stats;

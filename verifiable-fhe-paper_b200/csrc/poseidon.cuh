@@ -41,7 +41,7 @@ __device__ __forceinline__ u64 sbox7(u64 x) {
   return gl::mul_lazy(x3, x4);
 }
 
-// value = lo + 2^32 * hi with lo, hi < 2^43  ->  arbitrary-u64 representative mod p.
+// value = lo + 2^32 * hi with lo < 2^55, hi < 2^43  ->  arbitrary-u64 representative mod p.
 //   hi = hh * 2^32 + hl:  value = lo + hh * (2^32 - 1) + hl * 2^32   (2^64 = 2^32 - 1 mod p)
 __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
   u32 r0, r1;
@@ -49,7 +49,7 @@ __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
       ".reg .u32 hl, hh, t0, t1, bm;\n\t"
       ".reg .u64 t;\n\t"
       "mov.b64 {hl, hh}, %3;\n\t"
-      "mad.wide.u32 t, hh, 0xffffffff, %2;\n\t"  // < 2^44: no carry
+      "mad.wide.u32 t, hh, 0xffffffff, %2;\n\t"  // < 2^56: no carry
       "mov.b64 {t0, t1}, t;\n\t"
       "add.cc.u32 t1, t1, hl;\n\t"
       "addc.u32 bm, 0, 0;\n\t"                   // carry (0/1)
@@ -61,6 +61,95 @@ __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
       : "l"(lo), "l"(hi));
   return ((u64)r1 << 32) | r0;
 }
+
+// ---- MDS layer --------------------------------------------------------------------------------
+// Two implementations, selected at compile time: the FP64 form (default — fastest measured on
+// B200: 8.85 ms for 8.39 M permutations) and, with -DVPBS_MDS_INT32, a pure 32-bit integer form
+// (9.86 ms) kept as the documented alternative; both are bit-exact (tools/selftest.cu).
+//
+// What the integer pipes cost here (tools/microbench.cu + ncu, profiles/): IMAD.WIDE.U32 runs at
+// half rate and ptxas never uses its 64-bit addend, so a 64-bit multiply-accumulate is
+// IMAD.WIDE + IADD3 + IADD3.X; every IMAD-class instruction (incl. the IMAD.X / IMAD.MOV ptxas
+// likes to emit for adds and moves) goes to the fmaheavy half of the FMA pipe, which ends up the
+// busiest unit.  The MDS constants are tiny (<= 41).  The integer form:
+//   * split every state word into limbs of 22/21/21 bits; sum_i c_i * limb_i < 2^31 fits a 32-bit
+//     accumulator and each MAC is ONE IMAD;
+//   * the matrix is circulant (+ one diagonal entry), i.e. a length-12 cyclic convolution.
+//     x^12 - 1 = (x^6 - 1)(x^6 + 1) splits it into a cyclic and a negacyclic length-6 convolution
+//     on p_t = s_t + s_{t+6} and m_t = s_t - s_{t+6}:  2 y_r = Z+_r + Z-_r, 2 y_{r+6} = Z+_r - Z-_r
+//     (72 MACs per limb instead of 144; all arithmetic is exact mod 2^32, results < 2^32);
+//   * the doubled outputs are recombined and reduced once per lane (reduce96).
+#ifdef VPBS_MDS_INT32
+
+// {sum, difference} of the limbs of RC[r'], RC[r'+6]: [round][limb][r'][2]; row 30 = zeros.
+__constant__ u32 RCL[(ROUNDS + 1) * 36] = {
+#include "poseidon_rcl.inc"
+};
+
+namespace mds_detail {
+constexpr int CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+__host__ __device__ constexpr int cplus(int j) { return CIRC[j] + CIRC[j + 6]; }   // 30 28 80 34 36 48
+__host__ __device__ constexpr int cminus(int j) { return CIRC[j] - CIRC[j + 6]; }  //  4  2  2 -2 -32  8
+
+// Z+_r = init + sum_j c+_j p[(j + r) mod 6];  Z-_r = init + sum_j (+-)c-_j m[(j + r) mod 6]
+template <int R, int J>
+__device__ __forceinline__ void conv(const u32 (&p)[6], const u32 (&m)[6], u32& zp, u32& zm) {
+  constexpr int T = J + R;
+  constexpr u32 CP = (u32)cplus(J);
+  constexpr u32 CM = (u32)(T < 6 ? cminus(J) : -cminus(J));
+  zp += CP * p[T % 6];
+  zm += CM * m[T % 6];
+  if constexpr (J + 1 < 6) conv<R, J + 1>(p, m, zp, zm);
+}
+template <int R>
+__device__ __forceinline__ void rows(const u32 (&p)[6], const u32 (&m)[6], const u32 (&l)[WIDTH],
+                                     const u32* __restrict__ rcl, u32 (&y2)[WIDTH]) {
+  u32 zp = rcl[2 * R], zm = rcl[2 * R + 1];
+  conv<R, 0>(p, m, zp, zm);
+  y2[R] = zp + zm;
+  y2[R + 6] = zp - zm;
+  if constexpr (R == 0) y2[0] += 16u * l[0];  // MDS_MATRIX_DIAG = [8, 0, ..., 0], doubled
+  if constexpr (R + 1 < 6) rows<R + 1>(p, m, l, rcl, y2);
+}
+// One limb plane: y2[r] = 2 * (RC_limb[r] + sum_i CIRC[i] * l[(i + r) % 12] + DIAG[r] * l[r])
+__device__ __forceinline__ void plane(const u32 (&l)[WIDTH], const u32* __restrict__ rcl,
+                                      u32 (&y2)[WIDTH]) {
+  u32 p[6], m[6];
+#pragma unroll
+  for (int t = 0; t < 6; t++) {
+    p[t] = l[t] + l[t + 6];
+    m[t] = l[t] - l[t + 6];
+  }
+  rows<0>(p, m, l, rcl, y2);
+}
+}  // namespace mds_detail
+
+// MDS layer fused with the following constant layer:
+//   s'_r = RC_next[r] + sum_i CIRC[i] * s_{(i+r) mod 12} + DIAG[r] * s_r
+// `next_round` indexes the constants added after the MDS (ROUNDS = none).
+__device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
+  u32 l0[WIDTH], l1[WIDTH], l2[WIDTH], a[WIDTH], b[WIDTH], c[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) {
+    const u32 w0 = (u32)s[i], w1 = (u32)(s[i] >> 32);
+    l0[i] = w0 & 0x3FFFFFu;                              // bits  0..21
+    l1[i] = __funnelshift_r(w0, w1, 22) & 0x1FFFFFu;     // bits 22..42
+    l2[i] = w1 >> 11;                                    // bits 43..63
+  }
+  const u32* __restrict__ rcl = RCL + 36 * next_round;
+  mds_detail::plane(l0, rcl, a);
+  mds_detail::plane(l1, rcl + 12, b);
+  mds_detail::plane(l2, rcl + 24, c);
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) {
+    // value = a/2 + (b/2) * 2^22 + (c/2) * 2^43  with a, b, c even and < 2^32
+    const u64 lo = (u64)(a[r] >> 1) + ((u64)b[r] << 21);  // < 2^54
+    const u64 hi = (u64)c[r] << 10;                       // (c/2) * 2^43 = hi * 2^32, hi < 2^42
+    s[r] = reduce96(lo, hi);
+  }
+}
+
+#else  // FP64 MDS (default)
 
 // ---- MDS layer on the FP64 pipe ---------------------------------------------------------------
 // On B200 a 64-bit integer multiply-accumulate costs three issue slots (IMAD.WIDE.U32 runs at half
@@ -123,6 +212,8 @@ __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
   for (int r = 0; r < WIDTH; r++)
     s[r] = reduce96((u64)__double_as_longlong(al[r]) & MANT, (u64)__double_as_longlong(ah[r]) & MANT);
 }
+
+#endif  // VPBS_MDS_INT32
 
 // In-place permutation; input words arbitrary u64, output words arbitrary u64 (lazy).
 // One loop over the 30 rounds with a warp-uniform "full round" branch keeps a single copy of the

@@ -49,6 +49,9 @@ struct vpbs_ctx {
   // grow-only arena
   std::map<std::string, Buf> arena;
   cudaEvent_t ev[10] = {};
+  // host API: device->host copies run on their own stream, overlapped with the remaining kernels
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
 };
 
 namespace {
@@ -230,11 +233,18 @@ int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, uns
   return VPBS_OK;
 }
 
+// Points of the commit the host API hangs its overlapped output copies on.
+struct Overlap {
+  cudaEvent_t coeffs_ready = nullptr;      // after the IFFT
+  std::vector<cudaEvent_t> block_ready;    // after LDE block b (its n leaf rows are final)
+};
+
 struct Timer {
   vpbs_ctx* ctx;
   bool on;
   int n = 0;
   bool leaf_event = false;
+  Overlap* overlap = nullptr;
   void mark() {
     if (on && n < 4) cudaEventRecord(ctx->ev[n++], ctx->stream);
   }
@@ -296,6 +306,7 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
                             cudaMemcpyDeviceToDevice, ctx->stream));
   }
   tm->mark();  // 1
+  if (tm->overlap && tm->overlap->coeffs_ready) cudaEventRecord(tm->overlap->coeffs_ready, ctx->stream);
   // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
   // leaf rows.
   const u64 b0 = first_leaf >> log_n, nb = nleaves_shard >> log_n;
@@ -303,6 +314,8 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
     if ((rc = run_transform<false>(ctx, coeffs, n, ncols, log_n, work, Out::Leaf, d_leaves, width,
                                    b << log_n, coset + ((b0 + b) << log_n), 1)) != VPBS_OK)
       return rc;
+    if (tm->overlap && !d_salt && b < tm->overlap->block_ready.size())
+      cudaEventRecord(tm->overlap->block_ready[b], ctx->stream);
   }
   if (d_salt) {
     const u64 cnt = nleaves_shard * 4;
@@ -366,6 +379,7 @@ int vpbs_ctx_create(int device, vpbs_ctx** out) {
   ctx->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int i = 0; e == cudaSuccess && i < 10; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     fail(nullptr, VPBS_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
@@ -387,6 +401,8 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   if (ctx->roots) cudaFree(ctx->roots);
   for (int i = 0; i < 10; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->ov) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -669,25 +685,53 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
                               ctx->stream));
     }
   if (stats) cudaEventRecord(e1, ctx->stream);
+  // Output copies run on the copy stream as soon as their data is final: coefficients after the
+  // IFFT, each n-row leaf block after its last NTT pass, digests and cap after the tree.  All
+  // kernels are enqueued first, so the copies overlap the remaining NTT passes and the hashing.
+  const u64 nblocks = 1ULL << rate_bits;
+  while (ctx->ov.size() < nblocks + 2) {
+    cudaEvent_t e;
+    CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ov.push_back(e);
+  }
+  Overlap ovl;
+  ovl.coeffs_ready = ctx->ov[0];
+  ovl.block_ready.assign(ctx->ov.begin() + 1, ctx->ov.begin() + 1 + nblocks);
+  cudaEvent_t all_done = ctx->ov[nblocks + 1];
   Timer tm{ctx, stats != nullptr};
+  tm.overlap = &ovl;
   rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
                    inputs_are_coeffs ? nullptr : dco, dle, ddi, dca, &tm);
   if (rc) return rc;
+  CU(ctx, cudaEventRecord(all_done, ctx->stream));
   if (stats) cudaEventRecord(e2, ctx->stream);
+  cudaStream_t cs = ctx->copy_stream;
   if (coeffs_out) {
     const u64* csrc = inputs_are_coeffs ? din : dco;
+    CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_ready, 0));
     for (u32 c = 0; c < ncols; c++)
       if (coeffs_out[c])
-        CU(ctx, cudaMemcpyAsync(coeffs_out[c], csrc + (u64)c * n, n * 8, cudaMemcpyDeviceToHost,
-                                ctx->stream));
+        CU(ctx, cudaMemcpyAsync(coeffs_out[c], csrc + (u64)c * n, n * 8, cudaMemcpyDeviceToHost, cs));
   }
-  if (leaves_out)
-    CU(ctx, cudaMemcpyAsync(leaves_out, dle, (size_t)m * width * 8, cudaMemcpyDeviceToHost,
-                            ctx->stream));
+  if (leaves_out) {
+    if (salt_cols) {  // salt columns are scattered after the last block: leaves final only then
+      CU(ctx, cudaStreamWaitEvent(cs, all_done, 0));
+      CU(ctx, cudaMemcpyAsync(leaves_out, dle, (size_t)m * width * 8, cudaMemcpyDeviceToHost, cs));
+    } else {
+      const size_t block_elems = (size_t)n * width;
+      for (u64 blk = 0; blk < nblocks; blk++) {
+        CU(ctx, cudaStreamWaitEvent(cs, ovl.block_ready[blk], 0));
+        CU(ctx, cudaMemcpyAsync(leaves_out + blk * block_elems, dle + blk * block_elems,
+                                block_elems * 8, cudaMemcpyDeviceToHost, cs));
+      }
+    }
+  }
+  CU(ctx, cudaStreamWaitEvent(cs, all_done, 0));
   if (digests_out && ndig)
-    CU(ctx, cudaMemcpyAsync(digests_out, ddi, ndig * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaMemcpyAsync(cap_out, dca, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream));
-  if (stats) cudaEventRecord(e3, ctx->stream);
+    CU(ctx, cudaMemcpyAsync(digests_out, ddi, ndig * 32, cudaMemcpyDeviceToHost, cs));
+  CU(ctx, cudaMemcpyAsync(cap_out, dca, ncap * 32, cudaMemcpyDeviceToHost, cs));
+  if (stats) cudaEventRecord(e3, cs);
+  CU(ctx, cudaStreamSynchronize(cs));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   if (stats) {
     memset(stats, 0, sizeof *stats);
