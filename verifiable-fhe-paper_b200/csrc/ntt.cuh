@@ -158,6 +158,145 @@ pass_final(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
   }
 }
 
+// ---- radix-16 register kernels for 256-point passes (s = 8) --------------------------------------
+// The 2^16-row commits (the microbench and every N=1024 step commit) are two passes of 8 layers.
+// Here each thread keeps 16 elements in registers and runs 4 layers on them, the tile is exchanged
+// through shared memory ONCE, and 4 more layers run in registers: 1 barrier and 1 shared-memory
+// round trip per pass instead of 8, no per-butterfly index arithmetic, and the twiddles that are 1
+// (15 of the 64 butterflies per thread) cost nothing.  Tile = 256 points x 16 lanes, 256 threads.
+
+// 4 DIF layers over x[j], j = 0..15 (distance 8, 4, 2, 1 in j).  Butterfly (j, j + dd) of layer l
+// multiplies its difference by tw[((j mod dd) * jstride + off) << l]; tw[0] = 1 is skipped when the
+// exponent is known at compile time to be 0 (off == 0 && j mod dd == 0).
+template <bool HAS_OFF>
+__device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, unsigned jstride,
+                                      unsigned off, unsigned l0) {
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    const int dd = 8 >> l;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      if ((j & dd) == 0) {
+        const u64 a = x[j], c = x[j + dd];
+        x[j] = gl::add(a, c);
+        const u64 d = gl::sub(a, c);
+        const int jm = j & (dd - 1);
+        if (!HAS_OFF && jm == 0) x[j + dd] = d;
+        else x[j + dd] = gl::mul(d, tw[((unsigned)jm * jstride + off) << (l0 + l)]);
+      }
+    }
+  }
+}
+
+// 256-point DIF on a 256 x 16 tile held as 16 registers per thread.
+//  in : x[j] = element (q = 16 j + q_lo, lane), this thread's (q_lo, lane)
+//  out: x[j] = element (q = 16 q_hi + j, lane) after all 8 layers, this thread's (q_hi, lane);
+//       position q holds frequency bitrev8(q).
+// sm: 256 * pitch words; tw: 128 words, tw[e] = omega_256^(+-e).  The caller chooses the
+// (q_lo, lane) / (q_hi, lane) <-> threadIdx mappings (they differ between kernels for coalescing).
+__device__ __forceinline__ void dft256_regs(u64 (&x)[16], u64* sm, const u64* tw, unsigned pitch,
+                                            unsigned q_lo, unsigned lane_a, unsigned q_hi,
+                                            unsigned lane_b) {
+  // layers 0..3: q mod dd = (j mod ddj) * 16 + q_lo
+  dif16<true>(x, tw, 16, q_lo, 0);
+#pragma unroll
+  for (int j = 0; j < 16; j++) sm[(16 * j + q_lo) * pitch + lane_a] = x[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; j++) x[j] = sm[(16 * q_hi + j) * pitch + lane_b];
+  // layers 4..7: q mod dd = j mod dd
+  dif16<false>(x, tw, 1, 0, 4);
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(THREADS)
+pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restrict__ dst,
+                 u64 dst_col_stride, unsigned log_B, const u64* __restrict__ in_scale, Roots R) {
+  __shared__ u64 sm[256 * 16];
+  __shared__ u64 tw[128];
+  const unsigned log_sigma = log_B - 8;
+  const unsigned tiles_per_block_log = log_sigma - 4;
+  const u64 blk = blockIdx.x >> tiles_per_block_log;
+  const u64 low0 = (u64)(blockIdx.x & ((1u << tiles_per_block_log) - 1)) << 4;
+  const u64 base = blk << log_B;
+  src += (u64)blockIdx.y * src_col_stride;
+  dst += (u64)blockIdx.y * dst_col_stride;
+  const unsigned t = threadIdx.x & 15, qa = threadIdx.x >> 4;  // (q_lo | q_hi, lane): lane fastest
+  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  u64 x[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const u64 pos = base + ((u64)(16 * j + qa) << log_sigma) + low0 + t;
+    x[j] = gl::canon(__ldg(src + pos));
+    if (in_scale) x[j] = gl::mul(x[j], __ldg(in_scale + pos));
+  }
+  __syncthreads();  // tw ready
+  dft256_regs(x, sm, tw, 16, qa, t, qa, t);
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const unsigned q = 16 * qa + j;
+    const u64 pos = base + ((u64)q << log_sigma) + low0 + t;
+    const u64 e = (low0 + t) * (u64)brev(q, 8);  // < 2^log_B
+    u64 v = x[j];
+    if (e) v = gl::mul(v, root_of<INVERSE>(R, log_B, e));
+    dst[pos] = v;
+  }
+}
+
+template <bool INVERSE, int MODE>
+__global__ void __launch_bounds__(THREADS)
+pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
+               u64* __restrict__ dst, u64 dst_stride, u64 row0, unsigned log_n,
+               const u64* __restrict__ in_scale, u64 out_scale, Roots R) {
+  __shared__ u64 sm[256 * 17];
+  __shared__ u64 tw[128];
+  const unsigned log_nb = log_n - 8;
+  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  // load mapping: q_lo fastest (16 consecutive elements of one column / block per half warp)
+  const unsigned q_lo = threadIdx.x & 15, lane_a = threadIdx.x >> 4;
+  u64 x[16];
+  {
+    const u64* p = nullptr;
+    u64 pos0 = 0;
+    if (MODE == STORE_LEAF) {
+      const unsigned col = blockIdx.y * 16 + lane_a;
+      if (col < ncols) p = src + (u64)col * src_col_stride;
+      pos0 = (u64)blockIdx.x << 8;
+    } else {
+      p = src + (u64)blockIdx.y * src_col_stride;
+      pos0 = (u64)brev(blockIdx.x * 16 + lane_a, log_nb) << 8;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const u64 pos = pos0 + 16 * j + q_lo;
+      u64 v = 0;
+      if (p) {
+        v = gl::canon(__ldg(p + pos));
+        if (in_scale) v = gl::mul(v, __ldg(in_scale + pos));
+      }
+      x[j] = v;
+    }
+  }
+  __syncthreads();  // tw ready
+  // store mapping: lane fastest (16 consecutive columns of one row / 16 consecutive outputs)
+  const unsigned lane_b = threadIdx.x & 15, q_hi = threadIdx.x >> 4;
+  dft256_regs(x, sm, tw, 17, q_lo, lane_a, q_hi, lane_b);
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const unsigned q = 16 * q_hi + j;
+    u64 v = x[j];
+    if (out_scale != 1) v = gl::mul(v, out_scale);
+    if (MODE == STORE_LEAF) {
+      const unsigned col = blockIdx.y * 16 + lane_b;
+      const u64 pos = ((u64)blockIdx.x << 8) + q;
+      if (col < ncols) dst[(row0 + pos) * dst_stride + col] = v;
+    } else {
+      const u64 nat = ((u64)brev(q, 8) << log_nb) + (u64)blockIdx.x * 16 + lane_b;
+      dst[(u64)blockIdx.y * dst_stride + nat] = v;
+    }
+  }
+}
+
 // ---- tables ------------------------------------------------------------------------------------
 // w[t] = omega_N^t for t < N/2.
 __global__ void fill_roots(u64* w, unsigned log_N) {

@@ -173,8 +173,12 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
     if (log_T > log_sigma) log_T = log_sigma;
     const size_t smem = ((size_t)(1u << s << log_T) + (1u << s) / 2) * sizeof(u64);
     dim3 grid((unsigned)(n >> (s + log_T)), ncols);
-    ntt::pass_strided<INVERSE><<<grid, ntt::THREADS, smem, ctx->stream>>>(
-        cur, cur_stride, work, n, log_B, s, log_T, p == 0 ? in_scale : nullptr, R);
+    if (s == 8 && log_T == 4)  // 256-point pass: radix-16 register kernel
+      ntt::pass_strided_r16<INVERSE><<<grid, ntt::THREADS, 0, ctx->stream>>>(
+          cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R);
+    else
+      ntt::pass_strided<INVERSE><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+          cur, cur_stride, work, n, log_B, s, log_T, p == 0 ? in_scale : nullptr, R);
     ctx->launches++;
     cur = work;
     cur_stride = n;
@@ -187,15 +191,23 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
       const unsigned log_T = 4;
       const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
       dim3 grid((unsigned)(n >> s), (ncols + (1u << log_T) - 1) >> log_T);
-      ntt::pass_final<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, smem, ctx->stream>>>(
-          cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
+      if (s == 8)
+        ntt::pass_final_r16<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, 0, ctx->stream>>>(
+            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R);
+      else
+        ntt::pass_final<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
     } else {
       unsigned log_T = 4;
       if (log_T > log_n - s) log_T = log_n - s;
       const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
       dim3 grid((unsigned)(n >> (s + log_T)), ncols);
-      ntt::pass_final<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, smem, ctx->stream>>>(
-          cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
+      if (s == 8 && log_T == 4)
+        ntt::pass_final_r16<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, 0, ctx->stream>>>(
+            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R);
+      else
+        ntt::pass_final<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
     }
     ctx->launches++;
   }
