@@ -98,6 +98,64 @@ reduce_level(u64* __restrict__ digests, u64* __restrict__ cap, unsigned level, u
   store_hash(out, s);
 }
 
+// Levels level_from..log_sub of every cap subtree in ONE launch: one CTA per subtree, one
+// 16-thread group per node (poseidon::permute_coop), __syncthreads() between levels.  Used for the
+// top of the tree, where per-level launches of the thread-per-node kernel are latency bound
+// (~40 us per level; this kernel: ~7 us per level).
+constexpr int COOP_THREADS = 1024;
+__global__ void __launch_bounds__(COOP_THREADS)
+reduce_levels_coop(u64* __restrict__ digests, u64* __restrict__ cap, unsigned level_from,
+                   unsigned log_sub, u64 sub_digests) {
+  extern __shared__ double coop_sh[];
+  const u64 sub = blockIdx.x;
+  u64* base = digests + 4 * sub * sub_digests;
+  const unsigned group = threadIdx.x >> 4, l = threadIdx.x & 15, ngroups = blockDim.x >> 4;
+  double* sh = coop_sh + 48 * group;
+  for (unsigned level = level_from; level <= log_sub; level++) {
+    const u64 nodes = 1ULL << (log_sub - level);
+    for (u64 j0 = 0; j0 < nodes; j0 += ngroups) {  // same trip count for every thread of the CTA
+      const u64 jj = j0 + group;
+      const bool valid = jj < nodes;
+      u64 w = 0;
+      if (valid && l < 8)
+        w = __ldcg(base + 4 * (2 * ((jj << level) + (1ULL << (level - 1)) - 1)) + l);
+      // warps whose two groups both lie beyond the last node skip the work (warp-uniform branch)
+      if (j0 + (group & ~1u) < nodes) poseidon::permute_coop(w, sh, l);
+      if (valid && l < 4) {
+        u64* out = (level == log_sub)
+                       ? cap + 4 * sub
+                       : base + 4 * (2 * (((jj >> 1) << (level + 1)) + (1ULL << level) - 1) + (jj & 1));
+        out[l] = gl::canon(w);
+      }
+    }
+    __syncthreads();  // this level's digests are visible to the CTA before the next level reads them
+  }
+}
+
+// One level with one 16-thread group per node, nodes of all subtrees spread over the grid (for
+// levels with a few thousand nodes: enough CTAs to use every SM, ~4x lower latency than the
+// thread-per-node kernel).
+__global__ void __launch_bounds__(128)
+reduce_level_coop(u64* __restrict__ digests, u64* __restrict__ cap, unsigned level,
+                  unsigned log_sub, u64 sub_digests, u64 nnodes) {
+  __shared__ double sh_all[8 * 48];
+  const unsigned group = threadIdx.x >> 4, l = threadIdx.x & 15;
+  const u64 j = (u64)blockIdx.x * 8 + group;
+  const bool valid = j < nnodes;
+  const unsigned log_nodes = log_sub - level;
+  const u64 sub = j >> log_nodes, jj = j & ((1ULL << log_nodes) - 1);
+  u64* base = digests + 4 * sub * sub_digests;
+  u64 w = 0;
+  if (valid && l < 8) w = __ldcg(base + 4 * (2 * ((jj << level) + (1ULL << (level - 1)) - 1)) + l);
+  if ((u64)blockIdx.x * 8 + (group & ~1u) < nnodes) poseidon::permute_coop(w, sh_all + 48 * group, l);
+  if (valid && l < 4) {
+    u64* out = (level == log_sub)
+                   ? cap + 4 * sub
+                   : base + 4 * (2 * (((jj >> 1) << (level + 1)) + (1ULL << level) - 1) + (jj & 1));
+    out[l] = gl::canon(w);
+  }
+}
+
 // Blinding columns: leaves[k][first_col + s] = salt[s][bitrev(first_leaf + k)] (salt vectors are
 // extra lde_values() columns in natural order; they get transposed/bit-reversed like the rest).
 __global__ void scatter_salt(const u64* __restrict__ salt, u64 m, unsigned log_m, u64 first_leaf,

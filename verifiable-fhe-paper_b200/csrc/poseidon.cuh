@@ -168,6 +168,11 @@ __device__ __forceinline__ double half_to_f64(u32 x) {
 __constant__ double RCD[2 * (ROUNDS + 1) * WIDTH] = {
 #include "poseidon_rcd.inc"
 };
+// The same table in global memory for permute_coop, whose threads index it divergently (the
+// constant cache serialises distinct addresses within a warp; L1 does not).
+__device__ const double RCD_G[2 * (ROUNDS + 1) * WIDTH] = {
+#include "poseidon_rcd.inc"
+};
 
 // Input-stationary order: for each state word (converted to doubles on the fly) update all twelve
 // output accumulators.  Consecutive DFMAs then share their multiplicand, which the register reuse
@@ -230,6 +235,57 @@ __device__ __forceinline__ void permute_lazy(u64 (&s)[WIDTH]) {
     }
     s[0] = sbox7(s[0]);
     mds_add_rc(s, r + 1);
+  }
+}
+
+// ---- latency-optimised permutation: 12 threads of a 16-thread group share one state -----------
+// The top levels of a Merkle tree have too few nodes to fill the machine, and a lone thread needs
+// ~40 us per permutation (27 k dependent-ish instructions).  Here thread l (< 12) of a group owns
+// state word l: the S-boxes of a full round run in parallel, and each thread computes its own MDS
+// output from the other words' halves, exchanged as doubles through shared memory.
+// `sh` = 48 doubles of shared memory private to the group (low halves at [0,24), high halves at
+// [24,48), each stored twice so that the rotation (l + i) needs no wrap-around).
+// All 32 threads of the warp must call this together (it uses __syncwarp()).
+__device__ __forceinline__ void permute_coop(u64& w, double* __restrict__ sh, unsigned l) {
+  const bool active = l < WIDTH;
+  const unsigned ll = active ? l : 0;
+  if (active) {  // RC[l] = (lo32, hi32) parts of row 0 of RCD_G minus the 2^52 bias
+    const double2 rc0 = __ldg(reinterpret_cast<const double2*>(RCD_G) + ll);
+    const u64 c = ((u64)(u32)__double2loint(rc0.y) << 32) | (u32)__double2loint(rc0.x);
+    w = gl::add_lazy(w, c);
+  }
+  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
+  constexpr double CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+#pragma unroll 1
+  for (int r = 0; r < ROUNDS; r++) {
+    const bool full = r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS;
+    if (active && (full || l == 0)) w = sbox7(w);
+    if (active) {
+      const double dl = half_to_f64((u32)w), dh = half_to_f64((u32)(w >> 32));
+      sh[l] = dl;
+      sh[l + 12] = dl;
+      sh[24 + l] = dh;
+      sh[36 + l] = dh;
+    }
+    __syncwarp();
+    if (active) {
+      const double2 rc2 = __ldg(reinterpret_cast<const double2*>(RCD_G) + (WIDTH * (r + 1) + ll));
+      double al0 = rc2.x, ah0 = rc2.y, al1 = 0.0, ah1 = 0.0;  // two chains each: shorter latency
+#pragma unroll
+      for (int i = 0; i < WIDTH; i += 2) {
+        al0 = fma(sh[l + i], CIRC[i], al0);
+        ah0 = fma(sh[24 + l + i], CIRC[i], ah0);
+        al1 = fma(sh[l + i + 1], CIRC[i + 1], al1);
+        ah1 = fma(sh[24 + l + i + 1], CIRC[i + 1], ah1);
+      }
+      if (l == 0) {  // MDS_MATRIX_DIAG = [8, 0, ..., 0]
+        al1 = fma(sh[0], 8.0, al1);
+        ah1 = fma(sh[24], 8.0, ah1);
+      }
+      w = reduce96((u64)__double_as_longlong(al0 + al1) & MANT,
+                   (u64)__double_as_longlong(ah0 + ah1) & MANT);
+    }
+    __syncwarp();
   }
 }
 

@@ -235,10 +235,33 @@ int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, uns
       d_leaves, nleaves, width, all_cap ? d_roots : d_digests, log_sub, sub_digests, all_cap);
   ctx->launches++;
   if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
+  // Big levels: one thread per node, one launch per level.  Levels with at most 4096 nodes in
+  // total use one 16-thread group per node (lower latency); once a subtree is down to 16 nodes
+  // the rest of the tree runs in ONE launch (one CTA per subtree, no launch gaps).
+  unsigned total_log = 0;
+  while ((1ULL << total_log) < nleaves) total_log++;
+  const unsigned coop_from = total_log > 12 ? total_log - 12 : 1;   // first level with <= 4096 nodes
+  unsigned fused_from = log_sub > 4 ? log_sub - 4 : 1;               // <= 16 nodes per subtree
+  if (fused_from < coop_from) fused_from = coop_from;
+  const bool fuse = nsub <= 4096;
   for (unsigned level = 1; level <= log_sub; level++) {
     const u64 nnodes = nsub << (log_sub - level);
-    merkle::reduce_level<<<(unsigned)((nnodes + 127) / 128), 128, 0, ctx->stream>>>(
-        d_digests, d_roots, level, log_sub, sub_digests, nnodes);
+    if (fuse && level >= fused_from) {
+      const u64 nodes0 = 1ULL << (log_sub - level);
+      unsigned threads = (unsigned)(nodes0 * 16 < 32 ? 32 : nodes0 * 16);
+      if (threads > merkle::COOP_THREADS) threads = merkle::COOP_THREADS;
+      const size_t smem = (size_t)(threads / 16) * 48 * sizeof(double);
+      merkle::reduce_levels_coop<<<(unsigned)nsub, threads, smem, ctx->stream>>>(
+          d_digests, d_roots, level, log_sub, sub_digests);
+      ctx->launches++;
+      break;
+    }
+    if (level >= coop_from)
+      merkle::reduce_level_coop<<<(unsigned)((nnodes + 7) / 8), 128, 0, ctx->stream>>>(
+          d_digests, d_roots, level, log_sub, sub_digests, nnodes);
+    else
+      merkle::reduce_level<<<(unsigned)((nnodes + 127) / 128), 128, 0, ctx->stream>>>(
+          d_digests, d_roots, level, log_sub, sub_digests, nnodes);
     ctx->launches++;
   }
   CU(ctx, cudaGetLastError());
