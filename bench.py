@@ -335,25 +335,16 @@ def main():
     int_peak = SM_COUNT * IMAD_WIDE_LANES_PER_CLK_PER_SM * sm_max * 1e6 / 1e9  # G IMAD.WIDE/s
     int_ach = leaf_perms * IMAD_PER_PERMUTATION / (leaf_ms * 1e-3) / 1e9
     leaf_bytes = 8 * m * NCOLS + 32 * m
-    lde_bytes = 8 * NCOLS * n * 2 + 8 * NCOLS * m  # values in, coeffs out, leaves out
-    roofline = {
-        "kernel": "merkle::hash_leaves (Poseidon sponge over 2^19 rows x 128, one leaf per thread)",
-        "bound": "int", "achieved": int_ach, "peak": int_peak, "unit": "G IMAD.WIDE.U32-equivalent/s",
-        "frac": int_ach / int_peak,
-        "how": "algorithmic 32x32->64 MACs (SURVEY.md §8(d): %d per permutation x %d permutations per "
-               "launch) / mean launch duration from CUDA events on the launching stream; peak = 148 SM"
-               " x 64 IMAD.WIDE lanes/clk (measured, profiles/microbench_r1.jsonl) x sm_max_mhz"
-               % (IMAD_PER_PERMUTATION, leaf_perms),
-        "launch_ms": leaf_ms, "permutations_per_launch": leaf_perms,
-        "hbm_frac": leaf_bytes / (leaf_ms * 1e-3) / 1e9 / hbm_peak,
-        "traffic": traffic.get("hash_leaves_dram_bytes"),
-    }
+    lde_bytes = 8 * NCOLS * n + 8 * NCOLS * m  # coefficients in (once), leaves out
     roofline_hbm = {
-        "kernels": "ntt::pass_strided / ntt::pass_final (IFFT + coset LDE + fused transpose)",
-        "bound": "hbm", "achieved": lde_bytes / ((ifft_ms + fft_ms) * 1e-3) / 1e9, "peak": hbm_peak,
-        "unit": "GB/s", "frac": lde_bytes / ((ifft_ms + fft_ms) * 1e-3) / 1e9 / hbm_peak,
-        "peak_source": hbm_src, "algorithmic_bytes": lde_bytes, "ms": ifft_ms + fft_ms,
-        "traffic": traffic.get("ntt_dram_bytes"),
+        "kernels": "ntt::pass_strided_r16<fwd> + ntt::pass_final_r16<fwd, leaf> x 8 LDE blocks (coset LDE "
+                   "with fused transpose / bit-reversal; phase \"FFT + blinding\" + \"transpose LDEs\")",
+        "bound": "hbm", "achieved": lde_bytes / (fft_ms * 1e-3) / 1e9, "peak": hbm_peak,
+        "unit": "GB/s", "frac": lde_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
+        "peak_source": hbm_src, "algorithmic_bytes": lde_bytes, "ms": fft_ms,
+        "traffic": traffic.get("lde_forward_dram_bytes"),
+        "note": "ncu shows these kernels ALU-pipe bound (72 % alu, 57 % issue), not DRAM bound: "
+                "profiles/r1_ntt_r16_kernels.txt",
     }
     whole = {"algorithmic_bytes": algorithmic_bytes(NCOLS, n, RATE_BITS, CAP_HEIGHT),
              "permutations": permutations(NCOLS, n, RATE_BITS, CAP_HEIGHT),

@@ -405,3 +405,29 @@ def test_sharded_commit_over_nccl(V):
         p.join(timeout=300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_randomized_shapes_against_oracle(V, ctx, oracle):
+    """SURVEY.md §4 test plan (iii): random (log_n, cols, rate_bits, cap_height, from_values/coeffs)
+    with seeded inputs incl. non-canonical words, sizes bounded so the oracle stays fast."""
+    rnd = random.Random(20240451)
+    rng = np.random.default_rng(20240451)
+    done = 0
+    while done < 48:
+        log_n = rnd.randint(0, 17)
+        ncols = rnd.choice([1, 3, 4, 5, 8, 9, 16, 20, 33, 128, 135])
+        r = rnd.randint(0, 3)
+        if (ncols << (log_n + r)) > (1 << 23):
+            continue
+        h = rnd.randint(0, log_n + r)
+        coeffs = rnd.random() < 0.35
+        cols = rand_u64(rng, (ncols, 1 << log_n), 0.05)
+        f = V.PolynomialBatch.from_coeffs if coeffs else V.PolynomialBatch.from_values
+        b = f(cols, r, False, h, ctx=ctx)
+        ref = oracle.commit(cols, r, h, coeffs)
+        tag = (log_n, ncols, r, h, coeffs)
+        assert np.array_equal(b.merkle_tree.cap, ref["cap"]), tag
+        assert np.array_equal(b.merkle_tree.digests, ref["digests"]), tag
+        assert np.array_equal(b.merkle_tree.leaves, ref["leaves"]), tag
+        assert np.array_equal(b.polynomials, ref["coeffs"]), tag
+        done += 1

@@ -174,6 +174,7 @@ __device__ const double RCD_G[2 * (ROUNDS + 1) * WIDTH] = {
 #include "poseidon_rcd.inc"
 };
 
+#ifdef VPBS_MDS_FP64_DENSE
 // Input-stationary order: for each state word (converted to doubles on the fly) update all twelve
 // output accumulators.  Consecutive DFMAs then share their multiplicand, which the register reuse
 // cache serves without a second register-file read (a DFMA with three distinct 64-bit register
@@ -218,6 +219,114 @@ __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
     s[r] = reduce96((u64)__double_as_longlong(al[r]) & MANT, (u64)__double_as_longlong(ah[r]) & MANT);
 }
 
+#else  // split-convolution FP64 MDS (default)
+
+// The MDS matrix is circulant (plus one diagonal entry), i.e. y = c (*) s is a length-12 cyclic
+// convolution.  x^12 - 1 = (x^6 - 1)(x^6 + 1) splits it into a cyclic and a negacyclic length-6
+// convolution on p_t = s_t + s_{t+6} and m_t = s_t - s_{t+6}:
+//     Z+_r = sum_j (c_j + c_{j+6}) p_{(j+r) mod 6},   Z-_r = sum_j (+-)(c_j - c_{j+6}) m_{(j+r) mod 6}
+//     2 y_r = Z+_r + Z-_r,   2 y_{r+6} = Z+_r - Z-_r                      (r < 6)
+// 144 DFMA per round instead of 288 (plus 24 + 48 adds).  The FP64 pipe is what bounds the 22
+// partial rounds (ncu: one warp instruction per two cycles), so this is where the time goes.
+// Everything stays exact: |Z| < 2^42, the sums are even, and fma(S, 0.5, 2^52) halves and biases
+// in one step so that the mantissa is the integer result.
+// RCS[24 * round + 4 * r + {0,1,2,3}] = {lo+, lo-, hi+, hi-} sums/differences of the 32-bit halves
+// of RC[r], RC[r+6] (row 30 = zeros).
+__constant__ double RCS[(ROUNDS + 1) * 24] = {
+#include "poseidon_rcs.inc"
+};
+
+namespace mds_split {
+constexpr int CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+__host__ __device__ constexpr double cplus(int j) { return (double)(CIRC[j] + CIRC[j + 6]); }
+__host__ __device__ constexpr double cminus(int j) { return (double)(CIRC[j] - CIRC[j + 6]); }
+
+// input t (p_t, m_t) into every accumulator r: the term j with (j + r) mod 6 == t
+template <int T, int R>
+__device__ __forceinline__ void col(double pl, double ph, double ml, double mh, double (&zpl)[6],
+                                    double (&zph)[6], double (&zml)[6], double (&zmh)[6]) {
+  constexpr int J = (T - R + 6) % 6;
+  constexpr double CP = cplus(J);
+  constexpr double CM = (J + R < 6) ? cminus(J) : -cminus(J);
+  zpl[R] = fma(pl, CP, zpl[R]);
+  zph[R] = fma(ph, CP, zph[R]);
+  zml[R] = fma(ml, CM, zml[R]);
+  zmh[R] = fma(mh, CM, zmh[R]);
+  if constexpr (R + 1 < 6) col<T, R + 1>(pl, ph, ml, mh, zpl, zph, zml, zmh);
+}
+template <int T>
+__device__ __forceinline__ void cols(const u64 (&s)[WIDTH], double (&zpl)[6], double (&zph)[6],
+                                     double (&zml)[6], double (&zmh)[6], double& x0l, double& x0h) {
+  const double al = half_to_f64((u32)s[T]), ah = half_to_f64((u32)(s[T] >> 32));
+  const double bl = half_to_f64((u32)s[T + 6]), bh = half_to_f64((u32)(s[T + 6] >> 32));
+  if constexpr (T == 0) {
+    x0l = al;
+    x0h = ah;
+  }
+  // (forming p, m on the integer side with carry into the exponent word was tried: the carry
+  // costs ISETP + SEL per value and measured 1 % slower than these four DADDs)
+  col<T, 0>(al + bl, ah + bh, al - bl, ah - bh, zpl, zph, zml, zmh);
+  if constexpr (T + 1 < 6) cols<T + 1>(s, zpl, zph, zml, zmh, x0l, x0h);
+}
+}  // namespace mds_split
+
+struct MdsAcc {
+  double zpl[6], zph[6], zml[6], zmh[6], x0l, x0h;
+};
+__device__ __forceinline__ void mds_begin(MdsAcc& a, int next_round) {
+  const double4* __restrict__ rcs = reinterpret_cast<const double4*>(RCS) + 6 * next_round;
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const double4 c = rcs[r];
+    a.zpl[r] = c.x;
+    a.zml[r] = c.y;
+    a.zph[r] = c.z;
+    a.zmh[r] = c.w;
+  }
+}
+// feed state words T and T + 6 (final for this round) into all accumulators
+template <int T>
+__device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
+  const double al = half_to_f64((u32)s[T]), ah = half_to_f64((u32)(s[T] >> 32));
+  const double bl = half_to_f64((u32)s[T + 6]), bh = half_to_f64((u32)(s[T + 6] >> 32));
+  if constexpr (T == 0) {
+    a.x0l = al;
+    a.x0h = ah;
+  }
+  mds_split::col<T, 0>(al + bl, ah + bh, al - bl, ah - bh, a.zpl, a.zph, a.zml, a.zmh);
+}
+__device__ __forceinline__ void mds_finish(MdsAcc& a, u64 (&s)[WIDTH]) {
+  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
+  const double BIAS = 4503599627370496.0;  // 2^52
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    double s1l = a.zpl[r] + a.zml[r], s1h = a.zph[r] + a.zmh[r];        // 2 y_r
+    const double s2l = a.zpl[r] - a.zml[r], s2h = a.zph[r] - a.zmh[r];  // 2 y_{r+6}
+    if (r == 0) {  // MDS_MATRIX_DIAG = [8, 0, ..., 0] (doubled)
+      s1l = fma(a.x0l, 16.0, s1l);
+      s1h = fma(a.x0h, 16.0, s1h);
+    }
+    s[r] = reduce96((u64)__double_as_longlong(fma(s1l, 0.5, BIAS)) & MANT,
+                    (u64)__double_as_longlong(fma(s1h, 0.5, BIAS)) & MANT);
+    s[r + 6] = reduce96((u64)__double_as_longlong(fma(s2l, 0.5, BIAS)) & MANT,
+                        (u64)__double_as_longlong(fma(s2h, 0.5, BIAS)) & MANT);
+  }
+}
+#define VPBS_MDS_INTERLEAVED 1
+// The whole layer in one call (tests, tools/selftest.cu).
+__device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
+  MdsAcc acc;
+  mds_begin(acc, next_round);
+  mds_absorb<0>(acc, s);
+  mds_absorb<1>(acc, s);
+  mds_absorb<2>(acc, s);
+  mds_absorb<3>(acc, s);
+  mds_absorb<4>(acc, s);
+  mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+}
+
+#endif  // VPBS_MDS_FP64_DENSE
 #endif  // VPBS_MDS_INT32
 
 // In-place permutation; input words arbitrary u64, output words arbitrary u64 (lazy).
@@ -229,12 +338,34 @@ __device__ __forceinline__ void permute_lazy(u64 (&s)[WIDTH]) {
   for (int i = 0; i < WIDTH; i++) s[i] = gl::add_lazy(s[i], RC[i]);
 #pragma unroll 1
   for (int r = 0; r < ROUNDS; r++) {
-    if (r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS) {
+    const bool full = r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS;
+#ifdef VPBS_MDS_INTERLEAVED
+    // S-boxes (integer pipes) and MDS accumulation (FP64 pipe) interleaved pair by pair: as soon as
+    // words t and t + 6 are final they are fed to the accumulators.
+    MdsAcc acc;
+    mds_begin(acc, r + 1);
+    s[0] = sbox7(s[0]);
+    if (full) s[6] = sbox7(s[6]);
+    mds_absorb<0>(acc, s);
+    if (full) { s[1] = sbox7(s[1]); s[7] = sbox7(s[7]); }
+    mds_absorb<1>(acc, s);
+    if (full) { s[2] = sbox7(s[2]); s[8] = sbox7(s[8]); }
+    mds_absorb<2>(acc, s);
+    if (full) { s[3] = sbox7(s[3]); s[9] = sbox7(s[9]); }
+    mds_absorb<3>(acc, s);
+    if (full) { s[4] = sbox7(s[4]); s[10] = sbox7(s[10]); }
+    mds_absorb<4>(acc, s);
+    if (full) { s[5] = sbox7(s[5]); s[11] = sbox7(s[11]); }
+    mds_absorb<5>(acc, s);
+    mds_finish(acc, s);
+#else
+    if (full) {
 #pragma unroll
       for (int i = 1; i < WIDTH; i++) s[i] = sbox7(s[i]);
     }
     s[0] = sbox7(s[0]);
     mds_add_rc(s, r + 1);
+#endif
   }
 }
 
