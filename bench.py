@@ -175,6 +175,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-commit", action="store_true",
+                    help="strong scaling of ONE commit: every rank computes its row range "
+                         "(vpbs_commit_shard_dev) and the subtree roots are all-gathered over NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,7 +200,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     V.build.build()
     ctx = V.Context(local_rank)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # one explicit (non-default) stream for the library's kernels, the timing events and NCCL:
+    # a NULL stream handle means "the context's own stream" to vpbs_ctx_set_stream
+    bench_stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(bench_stream)
+    ctx.set_stream(bench_stream.cuda_stream)
 
     n, m = 1 << LOG_N, (1 << LOG_N) << RATE_BITS
     ncap = 1 << CAP_HEIGHT
@@ -225,6 +232,9 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.shard_commit:
+        return run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks)
 
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
@@ -336,6 +346,19 @@ def main():
     int_ach = leaf_perms * IMAD_PER_PERMUTATION / (leaf_ms * 1e-3) / 1e9
     leaf_bytes = 8 * m * NCOLS + 32 * m
     lde_bytes = 8 * NCOLS * n + 8 * NCOLS * m  # coefficients in (once), leaves out
+    roofline = {
+        "kernel": "merkle::hash_leaves (Poseidon sponge over 2^19 rows x 128, one leaf per thread)",
+        "share_of_step": leaf_ms / ms_per_step,
+        "bound": "int", "achieved": int_ach, "peak": int_peak, "unit": "G IMAD.WIDE.U32-equivalent/s",
+        "frac": int_ach / int_peak,
+        "how": "algorithmic 32x32->64 MACs (SURVEY.md §8(d): %d per permutation x %d permutations per "
+               "launch) / mean launch duration from CUDA events on the launching stream; peak = 148 SM"
+               " x 64 IMAD.WIDE lanes/clk (measured, profiles/microbench_r1.jsonl) x sm_max_mhz"
+               % (IMAD_PER_PERMUTATION, leaf_perms),
+        "launch_ms": leaf_ms, "permutations_per_launch": leaf_perms,
+        "hbm_frac": leaf_bytes / (leaf_ms * 1e-3) / 1e9 / hbm_peak,
+        "traffic": traffic.get("hash_leaves_dram_bytes"),
+    }
     roofline_hbm = {
         "kernels": "ntt::pass_strided_r16<fwd> + ntt::pass_final_r16<fwd, leaf> x 8 LDE blocks (coset LDE "
                    "with fused transpose / bit-reversal; phase \"FFT + blinding\" + \"transpose LDEs\")",
@@ -391,6 +414,37 @@ def main():
     for p in (p0, p1, p2, p3, p4):
         lib.vpbs_host_free(p)
     if world > 1:
+        dist.destroy_process_group()
+
+
+def run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks):
+    """One 2^16 x 128 commit split by row range over all ranks (SURVEY.md §8(e) partitioning B):
+    every rank holds all columns, computes m / world leaves + their digests, and only the subtree
+    roots (32 B per cap entry) are exchanged.  Strong scaling; prints its own JSON line."""
+    import torch
+    # every rank must commit the SAME batch
+    cols = torch.from_numpy(V.synthetic_columns(NCOLS, 1 << LOG_N, seed=0x5EED0000).view("int64")).to(dev)
+    for _ in range(args.warmup):
+        V.commit_sharded(ctx, cols, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, False, rank, world)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        plan, leaves, digests, cap, coeffs, _ = V.commit_sharded(ctx, cols, NCOLS, LOG_N, RATE_BITS,
+                                                                 CAP_HEIGHT, False, rank, world)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC + " — ONE commit sharded by row range", "value": (1 << LOG_N) / (ms * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": workload_config(world),
+            "collective": "all_gather of %d subtree roots per rank (NCCL)" % plan.ncap,
+            "cap0": "%016x" % (int(cap[0, 0].item()) & (2**64 - 1))}))
+    if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 

@@ -92,3 +92,44 @@ def test_reverse_bits_and_synthetic_inputs(V):
     assert not np.array_equal(a[0], a[1])
     raw = V.synthetic_columns(3, 16, canonical=False)
     assert np.array_equal(raw % np.uint64(V.P), a)
+
+
+def test_bench_and_entry_have_no_undefined_names():
+    """bench.py only runs on the GPU box: catch NameErrors (e.g. a dropped assignment) on CPU."""
+    import ast
+    import builtins
+    for fname in ("bench.py", "__graft_entry__.py"):
+        tree = ast.parse(open(os.path.join(ROOT, fname)).read())
+        module_names = set(dir(builtins))
+        for node in tree.body:
+            if isinstance(node, (ast.FunctionDef, ast.ClassDef)):
+                module_names.add(node.name)
+            elif isinstance(node, (ast.Import, ast.ImportFrom)):
+                module_names.update((a.asname or a.name).split(".")[0] for a in node.names)
+            elif isinstance(node, ast.Assign):
+                for t in node.targets:
+                    module_names.update(n.id for n in ast.walk(t) if isinstance(n, ast.Name))
+        for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+            assigned = set(module_names)
+            for n in ast.walk(fn):
+                if isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+                    assigned.add(n.id)
+                elif isinstance(n, ast.arg):
+                    assigned.add(n.arg)
+                elif isinstance(n, (ast.Import, ast.ImportFrom)):
+                    assigned.update((a.asname or a.name).split(".")[0] for a in n.names)
+                elif isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                    assigned.add(n.name)
+                elif isinstance(n, ast.ExceptHandler) and n.name:
+                    assigned.add(n.name)
+            missing = {n.id for n in ast.walk(fn)
+                       if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)} - assigned
+            assert not missing, "%s: %s uses undefined names %s" % (fname, fn.name, sorted(missing))
+
+
+def test_bench_help_runs():
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and "--impl" in out.stdout

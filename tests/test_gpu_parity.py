@@ -312,7 +312,7 @@ def test_row_range_shards_equal_full_commit(V, ctx, oracle, log_n, ncols, rate_b
     cols = V.synthetic_columns(ncols, 1 << log_n, seed=31337)
     ref = oracle.commit(cols, rate_bits, cap_height)
     d_cols = torch.from_numpy(cols.view(np.int64)).cuda()
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
     caps = []
     for rank in range(world):
         plan, leaves, digests, cap, coeffs, _ = _one_shard(V, ctx, d_cols, ncols, log_n, rate_bits,
@@ -325,7 +325,6 @@ def test_row_range_shards_equal_full_commit(V, ctx, oracle, log_n, ncols, rate_b
         assert np.array_equal(coeffs.cpu().numpy().view(np.uint64), ref["coeffs"])
         caps.append(cap.cpu().numpy().view(np.uint64))
     assert np.array_equal(np.concatenate(caps), ref["cap"])
-    ctx.set_stream(0)
 
 
 def _one_shard(V, ctx, d_cols, ncols, log_n, rate_bits, cap_height, rank, world):
@@ -367,7 +366,9 @@ def _nccl_worker(rank, world, port, q):
     import vfhe_b200 as V
     from oracle import binding as B
     c = V.Context(rank)
-    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    c.set_stream(stream.cuda_stream)
     log_n, ncols, r, h = 12, 20, 3, 4
     cols = V.synthetic_columns(ncols, 1 << log_n, seed=5)
     d_cols = torch.from_numpy(cols.view(np.int64)).cuda()
