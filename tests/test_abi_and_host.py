@@ -109,7 +109,7 @@ def test_bench_and_entry_have_no_undefined_names():
             elif isinstance(node, ast.Assign):
                 for t in node.targets:
                     module_names.update(n.id for n in ast.walk(t) if isinstance(n, ast.Name))
-        for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:  # closures share scope
             assigned = set(module_names)
             for n in ast.walk(fn):
                 if isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
