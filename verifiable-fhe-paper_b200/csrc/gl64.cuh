@@ -88,8 +88,8 @@ __host__ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
       "subc.u32 bm, 0, 0;\n\t"               // 0xffffffff on borrow
       "sub.cc.u32 t0, t0, bm;\n\t"           // borrow: t -= 2^32 - 1 (i.e. += p)
       "subc.u32 t1, t1, 0;\n\t"
-      "mul.wide.u32 w, h0, 0xffffffff;\n\t"  // h0 * (2^32 - 1)
-      "mov.b64 {e0, e1}, w;\n\t"
+      "sub.cc.u32 e0, 0, h0;\n\t"            // h0 * (2^32 - 1) = {-h0, h0 - (h0 != 0)}: two ALU ops
+      "subc.u32 e1, h0, 0;\n\t"              // instead of a half-rate IMAD.WIDE on the busiest pipe
       "add.cc.u32 t0, t0, e0;\n\t"
       "addc.cc.u32 t1, t1, e1;\n\t"
       "addc.u32 bm, 0, 0;\n\t"               // carry (0/1); NB: subc after add.cc sees CF inverted

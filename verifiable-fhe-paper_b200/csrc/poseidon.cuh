@@ -49,8 +49,10 @@ __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
       ".reg .u32 hl, hh, t0, t1, bm;\n\t"
       ".reg .u64 t;\n\t"
       "mov.b64 {hl, hh}, %3;\n\t"
-      "mad.wide.u32 t, hh, 0xffffffff, %2;\n\t"  // < 2^56: no carry
-      "mov.b64 {t0, t1}, t;\n\t"
+      "mov.b64 {t0, t1}, %2;\n\t"
+      "sub.cc.u32 t0, t0, hh;\n\t"               // lo + hh * (2^32 - 1) = lo - hh + (hh << 32)
+      "subc.u32 t1, t1, 0;\n\t"                  // (exact mod 2^64; the true value is < 2^56)
+      "add.u32 t1, t1, hh;\n\t"
       "add.cc.u32 t1, t1, hl;\n\t"
       "addc.u32 bm, 0, 0;\n\t"                   // carry (0/1)
       "neg.s32 bm, bm;\n\t"                      // 0xffffffff on carry
