@@ -296,6 +296,34 @@ def main():
     h2d_bytes = 8 * NCOLS * n
     d2h_bytes = 8 * NCOLS * n + 8 * m * NCOLS + 32 * 2 * (m - ncap) + 32 * ncap
     cap_matches = bool(np.array_equal(h_cap.view(np.int64), d_cap.cpu().numpy()))
+
+    # ---- the same call with the batch left in HBM (vpbs_batch_*): only the cap crosses PCIe at
+    # commit time; the 28 FRI-query rows + Merkle paths of a proof are fetched on demand
+    query_idx = np.random.default_rng(7).integers(0, m, size=28, dtype=np.uint64)
+    res_cap = np.empty((ncap, 4), np.uint64)
+    res_rows = np.empty((28, NCOLS), np.uint64)
+    res_sib = np.empty((28, LOG_N + RATE_BITS - CAP_HEIGHT, 4), np.uint64)
+
+    def resident_step():
+        h = ctypes.c_void_p()
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, colp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None,
+                                        res_cap.ctypes.data_as(u64p), ctypes.byref(h), None))
+        ctx.check(lib.vpbs_batch_get_leaves(h, query_idx.ctypes.data_as(u64p), 28,
+                                            res_rows.ctypes.data_as(u64p)))
+        ctx.check(lib.vpbs_batch_prove(h, query_idx.ctypes.data_as(u64p), 28,
+                                       res_sib.ctypes.data_as(u64p)))
+        lib.vpbs_batch_destroy(h)
+
+    for _ in range(2):
+        resident_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        resident_step()
+    torch.cuda.synchronize()
+    res_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    resident_ok = bool(np.array_equal(res_cap, h_cap) and np.array_equal(res_rows, h_leaves[query_idx]))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the N=1024 step stand-in (BASELINE.json configs[2]): wires / Z / quotient commits
@@ -406,6 +434,13 @@ def main():
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.e2e_steps * 1e3,
                 "steps": args.e2e_steps, "api": "vpbs_commit (host C ABI, pinned buffers)",
                 "phase_ms_last": e2e_stats.as_dict(), "cap_matches_device_path": cap_matches},
+        "e2e_resident": {"value": world * args.e2e_steps * n / res_s, "unit": UNIT,
+                         "ms_per_step": res_s / args.e2e_steps * 1e3,
+                         "h2d_bytes_per_step": h2d_bytes,
+                         "d2h_bytes_per_step": 32 * ncap + 28 * (8 * NCOLS + 32 * (LOG_N + RATE_BITS - CAP_HEIGHT)),
+                         "api": "vpbs_batch_commit + 28 x (vpbs_batch_get_leaves, vpbs_batch_prove): batch "
+                                "stays in HBM, cap + queried rows/paths only",
+                         "matches_eager_path": resident_ok},
         "step_standin": step_standin,
         "gpu_launches": int(launches),
         "clocks": clocks,

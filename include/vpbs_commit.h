@@ -166,6 +166,31 @@ int vpbs_commit_shard_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols,
                           uint64_t* d_leaves_out, uint64_t* d_digests_out, uint64_t* d_roots_out,
                           vpbs_stats* stats);
 
+/* ---- device-resident batches (keep the LDE in HBM, open lazily) ---------
+ * vpbs_batch_commit is vpbs_commit that returns only the cap and KEEPS coefficients, leaves and
+ * digests in device memory owned by the handle.  The readers below serve what plonky2 reads later
+ * from a PolynomialBatch: [P2] hash/merkle_tree.rs MerkleTree::get / prove and fri/oracle.rs
+ * get_lde_values (28 FRI queries x 4 batches per proof), so the m x width leaf matrix need not
+ * cross PCIe for batches that are only opened (the quotient and FRI commits). */
+typedef struct vpbs_batch vpbs_batch;
+int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                      uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                      const uint64_t* const* salt_cols, uint64_t* cap_out, vpbs_batch** out,
+                      vpbs_stats* stats);
+void vpbs_batch_destroy(vpbs_batch* batch);
+/* rows_out: count x width, row i = leaf leaf_indices[i] (salt columns included). */
+int vpbs_batch_get_leaves(vpbs_batch* batch, const uint64_t* leaf_indices, uint64_t count,
+                          uint64_t* rows_out);
+/* siblings_out: count x (log2 m - cap_height) hashes, MerkleProof.siblings of each leaf. */
+int vpbs_batch_prove(vpbs_batch* batch, const uint64_t* leaf_indices, uint64_t count,
+                     uint64_t* siblings_out);
+/* Bulk download of what vpbs_commit returns eagerly; any pointer may be NULL. */
+int vpbs_batch_download(vpbs_batch* batch, uint64_t* const* coeffs_out, uint64_t* leaves_out,
+                        uint64_t* digests_out);
+/* Shape of the batch: m = 2^(log_n + rate_bits) leaves of `width` elements. */
+int vpbs_batch_shape(vpbs_batch* batch, uint32_t* ncols, uint32_t* log_n, uint32_t* rate_bits,
+                     uint32_t* cap_height, uint32_t* width);
+
 #ifdef __cplusplus
 }
 #endif

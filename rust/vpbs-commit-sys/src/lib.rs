@@ -13,6 +13,11 @@ pub struct vpbs_ctx {
 }
 
 #[repr(C)]
+pub struct vpbs_batch {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
 #[derive(Default, Debug, Clone, Copy)]
 pub struct vpbs_stats {
     pub h2d_ms: f32,
@@ -69,6 +74,20 @@ extern "C" {
                                  first_leaf: u64, nleaves_shard: u64, d_coeffs_out: *mut u64,
                                  d_leaves_out: *mut u64, d_digests_out: *mut u64,
                                  d_roots_out: *mut u64, stats: *mut vpbs_stats) -> c_int;
+    // device-resident batches: only the cap crosses PCIe at commit time; rows / paths on demand
+    pub fn vpbs_batch_commit(ctx: *mut vpbs_ctx, cols: *const *const u64, ncols: u32, log_n: u32,
+                             rate_bits: u32, cap_height: u32, inputs_are_coeffs: c_int,
+                             salt_cols: *const *const u64, cap_out: *mut u64,
+                             out: *mut *mut vpbs_batch, stats: *mut vpbs_stats) -> c_int;
+    pub fn vpbs_batch_destroy(batch: *mut vpbs_batch);
+    pub fn vpbs_batch_get_leaves(batch: *mut vpbs_batch, leaf_indices: *const u64, count: u64,
+                                 rows_out: *mut u64) -> c_int;
+    pub fn vpbs_batch_prove(batch: *mut vpbs_batch, leaf_indices: *const u64, count: u64,
+                            siblings_out: *mut u64) -> c_int;
+    pub fn vpbs_batch_download(batch: *mut vpbs_batch, coeffs_out: *const *mut u64,
+                               leaves_out: *mut u64, digests_out: *mut u64) -> c_int;
+    pub fn vpbs_batch_shape(batch: *mut vpbs_batch, ncols: *mut u32, log_n: *mut u32,
+                            rate_bits: *mut u32, cap_height: *mut u32, width: *mut u32) -> c_int;
 }
 
 /// One device context (device arena + stream), reused across the 730 step proofs of a PBS.

@@ -432,3 +432,37 @@ def test_randomized_shapes_against_oracle(V, ctx, oracle):
         assert np.array_equal(b.merkle_tree.leaves, ref["leaves"]), tag
         assert np.array_equal(b.polynomials, ref["coeffs"]), tag
         done += 1
+
+
+@pytest.mark.parametrize("log_n,ncols,rate_bits,cap_height,coeffs,salted", [
+    (10, 135, 3, 4, False, False), (12, 16, 3, 4, True, False), (6, 20, 3, 9, False, False),
+    (8, 9, 2, 0, False, True), (0, 5, 3, 1, False, False)])
+def test_resident_batch_lazy_openings(V, ctx, oracle, log_n, ncols, rate_bits, cap_height, coeffs, salted):
+    """vpbs_batch_*: commit stays in HBM; rows and Merkle paths fetched on demand match the oracle's
+    leaves / MerkleTree::prove, verify against the cap, and download() equals the eager commit."""
+    rng = np.random.default_rng(log_n * 31 + ncols)
+    cols = rand_u64(rng, (ncols, 1 << log_n))
+    m = (1 << log_n) << rate_bits
+    salt = rand_u64(rng, (4, m)) if salted else None
+    rb = V.commit_resident(cols, rate_bits, salted, cap_height, coeffs, ctx=ctx, salt=salt)
+    ref = oracle.commit(cols, rate_bits, cap_height, coeffs, salt)
+    assert np.array_equal(rb.merkle_tree.cap, ref["cap"])
+    idx = rng.integers(0, m, size=min(28, m), dtype=np.uint64)
+    rows = rb.merkle_tree.get_many(idx)
+    proofs = rb.merkle_tree.prove_many(idx)
+    for k, i in enumerate(idx):
+        i = int(i)
+        assert np.array_equal(rows[k], ref["leaves"][i])
+        assert np.array_equal(proofs[k].siblings, oracle.merkle_prove(ref["digests"], m, cap_height, i))
+        assert oracle.merkle_verify(rows[k], i, proofs[k].siblings, ref["cap"])
+    j = int(idx[0])
+    nat = V.reverse_bits(j, log_n + rate_bits)
+    assert np.array_equal(rb.get_lde_values(nat), ref["leaves"][j][:ncols])
+    eager = rb.download()
+    assert np.array_equal(eager.merkle_tree.leaves, ref["leaves"])
+    assert np.array_equal(eager.merkle_tree.digests, ref["digests"])
+    if not coeffs:
+        assert np.array_equal(eager.polynomials, ref["coeffs"])
+    with pytest.raises(ValueError):
+        rb.merkle_tree.get(m)
+    rb.close()

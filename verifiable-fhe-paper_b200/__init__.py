@@ -7,7 +7,8 @@ The directory name is not a Python identifier; import it through the root module
 from . import _lib, build, sharding  # noqa: F401
 from ._lib import VpbsError, VpbsStats  # noqa: F401
 from .plonky2_api import (  # noqa: F401
-    COSET_SHIFT, P, SALT_SIZE, Context, MerkleProof, MerkleTree, PolynomialBatch, coset_fft,
+    COSET_SHIFT, P, SALT_SIZE, Context, MerkleProof, MerkleTree, PolynomialBatch,
+    ResidentMerkleTree, ResidentPolynomialBatch, commit_resident, coset_fft,
     commit_device, commit_shard_device, default_context, fft, hash_or_noop, ifft, lde_values,
     log2_strict, poseidon, reverse_bits, synthetic_columns, two_to_one,
     verify_merkle_proof_to_cap)

@@ -67,6 +67,14 @@ SIGNATURES = {
                                          _c.c_uint32, _c.c_int, _c.c_uint64, _c.c_uint64,
                                          _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                          _c.POINTER(VpbsStats)]),
+    "vpbs_batch_commit": (_c.c_int, [_ctx, u64pp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32,
+                                     _c.c_int, u64pp, u64p, _c.POINTER(_c.c_void_p),
+                                     _c.POINTER(VpbsStats)]),
+    "vpbs_batch_destroy": (None, [_c.c_void_p]),
+    "vpbs_batch_get_leaves": (_c.c_int, [_c.c_void_p, u64p, _c.c_uint64, u64p]),
+    "vpbs_batch_prove": (_c.c_int, [_c.c_void_p, u64p, _c.c_uint64, u64p]),
+    "vpbs_batch_download": (_c.c_int, [_c.c_void_p, u64pp, u64p, u64p]),
+    "vpbs_batch_shape": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint32)] * 5),
 }
 
 _lib = None

@@ -169,6 +169,33 @@ __global__ void scatter_salt(const u64* __restrict__ salt, u64 m, unsigned log_m
   leaves[k * width + first_col + s] = gl::canon(__ldg(salt + (u64)s * m + nat));
 }
 
+// ---- lazy openings of a device-resident tree ----------------------------------------------------
+// rows_out[i][:] = leaves[idx[i]][:]
+__global__ void gather_rows(const u64* __restrict__ leaves, u32 width, const u64* __restrict__ idx,
+                            u64 count, u64* __restrict__ rows_out) {
+  const u64 row = blockIdx.x;
+  if (row >= count) return;
+  const u64* src = leaves + idx[row] * width;
+  for (u32 c = threadIdx.x; c < width; c += blockDim.x) rows_out[row * width + c] = src[c];
+}
+// [P2] MerkleTree::prove index arithmetic, one thread per (query, layer).
+__global__ void gather_siblings(const u64* __restrict__ digests, const u64* __restrict__ idx,
+                                u64 count, unsigned num_layers, u64 sub_digests,
+                                u64* __restrict__ out) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * num_layers) return;
+  const u64 q = t / num_layers;
+  const unsigned i = (unsigned)(t % num_layers);
+  const u64 leaf = idx[q];
+  const u64 tree = leaf >> num_layers, l = leaf & ((1ULL << num_layers) - 1);
+  const u64 parity = (l >> i) & 1, pair = l >> (i + 1);
+  const u64 sib = 2 * ((pair << (i + 1)) + (1ULL << i) - 1) + (1 - parity);
+  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(digests + 4 * (tree * sub_digests + sib));
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + 4 * t);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
 // ---- small batch entry points (tests / callers that hash outside a tree) -----------------------
 __global__ void permute_batch(u64* states, u64 count) {
   const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;

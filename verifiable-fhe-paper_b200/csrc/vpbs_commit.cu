@@ -54,6 +54,14 @@ struct vpbs_ctx {
   std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
 };
 
+// A commit kept in HBM (vpbs_batch_*): owns its device buffers, reads go through the context.
+struct vpbs_batch {
+  vpbs_ctx* ctx = nullptr;
+  u32 ncols = 0, log_n = 0, rate_bits = 0, cap_height = 0, width = 0;
+  bool coeff_inputs = false;
+  u64 *coeffs = nullptr, *leaves = nullptr, *digests = nullptr, *cap = nullptr;
+};
+
 namespace {
 
 int fail(vpbs_ctx* ctx, int code, const std::string& msg) {
@@ -775,6 +783,190 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
     cudaEventElapsedTime(&stats->d2h_ms, e2, e3);
     cudaEventElapsedTime(&stats->total_ms, e0, e3);
   }
+  return VPBS_OK;
+}
+
+// ---- device-resident batches ---------------------------------------------------------------------------
+void vpbs_batch_destroy(vpbs_batch* b) {
+  if (!b) return;
+  if (b->ctx) {
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+  }
+  cudaFree(b->coeffs);
+  cudaFree(b->leaves);
+  cudaFree(b->digests);
+  cudaFree(b->cap);
+  delete b;
+}
+
+int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                      uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                      const uint64_t* const* salt_cols, uint64_t* cap_out, vpbs_batch** out,
+                      vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!cols || ncols == 0 || !cap_out || !out)
+    return fail(ctx, VPBS_ERR_ARG, "null pointer or ncols == 0");
+  *out = nullptr;
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  const unsigned log_m = log_n + rate_bits;
+  if (cap_height > log_m)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  const u64 n = 1ULL << log_n, m = n << rate_bits;
+  const u32 width = ncols + (salt_cols ? VPBS_SALT_SIZE : 0);
+  const u64 ncap = 1ULL << cap_height, ndig = 2 * (m - ncap);
+  vpbs_batch* b = new (std::nothrow) vpbs_batch();
+  if (!b) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
+  b->ctx = ctx;
+  b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+  b->width = width;
+  b->coeff_inputs = inputs_are_coeffs != 0;
+  cudaError_t e = cudaMalloc(&b->coeffs, (size_t)ncols * n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&b->leaves, (size_t)m * width * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&b->digests, ndig ? ndig * 32 : 32);
+  if (e == cudaSuccess) e = cudaMalloc(&b->cap, ncap * 32);
+  if (e != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, VPBS_ERR_OOM, std::string("batch allocation: ") + cudaGetErrorString(e));
+  }
+  u64 *din = nullptr, *dsa = nullptr;
+  if ((rc = arena_get(ctx, "in", (size_t)ncols * n * 8, (void**)&din)) ||
+      (salt_cols && (rc = arena_get(ctx, "salt", (size_t)4 * m * 8, (void**)&dsa)))) {
+    vpbs_batch_destroy(b);
+    return rc;
+  }
+  const uint64_t l0 = ctx->launches;
+  cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
+  if (stats) cudaEventRecord(e0, ctx->stream);
+  cudaError_t ce = cudaSuccess;
+  for (u32 c = 0; c < ncols && ce == cudaSuccess; c++) {
+    if (!cols[c]) { ce = cudaErrorInvalidValue; break; }
+    ce = cudaMemcpyAsync(din + (u64)c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (salt_cols)
+    for (int s = 0; s < VPBS_SALT_SIZE && ce == cudaSuccess; s++) {
+      if (!salt_cols[s]) { ce = cudaErrorInvalidValue; break; }
+      ce = cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice, ctx->stream);
+    }
+  if (ce != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, ce == cudaErrorInvalidValue ? VPBS_ERR_ARG : VPBS_ERR_CUDA,
+                std::string("batch input copy: ") + cudaGetErrorString(ce));
+  }
+  if (stats) cudaEventRecord(e1, ctx->stream);
+  Timer tm{ctx, stats != nullptr};
+  // coefficients always end up in the batch (from_coeffs: a device copy of the inputs)
+  rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
+                   b->coeffs, b->leaves, b->digests, b->cap, &tm);
+  if (rc) {
+    vpbs_batch_destroy(b);
+    return rc;
+  }
+  if (stats) cudaEventRecord(e2, ctx->stream);
+  ce = cudaMemcpyAsync(cap_out, b->cap, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream);
+  if (stats) cudaEventRecord(e3, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, VPBS_ERR_CUDA, std::string("batch commit: ") + cudaGetErrorString(ce));
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    fill_stats(stats, tm, ctx->launches - l0);
+    cudaEventElapsedTime(&stats->h2d_ms, e0, e1);
+    cudaEventElapsedTime(&stats->d2h_ms, e2, e3);
+    cudaEventElapsedTime(&stats->total_ms, e0, e3);
+  }
+  *out = b;
+  return VPBS_OK;
+}
+
+int vpbs_batch_shape(vpbs_batch* b, uint32_t* ncols, uint32_t* log_n, uint32_t* rate_bits,
+                     uint32_t* cap_height, uint32_t* width) {
+  if (!b) return VPBS_ERR_STATE;
+  if (ncols) *ncols = b->ncols;
+  if (log_n) *log_n = b->log_n;
+  if (rate_bits) *rate_bits = b->rate_bits;
+  if (cap_height) *cap_height = b->cap_height;
+  if (width) *width = b->width;
+  return VPBS_OK;
+}
+
+static int batch_indices(vpbs_batch* b, const uint64_t* idx, uint64_t count, u64** d_idx) {
+  vpbs_ctx* ctx = b->ctx;
+  const u64 m = 1ULL << (b->log_n + b->rate_bits);
+  for (uint64_t i = 0; i < count; i++)
+    if (idx[i] >= m) return fail(ctx, VPBS_ERR_ARG, "leaf index out of range");
+  int rc;
+  if ((rc = arena_get(ctx, "idx", count * 8, (void**)d_idx))) return rc;
+  CU(ctx, cudaMemcpyAsync(*d_idx, idx, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_batch_get_leaves(vpbs_batch* b, const uint64_t* leaf_indices, uint64_t count,
+                          uint64_t* rows_out) {
+  if (!b) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = b->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (count == 0) return VPBS_OK;
+  if (!leaf_indices || !rows_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  u64 *d_idx = nullptr, *d_rows = nullptr;
+  if ((rc = batch_indices(b, leaf_indices, count, &d_idx))) return rc;
+  if ((rc = arena_get(ctx, "rows", count * (size_t)b->width * 8, (void**)&d_rows))) return rc;
+  merkle::gather_rows<<<(unsigned)count, 128, 0, ctx->stream>>>(b->leaves, b->width, d_idx, count, d_rows);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(rows_out, d_rows, count * (size_t)b->width * 8, cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_batch_prove(vpbs_batch* b, const uint64_t* leaf_indices, uint64_t count,
+                     uint64_t* siblings_out) {
+  if (!b) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = b->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  const unsigned num_layers = b->log_n + b->rate_bits - b->cap_height;
+  if (count == 0 || num_layers == 0) return VPBS_OK;
+  if (!leaf_indices || !siblings_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  u64 *d_idx = nullptr, *d_sib = nullptr;
+  if ((rc = batch_indices(b, leaf_indices, count, &d_idx))) return rc;
+  const size_t bytes = count * (size_t)num_layers * 32;
+  if ((rc = arena_get(ctx, "rows", bytes, (void**)&d_sib))) return rc;
+  const u64 sub_digests = 2 * (1ULL << num_layers) - 2;
+  const u64 total = count * num_layers;
+  merkle::gather_siblings<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
+      b->digests, d_idx, count, num_layers, sub_digests, d_sib);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(siblings_out, d_sib, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_batch_download(vpbs_batch* b, uint64_t* const* coeffs_out, uint64_t* leaves_out,
+                        uint64_t* digests_out) {
+  if (!b) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = b->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  const u64 n = 1ULL << b->log_n, m = n << b->rate_bits;
+  const u64 ndig = 2 * (m - (1ULL << b->cap_height));
+  if (coeffs_out)
+    for (u32 c = 0; c < b->ncols; c++)
+      if (coeffs_out[c])
+        CU(ctx, cudaMemcpyAsync(coeffs_out[c], b->coeffs + (u64)c * n, n * 8, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  if (leaves_out)
+    CU(ctx, cudaMemcpyAsync(leaves_out, b->leaves, (size_t)m * b->width * 8, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  if (digests_out && ndig)
+    CU(ctx, cudaMemcpyAsync(digests_out, b->digests, ndig * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
   return VPBS_OK;
 }
 

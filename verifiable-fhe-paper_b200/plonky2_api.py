@@ -340,6 +340,118 @@ class PolynomialBatch:
         return row[: row.shape[0] - (SALT_SIZE if self.blinding else 0)]
 
 
+# ----------------------------------------------------------------------------- resident batches
+class ResidentMerkleTree:
+    """MerkleTree whose leaves and digests stay in HBM (vpbs_batch_*): `cap` is on the host, `get` /
+    `prove` fetch single rows / authentication paths on demand — what plonky2's FRI query phase
+    reads ([P2] fri/prover.rs: merkle_tree.get(i) + merkle_tree.prove(i), 28 queries per batch)."""
+
+    def __init__(self, batch, cap, nleaves, width):
+        self._b = batch
+        self.cap = cap
+        self.nleaves = nleaves
+        self.width = width
+
+    def get_many(self, indices) -> np.ndarray:
+        idx = _as_u64(indices).reshape(-1)
+        out = np.empty((idx.size, self.width), np.uint64)
+        b = self._b
+        b.ctx.check(b.ctx.lib.vpbs_batch_get_leaves(b.handle, _ptr(idx), idx.size, _ptr(out)))
+        return out
+
+    def get(self, i: int) -> np.ndarray:
+        return self.get_many([i])[0]
+
+    def prove_many(self, indices) -> List[MerkleProof]:
+        idx = _as_u64(indices).reshape(-1)
+        layers = log2_strict(self.nleaves) - log2_strict(self.cap.shape[0])
+        out = np.empty((idx.size, layers, 4), np.uint64)
+        b = self._b
+        b.ctx.check(b.ctx.lib.vpbs_batch_prove(b.handle, _ptr(idx), idx.size,
+                                               _ptr(out) if out.size else None))
+        return [MerkleProof(out[i]) for i in range(idx.size)]
+
+    def prove(self, leaf_index: int) -> MerkleProof:
+        return self.prove_many([leaf_index])[0]
+
+
+class ResidentPolynomialBatch:
+    """PolynomialBatch kept on the device: only the cap crosses PCIe at commit time."""
+
+    def __init__(self, ctx, handle, cap, ncols, degree_log, rate_bits, blinding, stats):
+        self.ctx = ctx
+        self.handle = handle
+        self.degree_log = degree_log
+        self.rate_bits = rate_bits
+        self.blinding = blinding
+        self.ncols = ncols
+        self.stats = stats
+        width = ncols + (SALT_SIZE if blinding else 0)
+        self.merkle_tree = ResidentMerkleTree(self, cap, 1 << (degree_log + rate_bits), width)
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.vpbs_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_lde_values(self, index: int, step: int = 1) -> np.ndarray:
+        k = reverse_bits(index * step, self.degree_log + self.rate_bits)
+        row = self.merkle_tree.get(k)
+        return row[: row.shape[0] - (SALT_SIZE if self.blinding else 0)]
+
+    def download(self) -> "PolynomialBatch":
+        """Materialise the eager form (polynomials, leaves, digests) on the host."""
+        n, m = 1 << self.degree_log, 1 << (self.degree_log + self.rate_bits)
+        cap = self.merkle_tree.cap
+        coeffs = np.empty((self.ncols, n), np.uint64)
+        cop = (u64p * self.ncols)(*[_ptr(coeffs[c]) for c in range(self.ncols)])
+        leaves = np.empty((m, self.merkle_tree.width), np.uint64)
+        digests = np.empty((2 * (m - cap.shape[0]), 4), np.uint64)
+        self.ctx.check(self.ctx.lib.vpbs_batch_download(self.handle, cop, _ptr(leaves),
+                                                        _ptr(digests) if digests.size else None))
+        return PolynomialBatch(coeffs, MerkleTree(leaves, digests, cap), self.degree_log,
+                               self.rate_bits, self.blinding, self.stats)
+
+
+def commit_resident(cols, rate_bits: int, blinding: bool, cap_height: int,
+                    inputs_are_coeffs: bool = False, *, ctx: Optional[Context] = None, salt=None,
+                    rng: Optional[np.random.Generator] = None) -> ResidentPolynomialBatch:
+    """PolynomialBatch::from_values / from_coeffs with the result left in HBM."""
+    ctx = ctx or default_context()
+    a = _as_u64(cols)
+    if a.ndim != 2 or a.shape[0] == 0:
+        raise ValueError("need a non-empty (ncols, n) matrix")
+    ncols, n = a.shape
+    log_n = log2_strict(n)
+    m = n << rate_bits
+    if cap_height > log_n + rate_bits:
+        raise ValueError("cap_height=%d should be at most log2(leaves.len())=%d"
+                         % (cap_height, log_n + rate_bits))
+    saltp, salt_arr = None, None
+    if blinding:
+        if salt is None:
+            rng = rng or np.random.default_rng()
+            salt = rng.integers(0, P, size=(SALT_SIZE, m), dtype=np.uint64)
+        salt_arr = _as_u64(salt)
+        if salt_arr.shape != (SALT_SIZE, m):
+            raise ValueError("salt must be (%d, %d)" % (SALT_SIZE, m))
+        saltp = (u64p * SALT_SIZE)(*[_ptr(salt_arr[s]) for s in range(SALT_SIZE)])
+    colp = (u64p * ncols)(*[_ptr(a[c]) for c in range(ncols)])
+    cap = np.empty((1 << cap_height, 4), np.uint64)
+    handle = ctypes.c_void_p()
+    st = VpbsStats()
+    ctx.check(ctx.lib.vpbs_batch_commit(ctx.handle, colp, ncols, log_n, rate_bits, cap_height,
+                                        int(inputs_are_coeffs), saltp, _ptr(cap),
+                                        ctypes.byref(handle), ctypes.byref(st)))
+    return ResidentPolynomialBatch(ctx, handle, cap, ncols, log_n, rate_bits, blinding, st.as_dict())
+
+
 # ----------------------------------------------------------------------------- device-resident
 def commit_device(ctx: Context, d_cols: int, ncols: int, log_n: int, rate_bits: int,
                   cap_height: int, inputs_are_coeffs: bool, d_coeffs: int, d_leaves: int,
