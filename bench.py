@@ -175,6 +175,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chain-steps", type=int, default=0,
+                    help="BASELINE configs[3] stand-in: that many sequentially dependent N=1024 IVC "
+                         "step stand-ins (3 commits each) through the host C ABI; prints its own line")
     ap.add_argument("--shard-commit", action="store_true",
                     help="strong scaling of ONE commit: every rank computes its row range "
                          "(vpbs_commit_shard_dev) and the subtree roots are all-gathered over NCCL")
@@ -235,6 +238,8 @@ def main():
 
     if args.shard_commit:
         return run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks)
+    if args.chain_steps:
+        return run_chain(args, V, ctx, rank, world, barrier, max_over_ranks)
 
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
@@ -449,6 +454,77 @@ def main():
     for p in (p0, p1, p2, p3, p4):
         lib.vpbs_host_free(p)
     if world > 1:
+        dist.destroy_process_group()
+
+
+def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks):
+    """BASELINE.json configs[3]/[4] stand-in: a chain of sequentially dependent IVC-step stand-ins,
+    one chain per GPU.  Each step = the three commits of one N=1024 step proof through the HOST C
+    ABI: wires (135 value columns) and Z/partial products (20) with full outputs (the CPU prover
+    reads their LDE), quotient chunks (16 coefficient columns) as a resident batch opened at 28
+    query positions.  Step k+1's inputs depend on step k's caps (as the real chain's witness
+    contains the previous proof, ivc_based_vpbs.rs:329), so nothing can be pipelined across steps.
+    The real step proof (witness generation, quotient, FRI) needs plonky2 and cannot run here."""
+    import numpy as np
+    lib, u64p = ctx.lib, V._lib.u64p
+    n, m, ncap = 1 << LOG_N, (1 << LOG_N) << RATE_BITS, 1 << CAP_HEIGHT
+
+    def pinned(shape):
+        p = lib.vpbs_host_alloc(int(np.prod(shape)) * 8)
+        buf = (ctypes.c_uint64 * int(np.prod(shape))).from_address(p)
+        return np.ctypeslib.as_array(buf).reshape(shape)
+
+    shapes = [(135, False), (20, False), (16, True)]
+    ins, coeffs, leaves, digests, caps = [], [], [], [], []
+    for i, (c, _) in enumerate(shapes):
+        a = pinned((c, n)); a[:] = V.synthetic_columns(c, n, 0x5EED0000 + 1000 * rank + c)
+        ins.append(a); coeffs.append(pinned((c, n))); caps.append(pinned((ncap, 4)))
+        if i < 2:
+            leaves.append(pinned((m, c))); digests.append(pinned((2 * (m - ncap), 4)))
+    qidx = np.random.default_rng(1).integers(0, m, size=28, dtype=np.uint64)
+    qrows = np.empty((28, 16), np.uint64)
+    qsib = np.empty((28, LOG_N + RATE_BITS - CAP_HEIGHT, 4), np.uint64)
+
+    def ptrs(a):
+        return (u64p * a.shape[0])(*[a[c].ctypes.data_as(u64p) for c in range(a.shape[0])])
+
+    pin, pco = [ptrs(a) for a in ins], [ptrs(a) for a in coeffs]
+
+    def step():
+        for i in range(2):
+            ctx.check(lib.vpbs_commit(ctx.handle, pin[i], shapes[i][0], LOG_N, RATE_BITS, CAP_HEIGHT, 0,
+                                      None, pco[i], leaves[i].ctypes.data_as(u64p),
+                                      digests[i].ctypes.data_as(u64p), caps[i].ctypes.data_as(u64p), None))
+            ins[i + 1][:, 0] ^= caps[i].reshape(-1)[: shapes[i + 1][0]] >> np.uint64(1)  # Fiat-Shamir-like dependency
+        h = ctypes.c_void_p()
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, LOG_N, RATE_BITS, CAP_HEIGHT, 1, None,
+                                        caps[2].ctypes.data_as(u64p), ctypes.byref(h), None))
+        ctx.check(lib.vpbs_batch_get_leaves(h, qidx.ctypes.data_as(u64p), 28, qrows.ctypes.data_as(u64p)))
+        ctx.check(lib.vpbs_batch_prove(h, qidx.ctypes.data_as(u64p), 28, qsib.ctypes.data_as(u64p)))
+        lib.vpbs_batch_destroy(h)
+        ins[0][:, 0] ^= np.resize(caps[2].reshape(-1), 135) >> np.uint64(1)  # next step depends on this one
+
+    for _ in range(3):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.chain_steps):
+        step()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "N=1024 vPBS IVC step stand-in (3 commits: 135 + 20 value columns, 16 coefficient "
+                      "columns, 2^16 rows) through the host C ABI, sequentially dependent chain",
+            "value": dt / args.chain_steps * 1e3, "unit": "ms per step (commit part only)",
+            "higher_is_better": False, "n_gpus": world, "steps": args.chain_steps,
+            "chains": world, "steps_per_s_all_gpus": world * args.chain_steps / dt,
+            "full_pbs_730_steps_s": 730 * dt / args.chain_steps, "scaling": "weak", "dtype": "u64",
+            "data": "synthetic", "vs_baseline": None,
+            "note": "commit path only: witness generation, quotient polynomials and FRI of the real "
+                    "step proof run in plonky2 on the CPU and are not part of this number"}))
+    if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 

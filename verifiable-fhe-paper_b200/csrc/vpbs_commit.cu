@@ -52,6 +52,10 @@ struct vpbs_ctx {
   // host API: device->host copies run on their own stream, overlapped with the remaining kernels
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
+  // Buffers of destroyed resident batches, kept for the next batch of the same shape (a prover
+  // commits the same shapes every step; cudaMalloc/cudaFree of ~0.6 GB cost milliseconds).
+  std::multimap<size_t, void*> pool;
+  size_t pool_bytes = 0;
 };
 
 // A commit kept in HBM (vpbs_batch_*): owns its device buffers, reads go through the context.
@@ -60,6 +64,7 @@ struct vpbs_batch {
   u32 ncols = 0, log_n = 0, rate_bits = 0, cap_height = 0, width = 0;
   bool coeff_inputs = false;
   u64 *coeffs = nullptr, *leaves = nullptr, *digests = nullptr, *cap = nullptr;
+  size_t coeffs_bytes = 0, leaves_bytes = 0, digests_bytes = 0, cap_bytes = 0;
 };
 
 namespace {
@@ -79,6 +84,36 @@ int fail(vpbs_ctx* ctx, int code, const std::string& msg) {
       return fail(ctx, e_ == cudaErrorMemoryAllocation ? VPBS_ERR_OOM : VPBS_ERR_CUDA,     \
                   std::string(#call) + ": " + cudaGetErrorString(e_));                     \
   } while (0)
+
+constexpr size_t POOL_LIMIT_BYTES = 8ULL << 30;  // at most 8 GiB parked in the pool
+
+cudaError_t pool_alloc(vpbs_ctx* ctx, size_t bytes, u64** out) {
+  auto it = ctx->pool.find(bytes);
+  if (it != ctx->pool.end()) {
+    *out = (u64*)it->second;
+    ctx->pool_bytes -= bytes;
+    ctx->pool.erase(it);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation && !ctx->pool.empty()) {  // give the pool back and retry
+    for (auto& kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
+    cudaGetLastError();
+    e = cudaMalloc(out, bytes);
+  }
+  return e;
+}
+void pool_free(vpbs_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  if (ctx && ctx->pool_bytes + bytes <= POOL_LIMIT_BYTES) {
+    ctx->pool.emplace(bytes, p);
+    ctx->pool_bytes += bytes;
+  } else {
+    cudaFree(p);
+  }
+}
 
 int arena_get(vpbs_ctx* ctx, const char* name, size_t bytes, void** out) {
   Buf& b = ctx->arena[name];
@@ -444,6 +479,7 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   if (ctx->roots) cudaFree(ctx->roots);
   for (int i = 0; i < 10; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (auto& kv : ctx->pool) cudaFree(kv.second);
   for (cudaEvent_t e : ctx->ov) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -793,10 +829,10 @@ void vpbs_batch_destroy(vpbs_batch* b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
   }
-  cudaFree(b->coeffs);
-  cudaFree(b->leaves);
-  cudaFree(b->digests);
-  cudaFree(b->cap);
+  pool_free(b->ctx, b->coeffs, b->coeffs_bytes);
+  pool_free(b->ctx, b->leaves, b->leaves_bytes);
+  pool_free(b->ctx, b->digests, b->digests_bytes);
+  pool_free(b->ctx, b->cap, b->cap_bytes);
   delete b;
 }
 
@@ -822,10 +858,14 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
   b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
   b->width = width;
   b->coeff_inputs = inputs_are_coeffs != 0;
-  cudaError_t e = cudaMalloc(&b->coeffs, (size_t)ncols * n * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&b->leaves, (size_t)m * width * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&b->digests, ndig ? ndig * 32 : 32);
-  if (e == cudaSuccess) e = cudaMalloc(&b->cap, ncap * 32);
+  b->coeffs_bytes = (size_t)ncols * n * 8;
+  b->leaves_bytes = (size_t)m * width * 8;
+  b->digests_bytes = ndig ? ndig * 32 : 32;
+  b->cap_bytes = ncap * 32;
+  cudaError_t e = pool_alloc(ctx, b->coeffs_bytes, &b->coeffs);
+  if (e == cudaSuccess) e = pool_alloc(ctx, b->leaves_bytes, &b->leaves);
+  if (e == cudaSuccess) e = pool_alloc(ctx, b->digests_bytes, &b->digests);
+  if (e == cudaSuccess) e = pool_alloc(ctx, b->cap_bytes, &b->cap);
   if (e != cudaSuccess) {
     vpbs_batch_destroy(b);
     return fail(ctx, VPBS_ERR_OOM, std::string("batch allocation: ") + cudaGetErrorString(e));
