@@ -117,6 +117,20 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process (and so its pinned host buffers, first-touch) to the CPUs closest to its GPU:
+    with 8 ranks streaming ~0.7 GB per step over PCIe each, copies that cross the socket
+    interconnect are the e2e bottleneck.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "cpu affinity = GPU %d's NUMA-local cores (%d cpus)" % (gpu_index, len(os.sched_getaffinity(0)))
+    except Exception as e:  # not fatal: affinity is an optimisation
+        return "unchanged (%s)" % type(e).__name__
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path on this box's host cores.
     plonky2 itself cannot be built here (no Rust toolchain; crates not vendored), so this is the C
@@ -127,7 +141,7 @@ def run_reference(args, rank, world):
     import vfhe_b200 as V
     from oracle import binding as B
     B.build()
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0))
     B.set_threads(cores)
     n = 1 << LOG_N
     cols = V.synthetic_columns(NCOLS, n)
@@ -189,6 +203,17 @@ def main():
         return run_reference(args, rank, world)
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly ONE JSON line: route everything libraries print while we work (e.g.
+    # NCCL's version banner) to stderr and restore fd 1 only for the result line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -198,8 +223,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the commit path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     V.build.build()
     ctx = V.Context(local_rank)
@@ -237,9 +265,9 @@ def main():
         return float(t.item())
 
     if args.shard_commit:
-        return run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks)
+        return run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks, emit)
     if args.chain_steps:
-        return run_chain(args, V, ctx, rank, world, barrier, max_over_ranks)
+        return run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit)
 
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
@@ -413,7 +441,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import binding as B
         B.build()
-        cores = os.cpu_count() or 1
+        try:  # the GPU arm pinned this process to one NUMA node; the CPU arm gets every core
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except OSError:
+            pass
+        cores = len(os.sched_getaffinity(0))
         B.set_threads(cores)
         t0 = time.perf_counter()
         ref = B.commit(host_cols, RATE_BITS, CAP_HEIGHT)
@@ -438,7 +470,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.e2e_steps * 1e3,
                 "steps": args.e2e_steps, "api": "vpbs_commit (host C ABI, pinned buffers)",
-                "phase_ms_last": e2e_stats.as_dict(), "cap_matches_device_path": cap_matches},
+                "phase_ms_last": e2e_stats.as_dict(), "cap_matches_device_path": cap_matches,
+                "host_affinity": numa},
         "e2e_resident": {"value": world * args.e2e_steps * n / res_s, "unit": UNIT,
                          "ms_per_step": res_s / args.e2e_steps * 1e3,
                          "h2d_bytes_per_step": h2d_bytes,
@@ -450,14 +483,14 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    print(json.dumps(out))
+    emit(out)
     for p in (p0, p1, p2, p3, p4):
         lib.vpbs_host_free(p)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks):
+def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     """BASELINE.json configs[3]/[4] stand-in: a chain of sequentially dependent IVC-step stand-ins,
     one chain per GPU.  Each step = the three commits of one N=1024 step proof through the HOST C
     ABI: wires (135 value columns) and Z/partial products (20) with full outputs (the CPU prover
@@ -513,7 +546,7 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks):
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "N=1024 vPBS IVC step stand-in (3 commits: 135 + 20 value columns, 16 coefficient "
                       "columns, 2^16 rows) through the host C ABI, sequentially dependent chain",
             "value": dt / args.chain_steps * 1e3, "unit": "ms per step (commit part only)",
@@ -528,7 +561,7 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks):
         dist.destroy_process_group()
 
 
-def run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks):
+def run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks, emit):
     """One 2^16 x 128 commit split by row range over all ranks (SURVEY.md §8(e) partitioning B):
     every rank holds all columns, computes m / world leaves + their digests, and only the subtree
     roots (32 B per cap entry) are exchanged.  Strong scaling; prints its own JSON line."""
@@ -547,7 +580,7 @@ def run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_r
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC + " — ONE commit sharded by row range", "value": (1 << LOG_N) / (ms * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
