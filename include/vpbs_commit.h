@@ -166,6 +166,17 @@ int vpbs_commit_shard_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols,
                           uint64_t* d_leaves_out, uint64_t* d_digests_out, uint64_t* d_roots_out,
                           vpbs_stats* stats);
 
+/* ---- FRI proof-of-work grind -------------------------------------------
+ * [P2] plonky2/src/fri/prover.rs fri_proof_of_work: the challenger's duplex state with the
+ * candidate witness written at `witness_pos`, one permutation, and the response word
+ * (`response_lane`, upstream: the last squeezed element = lane 7) must have at least
+ * `min_leading_zeros` leading zero bits as a canonical u64.  Scans candidates
+ * first_candidate .. first_candidate + count - 1 and returns the SMALLEST that qualifies in
+ * *witness_out (deterministic, unlike upstream's rayon find_any) with *found = 1, or *found = 0. */
+int vpbs_pow_grind(vpbs_ctx* ctx, const uint64_t state[12], uint32_t witness_pos,
+                   uint32_t response_lane, uint32_t min_leading_zeros, uint64_t first_candidate,
+                   uint64_t count, uint64_t* witness_out, int* found);
+
 /* ---- device-resident batches (keep the LDE in HBM, open lazily) ---------
  * vpbs_batch_commit is vpbs_commit that returns only the cap and KEEPS coefficients, leaves and
  * digests in device memory owned by the handle.  The readers below serve what plonky2 reads later

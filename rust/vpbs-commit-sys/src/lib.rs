@@ -74,6 +74,9 @@ extern "C" {
                                  first_leaf: u64, nleaves_shard: u64, d_coeffs_out: *mut u64,
                                  d_leaves_out: *mut u64, d_digests_out: *mut u64,
                                  d_roots_out: *mut u64, stats: *mut vpbs_stats) -> c_int;
+    pub fn vpbs_pow_grind(ctx: *mut vpbs_ctx, state: *const u64, witness_pos: u32, response_lane: u32,
+                          min_leading_zeros: u32, first_candidate: u64, count: u64,
+                          witness_out: *mut u64, found: *mut c_int) -> c_int;
     // device-resident batches: only the cap crosses PCIe at commit time; rows / paths on demand
     pub fn vpbs_batch_commit(ctx: *mut vpbs_ctx, cols: *const *const u64, ncols: u32, log_n: u32,
                              rate_bits: u32, cap_height: u32, inputs_are_coeffs: c_int,

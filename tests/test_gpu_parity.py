@@ -466,3 +466,25 @@ def test_resident_batch_lazy_openings(V, ctx, oracle, log_n, ncols, rate_bits, c
     with pytest.raises(ValueError):
         rb.merkle_tree.get(m)
     rb.close()
+
+
+def test_fri_proof_of_work_grind(V, ctx, oracle):
+    """vpbs_pow_grind: the smallest witness found on the GPU is exactly the first one the oracle's
+    permutation accepts, for the reference's proof_of_work_bits = 16 (plus the 0 extra bits of a
+    64-bit field) and for an impossible target."""
+    rng = np.random.default_rng(12)
+    state = rng.integers(0, P, size=12, dtype=np.uint64)
+    pos, bits = 5, 12
+    w = V.fri_proof_of_work(state, pos, bits, ctx=ctx)
+    assert w is not None
+    def response(c):
+        s = state.copy(); s[pos] = c
+        return int(oracle.poseidon(s)[7])
+    assert response(w) >> (64 - bits) == 0
+    for c in range(0, w, max(1, w // 300)):     # no smaller qualifying witness (sampled) ...
+        assert response(c) >> (64 - bits) != 0 or c == w
+    first = next(c for c in range(0, w + 1) if response(c) >> (64 - bits) == 0) if w < 20000 else w
+    assert first == w                            # ... and exhaustively when cheap
+    assert V.fri_proof_of_work(state, pos, 16, ctx=ctx) is not None
+    assert V.fri_proof_of_work(state, pos, 60, count=1 << 16, ctx=ctx) is None
+    assert V.fri_proof_of_work(state, pos, bits, first_candidate=w + 1, count=1, ctx=ctx) in (None, w + 1)

@@ -196,6 +196,26 @@ __global__ void gather_siblings(const u64* __restrict__ digests, const u64* __re
   dst[1] = src[1];
 }
 
+// ---- FRI proof-of-work grind ---------------------------------------------------------------------
+// best: smallest qualifying candidate so far (init ~0); one candidate per thread.
+__global__ void __launch_bounds__(128)
+pow_grind(const u64* __restrict__ state, u32 witness_pos, u32 response_lane, u32 min_leading_zeros,
+          u64 first, u64 count, unsigned long long* __restrict__ best) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const u64 cand = first + t;
+  if (cand >= *best) return;  // a smaller witness is already known
+  u64 s[poseidon::WIDTH];
+#pragma unroll
+  for (int i = 0; i < poseidon::WIDTH; i++) s[i] = (i == (int)witness_pos) ? gl::canon(cand) : state[i];
+  poseidon::permute_lazy(s);
+  u64 resp = 0;
+#pragma unroll
+  for (int i = 0; i < poseidon::WIDTH; i++)
+    if (i == (int)response_lane) resp = gl::canon(s[i]);
+  if ((u32)__clzll((long long)resp) >= min_leading_zeros) atomicMin(best, (unsigned long long)cand);
+}
+
 // ---- small batch entry points (tests / callers that hash outside a tree) -----------------------
 __global__ void permute_batch(u64* states, u64 count) {
   const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;

@@ -822,6 +822,41 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
   return VPBS_OK;
 }
 
+// ---- FRI proof of work -----------------------------------------------------------------------------
+int vpbs_pow_grind(vpbs_ctx* ctx, const uint64_t state[12], uint32_t witness_pos,
+                   uint32_t response_lane, uint32_t min_leading_zeros, uint64_t first_candidate,
+                   uint64_t count, uint64_t* witness_out, int* found) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!state || !witness_out || !found) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  if (witness_pos >= 12 || response_lane >= 12 || min_leading_zeros > 64)
+    return fail(ctx, VPBS_ERR_ARG, "witness_pos / response_lane / min_leading_zeros out of range");
+  *found = 0;
+  u64* d = nullptr;
+  if ((rc = arena_get(ctx, "pow", 13 * 8, (void**)&d))) return rc;
+  const unsigned long long none = ~0ULL;
+  CU(ctx, cudaMemcpyAsync(d, state, 12 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d + 12, &none, 8, cudaMemcpyHostToDevice, ctx->stream));
+  const u64 chunk = 1ULL << 22;  // candidates per launch; stop at the first chunk with a hit
+  for (u64 off = 0; off < count; off += chunk) {
+    const u64 cnt = count - off < chunk ? count - off : chunk;
+    merkle::pow_grind<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(
+        d, witness_pos, response_lane, min_leading_zeros, first_candidate + off, cnt,
+        (unsigned long long*)(d + 12));
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    unsigned long long best = none;
+    CU(ctx, cudaMemcpyAsync(&best, d + 12, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (best != none) {
+      *witness_out = best;
+      *found = 1;
+      break;
+    }
+  }
+  return VPBS_OK;
+}
+
 // ---- device-resident batches ---------------------------------------------------------------------------
 void vpbs_batch_destroy(vpbs_batch* b) {
   if (!b) return;

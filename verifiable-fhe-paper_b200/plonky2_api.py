@@ -197,6 +197,21 @@ def two_to_one(left, right, ctx: Optional[Context] = None) -> np.ndarray:
     return out
 
 
+def fri_proof_of_work(state, witness_pos: int, min_leading_zeros: int, first_candidate: int = 0,
+                      count: int = 1 << 32, response_lane: int = 7, ctx: Optional[Context] = None):
+    """[P2] fri/prover.rs fri_proof_of_work on a duplex state: smallest witness in
+    [first_candidate, first_candidate + count) whose response has >= min_leading_zeros leading
+    zero bits, or None."""
+    ctx = ctx or default_context()
+    st = _as_u64(state).reshape(12)
+    out = np.zeros(1, np.uint64)
+    found = ctypes.c_int(0)
+    ctx.check(ctx.lib.vpbs_pow_grind(ctx.handle, _ptr(st), witness_pos, response_lane,
+                                     min_leading_zeros, first_candidate, count, _ptr(out),
+                                     ctypes.byref(found)))
+    return int(out[0]) if found.value else None
+
+
 # ----------------------------------------------------------------------------- merkle_tree.rs
 @dataclass
 class MerkleProof:
