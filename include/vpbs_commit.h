@@ -166,6 +166,14 @@ int vpbs_commit_shard_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols,
                           uint64_t* d_leaves_out, uint64_t* d_digests_out, uint64_t* d_roots_out,
                           vpbs_stats* stats);
 
+/* ---- openings: evaluate polynomials at extension-field points -----------
+ * [P2] plonky2_field/src/polynomial/mod.rs PolynomialCoeffs::to_extension().eval(zeta) over
+ * QuadraticExtension<GoldilocksField> (F[X]/(X^2 - 7), an element is two consecutive uint64_t), as
+ * plonk/proof.rs OpeningSet::new does for every committed polynomial at zeta and g*zeta
+ * ("construct the opening set").  out[(p * ncols + c) * 2 + {0,1}] = poly_c(points[p]). */
+int vpbs_eval_ext2(vpbs_ctx* ctx, const uint64_t* const* coeff_cols, uint32_t ncols, uint32_t log_n,
+                   const uint64_t* points, uint32_t npoints, uint64_t* out);
+
 /* ---- FRI proof-of-work grind -------------------------------------------
  * [P2] plonky2/src/fri/prover.rs fri_proof_of_work: the challenger's duplex state with the
  * candidate witness written at `witness_pos`, one permutation, and the response word
@@ -198,6 +206,8 @@ int vpbs_batch_prove(vpbs_batch* batch, const uint64_t* leaf_indices, uint64_t c
 /* Bulk download of what vpbs_commit returns eagerly; any pointer may be NULL. */
 int vpbs_batch_download(vpbs_batch* batch, uint64_t* const* coeffs_out, uint64_t* leaves_out,
                         uint64_t* digests_out);
+/* vpbs_eval_ext2 on the coefficients the batch already holds in HBM (PolynomialBatch.polynomials). */
+int vpbs_batch_eval_ext2(vpbs_batch* batch, const uint64_t* points, uint32_t npoints, uint64_t* out);
 /* Shape of the batch: m = 2^(log_n + rate_bits) leaves of `width` elements. */
 int vpbs_batch_shape(vpbs_batch* batch, uint32_t* ncols, uint32_t* log_n, uint32_t* rate_bits,
                      uint32_t* cap_height, uint32_t* width);

@@ -67,6 +67,8 @@ def lib() -> ctypes.CDLL:
         L.orc_commit.restype = ctypes.c_int
         L.orc_commit.argtypes = [_u64pp, u32, u32, u32, u32, ctypes.c_int, _u64pp,
                                  _u64p, _u64p, _u64p, _u64p, _u64p]
+        L.orc_eval_ext2.restype = None
+        L.orc_eval_ext2.argtypes = [_u64pp, u32, u64, _u64p, _u64p]
         L.orc_set_threads.argtypes = [ctypes.c_int]
         L.orc_get_threads.restype = ctypes.c_int
         _lib = L
@@ -187,3 +189,12 @@ def commit(cols, rate_bits, cap_height, inputs_are_coeffs=False, salt_cols=None,
     if rc != 0:
         raise ValueError("orc_commit: bad arguments (rc=%d)" % rc)
     return dict(coeffs=coeffs, lde=ldec, leaves=leaves, digests=digests, cap=cap)
+
+
+def eval_ext2(cols, x):
+    """cols: (ncols, n) coefficients; x = (x0, x1) in F[X]/(X^2 - 7) -> (ncols, 2)."""
+    a = _arr(cols); ncols, n = a.shape
+    colp = (_u64p * ncols)(*[_p(a[c]) for c in range(ncols)])
+    xx = _arr(x); out = np.empty((ncols, 2), np.uint64)
+    lib().orc_eval_ext2(colp, ncols, n, _p(xx), _p(out))
+    return out

@@ -216,3 +216,20 @@ def commit(cols, rate_bits, cap_height, inputs_are_coeffs=False, salt_cols=None)
     leaves = [[col[bitrev(k, log_m)] for col in all_cols] for k in range(n << rate_bits)]
     digests, cap = merkle_new(leaves, cap_height)
     return dict(coeffs=coeffs, lde=lde_cols, leaves=leaves, digests=digests, cap=cap)
+
+
+# --------------------------------------------------------------------------- quadratic extension
+EXT_W = 7  # [P2] extension/quadratic.rs: GoldilocksField is Extendable<2> with W = 7
+
+
+def ext_mul(a, b):
+    return ((a[0] * b[0] + EXT_W * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def eval_ext2(coeffs, x):
+    """[P2] PolynomialCoeffs::to_extension().eval(x): sum_j c_j x^j by explicit powers."""
+    acc, pw = (0, 0), (1, 0)
+    for c in coeffs:
+        acc = ((acc[0] + c % P * pw[0]) % P, (acc[1] + c % P * pw[1]) % P)
+        pw = ext_mul(pw, x)
+    return acc

@@ -499,3 +499,26 @@ int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint
   free(roots_m);
   return rc;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Quadratic extension and polynomial evaluation.  [P2] plonky2_field/src/extension/quadratic.rs
+ * (W = 7), polynomial/mod.rs PolynomialCoeffs::eval (Horner from the highest coefficient).
+ * ---------------------------------------------------------------------------------------- */
+#define EXT_W 7ULL
+void orc_eval_ext2(const uint64_t* const* cols, uint32_t ncols, uint64_t n, const uint64_t x[2],
+                   uint64_t* out) {
+  const uint64_t x0 = canon(x[0]), x1 = canon(x[1]);
+#pragma omp parallel for num_threads(orc_get_threads()) schedule(dynamic)
+  for (uint32_t c = 0; c < ncols; c++) {
+    uint64_t a0 = 0, a1 = 0; /* acc = a0 + a1 X */
+    for (uint64_t j = n; j-- > 0;) {
+      /* acc = acc * x + coeff:  (a0 + a1 X)(x0 + x1 X) = a0 x0 + W a1 x1 + (a0 x1 + a1 x0) X */
+      uint64_t n0 = add_(mul_(a0, x0), mul_(EXT_W, mul_(a1, x1)));
+      uint64_t n1 = add_(mul_(a0, x1), mul_(a1, x0));
+      a0 = add_(n0, canon(cols[c][j]));
+      a1 = n1;
+    }
+    out[2 * c] = a0;
+    out[2 * c + 1] = a1;
+  }
+}

@@ -80,6 +80,14 @@ int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint
                uint64_t* coeffs_out, uint64_t* lde_cols_out, uint64_t* leaves_out,
                uint64_t* digests_out, uint64_t* cap_out);
 
+/* [P2] plonky2_field/src/extension/quadratic.rs QuadraticExtension<GoldilocksField> (W = 7:
+ * F[X]/(X^2 - 7)) and polynomial/mod.rs PolynomialCoeffs::eval / to_extension().eval(zeta), as used
+ * by plonk/proof.rs OpeningSet::new ("construct the opening set", reached from prove(),
+ * /root/reference/src/vtfhe/ivc_based_vpbs.rs:302): out[c] = sum_j cols[c][j] * x^j for the
+ * extension point x = (x[0], x[1]); out is ncols x 2. */
+void orc_eval_ext2(const uint64_t* const* cols, uint32_t ncols, uint64_t n, const uint64_t x[2],
+                   uint64_t* out);
+
 /* Threads used by the parallel regions (mirrors rayon's pool). */
 void orc_set_threads(int n);
 int orc_get_threads(void);

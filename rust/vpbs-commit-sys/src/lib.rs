@@ -74,6 +74,10 @@ extern "C" {
                                  first_leaf: u64, nleaves_shard: u64, d_coeffs_out: *mut u64,
                                  d_leaves_out: *mut u64, d_digests_out: *mut u64,
                                  d_roots_out: *mut u64, stats: *mut vpbs_stats) -> c_int;
+    pub fn vpbs_eval_ext2(ctx: *mut vpbs_ctx, coeff_cols: *const *const u64, ncols: u32, log_n: u32,
+                          points: *const u64, npoints: u32, out: *mut u64) -> c_int;
+    pub fn vpbs_batch_eval_ext2(batch: *mut vpbs_batch, points: *const u64, npoints: u32,
+                                out: *mut u64) -> c_int;
     pub fn vpbs_pow_grind(ctx: *mut vpbs_ctx, state: *const u64, witness_pos: u32, response_lane: u32,
                           min_leading_zeros: u32, first_candidate: u64, count: u64,
                           witness_out: *mut u64, found: *mut c_int) -> c_int;

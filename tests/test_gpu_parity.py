@@ -488,3 +488,28 @@ def test_fri_proof_of_work_grind(V, ctx, oracle):
     assert V.fri_proof_of_work(state, pos, 16, ctx=ctx) is not None
     assert V.fri_proof_of_work(state, pos, 60, count=1 << 16, ctx=ctx) is None
     assert V.fri_proof_of_work(state, pos, bits, first_candidate=w + 1, count=1, ctx=ctx) in (None, w + 1)
+
+
+@pytest.mark.parametrize("log_n,ncols", [(0, 3), (3, 5), (8, 9), (9, 2), (13, 20), (16, 7)])
+def test_eval_ext2_openings(V, ctx, oracle, log_n, ncols):
+    """Openings at extension-field points (OpeningSet::new's evaluations) vs the oracle's Horner."""
+    rng = np.random.default_rng(log_n + 100 * ncols)
+    coeffs = rand_u64(rng, (ncols, 1 << log_n))
+    pts = rand_u64(rng, (3, 2))
+    pts[2] = (5, 0)   # a base-field point: imaginary parts must come out 0 ... unless coefficients say otherwise
+    got = V.eval_ext2(coeffs, pts, ctx)
+    for p in range(3):
+        assert np.array_equal(got[p], oracle.eval_ext2(coeffs, pts[p])), (log_n, ncols, p)
+    assert (got[2][:, 1] == 0).all()
+
+
+def test_resident_batch_openings(V, ctx, oracle):
+    rng = np.random.default_rng(77)
+    cols = rand_u64(rng, (20, 1 << 10))
+    rb = V.commit_resident(cols, 3, False, 4, ctx=ctx)
+    ref = oracle.commit(cols, 3, 4, False)
+    zeta = rand_u64(rng, (2, 2))
+    got = rb.eval_ext2(zeta)
+    for p in range(2):
+        assert np.array_equal(got[p], oracle.eval_ext2(ref["coeffs"], zeta[p]))
+    rb.close()

@@ -148,3 +148,15 @@ def test_oracle_regression_pins(oracle, oracle_commits, V):
         assert sha(res["coeffs"]) == c["sha256_coeffs"]
         assert sha(res["leaves"]) == c["sha256_leaves"]
         assert sha(res["digests"]) == c["sha256_digests"]
+
+
+def test_extension_evaluation_against_model(oracle):
+    from oracle import model
+    rnd = random.Random(9)
+    for n in (1, 2, 8, 64):
+        cols = [[rnd.getrandbits(64) for _ in range(n)] for _ in range(3)]
+        x = (rnd.getrandbits(64), rnd.getrandbits(64))
+        got = oracle.eval_ext2(np.array(cols, dtype=np.uint64), x).tolist()
+        assert got == [list(model.eval_ext2(c, (x[0] % P, x[1] % P))) for c in cols]
+    # X^2 = 7: evaluating the polynomial t^2 at the point X gives (7, 0)
+    assert oracle.eval_ext2(np.array([[0, 0, 1, 0]], dtype=np.uint64), (0, 1)).tolist() == [[7, 0]]

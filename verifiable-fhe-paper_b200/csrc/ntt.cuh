@@ -297,6 +297,58 @@ pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
   }
 }
 
+// ---- polynomial evaluation at quadratic-extension points --------------------------------------------
+// F[X]/(X^2 - 7): (a0 + a1 X)(b0 + b1 X) = (a0 b0 + 7 a1 b1) + (a0 b1 + a1 b0) X.
+struct Ext2 {
+  u64 re, im;
+};
+__device__ __forceinline__ Ext2 ext_mul(Ext2 a, Ext2 b) {
+  const u64 t = gl::mul(a.im, b.im);
+  return Ext2{gl::add(gl::mul(a.re, b.re), gl::mul(7, t)), gl::add(gl::mul(a.re, b.im), gl::mul(a.im, b.re))};
+}
+// One CTA per (polynomial, point).  Thread t sums the coefficients j = t (mod 256) by Horner in
+// y = x^256 (coalesced reads), scales by x^t and the CTA adds the 256 partial values.
+__global__ void __launch_bounds__(256)
+eval_ext2(const u64* __restrict__ coeffs, u64 col_stride, unsigned log_n,
+          const u64* __restrict__ points, u64* __restrict__ out, unsigned ncols) {
+  __shared__ u64 sre[256], sim[256];
+  const unsigned col = blockIdx.x, pt = blockIdx.y, t = threadIdx.x;
+  const u64 n = 1ULL << log_n;
+  const Ext2 x{gl::canon(points[2 * pt]), gl::canon(points[2 * pt + 1])};
+  Ext2 y = x;  // x^256
+#pragma unroll
+  for (int i = 0; i < 8; i++) y = ext_mul(y, y);
+  const u64* c = coeffs + (u64)col * col_stride;
+  Ext2 acc{0, 0};
+  if (t < n) {
+    const u64 k_hi = (n - 1 - t) >> 8;  // largest k with 256 k + t < n
+    for (u64 k = k_hi + 1; k-- > 0;) {
+      acc = ext_mul(acc, y);
+      acc.re = gl::add(acc.re, gl::canon(__ldg(c + (k << 8) + t)));
+    }
+    Ext2 p{1, 0}, b = x;  // x^t by binary exponentiation (t < 256)
+    for (unsigned e = t; e; e >>= 1) {
+      if (e & 1) p = ext_mul(p, b);
+      b = ext_mul(b, b);
+    }
+    acc = ext_mul(acc, p);
+  }
+  sre[t] = acc.re;
+  sim[t] = acc.im;
+  __syncthreads();
+  for (unsigned s = 128; s > 0; s >>= 1) {
+    if (t < s) {
+      sre[t] = gl::add(sre[t], sre[t + s]);
+      sim[t] = gl::add(sim[t], sim[t + s]);
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    out[2 * ((u64)pt * ncols + col)] = sre[0];
+    out[2 * ((u64)pt * ncols + col) + 1] = sim[0];
+  }
+}
+
 // ---- tables ------------------------------------------------------------------------------------
 // w[t] = omega_N^t for t < N/2.
 __global__ void fill_roots(u64* w, unsigned log_N) {

@@ -822,6 +822,51 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
   return VPBS_OK;
 }
 
+// ---- openings ------------------------------------------------------------------------------------------
+static int eval_ext2_device(vpbs_ctx* ctx, const u64* d_coeffs, u32 ncols, u32 log_n,
+                            const uint64_t* points, u32 npoints, uint64_t* out) {
+  int rc;
+  u64 *d_pts = nullptr, *d_out = nullptr;
+  if ((rc = arena_get(ctx, "idx", (size_t)npoints * 16, (void**)&d_pts))) return rc;
+  if ((rc = arena_get(ctx, "rows", (size_t)npoints * ncols * 16, (void**)&d_out))) return rc;
+  CU(ctx, cudaMemcpyAsync(d_pts, points, (size_t)npoints * 16, cudaMemcpyHostToDevice, ctx->stream));
+  ntt::eval_ext2<<<dim3(ncols, npoints), 256, 0, ctx->stream>>>(d_coeffs, 1ULL << log_n, log_n, d_pts,
+                                                               d_out, ncols);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(out, d_out, (size_t)npoints * ncols * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_eval_ext2(vpbs_ctx* ctx, const uint64_t* const* coeff_cols, uint32_t ncols, uint32_t log_n,
+                   const uint64_t* points, uint32_t npoints, uint64_t* out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (npoints == 0 || ncols == 0) return VPBS_OK;
+  if (!coeff_cols || !points || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  if (log_n > 30 || npoints > 65535) return fail(ctx, VPBS_ERR_ARG, "log_n > 30 or too many points");
+  const u64 n = 1ULL << log_n;
+  u64* din = nullptr;
+  if ((rc = arena_get(ctx, "in", (size_t)ncols * n * 8, (void**)&din))) return rc;
+  for (u32 c = 0; c < ncols; c++) {
+    if (!coeff_cols[c]) return fail(ctx, VPBS_ERR_ARG, "coeff_cols[c] == NULL");
+    CU(ctx, cudaMemcpyAsync(din + (u64)c * n, coeff_cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return eval_ext2_device(ctx, din, ncols, log_n, points, npoints, out);
+}
+
+int vpbs_batch_eval_ext2(vpbs_batch* b, const uint64_t* points, uint32_t npoints, uint64_t* out) {
+  if (!b) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = b->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (npoints == 0) return VPBS_OK;
+  if (!points || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  if (npoints > 65535) return fail(ctx, VPBS_ERR_ARG, "too many points");
+  return eval_ext2_device(ctx, b->coeffs, b->ncols, b->log_n, points, npoints, out);
+}
+
 // ---- FRI proof of work -----------------------------------------------------------------------------
 int vpbs_pow_grind(vpbs_ctx* ctx, const uint64_t state[12], uint32_t witness_pos,
                    uint32_t response_lane, uint32_t min_leading_zeros, uint64_t first_candidate,

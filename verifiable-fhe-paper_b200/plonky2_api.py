@@ -197,6 +197,20 @@ def two_to_one(left, right, ctx: Optional[Context] = None) -> np.ndarray:
     return out
 
 
+def eval_ext2(coeff_cols, points, ctx: Optional[Context] = None) -> np.ndarray:
+    """[P2] PolynomialCoeffs::to_extension().eval(point) for every polynomial and every point of
+    F[X]/(X^2 - 7): coeff_cols (ncols, n), points (npoints, 2) -> (npoints, ncols, 2)."""
+    ctx = ctx or default_context()
+    a = _as_u64(coeff_cols)
+    pts = _as_u64(points).reshape(-1, 2)
+    ncols, n = a.shape
+    colp = (u64p * ncols)(*[_ptr(a[c]) for c in range(ncols)])
+    out = np.empty((pts.shape[0], ncols, 2), np.uint64)
+    ctx.check(ctx.lib.vpbs_eval_ext2(ctx.handle, colp, ncols, log2_strict(n), _ptr(pts), pts.shape[0],
+                                     _ptr(out)))
+    return out
+
+
 def fri_proof_of_work(state, witness_pos: int, min_leading_zeros: int, first_candidate: int = 0,
                       count: int = 1 << 32, response_lane: int = 7, ctx: Optional[Context] = None):
     """[P2] fri/prover.rs fri_proof_of_work on a duplex state: smallest witness in
@@ -419,6 +433,13 @@ class ResidentPolynomialBatch:
         k = reverse_bits(index * step, self.degree_log + self.rate_bits)
         row = self.merkle_tree.get(k)
         return row[: row.shape[0] - (SALT_SIZE if self.blinding else 0)]
+
+    def eval_ext2(self, points) -> np.ndarray:
+        """Openings of every polynomial of the batch at extension points: (npoints, ncols, 2)."""
+        pts = _as_u64(points).reshape(-1, 2)
+        out = np.empty((pts.shape[0], self.ncols, 2), np.uint64)
+        self.ctx.check(self.ctx.lib.vpbs_batch_eval_ext2(self.handle, _ptr(pts), pts.shape[0], _ptr(out)))
+        return out
 
     def download(self) -> "PolynomialBatch":
         """Materialise the eager form (polynomials, leaves, digests) on the host."""
