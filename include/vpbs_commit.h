@@ -174,6 +174,23 @@ int vpbs_commit_shard_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols,
 int vpbs_eval_ext2(vpbs_ctx* ctx, const uint64_t* const* coeff_cols, uint32_t ncols, uint32_t log_n,
                    const uint64_t* points, uint32_t npoints, uint64_t* out);
 
+/* ---- FRI commit phase, one reduction layer -----------------------------
+ * [P2] plonky2/src/fri/prover.rs fri_committed_trees over D = 2 extension elements stored as
+ * (re, im) pairs; the challenger stays with the caller (it supplies beta between the two calls).
+ *  vpbs_fri_layer_commit: reverse_index_bits_in_place(values); leaves = chunks of 2^arity_bits
+ *      values, flattened (2 * arity base elements per leaf); MerkleTree::new(leaves, cap_height).
+ *      leaves_out: (len >> arity_bits) x (2 << arity_bits), may be NULL; digests_out / cap_out as
+ *      vpbs_merkle_new.
+ *  vpbs_fri_fold: coeffs' = chunks_exact(arity).map(|c| reduce_with_powers(c, beta)) (len >>
+ *      arity_bits elements) and values' = coeffs'.coset_fft(shift_next) in natural order, where
+ *      shift_next = shift^arity is maintained by the caller as upstream does. */
+int vpbs_fri_layer_commit(vpbs_ctx* ctx, const uint64_t* values_ext, uint64_t len,
+                          uint32_t arity_bits, uint32_t cap_height, uint64_t* leaves_out,
+                          uint64_t* digests_out, uint64_t* cap_out);
+int vpbs_fri_fold(vpbs_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
+                  const uint64_t beta[2], uint64_t shift_next, uint64_t* coeffs_out,
+                  uint64_t* values_out);
+
 /* ---- FRI proof-of-work grind -------------------------------------------
  * [P2] plonky2/src/fri/prover.rs fri_proof_of_work: the challenger's duplex state with the
  * candidate witness written at `witness_pos`, one permutation, and the response word

@@ -69,6 +69,10 @@ def lib() -> ctypes.CDLL:
                                  _u64p, _u64p, _u64p, _u64p, _u64p]
         L.orc_eval_ext2.restype = None
         L.orc_eval_ext2.argtypes = [_u64pp, u32, u64, _u64p, _u64p]
+        L.orc_fri_layer_commit.restype = ctypes.c_int
+        L.orc_fri_layer_commit.argtypes = [_u64p, u64, u32, u32, _u64p, _u64p, _u64p]
+        L.orc_fri_fold.restype = None
+        L.orc_fri_fold.argtypes = [_u64p, u64, u32, _u64p, u64, _u64p, _u64p]
         L.orc_set_threads.argtypes = [ctypes.c_int]
         L.orc_get_threads.restype = ctypes.c_int
         _lib = L
@@ -198,3 +202,25 @@ def eval_ext2(cols, x):
     xx = _arr(x); out = np.empty((ncols, 2), np.uint64)
     lib().orc_eval_ext2(colp, ncols, n, _p(xx), _p(out))
     return out
+
+
+def fri_layer_commit(values_ext, arity_bits, cap_height):
+    """values_ext: (len, 2) -> dict(leaves (len/arity, 2*arity), digests, cap)."""
+    v = _arr(values_ext); ln = v.shape[0]; nl = ln >> arity_bits
+    leaves = np.empty((nl, 2 << arity_bits), np.uint64)
+    ncap = 1 << cap_height
+    digests = np.empty((2 * (nl - ncap) if nl >= ncap else 0, 4), np.uint64)
+    cap = np.empty((ncap, 4), np.uint64)
+    rc = lib().orc_fri_layer_commit(_p(v), ln, arity_bits, cap_height, _p(leaves),
+                                    _p(digests) if digests.size else None, _p(cap))
+    if rc != 0:
+        raise ValueError("orc_fri_layer_commit: bad arguments")
+    return dict(leaves=leaves, digests=digests, cap=cap)
+
+
+def fri_fold(coeffs_ext, arity_bits, beta, shift_next):
+    """coeffs_ext: (len, 2) -> (coeffs' (len/arity, 2), values' (len/arity, 2))."""
+    c = _arr(coeffs_ext); ln = c.shape[0]; ol = ln >> arity_bits
+    co = np.empty((ol, 2), np.uint64); vo = np.empty((ol, 2), np.uint64)
+    lib().orc_fri_fold(_p(c), ln, arity_bits, _p(_arr(beta)), int(shift_next), _p(co), _p(vo))
+    return co, vo

@@ -233,3 +233,31 @@ def eval_ext2(coeffs, x):
         acc = ((acc[0] + c % P * pw[0]) % P, (acc[1] + c % P * pw[1]) % P)
         pw = ext_mul(pw, x)
     return acc
+
+
+# --------------------------------------------------------------------------- FRI commit phase
+def fri_layer_commit(values, arity_bits, cap_height):
+    """[P2] fri/prover.rs fri_committed_trees, tree of one layer.  values: list of (re, im)."""
+    lg = len(values).bit_length() - 1
+    rev = [values[bitrev(k, lg)] for k in range(len(values))]
+    arity = 1 << arity_bits
+    leaves = [[x % P for pair in rev[j * arity:(j + 1) * arity] for x in pair]
+              for j in range(len(values) >> arity_bits)]
+    digests, cap = merkle_new(leaves, cap_height)
+    return leaves, digests, cap
+
+
+def fri_fold(coeffs, arity_bits, beta, shift_next):
+    """coeffs' = sum_i chunk[i] beta^i per chunk of `arity`; values' = coeffs'(shift_next * w^k)."""
+    arity = 1 << arity_bits
+    out = []
+    for j in range(len(coeffs) >> arity_bits):
+        acc, pw = (0, 0), (1, 0)
+        for i in range(arity):
+            t = ext_mul((coeffs[j * arity + i][0] % P, coeffs[j * arity + i][1] % P), pw)
+            acc = ((acc[0] + t[0]) % P, (acc[1] + t[1]) % P)
+            pw = ext_mul(pw, beta)
+        out.append(acc)
+    re = coset_fft([c[0] for c in out], shift_next)
+    im = coset_fft([c[1] for c in out], shift_next)
+    return out, list(zip(re, im))

@@ -522,3 +522,46 @@ void orc_eval_ext2(const uint64_t* const* cols, uint32_t ncols, uint64_t n, cons
     out[2 * c + 1] = a1;
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * FRI commit phase, one layer.  [P2] plonky2/src/fri/prover.rs fri_committed_trees.
+ * ---------------------------------------------------------------------------------------- */
+int orc_fri_layer_commit(const uint64_t* values_ext, uint64_t len, uint32_t arity_bits,
+                         uint32_t cap_height, uint64_t* leaves_out, uint64_t* digests_out,
+                         uint64_t* cap_out) {
+  int lg = log2_strict(len);
+  if (lg < 0 || (int)arity_bits > lg) return -1;
+  /* reverse_index_bits_in_place, then chunk: leaf j, slot i = values[bitrev(j * arity + i)] */
+  for (uint64_t k = 0; k < len; k++) {
+    uint64_t src = bitrev(k, (unsigned)lg);
+    leaves_out[2 * k] = canon(values_ext[2 * src]);
+    leaves_out[2 * k + 1] = canon(values_ext[2 * src + 1]);
+  }
+  return orc_merkle_new(leaves_out, len >> arity_bits, 2u << arity_bits, cap_height, digests_out, cap_out);
+}
+void orc_fri_fold(const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
+                  const uint64_t beta[2], uint64_t shift_next, uint64_t* coeffs_out,
+                  uint64_t* values_out) {
+  const uint64_t arity = 1ULL << arity_bits, out_len = len >> arity_bits;
+  const uint64_t b0 = canon(beta[0]), b1 = canon(beta[1]);
+  for (uint64_t j = 0; j < out_len; j++) {
+    uint64_t a0 = 0, a1 = 0; /* Horner: acc = acc * beta + chunk[i], i from high to low */
+    for (uint64_t i = arity; i-- > 0;) {
+      uint64_t n0 = add_(mul_(a0, b0), mul_(EXT_W, mul_(a1, b1)));
+      uint64_t n1 = add_(mul_(a0, b1), mul_(a1, b0));
+      a0 = add_(n0, canon(coeffs_ext[2 * (j * arity + i)]));
+      a1 = add_(n1, canon(coeffs_ext[2 * (j * arity + i) + 1]));
+    }
+    coeffs_out[2 * j] = a0;
+    coeffs_out[2 * j + 1] = a1;
+  }
+  /* coset_fft over the extension = the base-field transform applied to each component */
+  int lg = log2_strict(out_len);
+  uint64_t* tmp = (uint64_t*)malloc(sizeof(uint64_t) * out_len);
+  for (int comp = 0; comp < 2; comp++) {
+    for (uint64_t j = 0; j < out_len; j++) tmp[j] = coeffs_out[2 * j + comp];
+    orc_coset_fft(tmp, (unsigned)lg, shift_next);
+    for (uint64_t j = 0; j < out_len; j++) values_out[2 * j + comp] = tmp[j];
+  }
+  free(tmp);
+}

@@ -88,6 +88,19 @@ int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint
 void orc_eval_ext2(const uint64_t* const* cols, uint32_t ncols, uint64_t n, const uint64_t x[2],
                    uint64_t* out);
 
+/* [P2] plonky2/src/fri/prover.rs fri_committed_trees, one reduction layer (arity = 2^arity_bits) over
+ * D = 2 extension elements stored as (re, im) pairs:
+ *   commit: reverse_index_bits_in_place(values); leaves = chunks of `arity` values, flattened;
+ *           MerkleTree::new(leaves, cap_height).  leaves_out: (len/arity) x (2*arity).
+ *   fold:   coeffs' = chunks_exact(arity).map(reduce_with_powers(chunk, beta)) (= sum_i chunk[i] beta^i);
+ *           values' = coeffs'.coset_fft(shift_next) with shift_next = shift^arity (natural order). */
+int orc_fri_layer_commit(const uint64_t* values_ext, uint64_t len, uint32_t arity_bits,
+                         uint32_t cap_height, uint64_t* leaves_out, uint64_t* digests_out,
+                         uint64_t* cap_out);
+void orc_fri_fold(const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
+                  const uint64_t beta[2], uint64_t shift_next, uint64_t* coeffs_out,
+                  uint64_t* values_out);
+
 /* Threads used by the parallel regions (mirrors rayon's pool). */
 void orc_set_threads(int n);
 int orc_get_threads(void);

@@ -78,6 +78,12 @@ extern "C" {
                           points: *const u64, npoints: u32, out: *mut u64) -> c_int;
     pub fn vpbs_batch_eval_ext2(batch: *mut vpbs_batch, points: *const u64, npoints: u32,
                                 out: *mut u64) -> c_int;
+    pub fn vpbs_fri_layer_commit(ctx: *mut vpbs_ctx, values_ext: *const u64, len: u64, arity_bits: u32,
+                                 cap_height: u32, leaves_out: *mut u64, digests_out: *mut u64,
+                                 cap_out: *mut u64) -> c_int;
+    pub fn vpbs_fri_fold(ctx: *mut vpbs_ctx, coeffs_ext: *const u64, len: u64, arity_bits: u32,
+                         beta: *const u64, shift_next: u64, coeffs_out: *mut u64,
+                         values_out: *mut u64) -> c_int;
     pub fn vpbs_pow_grind(ctx: *mut vpbs_ctx, state: *const u64, witness_pos: u32, response_lane: u32,
                           min_leading_zeros: u32, first_candidate: u64, count: u64,
                           witness_out: *mut u64, found: *mut c_int) -> c_int;

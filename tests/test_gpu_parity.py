@@ -513,3 +513,43 @@ def test_resident_batch_openings(V, ctx, oracle):
     for p in range(2):
         assert np.array_equal(got[p], oracle.eval_ext2(ref["coeffs"], zeta[p]))
     rb.close()
+
+
+@pytest.mark.parametrize("log_len,arity_bits,cap_height", [(4, 2, 1), (8, 4, 4), (12, 4, 4),
+                                                            (19, 4, 4), (15, 4, 4), (6, 1, 0), (4, 4, 0)])
+def test_fri_commit_phase_layer(V, ctx, oracle, log_len, arity_bits, cap_height):
+    """One FRI reduction layer (tree of the bit-reversed, chunked values; fold with beta; next coset
+    evaluations) vs the oracle; shapes incl. the N=1024 proof's first layer (2^19 values, arity 16)."""
+    rng = np.random.default_rng(log_len * 10 + arity_bits)
+    vals = rand_u64(rng, (1 << log_len, 2), 0.02)
+    tree = V.fri_layer_commit(vals, arity_bits, cap_height, ctx)
+    ref = oracle.fri_layer_commit(vals, arity_bits, cap_height)
+    assert np.array_equal(tree.cap, ref["cap"])
+    assert np.array_equal(tree.digests, ref["digests"])
+    assert np.array_equal(tree.leaves, ref["leaves"])
+    if log_len <= 15:
+        beta = rng.integers(0, P, size=2, dtype=np.uint64)
+        shift = int(oracle.gl_pow(7, 1 << arity_bits))
+        co, vo = V.fri_fold(vals, arity_bits, beta, shift, ctx)
+        rco, rvo = oracle.fri_fold(vals, arity_bits, beta, shift)
+        assert np.array_equal(co, rco)
+        assert np.array_equal(vo, rvo)
+
+
+def test_fri_layers_chain_like_the_prover(V, ctx, oracle):
+    """Three chained layers as fri_committed_trees runs them (arity 16, shift <- shift^16):
+    values_k = coeffs_k.coset_fft(shift_k) must stay consistent layer after layer."""
+    rng = np.random.default_rng(5)
+    log_len, a = 14, 4
+    coeffs = rng.integers(0, P, size=(1 << log_len, 2), dtype=np.uint64)
+    shift = 7
+    values = np.stack([oracle.coset_fft(coeffs[:, 0].copy(), shift), oracle.coset_fft(coeffs[:, 1].copy(), shift)], 1)
+    for _ in range(3):
+        tree = V.fri_layer_commit(values, a, min(4, log_len - a), ctx)
+        assert np.array_equal(tree.cap, oracle.fri_layer_commit(values, a, min(4, log_len - a))["cap"])
+        beta = rng.integers(0, P, size=2, dtype=np.uint64)
+        shift = oracle.gl_pow(shift, 1 << a)
+        coeffs, values = V.fri_fold(coeffs, a, beta, shift, ctx)
+        log_len -= a
+        want = np.stack([oracle.coset_fft(coeffs[:, 0].copy(), shift), oracle.coset_fft(coeffs[:, 1].copy(), shift)], 1)
+        assert np.array_equal(values, want)

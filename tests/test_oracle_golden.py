@@ -160,3 +160,18 @@ def test_extension_evaluation_against_model(oracle):
         assert got == [list(model.eval_ext2(c, (x[0] % P, x[1] % P))) for c in cols]
     # X^2 = 7: evaluating the polynomial t^2 at the point X gives (7, 0)
     assert oracle.eval_ext2(np.array([[0, 0, 1, 0]], dtype=np.uint64), (0, 1)).tolist() == [[7, 0]]
+
+
+def test_fri_layer_against_model(oracle):
+    from oracle import model
+    rnd = random.Random(4)
+    for (lg, a, h) in [(4, 2, 1), (6, 4, 2), (5, 1, 0), (4, 4, 0)]:
+        vals = [(rnd.getrandbits(64), rnd.getrandbits(64)) for _ in range(1 << lg)]
+        r = oracle.fri_layer_commit(np.array(vals, dtype=np.uint64), a, h)
+        leaves, dig, cap = model.fri_layer_commit(vals, a, h)
+        assert r["leaves"].tolist() == leaves and r["digests"].tolist() == dig and r["cap"].tolist() == cap
+        beta = (rnd.getrandbits(64) % P, rnd.getrandbits(64) % P)
+        sh = rnd.getrandbits(64) % P
+        co, vo = oracle.fri_fold(np.array(vals, dtype=np.uint64), a, beta, sh)
+        mco, mvo = model.fri_fold(vals, a, beta, sh)
+        assert co.tolist() == [list(x) for x in mco] and vo.tolist() == [list(x) for x in mvo]

@@ -9,7 +9,8 @@ from ._lib import VpbsError, VpbsStats  # noqa: F401
 from .plonky2_api import (  # noqa: F401
     COSET_SHIFT, P, SALT_SIZE, Context, MerkleProof, MerkleTree, PolynomialBatch,
     ResidentMerkleTree, ResidentPolynomialBatch, commit_resident, coset_fft,
-    commit_device, commit_shard_device, default_context, eval_ext2, fft, fri_proof_of_work, hash_or_noop, ifft, lde_values,
+    commit_device, commit_shard_device, default_context, eval_ext2, fft, fri_fold, fri_layer_commit,
+    fri_proof_of_work, hash_or_noop, ifft, lde_values,
     log2_strict, poseidon, reverse_bits, synthetic_columns, two_to_one,
     verify_merkle_proof_to_cap)
 from .sharding import ShardPlan, commit_sharded, gather_cap, shard_plan  # noqa: F401,E402

@@ -69,6 +69,8 @@ SIGNATURES = {
                                          _c.POINTER(VpbsStats)]),
     "vpbs_eval_ext2": (_c.c_int, [_ctx, u64pp, _c.c_uint32, _c.c_uint32, u64p, _c.c_uint32, u64p]),
     "vpbs_batch_eval_ext2": (_c.c_int, [_c.c_void_p, u64p, _c.c_uint32, u64p]),
+    "vpbs_fri_layer_commit": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, _c.c_uint32, u64p, u64p, u64p]),
+    "vpbs_fri_fold": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, u64p, _c.c_uint64, u64p, u64p]),
     "vpbs_pow_grind": (_c.c_int, [_ctx, u64p, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint64,
                                   _c.c_uint64, u64p, _c.POINTER(_c.c_int)]),
     "vpbs_batch_commit": (_c.c_int, [_ctx, u64pp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32,

@@ -349,6 +349,42 @@ eval_ext2(const u64* __restrict__ coeffs, u64 col_stride, unsigned log_n,
   }
 }
 
+// ---- FRI commit-phase helpers (extension elements as (re, im) pairs) ---------------------------------
+// leaves[k] = canon(values[bitrev(k)]): reverse_index_bits_in_place + chunking is a pure re-indexing
+// because a leaf is `arity` consecutive elements of the reversed vector.
+__global__ void fri_gather_leaves(const ulonglong2* __restrict__ values, unsigned log_len,
+                                  ulonglong2* __restrict__ leaves) {
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (1ULL << log_len)) return;
+  const u64 src = log_len ? (__brevll(k) >> (64 - log_len)) : 0;
+  const ulonglong2 v = values[src];
+  leaves[k] = make_ulonglong2(gl::canon(v.x), gl::canon(v.y));
+}
+// coeffs'[j] = sum_i coeffs[j * arity + i] * beta^i  (Horner from the top); written interleaved to
+// `folded` and planar (re column, im column) to `planar` for the transform that follows.
+__global__ void fri_fold(const ulonglong2* __restrict__ coeffs, u64 out_len, unsigned arity_bits,
+                         u64 beta_re, u64 beta_im, ulonglong2* __restrict__ folded,
+                         u64* __restrict__ planar) {
+  const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= out_len) return;
+  const Ext2 beta{beta_re, beta_im};
+  const u64 arity = 1ULL << arity_bits;
+  Ext2 acc{0, 0};
+  for (u64 i = arity; i-- > 0;) {
+    const ulonglong2 c = coeffs[j * arity + i];
+    acc = ext_mul(acc, beta);
+    acc.re = gl::add(acc.re, gl::canon(c.x));
+    acc.im = gl::add(acc.im, gl::canon(c.y));
+  }
+  folded[j] = make_ulonglong2(acc.re, acc.im);
+  planar[j] = acc.re;
+  planar[out_len + j] = acc.im;
+}
+__global__ void interleave2(const u64* __restrict__ planar, u64 len, ulonglong2* __restrict__ out) {
+  const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < len) out[j] = make_ulonglong2(planar[j], planar[len + j]);
+}
+
 // ---- tables ------------------------------------------------------------------------------------
 // w[t] = omega_N^t for t < N/2.
 __global__ void fill_roots(u64* w, unsigned log_N) {

@@ -867,6 +867,77 @@ int vpbs_batch_eval_ext2(vpbs_batch* b, const uint64_t* points, uint32_t npoints
   return eval_ext2_device(ctx, b->coeffs, b->ncols, b->log_n, points, npoints, out);
 }
 
+// ---- FRI commit phase --------------------------------------------------------------------------------
+int vpbs_fri_layer_commit(vpbs_ctx* ctx, const uint64_t* values_ext, uint64_t len,
+                          uint32_t arity_bits, uint32_t cap_height, uint64_t* leaves_out,
+                          uint64_t* digests_out, uint64_t* cap_out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  const int lg = log2_strict(len);
+  if (lg < 0 || lg > 30) return fail(ctx, VPBS_ERR_ARG, "values.len() must be a power of two (<= 2^30)");
+  if ((int)arity_bits > lg) return fail(ctx, VPBS_ERR_ARG, "arity larger than the vector");
+  const u64 nleaves = len >> arity_bits;
+  const unsigned log_leaves = (unsigned)lg - arity_bits;
+  if (cap_height > log_leaves)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  if (!values_ext || !cap_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  const u64 ncap = 1ULL << cap_height, ndig = 2 * (nleaves - ncap);
+  if (ndig && !digests_out) return fail(ctx, VPBS_ERR_ARG, "digests_out == NULL");
+  u64 *dv = nullptr, *dl = nullptr, *dd = nullptr, *dc = nullptr;
+  if ((rc = arena_get(ctx, "in", len * 16, (void**)&dv))) return rc;
+  if ((rc = arena_get(ctx, "leaves", len * 16, (void**)&dl))) return rc;
+  if ((rc = arena_get(ctx, "digests", ndig * 32, (void**)&dd))) return rc;
+  if ((rc = arena_get(ctx, "cap", ncap * 32, (void**)&dc))) return rc;
+  CU(ctx, cudaMemcpyAsync(dv, values_ext, len * 16, cudaMemcpyHostToDevice, ctx->stream));
+  ntt::fri_gather_leaves<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(
+      (const ulonglong2*)dv, (unsigned)lg, (ulonglong2*)dl);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  if ((rc = merkle_build(ctx, dl, nleaves, 2u << arity_bits, log_leaves - cap_height, dd, dc))) return rc;
+  if (leaves_out) CU(ctx, cudaMemcpyAsync(leaves_out, dl, len * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ndig) CU(ctx, cudaMemcpyAsync(digests_out, dd, ndig * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(cap_out, dc, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_fri_fold(vpbs_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
+                  const uint64_t beta[2], uint64_t shift_next, uint64_t* coeffs_out,
+                  uint64_t* values_out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  const int lg = log2_strict(len);
+  if (lg < 0 || lg > 30) return fail(ctx, VPBS_ERR_ARG, "coeffs.len() must be a power of two (<= 2^30)");
+  if ((int)arity_bits > lg) return fail(ctx, VPBS_ERR_ARG, "arity larger than the vector");
+  if (!coeffs_ext || !beta || !coeffs_out || !values_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  const u64 out_len = len >> arity_bits;
+  const unsigned log_out = (unsigned)lg - arity_bits;
+  u64 *dc = nullptr, *df = nullptr, *dp = nullptr, *dw = nullptr, *dq = nullptr, *dv = nullptr;
+  if ((rc = arena_get(ctx, "in", len * 16, (void**)&dc))) return rc;
+  if ((rc = arena_get(ctx, "coeffs", out_len * 16, (void**)&df))) return rc;
+  if ((rc = arena_get(ctx, "pad", out_len * 16, (void**)&dp))) return rc;
+  if ((rc = arena_get(ctx, "work", out_len * 16, (void**)&dw))) return rc;
+  if ((rc = arena_get(ctx, "leaves", out_len * 16, (void**)&dq))) return rc;
+  if ((rc = arena_get(ctx, "rows", out_len * 16, (void**)&dv))) return rc;
+  if ((rc = ensure_roots(ctx, log_out))) return rc;
+  const u64* scale = nullptr;
+  if ((rc = get_coset_table(ctx, log_out, 0, shift_next, &scale))) return rc;
+  CU(ctx, cudaMemcpyAsync(dc, coeffs_ext, len * 16, cudaMemcpyHostToDevice, ctx->stream));
+  ntt::fri_fold<<<(unsigned)((out_len + 127) / 128), 128, 0, ctx->stream>>>(
+      (const ulonglong2*)dc, out_len, arity_bits, gl::canon(beta[0]), gl::canon(beta[1]),
+      (ulonglong2*)df, dp);
+  ctx->launches++;
+  if ((rc = run_transform<false>(ctx, dp, out_len, 2, log_out, dw, Out::Natural, dq, out_len, 0, scale, 1)))
+    return rc;
+  ntt::interleave2<<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->stream>>>(dq, out_len, (ulonglong2*)dv);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(coeffs_out, df, out_len * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(values_out, dv, out_len * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
 // ---- FRI proof of work -----------------------------------------------------------------------------
 int vpbs_pow_grind(vpbs_ctx* ctx, const uint64_t state[12], uint32_t witness_pos,
                    uint32_t response_lane, uint32_t min_leading_zeros, uint64_t first_candidate,

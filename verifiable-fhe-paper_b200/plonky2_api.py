@@ -211,6 +211,38 @@ def eval_ext2(coeff_cols, points, ctx: Optional[Context] = None) -> np.ndarray:
     return out
 
 
+def fri_layer_commit(values_ext, arity_bits: int, cap_height: int,
+                     ctx: Optional[Context] = None) -> MerkleTree:
+    """[P2] fri/prover.rs fri_committed_trees, the tree of one layer: values_ext (len, 2)."""
+    ctx = ctx or default_context()
+    v = _as_u64(values_ext).reshape(-1, 2)
+    ln = v.shape[0]
+    lg = log2_strict(ln)
+    if arity_bits > lg or cap_height > lg - arity_bits:
+        raise ValueError("cap_height should be at most log2(leaves.len())")
+    nl = ln >> arity_bits
+    leaves = np.empty((nl, 2 << arity_bits), np.uint64)
+    ndig = 2 * (nl - (1 << cap_height))
+    digests = np.empty((ndig, 4), np.uint64)
+    cap = np.empty((1 << cap_height, 4), np.uint64)
+    ctx.check(ctx.lib.vpbs_fri_layer_commit(ctx.handle, _ptr(v), ln, arity_bits, cap_height,
+                                            _ptr(leaves), _ptr(digests) if ndig else None, _ptr(cap)))
+    return MerkleTree(leaves, digests, cap)
+
+
+def fri_fold(coeffs_ext, arity_bits: int, beta, shift_next: int, ctx: Optional[Context] = None):
+    """[P2] fri_committed_trees fold: (coeffs' (len/arity, 2), values' = coeffs'.coset_fft(shift_next))."""
+    ctx = ctx or default_context()
+    c = _as_u64(coeffs_ext).reshape(-1, 2)
+    ln = c.shape[0]
+    log2_strict(ln)
+    ol = ln >> arity_bits
+    co, vo = np.empty((ol, 2), np.uint64), np.empty((ol, 2), np.uint64)
+    ctx.check(ctx.lib.vpbs_fri_fold(ctx.handle, _ptr(c), ln, arity_bits, _ptr(_as_u64(beta).reshape(2)),
+                                    int(shift_next) % 2**64, _ptr(co), _ptr(vo)))
+    return co, vo
+
+
 def fri_proof_of_work(state, witness_pos: int, min_leading_zeros: int, first_candidate: int = 0,
                       count: int = 1 << 32, response_lane: int = 7, ctx: Optional[Context] = None):
     """[P2] fri/prover.rs fri_proof_of_work on a duplex state: smallest witness in
