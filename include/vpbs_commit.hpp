@@ -221,4 +221,102 @@ class PolynomialBatch {
   }
 };
 
+
+// ---- PolynomialBatch kept in HBM: MerkleTree::get / prove and openings served on demand ----------
+class ResidentBatch {
+ public:
+  std::vector<HashOut> cap;
+  unsigned degree_log = 0, rate_bits = 0;
+  std::size_t ncols = 0, width = 0;
+
+  ResidentBatch(const Context& ctx, const std::vector<std::vector<F>>& cols, unsigned rate_bits_,
+                unsigned cap_height, bool inputs_are_coeffs)
+      : ctx_(ctx) {
+    if (cols.empty()) throw std::invalid_argument("empty batch");
+    degree_log = log2_strict(cols[0].size());
+    rate_bits = rate_bits_;
+    ncols = width = cols.size();
+    if (cap_height > degree_log + rate_bits)
+      throw std::invalid_argument("cap_height should be at most log2(leaves.len())");
+    std::vector<const F*> in(ncols);
+    for (std::size_t c = 0; c < ncols; c++) in[c] = cols[c].data();
+    cap.resize(std::size_t(1) << cap_height);
+    ctx.check(vpbs_batch_commit(ctx.get(), in.data(), (uint32_t)ncols, degree_log, rate_bits,
+                                cap_height, inputs_are_coeffs ? 1 : 0, nullptr, cap[0].elements, &h_,
+                                nullptr));
+  }
+  ~ResidentBatch() { vpbs_batch_destroy(h_); }
+  ResidentBatch(const ResidentBatch&) = delete;
+  ResidentBatch& operator=(const ResidentBatch&) = delete;
+
+  std::vector<F> get(std::size_t leaf_index) const {  // MerkleTree::get
+    std::vector<F> row(width);
+    uint64_t idx = leaf_index;
+    ctx_.check(vpbs_batch_get_leaves(h_, &idx, 1, row.data()));
+    return row;
+  }
+  MerkleProof prove(std::size_t leaf_index) const {  // MerkleTree::prove
+    MerkleProof p;
+    p.siblings.resize(degree_log + rate_bits - log2_strict(cap.size()));
+    uint64_t idx = leaf_index;
+    ctx_.check(vpbs_batch_prove(h_, &idx, 1, p.siblings.empty() ? nullptr : p.siblings[0].elements));
+    return p;
+  }
+  std::vector<F> get_lde_values(std::size_t index, std::size_t step = 1) const {
+    return get(reverse_bits(index * step, degree_log + rate_bits));
+  }
+  // openings of every polynomial at one point of F[X]/(X^2 - 7): ncols x (re, im)
+  std::vector<F> eval_ext2(const F (&point)[2]) const {
+    std::vector<F> out(2 * ncols);
+    ctx_.check(vpbs_batch_eval_ext2(h_, point, 1, out.data()));
+    return out;
+  }
+
+ private:
+  const Context& ctx_;
+  vpbs_batch* h_ = nullptr;
+};
+
+// ---- fri/prover.rs ------------------------------------------------------------------------------
+// fri_committed_trees, one layer: values are (re, im) pairs, flat.
+inline MerkleTree fri_layer_commit(const Context& ctx, const std::vector<F>& values_ext,
+                                   unsigned arity_bits, unsigned cap_height) {
+  const std::size_t len = values_ext.size() / 2;
+  const unsigned lg = log2_strict(len);
+  if (arity_bits > lg || cap_height > lg - arity_bits)
+    throw std::invalid_argument("cap_height should be at most log2(leaves.len())");
+  MerkleTree t;
+  t.leaf_len = std::size_t(2) << arity_bits;
+  t.leaves.resize(2 * len);
+  t.digests.resize(2 * ((len >> arity_bits) - (std::size_t(1) << cap_height)));
+  t.cap.resize(std::size_t(1) << cap_height);
+  ctx.check(vpbs_fri_layer_commit(ctx.get(), values_ext.data(), len, arity_bits, cap_height,
+                                  t.leaves.data(), t.digests.empty() ? nullptr : t.digests[0].elements,
+                                  t.cap[0].elements));
+  return t;
+}
+struct FriFold {
+  std::vector<F> coeffs, values;  // (re, im) pairs
+};
+inline FriFold fri_fold(const Context& ctx, const std::vector<F>& coeffs_ext, unsigned arity_bits,
+                        const F (&beta)[2], F shift_next) {
+  const std::size_t len = coeffs_ext.size() / 2;
+  log2_strict(len);
+  FriFold r;
+  r.coeffs.resize(2 * (len >> arity_bits));
+  r.values.resize(2 * (len >> arity_bits));
+  ctx.check(vpbs_fri_fold(ctx.get(), coeffs_ext.data(), len, arity_bits, beta, shift_next,
+                          r.coeffs.data(), r.values.data()));
+  return r;
+}
+// fri_proof_of_work: smallest witness in [first, first + count), or -1 if none.
+inline long long fri_proof_of_work(const Context& ctx, const F (&state)[12], unsigned witness_pos,
+                                   unsigned min_leading_zeros, uint64_t first = 0,
+                                   uint64_t count = uint64_t(1) << 32) {
+  uint64_t w = 0;
+  int found = 0;
+  ctx.check(vpbs_pow_grind(ctx.get(), state, witness_pos, 7, min_leading_zeros, first, count, &w, &found));
+  return found ? (long long)w : -1;
+}
+
 }  // namespace vpbs

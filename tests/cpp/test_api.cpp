@@ -72,6 +72,53 @@ int main() {
     auto back = vpbs::ifft(ctx, ev);
     for (std::size_t i = 0; i < v.size(); i++) CHECK(back[i] == v[i] % ORC_P);
   }
+  // resident batch: lazy get / prove / openings; FRI layer + fold; PoW
+  {
+    const unsigned log_n = 9, ncols = 20, rate_bits = 3, cap_height = 4;
+    const std::size_t n = std::size_t(1) << log_n, m = n << rate_bits;
+    std::vector<std::vector<F>> values(ncols, std::vector<F>(n));
+    for (auto& col : values)
+      for (auto& x : col) x = rng();
+    vpbs::ResidentBatch rb(ctx, values, rate_bits, cap_height, false);
+    auto eager = vpbs::PolynomialBatch::from_values(ctx, values, rate_bits, false, cap_height);
+    CHECK(std::memcmp(rb.cap.data(), eager.merkle_tree.cap.data(), rb.cap.size() * 32) == 0);
+    for (std::size_t i : {std::size_t(1), m / 2 + 3, m - 1}) {
+      auto row = rb.get(i);
+      CHECK(std::memcmp(row.data(), eager.merkle_tree.get(i), ncols * 8) == 0);
+      auto p1 = rb.prove(i), p2 = eager.merkle_tree.prove(i);
+      CHECK(p1.siblings.size() == p2.siblings.size());
+      CHECK(std::memcmp(p1.siblings.data(), p2.siblings.data(), p1.siblings.size() * 32) == 0);
+    }
+    const F zeta[2] = {rng(), rng()};
+    auto op = rb.eval_ext2(zeta);
+    std::vector<const uint64_t*> cp(ncols);
+    for (unsigned c = 0; c < ncols; c++) cp[c] = eager.polynomials[c].data();
+    std::vector<uint64_t> want(2 * ncols);
+    orc_eval_ext2(cp.data(), ncols, n, zeta, want.data());
+    CHECK(op == want);
+
+    std::vector<F> ext(2 * 4096);
+    for (auto& x : ext) x = rng() % ORC_P;
+    auto tree = vpbs::fri_layer_commit(ctx, ext, 4, 4);
+    std::vector<uint64_t> ol(ext.size()), od(8 * (256 - 16)), oc(64);
+    CHECK(orc_fri_layer_commit(ext.data(), 4096, 4, 4, ol.data(), od.data(), oc.data()) == 0);
+    CHECK(std::memcmp(tree.cap.data(), oc.data(), 64 * 8) == 0 && tree.leaves == ol);
+    const F beta[2] = {rng() % ORC_P, rng() % ORC_P};
+    auto fold = vpbs::fri_fold(ctx, ext, 4, beta, 33232930569601ULL /* 7^16 */);
+    std::vector<uint64_t> fc(512), fv(512);
+    orc_fri_fold(ext.data(), 4096, 4, beta, 33232930569601ULL, fc.data(), fv.data());
+    CHECK(fold.coeffs == fc && fold.values == fv);
+
+    F st[12];
+    for (auto& x : st) x = rng() % ORC_P;
+    long long w = vpbs::fri_proof_of_work(ctx, st, 4, 10);
+    CHECK(w >= 0);
+    uint64_t chk[12];
+    std::memcpy(chk, st, sizeof chk);
+    chk[4] = (uint64_t)w;
+    orc_poseidon(chk);
+    CHECK((chk[7] >> 54) == 0);
+  }
   // failure behaviour: what plonky2 asserts on
   bool threw = false;
   try {
