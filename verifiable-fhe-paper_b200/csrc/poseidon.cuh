@@ -64,6 +64,34 @@ __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
   return ((u64)r1 << 32) | r0;
 }
 
+// Recombine two biased accumulators into one state word, with NO conditional fix-up.
+//   dlo = 2^52 + L, dhi = 2^52 + H  (L, H < 2^42 exact integers): the low words of the doubles are
+//   l0 = L mod 2^32 and h0 = H mod 2^32, the high words are 0x43300000 + l1 and 0x43300000 + h1
+//   with l1, h1 < 2^10.   value = L + 2^32 H = l0 + (l1 + h0) 2^32 + h1 2^64,  2^64 = 2^32 - 1:
+//       value = (l0 - h1 - c) + (m + c) 2^32,   m + c 2^32 = l1 + h0 + h1.
+//   The low part can only borrow when h1 + c >= 1, and then m + c >= 1 absorbs the borrow; the
+//   high part cannot exceed 2^32 - 1 (if c = 1 then m < 2^11): the result is exact as is.
+__device__ __forceinline__ u64 combine_biased(double dlo, double dhi) {
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 l0, lh, h0, hh, h1, s1, m, c, kc;\n\t"
+      "mov.b64 {l0, lh}, %2;\n\t"
+      "mov.b64 {h0, hh}, %3;\n\t"
+      "add.u32 h1, hh, 0xbcd00000;\n\t"      // hh - 0x43300000
+      "add.u32 s1, lh, h1;\n\t"
+      "add.u32 s1, s1, 0xbcd00000;\n\t"      // l1 + h1
+      "add.cc.u32 m, s1, h0;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "add.u32 kc, h1, c;\n\t"
+      "add.u32 m, m, c;\n\t"
+      "sub.cc.u32 %0, l0, kc;\n\t"
+      "subc.u32 %1, m, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "d"(dlo), "d"(dhi));
+  return ((u64)r1 << 32) | r0;
+}
+
 // ---- MDS layer --------------------------------------------------------------------------------
 // Two implementations, selected at compile time: the FP64 form (default — fastest measured on
 // B200: 8.85 ms for 8.39 M permutations) and, with -DVPBS_MDS_INT32, a pure 32-bit integer form
@@ -287,18 +315,23 @@ __device__ __forceinline__ void mds_begin(MdsAcc& a, int next_round) {
   }
 }
 // feed state words T and T + 6 (final for this round) into all accumulators
+// biased view of a 32-bit half: the double 2^52 + x (no arithmetic, just a register pair)
+__device__ __forceinline__ double half_biased(u32 x) { return __hiloint2double(0x43300000, (int)x); }
 template <int T>
 __device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
-  const double al = half_to_f64((u32)s[T]), ah = half_to_f64((u32)(s[T] >> 32));
-  const double bl = half_to_f64((u32)s[T + 6]), bh = half_to_f64((u32)(s[T + 6] >> 32));
+  // p = x_T + x_{T+6}, m = x_T - x_{T+6} straight from the biased views: (2^52 + a) - (2^52 + b)
+  // is a - b, and (2^52 + a) + ((2^52 + b) - 2^53) is a + b; every step is exact (|.| < 2^53).
+  const double TWO53 = 9007199254740992.0;
+  const double cal = half_biased((u32)s[T]), cah = half_biased((u32)(s[T] >> 32));
+  const double cbl = half_biased((u32)s[T + 6]), cbh = half_biased((u32)(s[T + 6] >> 32));
   if constexpr (T == 0) {
-    a.x0l = al;
-    a.x0h = ah;
+    a.x0l = cal - 4503599627370496.0;
+    a.x0h = cah - 4503599627370496.0;
   }
-  mds_split::col<T, 0>(al + bl, ah + bh, al - bl, ah - bh, a.zpl, a.zph, a.zml, a.zmh);
+  mds_split::col<T, 0>(cal + (cbl - TWO53), cah + (cbh - TWO53), cal - cbl, cah - cbh, a.zpl, a.zph,
+                       a.zml, a.zmh);
 }
 __device__ __forceinline__ void mds_finish(MdsAcc& a, u64 (&s)[WIDTH]) {
-  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
   const double BIAS = 4503599627370496.0;  // 2^52
 #pragma unroll
   for (int r = 0; r < 6; r++) {
@@ -308,10 +341,8 @@ __device__ __forceinline__ void mds_finish(MdsAcc& a, u64 (&s)[WIDTH]) {
       s1l = fma(a.x0l, 16.0, s1l);
       s1h = fma(a.x0h, 16.0, s1h);
     }
-    s[r] = reduce96((u64)__double_as_longlong(fma(s1l, 0.5, BIAS)) & MANT,
-                    (u64)__double_as_longlong(fma(s1h, 0.5, BIAS)) & MANT);
-    s[r + 6] = reduce96((u64)__double_as_longlong(fma(s2l, 0.5, BIAS)) & MANT,
-                        (u64)__double_as_longlong(fma(s2h, 0.5, BIAS)) & MANT);
+    s[r] = combine_biased(fma(s1l, 0.5, BIAS), fma(s1h, 0.5, BIAS));
+    s[r + 6] = combine_biased(fma(s2l, 0.5, BIAS), fma(s2h, 0.5, BIAS));
   }
 }
 #define VPBS_MDS_INTERLEAVED 1
