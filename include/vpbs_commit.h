@@ -51,8 +51,10 @@ typedef struct vpbs_ctx vpbs_ctx;
  * /root/reference/src/vtfhe/ivc_based_vpbs.rs:301-309).  "transpose LDEs" is fused into the last
  * NTT pass here, so it is reported inside fft_ms. */
 typedef struct vpbs_stats {
-  float h2d_ms;    /* host -> device copies of the inputs (0 for *_dev calls)      */
-  float ifft_ms;   /* "IFFT"                                                       */
+  float h2d_ms;    /* host -> device copies of the inputs (0 for *_dev calls); for wide
+                      batches they are pipelined with the transforms (see fft_ms)  */
+  float ifft_ms;   /* "IFFT" (0 when the host API pipelines by column chunk: then
+                      the IFFTs are interleaved with the LDEs and counted there)   */
   float fft_ms;    /* "FFT + blinding" + "transpose LDEs"                          */
   float merkle_ms; /* "build Merkle tree" (leaf hashing + all levels)              */
   float leaf_hash_ms; /* the leaf-hashing kernel alone (part of merkle_ms)        */

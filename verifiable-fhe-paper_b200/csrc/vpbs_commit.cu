@@ -51,6 +51,7 @@ struct vpbs_ctx {
   cudaEvent_t ev[10] = {};
   // host API: device->host copies run on their own stream, overlapped with the remaining kernels
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t h2d_stream = nullptr;  // inputs of wide batches arrive chunk by chunk on this one
   std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
   // Buffers of destroyed resident batches, kept for the next batch of the same shape (a prover
   // commits the same shapes every step; cudaMalloc/cudaFree of ~0.6 GB cost milliseconds).
@@ -315,6 +316,12 @@ int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, uns
 struct Overlap {
   cudaEvent_t coeffs_ready = nullptr;      // after the IFFT
   std::vector<cudaEvent_t> block_ready;    // after LDE block b (its n leaf rows are final)
+  // Column-chunked mode (host API, wide batches): the inputs of chunk k arrive on another stream
+  // (wait h2d_ready[k]); chunk k's coefficients are final at coeffs_chunk_ready[k]; the leaf
+  // matrix is final at lde_done.  chunk_cols == 0: all columns at once (events above).
+  u32 chunk_cols = 0;
+  std::vector<cudaEvent_t> h2d_ready, coeffs_chunk_ready;
+  cudaEvent_t lde_done = nullptr;
 };
 
 struct Timer {
@@ -368,32 +375,45 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
     return rc;
 
   tm->mark();  // 0
-  // "IFFT": values -> coefficients (natural order), scaled by n^-1.
-  const u64* coeffs = d_cols;
-  if (!inputs_are_coeffs) {
-    u64* cbuf = d_coeffs_out;
-    if (!cbuf && (rc = arena_get(ctx, "coeffs", (size_t)ncols * n * sizeof(u64), (void**)&cbuf)))
-      return rc;
-    const u64 n_inv = gl::inv(n % gl::P);
-    if ((rc = run_transform<true>(ctx, d_cols, n, ncols, log_n, work, Out::Natural, cbuf, n, 0,
-                                  nullptr, n_inv)) != VPBS_OK)
-      return rc;
-    coeffs = cbuf;
-  } else if (d_coeffs_out && d_coeffs_out != d_cols) {
-    CU(ctx, cudaMemcpyAsync(d_coeffs_out, d_cols, (size_t)ncols * n * sizeof(u64),
-                            cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  tm->mark();  // 1
-  if (tm->overlap && tm->overlap->coeffs_ready) cudaEventRecord(tm->overlap->coeffs_ready, ctx->stream);
-  // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
-  // leaf rows.
   const u64 b0 = first_leaf >> log_n, nb = nleaves_shard >> log_n;
-  for (u64 b = 0; b < nb; b++) {
-    if ((rc = run_transform<false>(ctx, coeffs, n, ncols, log_n, work, Out::Leaf, d_leaves, width,
-                                   b << log_n, coset + ((b0 + b) << log_n), 1)) != VPBS_OK)
-      return rc;
-    if (tm->overlap && !d_salt && b < tm->overlap->block_ready.size())
-      cudaEventRecord(tm->overlap->block_ready[b], ctx->stream);
+  const u64 n_inv = gl::inv(n % gl::P);
+  u64* cbuf = d_coeffs_out;
+  if (!inputs_are_coeffs && !cbuf &&
+      (rc = arena_get(ctx, "coeffs", (size_t)ncols * n * sizeof(u64), (void**)&cbuf)))
+    return rc;
+  Overlap* ov = tm->overlap;
+  const u32 chunk = (ov && ov->chunk_cols && ov->chunk_cols < ncols) ? ov->chunk_cols : ncols;
+  const bool chunked = chunk < ncols;
+  if (chunked) tm->mark();  // 1: pipelined mode reports all transforms under "FFT + blinding"
+  for (u32 c0 = 0, k = 0; c0 < ncols; c0 += chunk, k++) {
+    const u32 nc = ncols - c0 < chunk ? ncols - c0 : chunk;
+    if (chunked && k < ov->h2d_ready.size()) CU(ctx, cudaStreamWaitEvent(ctx->stream, ov->h2d_ready[k], 0));
+    // "IFFT": values -> coefficients (natural order), scaled by n^-1.
+    const u64* coeffs = d_cols + (u64)c0 * n;
+    if (!inputs_are_coeffs) {
+      if ((rc = run_transform<true>(ctx, d_cols + (u64)c0 * n, n, nc, log_n, work, Out::Natural,
+                                    cbuf + (u64)c0 * n, n, 0, nullptr, n_inv)) != VPBS_OK)
+        return rc;
+      coeffs = cbuf + (u64)c0 * n;
+    } else if (d_coeffs_out && d_coeffs_out != d_cols) {
+      CU(ctx, cudaMemcpyAsync(d_coeffs_out + (u64)c0 * n, d_cols + (u64)c0 * n,
+                              (size_t)nc * n * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (!chunked) {
+      tm->mark();  // 1
+      if (ov && ov->coeffs_ready) cudaEventRecord(ov->coeffs_ready, ctx->stream);
+    } else if (k < ov->coeffs_chunk_ready.size()) {
+      cudaEventRecord(ov->coeffs_chunk_ready[k], ctx->stream);
+    }
+    // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
+    // leaf rows (columns c0 .. c0 + nc of the row-major matrix).
+    for (u64 b = 0; b < nb; b++) {
+      if ((rc = run_transform<false>(ctx, coeffs, n, nc, log_n, work, Out::Leaf, d_leaves + c0, width,
+                                     b << log_n, coset + ((b0 + b) << log_n), 1)) != VPBS_OK)
+        return rc;
+      if (!chunked && ov && !d_salt && b < ov->block_ready.size())
+        cudaEventRecord(ov->block_ready[b], ctx->stream);
+    }
   }
   if (d_salt) {
     const u64 cnt = nleaves_shard * 4;
@@ -401,6 +421,7 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
         d_salt, m, log_m, first_leaf, nleaves_shard, d_leaves, width, ncols);
     ctx->launches++;
   }
+  if (ov && ov->lde_done) cudaEventRecord(ov->lde_done, ctx->stream);
   tm->mark();  // 2
   // "build Merkle tree"
   if ((rc = merkle_build(ctx, d_leaves, nleaves_shard, width, log_sub, d_digests, d_roots,
@@ -458,6 +479,7 @@ int vpbs_ctx_create(int device, vpbs_ctx** out) {
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
   for (int i = 0; e == cudaSuccess && i < 10; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     fail(nullptr, VPBS_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
@@ -482,6 +504,7 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   for (auto& kv : ctx->pool) cudaFree(kv.second);
   for (cudaEvent_t e : ctx->ov) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -752,10 +775,36 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
 
   const uint64_t l0 = ctx->launches;
   cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
-  if (stats) cudaEventRecord(e0, ctx->stream);
-  for (u32 c = 0; c < ncols; c++) {
+  for (u32 c = 0; c < ncols; c++)
     if (!cols[c]) return fail(ctx, VPBS_ERR_ARG, "cols[c] == NULL");
-    CU(ctx, cudaMemcpyAsync(din + (u64)c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // Wide batches are pipelined by column chunk: chunk k's inputs travel on the H2D stream while
+  // chunk k-1 is already being transformed (IFFT + all LDE blocks of its columns).
+  const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? 32 : 0;
+  const u32 nchunks = chunk_cols ? (ncols + chunk_cols - 1) / chunk_cols : 0;
+  const u64 nblocks = 1ULL << rate_bits;
+  while (ctx->ov.size() < nblocks + 2 * (u64)nchunks + 4) {
+    cudaEvent_t e;
+    CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ov.push_back(e);
+  }
+  Overlap ovl;
+  size_t evi = 0;
+  ovl.coeffs_ready = ctx->ov[evi++];
+  cudaEvent_t all_done = ctx->ov[evi++];
+  ovl.lde_done = ctx->ov[evi++];
+  ovl.block_ready.assign(ctx->ov.begin() + evi, ctx->ov.begin() + evi + nblocks);
+  evi += nblocks;
+  if (nchunks) {
+    ovl.chunk_cols = chunk_cols;
+    ovl.h2d_ready.assign(ctx->ov.begin() + evi, ctx->ov.begin() + evi + nchunks);
+    evi += nchunks;
+    ovl.coeffs_chunk_ready.assign(ctx->ov.begin() + evi, ctx->ov.begin() + evi + nchunks);
+  }
+  cudaStream_t hs = nchunks ? ctx->h2d_stream : ctx->stream;
+  if (stats) cudaEventRecord(e0, ctx->stream);
+  if (nchunks) {  // the H2D stream starts after whatever the caller queued on the compute stream
+    CU(ctx, cudaEventRecord(all_done, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(hs, all_done, 0));
   }
   if (salt_cols)
     for (int s = 0; s < VPBS_SALT_SIZE; s++) {
@@ -763,46 +812,44 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
       CU(ctx, cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice,
                               ctx->stream));
     }
-  if (stats) cudaEventRecord(e1, ctx->stream);
-  // Output copies run on the copy stream as soon as their data is final: coefficients after the
-  // IFFT, each n-row leaf block after its last NTT pass, digests and cap after the tree.  All
-  // kernels are enqueued first, so the copies overlap the remaining NTT passes and the hashing.
-  const u64 nblocks = 1ULL << rate_bits;
-  while (ctx->ov.size() < nblocks + 2) {
-    cudaEvent_t e;
-    CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->ov.push_back(e);
+  for (u32 c = 0; c < ncols; c++) {
+    CU(ctx, cudaMemcpyAsync(din + (u64)c * n, cols[c], n * 8, cudaMemcpyHostToDevice, hs));
+    if (nchunks && ((c + 1) % chunk_cols == 0 || c + 1 == ncols))
+      CU(ctx, cudaEventRecord(ovl.h2d_ready[c / chunk_cols], hs));
   }
-  Overlap ovl;
-  ovl.coeffs_ready = ctx->ov[0];
-  ovl.block_ready.assign(ctx->ov.begin() + 1, ctx->ov.begin() + 1 + nblocks);
-  cudaEvent_t all_done = ctx->ov[nblocks + 1];
+  if (stats) cudaEventRecord(e1, hs);
+  // Output copies run on the copy stream as soon as their data is final: coefficients after the
+  // IFFT, leaf rows after their last NTT pass, digests and cap after the tree.  All kernels are
+  // enqueued first, so the copies overlap the remaining NTT passes and the hashing.
   Timer tm{ctx, stats != nullptr};
   tm.overlap = &ovl;
   rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
                    inputs_are_coeffs ? nullptr : dco, dle, ddi, dca, &tm);
-  if (rc) return rc;
+  if (rc) {
+    cudaStreamSynchronize(hs);
+    return rc;
+  }
   CU(ctx, cudaEventRecord(all_done, ctx->stream));
   if (stats) cudaEventRecord(e2, ctx->stream);
   cudaStream_t cs = ctx->copy_stream;
   if (coeffs_out) {
     const u64* csrc = inputs_are_coeffs ? din : dco;
-    CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_ready, 0));
-    for (u32 c = 0; c < ncols; c++)
+    for (u32 c = 0; c < ncols; c++) {
+      if (!nchunks && c == 0) CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_ready, 0));
+      if (nchunks && c % chunk_cols == 0)
+        CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_chunk_ready[c / chunk_cols], 0));
       if (coeffs_out[c])
         CU(ctx, cudaMemcpyAsync(coeffs_out[c], csrc + (u64)c * n, n * 8, cudaMemcpyDeviceToHost, cs));
+    }
   }
   if (leaves_out) {
-    if (salt_cols) {  // salt columns are scattered after the last block: leaves final only then
-      CU(ctx, cudaStreamWaitEvent(cs, all_done, 0));
-      CU(ctx, cudaMemcpyAsync(leaves_out, dle, (size_t)m * width * 8, cudaMemcpyDeviceToHost, cs));
-    } else {
-      const size_t block_elems = (size_t)n * width;
-      for (u64 blk = 0; blk < nblocks; blk++) {
-        CU(ctx, cudaStreamWaitEvent(cs, ovl.block_ready[blk], 0));
-        CU(ctx, cudaMemcpyAsync(leaves_out + blk * block_elems, dle + blk * block_elems,
-                                block_elems * 8, cudaMemcpyDeviceToHost, cs));
-      }
+    const size_t block_elems = (size_t)n * width;
+    if (nchunks || salt_cols)  // rows are final only after the last column chunk / the salt scatter
+      CU(ctx, cudaStreamWaitEvent(cs, ovl.lde_done, 0));
+    for (u64 blk = 0; blk < nblocks; blk++) {
+      if (!nchunks && !salt_cols) CU(ctx, cudaStreamWaitEvent(cs, ovl.block_ready[blk], 0));
+      CU(ctx, cudaMemcpyAsync(leaves_out + blk * block_elems, dle + blk * block_elems,
+                              block_elems * 8, cudaMemcpyDeviceToHost, cs));
     }
   }
   CU(ctx, cudaStreamWaitEvent(cs, all_done, 0));
@@ -812,6 +859,7 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
   if (stats) cudaEventRecord(e3, cs);
   CU(ctx, cudaStreamSynchronize(cs));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nchunks) CU(ctx, cudaStreamSynchronize(hs));
   if (stats) {
     memset(stats, 0, sizeof *stats);
     fill_stats(stats, tm, ctx->launches - l0);
