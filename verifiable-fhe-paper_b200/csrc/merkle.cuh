@@ -58,7 +58,7 @@ __device__ __forceinline__ u64 leaf_digest_pos(u64 l) { return 4 * (l >> 1) + (l
 #define VPBS_HASH_THREADS 128
 #endif
 #ifndef VPBS_HASH_MIN_BLOCKS
-#define VPBS_HASH_MIN_BLOCKS 5  // <= 102 registers: 7.77 ms vs 7.87 (4) / 8.9 (unbounded, 164 regs) at 2^19 x 128
+#define VPBS_HASH_MIN_BLOCKS 4  // <= 128 registers: no spills around the S-box calls (6.79 ms; 5 -> 7.10 ms, 6 -> 7.35 ms)
 #endif
 // One thread per leaf.  all_cap: the tree has no digests, leaf hashes are the cap.
 __global__ void __launch_bounds__(VPBS_HASH_THREADS, VPBS_HASH_MIN_BLOCKS)

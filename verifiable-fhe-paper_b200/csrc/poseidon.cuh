@@ -345,6 +345,116 @@ __device__ __forceinline__ void mds_finish(MdsAcc& a, u64 (&s)[WIDTH]) {
     s[r + 6] = combine_biased(fma(s2l, 0.5, BIAS), fma(s2h, 0.5, BIAS));
   }
 }
+// ---- two partial rounds at once ---------------------------------------------------------------------
+// In a partial round only lane 0 goes through the S-box, so two consecutive partial rounds are
+//   u  = (sbox(s_0), s_1 .. s_11)                x'  = M u + RC_{r+1}
+//   x'' = M (x' + delta e_0) + RC_{r+2},         delta = sbox(x'_0) - x'_0
+//       = M^2 u + (M RC_{r+1} + RC_{r+2}) + delta M e_0.
+// With M = C + 8 e_0 e_0^T (C circulant):  M^2 u = C^2 u + 8 u_0 C e_0 + 8 (M u)_0 e_0, and
+// (M u)_0 + delta = sbox(x'_0) - RC_{r+1,0}, so
+//   x'' = C^2 u + (8 u_0 + delta) C e_0 + 8 sbox(x'_0) e_0 + K',
+//   K'  = M RC_{r+1} + RC_{r+2} - 8 RC_{r+1,0} e_0    (precomputed, poseidon_rcp.inc).
+// C^2 is circulant too (constants c (*) c, row sum 2^16), so ONE split convolution serves both
+// rounds: the entries are < 2^13, every partial sum stays below 2^50 and is exact in a double.  Per
+// pair this is ~290 FP64 instructions and 13 recombinations instead of 2 x (236 and 12); x'_0
+// itself only needs row 0 of C u, which falls out of the same p_t / m_t inputs
+// ((C u)_0 = 1/2 sum_t (c+_t p_t + c-_t m_t)).
+__constant__ double RCP[11 * 24] = {
+#include "poseidon_rcp.inc"
+};
+namespace mds_pair {
+constexpr int CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+__host__ __device__ constexpr int cc(int d) {  // (c (*) c)_d, cyclic
+  int v = 0;
+  for (int a = 0; a < WIDTH; a++) v += CIRC[a] * CIRC[(d - a + WIDTH) % WIDTH];
+  return v;
+}
+__host__ __device__ constexpr double ccplus(int j) { return (double)(cc(j) + cc(j + 6)); }
+__host__ __device__ constexpr double ccminus(int j) { return (double)(cc(j) - cc(j + 6)); }
+template <int T, int R>
+__device__ __forceinline__ void col(double pl, double ph, double ml, double mh, double (&zpl)[6],
+                                    double (&zph)[6], double (&zml)[6], double (&zmh)[6]) {
+  constexpr int J = (T - R + 6) % 6;
+  constexpr double CP = ccplus(J);
+  constexpr double CM = (J + R < 6) ? ccminus(J) : -ccminus(J);
+  zpl[R] = fma(pl, CP, zpl[R]);
+  zph[R] = fma(ph, CP, zph[R]);
+  zml[R] = fma(ml, CM, zml[R]);
+  zmh[R] = fma(mh, CM, zmh[R]);
+  if constexpr (R + 1 < 6) col<T, R + 1>(pl, ph, ml, mh, zpl, zph, zml, zmh);
+}
+// words T and T + 6 of u into the C^2 accumulators and into row 0 of C u (xl, xh)
+template <int T>
+__device__ __forceinline__ void absorb(MdsAcc& a, const u64 (&s)[WIDTH], double& xl, double& xh) {
+  const double TWO53 = 9007199254740992.0;
+  const double cal = half_biased((u32)s[T]), cah = half_biased((u32)(s[T] >> 32));
+  const double cbl = half_biased((u32)s[T + 6]), cbh = half_biased((u32)(s[T + 6] >> 32));
+  const double pl = cal + (cbl - TWO53), ph = cah + (cbh - TWO53), ml = cal - cbl, mh = cah - cbh;
+  if constexpr (T == 0) {
+    a.x0l = cal - 4503599627370496.0;
+    a.x0h = cah - 4503599627370496.0;
+  }
+  constexpr double HP = 0.5 * mds_split::cplus(T), HM = 0.5 * mds_split::cminus(T);
+  xl = fma(pl, HP, fma(ml, HM, xl));
+  xh = fma(ph, HP, fma(mh, HM, xh));
+  col<T, 0>(pl, ph, ml, mh, a.zpl, a.zph, a.zml, a.zmh);
+}
+}  // namespace mds_pair
+
+// Partial rounds r = 4 + 2 * pair and r + 1.  In: state with RC_r added; out: state with RC_{r+2}.
+__device__ __forceinline__ void partial_pair(u64 (&s)[WIDTH], int pair) {
+  const double BIAS = 4503599627370496.0;  // 2^52
+  s[0] = sbox7(s[0]);                      // u_0
+  MdsAcc acc;
+  {
+    const double4* __restrict__ k = reinterpret_cast<const double4*>(RCP) + 6 * pair;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double4 c = k[r];
+      acc.zpl[r] = c.x;
+      acc.zml[r] = c.y;
+      acc.zph[r] = c.z;
+      acc.zmh[r] = c.w;
+    }
+  }
+  // x'_0 = RC_{r+1,0} + 8 u_0 + (C u)_0, accumulated on top of the biased constant
+  const int r1 = FULL_ROUNDS_HALF + 2 * pair + 1;
+  double xl = RCD[2 * WIDTH * r1], xh = RCD[2 * WIDTH * r1 + 1];
+  mds_pair::absorb<0>(acc, s, xl, xh);
+  xl = fma(acc.x0l, 8.0, xl);
+  xh = fma(acc.x0h, 8.0, xh);
+  mds_pair::absorb<1>(acc, s, xl, xh);
+  mds_pair::absorb<2>(acc, s, xl, xh);
+  mds_pair::absorb<3>(acc, s, xl, xh);
+  mds_pair::absorb<4>(acc, s, xl, xh);
+  mds_pair::absorb<5>(acc, s, xl, xh);
+  const u64 x1 = gl::canon(combine_biased(xl, xh));  // x'_0
+  const u64 u1 = gl::canon(sbox7(x1));               // sbox(x'_0)
+  const u64 delta = gl::sub(u1, x1);
+  // A = 8 u_0 + delta, and sbox(x'_0), as plain doubles per half
+  const double al = fma(acc.x0l, 8.0, half_to_f64((u32)delta));
+  const double ah = fma(acc.x0h, 8.0, half_to_f64((u32)(delta >> 32)));
+  const double u1l = half_to_f64((u32)u1), u1h = half_to_f64((u32)(u1 >> 32));
+  constexpr double G[WIDTH] = {17, 20, 34, 18, 39, 13, 13, 28, 2, 16, 41, 15};  // (C e_0)_r = c_{-r}
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    const double s1l = acc.zpl[r] + acc.zml[r], s1h = acc.zph[r] + acc.zmh[r];  // 2 (C^2 u + K')_r
+    const double s2l = acc.zpl[r] - acc.zml[r], s2h = acc.zph[r] - acc.zmh[r];  // ... _{r+6}
+    double d1l = fma(al, G[r], fma(s1l, 0.5, BIAS)), d1h = fma(ah, G[r], fma(s1h, 0.5, BIAS));
+    const double d2l = fma(al, G[r + 6], fma(s2l, 0.5, BIAS)), d2h = fma(ah, G[r + 6], fma(s2h, 0.5, BIAS));
+    if (r == 0) {
+      d1l = fma(u1l, 8.0, d1l);
+      d1h = fma(u1h, 8.0, d1h);
+    }
+    s[r] = combine_biased(d1l, d1h);
+    s[r + 6] = combine_biased(d2l, d2h);
+  }
+}
+#define VPBS_PARTIAL_PAIRS 1
+#ifndef VPBS_SBOX_INLINE
+#define VPBS_SBOX_CALL 1  // measured at 2^19 x 128 leaves: 6.79 ms, vs 7.48 ms with inlined S-boxes
+#endif
+
 #define VPBS_MDS_INTERLEAVED 1
 // The whole layer in one call (tests, tools/selftest.cu).
 __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
@@ -366,40 +476,113 @@ __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
 // One loop over the 30 rounds with a warp-uniform "full round" branch keeps a single copy of the
 // S-box and MDS code (~27 KB), which fits the 32 KB instruction cache; two unrolled round bodies
 // did not (ncu: 13 % icache misses, stall_no_instruction 1.3 per issue).
+// Two S-boxes as ONE out-of-line function: the eight full rounds call it six times each instead of
+// inlining twelve ~100-instruction S-boxes, which keeps the whole permutation (full-round loop +
+// partial-pair loop) inside the 32 KB instruction cache.  Two independent chains per call keep the
+// integer pipes fed.
+__device__ __noinline__ ulonglong2 sbox7_x2(u64 a, u64 b) {
+  return make_ulonglong2(sbox7(a), sbox7(b));
+}
+#define VPBS_SBOX2(i, j)                        \
+  {                                             \
+    const ulonglong2 v_ = sbox7_x2(s[i], s[j]); \
+    s[i] = v_.x;                                \
+    s[j] = v_.y;                                \
+  }
+
+struct Sbox4 {
+  u64 a, b, c, d;
+};
+__device__ __noinline__ Sbox4 sbox7_x4(u64 a, u64 b, u64 c, u64 d) {
+  return Sbox4{sbox7(a), sbox7(b), sbox7(c), sbox7(d)};
+}
+#define VPBS_SBOX4(i, j, k, l)                              \
+  {                                                         \
+    const Sbox4 v_ = sbox7_x4(s[i], s[j], s[k], s[l]);      \
+    s[i] = v_.a; s[j] = v_.b; s[k] = v_.c; s[l] = v_.d;     \
+  }
+
+__device__ __forceinline__ void full_round(u64 (&s)[WIDTH], int r) {
+#ifdef VPBS_SBOX_CALL4
+  MdsAcc acc;
+  mds_begin(acc, r + 1);
+  VPBS_SBOX4(0, 6, 1, 7)
+  mds_absorb<0>(acc, s);
+  mds_absorb<1>(acc, s);
+  VPBS_SBOX4(2, 8, 3, 9)
+  mds_absorb<2>(acc, s);
+  mds_absorb<3>(acc, s);
+  VPBS_SBOX4(4, 10, 5, 11)
+  mds_absorb<4>(acc, s);
+  mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+#elif defined(VPBS_SBOX_CALL)
+  MdsAcc acc;
+  mds_begin(acc, r + 1);
+  VPBS_SBOX2(0, 6)
+  mds_absorb<0>(acc, s);
+  VPBS_SBOX2(1, 7)
+  mds_absorb<1>(acc, s);
+  VPBS_SBOX2(2, 8)
+  mds_absorb<2>(acc, s);
+  VPBS_SBOX2(3, 9)
+  mds_absorb<3>(acc, s);
+  VPBS_SBOX2(4, 10)
+  mds_absorb<4>(acc, s);
+  VPBS_SBOX2(5, 11)
+  mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+#elif defined(VPBS_MDS_INTERLEAVED)
+  // S-boxes (integer pipes) and MDS accumulation (FP64 pipe) interleaved pair by pair: as soon as
+  // words t and t + 6 are final they are fed to the accumulators.
+  MdsAcc acc;
+  mds_begin(acc, r + 1);
+  s[0] = sbox7(s[0]); s[6] = sbox7(s[6]);
+  mds_absorb<0>(acc, s);
+  s[1] = sbox7(s[1]); s[7] = sbox7(s[7]);
+  mds_absorb<1>(acc, s);
+  s[2] = sbox7(s[2]); s[8] = sbox7(s[8]);
+  mds_absorb<2>(acc, s);
+  s[3] = sbox7(s[3]); s[9] = sbox7(s[9]);
+  mds_absorb<3>(acc, s);
+  s[4] = sbox7(s[4]); s[10] = sbox7(s[10]);
+  mds_absorb<4>(acc, s);
+  s[5] = sbox7(s[5]); s[11] = sbox7(s[11]);
+  mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+#else
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) s[i] = sbox7(s[i]);
+  mds_add_rc(s, r + 1);
+#endif
+}
+
 __device__ __forceinline__ void permute_lazy(u64 (&s)[WIDTH]) {
 #pragma unroll
   for (int i = 0; i < WIDTH; i++) s[i] = gl::add_lazy(s[i], RC[i]);
+#ifdef VPBS_PARTIAL_PAIRS
+  // 4 full rounds, 11 pairs of partial rounds, 4 full rounds; one copy of each loop body.
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int k = 0; k < FULL_ROUNDS_HALF; k++)
+      full_round(s, half * (FULL_ROUNDS_HALF + PARTIAL_ROUNDS) + k);
+    if (half == 0) {
+#pragma unroll 1
+      for (int p = 0; p < PARTIAL_ROUNDS / 2; p++) partial_pair(s, p);
+    }
+  }
+#else
 #pragma unroll 1
   for (int r = 0; r < ROUNDS; r++) {
-    const bool full = r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS;
-#ifdef VPBS_MDS_INTERLEAVED
-    // S-boxes (integer pipes) and MDS accumulation (FP64 pipe) interleaved pair by pair: as soon as
-    // words t and t + 6 are final they are fed to the accumulators.
-    MdsAcc acc;
-    mds_begin(acc, r + 1);
-    s[0] = sbox7(s[0]);
-    if (full) s[6] = sbox7(s[6]);
-    mds_absorb<0>(acc, s);
-    if (full) { s[1] = sbox7(s[1]); s[7] = sbox7(s[7]); }
-    mds_absorb<1>(acc, s);
-    if (full) { s[2] = sbox7(s[2]); s[8] = sbox7(s[8]); }
-    mds_absorb<2>(acc, s);
-    if (full) { s[3] = sbox7(s[3]); s[9] = sbox7(s[9]); }
-    mds_absorb<3>(acc, s);
-    if (full) { s[4] = sbox7(s[4]); s[10] = sbox7(s[10]); }
-    mds_absorb<4>(acc, s);
-    if (full) { s[5] = sbox7(s[5]); s[11] = sbox7(s[11]); }
-    mds_absorb<5>(acc, s);
-    mds_finish(acc, s);
-#else
-    if (full) {
-#pragma unroll
-      for (int i = 1; i < WIDTH; i++) s[i] = sbox7(s[i]);
+    if (r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS) {
+      full_round(s, r);
+    } else {
+      s[0] = sbox7(s[0]);
+      mds_add_rc(s, r + 1);
     }
-    s[0] = sbox7(s[0]);
-    mds_add_rc(s, r + 1);
-#endif
   }
+#endif
 }
 
 // ---- latency-optimised permutation: 12 threads of a 16-thread group share one state -----------

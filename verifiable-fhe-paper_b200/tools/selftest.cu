@@ -34,6 +34,36 @@ __global__ void k_mds(const u64* a, u64* out, int n) {  // n states of 12; rc_ne
 }
 
 static u64 modp(u128 x) { return (u64)(x % (u128)gl::P); }
+static const u64 HOST_RC[360] = {
+#include "poseidon_rc.inc"
+};
+static void host_permute(u64* s) {
+  const u64 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  for (int i = 0; i < 12; i++) s[i] = modp(s[i]);
+  for (int r = 0; r < 30; r++) {
+    for (int i = 0; i < 12; i++) s[i] = modp((u128)s[i] + HOST_RC[12 * r + i]);
+    for (int i = 0; i < ((r < 4 || r >= 26) ? 12 : 1); i++) {
+      u64 x = s[i], x2 = modp((u128)x * x), x4 = modp((u128)x2 * x2), x3 = modp((u128)x2 * x);
+      s[i] = modp((u128)x3 * x4);
+    }
+    u64 o[12];
+    for (int q = 0; q < 12; q++) {
+      u128 acc = 0;
+      for (int k = 0; k < 12; k++) acc += (u128)s[(k + q) % 12] * C[k];
+      if (q == 0) acc += (u128)s[0] * 8;
+      o[q] = modp(acc);
+    }
+    for (int i = 0; i < 12; i++) s[i] = o[i];
+  }
+}
+__global__ void k_perm(u64* a, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 s[12];
+  for (int k = 0; k < 12; k++) s[k] = a[i * 12 + k];
+  poseidon::permute_lazy(s);
+  for (int k = 0; k < 12; k++) a[i * 12 + k] = gl::canon(s[k]);
+}
 
 int main() {
   const int n = 1 << 16;
@@ -97,7 +127,19 @@ int main() {
       }
     }
   printf("mds: %d bad\n", bad4);
+  int bad5 = 0;
+  cudaMemcpy(da, a.data(), n * 12 * 8, cudaMemcpyHostToDevice);
+  k_perm<<<n / 256, 256>>>(da, n);
+  cudaMemcpy(out.data(), da, n * 12 * 8, cudaMemcpyDeviceToHost);
+  for (int i = 0; i < 4096; i++) {
+    u64 h[12];
+    for (int k = 0; k < 12; k++) h[k] = a[i * 12 + k];
+    host_permute(h);
+    for (int k = 0; k < 12; k++)
+      if (h[k] != out[i * 12 + k]) { if (bad5++ < 3) printf("permutation mismatch state %d lane %d\n", i, k); }
+  }
+  printf("permutation: %d bad\n", bad5);
   cudaError_t e = cudaDeviceSynchronize();
   printf("cuda: %s\n", cudaGetErrorString(e));
-  return bad + bad2 + bad3 + bad4 ? 1 : 0;
+  return bad + bad2 + bad3 + bad4 + bad5 ? 1 : 0;
 }
