@@ -22,6 +22,11 @@ __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
   u64 s = a + b;
   return s < a ? s + EPS : s;  // one wrap only: b < p bounds the wrapped sum below p - 1
 }
+// a - b, a any u64, b canonical.  Result any u64.
+__device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) {
+  u64 d = a - b;
+  return a < b ? d - EPS : d;  // one wrap only: b < p keeps the wrapped difference >= EPS
+}
 // a + b, both canonical, canonical result.
 __host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {
   u64 s = a + b;

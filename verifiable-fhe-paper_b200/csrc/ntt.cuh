@@ -168,6 +168,30 @@ pass_final(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
 // 4 DIF layers over x[j], j = 0..15 (distance 8, 4, 2, 1 in j).  Butterfly (j, j + dd) of layer l
 // multiplies its difference by tw[((j mod dd) * jstride + off) << l]; tw[0] = 1 is skipped when the
 // exponent is known at compile time to be 0 (off == 0 && j mod dd == 0).
+// Values inside the register layers are arbitrary u64 representatives ("lazy"): add_lazy / sub_lazy
+// need only their SECOND operand canonical, so each butterfly canonicalises one input (4 slots)
+// instead of paying for canonical add, sub and mul results (saves ~11 slots per butterfly).
+#ifndef VPBS_NTT_CANONICAL
+template <bool HAS_OFF>
+__device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, unsigned jstride,
+                                      unsigned off, unsigned l0) {
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    const int dd = 8 >> l;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      if ((j & dd) == 0) {
+        const u64 a = x[j], c = gl::canon(x[j + dd]);
+        x[j] = gl::add_lazy(a, c);
+        const u64 d = gl::sub_lazy(a, c);
+        const int jm = j & (dd - 1);
+        if (!HAS_OFF && jm == 0) x[j + dd] = d;
+        else x[j + dd] = gl::mul_lazy(d, tw[((unsigned)jm * jstride + off) << (l0 + l)]);
+      }
+    }
+  }
+}
+#else
 template <bool HAS_OFF>
 __device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, unsigned jstride,
                                       unsigned off, unsigned l0) {
@@ -187,6 +211,7 @@ __device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, 
     }
   }
 }
+#endif
 
 // 256-point DIF on a 256 x 16 tile held as 16 registers per thread.
 //  in : x[j] = element (q = 16 j + q_lo, lane), this thread's (q_lo, lane)
@@ -238,7 +263,7 @@ pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restric
     const u64 pos = base + ((u64)q << log_sigma) + low0 + t;
     const u64 e = (low0 + t) * (u64)brev(q, 8);  // < 2^log_B
     u64 v = x[j];
-    if (e) v = gl::mul(v, root_of<INVERSE>(R, log_B, e));
+    v = e ? gl::mul(v, root_of<INVERSE>(R, log_B, e)) : gl::canon(v);
     dst[pos] = v;
   }
 }
@@ -285,7 +310,7 @@ pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
   for (int j = 0; j < 16; j++) {
     const unsigned q = 16 * q_hi + j;
     u64 v = x[j];
-    if (out_scale != 1) v = gl::mul(v, out_scale);
+    v = (out_scale != 1) ? gl::mul(v, out_scale) : gl::canon(v);
     if (MODE == STORE_LEAF) {
       const unsigned col = blockIdx.y * 16 + lane_b;
       const u64 pos = ((u64)blockIdx.x << 8) + q;
