@@ -66,46 +66,52 @@ __host__ __device__ __forceinline__ void sqr_wide(u64 a, u64& lo, u64& hi) {
   lo = (mid2 << 32) | (u32)p00;
 }
 // Products of arbitrary u64 operands; result arbitrary u64.
+//
+// Device sequence (4 IMAD.WIDE.U32 + 14 integer instructions in SASS; the first version, a chain
+// of mad.wide with carry fix-ups after each reduce128 step, needed 4 + 22):
+//   p = a0 b0, x = a0 b1, y = a1 b0, z = a1 b1                     (32x32 -> 64 each)
+//   (t0, t1, t2) = x + y                                           65-bit sum of the cross terms
+//   (s1, u, h1)  = (t0, t1, t2) + (p1, z0, z1)                     product = (p0, s1, u, h1)
+//   product = p0 + s1 2^32 + u 2^64 + h1 2^96 == p0 + s1 2^32 + u (2^32 - 1) - h1     (mod p)
+//           = p0 - (u + h1) + (s1 + u) 2^32
+//   (v, cv) = s1 + u; the carry is worth 2^64 == 2^32 - 1: v' = v + cv (cannot wrap: cv = 1 means
+//             v <= 2^32 - 2) and w = u + h1 + cv (33 bits: w, cw)
+//   r = (p0, v') - (w, cw); on borrow the wrapped value is >= 2^64 - 2^33, and r - (2^32 - 1)
+//   is the representative.
+// One carry flag feeds two consumers below (addc without .cc leaves CC.CF alone).
 __host__ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
 #if defined(__CUDA_ARCH__) && !defined(VPBS_MUL_C)
-  // Hand-scheduled: 4 x IMAD.WIDE.U32 for the 128-bit product, carry flags (not compare/select)
-  // for reduce128.  lo = {p0, n0}, hi = {h0, h1}:  r = lo - h1 + h0 * (2^32 - 1)  (mod p).
-  // Measured in the Poseidon leaf kernel: 7.77 ms with this sequence vs 8.61 ms with the
-  // compiler's version of the C++ fallback below (-DVPBS_MUL_C).
   const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
   u32 r0, r1;
   asm("{\n\t"
-      ".reg .u32 p0, p1, m0, m1, n0, n1, h0, h1, t0, t1, e0, e1, bm;\n\t"
-      ".reg .u64 w, z;\n\t"
-      "mul.wide.u32 w, %2, %4;\n\t"          // a0*b0
-      "mov.b64 {p0, p1}, w;\n\t"
-      "mov.b64 z, {p1, %6};\n\t"
-      "mad.wide.u32 w, %2, %5, z;\n\t"       // a0*b1 + p1
-      "mov.b64 {m0, m1}, w;\n\t"
-      "mov.b64 z, {m0, %6};\n\t"
-      "mad.wide.u32 w, %3, %4, z;\n\t"       // a1*b0 + m0
-      "mov.b64 {n0, n1}, w;\n\t"
-      "mov.b64 z, {m1, %6};\n\t"
-      "mad.wide.u32 w, %3, %5, z;\n\t"       // a1*b1 + m1
-      "mov.b64 {h0, h1}, w;\n\t"
-      "add.cc.u32 h0, h0, n1;\n\t"
-      "addc.u32 h1, h1, 0;\n\t"
-      "sub.cc.u32 t0, p0, h1;\n\t"           // t = lo - h1
-      "subc.cc.u32 t1, n0, 0;\n\t"
-      "subc.u32 bm, 0, 0;\n\t"               // 0xffffffff on borrow
-      "sub.cc.u32 t0, t0, bm;\n\t"           // borrow: t -= 2^32 - 1 (i.e. += p)
-      "subc.u32 t1, t1, 0;\n\t"
-      "sub.cc.u32 e0, 0, h0;\n\t"            // h0 * (2^32 - 1) = {-h0, h0 - (h0 != 0)}: two ALU ops
-      "subc.u32 e1, h0, 0;\n\t"              // instead of a half-rate IMAD.WIDE on the busiest pipe
-      "add.cc.u32 t0, t0, e0;\n\t"
-      "addc.cc.u32 t1, t1, e1;\n\t"
-      "addc.u32 bm, 0, 0;\n\t"               // carry (0/1); NB: subc after add.cc sees CF inverted
-      "neg.s32 bm, bm;\n\t"                  // 0xffffffff on carry
-      "add.cc.u32 %0, t0, bm;\n\t"
-      "addc.u32 %1, t1, 0;\n\t"
+      ".reg .u32 p0, p1, x0, x1, y0, y1, z0, z1, t0, t1, t2, s1, u, h1, v, vv, w, cw, lo, hi, bm;\n\t"
+      ".reg .u64 q;\n\t"
+      "mul.wide.u32 q, %2, %4;\n\t"
+      "mov.b64 {p0, p1}, q;\n\t"
+      "mul.wide.u32 q, %2, %5;\n\t"
+      "mov.b64 {x0, x1}, q;\n\t"
+      "mul.wide.u32 q, %3, %4;\n\t"
+      "mov.b64 {y0, y1}, q;\n\t"
+      "mul.wide.u32 q, %3, %5;\n\t"
+      "mov.b64 {z0, z1}, q;\n\t"
+      "add.cc.u32 t0, x0, y0;\n\t"
+      "addc.cc.u32 t1, x1, y1;\n\t"
+      "addc.u32 t2, z1, 0;\n\t"      // z1 + carry of the cross sum
+      "add.cc.u32 s1, t0, p1;\n\t"
+      "addc.cc.u32 u, t1, z0;\n\t"
+      "addc.u32 h1, t2, 0;\n\t"
+      "add.cc.u32 v, s1, u;\n\t"
+      "addc.u32 vv, v, 0;\n\t"       // v' = v + cv
+      "addc.cc.u32 w, u, h1;\n\t"    // w = u + h1 + cv (same flag)
+      "addc.u32 cw, 0, 0;\n\t"
+      "sub.cc.u32 lo, p0, w;\n\t"
+      "subc.cc.u32 hi, vv, cw;\n\t"
+      "subc.u32 bm, 0, 0;\n\t"       // 0xffffffff on borrow
+      "sub.cc.u32 %0, lo, bm;\n\t"   // borrow: r -= 2^32 - 1
+      "subc.u32 %1, hi, 0;\n\t"
       "}"
       : "=r"(r0), "=r"(r1)
-      : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(0u));
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return ((u64)r1 << 32) | r0;
 #else
   u64 lo, hi;
@@ -113,7 +119,43 @@ __host__ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
   return reduce128(lo, hi);
 #endif
 }
-__host__ __device__ __forceinline__ u64 sqr_lazy(u64 a) { return mul_lazy(a, a); }
+// a * a: the cross product a0 a1 is formed once (3 IMAD.WIDE.U32), (t0, t1, t2) = 2 x.
+__host__ __device__ __forceinline__ u64 sqr_lazy(u64 a) {
+#if defined(__CUDA_ARCH__) && !defined(VPBS_MUL_C)
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 p0, p1, x0, x1, z0, z1, t0, t1, t2, s1, u, h1, v, vv, w, cw, lo, hi, bm;\n\t"
+      ".reg .u64 q;\n\t"
+      "mul.wide.u32 q, %2, %2;\n\t"
+      "mov.b64 {p0, p1}, q;\n\t"
+      "mul.wide.u32 q, %2, %3;\n\t"
+      "mov.b64 {x0, x1}, q;\n\t"
+      "mul.wide.u32 q, %3, %3;\n\t"
+      "mov.b64 {z0, z1}, q;\n\t"
+      "add.cc.u32 t0, x0, x0;\n\t"
+      "addc.cc.u32 t1, x1, x1;\n\t"
+      "addc.u32 t2, z1, 0;\n\t"
+      "add.cc.u32 s1, t0, p1;\n\t"
+      "addc.cc.u32 u, t1, z0;\n\t"
+      "addc.u32 h1, t2, 0;\n\t"
+      "add.cc.u32 v, s1, u;\n\t"
+      "addc.u32 vv, v, 0;\n\t"
+      "addc.cc.u32 w, u, h1;\n\t"
+      "addc.u32 cw, 0, 0;\n\t"
+      "sub.cc.u32 lo, p0, w;\n\t"
+      "subc.cc.u32 hi, vv, cw;\n\t"
+      "subc.u32 bm, 0, 0;\n\t"
+      "sub.cc.u32 %0, lo, bm;\n\t"
+      "subc.u32 %1, hi, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1));
+  return ((u64)r1 << 32) | r0;
+#else
+  return mul_lazy(a, a);
+#endif
+}
 __host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) { return canon(mul_lazy(a, b)); }
 
 __host__ __device__ inline u64 pow(u64 a, u64 e) {

@@ -321,6 +321,16 @@ template <int T>
 __device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
   // p = x_T + x_{T+6}, m = x_T - x_{T+6} straight from the biased views: (2^52 + a) - (2^52 + b)
   // is a - b, and (2^52 + a) + ((2^52 + b) - 2^53) is a + b; every step is exact (|.| < 2^53).
+#ifdef VPBS_HALF_I2F
+  // conversion unit variant: I2F.F64.U32 issues beside the FP64 pipe (26 lanes/clk/SM measured)
+  const double al = __uint2double_rn((u32)s[T]), ah = __uint2double_rn((u32)(s[T] >> 32));
+  const double bl = __uint2double_rn((u32)s[T + 6]), bh = __uint2double_rn((u32)(s[T + 6] >> 32));
+  if constexpr (T == 0) {
+    a.x0l = al;
+    a.x0h = ah;
+  }
+  mds_split::col<T, 0>(al + bl, ah + bh, al - bl, ah - bh, a.zpl, a.zph, a.zml, a.zmh);
+#else
   const double TWO53 = 9007199254740992.0;
   const double cal = half_biased((u32)s[T]), cah = half_biased((u32)(s[T] >> 32));
   const double cbl = half_biased((u32)s[T + 6]), cbh = half_biased((u32)(s[T + 6] >> 32));
@@ -330,6 +340,7 @@ __device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
   }
   mds_split::col<T, 0>(cal + (cbl - TWO53), cah + (cbh - TWO53), cal - cbl, cah - cbh, a.zpl, a.zph,
                        a.zml, a.zmh);
+#endif
 }
 __device__ __forceinline__ void mds_finish(MdsAcc& a, u64 (&s)[WIDTH]) {
   const double BIAS = 4503599627370496.0;  // 2^52
@@ -386,6 +397,15 @@ __device__ __forceinline__ void col(double pl, double ph, double ml, double mh, 
 // words T and T + 6 of u into the C^2 accumulators and into row 0 of C u (xl, xh)
 template <int T>
 __device__ __forceinline__ void absorb(MdsAcc& a, const u64 (&s)[WIDTH], double& xl, double& xh) {
+#ifdef VPBS_HALF_I2F
+  const double al = __uint2double_rn((u32)s[T]), ah = __uint2double_rn((u32)(s[T] >> 32));
+  const double bl = __uint2double_rn((u32)s[T + 6]), bh = __uint2double_rn((u32)(s[T + 6] >> 32));
+  const double pl = al + bl, ph = ah + bh, ml = al - bl, mh = ah - bh;
+  if constexpr (T == 0) {
+    a.x0l = al;
+    a.x0h = ah;
+  }
+#else
   const double TWO53 = 9007199254740992.0;
   const double cal = half_biased((u32)s[T]), cah = half_biased((u32)(s[T] >> 32));
   const double cbl = half_biased((u32)s[T + 6]), cbh = half_biased((u32)(s[T + 6] >> 32));
@@ -394,6 +414,7 @@ __device__ __forceinline__ void absorb(MdsAcc& a, const u64 (&s)[WIDTH], double&
     a.x0l = cal - 4503599627370496.0;
     a.x0h = cah - 4503599627370496.0;
   }
+#endif
   constexpr double HP = 0.5 * mds_split::cplus(T), HM = 0.5 * mds_split::cminus(T);
   xl = fma(pl, HP, fma(ml, HM, xl));
   xh = fma(ph, HP, fma(mh, HM, xh));
@@ -451,8 +472,12 @@ __device__ __forceinline__ void partial_pair(u64 (&s)[WIDTH], int pair) {
   }
 }
 #define VPBS_PARTIAL_PAIRS 1
-#ifndef VPBS_SBOX_INLINE
-#define VPBS_SBOX_CALL 1  // measured at 2^19 x 128 leaves: 6.79 ms, vs 7.48 ms with inlined S-boxes
+// S-boxes inline by default.  With the first modular multiply (26 SASS instructions) the inlined
+// round loop overflowed the 32 KB instruction cache and an out-of-line two-lane S-box was faster
+// (6.79 vs 7.48 ms at 2^19 x 128 leaves); with the 18-instruction multiply the inlined loop fits:
+// 5.70 ms inline, 5.79 ms with -DVPBS_SBOX_OUTLINE (calls), 5.73 ms with -DVPBS_SBOX_CALL4.
+#ifdef VPBS_SBOX_OUTLINE
+#define VPBS_SBOX_CALL 1
 #endif
 
 #define VPBS_MDS_INTERLEAVED 1

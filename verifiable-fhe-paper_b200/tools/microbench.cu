@@ -182,6 +182,38 @@ __global__ void k_mad_wide_acc2(unsigned long long* out, Clk* clk, unsigned seed
   KERNEL_EPILOGUE
 }
 
+// 8 independent chains of I2F.F64.U32 (+1 IADD to close the chain; only the conversion is counted)
+__global__ void k_i2f_f64(unsigned long long* out, Clk* clk, unsigned seed) {
+  KERNEL_PROLOGUE
+  unsigned b0 = a0, b1 = a1, b2 = a2, b3 = a3, b4 = a4, b5 = a5, b6 = a6, b7 = a7;
+#pragma unroll 1
+  for (int i = 0; i < ITER; i++) {
+#define OP(b) asm volatile("{.reg .f64 d; .reg .u32 l, h; cvt.rn.f64.u32 d, %0; mov.b64 {l, h}, d; add.u32 %0, l, h;}" : "+r"(b));
+    OP(b0) OP(b1) OP(b2) OP(b3) OP(b4) OP(b5) OP(b6) OP(b7)
+#undef OP
+  }
+  a0 = b0; a1 = b1; a2 = b2; a3 = b3; a4 = b4; a5 = b5; a6 = b6; a7 = b7;
+  KERNEL_EPILOGUE
+}
+// mixed: 6 DFMA chains + 2 I2F.F64.U32 chains (does the conversion share the FP64 pipe?)
+__global__ void k_mix_dfma_i2f(unsigned long long* out, Clk* clk, unsigned seed) {
+  KERNEL_PROLOGUE
+  double d0 = a0, d1 = a1, d2 = a2, d3 = a3, d4 = a4, d5 = a5, m = 1.0 + 1e-9 * seed;
+  unsigned b6 = a6, b7 = a7;
+#pragma unroll 1
+  for (int i = 0; i < ITER; i++) {
+#define OPD(d) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d) : "d"(m));
+#define OPC(b) asm volatile("{.reg .f64 d; .reg .u32 l, h; cvt.rn.f64.u32 d, %0; mov.b64 {l, h}, d; add.u32 %0, l, h;}" : "+r"(b));
+    OPD(d0) OPD(d1) OPD(d2) OPC(b6) OPD(d3) OPD(d4) OPD(d5) OPC(b7)
+#undef OPD
+#undef OPC
+  }
+  a0 = __double_as_longlong(d0); a1 = __double_as_longlong(d1); a2 = __double_as_longlong(d2);
+  a3 = __double_as_longlong(d3); a4 = __double_as_longlong(d4); a5 = __double_as_longlong(d5);
+  a6 = b6; a7 = b7;
+  KERNEL_EPILOGUE
+}
+
 typedef void (*kern_t)(unsigned long long*, Clk*, unsigned);
 
 int run(const char* name, kern_t k, double instr_per_op, int sms, int threads, int blocks_per_sm) {
@@ -238,6 +270,8 @@ int main() {
     run("dfma", k_dfma, 1, sms, 256, bps);
     run("mix imad_wide + dfma", k_mix_wide_dfma, 1, sms, 256, bps);
     run("ffma", k_ffma, 1, sms, 256, bps);
+    run("i2f_f64_u32", k_i2f_f64, 1, sms, 256, bps);
+    run("mix 6 dfma + 2 i2f_f64", k_mix_dfma_i2f, 1, sms, 256, bps);
   }
   return 0;
 }
