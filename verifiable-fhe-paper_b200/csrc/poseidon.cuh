@@ -254,22 +254,29 @@ __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
 // The MDS matrix is circulant (plus one diagonal entry), i.e. y = c (*) s is a length-12 cyclic
 // convolution.  x^12 - 1 = (x^6 - 1)(x^6 + 1) splits it into a cyclic and a negacyclic length-6
 // convolution on p_t = s_t + s_{t+6} and m_t = s_t - s_{t+6}:
-//     Z+_r = sum_j (c_j + c_{j+6}) p_{(j+r) mod 6},   Z-_r = sum_j (+-)(c_j - c_{j+6}) m_{(j+r) mod 6}
-//     2 y_r = Z+_r + Z-_r,   2 y_{r+6} = Z+_r - Z-_r                      (r < 6)
-// 144 DFMA per round instead of 288 (plus 24 + 48 adds).  The FP64 pipe is what bounds the 22
-// partial rounds (ncu: one warp instruction per two cycles), so this is where the time goes.
-// Everything stays exact: |Z| < 2^42, the sums are even, and fma(S, 0.5, 2^52) halves and biases
-// in one step so that the mantissa is the integer result.
-// RCS[24 * round + 4 * r + {0,1,2,3}] = {lo+, lo-, hi+, hi-} sums/differences of the 32-bit halves
-// of RC[r], RC[r+6] (row 30 = zeros).
+//     Z+_r = sum_j (c_j + c_{j+6})/2 p_{(j+r) mod 6},  Z-_r = sum_j (+-)(c_j - c_{j+6})/2 m_{(j+r) mod 6}
+//     y_r = Z+_r + Z-_r,   y_{r+6} = Z+_r - Z-_r                          (r < 6)
+// 144 DFMA per round instead of 288 (plus 24 + 24 adds).  Everything stays exact: the halved
+// coefficients are integers (c+ and c- are even), |Z| < 2^42, and Z+ starts at 2^52 + its share
+// of the round constants, so Z+ + Z- and Z+ - Z- are the biased results directly (the mantissa is
+// the integer sum; no scaling or conversion back).
+// RCS[24 * round + 4 * r + {0,1,2,3}] = {2^52 + (al+bl)/2, (al-bl)/2, 2^52 + (ah+bh)/2, (ah-bh)/2}
+// where (al, ah), (bl, bh) are half-splits of RC[r], RC[r+6] (value = l + 2^32 h mod p) chosen by
+// tools/gen_poseidon_consts.py so that both sums are even (row 30: RC = 0).
 __constant__ double RCS[(ROUNDS + 1) * 24] = {
 #include "poseidon_rcs.inc"
 };
 
 namespace mds_split {
 constexpr int CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-__host__ __device__ constexpr double cplus(int j) { return (double)(CIRC[j] + CIRC[j + 6]); }
-__host__ __device__ constexpr double cminus(int j) { return (double)(CIRC[j] - CIRC[j + 6]); }
+// HALVED sums / differences: c_j + c_{j+6} and c_j - c_{j+6} are all even for this matrix
+// (30 28 80 34 36 48 / 4 2 2 -2 -32 8), so Z+ and Z- below are the halves of the textbook ones and
+// y_r = Z+_r + Z-_r, y_{r+6} = Z+_r - Z-_r come out without the 1/2.
+static_assert((CIRC[0] + CIRC[6]) % 2 == 0 && (CIRC[1] + CIRC[7]) % 2 == 0 && (CIRC[2] + CIRC[8]) % 2 == 0 &&
+              (CIRC[3] + CIRC[9]) % 2 == 0 && (CIRC[4] + CIRC[10]) % 2 == 0 && (CIRC[5] + CIRC[11]) % 2 == 0,
+              "halved split convolution needs even c+ / c-");
+__host__ __device__ constexpr double cplus(int j) { return (double)((CIRC[j] + CIRC[j + 6]) / 2); }
+__host__ __device__ constexpr double cminus(int j) { return (double)((CIRC[j] - CIRC[j + 6]) / 2); }
 
 // input t (p_t, m_t) into every accumulator r: the term j with (j + r) mod 6 == t
 template <int T, int R>
@@ -343,17 +350,16 @@ __device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
 #endif
 }
 __device__ __forceinline__ void mds_finish(MdsAcc& a, u64 (&s)[WIDTH]) {
-  const double BIAS = 4503599627370496.0;  // 2^52
 #pragma unroll
   for (int r = 0; r < 6; r++) {
-    double s1l = a.zpl[r] + a.zml[r], s1h = a.zph[r] + a.zmh[r];        // 2 y_r
-    const double s2l = a.zpl[r] - a.zml[r], s2h = a.zph[r] - a.zmh[r];  // 2 y_{r+6}
-    if (r == 0) {  // MDS_MATRIX_DIAG = [8, 0, ..., 0] (doubled)
-      s1l = fma(a.x0l, 16.0, s1l);
-      s1h = fma(a.x0h, 16.0, s1h);
+    double s1l = a.zpl[r] + a.zml[r], s1h = a.zph[r] + a.zmh[r];        // 2^52 + y_r
+    const double s2l = a.zpl[r] - a.zml[r], s2h = a.zph[r] - a.zmh[r];  // 2^52 + y_{r+6}
+    if (r == 0) {  // MDS_MATRIX_DIAG = [8, 0, ..., 0]
+      s1l = fma(a.x0l, 8.0, s1l);
+      s1h = fma(a.x0h, 8.0, s1h);
     }
-    s[r] = combine_biased(fma(s1l, 0.5, BIAS), fma(s1h, 0.5, BIAS));
-    s[r + 6] = combine_biased(fma(s2l, 0.5, BIAS), fma(s2h, 0.5, BIAS));
+    s[r] = combine_biased(s1l, s1h);  // Z+ starts at 2^52 + ..., so sums and differences are biased
+    s[r + 6] = combine_biased(s2l, s2h);
   }
 }
 // ---- two partial rounds at once ---------------------------------------------------------------------
@@ -380,8 +386,9 @@ __host__ __device__ constexpr int cc(int d) {  // (c (*) c)_d, cyclic
   for (int a = 0; a < WIDTH; a++) v += CIRC[a] * CIRC[(d - a + WIDTH) % WIDTH];
   return v;
 }
-__host__ __device__ constexpr double ccplus(int j) { return (double)(cc(j) + cc(j + 6)); }
-__host__ __device__ constexpr double ccminus(int j) { return (double)(cc(j) - cc(j + 6)); }
+// halved like mds_split: (c (*) c)+ = c+ (*) c+ and (c (*) c)- = c- (*) c- are multiples of 4
+__host__ __device__ constexpr double ccplus(int j) { return (double)((cc(j) + cc(j + 6)) / 2); }
+__host__ __device__ constexpr double ccminus(int j) { return (double)((cc(j) - cc(j + 6)) / 2); }
 template <int T, int R>
 __device__ __forceinline__ void col(double pl, double ph, double ml, double mh, double (&zpl)[6],
                                     double (&zph)[6], double (&zml)[6], double (&zmh)[6]) {
@@ -415,7 +422,7 @@ __device__ __forceinline__ void absorb(MdsAcc& a, const u64 (&s)[WIDTH], double&
     a.x0h = cah - 4503599627370496.0;
   }
 #endif
-  constexpr double HP = 0.5 * mds_split::cplus(T), HM = 0.5 * mds_split::cminus(T);
+  constexpr double HP = mds_split::cplus(T), HM = mds_split::cminus(T);  // already halved
   xl = fma(pl, HP, fma(ml, HM, xl));
   xh = fma(ph, HP, fma(mh, HM, xh));
   col<T, 0>(pl, ph, ml, mh, a.zpl, a.zph, a.zml, a.zmh);
@@ -424,7 +431,6 @@ __device__ __forceinline__ void absorb(MdsAcc& a, const u64 (&s)[WIDTH], double&
 
 // Partial rounds r = 4 + 2 * pair and r + 1.  In: state with RC_r added; out: state with RC_{r+2}.
 __device__ __forceinline__ void partial_pair(u64 (&s)[WIDTH], int pair) {
-  const double BIAS = 4503599627370496.0;  // 2^52
   s[0] = sbox7(s[0]);                      // u_0
   MdsAcc acc;
   {
@@ -459,10 +465,10 @@ __device__ __forceinline__ void partial_pair(u64 (&s)[WIDTH], int pair) {
   constexpr double G[WIDTH] = {17, 20, 34, 18, 39, 13, 13, 28, 2, 16, 41, 15};  // (C e_0)_r = c_{-r}
 #pragma unroll
   for (int r = 0; r < 6; r++) {
-    const double s1l = acc.zpl[r] + acc.zml[r], s1h = acc.zph[r] + acc.zmh[r];  // 2 (C^2 u + K')_r
+    const double s1l = acc.zpl[r] + acc.zml[r], s1h = acc.zph[r] + acc.zmh[r];  // 2^52 + (C^2 u + K')_r
     const double s2l = acc.zpl[r] - acc.zml[r], s2h = acc.zph[r] - acc.zmh[r];  // ... _{r+6}
-    double d1l = fma(al, G[r], fma(s1l, 0.5, BIAS)), d1h = fma(ah, G[r], fma(s1h, 0.5, BIAS));
-    const double d2l = fma(al, G[r + 6], fma(s2l, 0.5, BIAS)), d2h = fma(ah, G[r + 6], fma(s2h, 0.5, BIAS));
+    double d1l = fma(al, G[r], s1l), d1h = fma(ah, G[r], s1h);
+    const double d2l = fma(al, G[r + 6], s2l), d2h = fma(ah, G[r + 6], s2h);
     if (r == 0) {
       d1l = fma(u1l, 8.0, d1l);
       d1h = fma(u1h, 8.0, d1h);
