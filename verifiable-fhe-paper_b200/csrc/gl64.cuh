@@ -15,17 +15,77 @@ typedef unsigned int u32;
 constexpr u64 P = 0xFFFFFFFF00000001ULL;
 constexpr u64 EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 
-__host__ __device__ __forceinline__ u64 canon(u64 x) { return x >= P ? x - P : x; }
+// x mod p for any u64 x.  x >= p exactly when x + (2^32 - 1) carries out of 64 bits, and then the
+// wrapped sum is x - p: on the device that is IADD3 + IADD3.X + 2 SEL on the carry predicate (the
+// compare-based C form costs 6 instructions).
+__host__ __device__ __forceinline__ u64 canon(u64 x) {
+#if defined(__CUDA_ARCH__) && !defined(VPBS_CANON_C)
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 x0, x1, t0, t1, c;\n\t"
+      ".reg .pred q;\n\t"
+      "mov.b64 {x0, x1}, %2;\n\t"
+      "add.cc.u32 t0, x0, 0xffffffff;\n\t"
+      "addc.cc.u32 t1, x1, 0;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "setp.ne.u32 q, c, 0;\n\t"
+      "selp.u32 %0, t0, x0, q;\n\t"
+      "selp.u32 %1, t1, x1, q;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "l"(x));
+  return ((u64)r1 << 32) | r0;
+#else
+  return x >= P ? x - P : x;
+#endif
+}
 
 // a + b, a any u64, b canonical.  Result any u64 (not necessarily canonical).
+// One wrap only: b < p bounds the wrapped sum below p - 1, so adding 2^64 mod p = 2^32 - 1 fits.
 __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
+#if !defined(VPBS_ADDSUB_C)
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 a0, a1, b0, b1, l, h, c, h2;\n\t"
+      "mov.b64 {a0, a1}, %2;\n\t"
+      "mov.b64 {b0, b1}, %3;\n\t"
+      "add.cc.u32 l, a0, b0;\n\t"
+      "addc.cc.u32 h, a1, b1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 %0, l, c;\n\t"    // + c (2^32 - 1): low word - c, high word + c - borrow
+      "subc.u32 h2, h, 0;\n\t"
+      "add.u32 %1, h2, c;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "l"(a), "l"(b));
+  return ((u64)r1 << 32) | r0;
+#else
   u64 s = a + b;
-  return s < a ? s + EPS : s;  // one wrap only: b < p bounds the wrapped sum below p - 1
+  return s < a ? s + EPS : s;
+#endif
 }
 // a - b, a any u64, b canonical.  Result any u64.
+// One wrap only: b < p keeps the wrapped difference >= 2^32 - 1.
 __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) {
+#if !defined(VPBS_ADDSUB_C)
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 a0, a1, b0, b1, l, h, bm;\n\t"
+      "mov.b64 {a0, a1}, %2;\n\t"
+      "mov.b64 {b0, b1}, %3;\n\t"
+      "sub.cc.u32 l, a0, b0;\n\t"
+      "subc.cc.u32 h, a1, b1;\n\t"
+      "subc.u32 bm, 0, 0;\n\t"      // 0xffffffff on borrow
+      "sub.cc.u32 %0, l, bm;\n\t"   // borrow: -= 2^32 - 1
+      "subc.u32 %1, h, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "l"(a), "l"(b));
+  return ((u64)r1 << 32) | r0;
+#else
   u64 d = a - b;
-  return a < b ? d - EPS : d;  // one wrap only: b < p keeps the wrapped difference >= EPS
+  return a < b ? d - EPS : d;
+#endif
 }
 // a + b, both canonical, canonical result.
 __host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {

@@ -233,7 +233,10 @@ __device__ __forceinline__ void dft256_regs(u64 (&x)[16], u64* sm, const u64* tw
   dif16<false>(x, tw, 1, 0, 4);
 }
 
-template <bool INVERSE>
+// OUT_TW = false leaves out the four-step twiddle w_B^(low * brev(q)) at the store: the following
+// pass_final_r16 applies it at its load (in_tw_log_B), where one CTA needs only 256 distinct
+// twiddles shared by its 16 columns instead of 4096 scattered table reads per CTA here.
+template <bool INVERSE, bool OUT_TW = true>
 __global__ void __launch_bounds__(THREADS)
 pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restrict__ dst,
                  u64 dst_col_stride, unsigned log_B, const u64* __restrict__ in_scale, Roots R) {
@@ -252,8 +255,8 @@ pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restric
 #pragma unroll
   for (int j = 0; j < 16; j++) {
     const u64 pos = base + ((u64)(16 * j + qa) << log_sigma) + low0 + t;
-    x[j] = gl::canon(__ldg(src + pos));
-    if (in_scale) x[j] = gl::mul(x[j], __ldg(in_scale + pos));
+    x[j] = __ldg(src + pos);  // any representative: dif16 canonicalises what it must
+    if (in_scale) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + pos));
   }
   __syncthreads();  // tw ready
   dft256_regs(x, sm, tw, 16, qa, t, qa, t);
@@ -261,10 +264,13 @@ pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restric
   for (int j = 0; j < 16; j++) {
     const unsigned q = 16 * qa + j;
     const u64 pos = base + ((u64)q << log_sigma) + low0 + t;
-    const u64 e = (low0 + t) * (u64)brev(q, 8);  // < 2^log_B
-    u64 v = x[j];
-    v = e ? gl::mul(v, root_of<INVERSE>(R, log_B, e)) : gl::canon(v);
-    dst[pos] = v;
+    // the work buffer holds arbitrary representatives; the next pass reduces them
+    if (OUT_TW) {
+      const u64 e = (low0 + t) * (u64)brev(q, 8);  // < 2^log_B
+      dst[pos] = e ? gl::mul_lazy(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
+    } else {
+      dst[pos] = x[j];
+    }
   }
 }
 
@@ -272,11 +278,19 @@ template <bool INVERSE, int MODE>
 __global__ void __launch_bounds__(THREADS)
 pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
                u64* __restrict__ dst, u64 dst_stride, u64 row0, unsigned log_n,
-               const u64* __restrict__ in_scale, u64 out_scale, Roots R) {
+               const u64* __restrict__ in_scale, u64 out_scale, Roots R,
+               unsigned in_tw_log_B = 0) {
   __shared__ u64 sm[256 * 17];
   __shared__ u64 tw[128];
+  __shared__ u64 tws[256];
   const unsigned log_nb = log_n - 8;
   if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  // STORE_LEAF after a pass_strided_r16<.., false> over blocks of 2^in_tw_log_B with 256-element
+  // sub-blocks: this CTA's 256 positions are (q = blockIdx.x mod 256, low = 0..255) and their
+  // pending twiddles w_B^(low * brev(q)) do not depend on the column.
+  const bool in_tw = MODE == STORE_LEAF && in_tw_log_B != 0;
+  if (in_tw)
+    tws[threadIdx.x] = root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev(blockIdx.x & 255u, 8));
   // load mapping: q_lo fastest (16 consecutive elements of one column / block per half warp)
   const unsigned q_lo = threadIdx.x & 15, lane_a = threadIdx.x >> 4;
   u64 x[16];
@@ -296,13 +310,17 @@ pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
       const u64 pos = pos0 + 16 * j + q_lo;
       u64 v = 0;
       if (p) {
-        v = gl::canon(__ldg(p + pos));
-        if (in_scale) v = gl::mul(v, __ldg(in_scale + pos));
+        v = __ldg(p + pos);
+        if (in_scale) v = gl::mul_lazy(v, __ldg(in_scale + pos));
       }
       x[j] = v;
     }
   }
   __syncthreads();  // tw ready
+  if (in_tw) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], tws[16 * j + q_lo]);
+  }
   // store mapping: lane fastest (16 consecutive columns of one row / 16 consecutive outputs)
   const unsigned lane_b = threadIdx.x & 15, q_hi = threadIdx.x >> 4;
   dft256_regs(x, sm, tw, 17, q_lo, lane_a, q_hi, lane_b);

@@ -52,6 +52,10 @@ struct vpbs_ctx {
   // host API: device->host copies run on their own stream, overlapped with the remaining kernels
   cudaStream_t copy_stream = nullptr;
   cudaStream_t h2d_stream = nullptr;  // inputs of wide batches arrive chunk by chunk on this one
+  // Odd LDE blocks run on this stream with their own work buffer: one 256-point pass is 2048 CTAs
+  // = 3.46 waves of 148 x 4, and the other stream's CTAs fill the tail wave (LDE 1.67 -> 1.46 ms).
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
   // Buffers of destroyed resident batches, kept for the next batch of the same shape (a prover
   // commits the same shapes every step; cudaMalloc/cudaFree of ~0.6 GB cost milliseconds).
@@ -203,13 +207,18 @@ enum class Out { Leaf, Natural };
 template <bool INVERSE>
 int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols, unsigned log_n,
                   u64* work, Out mode, u64* dst, u64 dst_stride, u64 row0, const u64* in_scale,
-                  u64 out_scale) {
+                  u64 out_scale, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->stream;
   const ntt::Roots R{ctx->roots, ctx->roots_log};
   const Plan plan = make_plan(log_n);
   const u64 n = 1ULL << log_n;
   unsigned log_B = log_n;
   const u64* cur = src;
   u64 cur_stride = src_stride;
+  // 2^16-point forward transforms into leaf rows (two 256-point passes): the four-step twiddle
+  // between the passes is applied by the second pass at its load, see ntt::pass_strided_r16.
+  const bool tw_at_load = !INVERSE && mode == Out::Leaf && plan.npass == 2 && plan.s[0] == 8 &&
+                          plan.s[1] == 8 && log_n == 16;
   for (unsigned p = 0; p + 1 < plan.npass; p++) {
     const unsigned s = plan.s[p];
     const unsigned log_sigma = log_B - s;
@@ -217,11 +226,14 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
     if (log_T > log_sigma) log_T = log_sigma;
     const size_t smem = ((size_t)(1u << s << log_T) + (1u << s) / 2) * sizeof(u64);
     dim3 grid((unsigned)(n >> (s + log_T)), ncols);
-    if (s == 8 && log_T == 4)  // 256-point pass: radix-16 register kernel
-      ntt::pass_strided_r16<INVERSE><<<grid, ntt::THREADS, 0, ctx->stream>>>(
+    if (s == 8 && log_T == 4 && tw_at_load)
+      ntt::pass_strided_r16<INVERSE, false><<<grid, ntt::THREADS, 0, stream>>>(
+          cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R);
+    else if (s == 8 && log_T == 4)  // 256-point pass: radix-16 register kernel
+      ntt::pass_strided_r16<INVERSE><<<grid, ntt::THREADS, 0, stream>>>(
           cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R);
     else
-      ntt::pass_strided<INVERSE><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+      ntt::pass_strided<INVERSE><<<grid, ntt::THREADS, smem, stream>>>(
           cur, cur_stride, work, n, log_B, s, log_T, p == 0 ? in_scale : nullptr, R);
     ctx->launches++;
     cur = work;
@@ -236,10 +248,11 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
       const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
       dim3 grid((unsigned)(n >> s), (ncols + (1u << log_T) - 1) >> log_T);
       if (s == 8)
-        ntt::pass_final_r16<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, 0, ctx->stream>>>(
-            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R);
+        ntt::pass_final_r16<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, 0, stream>>>(
+            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R,
+            tw_at_load ? log_n : 0u);
       else
-        ntt::pass_final<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+        ntt::pass_final<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, smem, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
     } else {
       unsigned log_T = 4;
@@ -247,10 +260,10 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
       const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
       dim3 grid((unsigned)(n >> (s + log_T)), ncols);
       if (s == 8 && log_T == 4)
-        ntt::pass_final_r16<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, 0, ctx->stream>>>(
+        ntt::pass_final_r16<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, 0, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R);
       else
-        ntt::pass_final<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, smem, ctx->stream>>>(
+        ntt::pass_final<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, smem, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
     }
     ctx->launches++;
@@ -370,8 +383,12 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   if ((rc = ensure_roots(ctx, log_m)) != VPBS_OK) return rc;
   const u64* coset = nullptr;
   if ((rc = get_coset_table(ctx, log_n, rate_bits, gl::COSET_SHIFT, &coset)) != VPBS_OK) return rc;
-  u64* work = nullptr;
+  u64 *work = nullptr, *work2 = nullptr;
   if ((rc = arena_get(ctx, "work", (size_t)ncols * n * sizeof(u64), (void**)&work)) != VPBS_OK)
+    return rc;
+  const bool two_streams = (nleaves_shard >> log_n) > 1;
+  if (two_streams &&
+      (rc = arena_get(ctx, "work2", (size_t)ncols * n * sizeof(u64), (void**)&work2)) != VPBS_OK)
     return rc;
 
   tm->mark();  // 0
@@ -407,12 +424,23 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
     }
     // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
     // leaf rows (columns c0 .. c0 + nc of the row-major matrix).
+    if (two_streams) {  // odd blocks on the auxiliary stream, once the coefficients are there
+      CU(ctx, cudaEventRecord(ctx->aux_fork, ctx->stream));
+      CU(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+    }
     for (u64 b = 0; b < nb; b++) {
-      if ((rc = run_transform<false>(ctx, coeffs, n, nc, log_n, work, Out::Leaf, d_leaves + c0, width,
-                                     b << log_n, coset + ((b0 + b) << log_n), 1)) != VPBS_OK)
+      const bool aux = two_streams && (b & 1);
+      cudaStream_t st = aux ? ctx->aux_stream : ctx->stream;
+      if ((rc = run_transform<false>(ctx, coeffs, n, nc, log_n, aux ? work2 : work, Out::Leaf,
+                                     d_leaves + c0, width, b << log_n, coset + ((b0 + b) << log_n), 1,
+                                     st)) != VPBS_OK)
         return rc;
       if (!chunked && ov && !d_salt && b < ov->block_ready.size())
-        cudaEventRecord(ov->block_ready[b], ctx->stream);
+        cudaEventRecord(ov->block_ready[b], st);
+    }
+    if (two_streams) {
+      CU(ctx, cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+      CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
     }
   }
   if (d_salt) {
@@ -480,6 +508,9 @@ int vpbs_ctx_create(int device, vpbs_ctx** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
   for (int i = 0; e == cudaSuccess && i < 10; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     fail(nullptr, VPBS_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
@@ -505,6 +536,9 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   for (cudaEvent_t e : ctx->ov) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+  if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
