@@ -637,6 +637,8 @@ __device__ __forceinline__ void permute_coop(u64& w, double* __restrict__ sh, un
 #pragma unroll 1
   for (int r = 0; r < ROUNDS; r++) {
     const bool full = r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS;
+    // next round's constants: issued before the S-box so that the load latency hides behind it
+    const double2 rc2 = __ldg(reinterpret_cast<const double2*>(RCD_G) + (WIDTH * (r + 1) + ll));
     if (active && (full || l == 0)) w = sbox7(w);
     if (active) {
       const double dl = half_to_f64((u32)w), dh = half_to_f64((u32)(w >> 32));
@@ -647,7 +649,6 @@ __device__ __forceinline__ void permute_coop(u64& w, double* __restrict__ sh, un
     }
     __syncwarp();
     if (active) {
-      const double2 rc2 = __ldg(reinterpret_cast<const double2*>(RCD_G) + (WIDTH * (r + 1) + ll));
       double al0 = rc2.x, ah0 = rc2.y, al1 = 0.0, ah1 = 0.0;  // two chains each: shorter latency
 #pragma unroll
       for (int i = 0; i < WIDTH; i += 2) {

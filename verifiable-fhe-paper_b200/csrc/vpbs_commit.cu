@@ -10,6 +10,8 @@
 // There is no CPU fallback anywhere in this file: every path ends in a kernel launch or an error.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -297,7 +299,12 @@ int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, uns
   // the rest of the tree runs in ONE launch (one CTA per subtree, no launch gaps).
   unsigned total_log = 0;
   while ((1ULL << total_log) < nleaves) total_log++;
-  const unsigned coop_from = total_log > 12 ? total_log - 12 : 1;   // first level with <= 4096 nodes
+  static const unsigned coop_log = [] {  // developer knob for threshold sweeps
+    const char* e = getenv("VPBS_COOP_LOG");
+    const int v = e ? atoi(e) : 12;
+    return (unsigned)(v < 4 ? 4 : v > 24 ? 24 : v);
+  }();
+  const unsigned coop_from = total_log > coop_log ? total_log - coop_log : 1;  // first level with <= 2^coop_log nodes
   unsigned fused_from = log_sub > 4 ? log_sub - 4 : 1;               // <= 16 nodes per subtree
   if (fused_from < coop_from) fused_from = coop_from;
   const bool fuse = nsub <= 4096;
