@@ -330,6 +330,45 @@ def main():
     d2h_bytes = 8 * NCOLS * n + 8 * m * NCOLS + 32 * 2 * (m - ncap) + 32 * ncap
     cap_matches = bool(np.array_equal(h_cap.view(np.int64), d_cap.cpu().numpy()))
 
+    # ---- what the host link of this box can do (explains e2e): H2D alone, D2H alone, both at once
+    pcie = None
+    if rank == 0:
+        try:
+            nel = 32 << 20  # 256 MiB each way, from / to the pinned leaf buffer
+            flat = torch.from_numpy(h_leaves.view(np.int64).reshape(-1))
+            h_a, h_b = flat[:nel], flat[nel:2 * nel]
+            d_a = torch.empty(nel, dtype=torch.int64, device=dev)
+            d_b = torch.empty(nel, dtype=torch.int64, device=dev)
+            sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+            def timed(do_h2d, do_d2h):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if do_h2d:
+                    with torch.cuda.stream(sa):
+                        d_a.copy_(h_a, non_blocking=True)
+                if do_d2h:
+                    with torch.cuda.stream(sb):
+                        h_b.copy_(d_b, non_blocking=True)
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
+
+            timed(True, True)
+            gb = nel * 8 / 1e9
+            t_h = min(timed(True, False) for _ in range(3))
+            t_d = min(timed(False, True) for _ in range(3))
+            t_b = min(timed(True, True) for _ in range(3))
+            pcie = {"h2d_gbs": gb / t_h, "d2h_gbs": gb / t_d, "both_directions_total_gbs": 2 * gb / t_b,
+                    "pinned": bool(h_a.is_pinned()),
+                    "e2e_floor_ms": max(d2h_bytes / (gb / t_d * 1e9),
+                                        (h2d_bytes + d2h_bytes) / (2 * gb / t_b * 1e9)) * 1e3,
+                    "note": "256 MiB copies between the pinned leaf buffer and HBM; e2e_floor_ms = the "
+                            "step's PCIe bytes at these rates (D2H alone, or all bytes at the "
+                            "two-direction total, whichever is larger)"}
+            del d_a, d_b
+        except Exception as ex:  # informational only
+            pcie = {"error": repr(ex)}
+
     # ---- the same call with the batch left in HBM (vpbs_batch_*): only the cap crosses PCIe at
     # commit time; the 28 FRI-query rows + Merkle paths of a proof are fetched on demand
     query_idx = np.random.default_rng(7).integers(0, m, size=28, dtype=np.uint64)
@@ -471,6 +510,7 @@ def main():
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.e2e_steps * 1e3,
                 "steps": args.e2e_steps, "api": "vpbs_commit (host C ABI, pinned buffers)",
                 "phase_ms_last": e2e_stats.as_dict(), "cap_matches_device_path": cap_matches,
+                "pcie": pcie,
                 "host_affinity": numa},
         "e2e_resident": {"value": world * args.e2e_steps * n / res_s, "unit": UNIT,
                          "ms_per_step": res_s / args.e2e_steps * 1e3,

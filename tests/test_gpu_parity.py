@@ -436,7 +436,9 @@ def test_randomized_shapes_against_oracle(V, ctx, oracle):
 
 @pytest.mark.parametrize("log_n,ncols,rate_bits,cap_height,coeffs,salted", [
     (10, 135, 3, 4, False, False), (12, 16, 3, 4, True, False), (6, 20, 3, 9, False, False),
-    (8, 9, 2, 0, False, True), (0, 5, 3, 1, False, False)])
+    (8, 9, 2, 0, False, True), (0, 5, 3, 1, False, False),
+    # wide enough for the column-chunked upload (ragged last chunk; coefficients + salt)
+    (12, 70, 2, 3, False, False), (12, 64, 1, 2, True, True)])
 def test_resident_batch_lazy_openings(V, ctx, oracle, log_n, ncols, rate_bits, cap_height, coeffs, salted):
     """vpbs_batch_*: commit stays in HBM; rows and Merkle paths fetched on demand match the oracle's
     leaves / MerkleTree::prove, verify against the cap, and download() equals the eager commit."""

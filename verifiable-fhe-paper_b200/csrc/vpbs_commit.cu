@@ -340,6 +340,7 @@ struct Overlap {
   // (wait h2d_ready[k]); chunk k's coefficients are final at coeffs_chunk_ready[k]; the leaf
   // matrix is final at lde_done.  chunk_cols == 0: all columns at once (events above).
   u32 chunk_cols = 0;
+  bool lde_by_block = false;  // chunked inputs, but LDE over all columns block by block (see commit_core)
   std::vector<cudaEvent_t> h2d_ready, coeffs_chunk_ready;
   cudaEvent_t lde_done = nullptr;
 };
@@ -409,6 +410,34 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   const u32 chunk = (ov && ov->chunk_cols && ov->chunk_cols < ncols) ? ov->chunk_cols : ncols;
   const bool chunked = chunk < ncols;
   if (chunked) tm->mark();  // 1: pipelined mode reports all transforms under "FFT + blinding"
+  // Chunked inputs, two orders for the LDE: per column chunk right after its IFFT (the GPU starts
+  // early: best when little is copied back), or — by_block — once all coefficients are there,
+  // block by block over all columns, so that finished leaf rows can stream out while later
+  // blocks are still being transformed (best when the leaf matrix is copied to the host).
+  const bool by_block = chunked && ov->lde_by_block;
+  // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
+  // leaf rows (columns c0 .. c0 + nc of the row-major matrix).
+  auto lde_blocks = [&](const u64* coeffs, u32 c0, u32 nc, bool block_events) -> int {
+    if (two_streams) {  // odd blocks on the auxiliary stream, once the coefficients are there
+      CU(ctx, cudaEventRecord(ctx->aux_fork, ctx->stream));
+      CU(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+    }
+    for (u64 b = 0; b < nb; b++) {
+      const bool aux = two_streams && (b & 1);
+      cudaStream_t st = aux ? ctx->aux_stream : ctx->stream;
+      int rc2 = run_transform<false>(ctx, coeffs, n, nc, log_n, aux ? work2 : work, Out::Leaf,
+                                     d_leaves + c0, width, b << log_n, coset + ((b0 + b) << log_n), 1,
+                                     st);
+      if (rc2 != VPBS_OK) return rc2;
+      if (block_events && ov && !d_salt && b < ov->block_ready.size())
+        cudaEventRecord(ov->block_ready[b], st);
+    }
+    if (two_streams) {
+      CU(ctx, cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+      CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
+    }
+    return VPBS_OK;
+  };
   for (u32 c0 = 0, k = 0; c0 < ncols; c0 += chunk, k++) {
     const u32 nc = ncols - c0 < chunk ? ncols - c0 : chunk;
     if (chunked && k < ov->h2d_ready.size()) CU(ctx, cudaStreamWaitEvent(ctx->stream, ov->h2d_ready[k], 0));
@@ -429,27 +458,11 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
     } else if (k < ov->coeffs_chunk_ready.size()) {
       cudaEventRecord(ov->coeffs_chunk_ready[k], ctx->stream);
     }
-    // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
-    // leaf rows (columns c0 .. c0 + nc of the row-major matrix).
-    if (two_streams) {  // odd blocks on the auxiliary stream, once the coefficients are there
-      CU(ctx, cudaEventRecord(ctx->aux_fork, ctx->stream));
-      CU(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
-    }
-    for (u64 b = 0; b < nb; b++) {
-      const bool aux = two_streams && (b & 1);
-      cudaStream_t st = aux ? ctx->aux_stream : ctx->stream;
-      if ((rc = run_transform<false>(ctx, coeffs, n, nc, log_n, aux ? work2 : work, Out::Leaf,
-                                     d_leaves + c0, width, b << log_n, coset + ((b0 + b) << log_n), 1,
-                                     st)) != VPBS_OK)
-        return rc;
-      if (!chunked && ov && !d_salt && b < ov->block_ready.size())
-        cudaEventRecord(ov->block_ready[b], st);
-    }
-    if (two_streams) {
-      CU(ctx, cudaEventRecord(ctx->aux_join, ctx->aux_stream));
-      CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
-    }
+    if (!by_block && (rc = lde_blocks(coeffs, c0, nc, !chunked)) != VPBS_OK) return rc;
   }
+  if (by_block &&
+      (rc = lde_blocks(inputs_are_coeffs ? d_cols : cbuf, 0, ncols, true)) != VPBS_OK)
+    return rc;
   if (d_salt) {
     const u64 cnt = nleaves_shard * 4;
     merkle::scatter_salt<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(
@@ -478,6 +491,30 @@ void fill_stats(vpbs_stats* st, Timer& tm, uint64_t launches) {
 }
 
 bool usable(vpbs_ctx* ctx) { return ctx != nullptr; }
+
+// Copies columns [c0, c1) between per-column host pointers and a column-major device buffer
+// (column c at dev + c * n).  Host columns that happen to be adjacent in memory (one allocation, as
+// plonky2's flattened buffers or this repo's hosts provide) travel as ONE transfer: 128 separate
+// 512 KB copies per direction cost the 2^16 x 128 commit about a millisecond of DMA set-up.
+cudaError_t copy_columns(u64* dev, const uint64_t* const* host, u32 c0, u32 c1, u64 n, bool to_device,
+                         cudaStream_t st) {
+  u32 c = c0;
+  while (c < c1) {
+    if (!host[c]) {  // skipped output column
+      c++;
+      continue;
+    }
+    u32 e = c + 1;
+    while (e < c1 && host[e] == host[e - 1] + n) e++;
+    const size_t bytes = (size_t)(e - c) * n * sizeof(u64);
+    cudaError_t err = to_device
+        ? cudaMemcpyAsync(dev + (u64)c * n, host[c], bytes, cudaMemcpyHostToDevice, st)
+        : cudaMemcpyAsync(const_cast<uint64_t*>(host[c]), dev + (u64)c * n, bytes, cudaMemcpyDeviceToHost, st);
+    if (err != cudaSuccess) return err;
+    c = e;
+  }
+  return cudaSuccess;
+}
 
 int bind(vpbs_ctx* ctx) {
   if (!usable(ctx)) return VPBS_ERR_STATE;
@@ -837,6 +874,7 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
   evi += nblocks;
   if (nchunks) {
     ovl.chunk_cols = chunk_cols;
+    ovl.lde_by_block = leaves_out != nullptr;
     ovl.h2d_ready.assign(ctx->ov.begin() + evi, ctx->ov.begin() + evi + nchunks);
     evi += nchunks;
     ovl.coeffs_chunk_ready.assign(ctx->ov.begin() + evi, ctx->ov.begin() + evi + nchunks);
@@ -853,10 +891,11 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
       CU(ctx, cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice,
                               ctx->stream));
     }
-  for (u32 c = 0; c < ncols; c++) {
-    CU(ctx, cudaMemcpyAsync(din + (u64)c * n, cols[c], n * 8, cudaMemcpyHostToDevice, hs));
-    if (nchunks && ((c + 1) % chunk_cols == 0 || c + 1 == ncols))
-      CU(ctx, cudaEventRecord(ovl.h2d_ready[c / chunk_cols], hs));
+  for (u32 c0 = 0, k = 0; c0 < ncols; k++) {
+    const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
+    CU(ctx, copy_columns(din, cols, c0, c1, n, true, hs));
+    if (nchunks) CU(ctx, cudaEventRecord(ovl.h2d_ready[k], hs));
+    c0 = c1;
   }
   if (stats) cudaEventRecord(e1, hs);
   // Output copies run on the copy stream as soon as their data is final: coefficients after the
@@ -874,21 +913,22 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
   if (stats) cudaEventRecord(e2, ctx->stream);
   cudaStream_t cs = ctx->copy_stream;
   if (coeffs_out) {
-    const u64* csrc = inputs_are_coeffs ? din : dco;
-    for (u32 c = 0; c < ncols; c++) {
-      if (!nchunks && c == 0) CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_ready, 0));
-      if (nchunks && c % chunk_cols == 0)
-        CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_chunk_ready[c / chunk_cols], 0));
-      if (coeffs_out[c])
-        CU(ctx, cudaMemcpyAsync(coeffs_out[c], csrc + (u64)c * n, n * 8, cudaMemcpyDeviceToHost, cs));
+    u64* csrc = inputs_are_coeffs ? din : dco;
+    if (!nchunks) CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_ready, 0));
+    for (u32 c0 = 0, k = 0; c0 < ncols; k++) {
+      const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
+      if (nchunks) CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_chunk_ready[k], 0));
+      CU(ctx, copy_columns(csrc, coeffs_out, c0, c1, n, false, cs));
+      c0 = c1;
     }
   }
   if (leaves_out) {
     const size_t block_elems = (size_t)n * width;
-    if (nchunks || salt_cols)  // rows are final only after the last column chunk / the salt scatter
+    const bool per_block = (!nchunks || ovl.lde_by_block) && !salt_cols;
+    if (!per_block)  // rows are final only after the last column chunk / the salt scatter
       CU(ctx, cudaStreamWaitEvent(cs, ovl.lde_done, 0));
     for (u64 blk = 0; blk < nblocks; blk++) {
-      if (!nchunks && !salt_cols) CU(ctx, cudaStreamWaitEvent(cs, ovl.block_ready[blk], 0));
+      if (per_block) CU(ctx, cudaStreamWaitEvent(cs, ovl.block_ready[blk], 0));
       CU(ctx, cudaMemcpyAsync(leaves_out + blk * block_elems, dle + blk * block_elems,
                               block_elems * 8, cudaMemcpyDeviceToHost, cs));
     }
@@ -1120,9 +1160,33 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
   cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
   if (stats) cudaEventRecord(e0, ctx->stream);
   cudaError_t ce = cudaSuccess;
-  for (u32 c = 0; c < ncols && ce == cudaSuccess; c++) {
-    if (!cols[c]) { ce = cudaErrorInvalidValue; break; }
-    ce = cudaMemcpyAsync(din + (u64)c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  // Wide batches: inputs travel in column chunks on the H2D stream and chunk k is transformed
+  // (IFFT + its columns of every LDE block) while chunk k+1 is still on the bus.
+  const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? 32 : 0;
+  const u32 nchunks = chunk_cols ? (ncols + chunk_cols - 1) / chunk_cols : 0;
+  Overlap ovl;
+  cudaStream_t hs = nchunks ? ctx->h2d_stream : ctx->stream;
+  if (nchunks) {
+    while (ctx->ov.size() < (size_t)nchunks + 1 && ce == cudaSuccess) {
+      cudaEvent_t e;
+      ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (ce == cudaSuccess) ctx->ov.push_back(e);
+    }
+    if (ce == cudaSuccess) {
+      ovl.chunk_cols = chunk_cols;
+      ovl.h2d_ready.assign(ctx->ov.begin() + 1, ctx->ov.begin() + 1 + nchunks);
+      // the H2D stream starts after whatever the caller queued on the compute stream
+      ce = cudaEventRecord(ctx->ov[0], ctx->stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(hs, ctx->ov[0], 0);
+    }
+  }
+  for (u32 c = 0; c < ncols && ce == cudaSuccess; c++)
+    if (!cols[c]) ce = cudaErrorInvalidValue;
+  for (u32 c0 = 0, k = 0; c0 < ncols && ce == cudaSuccess; k++) {
+    const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
+    ce = copy_columns(din, cols, c0, c1, n, true, hs);
+    if (ce == cudaSuccess && nchunks) ce = cudaEventRecord(ovl.h2d_ready[k], hs);
+    c0 = c1;
   }
   if (salt_cols)
     for (int s = 0; s < VPBS_SALT_SIZE && ce == cudaSuccess; s++) {
@@ -1130,16 +1194,19 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
       ce = cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice, ctx->stream);
     }
   if (ce != cudaSuccess) {
+    if (nchunks) cudaStreamSynchronize(hs);
     vpbs_batch_destroy(b);
     return fail(ctx, ce == cudaErrorInvalidValue ? VPBS_ERR_ARG : VPBS_ERR_CUDA,
                 std::string("batch input copy: ") + cudaGetErrorString(ce));
   }
-  if (stats) cudaEventRecord(e1, ctx->stream);
+  if (stats) cudaEventRecord(e1, hs);
   Timer tm{ctx, stats != nullptr};
+  if (nchunks) tm.overlap = &ovl;
   // coefficients always end up in the batch (from_coeffs: a device copy of the inputs)
   rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
                    b->coeffs, b->leaves, b->digests, b->cap, &tm);
   if (rc) {
+    if (nchunks) cudaStreamSynchronize(hs);
     vpbs_batch_destroy(b);
     return rc;
   }
