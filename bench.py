@@ -172,6 +172,77 @@ def run_reference(args, rank, world):
     }))
 
 
+def run_multi_commit(args):
+    """Strong scaling of the end-to-end call: one configs[1] commit through vpbs_commit_multi, host
+    buffers in, all outputs (coefficients, leaves, digests, cap) back in host memory, G GPUs of
+    this process each moving 1/G of the D2H bytes over its own link."""
+    import ctypes
+    import numpy as np
+    import torch
+    import vfhe_b200 as V
+    G = args.multi_commit
+    if not torch.cuda.is_available() or torch.cuda.device_count() < G:
+        raise SystemExit("--multi-commit %d needs %d CUDA devices" % (G, G))
+    V.build.build()
+    ctxs = [V.Context(g) for g in range(G)]
+    lib = ctxs[0].lib
+    n, m, ncap = 1 << LOG_N, (1 << LOG_N) << RATE_BITS, 1 << CAP_HEIGHT
+    host_cols = V.synthetic_columns(NCOLS, n, seed=0x5EED0000)
+
+    def pinned(shape):
+        nbytes = int(np.prod(shape)) * 8
+        p = lib.vpbs_host_alloc(nbytes)
+        if not p:
+            raise SystemExit("vpbs_host_alloc failed")
+        return np.ctypeslib.as_array((ctypes.c_uint64 * (nbytes // 8)).from_address(p)).reshape(shape)
+
+    h_cols = pinned((NCOLS, n))
+    h_cols[:] = host_cols
+    h_coeffs, h_leaves = pinned((NCOLS, n)), pinned((m, NCOLS))
+    h_digests, h_cap = pinned((2 * (m - ncap), 4)), pinned((ncap, 4))
+    u64p = V._lib.u64p
+    colp = (u64p * NCOLS)(*[h_cols[c].ctypes.data_as(u64p) for c in range(NCOLS)])
+    cop = (u64p * NCOLS)(*[h_coeffs[c].ctypes.data_as(u64p) for c in range(NCOLS)])
+    handles = (ctypes.c_void_p * G)(*[c.handle for c in ctxs])
+    st = V.VpbsStats()
+
+    def step():
+        ctxs[0].check(lib.vpbs_commit_multi(handles, G, colp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0,
+                                            None, cop, h_leaves.ctypes.data_as(u64p),
+                                            h_digests.ctypes.data_as(u64p),
+                                            h_cap.ctypes.data_as(u64p), ctypes.byref(st)))
+
+    sampler = ClockSampler(0)
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps * 4):
+        step()
+    dt = (time.perf_counter() - t0) / (args.e2e_steps * 4)
+    clocks = sampler.stop()
+    # parity with the single-GPU host call on the same inputs (cap, a digest checksum, sampled rows)
+    one = V.PolynomialBatch.from_values(host_cols, RATE_BITS, False, CAP_HEIGHT, ctx=ctxs[0])
+    same = bool(np.array_equal(one.merkle_tree.cap, h_cap) and
+                np.array_equal(one.merkle_tree.digests, h_digests) and
+                np.array_equal(one.merkle_tree.leaves[::4099], h_leaves[::4099]) and
+                np.array_equal(one.polynomials, h_coeffs))
+    h2d = 8 * NCOLS * n * G
+    d2h = 8 * NCOLS * n + 8 * m * NCOLS + 32 * 2 * (m - ncap) + 32 * ncap
+    print(json.dumps({
+        "metric": METRIC, "mode": "multi-commit (strong scaling of one commit, single process)",
+        "value": n / dt, "unit": UNIT, "n_gpus": G, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "dtype": "u64", "data": "synthetic",
+        "config": dict(workload_config(1), parallelism="one commit over %d GPUs: row ranges "
+                       "(whole LDE blocks / cap subtrees) per GPU, no GPU-to-GPU traffic" % G),
+        "e2e": {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "vpbs_commit_multi (host C ABI, pinned buffers)",
+                "slowest_device_phase_ms": st.as_dict()},
+        "matches_single_gpu_commit": same, "gpu_launches": int(st.kernel_launches), "clocks": clocks}),
+        flush=True)
+
+
 def workload_config(world):
     return {"workload": "configs[1]: standalone commit microbench, 2^16 rows x 128 Goldilocks columns, "
                         "rate_bits=3, Poseidon cap_height=4, from values, blinding off",
@@ -195,7 +266,12 @@ def main():
     ap.add_argument("--shard-commit", action="store_true",
                     help="strong scaling of ONE commit: every rank computes its row range "
                          "(vpbs_commit_shard_dev) and the subtree roots are all-gathered over NCCL")
+    ap.add_argument("--multi-commit", type=int, default=0, metavar="G",
+                    help="single process (do not launch under torchrun): ONE commit spread over G "
+                         "GPUs through vpbs_commit_multi with host buffers; prints its own line")
     args = ap.parse_args()
+    if args.multi_commit:
+        return run_multi_commit(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

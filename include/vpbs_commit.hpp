@@ -172,6 +172,22 @@ class PolynomialBatch {
                                      const std::vector<std::vector<F>>* salt = nullptr) {
     return commit(ctx, polys, rate_bits, blinding, cap_height, true, salt);
   }
+  // The same commit spread over several GPUs of this process (vpbs_commit_multi): row ranges per GPU,
+  // no GPU-to-GPU traffic, identical outputs.  ctxs: contexts on distinct devices.
+  static PolynomialBatch from_values(const std::vector<const Context*>& ctxs,
+                                     const std::vector<std::vector<F>>& values, unsigned rate_bits,
+                                     bool blinding, unsigned cap_height,
+                                     const std::vector<std::vector<F>>* salt = nullptr) {
+    if (ctxs.empty() || !ctxs[0]) throw std::invalid_argument("no contexts");
+    return commit(*ctxs[0], values, rate_bits, blinding, cap_height, false, salt, &ctxs);
+  }
+  static PolynomialBatch from_coeffs(const std::vector<const Context*>& ctxs,
+                                     const std::vector<std::vector<F>>& polys, unsigned rate_bits,
+                                     bool blinding, unsigned cap_height,
+                                     const std::vector<std::vector<F>>* salt = nullptr) {
+    if (ctxs.empty() || !ctxs[0]) throw std::invalid_argument("no contexts");
+    return commit(*ctxs[0], polys, rate_bits, blinding, cap_height, true, salt, &ctxs);
+  }
   // get_lde_values(index, step): leaf reverse_bits(index * step) without the salt.
   std::vector<F> get_lde_values(std::size_t index, std::size_t step = 1) const {
     const std::size_t k = reverse_bits(index * step, degree_log + rate_bits);
@@ -182,7 +198,8 @@ class PolynomialBatch {
  private:
   static PolynomialBatch commit(const Context& ctx, const std::vector<std::vector<F>>& cols,
                                 unsigned rate_bits, bool blinding, unsigned cap_height,
-                                bool are_coeffs, const std::vector<std::vector<F>>* salt) {
+                                bool are_coeffs, const std::vector<std::vector<F>>* salt,
+                                const std::vector<const Context*>* multi = nullptr) {
     if (cols.empty()) throw std::invalid_argument("empty batch");
     const std::size_t n = cols[0].size();
     const unsigned log_n = log2_strict(n);
@@ -213,6 +230,16 @@ class PolynomialBatch {
     t.leaves.resize(m * t.leaf_len);
     t.digests.resize(2 * (m - (std::size_t(1) << cap_height)));
     t.cap.resize(std::size_t(1) << cap_height);
+    if (multi) {
+      std::vector<vpbs_ctx*> hs;
+      for (const Context* c : *multi) hs.push_back(c ? c->get() : nullptr);
+      ctx.check(vpbs_commit_multi(hs.data(), (int)hs.size(), in.data(), (uint32_t)ncols, log_n,
+                                  rate_bits, cap_height, are_coeffs ? 1 : 0,
+                                  blinding ? sp.data() : nullptr, co.data(), t.leaves.data(),
+                                  t.digests.empty() ? nullptr : t.digests[0].elements,
+                                  t.cap[0].elements, &b.stats));
+      return b;
+    }
     ctx.check(vpbs_commit(ctx.get(), in.data(), (uint32_t)ncols, log_n, rate_bits, cap_height,
                           are_coeffs ? 1 : 0, blinding ? sp.data() : nullptr, co.data(),
                           t.leaves.data(), t.digests.empty() ? nullptr : t.digests[0].elements,

@@ -64,6 +64,12 @@ extern "C" {
                        salt_cols: *const *const u64, coeffs_out: *const *mut u64,
                        leaves_out: *mut u64, digests_out: *mut u64, cap_out: *mut u64,
                        stats: *mut vpbs_stats) -> c_int;
+    pub fn vpbs_commit_multi(ctxs: *const *mut vpbs_ctx, nctx: c_int, cols: *const *const u64,
+                             ncols: u32, log_n: u32, rate_bits: u32, cap_height: u32,
+                             inputs_are_coeffs: c_int, salt_cols: *const *const u64,
+                             coeffs_out: *const *mut u64, leaves_out: *mut u64,
+                             digests_out: *mut u64, cap_out: *mut u64,
+                             stats: *mut vpbs_stats) -> c_int;
     pub fn vpbs_commit_dev(ctx: *mut vpbs_ctx, d_cols: *const u64, ncols: u32, log_n: u32,
                            rate_bits: u32, cap_height: u32, inputs_are_coeffs: c_int,
                            d_salt: *const u64, d_coeffs_out: *mut u64, d_leaves_out: *mut u64,

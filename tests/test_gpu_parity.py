@@ -354,6 +354,51 @@ def test_shard_rejects_bad_ranges(V, ctx):
                               out.data_ptr(), out.data_ptr())
 
 
+@pytest.mark.parametrize("log_n,ncols,rate_bits,cap_height,coeffs,salted,nctx", [
+    (10, 9, 3, 4, False, False, 2), (10, 9, 3, 4, False, False, 8), (12, 70, 3, 3, False, False, 4),
+    (12, 64, 2, 2, True, True, 4), (6, 5, 1, 6, False, False, 2), (13, 135, 3, 4, False, False, 8),
+    (4, 3, 3, 7, True, False, 1)])
+def test_commit_multi_matches_single_commit(V, oracle, log_n, ncols, rate_bits, cap_height, coeffs,
+                                            salted, nctx):
+    """vpbs_commit_multi: one commit spread over nctx contexts (row ranges; here the contexts may
+    share a device — the data path is the same as on distinct GPUs) equals the oracle bit for bit:
+    coefficients, leaves, digests in plonky2 layout, cap."""
+    import torch
+    ndev = torch.cuda.device_count()
+    ctxs = [V.Context(g % ndev) for g in range(nctx)]
+    rng = np.random.default_rng(1000 * log_n + ncols + nctx)
+    cols = rand_u64(rng, (ncols, 1 << log_n), 0.05)
+    m = (1 << log_n) << rate_bits
+    salt = rand_u64(rng, (4, m)) if salted else None
+    f = V.PolynomialBatch.from_coeffs if coeffs else V.PolynomialBatch.from_values
+    b = f(cols, rate_bits, salted, cap_height, ctxs=ctxs, salt=salt)
+    ref = oracle.commit(cols, rate_bits, cap_height, coeffs, salt)
+    assert np.array_equal(b.merkle_tree.cap, ref["cap"])
+    assert np.array_equal(b.merkle_tree.digests, ref["digests"])
+    assert np.array_equal(b.merkle_tree.leaves, ref["leaves"])
+    assert np.array_equal(b.polynomials, ref["coeffs"])
+    assert b.stats["kernel_launches"] > 0
+    for c in ctxs:
+        c.close()
+
+
+def test_commit_multi_rejects_bad_context_lists(V, ctx):
+    cols = V.synthetic_columns(4, 1 << 6)
+    a, b, c = V.Context(0), V.Context(0), V.Context(0)
+    with pytest.raises(ValueError):   # not a power of two
+        V.PolynomialBatch.from_values(cols, 3, False, 4, ctxs=[a, b, c])
+    with pytest.raises(ValueError):   # more GPUs than LDE blocks
+        V.PolynomialBatch.from_values(cols, 0, False, 4, ctxs=[a, b])
+    with pytest.raises(ValueError):   # more GPUs than cap subtrees
+        V.PolynomialBatch.from_values(cols, 3, False, 0, ctxs=[a, b])
+    with pytest.raises(ValueError):   # the same context twice
+        V.PolynomialBatch.from_values(cols, 3, False, 4, ctxs=[a, a])
+    with pytest.raises(ValueError):
+        V.PolynomialBatch.from_values(cols, 3, False, 4, ctxs=[])
+    for x in (a, b, c):
+        x.close()
+
+
 def _nccl_worker(rank, world, port, q):
     import os
     import sys

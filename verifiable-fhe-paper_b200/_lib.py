@@ -60,6 +60,9 @@ SIGNATURES = {
                                   u64pp, u64p]),
     "vpbs_commit": (_c.c_int, [_ctx, u64pp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32,
                                _c.c_int, u64pp, u64pp, u64p, u64p, u64p, _c.POINTER(VpbsStats)]),
+    "vpbs_commit_multi": (_c.c_int, [_c.POINTER(_ctx), _c.c_int, u64pp, _c.c_uint32, _c.c_uint32,
+                                     _c.c_uint32, _c.c_uint32, _c.c_int, u64pp, u64pp, u64p, u64p,
+                                     u64p, _c.POINTER(VpbsStats)]),
     "vpbs_commit_dev": (_c.c_int, [_ctx, _c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_uint32,
                                    _c.c_uint32, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.POINTER(VpbsStats)]),

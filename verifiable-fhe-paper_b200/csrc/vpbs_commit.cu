@@ -829,37 +829,51 @@ int vpbs_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint3
   return VPBS_OK;
 }
 
-int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
-                uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
-                const uint64_t* const* salt_cols, uint64_t* const* coeffs_out, uint64_t* leaves_out,
-                uint64_t* digests_out, uint64_t* cap_out, vpbs_stats* stats) {
-  int rc = bind(ctx);
-  if (rc) return rc;
-  if (!cols || ncols == 0 || !cap_out) return fail(ctx, VPBS_ERR_ARG, "null pointer or ncols == 0");
-  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+}  // extern "C"
+
+namespace {
+
+// State between commit_host_enqueue and commit_host_finish.
+struct HostRun {
+  Timer tm{nullptr, false};
+  bool chunked = false;
+  uint64_t l0 = 0;
+};
+
+// One commit — or the row-range shard [first_leaf, first_leaf + nleaves_shard) of one — from host
+// buffers: uploads, kernels and downloads are all ENQUEUED here and nothing is waited for, so that
+// a caller can start several devices before finishing any (vpbs_commit_multi).  This device
+// downloads coefficient columns [cc0, cc1), its leaf rows, and the digests / cap entries of the cap
+// subtrees it owns; the *_out pointers address the shard's own part of the caller's buffers.
+int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                        uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                        const uint64_t* const* salt_cols, u64 first_leaf, u64 nleaves_shard,
+                        uint64_t* const* coeffs_out, u32 cc0, u32 cc1, uint64_t* leaves_out,
+                        uint64_t* digests_out, uint64_t* roots_out, bool want_stats, HostRun* run) {
+  int rc;
   const unsigned log_m = log_n + rate_bits;
-  if (cap_height > log_m)
-    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
   const u64 n = 1ULL << log_n, m = n << rate_bits;
   const u32 width = ncols + (salt_cols ? VPBS_SALT_SIZE : 0);
-  const u64 ncap = 1ULL << cap_height, ndig = 2 * (m - ncap);
+  const unsigned log_sub = log_m - cap_height;
+  const u64 nroots = (nleaves_shard >> log_sub) ? (nleaves_shard >> log_sub) : 1;
+  const u64 ndig = 2 * (nleaves_shard - nroots);
   u64 *din = nullptr, *dco = nullptr, *dle = nullptr, *ddi = nullptr, *dca = nullptr, *dsa = nullptr;
   if ((rc = arena_get(ctx, "in", (size_t)ncols * n * 8, (void**)&din))) return rc;
   if ((rc = arena_get(ctx, "coeffs", (size_t)ncols * n * 8, (void**)&dco))) return rc;
-  if ((rc = arena_get(ctx, "leaves", (size_t)m * width * 8, (void**)&dle))) return rc;
+  if ((rc = arena_get(ctx, "leaves", (size_t)nleaves_shard * width * 8, (void**)&dle))) return rc;
   if ((rc = arena_get(ctx, "digests", ndig * 32, (void**)&ddi))) return rc;
-  if ((rc = arena_get(ctx, "cap", ncap * 32, (void**)&dca))) return rc;
+  if ((rc = arena_get(ctx, "cap", nroots * 32, (void**)&dca))) return rc;
   if (salt_cols && (rc = arena_get(ctx, "salt", (size_t)4 * m * 8, (void**)&dsa))) return rc;
 
-  const uint64_t l0 = ctx->launches;
+  run->l0 = ctx->launches;
   cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
   for (u32 c = 0; c < ncols; c++)
     if (!cols[c]) return fail(ctx, VPBS_ERR_ARG, "cols[c] == NULL");
   // Wide batches are pipelined by column chunk: chunk k's inputs travel on the H2D stream while
-  // chunk k-1 is already being transformed (IFFT + all LDE blocks of its columns).
+  // chunk k-1 is already being transformed.
   const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? 32 : 0;
   const u32 nchunks = chunk_cols ? (ncols + chunk_cols - 1) / chunk_cols : 0;
-  const u64 nblocks = 1ULL << rate_bits;
+  const u64 nblocks = nleaves_shard >> log_n;
   while (ctx->ov.size() < nblocks + 2 * (u64)nchunks + 4) {
     cudaEvent_t e;
     CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -879,8 +893,9 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
     evi += nchunks;
     ovl.coeffs_chunk_ready.assign(ctx->ov.begin() + evi, ctx->ov.begin() + evi + nchunks);
   }
+  run->chunked = nchunks != 0;
   cudaStream_t hs = nchunks ? ctx->h2d_stream : ctx->stream;
-  if (stats) cudaEventRecord(e0, ctx->stream);
+  if (want_stats) cudaEventRecord(e0, ctx->stream);
   if (nchunks) {  // the H2D stream starts after whatever the caller queued on the compute stream
     CU(ctx, cudaEventRecord(all_done, ctx->stream));
     CU(ctx, cudaStreamWaitEvent(hs, all_done, 0));
@@ -897,28 +912,32 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
     if (nchunks) CU(ctx, cudaEventRecord(ovl.h2d_ready[k], hs));
     c0 = c1;
   }
-  if (stats) cudaEventRecord(e1, hs);
+  if (want_stats) cudaEventRecord(e1, hs);
   // Output copies run on the copy stream as soon as their data is final: coefficients after the
   // IFFT, leaf rows after their last NTT pass, digests and cap after the tree.  All kernels are
   // enqueued first, so the copies overlap the remaining NTT passes and the hashing.
-  Timer tm{ctx, stats != nullptr};
-  tm.overlap = &ovl;
-  rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
-                   inputs_are_coeffs ? nullptr : dco, dle, ddi, dca, &tm);
+  run->tm = Timer{ctx, want_stats};
+  run->tm.overlap = &ovl;
+  rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, first_leaf,
+                   nleaves_shard, inputs_are_coeffs ? nullptr : dco, dle, ddi, dca, &run->tm);
+  run->tm.overlap = nullptr;
   if (rc) {
     cudaStreamSynchronize(hs);
     return rc;
   }
   CU(ctx, cudaEventRecord(all_done, ctx->stream));
-  if (stats) cudaEventRecord(e2, ctx->stream);
+  if (want_stats) cudaEventRecord(e2, ctx->stream);
   cudaStream_t cs = ctx->copy_stream;
-  if (coeffs_out) {
+  if (coeffs_out && cc0 < cc1) {
     u64* csrc = inputs_are_coeffs ? din : dco;
     if (!nchunks) CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_ready, 0));
     for (u32 c0 = 0, k = 0; c0 < ncols; k++) {
       const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
-      if (nchunks) CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_chunk_ready[k], 0));
-      CU(ctx, copy_columns(csrc, coeffs_out, c0, c1, n, false, cs));
+      const u32 lo = c0 > cc0 ? c0 : cc0, hi = c1 < cc1 ? c1 : cc1;
+      if (lo < hi) {
+        if (nchunks) CU(ctx, cudaStreamWaitEvent(cs, ovl.coeffs_chunk_ready[k], 0));
+        CU(ctx, copy_columns(csrc, coeffs_out, lo, hi, n, false, cs));
+      }
       c0 = c1;
     }
   }
@@ -936,17 +955,115 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
   CU(ctx, cudaStreamWaitEvent(cs, all_done, 0));
   if (digests_out && ndig)
     CU(ctx, cudaMemcpyAsync(digests_out, ddi, ndig * 32, cudaMemcpyDeviceToHost, cs));
-  CU(ctx, cudaMemcpyAsync(cap_out, dca, ncap * 32, cudaMemcpyDeviceToHost, cs));
-  if (stats) cudaEventRecord(e3, cs);
-  CU(ctx, cudaStreamSynchronize(cs));
+  CU(ctx, cudaMemcpyAsync(roots_out, dca, nroots * 32, cudaMemcpyDeviceToHost, cs));
+  if (want_stats) cudaEventRecord(e3, cs);
+  return VPBS_OK;
+}
+
+int commit_host_finish(vpbs_ctx* ctx, HostRun* run, vpbs_stats* stats) {
+  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
-  if (nchunks) CU(ctx, cudaStreamSynchronize(hs));
+  if (run->chunked) CU(ctx, cudaStreamSynchronize(ctx->h2d_stream));
   if (stats) {
     memset(stats, 0, sizeof *stats);
-    fill_stats(stats, tm, ctx->launches - l0);
-    cudaEventElapsedTime(&stats->h2d_ms, e0, e1);
-    cudaEventElapsedTime(&stats->d2h_ms, e2, e3);
-    cudaEventElapsedTime(&stats->total_ms, e0, e3);
+    fill_stats(stats, run->tm, ctx->launches - run->l0);
+    cudaEventElapsedTime(&stats->h2d_ms, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&stats->d2h_ms, ctx->ev[6], ctx->ev[7]);
+    cudaEventElapsedTime(&stats->total_ms, ctx->ev[4], ctx->ev[7]);
+  }
+  return VPBS_OK;
+}
+
+int check_commit_args(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                      uint32_t rate_bits, uint32_t cap_height, const uint64_t* cap_out) {
+  if (!cols || ncols == 0 || !cap_out) return fail(ctx, VPBS_ERR_ARG, "null pointer or ncols == 0");
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  if (cap_height > log_n + rate_bits)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  return VPBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
+                uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                const uint64_t* const* salt_cols, uint64_t* const* coeffs_out, uint64_t* leaves_out,
+                uint64_t* digests_out, uint64_t* cap_out, vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if ((rc = check_commit_args(ctx, cols, ncols, log_n, rate_bits, cap_height, cap_out))) return rc;
+  HostRun run;
+  rc = commit_host_enqueue(ctx, cols, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, salt_cols,
+                           0, 1ULL << (log_n + rate_bits), coeffs_out, 0, ncols, leaves_out,
+                           digests_out, cap_out, stats != nullptr, &run);
+  if (rc) return rc;
+  return commit_host_finish(ctx, &run, stats);
+}
+
+int vpbs_commit_multi(vpbs_ctx* const* ctxs, int nctx, const uint64_t* const* cols, uint32_t ncols,
+                      uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                      const uint64_t* const* salt_cols, uint64_t* const* coeffs_out,
+                      uint64_t* leaves_out, uint64_t* digests_out, uint64_t* cap_out,
+                      vpbs_stats* stats) {
+  if (!ctxs || nctx < 1 || !ctxs[0]) return fail(nullptr, VPBS_ERR_ARG, "no contexts");
+  vpbs_ctx* c0 = ctxs[0];
+  int rc;
+  if ((rc = check_commit_args(c0, cols, ncols, log_n, rate_bits, cap_height, cap_out))) return rc;
+  if (nctx & (nctx - 1)) return fail(c0, VPBS_ERR_ARG, "nctx must be a power of two");
+  if ((u64)nctx > (1ULL << rate_bits) || (u64)nctx > (1ULL << cap_height))
+    return fail(c0, VPBS_ERR_ARG,
+                "nctx must not exceed 2^rate_bits (whole LDE blocks per GPU) or 2^cap_height "
+                "(whole cap subtrees per GPU)");
+  for (int g = 0; g < nctx; g++) {
+    if (!ctxs[g]) return fail(c0, VPBS_ERR_ARG, "ctxs[g] == NULL");
+    for (int k = 0; k < g; k++)
+      if (ctxs[k] == ctxs[g]) return fail(c0, VPBS_ERR_ARG, "the same context twice");
+  }
+  const u64 n = 1ULL << log_n, m = n << rate_bits;
+  const u32 width = ncols + (salt_cols ? VPBS_SALT_SIZE : 0);
+  const u64 ncap = 1ULL << cap_height;
+  const u64 shard = m / (u64)nctx, cap_per = ncap / (u64)nctx, dig_per = 2 * (shard - cap_per);
+  std::vector<HostRun> runs((size_t)nctx);
+  std::vector<vpbs_stats> st((size_t)nctx);
+  int enq = 0;
+  for (; enq < nctx; enq++) {  // start every device ...
+    vpbs_ctx* ctx = ctxs[enq];
+    if ((rc = bind(ctx))) break;
+    const u32 cc0 = (u32)((u64)ncols * enq / nctx), cc1 = (u32)((u64)ncols * (enq + 1) / nctx);
+    rc = commit_host_enqueue(ctx, cols, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs,
+                             salt_cols, shard * enq, shard, coeffs_out, cc0, cc1,
+                             leaves_out ? leaves_out + shard * enq * width : nullptr,
+                             digests_out ? digests_out + dig_per * enq * 4 : nullptr,
+                             cap_out + cap_per * enq * 4, stats != nullptr, &runs[enq]);
+    if (rc) break;
+  }
+  int first_err = rc;
+  vpbs_ctx* err_ctx = rc ? ctxs[enq] : nullptr;
+  for (int g = 0; g < enq; g++) {  // ... then wait for all of them
+    vpbs_ctx* ctx = ctxs[g];
+    int r2 = bind(ctx);
+    if (!r2) r2 = commit_host_finish(ctx, &runs[g], stats ? &st[g] : nullptr);
+    if (r2 && !first_err) {
+      first_err = r2;
+      err_ctx = ctx;
+    }
+  }
+  if (first_err) {
+    if (err_ctx && err_ctx != c0) c0->err = err_ctx->err;  // vpbs_last_error(ctxs[0]) explains
+    return first_err;
+  }
+  if (stats) {  // the slowest device bounds the call; launches add up
+    *stats = st[0];
+    for (int g = 1; g < nctx; g++) {
+      stats->kernel_launches += st[g].kernel_launches;
+      if (st[g].total_ms > stats->total_ms) {
+        const uint64_t l = stats->kernel_launches;
+        *stats = st[g];
+        stats->kernel_launches = l;
+      }
+    }
   }
   return VPBS_OK;
 }

@@ -342,19 +342,26 @@ class PolynomialBatch:
     @classmethod
     def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
                     fft_root_table=None, *, ctx: Optional[Context] = None, salt=None,
-                    rng: Optional[np.random.Generator] = None) -> "PolynomialBatch":
+                    rng: Optional[np.random.Generator] = None, ctxs=None) -> "PolynomialBatch":
         """values: (ncols, n) evaluations over <w_n>.  `timing` / `fft_root_table` are accepted for
-        signature parity (timings come back in .stats; root tables are cached on the device)."""
-        return cls._commit(values, rate_bits, blinding, cap_height, False, ctx, salt, rng)
+        signature parity (timings come back in .stats; root tables are cached on the device).
+        ctxs: a list of Contexts on distinct GPUs spreads this one commit over them
+        (vpbs_commit_multi: row ranges per GPU, no GPU-to-GPU traffic, identical outputs)."""
+        return cls._commit(values, rate_bits, blinding, cap_height, False, ctx, salt, rng, ctxs)
 
     @classmethod
     def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
                     fft_root_table=None, *, ctx: Optional[Context] = None, salt=None,
-                    rng: Optional[np.random.Generator] = None) -> "PolynomialBatch":
-        return cls._commit(polynomials, rate_bits, blinding, cap_height, True, ctx, salt, rng)
+                    rng: Optional[np.random.Generator] = None, ctxs=None) -> "PolynomialBatch":
+        return cls._commit(polynomials, rate_bits, blinding, cap_height, True, ctx, salt, rng, ctxs)
 
     @classmethod
-    def _commit(cls, cols, rate_bits, blinding, cap_height, are_coeffs, ctx, salt, rng):
+    def _commit(cls, cols, rate_bits, blinding, cap_height, are_coeffs, ctx, salt, rng, ctxs=None):
+        if ctxs is not None:
+            ctxs = list(ctxs)
+            if not ctxs:
+                raise ValueError("ctxs must not be empty")
+            ctx = ctxs[0]
         ctx = ctx or default_context()
         a = _as_u64(cols)
         if a.ndim != 2 or a.shape[0] == 0:
@@ -384,10 +391,17 @@ class PolynomialBatch:
         digests = np.empty((ndig, 4), np.uint64)
         cap = np.empty((1 << cap_height, 4), np.uint64)
         st = VpbsStats()
-        ctx.check(ctx.lib.vpbs_commit(ctx.handle, colp, ncols, log_n, rate_bits, cap_height,
-                                      int(are_coeffs), saltp, cop, _ptr(leaves),
-                                      _ptr(digests) if ndig else None, _ptr(cap),
-                                      ctypes.byref(st)))
+        if ctxs is not None:
+            handles = (ctypes.c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+            ctx.check(ctx.lib.vpbs_commit_multi(handles, len(ctxs), colp, ncols, log_n, rate_bits,
+                                                cap_height, int(are_coeffs), saltp, cop, _ptr(leaves),
+                                                _ptr(digests) if ndig else None, _ptr(cap),
+                                                ctypes.byref(st)))
+        else:
+            ctx.check(ctx.lib.vpbs_commit(ctx.handle, colp, ncols, log_n, rate_bits, cap_height,
+                                          int(are_coeffs), saltp, cop, _ptr(leaves),
+                                          _ptr(digests) if ndig else None, _ptr(cap),
+                                          ctypes.byref(st)))
         if are_coeffs:
             coeffs = a % np.uint64(P) if (a >= np.uint64(P)).any() else a
         return cls(coeffs, MerkleTree(leaves, digests, cap), log_n, rate_bits, blinding,
