@@ -58,7 +58,10 @@ __device__ __forceinline__ u64 leaf_digest_pos(u64 l) { return 4 * (l >> 1) + (l
 #define VPBS_HASH_THREADS 128
 #endif
 #ifndef VPBS_HASH_MIN_BLOCKS
-#define VPBS_HASH_MIN_BLOCKS 4  // <= 128 registers: no spills around the S-box calls (6.79 ms; 5 -> 7.10 ms, 6 -> 7.35 ms)
+// Occupancy does not matter any more (the kernel is bound by the ALU pipe in the full rounds and
+// the FP64 pipe in the pair steps): 3 / 4 / 5 / 6 CTAs per SM measure 5.55 / 5.54 / 5.52 / 5.59 ms,
+// 64- and 256-thread CTAs the same.
+#define VPBS_HASH_MIN_BLOCKS 4
 #endif
 // One thread per leaf.  all_cap: the tree has no digests, leaf hashes are the cap.
 __global__ void __launch_bounds__(VPBS_HASH_THREADS, VPBS_HASH_MIN_BLOCKS)
