@@ -28,6 +28,9 @@ using gl::u64;
 constexpr int THREADS = 256;
 constexpr unsigned LOG_TILE = 12;  // 4096 elements (32 KB) per CTA
 constexpr unsigned MAX_PASS_BITS = 8;
+#ifndef VPBS_NTT_R16_MIN_BLOCKS
+#define VPBS_NTT_R16_MIN_BLOCKS 4  // 64 registers: 4 CTAs (32 warps) per SM to cover the load latency
+#endif
 
 struct Roots {
   const u64* w;    // w[t] = omega_N^t, t < N/2
@@ -236,12 +239,18 @@ __device__ __forceinline__ void dft256_regs(u64 (&x)[16], u64* sm, const u64* tw
 // OUT_TW = false leaves out the four-step twiddle w_B^(low * brev(q)) at the store: the following
 // pass_final_r16 applies it at its load (in_tw_log_B), where one CTA needs only 256 distinct
 // twiddles shared by its 16 columns instead of 4096 scattered table reads per CTA here.
+// With OUT_TW = false the input scaling is split as well: in_scale[pos] = g^pos with
+// pos = q * 2^log_sigma + low factors into g^(q 2^log_sigma) * g^low, and g^low is constant along
+// the 256-point DFT (over q), so this pass applies only the 256 factors g^(q 2^log_sigma) (gathered
+// into shared memory once per CTA) and the next pass folds g^low into its twiddle table.  No
+// per-element scale loads from global memory remain (they were the largest stall of this kernel).
 template <bool INVERSE, bool OUT_TW = true>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, VPBS_NTT_R16_MIN_BLOCKS)
 pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restrict__ dst,
                  u64 dst_col_stride, unsigned log_B, const u64* __restrict__ in_scale, Roots R) {
   __shared__ u64 sm[256 * 16];
   __shared__ u64 tw[128];
+  __shared__ u64 sq[OUT_TW ? 1 : 256];
   const unsigned log_sigma = log_B - 8;
   const unsigned tiles_per_block_log = log_sigma - 4;
   const u64 blk = blockIdx.x >> tiles_per_block_log;
@@ -251,14 +260,19 @@ pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restric
   dst += (u64)blockIdx.y * dst_col_stride;
   const unsigned t = threadIdx.x & 15, qa = threadIdx.x >> 4;  // (q_lo | q_hi, lane): lane fastest
   if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  if (!OUT_TW && in_scale) sq[threadIdx.x] = __ldg(in_scale + base + ((u64)threadIdx.x << log_sigma));
   u64 x[16];
 #pragma unroll
   for (int j = 0; j < 16; j++) {
     const u64 pos = base + ((u64)(16 * j + qa) << log_sigma) + low0 + t;
     x[j] = __ldg(src + pos);  // any representative: dif16 canonicalises what it must
-    if (in_scale) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + pos));
+    if (OUT_TW && in_scale) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + pos));
   }
-  __syncthreads();  // tw ready
+  __syncthreads();  // tw, sq ready
+  if (!OUT_TW && in_scale) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], sq[16 * j + qa]);
+  }
   dft256_regs(x, sm, tw, 16, qa, t, qa, t);
 #pragma unroll
   for (int j = 0; j < 16; j++) {
@@ -275,11 +289,11 @@ pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restric
 }
 
 template <bool INVERSE, int MODE>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, VPBS_NTT_R16_MIN_BLOCKS)
 pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
                u64* __restrict__ dst, u64 dst_stride, u64 row0, unsigned log_n,
                const u64* __restrict__ in_scale, u64 out_scale, Roots R,
-               unsigned in_tw_log_B = 0) {
+               unsigned in_tw_log_B = 0, const u64* __restrict__ in_tw_scale = nullptr) {
   __shared__ u64 sm[256 * 17];
   __shared__ u64 tw[128];
   __shared__ u64 tws[256];
@@ -289,8 +303,11 @@ pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
   // sub-blocks: this CTA's 256 positions are (q = blockIdx.x mod 256, low = 0..255) and their
   // pending twiddles w_B^(low * brev(q)) do not depend on the column.
   const bool in_tw = MODE == STORE_LEAF && in_tw_log_B != 0;
-  if (in_tw)
-    tws[threadIdx.x] = root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev(blockIdx.x & 255u, 8));
+  if (in_tw) {  // ... times the g^low half of the previous pass's input scaling, if it left one
+    u64 w = root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev(blockIdx.x & 255u, 8));
+    if (in_tw_scale) w = gl::mul_lazy(w, __ldg(in_tw_scale + threadIdx.x));
+    tws[threadIdx.x] = w;
+  }
   // load mapping: q_lo fastest (16 consecutive elements of one column / block per half warp)
   const unsigned q_lo = threadIdx.x & 15, lane_a = threadIdx.x >> 4;
   u64 x[16];
@@ -338,6 +355,203 @@ pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
       dst[(u64)blockIdx.y * dst_stride + nat] = v;
     }
   }
+}
+
+// ---- persistent radix-16 passes with asynchronous tile prefetch ---------------------------------
+// ncu on the kernels above (profiles/r1_ntt_r16_kernels_v2.txt): issue slots 41-47 % busy, the
+// largest stall by far is the global-load scoreboard — every CTA loads, then computes, then stores,
+// and with 4 CTAs per SM the load phases are not covered.  Here a CTA walks over tiles and the
+// NEXT tile's elements travel global -> shared with cp.async while the current tile is being
+// transformed.  Every thread copies exactly the 16 elements it will later pick up, into exactly
+// the shared-memory slots it later uses for the register exchange, so the staging buffer doubles
+// as the exchange buffer and no barrier is needed for the copies themselves (two buffers of one
+// tile each; 3 CTAs per SM).
+__device__ __forceinline__ void cp_async8(u64* smem_dst, const u64* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int R16P_MIN_BLOCKS = 3;
+constexpr size_t R16P_STRIDED_SMEM = (2 * 256 * 16 + 128 + 256) * sizeof(u64);
+constexpr size_t R16P_FINAL_SMEM = (2 * 256 * 17 + 128 + 2 * 256) * sizeof(u64);
+
+// pass_strided_r16 over tiles (tile_x < tiles_x, column < ncols), tile = column * tiles_x + tile_x.
+template <bool INVERSE, bool OUT_TW>
+__global__ void __launch_bounds__(THREADS, R16P_MIN_BLOCKS)
+pass_strided_r16p(const u64* __restrict__ src, u64 src_col_stride, u64* __restrict__ dst,
+                  u64 dst_col_stride, unsigned log_B, const u64* __restrict__ in_scale, Roots R,
+                  unsigned tiles_x, unsigned ntiles) {
+  extern __shared__ u64 dyn[];
+  u64* buf = dyn;                  // [2][256 * 16]
+  u64* tw = dyn + 2 * 256 * 16;    // [128]
+  u64* sq = tw + 128;              // [256]
+  const unsigned log_sigma = log_B - 8;
+  const unsigned tiles_per_block_log = log_sigma - 4;
+  const unsigned t = threadIdx.x & 15, qa = threadIdx.x >> 4;
+  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  unsigned tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  auto issue = [&](unsigned tl, u64* b) {
+    const unsigned bx = tl % tiles_x, by = tl / tiles_x;
+    const u64 blk = bx >> tiles_per_block_log;
+    const u64 low0 = (u64)(bx & ((1u << tiles_per_block_log) - 1)) << 4;
+    const u64* p = src + (u64)by * src_col_stride + (blk << log_B) + low0 + t;
+#pragma unroll
+    for (int j = 0; j < 16; j++) cp_async8(b + (16 * j + qa) * 16 + t, p + ((u64)(16 * j + qa) << log_sigma));
+  };
+  issue(tile, buf);
+  cp_async_commit();
+  // the split input scaling needs one block per transform (blk == 0), which is what OUT_TW = false
+  // is used for; the general form reads the scale per element below
+  if (!OUT_TW && in_scale) sq[threadIdx.x] = __ldg(in_scale + ((u64)threadIdx.x << log_sigma));
+  __syncthreads();  // tw, sq ready
+  for (unsigned it = 0;; it++) {
+    u64* cur = buf + (it & 1) * (256 * 16);
+    const unsigned next = tile + gridDim.x;
+    if (next < ntiles) issue(next, buf + ((it & 1) ^ 1) * (256 * 16));
+    cp_async_commit();
+    cp_async_wait<1>();  // this tile's copies (issued one iteration ago) have landed
+    const unsigned bx = tile % tiles_x, by = tile / tiles_x;
+    const u64 blk = bx >> tiles_per_block_log;
+    const u64 low0 = (u64)(bx & ((1u << tiles_per_block_log) - 1)) << 4;
+    const u64 base = blk << log_B;
+    u64 x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = cur[(16 * j + qa) * 16 + t];
+    if (in_scale) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        if (OUT_TW) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + base + ((u64)(16 * j + qa) << log_sigma) + low0 + t));
+        else x[j] = gl::mul_lazy(x[j], sq[16 * j + qa]);
+      }
+    }
+    dif16<true>(x, tw, 16, qa, 0);
+#pragma unroll
+    for (int j = 0; j < 16; j++) cur[(16 * j + qa) * 16 + t] = x[j];  // own slots only
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = cur[(16 * qa + j) * 16 + t];
+    __syncthreads();  // everyone is done with `cur` before the next iteration refills it
+    dif16<false>(x, tw, 1, 0, 4);
+    u64* out = dst + (u64)by * dst_col_stride + base + low0 + t;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const unsigned q = 16 * qa + j;
+      if (OUT_TW) {
+        const u64 e = (low0 + t) * (u64)brev(q, 8);
+        out[(u64)q << log_sigma] = e ? gl::mul_lazy(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
+      } else {
+        out[(u64)q << log_sigma] = x[j];
+      }
+    }
+    if (next >= ntiles) break;
+    tile = next;
+  }
+  cp_async_wait<0>();
+}
+
+// pass_final_r16 over tiles (tile_x < tiles_x, tile_y < tiles_y), tile = tile_y * tiles_x + tile_x
+// (STORE_LEAF: tile_y = group of 16 columns; STORE_NATURAL: tile_y = column).
+template <bool INVERSE, int MODE>
+__global__ void __launch_bounds__(THREADS, R16P_MIN_BLOCKS)
+pass_final_r16p(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
+                u64* __restrict__ dst, u64 dst_stride, u64 row0, unsigned log_n,
+                const u64* __restrict__ in_scale, u64 out_scale, Roots R, unsigned in_tw_log_B,
+                const u64* __restrict__ in_tw_scale, unsigned tiles_x, unsigned ntiles) {
+  extern __shared__ u64 dyn[];
+  u64* buf = dyn;                  // [2][256 * 17]
+  u64* tw = dyn + 2 * 256 * 17;    // [128]
+  u64* tws = tw + 128;             // [2][256]
+  const unsigned log_nb = log_n - 8;
+  const bool in_tw = MODE == STORE_LEAF && in_tw_log_B != 0;
+  const unsigned q_lo = threadIdx.x & 15, lane_a = threadIdx.x >> 4;
+  const unsigned lane_b = threadIdx.x & 15, q_hi = threadIdx.x >> 4;
+  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  unsigned tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  // source of this thread's 16 elements of tile tl (nullptr: column beyond ncols)
+  auto source = [&](unsigned tl) -> const u64* {
+    const unsigned bx = tl % tiles_x, by = tl / tiles_x;
+    if (MODE == STORE_LEAF) {
+      const unsigned col = by * 16 + lane_a;
+      return col < ncols ? src + (u64)col * src_col_stride + ((u64)bx << 8) + q_lo : nullptr;
+    }
+    return src + (u64)by * src_col_stride + ((u64)brev(bx * 16 + lane_a, log_nb) << 8) + q_lo;
+  };
+  auto issue = [&](unsigned tl, u64* b) {
+    const u64* p = source(tl);
+    if (p) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) cp_async8(b + (16 * j + q_lo) * 17 + lane_a, p + 16 * j);
+    }
+  };
+  auto twiddle = [&](unsigned tl) -> u64 {  // pending four-step twiddle (times the g^low scaling)
+    return root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev((tl % tiles_x) & 255u, 8));
+  };
+  const u64 tw_scale = (in_tw && in_tw_scale) ? __ldg(in_tw_scale + threadIdx.x) : 1;
+  issue(tile, buf);
+  cp_async_commit();
+  if (in_tw) tws[threadIdx.x] = gl::mul_lazy(twiddle(tile), tw_scale);
+  for (unsigned it = 0;; it++) {
+    u64* cur = buf + (it & 1) * (256 * 17);
+    const u64* twc = tws + (it & 1) * 256;
+    const unsigned next = tile + gridDim.x;
+    u64 w_next = 0;
+    if (next < ntiles) {
+      issue(next, buf + ((it & 1) ^ 1) * (256 * 17));
+      if (in_tw) w_next = twiddle(next);  // the load completes behind this tile's arithmetic
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();  // tw / this tile's tws visible
+    const bool have = source(tile) != nullptr;
+    u64 x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = have ? cur[(16 * j + q_lo) * 17 + lane_a] : 0;
+    if (in_scale && have) {
+      const unsigned bx = tile % tiles_x;
+      const u64 pos0 = MODE == STORE_LEAF ? ((u64)bx << 8) : ((u64)brev(bx * 16 + lane_a, log_nb) << 8);
+#pragma unroll
+      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + pos0 + 16 * j + q_lo));
+    }
+    if (in_tw) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], twc[16 * j + q_lo]);
+    }
+    dif16<true>(x, tw, 16, q_lo, 0);
+#pragma unroll
+    for (int j = 0; j < 16; j++) cur[(16 * j + q_lo) * 17 + lane_a] = x[j];  // own slots only
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = cur[(16 * q_hi + j) * 17 + lane_b];
+    if (in_tw && next < ntiles) tws[((it & 1) ^ 1) * 256 + threadIdx.x] = gl::mul_lazy(w_next, tw_scale);
+    __syncthreads();  // everyone is done with `cur` before the next iteration refills it
+    dif16<false>(x, tw, 1, 0, 4);
+    const unsigned bx = tile % tiles_x, by = tile / tiles_x;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const unsigned q = 16 * q_hi + j;
+      u64 v = x[j];
+      v = (out_scale != 1) ? gl::mul(v, out_scale) : gl::canon(v);
+      if (MODE == STORE_LEAF) {
+        const unsigned col = by * 16 + lane_b;
+        const u64 pos = ((u64)bx << 8) + q;
+        if (col < ncols) dst[(row0 + pos) * dst_stride + col] = v;
+      } else {
+        const u64 nat = ((u64)brev(q, 8) << log_nb) + (u64)bx * 16 + lane_b;
+        dst[(u64)by * dst_stride + nat] = v;
+      }
+    }
+    if (next >= ntiles) break;
+    tile = next;
+  }
+  cp_async_wait<0>();
 }
 
 // ---- polynomial evaluation at quadratic-extension points --------------------------------------------

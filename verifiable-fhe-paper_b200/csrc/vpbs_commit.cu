@@ -58,6 +58,7 @@ struct vpbs_ctx {
   // = 3.46 waves of 148 x 4, and the other stream's CTAs fill the tail wave (LDE 1.67 -> 1.46 ms).
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  unsigned sms = 148;  // persistent NTT passes launch sms * ntt::R16P_MIN_BLOCKS CTAs
   std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
   // Buffers of destroyed resident batches, kept for the next batch of the same shape (a prover
   // commits the same shapes every step; cudaMalloc/cudaFree of ~0.6 GB cost milliseconds).
@@ -228,12 +229,14 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
     if (log_T > log_sigma) log_T = log_sigma;
     const size_t smem = ((size_t)(1u << s << log_T) + (1u << s) / 2) * sizeof(u64);
     dim3 grid((unsigned)(n >> (s + log_T)), ncols);
-    if (s == 8 && log_T == 4 && tw_at_load)
-      ntt::pass_strided_r16<INVERSE, false><<<grid, ntt::THREADS, 0, stream>>>(
-          cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R);
-    else if (s == 8 && log_T == 4)  // 256-point pass: radix-16 register kernel
-      ntt::pass_strided_r16<INVERSE><<<grid, ntt::THREADS, 0, stream>>>(
-          cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R);
+    const unsigned ntiles = grid.x * grid.y;
+    const unsigned pgrid = ntiles < ctx->sms * ntt::R16P_MIN_BLOCKS ? ntiles : ctx->sms * ntt::R16P_MIN_BLOCKS;
+    if (s == 8 && log_T == 4 && tw_at_load)  // 256-point pass: persistent radix-16 register kernel
+      ntt::pass_strided_r16p<INVERSE, false><<<pgrid, ntt::THREADS, ntt::R16P_STRIDED_SMEM, stream>>>(
+          cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R, grid.x, ntiles);
+    else if (s == 8 && log_T == 4)
+      ntt::pass_strided_r16p<INVERSE, true><<<pgrid, ntt::THREADS, ntt::R16P_STRIDED_SMEM, stream>>>(
+          cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R, grid.x, ntiles);
     else
       ntt::pass_strided<INVERSE><<<grid, ntt::THREADS, smem, stream>>>(
           cur, cur_stride, work, n, log_B, s, log_T, p == 0 ? in_scale : nullptr, R);
@@ -249,10 +252,12 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
       const unsigned log_T = 4;
       const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
       dim3 grid((unsigned)(n >> s), (ncols + (1u << log_T) - 1) >> log_T);
+      const unsigned ntiles = grid.x * grid.y;
+      const unsigned pgrid = ntiles < ctx->sms * ntt::R16P_MIN_BLOCKS ? ntiles : ctx->sms * ntt::R16P_MIN_BLOCKS;
       if (s == 8)
-        ntt::pass_final_r16<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, 0, stream>>>(
+        ntt::pass_final_r16p<INVERSE, ntt::STORE_LEAF><<<pgrid, ntt::THREADS, ntt::R16P_FINAL_SMEM, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R,
-            tw_at_load ? log_n : 0u);
+            tw_at_load ? log_n : 0u, tw_at_load ? in_scale : nullptr, grid.x, ntiles);
       else
         ntt::pass_final<INVERSE, ntt::STORE_LEAF><<<grid, ntt::THREADS, smem, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
@@ -261,9 +266,12 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
       if (log_T > log_n - s) log_T = log_n - s;
       const size_t smem = ((size_t)(1u << s) * ((1u << log_T) + 1) + (1u << s) / 2) * sizeof(u64);
       dim3 grid((unsigned)(n >> (s + log_T)), ncols);
+      const unsigned ntiles = grid.x * grid.y;
+      const unsigned pgrid = ntiles < ctx->sms * ntt::R16P_MIN_BLOCKS ? ntiles : ctx->sms * ntt::R16P_MIN_BLOCKS;
       if (s == 8 && log_T == 4)
-        ntt::pass_final_r16<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, 0, stream>>>(
-            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R);
+        ntt::pass_final_r16p<INVERSE, ntt::STORE_NATURAL><<<pgrid, ntt::THREADS, ntt::R16P_FINAL_SMEM, stream>>>(
+            cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R, 0u, nullptr,
+            grid.x, ntiles);
       else
         ntt::pass_final<INVERSE, ntt::STORE_NATURAL><<<grid, ntt::THREADS, smem, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, s, log_T, scale, out_scale, R);
@@ -492,6 +500,25 @@ void fill_stats(vpbs_stats* st, Timer& tm, uint64_t launches) {
 
 bool usable(vpbs_ctx* ctx) { return ctx != nullptr; }
 
+// The persistent NTT passes use two tile buffers (64-68 KB of dynamic shared memory): opt in, on
+// the current device, for every instantiation run_transform launches.
+cudaError_t allow_large_smem() {
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* f, size_t bytes) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  };
+  set((const void*)ntt::pass_strided_r16p<false, false>, ntt::R16P_STRIDED_SMEM);
+  set((const void*)ntt::pass_strided_r16p<false, true>, ntt::R16P_STRIDED_SMEM);
+  set((const void*)ntt::pass_strided_r16p<true, false>, ntt::R16P_STRIDED_SMEM);
+  set((const void*)ntt::pass_strided_r16p<true, true>, ntt::R16P_STRIDED_SMEM);
+  set((const void*)ntt::pass_final_r16p<false, ntt::STORE_LEAF>, ntt::R16P_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16p<false, ntt::STORE_NATURAL>, ntt::R16P_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16p<true, ntt::STORE_LEAF>, ntt::R16P_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16p<true, ntt::STORE_NATURAL>, ntt::R16P_FINAL_SMEM);
+  return e;
+}
+
 // Copies columns [c0, c1) between per-column host pointers and a column-major device buffer
 // (column c at dev + c * n).  Host columns that happen to be adjacent in memory (one allocation, as
 // plonky2's flattened buffers or this repo's hosts provide) travel as ONE transfer: 128 separate
@@ -556,6 +583,12 @@ int vpbs_ctx_create(int device, vpbs_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
   for (int i = 0; e == cudaSuccess && i < 10; i++) e = cudaEventCreate(&ctx->ev[i]);
+  if (e == cudaSuccess) {
+    int sms = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess && sms > 0) ctx->sms = (unsigned)sms;
+  }
+  if (e == cudaSuccess) e = allow_large_smem();
   if (e != cudaSuccess) {
     fail(nullptr, VPBS_ERR_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
     delete ctx;

@@ -48,6 +48,10 @@ int main(int argc, char** argv) {
   const u64 n_inv = gl::inv(n);
   cudaEvent_t e[3];
   for (auto& x : e) cudaEventCreate(&x);
+  cudaFuncSetAttribute(ntt::pass_strided_r16p<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)ntt::R16P_STRIDED_SMEM);
+  cudaFuncSetAttribute(ntt::pass_final_r16p<false, ntt::STORE_LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)ntt::R16P_FINAL_SMEM);
   u64* work2;
   cudaMalloc(&work2, C * n * 8);
   cudaStream_t st[2];
@@ -76,10 +80,18 @@ int main(int argc, char** argv) {
       dim3 g1((unsigned)(n >> 12), C), g2((unsigned)(n >> 8), (C + 15) / 16);
       cudaStream_t q = st[b & 1];
       u64* wk = (b & 1) ? work2 : work;
+#ifdef NTT_BENCH_PERSIST
+      const unsigned nt1 = g1.x * g1.y, nt2 = g2.x * g2.y, cap = 148 * NTT_BENCH_PERSIST;
+      ntt::pass_strided_r16p<false, false><<<nt1 < cap ? nt1 : cap, ntt::THREADS, ntt::R16P_STRIDED_SMEM, q>>>(
+          coeffs, n, wk, n, log_n, coset + (b << log_n), R, g1.x, nt1);
+      ntt::pass_final_r16p<false, ntt::STORE_LEAF><<<nt2 < cap ? nt2 : cap, ntt::THREADS, ntt::R16P_FINAL_SMEM, q>>>(
+          wk, n, C, leaves, C, b << log_n, log_n, nullptr, 1, R, log_n, coset + (b << log_n), g2.x, nt2);
+#else
       ntt::pass_strided_r16<false, false><<<g1, ntt::THREADS, 0, q>>>(coeffs, n, wk, n, log_n,
                                                                       coset + (b << log_n), R);
       ntt::pass_final_r16<false, ntt::STORE_LEAF><<<g2, ntt::THREADS, 0, q>>>(wk, n, C, leaves, C, b << log_n,
-                                                                            log_n, nullptr, 1, R, log_n);
+                                                                            log_n, nullptr, 1, R, log_n, coset + (b << log_n));
+#endif
     }
     cudaEventRecord(join[0], st[0]);
     cudaEventRecord(join[1], st[1]);
@@ -97,7 +109,7 @@ int main(int argc, char** argv) {
       ntt::pass_strided_r16<false, false><<<g1, ntt::THREADS>>>(coeffs, n, work, n, log_n,
                                                                 coset + (b << log_n), R);
       ntt::pass_final_r16<false, ntt::STORE_LEAF><<<g2, ntt::THREADS>>>(work, n, C, leaves, C, b << log_n,
-                                                                      log_n, nullptr, 1, R, log_n);
+                                                                      log_n, nullptr, 1, R, log_n, coset + (b << log_n));
 #endif
     }
     cudaEventRecord(e[2]);
