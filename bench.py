@@ -536,14 +536,14 @@ def main():
         "traffic": traffic.get("hash_leaves_dram_bytes"),
     }
     roofline_hbm = {
-        "kernels": "ntt::pass_strided_r16<fwd> + ntt::pass_final_r16<fwd, leaf> x 8 LDE blocks (coset LDE "
+        "kernels": "ntt::pass_strided_r16p<fwd> + ntt::pass_final_r16p<fwd, leaf> x 8 LDE blocks (coset LDE "
                    "with fused transpose / bit-reversal; phase \"FFT + blinding\" + \"transpose LDEs\")",
         "bound": "hbm", "achieved": lde_bytes / (fft_ms * 1e-3) / 1e9, "peak": hbm_peak,
         "unit": "GB/s", "frac": lde_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
         "peak_source": hbm_src, "algorithmic_bytes": lde_bytes, "ms": fft_ms,
         "traffic": traffic.get("lde_forward_dram_bytes"),
-        "note": "ncu shows these kernels ALU-pipe bound (72 % alu, 57 % issue), not DRAM bound: "
-                "profiles/r1_ntt_r16_kernels.txt",
+        "note": "ncu shows these kernels bound by the ALU pipe and load latency, not by DRAM "
+                "(DRAM throughput ~11 % of peak): profiles/r1_ntt_r16p_kernels.txt",
     }
     whole = {"algorithmic_bytes": algorithmic_bytes(NCOLS, n, RATE_BITS, CAP_HEIGHT),
              "permutations": permutations(NCOLS, n, RATE_BITS, CAP_HEIGHT),
