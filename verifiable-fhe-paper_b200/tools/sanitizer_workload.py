@@ -17,4 +17,10 @@ vals = rng.integers(0, 2**64, size=(1 << 10, 2), dtype=np.uint64)
 V.fri_layer_commit(vals, 4, 2, ctx); V.fri_fold(vals, 4, (3, 4), 49, ctx)
 V.fri_proof_of_work(rng.integers(0, 2**63, size=12, dtype=np.uint64), 3, 8, ctx=ctx)
 V.MerkleTree.new(rng.integers(0, 2**64, size=(1 << 12, 33), dtype=np.uint64), 3, ctx)
+# multi-context commit (row ranges) and a 2^16-row, 70-column batch: chunked upload, persistent NTT
+# passes over several tiles per CTA (cp.async staging buffers reused), two-stream LDE
+cols = rng.integers(0, 2**64, size=(70, 1 << 16), dtype=np.uint64)
+ctxs = [V.Context(0), V.Context(0)]
+V.PolynomialBatch.from_values(cols, 1, False, 2, ctxs=ctxs)
+V.PolynomialBatch.from_values(cols, 1, False, 2, ctx=ctx)
 print("sanitizer workload done")
