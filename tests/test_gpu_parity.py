@@ -382,6 +382,46 @@ def test_commit_multi_matches_single_commit(V, oracle, log_n, ncols, rate_bits, 
         c.close()
 
 
+@pytest.mark.parametrize("log_n,ncols", [(12, 70), (8, 5)])
+def test_commit_with_scattered_host_columns(V, ctx, oracle, log_n, ncols):
+    """The C ABI takes one pointer per column (a Vec<PolynomialValues<F>> is ncols separate
+    allocations).  Adjacent columns are merged into one transfer, so exercise the other cases:
+    separately allocated columns, columns in reverse address order, runs of adjacent columns with
+    gaps, and NULL entries in coeffs_out (columns the caller does not want back)."""
+    import ctypes
+    rng = np.random.default_rng(log_n + ncols)
+    n = 1 << log_n
+    r, h = 2, 3
+    m = n << r
+    backing = rand_u64(rng, (2 * ncols + 8, n))          # columns live at odd rows, reversed order
+    rows = [2 * (ncols - 1 - c) + 1 for c in range(ncols)]
+    rows[:4] = [2 * ncols + 1, 2 * ncols + 2, 2 * ncols + 3, 2 * ncols + 5]  # a run of 3, a gap, 1
+    cols = np.stack([backing[i] for i in rows])
+    u64p = V._lib.u64p
+    colp = (u64p * ncols)(*[backing[i].ctypes.data_as(u64p) for i in rows])
+    out_back = np.zeros((ncols + 2, n), np.uint64)
+    want = [c for c in range(ncols) if c % 3 != 1]
+    cop = (u64p * ncols)(*[out_back[c + (c > 2)].ctypes.data_as(u64p) if c in want else None
+                           for c in range(ncols)])
+    leaves = np.empty((m, ncols), np.uint64)
+    digests = np.empty((2 * (m - (1 << h)), 4), np.uint64)
+    cap = np.empty((1 << h, 4), np.uint64)
+    ctx.check(ctx.lib.vpbs_commit(ctx.handle, colp, ncols, log_n, r, h, 0, None, cop,
+                                  leaves.ctypes.data_as(u64p), digests.ctypes.data_as(u64p),
+                                  cap.ctypes.data_as(u64p), None))
+    ref = oracle.commit(cols, r, h, False)
+    assert np.array_equal(cap, ref["cap"])
+    assert np.array_equal(digests, ref["digests"])
+    assert np.array_equal(leaves, ref["leaves"])
+    for c in range(ncols):
+        got = out_back[c + (c > 2)]
+        if c in want:
+            assert np.array_equal(got, ref["coeffs"][c]), c
+        else:
+            assert not got.any(), c   # skipped outputs stay untouched
+    assert not out_back[3].any()      # the gap row between outputs 2 and 3
+
+
 def test_commit_multi_rejects_bad_context_lists(V, ctx):
     cols = V.synthetic_columns(4, 1 << 6)
     a, b, c = V.Context(0), V.Context(0), V.Context(0)

@@ -624,45 +624,51 @@ __device__ __forceinline__ void permute_lazy(u64 (&s)[WIDTH]) {
 // `sh` = 48 doubles of shared memory private to the group (low halves at [0,24), high halves at
 // [24,48), each stored twice so that the rotation (l + i) needs no wrap-around).
 // All 32 threads of the warp must call this together (it uses __syncwarp()).
-__device__ __forceinline__ void permute_coop(u64& w, double* __restrict__ sh, unsigned l) {
+__device__ __forceinline__ u64 mad_wide(u32 x, u32 c, u64 acc) {
+  asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "r"(c));
+  return acc;
+}
+// The MDS layer here is the INTEGER form (IMAD.WIDE chains on the 32-bit halves): this routine is
+// latency bound, a dependent DFMA costs ~64 cycles on this part against ~6-10 for IMAD.WIDE + carry,
+// and the FP64 form spent three quarters of every round waiting on its accumulation chains (one
+// tree level 27 us -> see DESIGN.md 4.3).  Throughput does not matter at these sizes.
+__device__ __forceinline__ void permute_coop(u64& w, double* __restrict__ sh_d, unsigned l) {
+  u64* __restrict__ sh = reinterpret_cast<u64*>(sh_d);  // [0,24): the 12 words, stored twice
   const bool active = l < WIDTH;
   const unsigned ll = active ? l : 0;
-  if (active) {  // RC[l] = (lo32, hi32) parts of row 0 of RCD_G minus the 2^52 bias
-    const double2 rc0 = __ldg(reinterpret_cast<const double2*>(RCD_G) + ll);
-    const u64 c = ((u64)(u32)__double2loint(rc0.y) << 32) | (u32)__double2loint(rc0.x);
-    w = gl::add_lazy(w, c);
-  }
-  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
-  constexpr double CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  auto rc_of = [&](int r) -> u64 {  // RC[r][l] from the split table (2^52-biased halves)
+    const double2 rc = __ldg(reinterpret_cast<const double2*>(RCD_G) + (WIDTH * r + ll));
+    return ((u64)(u32)__double2loint(rc.y) << 32) | (u32)__double2loint(rc.x);
+  };
+  if (active) w = gl::add_lazy(w, rc_of(0));
+  constexpr u32 CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 #pragma unroll 1
   for (int r = 0; r < ROUNDS; r++) {
     const bool full = r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS;
     // next round's constants: issued before the S-box so that the load latency hides behind it
-    const double2 rc2 = __ldg(reinterpret_cast<const double2*>(RCD_G) + (WIDTH * (r + 1) + ll));
+    const u64 rc = rc_of(r + 1);
     if (active && (full || l == 0)) w = sbox7(w);
     if (active) {
-      const double dl = half_to_f64((u32)w), dh = half_to_f64((u32)(w >> 32));
-      sh[l] = dl;
-      sh[l + 12] = dl;
-      sh[24 + l] = dh;
-      sh[36 + l] = dh;
+      sh[l] = w;
+      sh[l + 12] = w;
     }
     __syncwarp();
     if (active) {
-      double al0 = rc2.x, ah0 = rc2.y, al1 = 0.0, ah1 = 0.0;  // two chains each: shorter latency
+      u64 al0 = (u32)rc, ah0 = rc >> 32, al1 = 0, ah1 = 0;  // two chains per half: shorter latency
 #pragma unroll
       for (int i = 0; i < WIDTH; i += 2) {
-        al0 = fma(sh[l + i], CIRC[i], al0);
-        ah0 = fma(sh[24 + l + i], CIRC[i], ah0);
-        al1 = fma(sh[l + i + 1], CIRC[i + 1], al1);
-        ah1 = fma(sh[24 + l + i + 1], CIRC[i + 1], ah1);
+        const u64 x0 = sh[l + i], x1 = sh[l + i + 1];
+        al0 = mad_wide((u32)x0, CIRC[i], al0);
+        ah0 = mad_wide((u32)(x0 >> 32), CIRC[i], ah0);
+        al1 = mad_wide((u32)x1, CIRC[i + 1], al1);
+        ah1 = mad_wide((u32)(x1 >> 32), CIRC[i + 1], ah1);
       }
       if (l == 0) {  // MDS_MATRIX_DIAG = [8, 0, ..., 0]
-        al1 = fma(sh[0], 8.0, al1);
-        ah1 = fma(sh[24], 8.0, ah1);
+        const u64 x0 = sh[0];
+        al1 = mad_wide((u32)x0, 8u, al1);
+        ah1 = mad_wide((u32)(x0 >> 32), 8u, ah1);
       }
-      w = reduce96((u64)__double_as_longlong(al0 + al1) & MANT,
-                   (u64)__double_as_longlong(ah0 + ah1) & MANT);
+      w = reduce96(al0 + al1, ah0 + ah1);  // each sum < 2^43
     }
     __syncwarp();
   }

@@ -313,7 +313,12 @@ int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, uns
     return (unsigned)(v < 4 ? 4 : v > 24 ? 24 : v);
   }();
   const unsigned coop_from = total_log > coop_log ? total_log - coop_log : 1;  // first level with <= 2^coop_log nodes
-  unsigned fused_from = log_sub > 4 ? log_sub - 4 : 1;               // <= 16 nodes per subtree
+  static const unsigned fuse_log = [] {  // developer knob for threshold sweeps
+    const char* e = getenv("VPBS_FUSE_LOG");
+    const int v = e ? atoi(e) : 4;
+    return (unsigned)(v < 1 ? 1 : v > 12 ? 12 : v);
+  }();
+  unsigned fused_from = log_sub > fuse_log ? log_sub - fuse_log : 1;  // <= 2^fuse_log nodes per subtree
   if (fused_from < coop_from) fused_from = coop_from;
   const bool fuse = nsub <= 4096;
   for (unsigned level = 1; level <= log_sub; level++) {
