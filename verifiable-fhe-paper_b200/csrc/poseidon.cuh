@@ -456,8 +456,8 @@ __device__ __forceinline__ void partial_pair(u64 (&s)[WIDTH], int pair) {
   mds_pair::absorb<4>(acc, s, xl, xh);
   mds_pair::absorb<5>(acc, s, xl, xh);
   const u64 x1 = gl::canon(combine_biased(xl, xh));  // x'_0
-  const u64 u1 = gl::canon(sbox7(x1));               // sbox(x'_0)
-  const u64 delta = gl::sub(u1, x1);
+  const u64 u1 = sbox7(x1);                          // sbox(x'_0), any representative
+  const u64 delta = gl::sub_lazy(u1, x1);            // x1 canonical; the halves only feed linear terms
   // A = 8 u_0 + delta, and sbox(x'_0), as plain doubles per half
   const double al = fma(acc.x0l, 8.0, half_to_f64((u32)delta));
   const double ah = fma(acc.x0h, 8.0, half_to_f64((u32)(delta >> 32)));
