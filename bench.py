@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 LOG_N, NCOLS, RATE_BITS, CAP_HEIGHT = 16, 128, 3, 4
 METRIC = "LDE+Merkle commit rows/s (2^16-row x 128-col Goldilocks batch, rate_bits=3, cap_height=4)"
 UNIT = "trace rows/s"
+P_GL = 0xFFFFFFFF00000001
 # integer work per Poseidon permutation in 32x32->64 multiply-accumulates
 # (1,077 full modmuls x 4 + 2,304 + 44 small MACs), and the IMAD.WIDE issue rate it is held against.
 IMAD_PER_PERMUTATION = 6700
@@ -243,6 +244,90 @@ def run_multi_commit(args):
         flush=True)
 
 
+def run_fri_commit_phase(args):
+    """[P2] fri/prover.rs fri_committed_trees + fri_proof_of_work at the N=1024 step's size: the
+    final polynomial's LDE has 2^19 values in the quadratic extension; ConstantArityBits(4, 5) gives
+    arity-16 reduction layers (2^19 -> 2^15 -> 2^11 -> 2^7 values); every layer commits to the
+    bit-reversed, chunked values (Merkle tree, cap height 4) and folds with a challenge; then the
+    prover grinds a 16-bit proof of work.  The challenger (Fiat-Shamir) stays on the CPU, so every
+    layer is one host call with host buffers, exactly how a patched plonky2 would drive it."""
+    import numpy as np
+    import torch
+    import vfhe_b200 as V
+    from oracle import binding as orc
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the commit path has no CPU fallback")
+    V.build.build()
+    orc.build()
+    ctx = V.Context(0)
+    rng = np.random.default_rng(11)
+    log_len, arity_bits, cap_h = LOG_N + RATE_BITS, 4, CAP_HEIGHT
+    coeffs0 = rng.integers(0, P_GL, size=(1 << LOG_N, 2), dtype=np.uint64)
+    # LDE of the final polynomial: pad to 2^19 coefficients, coset FFT with shift 7
+    padded = np.zeros((1 << log_len, 2), np.uint64)
+    padded[: 1 << LOG_N] = coeffs0
+    values0 = np.stack([V.coset_fft(padded[:, 0].copy(), 7, ctx), V.coset_fft(padded[:, 1].copy(), 7, ctx)], 1)
+    betas = rng.integers(0, P_GL, size=(8, 2), dtype=np.uint64)
+    pow_state = rng.integers(0, P_GL, size=12, dtype=np.uint64)
+
+    def phase(layer_commit, fold, grind):
+        coeffs, values, shift, lg, caps, k = padded, values0, 7, log_len, [], 0
+        # [P2] fri/reduction_strategies.rs ConstantArityBits(4, 5): reduce while the degree exceeds
+        # 2^5 and the layer still has at least 2^cap_height leaves
+        while lg - RATE_BITS > 5 and lg - arity_bits >= cap_h:
+            caps.append(layer_commit(values, arity_bits, min(cap_h, lg - arity_bits)))
+            shift = pow(shift, 1 << arity_bits, P_GL)
+            coeffs, values = fold(coeffs, arity_bits, betas[k], shift)
+            lg -= arity_bits
+            k += 1
+        return caps, coeffs, grind(pow_state)
+
+    gpu = lambda: phase(lambda v, a, h: V.fri_layer_commit(v, a, h, ctx).cap,
+                        lambda c, a, b, sh: V.fri_fold(c, a, b, sh, ctx),
+                        lambda st: V.fri_proof_of_work(st, 5, 16, ctx=ctx))
+    sampler = ClockSampler(0)
+    for _ in range(3):
+        got = gpu()
+    sampler.start()
+    t0 = time.perf_counter()
+    reps = max(5, args.e2e_steps * 2)
+    for _ in range(reps):
+        got = gpu()
+    dt = (time.perf_counter() - t0) / reps
+    clocks = sampler.stop()
+
+    def cpu_grind(st):
+        s = st.copy()
+        for c in range(1 << 20):
+            s[5] = c
+            if int(orc.poseidon(s)[7]) >> 48 == 0:
+                return c
+        return None
+
+    t0 = time.perf_counter()
+    ref = phase(lambda v, a, h: orc.fri_layer_commit(v, a, h)["cap"],
+                lambda c, a, b, sh: orc.fri_fold(c, a, b, sh), lambda st: None)
+    cpu_dt = time.perf_counter() - t0
+    same = all(np.array_equal(a, b) for a, b in zip(got[0], ref[0])) and np.array_equal(got[1], ref[1])
+    w = got[2]
+    chk = pow_state.copy()
+    chk[5] = w if w is not None else 0
+    pow_ok = w is not None and int(orc.poseidon(chk)[7]) >> 48 == 0
+    print(json.dumps({
+        "metric": "FRI commit phase of one N=1024 step proof (stand-in): 3 arity-16 layers from 2^19 "
+                  "extension values (tree + fold each) + 16-bit proof-of-work grind, host C ABI",
+        "value": dt * 1e3, "unit": "ms per commit phase", "higher_is_better": False, "n_gpus": 1,
+        "steps": reps, "layers": len(got[0]), "final_poly_len": int(got[1].shape[0]) >> RATE_BITS,
+        "dtype": "u64", "data": "synthetic", "vs_baseline": None,
+        "cpu_baseline": {"value": cpu_dt * 1e3, "unit": "ms per commit phase (trees + folds, no grind)",
+                         "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                         "sample": "one full commit phase by oracle/liboracle.so (OpenMP)"},
+        "matches_oracle": bool(same), "pow_witness_valid": bool(pow_ok),
+        "gpu_launches": int(ctx.kernel_launches), "clocks": clocks,
+        "note": "the Fiat-Shamir challenger stays on the CPU: every layer is one host call (H2D of the "
+                "layer's values, D2H of leaves/digests/cap); SURVEY 8(f) row 1"}), flush=True)
+
+
 def workload_config(world):
     return {"workload": "configs[1]: standalone commit microbench, 2^16 rows x 128 Goldilocks columns, "
                         "rate_bits=3, Poseidon cap_height=4, from values, blinding off",
@@ -266,12 +351,19 @@ def main():
     ap.add_argument("--shard-commit", action="store_true",
                     help="strong scaling of ONE commit: every rank computes its row range "
                          "(vpbs_commit_shard_dev) and the subtree roots are all-gathered over NCCL")
+    ap.add_argument("--fri-commit-phase", action="store_true",
+                    help="SURVEY 8(f) row 1 stand-in: the FRI commit phase of one N=1024 step proof "
+                         "(2^19 extension values, arity-16 layers: tree + fold per layer, then the "
+                         "16-bit proof-of-work grind) through the host C ABI, beside the CPU port; "
+                         "prints its own line")
     ap.add_argument("--multi-commit", type=int, default=0, metavar="G",
                     help="single process (do not launch under torchrun): ONE commit spread over G "
                          "GPUs through vpbs_commit_multi with host buffers; prints its own line")
     args = ap.parse_args()
     if args.multi_commit:
         return run_multi_commit(args)
+    if args.fri_commit_phase:
+        return run_fri_commit_phase(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
