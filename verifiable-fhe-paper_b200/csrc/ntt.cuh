@@ -28,9 +28,6 @@ using gl::u64;
 constexpr int THREADS = 256;
 constexpr unsigned LOG_TILE = 12;  // 4096 elements (32 KB) per CTA
 constexpr unsigned MAX_PASS_BITS = 8;
-#ifndef VPBS_NTT_R16_MIN_BLOCKS
-#define VPBS_NTT_R16_MIN_BLOCKS 4  // 64 registers: 4 CTAs (32 warps) per SM to cover the load latency
-#endif
 
 struct Roots {
   const u64* w;    // w[t] = omega_N^t, t < N/2
@@ -216,149 +213,27 @@ __device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, 
 }
 #endif
 
-// 256-point DIF on a 256 x 16 tile held as 16 registers per thread.
-//  in : x[j] = element (q = 16 j + q_lo, lane), this thread's (q_lo, lane)
-//  out: x[j] = element (q = 16 q_hi + j, lane) after all 8 layers, this thread's (q_hi, lane);
-//       position q holds frequency bitrev8(q).
-// sm: 256 * pitch words; tw: 128 words, tw[e] = omega_256^(+-e).  The caller chooses the
-// (q_lo, lane) / (q_hi, lane) <-> threadIdx mappings (they differ between kernels for coalescing).
-__device__ __forceinline__ void dft256_regs(u64 (&x)[16], u64* sm, const u64* tw, unsigned pitch,
-                                            unsigned q_lo, unsigned lane_a, unsigned q_hi,
-                                            unsigned lane_b) {
-  // layers 0..3: q mod dd = (j mod ddj) * 16 + q_lo
-  dif16<true>(x, tw, 16, q_lo, 0);
-#pragma unroll
-  for (int j = 0; j < 16; j++) sm[(16 * j + q_lo) * pitch + lane_a] = x[j];
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 16; j++) x[j] = sm[(16 * q_hi + j) * pitch + lane_b];
-  // layers 4..7: q mod dd = j mod dd
-  dif16<false>(x, tw, 1, 0, 4);
-}
+// A 256-point DIF on a 256 x 16 tile is two of these with one exchange through shared memory in
+// between: layers 0..3 on x[j] = element (q = 16 j + q_lo, lane) with dif16<true>(x, tw, 16, q_lo, 0),
+// then layers 4..7 on x[j] = element (q = 16 q_hi + j, lane) with dif16<false>(x, tw, 1, 0, 4);
+// afterwards position q holds frequency bitrev8(q).  tw[e] = omega_256^(+-e), 128 words.
 
-// OUT_TW = false leaves out the four-step twiddle w_B^(low * brev(q)) at the store: the following
-// pass_final_r16 applies it at its load (in_tw_log_B), where one CTA needs only 256 distinct
-// twiddles shared by its 16 columns instead of 4096 scattered table reads per CTA here.
-// With OUT_TW = false the input scaling is split as well: in_scale[pos] = g^pos with
-// pos = q * 2^log_sigma + low factors into g^(q 2^log_sigma) * g^low, and g^low is constant along
-// the 256-point DFT (over q), so this pass applies only the 256 factors g^(q 2^log_sigma) (gathered
-// into shared memory once per CTA) and the next pass folds g^low into its twiddle table.  No
-// per-element scale loads from global memory remain (they were the largest stall of this kernel).
-template <bool INVERSE, bool OUT_TW = true>
-__global__ void __launch_bounds__(THREADS, VPBS_NTT_R16_MIN_BLOCKS)
-pass_strided_r16(const u64* __restrict__ src, u64 src_col_stride, u64* __restrict__ dst,
-                 u64 dst_col_stride, unsigned log_B, const u64* __restrict__ in_scale, Roots R) {
-  __shared__ u64 sm[256 * 16];
-  __shared__ u64 tw[128];
-  __shared__ u64 sq[OUT_TW ? 1 : 256];
-  const unsigned log_sigma = log_B - 8;
-  const unsigned tiles_per_block_log = log_sigma - 4;
-  const u64 blk = blockIdx.x >> tiles_per_block_log;
-  const u64 low0 = (u64)(blockIdx.x & ((1u << tiles_per_block_log) - 1)) << 4;
-  const u64 base = blk << log_B;
-  src += (u64)blockIdx.y * src_col_stride;
-  dst += (u64)blockIdx.y * dst_col_stride;
-  const unsigned t = threadIdx.x & 15, qa = threadIdx.x >> 4;  // (q_lo | q_hi, lane): lane fastest
-  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
-  if (!OUT_TW && in_scale) sq[threadIdx.x] = __ldg(in_scale + base + ((u64)threadIdx.x << log_sigma));
-  u64 x[16];
-#pragma unroll
-  for (int j = 0; j < 16; j++) {
-    const u64 pos = base + ((u64)(16 * j + qa) << log_sigma) + low0 + t;
-    x[j] = __ldg(src + pos);  // any representative: dif16 canonicalises what it must
-    if (OUT_TW && in_scale) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + pos));
-  }
-  __syncthreads();  // tw, sq ready
-  if (!OUT_TW && in_scale) {
-#pragma unroll
-    for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], sq[16 * j + qa]);
-  }
-  dft256_regs(x, sm, tw, 16, qa, t, qa, t);
-#pragma unroll
-  for (int j = 0; j < 16; j++) {
-    const unsigned q = 16 * qa + j;
-    const u64 pos = base + ((u64)q << log_sigma) + low0 + t;
-    // the work buffer holds arbitrary representatives; the next pass reduces them
-    if (OUT_TW) {
-      const u64 e = (low0 + t) * (u64)brev(q, 8);  // < 2^log_B
-      dst[pos] = e ? gl::mul_lazy(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
-    } else {
-      dst[pos] = x[j];
-    }
-  }
-}
+// Two refinements of the four-step scheme used when a 2^16-point transform is two 256-point passes
+// (template / run-time switches of the kernels below):
+//  * OUT_TW = false leaves out the four-step twiddle w_B^(low * brev(q)) at the first pass's store:
+//    the final pass applies it at its load (in_tw_log_B), where one CTA needs only 256 distinct
+//    twiddles shared by its 16 columns instead of 4096 scattered table reads per CTA;
+//  * the input scaling is split the same way: in_scale[pos] = g^pos with pos = q * 2^log_sigma + low
+//    factors into g^(q 2^log_sigma) * g^low, and g^low is constant along the 256-point DFT (over
+//    q), so the first pass applies only the 256 factors g^(q 2^log_sigma) (gathered into shared
+//    memory once per CTA) and the final pass folds g^low into its twiddle table (in_tw_scale).  No
+//    per-element scale loads from global memory remain (they were the largest stall).
+// (The first, non-persistent versions of these kernels — one tile per CTA, loads straight into
+// registers — are in the history; profiles/r1_ntt_r16_kernels_v1/v2.txt are their ncu captures.)
 
-template <bool INVERSE, int MODE>
-__global__ void __launch_bounds__(THREADS, VPBS_NTT_R16_MIN_BLOCKS)
-pass_final_r16(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
-               u64* __restrict__ dst, u64 dst_stride, u64 row0, unsigned log_n,
-               const u64* __restrict__ in_scale, u64 out_scale, Roots R,
-               unsigned in_tw_log_B = 0, const u64* __restrict__ in_tw_scale = nullptr) {
-  __shared__ u64 sm[256 * 17];
-  __shared__ u64 tw[128];
-  __shared__ u64 tws[256];
-  const unsigned log_nb = log_n - 8;
-  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
-  // STORE_LEAF after a pass_strided_r16<.., false> over blocks of 2^in_tw_log_B with 256-element
-  // sub-blocks: this CTA's 256 positions are (q = blockIdx.x mod 256, low = 0..255) and their
-  // pending twiddles w_B^(low * brev(q)) do not depend on the column.
-  const bool in_tw = MODE == STORE_LEAF && in_tw_log_B != 0;
-  if (in_tw) {  // ... times the g^low half of the previous pass's input scaling, if it left one
-    u64 w = root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev(blockIdx.x & 255u, 8));
-    if (in_tw_scale) w = gl::mul_lazy(w, __ldg(in_tw_scale + threadIdx.x));
-    tws[threadIdx.x] = w;
-  }
-  // load mapping: q_lo fastest (16 consecutive elements of one column / block per half warp)
-  const unsigned q_lo = threadIdx.x & 15, lane_a = threadIdx.x >> 4;
-  u64 x[16];
-  {
-    const u64* p = nullptr;
-    u64 pos0 = 0;
-    if (MODE == STORE_LEAF) {
-      const unsigned col = blockIdx.y * 16 + lane_a;
-      if (col < ncols) p = src + (u64)col * src_col_stride;
-      pos0 = (u64)blockIdx.x << 8;
-    } else {
-      p = src + (u64)blockIdx.y * src_col_stride;
-      pos0 = (u64)brev(blockIdx.x * 16 + lane_a, log_nb) << 8;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const u64 pos = pos0 + 16 * j + q_lo;
-      u64 v = 0;
-      if (p) {
-        v = __ldg(p + pos);
-        if (in_scale) v = gl::mul_lazy(v, __ldg(in_scale + pos));
-      }
-      x[j] = v;
-    }
-  }
-  __syncthreads();  // tw ready
-  if (in_tw) {
-#pragma unroll
-    for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], tws[16 * j + q_lo]);
-  }
-  // store mapping: lane fastest (16 consecutive columns of one row / 16 consecutive outputs)
-  const unsigned lane_b = threadIdx.x & 15, q_hi = threadIdx.x >> 4;
-  dft256_regs(x, sm, tw, 17, q_lo, lane_a, q_hi, lane_b);
-#pragma unroll
-  for (int j = 0; j < 16; j++) {
-    const unsigned q = 16 * q_hi + j;
-    u64 v = x[j];
-    v = (out_scale != 1) ? gl::mul(v, out_scale) : gl::canon(v);
-    if (MODE == STORE_LEAF) {
-      const unsigned col = blockIdx.y * 16 + lane_b;
-      const u64 pos = ((u64)blockIdx.x << 8) + q;
-      if (col < ncols) dst[(row0 + pos) * dst_stride + col] = v;
-    } else {
-      const u64 nat = ((u64)brev(q, 8) << log_nb) + (u64)blockIdx.x * 16 + lane_b;
-      dst[(u64)blockIdx.y * dst_stride + nat] = v;
-    }
-  }
-}
 
 // ---- persistent radix-16 passes with asynchronous tile prefetch ---------------------------------
-// ncu on the kernels above (profiles/r1_ntt_r16_kernels_v2.txt): issue slots 41-47 % busy, the
+// ncu on the one-tile-per-CTA versions (profiles/r1_ntt_r16_kernels_v2.txt): issue slots 41-47 % busy, the
 // largest stall by far is the global-load scoreboard — every CTA loads, then computes, then stores,
 // and with 4 CTAs per SM the load phases are not covered.  Here a CTA walks over tiles and the
 // NEXT tile's elements travel global -> shared with cp.async while the current tile is being

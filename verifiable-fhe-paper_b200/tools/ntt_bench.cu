@@ -1,9 +1,11 @@
 // ntt_bench.cu — standalone timing of the 2^16-row commit's transform kernels (developer tool for
 // kernel iterations; bench.py is the number of record): IFFT of C columns, then the 2^rate_bits
-// coset LDE blocks written as leaf rows, exactly the launch sequence of run_transform in
-// csrc/vpbs_commit.cu.  Prints the time of each phase and a checksum of coefficients and leaves so
-// that variants can be compared bit for bit.
+// coset LDE blocks written as leaf rows — the launch sequence of run_transform / commit_core in
+// csrc/vpbs_commit.cu (persistent passes, twiddle and scale split across the two passes, LDE blocks
+// alternating between two streams).  Prints the time of each phase and a checksum of coefficients
+// and leaves so that variants can be compared bit for bit.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../csrc -o ntt_bench ntt_bench.cu
+//   [-DNTT_BENCH_ONE_STREAM] [-DNTT_BENCH_CTAS_PER_SM=k]
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -12,6 +14,10 @@
 #include "ntt.cuh"
 
 using gl::u64;
+
+#ifndef NTT_BENCH_CTAS_PER_SM
+#define NTT_BENCH_CTAS_PER_SM 3
+#endif
 
 __global__ void fill(u64* p, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,13 +35,19 @@ __global__ void checksum(const u64* p, size_t n, u64* out) {
   atomicAdd((unsigned long long*)out, (unsigned long long)acc);
 }
 
+template <typename K>
+static void big_smem(K k, size_t bytes) {
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 int main(int argc, char** argv) {
   const unsigned C = argc > 1 ? atoi(argv[1]) : 128, log_n = 16, r = 3;
   const u64 n = 1ULL << log_n, m = n << r;
-  u64 *cols, *coeffs, *work, *leaves, *roots, *coset, *sum;
+  u64 *cols, *coeffs, *work, *work2, *leaves, *roots, *coset, *sum;
   cudaMalloc(&cols, C * n * 8);
   cudaMalloc(&coeffs, C * n * 8);
   cudaMalloc(&work, C * n * 8);
+  cudaMalloc(&work2, C * n * 8);
   cudaMalloc(&leaves, C * m * 8);
   cudaMalloc(&roots, (m / 2) * 8);
   cudaMalloc(&coset, m * 8);
@@ -46,72 +58,51 @@ int main(int argc, char** argv) {
   ntt::fill_coset_powers<<<(unsigned)((m + 255) / 256), 256>>>(coset, log_n, r, gl::COSET_SHIFT);
   const ntt::Roots R{roots, log_n + r};
   const u64 n_inv = gl::inv(n);
-  cudaEvent_t e[3];
+  big_smem(ntt::pass_strided_r16p<true, true>, ntt::R16P_STRIDED_SMEM);
+  big_smem(ntt::pass_strided_r16p<false, false>, ntt::R16P_STRIDED_SMEM);
+  big_smem(ntt::pass_final_r16p<true, ntt::STORE_NATURAL>, ntt::R16P_FINAL_SMEM);
+  big_smem(ntt::pass_final_r16p<false, ntt::STORE_LEAF>, ntt::R16P_FINAL_SMEM);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const unsigned cap = (unsigned)sms * NTT_BENCH_CTAS_PER_SM;
+  cudaEvent_t e[3], fork, join[2];
   for (auto& x : e) cudaEventCreate(&x);
-  cudaFuncSetAttribute(ntt::pass_strided_r16p<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)ntt::R16P_STRIDED_SMEM);
-  cudaFuncSetAttribute(ntt::pass_final_r16p<false, ntt::STORE_LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)ntt::R16P_FINAL_SMEM);
-  u64* work2;
-  cudaMalloc(&work2, C * n * 8);
   cudaStream_t st[2];
-  cudaEvent_t fork, join[2];
   for (auto& x : st) cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
   for (auto& x : join) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
-  (void)work2; (void)st; (void)fork; (void)join;
+  const unsigned tx1 = (unsigned)(n >> 12), nt1 = tx1 * C;                 // strided: 16 x C tiles
+  const unsigned txn = (unsigned)(n >> 12), ntn = txn * C;                 // final, natural store
+  const unsigned txl = (unsigned)(n >> 8), ntl = txl * ((C + 15) / 16);    // final, leaf store
+  auto grid = [&](unsigned nt) { return nt < cap ? nt : cap; };
   float best_i = 1e9f, best_f = 1e9f;
   for (int it = 0; it < 12; it++) {
     cudaEventRecord(e[0]);
-    {
-      dim3 g1((unsigned)(n >> 12), C), g2((unsigned)(n >> 12), C);
-      ntt::pass_strided_r16<true><<<g1, ntt::THREADS>>>(cols, n, work, n, log_n, nullptr, R);
-      ntt::pass_final_r16<true, ntt::STORE_NATURAL><<<g2, ntt::THREADS>>>(work, n, C, coeffs, n, 0, log_n,
-                                                                        nullptr, n_inv, R);
-    }
+    ntt::pass_strided_r16p<true, true><<<grid(nt1), ntt::THREADS, ntt::R16P_STRIDED_SMEM>>>(
+        cols, n, work, n, log_n, nullptr, R, tx1, nt1);
+    ntt::pass_final_r16p<true, ntt::STORE_NATURAL><<<grid(ntn), ntt::THREADS, ntt::R16P_FINAL_SMEM>>>(
+        work, n, C, coeffs, n, 0, log_n, nullptr, n_inv, R, 0u, nullptr, txn, ntn);
     cudaEventRecord(e[1]);
-#ifdef NTT_BENCH_TWO_STREAMS
-    // blocks alternate between two streams and two work buffers: the tail wave of one kernel
-    // (2048 CTAs = 3.46 waves of 592) is filled by the other stream's CTAs
     cudaEventRecord(fork, 0);
     cudaStreamWaitEvent(st[0], fork, 0);
     cudaStreamWaitEvent(st[1], fork, 0);
     for (u64 b = 0; b < (1u << r); b++) {
-      dim3 g1((unsigned)(n >> 12), C), g2((unsigned)(n >> 8), (C + 15) / 16);
+#ifdef NTT_BENCH_ONE_STREAM
+      cudaStream_t q = st[0];
+      u64* wk = work;
+#else
       cudaStream_t q = st[b & 1];
       u64* wk = (b & 1) ? work2 : work;
-#ifdef NTT_BENCH_PERSIST
-      const unsigned nt1 = g1.x * g1.y, nt2 = g2.x * g2.y, cap = 148 * NTT_BENCH_PERSIST;
-      ntt::pass_strided_r16p<false, false><<<nt1 < cap ? nt1 : cap, ntt::THREADS, ntt::R16P_STRIDED_SMEM, q>>>(
-          coeffs, n, wk, n, log_n, coset + (b << log_n), R, g1.x, nt1);
-      ntt::pass_final_r16p<false, ntt::STORE_LEAF><<<nt2 < cap ? nt2 : cap, ntt::THREADS, ntt::R16P_FINAL_SMEM, q>>>(
-          wk, n, C, leaves, C, b << log_n, log_n, nullptr, 1, R, log_n, coset + (b << log_n), g2.x, nt2);
-#else
-      ntt::pass_strided_r16<false, false><<<g1, ntt::THREADS, 0, q>>>(coeffs, n, wk, n, log_n,
-                                                                      coset + (b << log_n), R);
-      ntt::pass_final_r16<false, ntt::STORE_LEAF><<<g2, ntt::THREADS, 0, q>>>(wk, n, C, leaves, C, b << log_n,
-                                                                            log_n, nullptr, 1, R, log_n, coset + (b << log_n));
 #endif
+      ntt::pass_strided_r16p<false, false><<<grid(nt1), ntt::THREADS, ntt::R16P_STRIDED_SMEM, q>>>(
+          coeffs, n, wk, n, log_n, coset + (b << log_n), R, tx1, nt1);
+      ntt::pass_final_r16p<false, ntt::STORE_LEAF><<<grid(ntl), ntt::THREADS, ntt::R16P_FINAL_SMEM, q>>>(
+          wk, n, C, leaves, C, b << log_n, log_n, nullptr, 1, R, log_n, coset + (b << log_n), txl, ntl);
     }
     cudaEventRecord(join[0], st[0]);
     cudaEventRecord(join[1], st[1]);
     cudaStreamWaitEvent(0, join[0], 0);
     cudaStreamWaitEvent(0, join[1], 0);
-    if (0)
-#endif
-    for (u64 b = 0; b < (1u << r); b++) {
-      dim3 g1((unsigned)(n >> 12), C), g2((unsigned)(n >> 8), (C + 15) / 16);
-#ifdef NTT_BENCH_TW_AT_STORE
-      ntt::pass_strided_r16<false><<<g1, ntt::THREADS>>>(coeffs, n, work, n, log_n, coset + (b << log_n), R);
-      ntt::pass_final_r16<false, ntt::STORE_LEAF><<<g2, ntt::THREADS>>>(work, n, C, leaves, C, b << log_n,
-                                                                      log_n, nullptr, 1, R);
-#else
-      ntt::pass_strided_r16<false, false><<<g1, ntt::THREADS>>>(coeffs, n, work, n, log_n,
-                                                                coset + (b << log_n), R);
-      ntt::pass_final_r16<false, ntt::STORE_LEAF><<<g2, ntt::THREADS>>>(work, n, C, leaves, C, b << log_n,
-                                                                      log_n, nullptr, 1, R, log_n, coset + (b << log_n));
-#endif
-    }
     cudaEventRecord(e[2]);
     cudaEventSynchronize(e[2]);
     float a, b;
