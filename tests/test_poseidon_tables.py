@@ -106,16 +106,48 @@ def _sbox(x):
     return pow(x, 7, P)
 
 
-def _full_round(s, r):
-    s = [_sbox(x) for x in s]
-    zpl, zml, zph, zmh = _split_conv(s, RCS[24 * (r + 1):24 * (r + 2)], _cplus, _cminus)
+def _sbox_words(x, lift):
+    """sbox7_words: x^7 = x^3 * x^4 with the last 128-bit product left unreduced, returned as the
+    two "halves" (L, H) = (p0 - u - h1, s1 + u) the kernel's mds_absorb_words forms.  `lift` picks
+    non-canonical representatives of x^3 / x^4 where they fit in 64 bits (the kernel's are lazy)."""
+    x3, x4 = pow(x, 3, P), pow(x, 4, P)
+    if lift and x3 + P < 2**64:
+        x3 += P
+    if lift and x4 + P < 2**64:
+        x4 += P
+    prod = x3 * x4
+    p0, s1, u, h1 = [(prod >> (32 * k)) & M32 for k in range(4)]
+    L, H = p0 - u - h1, s1 + u
+    assert (L + (H << 32)) % P == pow(x, 7, P)
+    assert -2**33 < L < 2**32 and 0 <= H < 2**33
+    return L, H
+
+
+def _full_round(s, r, lift=False):
+    halves = [_sbox_words(x, lift) for x in s]   # (L, H) per lane, as the kernel feeds them
+    init = RCS[24 * (r + 1):24 * (r + 2)]
+    zpl = [init[4 * q + 0] for q in range(6)]
+    zml = [init[4 * q + 1] for q in range(6)]
+    zph = [init[4 * q + 2] for q in range(6)]
+    zmh = [init[4 * q + 3] for q in range(6)]
+    for t in range(6):
+        (al, ah), (bl, bh) = halves[t], halves[t + 6]
+        pl, ph, ml, mh = al + bl, ah + bh, al - bl, ah - bh
+        for q in range(6):
+            j = (t - q) % 6
+            c_p = _cplus(j)
+            c_m = _cminus(j) if j + q < 6 else -_cminus(j)
+            zpl[q] = _exact(zpl[q] + pl * c_p)
+            zph[q] = _exact(zph[q] + ph * c_p)
+            zml[q] = _exact(zml[q] + ml * c_m)
+            zmh[q] = _exact(zmh[q] + mh * c_m)
     out = [0] * 12
     for q in range(6):
         s1l, s1h = zpl[q] + zml[q], zph[q] + zmh[q]
         s2l, s2h = zpl[q] - zml[q], zph[q] - zmh[q]
         if q == 0:
-            s1l += 8 * (s[0] & M32)
-            s1h += 8 * (s[0] >> 32)
+            s1l += 8 * halves[0][0]
+            s1h += 8 * halves[0][1]
         out[q] = _combine(_exact(s1l), _exact(s1h))
         out[q + 6] = _combine(_exact(s2l), _exact(s2h))
     return out
@@ -156,11 +188,11 @@ def _partial_pair(s, pair):
     return out
 
 
-def permute_from_tables(state):
+def permute_from_tables(state, lift=False):
     s = [(x + RC[i]) % P for i, x in enumerate(state)]
     for half in range(2):
         for k in range(4):
-            s = _full_round(s, half * 26 + k)
+            s = _full_round(s, half * 26 + k, lift)
         if half == 0:
             for pair in range(11):
                 s = _partial_pair(s, pair)
@@ -180,7 +212,7 @@ def test_tables_are_what_the_generator_writes(tmp_path):
         row = rc[12 * r:12 * r + 12] if r < 30 else [0] * 12
         want = []
         for t in range(6):
-            want += gen.split_init(row[t], row[t + 6])
+            want += gen.split_init(row[t], row[t + 6], offset=True)
         assert RCS[24 * r:24 * r + 24] == want
     assert len(RCS) == 31 * 24 and len(RCP) == 11 * 24 and len(RCD) == 31 * 24
 
@@ -202,9 +234,10 @@ def test_table_driven_permutation_matches_oracle():
     inputs += [[rng.randrange(P) for _ in range(12)] for _ in range(12)]
     inputs += [[rng.choice([0, 1, P - 1, P - 2, 2**32 - 1, 2**32, 2**63]) for _ in range(12)] for _ in range(6)]
     for st in inputs:
-        got = permute_from_tables(st)
         want = [int(x) for x in orc.poseidon(np.array(st, dtype=np.uint64))]
-        assert [g % P for g in got] == want
+        for lift in (False, True):
+            got = permute_from_tables(st, lift)
+            assert [g % P for g in got] == want
     # and the published vectors themselves
     assert len(kat["vectors"]) >= 3
     for case in kat["vectors"]:

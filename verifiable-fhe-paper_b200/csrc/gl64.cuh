@@ -179,6 +179,37 @@ __host__ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
   return reduce128(lo, hi);
 #endif
 }
+// The 128-bit product only, as four 32-bit words (p0, s1, u, h1), without the reduction: for
+// consumers that are linear in the result (Poseidon's MDS layer takes
+// p0 - u - h1 + (s1 + u) 2^32 == a b (mod p) apart on the FP64 pipe, see poseidon.cuh).
+struct Words128 {
+  u32 p0, s1, u, h1;
+};
+__device__ __forceinline__ Words128 mul_words(u64 a, u64 b) {
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  Words128 w;
+  asm("{\n\t"
+      ".reg .u32 p1, x0, x1, y0, y1, z0, z1, t0, t1, t2;\n\t"
+      ".reg .u64 q;\n\t"
+      "mul.wide.u32 q, %4, %6;\n\t"
+      "mov.b64 {%0, p1}, q;\n\t"
+      "mul.wide.u32 q, %4, %7;\n\t"
+      "mov.b64 {x0, x1}, q;\n\t"
+      "mul.wide.u32 q, %5, %6;\n\t"
+      "mov.b64 {y0, y1}, q;\n\t"
+      "mul.wide.u32 q, %5, %7;\n\t"
+      "mov.b64 {z0, z1}, q;\n\t"
+      "add.cc.u32 t0, x0, y0;\n\t"
+      "addc.cc.u32 t1, x1, y1;\n\t"
+      "addc.u32 t2, z1, 0;\n\t"
+      "add.cc.u32 %1, t0, p1;\n\t"
+      "addc.cc.u32 %2, t1, z0;\n\t"
+      "addc.u32 %3, t2, 0;\n\t"
+      "}"
+      : "=r"(w.p0), "=r"(w.s1), "=r"(w.u), "=r"(w.h1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return w;
+}
 // a * a: the cross product a0 a1 is formed once (3 IMAD.WIDE.U32), (t0, t1, t2) = 2 x.
 __host__ __device__ __forceinline__ u64 sqr_lazy(u64 a) {
 #if defined(__CUDA_ARCH__) && !defined(VPBS_MUL_C)

@@ -41,6 +41,17 @@ __device__ __forceinline__ u64 sbox7(u64 x) {
   return gl::mul_lazy(x3, x4);
 }
 
+// x^7 with the last product left unreduced (four 32-bit words): its only consumer in a full round is
+// the linear layer, which takes the words apart on the FP64 pipe (mds_absorb_words) — the integer
+// reduction of that product (7 ALU-pipe instructions, the pipe that bounds the full rounds) is not
+// executed at all.
+__device__ __forceinline__ gl::Words128 sbox7_words(u64 x) {
+  u64 x2 = gl::sqr_lazy(x);
+  u64 x4 = gl::sqr_lazy(x2);
+  u64 x3 = gl::mul_lazy(x, x2);
+  return gl::mul_words(x3, x4);
+}
+
 // value = lo + 2^32 * hi with lo < 2^55, hi < 2^43  ->  arbitrary-u64 representative mod p.
 //   hi = hh * 2^32 + hl:  value = lo + hh * (2^32 - 1) + hl * 2^32   (2^64 = 2^32 - 1 mod p)
 __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
@@ -349,6 +360,25 @@ __device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
                        a.zml, a.zmh);
 #endif
 }
+// The same for two state words given as unreduced 128-bit products (p0, s1, u, h1):
+//   p0 + s1 2^32 + u 2^64 + h1 2^96 == L + H 2^32 (mod p),  L = p0 - u - h1,  H = s1 + u,
+// with L in (-2^33, 2^32) and H in [0, 2^33): the layer is linear, so (L, H) serve as the two
+// "halves" as they are.  Everything is formed from the biased views 2^52 + word (register pairs, no
+// arithmetic) with exact DADDs; Z+ starts 2^42 higher in its low half and 2^10 lower in its high
+// half (value-neutral, poseidon_rcs.inc) so that the low sums stay positive.
+template <int T>
+__device__ __forceinline__ void mds_absorb_words(MdsAcc& a, const gl::Words128& wa, const gl::Words128& wb) {
+  const double B52 = 4503599627370496.0, B53 = 9007199254740992.0;
+  const double al = (half_biased(wa.p0) - half_biased(wa.u)) - (half_biased(wa.h1) - B52);
+  const double ah = half_biased(wa.s1) + (half_biased(wa.u) - B53);
+  const double bl = (half_biased(wb.p0) - half_biased(wb.u)) - (half_biased(wb.h1) - B52);
+  const double bh = half_biased(wb.s1) + (half_biased(wb.u) - B53);
+  if constexpr (T == 0) {
+    a.x0l = al;
+    a.x0h = ah;
+  }
+  mds_split::col<T, 0>(al + bl, ah + bh, al - bl, ah - bh, a.zpl, a.zph, a.zml, a.zmh);
+}
 __device__ __forceinline__ void mds_finish(MdsAcc& a, u64 (&s)[WIDTH]) {
 #pragma unroll
   for (int r = 0; r < 6; r++) {
@@ -562,6 +592,26 @@ __device__ __forceinline__ void full_round(u64 (&s)[WIDTH], int r) {
   mds_absorb<4>(acc, s);
   VPBS_SBOX2(5, 11)
   mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+#elif defined(VPBS_MDS_INTERLEAVED) && !defined(VPBS_SBOX_REDUCED)
+  // S-boxes (integer pipes) and MDS accumulation (FP64 pipe) interleaved pair by pair; the last
+  // product of every S-box stays unreduced (sbox7_words / mds_absorb_words).
+  MdsAcc acc;
+  mds_begin(acc, r + 1);
+  {
+    const gl::Words128 a0 = sbox7_words(s[0]), b0 = sbox7_words(s[6]);
+    mds_absorb_words<0>(acc, a0, b0);
+    const gl::Words128 a1 = sbox7_words(s[1]), b1 = sbox7_words(s[7]);
+    mds_absorb_words<1>(acc, a1, b1);
+    const gl::Words128 a2 = sbox7_words(s[2]), b2 = sbox7_words(s[8]);
+    mds_absorb_words<2>(acc, a2, b2);
+    const gl::Words128 a3 = sbox7_words(s[3]), b3 = sbox7_words(s[9]);
+    mds_absorb_words<3>(acc, a3, b3);
+    const gl::Words128 a4 = sbox7_words(s[4]), b4 = sbox7_words(s[10]);
+    mds_absorb_words<4>(acc, a4, b4);
+    const gl::Words128 a5 = sbox7_words(s[5]), b5 = sbox7_words(s[11]);
+    mds_absorb_words<5>(acc, a5, b5);
+  }
   mds_finish(acc, s);
 #elif defined(VPBS_MDS_INTERLEAVED)
   // S-boxes (integer pipes) and MDS accumulation (FP64 pipe) interleaved pair by pair: as soon as
