@@ -85,18 +85,17 @@ __device__ __forceinline__ u64 reduce96(u64 lo, u64 hi) {
 __device__ __forceinline__ u64 combine_biased(double dlo, double dhi) {
   u32 r0, r1;
   asm("{\n\t"
-      ".reg .u32 l0, lh, h0, hh, h1, s1, m, c, kc;\n\t"
+      ".reg .u32 l0, lh, h0, hh, h1, s1, m, m2, kc;\n\t"
       "mov.b64 {l0, lh}, %2;\n\t"
       "mov.b64 {h0, hh}, %3;\n\t"
       "add.u32 h1, hh, 0xbcd00000;\n\t"      // hh - 0x43300000
       "add.u32 s1, lh, h1;\n\t"
       "add.u32 s1, s1, 0xbcd00000;\n\t"      // l1 + h1
-      "add.cc.u32 m, s1, h0;\n\t"
-      "addc.u32 c, 0, 0;\n\t"
-      "add.u32 kc, h1, c;\n\t"
-      "add.u32 m, m, c;\n\t"
+      "add.cc.u32 m, s1, h0;\n\t"            // carry c
+      "addc.u32 kc, h1, 0;\n\t"              // h1 + c   (addc without .cc leaves the flag alone:
+      "addc.u32 m2, m, 0;\n\t"               // m + c     both read the same carry; 6 SASS instructions)
       "sub.cc.u32 %0, l0, kc;\n\t"
-      "subc.u32 %1, m, 0;\n\t"
+      "subc.u32 %1, m2, 0;\n\t"
       "}"
       : "=r"(r0), "=r"(r1)
       : "d"(dlo), "d"(dhi));
