@@ -909,7 +909,14 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
     if (!cols[c]) return fail(ctx, VPBS_ERR_ARG, "cols[c] == NULL");
   // Wide batches are pipelined by column chunk: chunk k's inputs travel on the H2D stream while
   // chunk k-1 is already being transformed.
-  const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? 32 : 0;
+  // chunk width swept with tools/e2e_sweep.py (2^16 x 128, e2e ms): 8 -> 12.21, 16 -> 12.19,
+  // 32 -> 12.08, 64 -> 12.35
+  static const u32 host_chunk = [] {  // developer knob
+    const char* e = getenv("VPBS_HOST_CHUNK");
+    const int v = e ? atoi(e) : 32;
+    return (u32)(v < 4 ? 4 : v > 256 ? 256 : v);
+  }();
+  const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? host_chunk : 0;
   const u32 nchunks = chunk_cols ? (ncols + chunk_cols - 1) / chunk_cols : 0;
   const u64 nblocks = nleaves_shard >> log_n;
   while (ctx->ov.size() < nblocks + 2 * (u64)nchunks + 4) {
