@@ -103,9 +103,10 @@ __device__ __forceinline__ u64 combine_biased(double dlo, double dhi) {
 }
 
 // ---- MDS layer --------------------------------------------------------------------------------
-// Two implementations, selected at compile time: the FP64 form (default — fastest measured on
-// B200: 8.85 ms for 8.39 M permutations) and, with -DVPBS_MDS_INT32, a pure 32-bit integer form
-// (9.86 ms) kept as the documented alternative; both are bit-exact (tools/selftest.cu).
+// Three implementations, selected at compile time and all bit-exact (tools/selftest.cu): the
+// split-convolution FP64 form with pair-merged partial rounds (default: 5.32 ms for 8.39 M
+// permutations on B200), the dense FP64 form (-DVPBS_MDS_FP64_DENSE, 7.80 ms) and a pure 32-bit
+// integer form (-DVPBS_MDS_INT32, 8.21 ms), the last two with one linear layer per round.
 //
 // What the integer pipes cost here (tools/microbench.cu + ncu, profiles/): IMAD.WIDE.U32 runs at
 // half rate and ptxas never uses its 64-bit addend, so a 64-bit multiply-accumulate is
@@ -119,6 +120,17 @@ __device__ __forceinline__ u64 combine_biased(double dlo, double dhi) {
 //     on p_t = s_t + s_{t+6} and m_t = s_t - s_{t+6}:  2 y_r = Z+_r + Z-_r, 2 y_{r+6} = Z+_r - Z-_r
 //     (72 MACs per limb instead of 144; all arithmetic is exact mod 2^32, results < 2^32);
 //   * the doubled outputs are recombined and reduced once per lane (reduce96).
+// Round constants pre-split for the accumulators: RCD[2*(12*r+i)] = 2^52 + lo32(RC),
+// RCD[2*(12*r+i)+1] = 2^52 + hi32(RC) (exact doubles; row 30 is the all-zero "no next round").
+__constant__ double RCD[2 * (ROUNDS + 1) * WIDTH] = {
+#include "poseidon_rcd.inc"
+};
+// The same table in global memory for permute_coop, whose threads index it divergently (the
+// constant cache serialises distinct addresses within a warp; L1 does not).
+__device__ const double RCD_G[2 * (ROUNDS + 1) * WIDTH] = {
+#include "poseidon_rcd.inc"
+};
+
 #ifdef VPBS_MDS_INT32
 
 // {sum, difference} of the limbs of RC[r'], RC[r'+6]: [round][limb][r'][2]; row 30 = zeros.
@@ -203,17 +215,6 @@ __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
 __device__ __forceinline__ double half_to_f64(u32 x) {
   return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
 }
-// Round constants pre-split for the accumulators: RCD[2*(12*r+i)] = 2^52 + lo32(RC),
-// RCD[2*(12*r+i)+1] = 2^52 + hi32(RC) (exact doubles; row 30 is the all-zero "no next round").
-__constant__ double RCD[2 * (ROUNDS + 1) * WIDTH] = {
-#include "poseidon_rcd.inc"
-};
-// The same table in global memory for permute_coop, whose threads index it divergently (the
-// constant cache serialises distinct addresses within a warp; L1 does not).
-__device__ const double RCD_G[2 * (ROUNDS + 1) * WIDTH] = {
-#include "poseidon_rcd.inc"
-};
-
 #ifdef VPBS_MDS_FP64_DENSE
 // Input-stationary order: for each state word (converted to doubles on the fly) update all twelve
 // output accumulators.  Consecutive DFMAs then share their multiplicand, which the register reuse
