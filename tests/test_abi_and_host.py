@@ -133,3 +133,26 @@ def test_bench_help_runs():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"],
                          capture_output=True, text=True)
     assert out.returncode == 0 and "--impl" in out.stdout
+
+
+@pytest.mark.parametrize("flag", ["VPBS_MDS_INT32", "VPBS_MDS_FP64_DENSE", "VPBS_SBOX_REDUCED",
+                                  "VPBS_SBOX_OUTLINE", "VPBS_NO_PIPE_INTERLEAVE", "VPBS_MUL_C",
+                                  "VPBS_ADDSUB_C", "VPBS_HALF_I2F"])
+def test_documented_kernel_variants_still_compile(flag, tmp_path):
+    """DESIGN.md quotes measurements of alternative kernel forms that are kept in the source behind
+    compile-time switches; they have to keep building for sm_100a (their bit-exactness is what
+    tools/selftest.cu checks on a GPU)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "verifiable-fhe-paper_b200")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17",
+                        "-I", os.path.join(pkg, "csrc"), "-D" + flag, "-c", "-o", str(tmp_path / "v.o"),
+                        os.path.join(pkg, "tools", "selftest.cu")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
