@@ -432,6 +432,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    fail_checks = []  # every self-check of this run; any entry makes the process exit non-zero
     if args.shard_commit:
         return run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks, emit)
     if args.chain_steps:
@@ -502,11 +503,12 @@ def main():
     pcie = None
     if rank == 0:
         try:
-            nel = 32 << 20  # 256 MiB each way, from / to the pinned leaf buffer
-            flat = torch.from_numpy(h_leaves.view(np.int64).reshape(-1))
+            nel = 32 << 20  # 256 MiB each way, between its own pinned scratch and HBM
+            scratch, p_scratch = pinned((2 * nel,))
+            flat = torch.from_numpy(scratch.view(np.int64))
             h_a, h_b = flat[:nel], flat[nel:2 * nel]
-            d_a = torch.empty(nel, dtype=torch.int64, device=dev)
-            d_b = torch.empty(nel, dtype=torch.int64, device=dev)
+            d_a = torch.zeros(nel, dtype=torch.int64, device=dev)
+            d_b = torch.zeros(nel, dtype=torch.int64, device=dev)
             sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
             def timed(do_h2d, do_d2h):
@@ -530,10 +532,11 @@ def main():
                     "pinned": bool(h_a.is_pinned()),
                     "e2e_floor_ms": max(d2h_bytes / (gb / t_d * 1e9),
                                         (h2d_bytes + d2h_bytes) / (2 * gb / t_b * 1e9)) * 1e3,
-                    "note": "256 MiB copies between the pinned leaf buffer and HBM; e2e_floor_ms = the "
+                    "note": "256 MiB copies between a pinned scratch buffer and HBM; e2e_floor_ms = the "
                             "step's PCIe bytes at these rates (D2H alone, or all bytes at the "
                             "two-direction total, whichever is larger)"}
-            del d_a, d_b
+            del d_a, d_b, flat, h_a, h_b, scratch
+            lib.vpbs_host_free(p_scratch)
         except Exception as ex:  # informational only
             pcie = {"error": repr(ex)}
 

@@ -111,6 +111,13 @@ int vpbs_merkle_new(vpbs_ctx* ctx, const uint64_t* leaves_rowmajor, uint64_t nle
                     uint32_t leaf_len, uint32_t cap_height, uint64_t* digests_out,
                     uint64_t* cap_out);
 
+/* MerkleTree::new on device-resident leaves (nleaves x leaf_len row-major on the context's device);
+ * digests / cap stay on the device.  Asynchronous on the context's stream; stats forces a sync
+ * and reports leaf_hash_ms / merkle_ms. */
+int vpbs_merkle_new_dev(vpbs_ctx* ctx, const uint64_t* d_leaves, uint64_t nleaves, uint32_t leaf_len,
+                        uint32_t cap_height, uint64_t* d_digests_out, uint64_t* d_cap_out,
+                        vpbs_stats* stats);
+
 /* ---- [P2] plonky2/src/fri/oracle.rs PolynomialBatch::lde_values --------------------------------
  * cols: ncols pointers to n = 2^log_n elements each (a Vec<PolynomialValues<F>> is ncols separately
  * allocated Vec<F>).  inputs_are_coeffs = 0: values (ifft first, as from_values), 1: coefficients.
@@ -167,15 +174,19 @@ int vpbs_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint3
                     uint64_t* d_digests_out, uint64_t* d_cap_out, vpbs_stats* stats);
 
 /* Row-range shard of one commit for multi-GPU proving (SURVEY.md §8(e) partitioning B): computes
- * only leaves [first_leaf, first_leaf + nleaves_shard) of the m-leaf tree, where the shard is a
- * whole number of cap subtrees (or, if smaller than a cap subtree, a power-of-two aligned piece of
- * one) — already in leaf order — and the digests and subtree roots under it.
+ * only leaves [first_leaf, first_leaf + nleaves_shard) of the m-leaf tree — already in leaf order —
+ * and the digests and subtree roots under it.  A shard is a whole number of n-row LDE blocks
+ * (first_leaf and nleaves_shard multiples of n = 2^log_n); unless it is the whole tree it must also
+ * be a power of two, aligned to its own size, and cover whole cap subtrees
+ * (nleaves_shard >= m >> cap_height).  Anything else returns VPBS_ERR_ARG.
  *  d_cols            all ncols x n inputs (every shard needs every coefficient column)
+ *  d_coeffs_out      NULL or ncols x n; with inputs_are_coeffs = 1 it receives a plain copy of the
+ *                    inputs (not canonicalised)
  *  d_leaves_out      nleaves_shard x width
  *  d_digests_out     the plonky2-layout digests of the cap subtrees this shard owns
  *                    (2*(nleaves_shard - nroots) hashes)
- *  d_roots_out       nroots = max(1, nleaves_shard >> (log2 m - cap_height)) hashes: the cap
- *                    entries first_leaf >> (log2 m - cap_height) ... owned by this shard.
+ *  d_roots_out       nroots = nleaves_shard >> (log2 m - cap_height) hashes: the cap entries
+ *                    first_leaf >> (log2 m - cap_height) ... owned by this shard.
  * The only cross-GPU traffic of a sharded commit is the gather of d_roots_out (32 B per entry). */
 int vpbs_commit_shard_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
                           uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,

@@ -73,6 +73,8 @@ def lib() -> ctypes.CDLL:
         L.orc_fri_layer_commit.argtypes = [_u64p, u64, u32, u32, _u64p, _u64p, _u64p]
         L.orc_fri_fold.restype = None
         L.orc_fri_fold.argtypes = [_u64p, u64, u32, _u64p, u64, _u64p, _u64p]
+        L.orc_zs_partial_products.restype = ctypes.c_int
+        L.orc_zs_partial_products.argtypes = [_u64pp, _u64pp, _u64p, u32, u32, u32, u64, u64, _u64p]
         L.orc_set_threads.argtypes = [ctypes.c_int]
         L.orc_get_threads.restype = ctypes.c_int
         _lib = L
@@ -224,3 +226,21 @@ def fri_fold(coeffs_ext, arity_bits, beta, shift_next):
     co = np.empty((ol, 2), np.uint64); vo = np.empty((ol, 2), np.uint64)
     lib().orc_fri_fold(_p(c), ln, arity_bits, _p(_arr(beta)), int(shift_next), _p(co), _p(vo))
     return co, vo
+
+
+def zs_partial_products(wires, sigmas, k_is, max_degree, beta, gamma):
+    """[P2] plonk/prover.rs wires_permutation_partial_products_and_zs for one (beta, gamma).
+    wires, sigmas: (num_routed, n); returns (K, n) columns [Z, pp_0 .. pp_{K-2}]."""
+    w, s, k = _arr(wires), _arr(sigmas), _arr(k_is)
+    nr, n = w.shape
+    assert s.shape == w.shape and k.size == nr
+    K = -(-nr // max_degree)
+    out = np.zeros((K, n), np.uint64)
+    wp = (_u64p * nr)(*[_p(w[j]) for j in range(nr)])
+    sp = (_u64p * nr)(*[_p(s[j]) for j in range(nr)])
+    rc = lib().orc_zs_partial_products(wp, sp, _p(k), nr, _log2(n), max_degree, int(beta), int(gamma), _p(out))
+    if rc == -2:
+        raise ZeroDivisionError("a permutation denominator is zero (plonky2 panics here)")
+    if rc != 0:
+        raise ValueError("bad arguments")
+    return out

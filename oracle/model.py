@@ -261,3 +261,28 @@ def fri_fold(coeffs, arity_bits, beta, shift_next):
     re = coset_fft([c[0] for c in out], shift_next)
     im = coset_fft([c[1] for c in out], shift_next)
     return out, list(zip(re, im))
+
+
+# --------------------------------------------------------------------------- permutation argument
+def zs_partial_products(wires, sigmas, k_is, max_degree, beta, gamma):
+    """[P2] plonk/prover.rs wires_permutation_partial_products_and_zs for one (beta, gamma), from the
+    definitions: wires[j][i], sigmas[j][i] over the subgroup x_i = w_n^i.  Returns the columns in
+    commit order [Z, pp_0, .., pp_{K-2}] (K = ceil(num_routed / max_degree) chunks per row)."""
+    num_routed, n = len(wires), len(wires[0])
+    w = primitive_root_of_unity(n.bit_length() - 1)
+    K = -(-num_routed // max_degree)
+    cols = [[0] * n for _ in range(K)]
+    z = 1
+    for i in range(n):
+        x = pow(w, i, P)
+        cols[0][i] = z
+        acc = z
+        for k in range(K):
+            for j in range(k * max_degree, min((k + 1) * max_degree, num_routed)):
+                num = (wires[j][i] + beta * k_is[j] * x + gamma) % P
+                den = (wires[j][i] + beta * sigmas[j][i] + gamma) % P
+                acc = acc * num * pow(den, P - 2, P) % P
+            if k + 1 < K:
+                cols[1 + k][i] = acc
+        z = acc
+    return cols

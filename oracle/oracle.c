@@ -565,3 +565,58 @@ void orc_fri_fold(const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
   }
   free(tmp);
 }
+
+/* ---- [P2] plonk/prover.rs wires_permutation_partial_products_and_zs -------------------------- */
+int orc_zs_partial_products(const uint64_t* const* wires, const uint64_t* const* sigmas,
+                            const uint64_t* k_is, uint32_t num_routed, uint32_t log_n,
+                            uint32_t max_degree, uint64_t beta, uint64_t gamma, uint64_t* out) {
+  if (!wires || !sigmas || !k_is || !out || num_routed == 0 || max_degree < 2 || log_n > 30) return -1;
+  const uint64_t n = 1ULL << log_n;
+  const uint32_t K = (num_routed + max_degree - 1) / max_degree; /* chunks = partial products + 1 */
+  beta = canon(beta);
+  gamma = canon(gamma);
+  /* all_quotient_chunk_products[i][k] (par_iter over the subgroup upstream) */
+  uint64_t* chunks = malloc((size_t)n * K * sizeof(uint64_t));
+  uint64_t* subgroup = malloc((size_t)n * sizeof(uint64_t));
+  if (!chunks || !subgroup) {
+    free(chunks);
+    free(subgroup);
+    return -1;
+  }
+  const uint64_t w = orc_primitive_root_of_unity(log_n);
+  subgroup[0] = 1;
+  for (uint64_t i = 1; i < n; i++) subgroup[i] = mul_(subgroup[i - 1], w);
+  int zero_den = 0;
+#pragma omp parallel for schedule(static) num_threads(orc_get_threads()) reduction(| : zero_den)
+  for (uint64_t i = 0; i < n; i++) {
+    const uint64_t x = subgroup[i];
+    for (uint32_t k = 0; k < K; k++) {
+      uint64_t num = 1, den = 1;
+      for (uint32_t j = k * max_degree; j < (k + 1) * max_degree && j < num_routed; j++) {
+        const uint64_t wv = canon(wires[j][i]);
+        const uint64_t s_id = mul_(canon(k_is[j]), x);
+        num = mul_(num, add_(add_(wv, mul_(beta, s_id)), gamma));
+        den = mul_(den, add_(add_(wv, mul_(beta, canon(sigmas[j][i]))), gamma));
+      }
+      /* prod(num_j / den_j) = prod(num_j) / prod(den_j): field inverses are unique, so this equals
+       * upstream's batch_multiplicative_inverse + per-wire multiply bit for bit */
+      if (den == 0) zero_den |= 1;
+      chunks[i * K + k] = mul_(num, orc_gl_inv(den));
+    }
+  }
+  if (!zero_den) {
+    uint64_t z_x = 1; /* [P2] "let mut z_x = F::ONE" */
+    for (uint64_t i = 0; i < n; i++) {
+      uint64_t acc = z_x;
+      out[i] = z_x; /* the last partial product is Z(gx); Z(x) takes its place in the row */
+      for (uint32_t k = 0; k < K; k++) {
+        acc = mul_(acc, chunks[i * K + k]);
+        if (k + 1 < K) out[(uint64_t)(1 + k) * n + i] = acc;
+      }
+      z_x = acc;
+    }
+  }
+  free(chunks);
+  free(subgroup);
+  return zero_den ? -2 : 0;
+}

@@ -101,6 +101,22 @@ void orc_fri_fold(const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
                   const uint64_t beta[2], uint64_t shift_next, uint64_t* coeffs_out,
                   uint64_t* values_out);
 
+/* [P2] plonky2/src/plonk/prover.rs wires_permutation_partial_products_and_zs with
+ * util/partial_products.rs quotient_chunk_products / partial_products_and_z_gx, for ONE challenge
+ * pair (beta, gamma) — step 4 of prove() ("compute partial products"), reached from
+ * /root/reference/src/vtfhe/ivc_based_vpbs.rs:302,333,364:
+ *   row i (x_i = w_n^i):  q_j = (wire_j + beta k_j x_i + gamma) / (wire_j + beta sigma_j(x_i) + gamma)
+ *   chunk products c_k = prod of q_j over chunks of max_degree routed wires
+ *   Z(x_0) = 1,  pp_k(x_i) = Z(x_i) c_0 .. c_k,  Z(x_{i+1}) = Z(x_i) c_0 .. c_{K-1}
+ *  wires / sigmas: num_routed pointers to n = 2^log_n values each (wires[j][i] =
+ *  witness.get_wire(i, j), sigmas[j][i] = prover_data.sigmas[i][j]); k_is: num_routed coset shifts.
+ *  out: K = ceil(num_routed / max_degree) columns of n, column-major: out[0] = Z, out[1 + k] =
+ *  partial product k for k < K - 1 (the order prove() commits them in: Zs at the front).
+ * Returns 0, -1 on bad arguments, -2 if some denominator is zero (upstream panics there). */
+int orc_zs_partial_products(const uint64_t* const* wires, const uint64_t* const* sigmas,
+                            const uint64_t* k_is, uint32_t num_routed, uint32_t log_n,
+                            uint32_t max_degree, uint64_t beta, uint64_t gamma, uint64_t* out);
+
 /* Threads used by the parallel regions (mirrors rayon's pool). */
 void orc_set_threads(int n);
 int orc_get_threads(void);

@@ -56,6 +56,8 @@ SIGNATURES = {
     "vpbs_hash_or_noop_batch": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, u64p]),
     "vpbs_two_to_one_batch": (_c.c_int, [_ctx, u64p, u64p, _c.c_uint64, u64p]),
     "vpbs_merkle_new": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, _c.c_uint32, u64p, u64p]),
+    "vpbs_merkle_new_dev": (_c.c_int, [_ctx, _c.c_void_p, _c.c_uint64, _c.c_uint32, _c.c_uint32,
+                                       _c.c_void_p, _c.c_void_p, _c.POINTER(VpbsStats)]),
     "vpbs_lde_batch": (_c.c_int, [_ctx, u64pp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_int,
                                   u64pp, u64p]),
     "vpbs_commit": (_c.c_int, [_ctx, u64pp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32,

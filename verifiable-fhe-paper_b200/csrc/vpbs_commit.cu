@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -58,12 +59,16 @@ struct vpbs_ctx {
   // = 3.46 waves of 148 x 4, and the other stream's CTAs fill the tail wave (LDE 1.67 -> 1.46 ms).
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+
   unsigned sms = 148;  // persistent NTT passes launch sms * ntt::R16P_MIN_BLOCKS CTAs
   std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
   // Buffers of destroyed resident batches, kept for the next batch of the same shape (a prover
   // commits the same shapes every step; cudaMalloc/cudaFree of ~0.6 GB cost milliseconds).
   std::multimap<size_t, void*> pool;
   size_t pool_bytes = 0;
+  // Live resident batches of this context: vpbs_ctx_destroy frees their device buffers and orphans
+  // the handles (a batch outliving its context is then inert instead of a use-after-free).
+  std::set<struct vpbs_batch*> batches;
 };
 
 // A commit kept in HBM (vpbs_batch_*): owns its device buffers, reads go through the context.
@@ -289,36 +294,39 @@ int log2_strict(u64 n) {
   return l;
 }
 
-// MerkleTree::new over device leaves.  nleaves leaves of `width`, split into `nsub` subtrees whose
-// roots go to d_roots; digests in plonky2 layout per subtree.
-int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, unsigned log_sub,
-                 u64* d_digests, u64* d_roots, cudaEvent_t after_leaves = nullptr) {
+// MerkleTree::new over device leaves, in two steps so that callers can put them on different
+// streams.  nleaves leaves of `width`, split into subtrees of 2^log_sub leaves whose roots go to
+// d_roots; digests in plonky2 layout per subtree.
+constexpr unsigned COOP_LOG = 12;  // levels with <= 2^12 nodes: one 16-thread group per node
+constexpr unsigned FUSE_LOG = 4;   // <= 2^4 nodes per subtree: all remaining levels in one launch
+// (both thresholds swept on B200 in round 1: 2^12 nodes and 16 nodes per subtree are the minima)
+
+int merkle_leaves(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, unsigned log_sub,
+                  u64* d_digests, u64* d_roots, cudaStream_t st) {
+  if (nleaves == 0) return VPBS_OK;
+  const u64 sub_digests = 2 * (1ULL << log_sub) - 2;
+  const int all_cap = log_sub == 0;
+  merkle::hash_leaves<<<(unsigned)((nleaves + 127) / 128), 128, 0, st>>>(
+      d_leaves, nleaves, width, all_cap ? d_roots : d_digests, log_sub, sub_digests, all_cap);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  return VPBS_OK;
+}
+
+// Levels 1..log_sub above the leaf digests of nleaves >> log_sub subtrees.
+int merkle_levels(vpbs_ctx* ctx, u64 nleaves, unsigned log_sub, u64* d_digests, u64* d_roots,
+                  cudaStream_t st) {
+  if (nleaves == 0 || log_sub == 0) return VPBS_OK;
   const u64 sub_leaves = 1ULL << log_sub;
   const u64 nsub = nleaves >> log_sub;
   const u64 sub_digests = 2 * sub_leaves - 2;
-  const int all_cap = log_sub == 0;
-  if (nleaves == 0) return VPBS_OK;
-  merkle::hash_leaves<<<(unsigned)((nleaves + 127) / 128), 128, 0, ctx->stream>>>(
-      d_leaves, nleaves, width, all_cap ? d_roots : d_digests, log_sub, sub_digests, all_cap);
-  ctx->launches++;
-  if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
   // Big levels: one thread per node, one launch per level.  Levels with at most 4096 nodes in
   // total use one 16-thread group per node (lower latency); once a subtree is down to 16 nodes
   // the rest of the tree runs in ONE launch (one CTA per subtree, no launch gaps).
   unsigned total_log = 0;
   while ((1ULL << total_log) < nleaves) total_log++;
-  static const unsigned coop_log = [] {  // developer knob for threshold sweeps
-    const char* e = getenv("VPBS_COOP_LOG");
-    const int v = e ? atoi(e) : 12;
-    return (unsigned)(v < 4 ? 4 : v > 24 ? 24 : v);
-  }();
-  const unsigned coop_from = total_log > coop_log ? total_log - coop_log : 1;  // first level with <= 2^coop_log nodes
-  static const unsigned fuse_log = [] {  // developer knob for threshold sweeps
-    const char* e = getenv("VPBS_FUSE_LOG");
-    const int v = e ? atoi(e) : 4;
-    return (unsigned)(v < 1 ? 1 : v > 12 ? 12 : v);
-  }();
-  unsigned fused_from = log_sub > fuse_log ? log_sub - fuse_log : 1;  // <= 2^fuse_log nodes per subtree
+  const unsigned coop_from = total_log > COOP_LOG ? total_log - COOP_LOG : 1;  // first level with <= 2^COOP_LOG nodes
+  unsigned fused_from = log_sub > FUSE_LOG ? log_sub - FUSE_LOG : 1;  // <= 2^FUSE_LOG nodes per subtree
   if (fused_from < coop_from) fused_from = coop_from;
   const bool fuse = nsub <= 4096;
   for (unsigned level = 1; level <= log_sub; level++) {
@@ -328,21 +336,29 @@ int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, uns
       unsigned threads = (unsigned)(nodes0 * 16 < 32 ? 32 : nodes0 * 16);
       if (threads > merkle::COOP_THREADS) threads = merkle::COOP_THREADS;
       const size_t smem = (size_t)(threads / 16) * 48 * sizeof(double);
-      merkle::reduce_levels_coop<<<(unsigned)nsub, threads, smem, ctx->stream>>>(
-          d_digests, d_roots, level, log_sub, sub_digests);
+      merkle::reduce_levels_coop<<<(unsigned)nsub, threads, smem, st>>>(d_digests, d_roots, level,
+                                                                       log_sub, sub_digests);
       ctx->launches++;
       break;
     }
     if (level >= coop_from)
-      merkle::reduce_level_coop<<<(unsigned)((nnodes + 7) / 8), 128, 0, ctx->stream>>>(
+      merkle::reduce_level_coop<<<(unsigned)((nnodes + 7) / 8), 128, 0, st>>>(
           d_digests, d_roots, level, log_sub, sub_digests, nnodes);
     else
-      merkle::reduce_level<<<(unsigned)((nnodes + 127) / 128), 128, 0, ctx->stream>>>(
+      merkle::reduce_level<<<(unsigned)((nnodes + 127) / 128), 128, 0, st>>>(
           d_digests, d_roots, level, log_sub, sub_digests, nnodes);
     ctx->launches++;
   }
   CU(ctx, cudaGetLastError());
   return VPBS_OK;
+}
+
+int merkle_build(vpbs_ctx* ctx, const u64* d_leaves, u64 nleaves, u32 width, unsigned log_sub,
+                 u64* d_digests, u64* d_roots, cudaEvent_t after_leaves = nullptr) {
+  int rc = merkle_leaves(ctx, d_leaves, nleaves, width, log_sub, d_digests, d_roots, ctx->stream);
+  if (rc) return rc;
+  if (after_leaves) cudaEventRecord(after_leaves, ctx->stream);
+  return merkle_levels(ctx, nleaves, log_sub, d_digests, d_roots, ctx->stream);
 }
 
 // Points of the commit the host API hangs its overlapped output copies on.
@@ -453,7 +469,11 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   };
   for (u32 c0 = 0, k = 0; c0 < ncols; c0 += chunk, k++) {
     const u32 nc = ncols - c0 < chunk ? ncols - c0 : chunk;
-    if (chunked && k < ov->h2d_ready.size()) CU(ctx, cudaStreamWaitEvent(ctx->stream, ov->h2d_ready[k], 0));
+    if (chunked && k < ov->h2d_ready.size()) {
+      CU(ctx, cudaStreamWaitEvent(ctx->stream, ov->h2d_ready[k], 0));
+    } else if (!chunked && ov) {  // uploads on the H2D stream but a single compute chunk: wait for all
+      for (cudaEvent_t e : ov->h2d_ready) CU(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
+    }
     // "IFFT": values -> coefficients (natural order), scaled by n^-1.
     const u64* coeffs = d_cols + (u64)c0 * n;
     if (!inputs_are_coeffs) {
@@ -484,7 +504,11 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   }
   if (ov && ov->lde_done) cudaEventRecord(ov->lde_done, ctx->stream);
   tm->mark();  // 2
-  // "build Merkle tree"
+  // "build Merkle tree".  (Hashing every LDE block right after its transform, on the two LDE streams
+  // with the tree levels on a third, was built and measured in round 2: 8.30 ms against 7.03 ms for
+  // this phase-by-phase order at 2^16 x 128 — a 65,536-leaf launch is less than one wave of 128-thread
+  // CTAs, each of which lives ~1 ms (16 sequential permutations), so the per-block kernels fragment
+  // the machine)
   if ((rc = merkle_build(ctx, d_leaves, nleaves_shard, width, log_sub, d_digests, d_roots,
                          tm->on ? ctx->ev[8] : nullptr)) != VPBS_OK)
     return rc;
@@ -587,6 +611,7 @@ int vpbs_ctx_create(int device, vpbs_ctx** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming);
+
   for (int i = 0; e == cudaSuccess && i < 10; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e == cudaSuccess) {
     int sms = 0;
@@ -608,6 +633,15 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (vpbs_batch* b : ctx->batches) {  // orphan: the handle stays valid but holds nothing
+    cudaFree(b->coeffs);
+    cudaFree(b->leaves);
+    cudaFree(b->digests);
+    cudaFree(b->cap);
+    b->coeffs = b->leaves = b->digests = b->cap = nullptr;
+    b->ctx = nullptr;
+  }
+  ctx->batches.clear();
   for (auto& kv : ctx->arena)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : ctx->coset_tables) cudaFree(kv.second);
@@ -621,6 +655,7 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
   if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
+
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -775,6 +810,35 @@ int vpbs_merkle_new(vpbs_ctx* ctx, const uint64_t* leaves, uint64_t nleaves, uin
   return VPBS_OK;
 }
 
+int vpbs_merkle_new_dev(vpbs_ctx* ctx, const uint64_t* d_leaves, uint64_t nleaves, uint32_t leaf_len,
+                        uint32_t cap_height, uint64_t* d_digests_out, uint64_t* d_cap_out,
+                        vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  const int lg = log2_strict(nleaves);
+  if (lg < 0) return fail(ctx, VPBS_ERR_ARG, "leaves.len() must be a power of two");
+  if ((int)cap_height > lg)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  if (!d_cap_out || (leaf_len && !d_leaves)) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  if ((1ULL << cap_height) < nleaves && !d_digests_out)
+    return fail(ctx, VPBS_ERR_ARG, "digests buffer required");
+  const uint64_t l0 = ctx->launches;
+  if (stats) cudaEventRecord(ctx->ev[0], ctx->stream);
+  if ((rc = merkle_build(ctx, d_leaves, nleaves, leaf_len, (unsigned)lg - cap_height, d_digests_out,
+                         d_cap_out, stats ? ctx->ev[8] : nullptr)))
+    return rc;
+  if (stats) {
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(stats, 0, sizeof *stats);
+    cudaEventElapsedTime(&stats->leaf_hash_ms, ctx->ev[0], ctx->ev[8]);
+    cudaEventElapsedTime(&stats->merkle_ms, ctx->ev[0], ctx->ev[1]);
+    stats->total_ms = stats->merkle_ms;
+    stats->kernel_launches = ctx->launches - l0;
+  }
+  return VPBS_OK;
+}
+
 // ---- PolynomialBatch::lde_values -------------------------------------------------------------------
 int vpbs_lde_batch(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n,
                    uint32_t rate_bits, int inputs_are_coeffs, uint64_t* const* coeffs_out,
@@ -911,11 +975,7 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
   // chunk k-1 is already being transformed.
   // chunk width swept with tools/e2e_sweep.py (2^16 x 128, e2e ms): 8 -> 12.21, 16 -> 12.19,
   // 32 -> 12.08, 64 -> 12.35
-  static const u32 host_chunk = [] {  // developer knob
-    const char* e = getenv("VPBS_HOST_CHUNK");
-    const int v = e ? atoi(e) : 32;
-    return (u32)(v < 4 ? 4 : v > 256 ? 256 : v);
-  }();
+  constexpr u32 host_chunk = 32;
   const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? host_chunk : 0;
   const u32 nchunks = chunk_cols ? (ncols + chunk_cols - 1) / chunk_cols : 0;
   const u64 nblocks = nleaves_shard >> log_n;
@@ -1267,10 +1327,13 @@ int vpbs_pow_grind(vpbs_ctx* ctx, const uint64_t state[12], uint32_t witness_pos
 // ---- device-resident batches ---------------------------------------------------------------------------
 void vpbs_batch_destroy(vpbs_batch* b) {
   if (!b) return;
-  if (b->ctx) {
-    cudaSetDevice(b->ctx->device);
-    cudaStreamSynchronize(b->ctx->stream);
+  if (!b->ctx) {  // the context went first and already released the device buffers
+    delete b;
+    return;
   }
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  b->ctx->batches.erase(b);
   pool_free(b->ctx, b->coeffs, b->coeffs_bytes);
   pool_free(b->ctx, b->leaves, b->leaves_bytes);
   pool_free(b->ctx, b->digests, b->digests_bytes);
@@ -1387,6 +1450,7 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
     cudaEventElapsedTime(&stats->d2h_ms, e2, e3);
     cudaEventElapsedTime(&stats->total_ms, e0, e3);
   }
+  ctx->batches.insert(b);
   *out = b;
   return VPBS_OK;
 }

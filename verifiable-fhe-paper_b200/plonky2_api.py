@@ -68,6 +68,7 @@ class Context:
             raise VpbsError(rc, (self._L.vpbs_last_error(None) or b"").decode())
         self._h = h
         self.device = device
+        self._stream = 0  # 0 = the context's own stream
 
     def close(self):
         if getattr(self, "_h", None):
@@ -103,7 +104,14 @@ class Context:
         return self._L
 
     def set_stream(self, cuda_stream: int):
-        self.check(self._L.vpbs_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+        """Run this context's kernels on an existing CUDA stream (0 / None = its own stream)."""
+        self.check(self._L.vpbs_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+        self._stream = cuda_stream or 0
+
+    @property
+    def stream(self) -> int:
+        return self._stream
+
 
     def sync(self):
         self.check(self._L.vpbs_ctx_sync(self._h))

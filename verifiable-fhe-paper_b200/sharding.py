@@ -65,20 +65,38 @@ def commit_sharded(ctx, d_cols, ncols: int, log_n: int, rate_bits: int, cap_heig
                    inputs_are_coeffs: bool, rank: int, world: int, want_stats: bool = False):
     """One rank's part of a sharded commit on device tensors.  d_cols: torch int64 (ncols, n) on this
     rank's GPU holding ALL columns.  Returns (plan, leaves, digests, cap, coeffs, stats): leaves and
-    digests are this rank's shard, cap is the full gathered cap."""
+    digests are this rank's shard, cap is the full gathered cap.
+
+    Stream contract: the kernels run on torch's CURRENT stream of d_cols' device (the context is
+    switched to it for the call and switched back afterwards), so they are ordered after whatever
+    produced d_cols and before the NCCL all_gather of the roots, which torch enqueues on / orders
+    against that same stream.  If torch's current stream is the legacy default stream (handle 0,
+    which the context cannot adopt), the call synchronises explicitly on both sides instead."""
     import torch
     from .plonky2_api import commit_shard_device
     plan = shard_plan(log_n, rate_bits, cap_height, rank, world)
     dev = d_cols.device
     n = 1 << log_n
+    cur = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
+    prev = ctx.stream
+    if cur:
+        ctx.set_stream(cur)
+    else:
+        torch.cuda.current_stream(dev).synchronize()  # d_cols is final before our own stream reads it
     coeffs = torch.empty((ncols, n), dtype=torch.int64, device=dev)
     leaves = torch.empty((plan.nleaves, ncols), dtype=torch.int64, device=dev)
     digests = torch.empty((max(plan.ndigests, 1), 4), dtype=torch.int64, device=dev)
     roots = torch.empty((plan.ncap, 4), dtype=torch.int64, device=dev)
-    stats = commit_shard_device(ctx, d_cols.data_ptr(), ncols, log_n, rate_bits, cap_height,
-                                inputs_are_coeffs, plan.first_leaf, plan.nleaves,
-                                coeffs.data_ptr(), leaves.data_ptr(),
-                                digests.data_ptr() if plan.ndigests else 0, roots.data_ptr(),
-                                want_stats=want_stats)
+    try:
+        stats = commit_shard_device(ctx, d_cols.data_ptr(), ncols, log_n, rate_bits, cap_height,
+                                    inputs_are_coeffs, plan.first_leaf, plan.nleaves,
+                                    coeffs.data_ptr(), leaves.data_ptr(),
+                                    digests.data_ptr() if plan.ndigests else 0, roots.data_ptr(),
+                                    want_stats=want_stats)
+        if not cur:
+            ctx.sync()  # own stream: the roots are final before NCCL reads them
+    finally:
+        if cur:
+            ctx.set_stream(prev)
     cap = gather_cap(roots, world)
     return plan, leaves, digests[:plan.ndigests], cap, coeffs, stats

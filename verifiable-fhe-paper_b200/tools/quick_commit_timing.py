@@ -3,7 +3,7 @@ sys.path.insert(0, '.')
 import numpy as np, torch
 import vfhe_b200 as V
 ctx = V.Context(0)
-for (C, lg) in ((128, 16), (135, 16), (20, 16), (135, 13)):
+for (C, lg) in ((128, 16), (135, 16), (20, 16), (16, 16), (85, 16), (135, 13)):
     n = 1 << lg; m = n << 3
     cols = torch.from_numpy(V.synthetic_columns(C, n).view(np.int64)).cuda()
     coeffs = torch.empty((C, n), dtype=torch.int64, device='cuda')
