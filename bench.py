@@ -242,6 +242,8 @@ def run_multi_commit(args):
                 "slowest_device_phase_ms": st.as_dict()},
         "matches_single_gpu_commit": same, "gpu_launches": int(st.kernel_launches), "clocks": clocks}),
         flush=True)
+    if not same:
+        sys.exit(3)
 
 
 def run_fri_commit_phase(args):
@@ -285,16 +287,39 @@ def run_fri_commit_phase(args):
     gpu = lambda: phase(lambda v, a, h: V.fri_layer_commit(v, a, h, ctx).cap,
                         lambda c, a, b, sh: V.fri_fold(c, a, b, sh, ctx),
                         lambda st: V.fri_proof_of_work(st, 5, 16, ctx=ctx))
+
+    def chain():
+        """the same phase as ONE device-resident chain (vpbs_fri_*): coefficients up once, per layer
+        only the cap comes back and beta goes down; final polynomial + PoW witness at the end"""
+        fri = V.FriCommitPhase(coeffs0, RATE_BITS, ctx)
+        lg, caps, k = log_len, [], 0
+        while lg - RATE_BITS > 5 and lg - arity_bits >= cap_h:
+            caps.append(fri.commit_layer(arity_bits, min(cap_h, lg - arity_bits)))
+            fri.fold(betas[k])
+            lg -= arity_bits
+            k += 1
+        final = fri.final_poly()
+        w = V.fri_proof_of_work(pow_state, 5, 16, ctx=ctx)
+        fri.close()
+        return caps, final, w
+
     sampler = ClockSampler(0)
     for _ in range(3):
         got = gpu()
-    sampler.start()
-    t0 = time.perf_counter()
+        got_chain = chain()
     reps = max(5, args.e2e_steps * 2)
+    t0 = time.perf_counter()
     for _ in range(reps):
         got = gpu()
     dt = (time.perf_counter() - t0) / reps
+    launches0 = ctx.kernel_launches
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        got_chain = chain()
+    dt_chain = (time.perf_counter() - t0) / reps
     clocks = sampler.stop()
+    chain_launches = (ctx.kernel_launches - launches0) // reps
 
     def cpu_grind(st):
         s = st.copy()
@@ -309,23 +334,36 @@ def run_fri_commit_phase(args):
                 lambda c, a, b, sh: orc.fri_fold(c, a, b, sh), lambda st: None)
     cpu_dt = time.perf_counter() - t0
     same = all(np.array_equal(a, b) for a, b in zip(got[0], ref[0])) and np.array_equal(got[1], ref[1])
-    w = got[2]
+    final_ref = ref[1][: ref[1].shape[0] >> RATE_BITS]
+    same_chain = (len(got_chain[0]) == len(ref[0]) and
+                  all(np.array_equal(a, b) for a, b in zip(got_chain[0], ref[0])) and
+                  np.array_equal(got_chain[1], final_ref))
+    w = got_chain[2]
     chk = pow_state.copy()
     chk[5] = w if w is not None else 0
-    pow_ok = w is not None and int(orc.poseidon(chk)[7]) >> 48 == 0
+    pow_ok = w is not None and int(orc.poseidon(chk)[7]) >> 48 == 0 and w == got[2]
+    nl = len(ref[0])
+    pcie_chain = 16 * (1 << LOG_N) + nl * (32 * (1 << cap_h) + 16) + 16 * final_ref.shape[0] + 13 * 8 + 8
     print(json.dumps({
-        "metric": "FRI commit phase of one N=1024 step proof (stand-in): 3 arity-16 layers from 2^19 "
-                  "extension values (tree + fold each) + 16-bit proof-of-work grind, host C ABI",
-        "value": dt * 1e3, "unit": "ms per commit phase", "higher_is_better": False, "n_gpus": 1,
-        "steps": reps, "layers": len(got[0]), "final_poly_len": int(got[1].shape[0]) >> RATE_BITS,
+        "metric": "FRI commit phase of one N=1024 step proof (stand-in): final-polynomial LDE (2^16 -> 2^19 "
+                  "extension values), 3 arity-16 layers (tree + fold each), final polynomial, 16-bit "
+                  "proof-of-work grind; device-resident chain through the host C ABI (vpbs_fri_*)",
+        "value": dt_chain * 1e3, "unit": "ms per commit phase", "higher_is_better": False, "n_gpus": 1,
+        "steps": reps, "layers": nl, "final_poly_len": int(final_ref.shape[0]),
         "dtype": "u64", "data": "synthetic", "vs_baseline": None,
-        "cpu_baseline": {"value": cpu_dt * 1e3, "unit": "ms per commit phase (trees + folds, no grind)",
+        "pcie_bytes_per_phase": pcie_chain,
+        "per_layer_host_calls_ms": dt * 1e3,
+        "per_layer_host_calls_note": "round-1 form (vpbs_fri_layer_commit + vpbs_fri_fold per layer: values "
+                                     "up, leaves/digests/cap and folded vectors down), without the initial LDE",
+        "cpu_baseline": {"value": cpu_dt * 1e3, "unit": "ms per commit phase (trees + folds, no LDE, no grind)",
                          "cores": len(os.sched_getaffinity(0)), "kind": "port",
                          "sample": "one full commit phase by oracle/liboracle.so (OpenMP)"},
-        "matches_oracle": bool(same), "pow_witness_valid": bool(pow_ok),
-        "gpu_launches": int(ctx.kernel_launches), "clocks": clocks,
-        "note": "the Fiat-Shamir challenger stays on the CPU: every layer is one host call (H2D of the "
-                "layer's values, D2H of leaves/digests/cap); SURVEY 8(f) row 1"}), flush=True)
+        "matches_oracle": bool(same and same_chain), "pow_witness_valid": bool(pow_ok),
+        "gpu_launches": int(chain_launches), "clocks": clocks,
+        "note": "the Fiat-Shamir challenger stays on the CPU: per layer the cap comes back and beta goes "
+                "down, nothing else crosses PCIe; SURVEY 8(f) row 1"}), flush=True)
+    if not (same and same_chain and pow_ok):
+        sys.exit(3)
 
 
 def workload_config(world):
@@ -433,8 +471,15 @@ def main():
         return float(t.item())
 
     fail_checks = []  # every self-check of this run; any entry makes the process exit non-zero
+    checks_passed = [0]
+
+    def check(name, ok):
+        if ok:
+            checks_passed[0] += 1
+        else:
+            fail_checks.append(name)
     if args.shard_commit:
-        return run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks, emit)
+        return run_shard_commit(args, V, ctx, rank, world, dev, barrier, max_over_ranks, emit)
     if args.chain_steps:
         return run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit)
 
@@ -458,53 +503,125 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = world * args.steps * n / (elapsed_ms * 1e-3)
 
-    # ---- end to end through the host C ABI: pinned host buffers, H2D + D2H inside the timed region
+    # ---- end to end through the host C ABI (host buffers in, H2D + D2H inside the timed region)
     lib = ctx.lib
+    u64p = V._lib.u64p
+    pinned_ptrs = []
 
     def pinned(shape):
         nbytes = int(np.prod(shape)) * 8
         p = lib.vpbs_host_alloc(nbytes)
         if not p:
             raise SystemExit("vpbs_host_alloc failed")
+        pinned_ptrs.append(p)
         buf = (ctypes.c_uint64 * (nbytes // 8)).from_address(p)
-        return np.ctypeslib.as_array(buf).reshape(shape), p
+        return np.ctypeslib.as_array(buf).reshape(shape)
 
-    h_cols, p0 = pinned((NCOLS, n))
+    def colptrs(a):
+        return (u64p * a.shape[0])(*[a[c].ctypes.data_as(u64p) for c in range(a.shape[0])])
+
+    def timed_host_loop(fn, steps):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return dt / steps
+
+    h_cols = pinned((NCOLS, n))
     h_cols[:] = host_cols
-    h_coeffs, p1 = pinned((NCOLS, n))
-    h_leaves, p2 = pinned((m, NCOLS))
-    h_digests, p3 = pinned((2 * (m - ncap), 4))
-    h_cap, p4 = pinned((ncap, 4))
-    u64p = V._lib.u64p
-    colp = (u64p * NCOLS)(*[h_cols[c].ctypes.data_as(u64p) for c in range(NCOLS)])
-    cop = (u64p * NCOLS)(*[h_coeffs[c].ctypes.data_as(u64p) for c in range(NCOLS)])
+    colp = colptrs(h_cols)
+    h2d_bytes = 8 * NCOLS * n
+    nlayers = LOG_N + RATE_BITS - CAP_HEIGHT
+
+    # (1) e2e — the product path: PolynomialBatch::from_values with the batch left in HBM
+    # (vpbs_batch_*).  Per step: H2D of the 128 value columns, the commit, D2H of the cap (the
+    # commitment), the openings of all 128 polynomials at two extension points (OpeningSet: zeta,
+    # g * zeta) and the 28 FRI-query rows + Merkle paths — everything a proof takes from a batch whose
+    # LDE consumers run on the device.
+    query_idx = np.random.default_rng(7).integers(0, m, size=28, dtype=np.uint64)
+    zeta = np.random.default_rng(8).integers(0, P_GL, size=(2, 2), dtype=np.uint64)
+    res_cap = np.empty((ncap, 4), np.uint64)
+    res_rows = np.empty((28, NCOLS), np.uint64)
+    res_sib = np.empty((28, nlayers, 4), np.uint64)
+    res_open = np.empty((2, NCOLS, 2), np.uint64)
+
+    def resident_step():
+        h = ctypes.c_void_p()
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, colp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None,
+                                        res_cap.ctypes.data_as(u64p), ctypes.byref(h), None))
+        ctx.check(lib.vpbs_batch_eval_ext2(h, zeta.ctypes.data_as(u64p), 2, res_open.ctypes.data_as(u64p)))
+        ctx.check(lib.vpbs_batch_get_leaves(h, query_idx.ctypes.data_as(u64p), 28,
+                                            res_rows.ctypes.data_as(u64p)))
+        ctx.check(lib.vpbs_batch_prove(h, query_idx.ctypes.data_as(u64p), 28,
+                                       res_sib.ctypes.data_as(u64p)))
+        lib.vpbs_batch_destroy(h)
+
+    res_s = timed_host_loop(resident_step, args.e2e_steps)
+    res_d2h = 32 * ncap + 2 * NCOLS * 16 + 28 * (8 * NCOLS + 32 * nlayers)
+
+    # (2) e2e_eager — the same commit with EVERY output copied to pinned host memory before the call
+    # returns (coefficients, the 512 MiB leaf matrix, digests, cap): what plonky2's stock
+    # PolynomialBatch holds, needed only while the LDE's consumers still run on the CPU
+    h_coeffs, h_leaves = pinned((NCOLS, n)), pinned((m, NCOLS))
+    h_digests, h_cap = pinned((2 * (m - ncap), 4)), pinned((ncap, 4))
+    cop = colptrs(h_coeffs)
     e2e_stats = V.VpbsStats()
 
-    def e2e_step():
+    def eager_step():
         ctx.check(lib.vpbs_commit(ctx.handle, colp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None, cop,
                                   h_leaves.ctypes.data_as(u64p), h_digests.ctypes.data_as(u64p),
                                   h_cap.ctypes.data_as(u64p), ctypes.byref(e2e_stats)))
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = world * args.e2e_steps * n / e2e_s
-    h2d_bytes = 8 * NCOLS * n
-    d2h_bytes = 8 * NCOLS * n + 8 * m * NCOLS + 32 * 2 * (m - ncap) + 32 * ncap
-    cap_matches = bool(np.array_equal(h_cap.view(np.int64), d_cap.cpu().numpy()))
+    eager_s = timed_host_loop(eager_step, args.e2e_steps)
+    eager_d2h = 8 * NCOLS * n + 8 * m * NCOLS + 32 * 2 * (m - ncap) + 32 * ncap
+    check("e2e_eager.cap_matches_device_path", np.array_equal(h_cap.view(np.int64), d_cap.cpu().numpy()))
+    check("e2e.cap_matches_eager_path", np.array_equal(res_cap, h_cap))
+    check("e2e.opened_rows_match_eager_leaves", np.array_equal(res_rows, h_leaves[query_idx]))
+    # Merkle paths of the resident batch against the eager digests (plonky2's prove() index formula)
+    eager_tree = V.MerkleTree(h_leaves, h_digests, h_cap)
+    check("e2e.merkle_paths_match_eager_digests",
+          all(np.array_equal(res_sib[k], eager_tree.prove(int(i)).siblings) for k, i in enumerate(query_idx)))
 
-    # ---- what the host link of this box can do (explains e2e): H2D alone, D2H alone, both at once
+    # (3) e2e_pageable — the eager call with ordinary (pageable) host buffers, as a caller that
+    # passes plain Vec<F> memory sees it (rank 0 only: informational)
+    pageable = None
+    if rank == 0:
+        g_cols = host_cols.copy()
+        g_coeffs, g_leaves = np.empty((NCOLS, n), np.uint64), np.empty((m, NCOLS), np.uint64)
+        g_digests, g_cap = np.empty((2 * (m - ncap), 4), np.uint64), np.empty((ncap, 4), np.uint64)
+        gcolp, gcop = colptrs(g_cols), colptrs(g_coeffs)
+
+        def pageable_step():
+            ctx.check(lib.vpbs_commit(ctx.handle, gcolp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None, gcop,
+                                      g_leaves.ctypes.data_as(u64p), g_digests.ctypes.data_as(u64p),
+                                      g_cap.ctypes.data_as(u64p), None))
+
+        for _ in range(2):
+            pageable_step()
+        t0 = time.perf_counter()
+        for _ in range(max(2, args.e2e_steps // 2)):
+            pageable_step()
+        pg_s = (time.perf_counter() - t0) / max(2, args.e2e_steps // 2)
+        check("e2e_pageable.outputs_match_pinned_path",
+              np.array_equal(g_cap, h_cap) and np.array_equal(g_leaves[::4099], h_leaves[::4099])
+              and np.array_equal(g_digests, h_digests))
+        pageable = {"value": n / pg_s, "unit": UNIT, "ms_per_step": pg_s * 1e3,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": eager_d2h,
+                    "api": "vpbs_commit, pageable host buffers (numpy.empty): the driver stages every "
+                           "copy through its own pinned bounce buffers and nothing overlaps"}
+        del g_cols, g_coeffs, g_leaves, g_digests
+
+    # (4) what the host link of this box can do (explains e2e_eager): H2D alone, D2H alone, both
     pcie = None
     if rank == 0:
         try:
             nel = 32 << 20  # 256 MiB each way, between its own pinned scratch and HBM
-            scratch, p_scratch = pinned((2 * nel,))
+            scratch = pinned((2 * nel,))
             flat = torch.from_numpy(scratch.view(np.int64))
             h_a, h_b = flat[:nel], flat[nel:2 * nel]
             d_a = torch.zeros(nel, dtype=torch.int64, device=dev)
@@ -530,69 +647,55 @@ def main():
             t_b = min(timed(True, True) for _ in range(3))
             pcie = {"h2d_gbs": gb / t_h, "d2h_gbs": gb / t_d, "both_directions_total_gbs": 2 * gb / t_b,
                     "pinned": bool(h_a.is_pinned()),
-                    "e2e_floor_ms": max(d2h_bytes / (gb / t_d * 1e9),
-                                        (h2d_bytes + d2h_bytes) / (2 * gb / t_b * 1e9)) * 1e3,
-                    "note": "256 MiB copies between a pinned scratch buffer and HBM; e2e_floor_ms = the "
-                            "step's PCIe bytes at these rates (D2H alone, or all bytes at the "
-                            "two-direction total, whichever is larger)"}
+                    "e2e_eager_floor_ms": max(eager_d2h / (gb / t_d * 1e9),
+                                              (h2d_bytes + eager_d2h) / (2 * gb / t_b * 1e9)) * 1e3,
+                    "e2e_floor_ms": h2d_bytes / (gb / t_h * 1e9) * 1e3,
+                    "note": "256 MiB copies between a pinned scratch buffer and HBM; *_floor_ms = the "
+                            "step's PCIe bytes at these rates"}
             del d_a, d_b, flat, h_a, h_b, scratch
-            lib.vpbs_host_free(p_scratch)
         except Exception as ex:  # informational only
             pcie = {"error": repr(ex)}
 
-    # ---- the same call with the batch left in HBM (vpbs_batch_*): only the cap crosses PCIe at
-    # commit time; the 28 FRI-query rows + Merkle paths of a proof are fetched on demand
-    query_idx = np.random.default_rng(7).integers(0, m, size=28, dtype=np.uint64)
-    res_cap = np.empty((ncap, 4), np.uint64)
-    res_rows = np.empty((28, NCOLS), np.uint64)
-    res_sib = np.empty((28, LOG_N + RATE_BITS - CAP_HEIGHT, 4), np.uint64)
-
-    def resident_step():
+    # (5) lazy LDE pull: what a CPU quotient (compute_quotient_polys) costs on top of `e2e` while it
+    # still runs on the host — every LDE row of a resident batch fetched in 2^16-row blocks
+    lde_pull = None
+    if rank == 0:
         h = ctypes.c_void_p()
         ctx.check(lib.vpbs_batch_commit(ctx.handle, colp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None,
                                         res_cap.ctypes.data_as(u64p), ctypes.byref(h), None))
-        ctx.check(lib.vpbs_batch_get_leaves(h, query_idx.ctypes.data_as(u64p), 28,
-                                            res_rows.ctypes.data_as(u64p)))
-        ctx.check(lib.vpbs_batch_prove(h, query_idx.ctypes.data_as(u64p), 28,
-                                       res_sib.ctypes.data_as(u64p)))
+        blk = 1 << 16
+        probe = [0, 1, 12345, m - 1]  # natural LDE row i = leaf reverse_bits(i) of the eager matrix
+        expect = [h_leaves[V.reverse_bits(i, LOG_N + RATE_BITS)].copy() for i in probe]
+        ctx.check(lib.vpbs_batch_get_lde_rows(h, 0, 1, blk, h_leaves.ctypes.data_as(u64p)))
+        t0 = time.perf_counter()
+        for b0 in range(0, m, blk):
+            ctx.check(lib.vpbs_batch_get_lde_rows(h, b0, 1, blk, h_leaves[b0:b0 + blk].ctypes.data_as(u64p)))
+        dt = time.perf_counter() - t0
+        check("lde_pull.rows_match_eager_leaves_of_reversed_index",
+              all(np.array_equal(h_leaves[i], e) for i, e in zip(probe, expect)))
         lib.vpbs_batch_destroy(h)
+        lde_pull = {"ms": dt * 1e3, "bytes": 8 * m * NCOLS, "gbs": 8 * m * NCOLS / dt / 1e9,
+                    "api": "vpbs_batch_get_lde_rows, 8 blocks of 2^16 natural-order rows into pinned memory"}
 
-    for _ in range(2):
-        resident_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        resident_step()
-    torch.cuda.synchronize()
-    res_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    resident_ok = bool(np.array_equal(res_cap, h_cap) and np.array_equal(res_rows, h_leaves[query_idx]))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the N=1024 step stand-in (BASELINE.json configs[2]): wires / Z / quotient commits
     step_standin = None
     if rank == 0:
-        tot = []
-        bufs = {}
-        for (c, coeffs) in ((135, False), (20, False), (16, True)):
-            bufs[c] = (torch.from_numpy(V.synthetic_columns(c, n, 0x5EED0000 + c).view(np.int64)).to(dev),
-                       torch.empty((c, n), dtype=torch.int64, device=dev),
-                       torch.empty((m, c), dtype=torch.int64, device=dev))
-        for it in range(4):
-            t = 0.0
-            for (c, coeffs) in ((135, False), (20, False), (16, True)):
-                a, b, l = bufs[c]
-                st = V.commit_device(ctx, a.data_ptr(), c, LOG_N, RATE_BITS, CAP_HEIGHT, coeffs,
-                                     b.data_ptr(), l.data_ptr(), d_digests.data_ptr(),
-                                     d_cap.data_ptr(), want_stats=True)
-                t += st["total_ms"]
-            tot.append(t)
-        step_standin = {"what": "three commits of one N=1024 IVC step (135 + 20 value columns, 16 "
-                                "coefficient columns, 2^16 rows), kernels only, inputs in HBM",
-                        "ms": min(tot[1:]), "permutations": sum(permutations(c, n, RATE_BITS, CAP_HEIGHT)
-                                                                 for c in (135, 20, 16))}
-        del bufs
+        step_standin = run_step_standin(V, ctx, dev, n, m, ncap, d_digests, d_cap, pinned, colptrs,
+                                        check, int_peak_gimad(clocks))
 
+    # ---- ONE commit split by row range over all ranks (north_star: "partitioned ... by row range for
+    # the Merkle subtrees, with only the subtree roots gathered over NVLink")
+    shard = run_shard_commit_record(V, ctx, rank, world, dev, barrier, max_over_ranks, check,
+                                    ms_per_step if world == 1 else None)
+
+    if world > 1:  # every rank's self-checks count
+        flags = [None] * world
+        dist.all_gather_object(flags, list(fail_checks))
+        if rank == 0:
+            for r, fl in enumerate(flags[1:], 1):
+                fail_checks.extend("rank %d: %s" % (r, f) for f in fl)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -610,10 +713,8 @@ def main():
     merkle_ms = statistics.mean(s["merkle_ms"] for s in per_phase)
     ifft_ms = statistics.mean(s["ifft_ms"] for s in per_phase)
     fft_ms = statistics.mean(s["fft_ms"] for s in per_phase)
-    sm_mhz = (clocks or {}).get("sm_mhz") or (peaks or {}).get("sm_max_mhz", 1965.0)
-    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     leaf_perms = m * ((NCOLS + 7) // 8)
-    int_peak = SM_COUNT * IMAD_WIDE_LANES_PER_CLK_PER_SM * sm_max * 1e6 / 1e9  # G IMAD.WIDE/s
+    int_peak = int_peak_gimad(clocks)
     int_ach = leaf_perms * IMAD_PER_PERMUTATION / (leaf_ms * 1e-3) / 1e9
     leaf_bytes = 8 * m * NCOLS + 32 * m
     lde_bytes = 8 * NCOLS * n + 8 * NCOLS * m  # coefficients in (once), leaves out
@@ -637,8 +738,8 @@ def main():
         "unit": "GB/s", "frac": lde_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak,
         "peak_source": hbm_src, "algorithmic_bytes": lde_bytes, "ms": fft_ms,
         "traffic": traffic.get("lde_forward_dram_bytes"),
-        "note": "ncu shows these kernels bound by the ALU pipe and load latency, not by DRAM "
-                "(DRAM throughput ~11 % of peak): profiles/r1_ntt_r16p_kernels.txt",
+        "note": "ncu shows these kernels bound by instruction issue (ALU / FMA pipes), not by DRAM: "
+                "profiles/r2_ntt_*.txt",
     }
     whole = {"algorithmic_bytes": algorithmic_bytes(NCOLS, n, RATE_BITS, CAP_HEIGHT),
              "permutations": permutations(NCOLS, n, RATE_BITS, CAP_HEIGHT),
@@ -660,12 +761,12 @@ def main():
         t0 = time.perf_counter()
         ref = B.commit(host_cols, RATE_BITS, CAP_HEIGHT)
         dt = time.perf_counter() - t0
-        same = bool(np.array_equal(ref["cap"].view(np.int64), d_cap_check(ctx, V, host_cols, np)))
+        check("cpu_baseline.cap_matches_gpu", np.array_equal(ref["cap"], h_cap))
+        check("cpu_baseline.digests_match_gpu", np.array_equal(ref["digests"], h_digests))
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "one full 2^16x128 commit (%.1f s) by the C restatement of plonky2 "
+                        "sample": "one full 2^16x128 commit (%.2f s) by the C restatement of plonky2 "
                                   "0.2.0's CPU path (oracle/liboracle.so, OpenMP); plonky2 itself "
-                                  "cannot be built here (no Rust toolchain)" % dt,
-                        "cap_matches_gpu": same}
+                                  "cannot be built here (no Rust toolchain)" % dt}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -677,28 +778,202 @@ def main():
                      "leaf_hash": leaf_ms},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_whole_commit": whole,
         "cpu_baseline": cpu_baseline,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.e2e_steps * 1e3,
-                "steps": args.e2e_steps, "api": "vpbs_commit (host C ABI, pinned buffers)",
-                "phase_ms_last": e2e_stats.as_dict(), "cap_matches_device_path": cap_matches,
-                "pcie": pcie,
-                "host_affinity": numa},
-        "e2e_resident": {"value": world * args.e2e_steps * n / res_s, "unit": UNIT,
-                         "ms_per_step": res_s / args.e2e_steps * 1e3,
-                         "h2d_bytes_per_step": h2d_bytes,
-                         "d2h_bytes_per_step": 32 * ncap + 28 * (8 * NCOLS + 32 * (LOG_N + RATE_BITS - CAP_HEIGHT)),
-                         "api": "vpbs_batch_commit + 28 x (vpbs_batch_get_leaves, vpbs_batch_prove): batch "
-                                "stays in HBM, cap + queried rows/paths only",
-                         "matches_eager_path": resident_ok},
+        "e2e": {"value": world * n / res_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": res_d2h, "ms_per_step": res_s * 1e3, "steps": args.e2e_steps,
+                "api": "vpbs_batch_commit (host C ABI, pinned input columns) + vpbs_batch_eval_ext2 at 2 "
+                       "points + 28 x (vpbs_batch_get_leaves, vpbs_batch_prove): the batch stays in HBM; "
+                       "cap, openings, queried rows and Merkle paths come back",
+                "note": "leaves / digests are NOT shipped to the host: e2e_eager is the same commit with "
+                        "every output downloaded, lde_pull the cost of fetching the LDE rows on demand "
+                        "for a quotient that still runs on the CPU",
+                "pcie": pcie, "host_affinity": numa},
+        "e2e_eager": {"value": world * n / eager_s, "unit": UNIT, "ms_per_step": eager_s * 1e3,
+                      "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": eager_d2h,
+                      "api": "vpbs_commit (host C ABI, pinned buffers, all outputs)",
+                      "phase_ms_last": e2e_stats.as_dict()},
+        "e2e_pageable": pageable,
+        "lde_pull": lde_pull,
         "step_standin": step_standin,
+        "shard_commit": shard,
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "self_checks": {"failed": list(fail_checks), "passed": checks_passed[0]},
     }
     emit(out)
-    for p in (p0, p1, p2, p3, p4):
+    for p in pinned_ptrs:
         lib.vpbs_host_free(p)
     if world > 1:
         dist.destroy_process_group()
+    if fail_checks:
+        sys.stderr.write("bench.py: self-check(s) failed: %s\n" % "; ".join(fail_checks))
+        sys.exit(3)
+
+
+def int_peak_gimad(clocks):
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    return SM_COUNT * IMAD_WIDE_LANES_PER_CLK_PER_SM * sm_max * 1e6 / 1e9  # G IMAD.WIDE/s
+
+
+def run_step_standin(V, ctx, dev, n, m, ncap, d_digests, d_cap, pinned, colptrs, check, int_peak):
+    """BASELINE.json configs[2] stand-in: the three commits of one N=1024 IVC step proof
+    (135 wire + 20 Z/partial-product value columns, 16 quotient coefficient columns, 2^16 rows),
+    (a) kernels only with inputs in HBM, (b) as the device-resident pipeline through the host C ABI:
+    wires from host values -> Z / partial products computed on the device from the resident wires
+    batch -> quotient chunks from host coefficients; per batch the cap, the openings at two extension
+    points and 28 query rows + Merkle paths come back.  The real step proof (witness generation, gate
+    constraints of the quotient, the FRI challenger) needs plonky2 and cannot run here."""
+    import numpy as np
+    import torch
+    lib, u64p = ctx.lib, V._lib.u64p
+    shapes = ((135, False), (20, False), (16, True))
+    bufs = {}
+    for (c, coeffs) in shapes:
+        bufs[c] = (torch.from_numpy(V.synthetic_columns(c, n, 0x5EED0000 + c).view(np.int64)).to(dev),
+                   torch.empty((c, n), dtype=torch.int64, device=dev),
+                   torch.empty((m, c), dtype=torch.int64, device=dev))
+    tot = []
+    for it in range(5):
+        t = 0.0
+        for (c, coeffs) in shapes:
+            a, b, l = bufs[c]
+            st = V.commit_device(ctx, a.data_ptr(), c, LOG_N, RATE_BITS, CAP_HEIGHT, coeffs,
+                                 b.data_ptr(), l.data_ptr(), d_digests.data_ptr(),
+                                 d_cap.data_ptr(), want_stats=True)
+            t += st["total_ms"]
+        tot.append(t)
+    del bufs
+    perms = sum(permutations(c, n, RATE_BITS, CAP_HEIGHT) for c, _ in shapes)
+    kernels_ms = min(tot[1:])
+
+    # (b) resident pipeline
+    num_routed, max_degree = 80, 8
+    h_w = pinned((135, n)); h_w[:] = V.synthetic_columns(135, n, 0x5EED0000 + 135)
+    h_q = pinned((16, n)); h_q[:] = V.synthetic_columns(16, n, 0x5EED0000 + 16)
+    sig = V.Sigmas(V.synthetic_columns(num_routed, n, 0x51630000), V.get_unique_coset_shifts(n, num_routed), ctx)
+    rng = np.random.default_rng(3)
+    betas = rng.integers(0, P_GL, size=2, dtype=np.uint64)
+    gammas = rng.integers(0, P_GL, size=2, dtype=np.uint64)
+    zeta = rng.integers(0, P_GL, size=(2, 2), dtype=np.uint64)
+    qidx = rng.integers(0, m, size=28, dtype=np.uint64)
+    nlayers = LOG_N + RATE_BITS - CAP_HEIGHT
+    wp, qp = colptrs(h_w), colptrs(h_q)
+    caps = [np.empty((ncap, 4), np.uint64) for _ in range(3)]
+    opens = [np.empty((2, c, 2), np.uint64) for c in (135, 20, 16)]
+    rows = [np.empty((28, c), np.uint64) for c in (135, 20, 16)]
+    sibs = [np.empty((28, nlayers, 4), np.uint64) for _ in range(3)]
+
+    def serve(h, k):
+        ctx.check(lib.vpbs_batch_eval_ext2(h, zeta.ctypes.data_as(u64p), 2, opens[k].ctypes.data_as(u64p)))
+        ctx.check(lib.vpbs_batch_get_leaves(h, qidx.ctypes.data_as(u64p), 28, rows[k].ctypes.data_as(u64p)))
+        ctx.check(lib.vpbs_batch_prove(h, qidx.ctypes.data_as(u64p), 28, sibs[k].ctypes.data_as(u64p)))
+
+    def step():
+        hw, hz, hq = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, wp, 135, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None,
+                                        caps[0].ctypes.data_as(u64p), ctypes.byref(hw), None))
+        ctx.check(lib.vpbs_batch_zs_partial_products(hw, sig.handle, max_degree, betas.ctypes.data_as(u64p),
+                                                     gammas.ctypes.data_as(u64p), 2, RATE_BITS, CAP_HEIGHT,
+                                                     caps[1].ctypes.data_as(u64p), ctypes.byref(hz), None))
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, qp, 16, LOG_N, RATE_BITS, CAP_HEIGHT, 1, None,
+                                        caps[2].ctypes.data_as(u64p), ctypes.byref(hq), None))
+        for k, h in enumerate((hw, hz, hq)):
+            serve(h, k)
+        for h in (hq, hz, hw):
+            lib.vpbs_batch_destroy(h)
+
+    for _ in range(2):
+        step()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        step()
+    res_ms = (time.perf_counter() - t0) / reps * 1e3
+    # self-check: the device-computed Z batch equals committing the host-computed columns
+    zcols = V.all_wires_permutation_partial_products(h_w[:num_routed], sig, betas, gammas, max_degree)
+    ref = V.PolynomialBatch.from_values(zcols, RATE_BITS, False, CAP_HEIGHT, ctx=ctx)
+    check("step_standin.resident_z_batch_matches_host_pipeline",
+          np.array_equal(ref.merkle_tree.cap, caps[1]) and np.array_equal(ref.merkle_tree.leaves[qidx], rows[1]))
+    sig.close()
+    h2d = 8 * n * (135 + 16)
+    d2h = sum(32 * ncap + 2 * c * 16 + 28 * (8 * c + 32 * nlayers) for c in (135, 20, 16))
+    return {"what": "three commits of one N=1024 IVC step (135 wire + 20 Z/partial-product value "
+                    "columns, 16 quotient coefficient columns, 2^16 rows)",
+            "kernels_ms": kernels_ms, "permutations": perms,
+            "int_frac": perms * IMAD_PER_PERMUTATION / (kernels_ms * 1e-3) / 1e9 / int_peak,
+            "resident_pipeline_ms": res_ms, "resident_h2d_bytes": h2d, "resident_d2h_bytes": d2h,
+            "resident_api": "vpbs_batch_commit(wires) -> vpbs_batch_zs_partial_products (Z computed and "
+                            "committed on the device) -> vpbs_batch_commit(quotient, from coefficients); "
+                            "per batch: cap + openings at 2 points + 28 rows and Merkle paths",
+            "full_pbs_730_steps_s_commit_part": 730 * res_ms * 1e-3}
+
+
+def run_shard_commit_record(V, ctx, rank, world, dev, barrier, max_over_ranks, check, single_ms):
+    """ONE configs[1] commit split by row range over the `world` ranks: every rank computes
+    m / world leaves + their digests (vpbs_commit_shard_dev) and the subtree roots are all-gathered
+    over NCCL.  The gathered cap, the digests and a checksum of the leaves are compared with rank 0's
+    single-GPU commit of the same batch."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if world & (world - 1) or world > (1 << RATE_BITS) or world > (1 << CAP_HEIGHT):
+        return {"skipped": "world size %d does not divide the commit into whole LDE blocks / cap subtrees" % world}
+    n, m, ncap = 1 << LOG_N, (1 << LOG_N) << RATE_BITS, 1 << CAP_HEIGHT
+    cols = torch.from_numpy(V.synthetic_columns(NCOLS, n, seed=0x5EED0000).view(np.int64)).to(dev)
+    torch.cuda.current_stream(dev).synchronize()
+    steps, warm = 10, 3
+    for _ in range(warm):
+        V.commit_sharded(ctx, cols, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, False, rank, world)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        plan, leaves, digests, cap, coeffs, _ = V.commit_sharded(ctx, cols, NCOLS, LOG_N, RATE_BITS,
+                                                                 CAP_HEIGHT, False, rank, world)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+
+    def checksum(t):  # position-dependent, wrapping int64 arithmetic (exact, order-independent)
+        f = t.reshape(-1)
+        w = torch.arange(1, f.numel() + 1, dtype=torch.int64, device=f.device) * 2 + 1
+        return int((f * w).sum().item())
+
+    mine = torch.tensor([checksum(leaves), checksum(digests)], dtype=torch.int64, device=dev)
+    if world > 1:
+        allsums = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allsums, mine)
+    else:
+        allsums = [mine]
+    rec = None
+    if rank == 0:
+        full_leaves = torch.empty((m, NCOLS), dtype=torch.int64, device=dev)
+        full_dig = torch.empty((2 * (m - ncap), 4), dtype=torch.int64, device=dev)
+        full_cap = torch.empty((ncap, 4), dtype=torch.int64, device=dev)
+        t_single = []
+        for _ in range(4):
+            st = V.commit_device(ctx, cols.data_ptr(), NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, False, 0,
+                                 full_leaves.data_ptr(), full_dig.data_ptr(), full_cap.data_ptr(),
+                                 want_stats=True)
+            t_single.append(st["total_ms"])
+        torch.cuda.synchronize()
+        per = m // world
+        dper = 2 * (per - ncap // world)
+        ok_cap = bool(torch.equal(cap, full_cap))
+        ok_sum = all(int(allsums[r][0].item()) == checksum(full_leaves[r * per:(r + 1) * per]) and
+                     int(allsums[r][1].item()) == checksum(full_dig[r * dper:(r + 1) * dper])
+                     for r in range(world))
+        check("shard_commit.cap_matches_single_gpu", ok_cap)
+        check("shard_commit.leaf_and_digest_checksums_match_single_gpu", ok_sum)
+        t1 = min(t_single[1:])
+        rec = {"what": "ONE 2^16 x 128 commit split by row range over %d rank(s): vpbs_commit_shard_dev per "
+                       "rank + all_gather of the subtree roots (NCCL), device-resident" % world,
+               "ms_per_step": ms, "single_gpu_ms": t1, "speedup": t1 / ms,
+               "strong_scaling_efficiency": t1 / ms / world,
+               "matches_single_gpu": bool(ok_cap and ok_sum),
+               "collective": "all_gather_into_tensor of %d x 32 B roots per rank" % plan.ncap,
+               "cap0": "%016x" % (int(cap[0, 0].item()) & (2**64 - 1))}
+        del full_leaves, full_dig
+    return rec
 
 
 def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
@@ -772,41 +1047,20 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         dist.destroy_process_group()
 
 
-def run_shard_commit(args, V, ctx, d_cols, rank, world, dev, barrier, max_over_ranks, emit):
-    """One 2^16 x 128 commit split by row range over all ranks (SURVEY.md §8(e) partitioning B):
-    every rank holds all columns, computes m / world leaves + their digests, and only the subtree
-    roots (32 B per cap entry) are exchanged.  Strong scaling; prints its own JSON line."""
-    import torch
-    # every rank must commit the SAME batch
-    cols = torch.from_numpy(V.synthetic_columns(NCOLS, 1 << LOG_N, seed=0x5EED0000).view("int64")).to(dev)
-    for _ in range(args.warmup):
-        V.commit_sharded(ctx, cols, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, False, rank, world)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        plan, leaves, digests, cap, coeffs, _ = V.commit_sharded(ctx, cols, NCOLS, LOG_N, RATE_BITS,
-                                                                 CAP_HEIGHT, False, rank, world)
-    ev1.record()
-    barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+def run_shard_commit(args, V, ctx, rank, world, dev, barrier, max_over_ranks, emit):
+    """--shard-commit: only the sharded-commit record (see run_shard_commit_record), as its own line."""
+    failed = []
+    rec = run_shard_commit_record(V, ctx, rank, world, dev, barrier, max_over_ranks,
+                                  lambda name, ok: None if ok else failed.append(name), None)
     if rank == 0:
-        emit(({
-            "metric": METRIC + " — ONE commit sharded by row range", "value": (1 << LOG_N) / (ms * 1e-3),
-            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic", "config": workload_config(world),
-            "collective": "all_gather of %d subtree roots per rank (NCCL)" % plan.ncap,
-            "cap0": "%016x" % (int(cap[0, 0].item()) & (2**64 - 1))}))
+        emit(dict({"metric": METRIC + " — ONE commit sharded by row range", "unit": "ms per commit",
+                   "n_gpus": world, "scaling": "strong", "dtype": "u64", "data": "synthetic",
+                   "config": workload_config(world), "self_checks_failed": failed}, **(rec or {})))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-
-
-def d_cap_check(ctx, V, host_cols, np):
-    """cap of the same batch through the host API (for the cpu_baseline cross-check)."""
-    b = V.PolynomialBatch.from_values(host_cols, RATE_BITS, False, CAP_HEIGHT, ctx=ctx)
-    return b.merkle_tree.cap.view(np.int64)
+    if failed:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

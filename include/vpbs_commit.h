@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VPBS_ABI_VERSION 1
+#define VPBS_ABI_VERSION 2
 #define VPBS_SALT_SIZE 4 /* [P2] fri/oracle.rs SALT_SIZE */
 
 typedef enum vpbs_status {
@@ -219,6 +219,32 @@ int vpbs_fri_fold(vpbs_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len, uint3
                   const uint64_t beta[2], uint64_t shift_next, uint64_t* coeffs_out,
                   uint64_t* values_out);
 
+/* The same commit phase as ONE device-resident chain: the polynomial (coefficients and coset
+ * evaluations) and every layer's tree stay in HBM; per layer the host supplies only beta and gets
+ * back only the cap, as [P2] fri/prover.rs fri_committed_trees needs for the challenger.
+ *   vpbs_fri_begin        final_poly_coeffs_ext: ncoeffs extension coefficients (host).  Does what
+ *                         [P2] fri/oracle.rs prove_openings does before fri_proof: lde(rate_bits)
+ *                         (zero padding) and coset_fft(F::coset_shift()) ("perform final FFT").
+ *   vpbs_fri_commit_layer reverse_index_bits + chunk(2^arity_bits) + MerkleTree::new(cap_height) on the
+ *                         current values; cap_out: 2^cap_height hashes.  The tree is kept as layer
+ *                         number (calls so far).
+ *   vpbs_fri_fold_layer   coeffs <- reduce_with_powers(chunks, beta), shift <- shift^arity,
+ *                         values <- coeffs.coset_fft(shift); arity = that of the layer just committed.
+ *   vpbs_fri_final_poly   coeffs.truncate(len >> rate_bits) -> coeffs_out ((len >> rate_bits) x 2).
+ *   vpbs_fri_query_layer  [P2] fri_prover_query_round: MerkleTree::get / prove of a layer's tree;
+ *                         rows_out: count x (2 << arity_bits), siblings_out: count x (log2 leaves -
+ *                         cap_height) hashes (may be NULL).
+ * Calls must alternate commit_layer / fold_layer (VPBS_ERR_STATE otherwise). */
+typedef struct vpbs_fri vpbs_fri;
+int vpbs_fri_begin(vpbs_ctx* ctx, const uint64_t* final_poly_coeffs_ext, uint64_t ncoeffs,
+                   uint32_t rate_bits, vpbs_fri** out);
+int vpbs_fri_commit_layer(vpbs_fri* fri, uint32_t arity_bits, uint32_t cap_height, uint64_t* cap_out);
+int vpbs_fri_fold_layer(vpbs_fri* fri, const uint64_t beta[2]);
+int vpbs_fri_final_poly(vpbs_fri* fri, uint32_t rate_bits, uint64_t* coeffs_out);
+int vpbs_fri_query_layer(vpbs_fri* fri, uint32_t layer, const uint64_t* leaf_indices, uint64_t count,
+                         uint64_t* rows_out, uint64_t* siblings_out);
+void vpbs_fri_destroy(vpbs_fri* fri);
+
 /* ---- FRI proof-of-work grind -------------------------------------------
  * [P2] plonky2/src/fri/prover.rs fri_proof_of_work: the challenger's duplex state with the
  * candidate witness written at `witness_pos`, one permutation, and the response word
@@ -241,6 +267,9 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
                       uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
                       const uint64_t* const* salt_cols, uint64_t* cap_out, vpbs_batch** out,
                       vpbs_stats* stats);
+/* A batch may outlive its context: vpbs_ctx_destroy releases the device buffers of every live batch
+ * (and sigma set) of that context and leaves the handles inert — later reads return VPBS_ERR_STATE,
+ * and vpbs_batch_destroy only frees the handle. */
 void vpbs_batch_destroy(vpbs_batch* batch);
 /* rows_out: count x width, row i = leaf leaf_indices[i] (salt columns included). */
 int vpbs_batch_get_leaves(vpbs_batch* batch, const uint64_t* leaf_indices, uint64_t count,
@@ -253,9 +282,56 @@ int vpbs_batch_download(vpbs_batch* batch, uint64_t* const* coeffs_out, uint64_t
                         uint64_t* digests_out);
 /* vpbs_eval_ext2 on the coefficients the batch already holds in HBM (PolynomialBatch.polynomials). */
 int vpbs_batch_eval_ext2(vpbs_batch* batch, const uint64_t* points, uint32_t npoints, uint64_t* out);
+/* vpbs_batch_commit on columns that are already in HBM (d_cols: ncols x n column-major on the
+ * context's device, e.g. produced by another kernel of the prover); no salt. */
+int vpbs_batch_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
+                          uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                          uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats);
+/* [P2] fri/oracle.rs PolynomialBatch::get_lde_values(index, 1) for the LDE indices
+ * first_index + i * step, i < count — what plonk/prover.rs compute_quotient_polys reads row block
+ * by row block (get_lde_values_packed).  rows_out: count x ncols (salt columns dropped), row i =
+ * leaf reverse_bits(first_index + i * step).  Lets a CPU quotient pull the LDE lazily, in blocks,
+ * instead of receiving the whole m x width matrix at commit time. */
+int vpbs_batch_get_lde_rows(vpbs_batch* batch, uint64_t first_index, uint64_t step, uint64_t count,
+                            uint64_t* rows_out);
 /* Shape of the batch: m = 2^(log_n + rate_bits) leaves of `width` elements. */
 int vpbs_batch_shape(vpbs_batch* batch, uint32_t* ncols, uint32_t* log_n, uint32_t* rate_bits,
                      uint32_t* cap_height, uint32_t* width);
+
+/* ---- permutation argument: Z and partial products (first device consumer) ---
+ * [P2] plonky2/src/plonk/prover.rs wires_permutation_partial_products_and_zs /
+ * all_wires_permutation_partial_products with util/partial_products.rs quotient_chunk_products and
+ * partial_products_and_z_gx: step 4 of prove() ("compute partial products"), reached from
+ * /root/reference/src/vtfhe/ivc_based_vpbs.rs:302, :333, :364.  For challenge c and row i
+ * (x_i = w_n^i):  q_j = (wire_j + beta_c k_j x_i + gamma_c) / (wire_j + beta_c sigma_j(x_i) + gamma_c),
+ * chunk products over max_degree (= quotient_degree_factor) routed wires, K = ceil(num_routed /
+ * max_degree) chunks; Z_c(x_0) = 1, partial product k = Z_c(x_i) * chunk_0 .. chunk_k (k < K - 1),
+ * Z_c(x_{i+1}) = Z_c(x_i) * chunk_0 .. chunk_{K-1}.
+ * Output columns are in the order prove() commits them ("Z is expected at the front of our batch"):
+ * Z_0 .. Z_{C-1}, then the K - 1 partial products of challenge 0, of challenge 1, ... (C * K columns:
+ * 2 + 18 = 20 for CircuitConfig::standard_recursion_config()).
+ * VPBS_ERR_ARG if a denominator is zero (upstream's batch_multiplicative_inverse panics). */
+typedef struct vpbs_sigmas vpbs_sigmas;
+/* The circuit's sigma polynomial VALUES and coset shifts, uploaded once per circuit
+ * ([P2] ProverOnlyCircuitData.sigmas transposed: sigma_cols[j][i] = sigmas[i][j]; k_is =
+ * CommonCircuitData.k_is).  num_routed pointers to n = 2^log_n values each. */
+int vpbs_sigmas_upload(vpbs_ctx* ctx, const uint64_t* const* sigma_cols, const uint64_t* k_is,
+                       uint32_t num_routed, uint32_t log_n, vpbs_sigmas** out);
+void vpbs_sigmas_destroy(vpbs_sigmas* sigmas);
+/* Host in, host out: wire_cols[j][i] = witness.get_wire(i, j) for the num_routed routed wires;
+ * cols_out: num_challenges * K pointers (NULL entries are skipped) receiving n values each. */
+int vpbs_zs_partial_products(vpbs_ctx* ctx, const uint64_t* const* wire_cols,
+                             const vpbs_sigmas* sigmas, uint32_t max_degree, const uint64_t* betas,
+                             const uint64_t* gammas, uint32_t num_challenges,
+                             uint64_t* const* cols_out);
+/* Device-resident form: the routed wire values are recovered from the first num_routed coefficient
+ * columns of the resident wires batch (one forward transform in HBM), and the C * K result columns
+ * are committed at once as a new resident batch (PolynomialBatch::from_values(zs_partial_products,
+ * rate_bits, false, cap_height)): only the cap crosses PCIe. */
+int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas, uint32_t max_degree,
+                                   const uint64_t* betas, const uint64_t* gammas,
+                                   uint32_t num_challenges, uint32_t rate_bits, uint32_t cap_height,
+                                   uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats);
 
 #ifdef __cplusplus
 }

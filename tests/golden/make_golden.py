@@ -116,6 +116,15 @@ def model_anchors():
             coeffs=[hx(x) for x in res["coeffs"]], lde=[hx(x) for x in res["lde"]],
             leaves=[hx(x) for x in res["leaves"]], digests=[hx(x) for x in res["digests"]],
             cap=[hx(x) for x in res["cap"]]))
+    # [P2] plonk/prover.rs wires_permutation_partial_products_and_zs on a fixed 5-wire x 8-row case
+    # (max_degree 2 -> 3 chunks per row: columns Z, pp_0, pp_1)
+    P = M.P
+    beta, gamma = 0x123456789ABCDEF, 0xFEDCBA987654321
+    wa = [[8 * j + i + 1 for i in range(8)] for j in range(5)]
+    sa = [[3 * j + 5 * i + 2 for i in range(8)] for j in range(5)]
+    ka = [pow(7, j, P) for j in range(5)]
+    out["zs_partial_products"] = dict(beta=beta, gamma=gamma, max_degree=2,
+                                      columns=[hx(c) for c in M.zs_partial_products(wa, sa, ka, 2, beta, gamma)])
     json.dump(out, open(os.path.join(HERE, "model_anchors.json"), "w"))
 
 

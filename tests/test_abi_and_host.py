@@ -23,7 +23,7 @@ def test_library_builds_and_exports_every_declared_symbol(V):
     for s in syms:
         assert hasattr(lib, s), "libvpbs_commit.so does not export %s" % s
     assert sorted(V._lib.SIGNATURES) == syms, "binding and header disagree"
-    assert lib.vpbs_abi_version() == 1
+    assert lib.vpbs_abi_version() == 2
 
 
 def test_library_contains_sm100a_code_only(V):
@@ -127,6 +127,19 @@ def test_bench_and_entry_have_no_undefined_names():
             assert not missing, "%s: %s uses undefined names %s" % (fname, fn.name, sorted(missing))
 
 
+def test_product_sources_carry_no_developer_knobs():
+    """csrc/ is the product: no getenv() tuning knobs and no alternative kernel forms behind -D
+    switches (those are in tools/variants/)."""
+    pkg = os.path.join(ROOT, "verifiable-fhe-paper_b200", "csrc")
+    for f in os.listdir(pkg):
+        text = open(os.path.join(pkg, f)).read()
+        assert "getenv" not in text, f
+        for flag in ("VPBS_MDS_INT32", "VPBS_MDS_FP64_DENSE", "VPBS_SBOX_REDUCED", "VPBS_SBOX_OUTLINE",
+                     "VPBS_NO_PIPE_INTERLEAVE", "VPBS_MUL_C", "VPBS_ADDSUB_C", "VPBS_HALF_I2F",
+                     "VPBS_CANON_C", "VPBS_NTT_CANONICAL"):
+            assert flag not in text, (f, flag)
+
+
 def test_bench_help_runs():
     import subprocess
     import sys
@@ -139,9 +152,9 @@ def test_bench_help_runs():
                                   "VPBS_SBOX_OUTLINE", "VPBS_NO_PIPE_INTERLEAVE", "VPBS_MUL_C",
                                   "VPBS_ADDSUB_C", "VPBS_HALF_I2F"])
 def test_documented_kernel_variants_still_compile(flag, tmp_path):
-    """DESIGN.md quotes measurements of alternative kernel forms that are kept in the source behind
-    compile-time switches; they have to keep building for sm_100a (their bit-exactness is what
-    tools/selftest.cu checks on a GPU)."""
+    """DESIGN.md quotes measurements of alternative kernel forms; they live outside the product, in
+    tools/variants/ (round-1 headers with every compile-time switch), and have to keep building for
+    sm_100a (their bit-exactness is what tools/selftest.cu checks on a GPU)."""
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -153,6 +166,7 @@ def test_documented_kernel_variants_still_compile(flag, tmp_path):
     env.pop("CC", None)
     env.pop("CXX", None)
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17",
-                        "-I", os.path.join(pkg, "csrc"), "-D" + flag, "-c", "-o", str(tmp_path / "v.o"),
+                        "-I", os.path.join(pkg, "tools", "variants"), "-I", os.path.join(pkg, "csrc"),
+                        "-D" + flag, "-c", "-o", str(tmp_path / "v.o"),
                         os.path.join(pkg, "tools", "selftest.cu")], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr[-2000:]

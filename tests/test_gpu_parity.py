@@ -640,3 +640,210 @@ def test_fri_layers_chain_like_the_prover(V, ctx, oracle):
         log_len -= a
         want = np.stack([oracle.coset_fft(coeffs[:, 0].copy(), shift), oracle.coset_fft(coeffs[:, 1].copy(), shift)], 1)
         assert np.array_equal(values, want)
+
+
+# ------------------------------------------------------------------------------ permutation argument
+def _perm_inputs(rng, num_routed, log_n, noncanonical=True):
+    n = 1 << log_n
+    wires = rand_u64(rng, (num_routed, n)) if noncanonical else rng.integers(0, P, size=(num_routed, n), dtype=np.uint64)
+    sigmas = rand_u64(rng, (num_routed, n))
+    return wires, sigmas
+
+
+@pytest.mark.parametrize("num_routed,log_n,max_degree,nch", [
+    (80, 10, 8, 2), (80, 0, 8, 2), (8, 3, 8, 1), (5, 2, 2, 3), (7, 5, 3, 2), (20, 9, 8, 2),
+    (33, 13, 8, 2), (80, 16, 8, 2)])
+def test_zs_partial_products_against_oracle(V, ctx, oracle, num_routed, log_n, max_degree, nch):
+    """[P2] all_wires_permutation_partial_products through the C ABI (host in / host out) against the
+    oracle, incl. the N=1024 step's shape (80 routed wires x 2^16 rows, 2 challenges -> 20 columns),
+    ragged last chunks, one row, non-canonical inputs."""
+    rng = np.random.default_rng(num_routed * 100 + log_n)
+    wires, sigmas = _perm_inputs(rng, num_routed, log_n)
+    k_is = V.get_unique_coset_shifts(1 << log_n, num_routed)
+    betas, gammas = rand_u64(rng, nch), rand_u64(rng, nch)
+    sg = V.Sigmas(sigmas, k_is, ctx)
+    got = V.all_wires_permutation_partial_products(wires, sg, betas, gammas, max_degree)
+    K = -(-num_routed // max_degree)
+    assert got.shape == (nch * K, 1 << log_n)
+    for c in range(nch):
+        ref = oracle.zs_partial_products(wires, sigmas, k_is, max_degree, betas[c], gammas[c])
+        assert np.array_equal(got[c], ref[0]), "Z of challenge %d" % c
+        assert np.array_equal(got[nch + c * (K - 1): nch + (c + 1) * (K - 1)], ref[1:]), "partial products"
+    sg.close()
+
+
+def test_zs_of_a_real_permutation_closes(V, ctx):
+    """Size-independent property at full size: when the wires satisfy a copy-constraint permutation,
+    the running product returns to 1 — Z(g^n) = Z(1) — i.e. the last row's full chunk product times
+    Z(x_{n-1}) is 1.  Checked through the last partial product and the chunk values on the device."""
+    rng = np.random.default_rng(4)
+    num_routed, log_n, deg = 16, 12, 8
+    n = 1 << log_n
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    w = pow(7, (P - 1) >> log_n, P)
+    sub = np.array([pow(w, i, P) for i in range(n)], dtype=object)
+    ncell = num_routed * n
+    perm = rng.permutation(ncell)
+    # wire values constant along every cycle of the permutation
+    label = np.full(ncell, -1, dtype=np.int64)
+    vals = rng.integers(0, P, size=ncell, dtype=np.uint64)
+    for c0 in range(ncell):
+        c = c0
+        while label[c] < 0:
+            label[c] = c0
+            c = perm[c]
+    wires = vals[label].reshape(num_routed, n)
+    tj, ti = np.divmod(perm, n)
+    sig = np.array([int(k_is[j]) * int(sub[i]) % P for j, i in zip(tj, ti)], dtype=np.uint64).reshape(num_routed, n)
+    sg = V.Sigmas(sig, k_is, ctx)
+    beta, gamma = rand_u64(rng, 1), rand_u64(rng, 1)
+    out = V.all_wires_permutation_partial_products(wires, sg, beta, gamma, deg)
+    K = num_routed // deg
+    # Z(x_{n-1}) * prod of the last row's quotients == 1: recompute that row's quotient product
+    i = n - 1
+    num = den = 1
+    b, g = int(beta[0]) % P, int(gamma[0]) % P
+    for j in range(num_routed):
+        num = num * ((int(wires[j, i]) + b * int(k_is[j]) * int(sub[i]) + g) % P) % P
+        den = den * ((int(wires[j, i]) + b * int(sig[j, i]) + g) % P) % P
+    assert int(out[0, i]) * num % P * pow(den, P - 2, P) % P == 1
+    assert int(out[0, 0]) == 1 and K == 2
+    sg.close()
+
+
+def test_zs_zero_denominator_is_an_error(V, ctx):
+    """plonky2's batch_multiplicative_inverse panics on a zero denominator; the ABI returns
+    VPBS_ERR_ARG (ValueError in the mirror)."""
+    rng = np.random.default_rng(8)
+    num_routed, log_n = 8, 4
+    wires, sigmas = _perm_inputs(rng, num_routed, log_n, noncanonical=False)
+    k_is = V.get_unique_coset_shifts(1 << log_n, num_routed)
+    beta, gamma = 5, 11
+    # force wire + beta * sigma + gamma == 0 at (wire 3, row 7)
+    sigmas[3, 7] = (P - (int(wires[3, 7]) + gamma) % P) * pow(beta, P - 2, P) % P
+    sg = V.Sigmas(sigmas, k_is, ctx)
+    with pytest.raises(ValueError):
+        V.all_wires_permutation_partial_products(wires, sg, [beta], [gamma], 8)
+    sg.close()
+
+
+@pytest.mark.parametrize("log_n,ncols,num_routed", [(10, 135, 80), (6, 9, 8), (13, 20, 20)])
+def test_resident_zs_commit_matches_host_pipeline(V, ctx, oracle, log_n, ncols, num_routed):
+    """prove() steps 2-5 with both batches resident: wires commit -> Z / partial products computed
+    from the wires batch's coefficients in HBM -> committed as a new resident batch.  The cap, opened
+    rows and coefficients equal the oracle's from_values on the oracle's Z columns."""
+    rng = np.random.default_rng(log_n + ncols)
+    n = 1 << log_n
+    wires = rand_u64(rng, (ncols, n))
+    sigmas = rand_u64(rng, (num_routed, n))
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    betas, gammas = rand_u64(rng, 2), rand_u64(rng, 2)
+    wb = V.commit_resident(wires, 3, False, 4, ctx=ctx)
+    sg = V.Sigmas(sigmas, k_is, ctx)
+    zb = V.commit_zs_partial_products(wb, sg, betas, gammas, 8, 3, 4)
+    K = -(-num_routed // 8)
+    per = [oracle.zs_partial_products(wires[:num_routed], sigmas, k_is, 8, betas[c], gammas[c]) for c in range(2)]
+    zcols = np.concatenate([np.stack([per[0][0], per[1][0]]), per[0][1:], per[1][1:]])
+    assert zcols.shape[0] == 2 * K == zb.ncols
+    ref = oracle.commit(zcols, 3, 4)
+    assert np.array_equal(zb.merkle_tree.cap, ref["cap"])
+    m = n << 3
+    idx = rng.integers(0, m, size=12, dtype=np.uint64)
+    rows = zb.merkle_tree.get_many(idx)
+    for k, i in enumerate(idx):
+        assert np.array_equal(rows[k], ref["leaves"][int(i)])
+    eager = zb.download()
+    assert np.array_equal(eager.polynomials, ref["coeffs"])
+    assert np.array_equal(eager.merkle_tree.digests, ref["digests"])
+    zb.close(); wb.close(); sg.close()
+
+
+@pytest.mark.parametrize("log_n,ncols,rate_bits,salted", [(8, 9, 3, False), (10, 135, 3, False), (5, 6, 2, True), (0, 3, 3, False)])
+def test_batch_get_lde_rows(V, ctx, oracle, log_n, ncols, rate_bits, salted):
+    """vpbs_batch_get_lde_rows == [get_lde_values(first + i * step) for i] (what the quotient reads)."""
+    rng = np.random.default_rng(log_n * 7 + ncols)
+    cols = rand_u64(rng, (ncols, 1 << log_n))
+    m = (1 << log_n) << rate_bits
+    salt = rand_u64(rng, (4, m)) if salted else None
+    rb = V.commit_resident(cols, rate_bits, salted, min(2, log_n + rate_bits), ctx=ctx, salt=salt)
+    ref = oracle.commit(cols, rate_bits, min(2, log_n + rate_bits), False, salt)
+    lg = log_n + rate_bits
+    for first, step, count in [(0, 1, m), (1, 3, (m - 1 + 2) // 3), (m - 1, 1, 1), (0, 1 << rate_bits, 1 << log_n), (2, 5, 0)]:
+        first = min(first, m - 1)
+        if count and first + (count - 1) * step >= m:
+            count = (m - 1 - first) // step + 1
+        got = rb.get_lde_rows(first, step, count)
+        want = np.array([ref["leaves"][V.reverse_bits(first + i * step, lg)][:ncols] for i in range(count)],
+                        dtype=np.uint64).reshape(count, ncols)
+        assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        rb.get_lde_rows(0, 1, m + 1)
+    with pytest.raises(ValueError):
+        rb.get_lde_rows(m, 1, 1)
+    rb.close()
+
+
+def test_batch_outliving_its_context_is_inert(V):
+    """vpbs_ctx_destroy releases the device buffers of live batches and orphans the handles: reads
+    fail with VPBS_ERR_STATE, destroy only frees the handle (no use-after-free)."""
+    c = V.Context(0)
+    rb = V.commit_resident(V.synthetic_columns(5, 64), 3, False, 2, ctx=c)
+    sg = V.Sigmas(V.synthetic_columns(4, 64), V.get_unique_coset_shifts(64, 4), c)
+    c.close()
+    out = np.empty((1, 5), np.uint64)
+    idx = np.zeros(1, np.uint64)
+    rc = rb.ctx.lib.vpbs_batch_get_leaves(rb.handle, idx.ctypes.data_as(V._lib.u64p), 1,
+                                          out.ctypes.data_as(V._lib.u64p))
+    assert rc == V._lib.VPBS_ERR_STATE
+    rb.close()
+    sg.close()
+
+
+def test_commit_resident_device_columns(V, ctx, oracle):
+    """vpbs_batch_commit_dev: resident batch from columns already in HBM."""
+    import torch
+    cols = V.synthetic_columns(20, 1 << 9, seed=77, canonical=False)
+    d = torch.from_numpy(cols.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    rb = V.commit_resident_device(ctx, d.data_ptr(), 20, 9, 3, 4)
+    ref = oracle.commit(cols, 3, 4)
+    assert np.array_equal(rb.merkle_tree.cap, ref["cap"])
+    assert np.array_equal(rb.download().merkle_tree.leaves, ref["leaves"])
+    rb.close()
+
+
+@pytest.mark.parametrize("log_n,rate_bits,arities,cap_height", [
+    (16, 3, [4, 4, 4], 4),    # the N=1024 step's commit phase: 2^19 -> 2^15 -> 2^11 -> 2^7 values
+    (13, 3, [4, 4], 4), (6, 1, [2, 1, 3], 1), (4, 0, [4], 0), (3, 2, [], 2)])
+def test_fri_commit_phase_resident_chain(V, ctx, oracle, log_n, rate_bits, arities, cap_height):
+    """vpbs_fri_*: the whole commit phase with polynomial and trees resident in HBM equals the oracle's
+    layer-by-layer chain: caps, final polynomial, and queried rows + Merkle paths of every layer."""
+    rng = np.random.default_rng(log_n * 13 + rate_bits)
+    coeffs0 = rand_u64(rng, (1 << log_n, 2))
+    fri = V.FriCommitPhase(coeffs0, rate_bits, ctx)
+    m = (1 << log_n) << rate_bits
+    coeffs = np.zeros((m, 2), np.uint64)
+    coeffs[: 1 << log_n] = coeffs0 % np.uint64(P)
+    shift = 7
+    values = np.stack([oracle.coset_fft(coeffs[:, 0].copy(), shift), oracle.coset_fft(coeffs[:, 1].copy(), shift)], 1)
+    lg = log_n + rate_bits
+    for k, a in enumerate(arities):
+        h = min(cap_height, lg - a)
+        ref = oracle.fri_layer_commit(values, a, h)
+        cap = fri.commit_layer(a, h)
+        assert np.array_equal(cap, ref["cap"]), "cap of layer %d" % k
+        nleaves = 1 << (lg - a)
+        idx = rng.integers(0, nleaves, size=min(28, nleaves), dtype=np.uint64)
+        rows, sib = fri.query(k, idx)
+        for q, i in enumerate(idx):
+            assert np.array_equal(rows[q], ref["leaves"][int(i)])
+            assert np.array_equal(sib[q], oracle.merkle_prove(ref["digests"], nleaves, h, int(i)))
+        beta = rand_u64(rng, 2)
+        shift = oracle.gl_pow(shift, 1 << a)
+        coeffs, values = oracle.fri_fold(coeffs, a, beta, shift)
+        fri.fold(beta)
+        lg -= a
+    assert np.array_equal(fri.final_poly(), coeffs[: coeffs.shape[0] >> rate_bits])
+    with pytest.raises(V.VpbsError):
+        fri.fold([1, 2])  # nothing committed to fold
+    fri.close()

@@ -175,3 +175,48 @@ def test_fri_layer_against_model(oracle):
         co, vo = oracle.fri_fold(np.array(vals, dtype=np.uint64), a, beta, sh)
         mco, mvo = model.fri_fold(vals, a, beta, sh)
         assert co.tolist() == [list(x) for x in mco] and vo.tolist() == [list(x) for x in mvo]
+
+
+# ------------------------------------------------------------------------------ permutation argument
+def test_zs_partial_products_oracle_vs_model(oracle):
+    """[P2] wires_permutation_partial_products_and_zs: the C restatement against the big-integer
+    model written from the definitions, incl. ragged chunks and the reference's config
+    (80 routed wires, max_degree 8 -> 10 columns per challenge)."""
+    from oracle import model as M
+    rng = np.random.default_rng(1)
+    P = oracle.P
+    for (nr, lg, deg) in [(8, 3, 8), (80, 4, 8), (5, 2, 2), (7, 3, 3), (80, 0, 8), (9, 5, 4)]:
+        n = 1 << lg
+        w = rng.integers(0, P, size=(nr, n), dtype=np.uint64)
+        s = rng.integers(0, P, size=(nr, n), dtype=np.uint64)
+        k = np.array([pow(7, j, P) for j in range(nr)], dtype=np.uint64)
+        beta, gamma = int(rng.integers(0, P, dtype=np.uint64)), int(rng.integers(0, P, dtype=np.uint64))
+        a = oracle.zs_partial_products(w, s, k, deg, beta, gamma)
+        b = M.zs_partial_products([[int(x) for x in r] for r in w], [[int(x) for x in r] for r in s],
+                                  [int(x) for x in k], deg, beta, gamma)
+        assert np.array_equal(a, np.array(b, dtype=np.uint64)), (nr, lg, deg)
+
+
+def test_zs_identity_permutation_and_golden(oracle, model_anchors):
+    """sigma = identity (sigma_j(x) = k_j x) makes every quotient 1, so Z and all partial products are
+    1; plus the model anchor recorded in tests/golden/model_anchors.json."""
+    P = oracle.P
+    nr, lg = 16, 4
+    n = 1 << lg
+    rng = np.random.default_rng(2)
+    w = rng.integers(0, P, size=(nr, n), dtype=np.uint64)
+    k = np.array([pow(7, j, P) for j in range(nr)], dtype=np.uint64)
+    wn = oracle.primitive_root_of_unity(lg)
+    sub = [pow(wn, i, P) for i in range(n)]
+    sig = np.array([[int(kk) * x % P for x in sub] for kk in k], dtype=np.uint64)
+    assert (oracle.zs_partial_products(w, sig, k, 8, 123, 456) == 1).all()
+    with pytest.raises(ZeroDivisionError):
+        sig2 = sig.copy()
+        sig2[3, 7] = (P - (int(w[3, 7]) + 11) % P) * pow(5, P - 2, P) % P
+        oracle.zs_partial_products(w, sig2, k, 8, 5, 11)
+    g = model_anchors["zs_partial_products"]
+    wa = np.array([[8 * j + i + 1 for i in range(8)] for j in range(5)], dtype=np.uint64)
+    sa = np.array([[(3 * j + 5 * i + 2) for i in range(8)] for j in range(5)], dtype=np.uint64)
+    ka = np.array([pow(7, j, P) for j in range(5)], dtype=np.uint64)
+    got = oracle.zs_partial_products(wa, sa, ka, 2, g["beta"], g["gamma"])
+    assert [["%016x" % int(x) for x in row] for row in got] == g["columns"]

@@ -76,6 +76,12 @@ SIGNATURES = {
     "vpbs_batch_eval_ext2": (_c.c_int, [_c.c_void_p, u64p, _c.c_uint32, u64p]),
     "vpbs_fri_layer_commit": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, _c.c_uint32, u64p, u64p, u64p]),
     "vpbs_fri_fold": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, u64p, _c.c_uint64, u64p, u64p]),
+    "vpbs_fri_begin": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
+    "vpbs_fri_commit_layer": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, u64p]),
+    "vpbs_fri_fold_layer": (_c.c_int, [_c.c_void_p, u64p]),
+    "vpbs_fri_final_poly": (_c.c_int, [_c.c_void_p, _c.c_uint32, u64p]),
+    "vpbs_fri_query_layer": (_c.c_int, [_c.c_void_p, _c.c_uint32, u64p, _c.c_uint64, u64p, u64p]),
+    "vpbs_fri_destroy": (None, [_c.c_void_p]),
     "vpbs_pow_grind": (_c.c_int, [_ctx, u64p, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint64,
                                   _c.c_uint64, u64p, _c.POINTER(_c.c_int)]),
     "vpbs_batch_commit": (_c.c_int, [_ctx, u64pp, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32,
@@ -85,6 +91,18 @@ SIGNATURES = {
     "vpbs_batch_get_leaves": (_c.c_int, [_c.c_void_p, u64p, _c.c_uint64, u64p]),
     "vpbs_batch_prove": (_c.c_int, [_c.c_void_p, u64p, _c.c_uint64, u64p]),
     "vpbs_batch_download": (_c.c_int, [_c.c_void_p, u64pp, u64p, u64p]),
+    "vpbs_batch_commit_dev": (_c.c_int, [_ctx, _c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_uint32,
+                                         _c.c_uint32, _c.c_int, u64p, _c.POINTER(_c.c_void_p),
+                                         _c.POINTER(VpbsStats)]),
+    "vpbs_batch_get_lde_rows": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_uint64, _c.c_uint64, u64p]),
+    "vpbs_sigmas_upload": (_c.c_int, [_ctx, u64pp, u64p, _c.c_uint32, _c.c_uint32,
+                                      _c.POINTER(_c.c_void_p)]),
+    "vpbs_sigmas_destroy": (None, [_c.c_void_p]),
+    "vpbs_zs_partial_products": (_c.c_int, [_ctx, u64pp, _c.c_void_p, _c.c_uint32, u64p, u64p,
+                                            _c.c_uint32, u64pp]),
+    "vpbs_batch_zs_partial_products": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint32, u64p, u64p,
+                                                  _c.c_uint32, _c.c_uint32, _c.c_uint32, u64p,
+                                                  _c.POINTER(_c.c_void_p), _c.POINTER(VpbsStats)]),
     "vpbs_batch_shape": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint32)] * 5),
 }
 

@@ -171,7 +171,6 @@ pass_final(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
 // Values inside the register layers are arbitrary u64 representatives ("lazy"): add_lazy / sub_lazy
 // need only their SECOND operand canonical, so each butterfly canonicalises one input (4 slots)
 // instead of paying for canonical add, sub and mul results (saves ~11 slots per butterfly).
-#ifndef VPBS_NTT_CANONICAL
 template <bool HAS_OFF>
 __device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, unsigned jstride,
                                       unsigned off, unsigned l0) {
@@ -191,27 +190,6 @@ __device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, 
     }
   }
 }
-#else
-template <bool HAS_OFF>
-__device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, unsigned jstride,
-                                      unsigned off, unsigned l0) {
-#pragma unroll
-  for (int l = 0; l < 4; l++) {
-    const int dd = 8 >> l;
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-      if ((j & dd) == 0) {
-        const u64 a = x[j], c = x[j + dd];
-        x[j] = gl::add(a, c);
-        const u64 d = gl::sub(a, c);
-        const int jm = j & (dd - 1);
-        if (!HAS_OFF && jm == 0) x[j + dd] = d;
-        else x[j + dd] = gl::mul(d, tw[((unsigned)jm * jstride + off) << (l0 + l)]);
-      }
-    }
-  }
-}
-#endif
 
 // A 256-point DIF on a 256 x 16 tile is two of these with one exchange through shared memory in
 // between: layers 0..3 on x[j] = element (q = 16 j + q_lo, lane) with dif16<true>(x, tw, 16, q_lo, 0),
@@ -511,6 +489,17 @@ __global__ void fri_fold(const ulonglong2* __restrict__ coeffs, u64 out_len, uns
   folded[j] = make_ulonglong2(acc.re, acc.im);
   planar[j] = acc.re;
   planar[out_len + j] = acc.im;
+}
+// planar[j] = canon(re), planar[out_len + j] = canon(im) for j < in_len, zero beyond (zero padding
+// of PolynomialCoeffs::lde made explicit for the extension-field final polynomial).
+__global__ void deinterleave2_pad(const ulonglong2* __restrict__ in, u64 in_len, u64 out_len,
+                                  u64* __restrict__ planar) {
+  const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= out_len) return;
+  ulonglong2 v = make_ulonglong2(0, 0);
+  if (j < in_len) v = in[j];
+  planar[j] = gl::canon(v.x);
+  planar[out_len + j] = gl::canon(v.y);
 }
 __global__ void interleave2(const u64* __restrict__ planar, u64 len, ulonglong2* __restrict__ out) {
   const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,194 @@
+// permutation.cuh — Z and partial-product polynomials of PLONK's permutation argument (sm_100a).
+//
+// Replaces, for F = GoldilocksField:
+//   [P2] plonky2 0.2.0 src/plonk/prover.rs        wires_permutation_partial_products_and_zs
+//   [P2] plonky2 0.2.0 src/util/partial_products.rs quotient_chunk_products, partial_products_and_z_gx
+// i.e. step 4 of prove() ("compute partial products"), reached from
+// /root/reference/src/vtfhe/ivc_based_vpbs.rs:302, :333, :364.  It is the first consumer of a
+// committed batch that runs on the device: the routed wire values are
+// recovered from the wires batch's coefficients in HBM and the 2 + 18 resulting columns go straight
+// into the next commit without touching the host.
+//
+// Per row i (x_i = w_n^i), challenge (beta, gamma), routed wire j:
+//     q_j = (wire_j + beta k_j x_i + gamma) / (wire_j + beta sigma_j(x_i) + gamma)
+// chunk products c_k = prod of q_j over chunks of max_degree wires (K chunks), then
+//     Z(x_0) = 1,   pp_k(x_i) = Z(x_i) c_0 .. c_k  (k < K - 1),   Z(x_{i+1}) = Z(x_i) c_0 .. c_{K-1}.
+// Field inverses are unique, so dividing the chunk's numerator product by its denominator product
+// (one Montgomery batch inversion per row) equals upstream's batch_multiplicative_inverse followed
+// by per-wire multiplications bit for bit; the running product over the rows is a parallel prefix
+// product (exact arithmetic: any association gives the same values).
+#pragma once
+#include "ntt.cuh"
+
+namespace perm {
+
+using gl::u32;
+using gl::u64;
+
+constexpr int MAX_CHUNKS = 32;  // K = ceil(num_routed / max_degree); plonky2's standard config: 10
+
+// a^(p-2) for canonical a != 0.  p - 2 = 2^64 - 2^32 - 1 = (2^32 - 1) * 2^32 + (2^32 - 1) - ... is
+// evaluated with the chain x^(2^32 - 1) -> shift by 32 -> times x^(2^32 - 2) ... ; 63 squarings + 8
+// multiplies in the classic form for this prime:
+//   e = p - 2 = 0xFFFFFFFE_FFFFFFFF:  bits 63..33 ones, bit 32 zero, bits 31..0 ones.
+__device__ __forceinline__ u64 inv_nonzero(u64 a) {
+  // t_k = a^(2^k - 1)
+  u64 t1 = a;
+  u64 t2 = gl::mul_lazy(gl::sqr_lazy(t1), t1);                              // 2^2 - 1
+  u64 t4 = t2;
+  for (int i = 0; i < 2; i++) t4 = gl::sqr_lazy(t4);
+  t4 = gl::mul_lazy(t4, t2);                                                // 2^4 - 1
+  u64 t8 = t4;
+  for (int i = 0; i < 4; i++) t8 = gl::sqr_lazy(t8);
+  t8 = gl::mul_lazy(t8, t4);                                                // 2^8 - 1
+  u64 t16 = t8;
+  for (int i = 0; i < 8; i++) t16 = gl::sqr_lazy(t16);
+  t16 = gl::mul_lazy(t16, t8);                                              // 2^16 - 1
+  u64 t31 = t16;
+  for (int i = 0; i < 8; i++) t31 = gl::sqr_lazy(t31);
+  t31 = gl::mul_lazy(t31, t8);                                              // 2^24 - 1
+  for (int i = 0; i < 4; i++) t31 = gl::sqr_lazy(t31);
+  t31 = gl::mul_lazy(t31, t4);                                              // 2^28 - 1
+  for (int i = 0; i < 2; i++) t31 = gl::sqr_lazy(t31);
+  t31 = gl::mul_lazy(t31, t2);                                              // 2^30 - 1
+  t31 = gl::mul_lazy(gl::sqr_lazy(t31), t1);                                // 2^31 - 1
+  u64 t32 = gl::mul_lazy(gl::sqr_lazy(t31), t1);                            // 2^32 - 1
+  // exponent = (2^31 - 1) * 2^33 + (2^32 - 1)
+  u64 r = t31;
+  for (int i = 0; i < 33; i++) r = gl::sqr_lazy(r);
+  return gl::canon(gl::mul_lazy(r, t32));
+}
+
+// One thread per row.  wires / sigmas: column-major (column j at + j * col_stride), natural order.
+// quot[k * n + i] = chunk product c_k of row i; rowprod[i] = c_0 .. c_{K-1}.
+// *zero_flag is set if some chunk's denominator product is zero (upstream panics there).
+__global__ void __launch_bounds__(128)
+chunk_quotients(const u64* __restrict__ wires, u64 wires_stride, const u64* __restrict__ sigmas,
+                u64 sigmas_stride, const u64* __restrict__ k_is, u32 num_routed, u32 max_degree,
+                unsigned log_n, u64 beta, u64 gamma, ntt::Roots R, u64* __restrict__ quot,
+                u64* __restrict__ rowprod, int* __restrict__ zero_flag) {
+  const u64 n = 1ULL << log_n;
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 x = log_n ? ntt::root_of<false>(R, log_n, i) : 1;
+  const u64 bx = gl::mul(beta, x);  // beta * x_i
+  const u32 K = (num_routed + max_degree - 1) / max_degree;
+  u64 num[MAX_CHUNKS], den[MAX_CHUNKS];
+#pragma unroll 1
+  for (u32 k = 0; k < K; k++) {
+    u64 pn = 1, pd = 1;
+    const u32 j1 = (k + 1) * max_degree < num_routed ? (k + 1) * max_degree : num_routed;
+#pragma unroll 1
+    for (u32 j = k * max_degree; j < j1; j++) {
+      const u64 w = gl::canon(__ldg(wires + (u64)j * wires_stride + i));
+      const u64 s = __ldg(sigmas + (u64)j * sigmas_stride + i);
+      const u64 wg = gl::add(w, gamma);
+      const u64 a = gl::add(wg, gl::mul(__ldg(k_is + j), bx));   // wire + beta k_j x + gamma
+      const u64 b = gl::add(wg, gl::mul(beta, s));               // wire + beta sigma_j + gamma
+      pn = gl::mul_lazy(pn, a);
+      pd = gl::mul_lazy(pd, b);
+    }
+    num[k] = gl::canon(pn);
+    den[k] = gl::canon(pd);
+  }
+  // Montgomery batch inversion of den[0..K): prefix products, one inversion, walk back.
+  u64 pre[MAX_CHUNKS];
+  u64 acc = 1;
+#pragma unroll 1
+  for (u32 k = 0; k < K; k++) {
+    pre[k] = acc;
+    acc = gl::mul(acc, den[k]);
+  }
+  if (acc == 0) {
+    atomicOr(zero_flag, 1);
+    return;
+  }
+  u64 inv = inv_nonzero(acc);
+  u64 row = 1;
+#pragma unroll 1
+  for (u32 k = K; k-- > 0;) {
+    const u64 dinv = gl::mul(inv, pre[k]);  // 1 / den[k]
+    inv = gl::mul(inv, den[k]);
+    num[k] = gl::mul(num[k], dinv);
+  }
+#pragma unroll 1
+  for (u32 k = 0; k < K; k++) {
+    quot[(u64)k * n + i] = num[k];
+    row = gl::mul(row, num[k]);
+  }
+  rowprod[i] = row;
+}
+
+// ---- inclusive prefix product (Goldilocks), 256 elements per CTA ----------------------------------
+constexpr int SCAN_THREADS = 256;
+__device__ __forceinline__ u64 shfl_up64(u64 v, unsigned d) {
+  const u32 lo = __shfl_up_sync(0xffffffffu, (u32)v, d), hi = __shfl_up_sync(0xffffffffu, (u32)(v >> 32), d);
+  return ((u64)hi << 32) | lo;
+}
+// data[i] <- data[first of its 256-block] * .. * data[i]; totals[block] <- product of the block
+// (elements beyond count behave as 1).
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_blocks(u64* __restrict__ data, u64 count, u64* __restrict__ totals) {
+  __shared__ u64 warp_tot[SCAN_THREADS / 32];
+  const u64 i = (u64)blockIdx.x * SCAN_THREADS + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u64 v = i < count ? data[i] : 1;
+#pragma unroll
+  for (unsigned d = 1; d < 32; d <<= 1) {
+    const u64 o = shfl_up64(v, d);
+    if (lane >= d) v = gl::mul(v, o);
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    u64 t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 1;
+#pragma unroll
+    for (unsigned d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+      const u64 o = shfl_up64(t, d);
+      if (lane >= d) t = gl::mul(t, o);
+    }
+    if (lane < SCAN_THREADS / 32) warp_tot[lane] = t;
+  }
+  __syncthreads();
+  if (warp > 0) v = gl::mul(v, warp_tot[warp - 1]);
+  if (i < count) data[i] = v;
+  if (totals && threadIdx.x == SCAN_THREADS - 1) totals[blockIdx.x] = v;
+}
+// data[i] *= scanned_totals[block - 1] for every block but the first.
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply(u64* __restrict__ data, u64 count, const u64* __restrict__ scanned_totals) {
+  const u64 i = (u64)blockIdx.x * SCAN_THREADS + threadIdx.x;
+  if (blockIdx.x == 0 || i >= count) return;
+  data[i] = gl::mul(data[i], scanned_totals[blockIdx.x - 1]);
+}
+
+// out column 0 (Z) and columns 1 .. K-1 (partial products) of one challenge; rowscan = inclusive
+// prefix product of the row products.  z_col / pp_col0: destination columns (stride n).
+__global__ void __launch_bounds__(128)
+finish_rows(const u64* __restrict__ quot, const u64* __restrict__ rowscan, unsigned log_n, u32 K,
+            u64* __restrict__ z_col, u64* __restrict__ pp_col0) {
+  const u64 n = 1ULL << log_n;
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 acc = i ? rowscan[i - 1] : 1;  // Z(x_i)
+  z_col[i] = acc;
+  for (u32 k = 0; k + 1 < K; k++) {
+    acc = gl::mul(acc, quot[(u64)k * n + i]);
+    pp_col0[(u64)k * n + i] = acc;
+  }
+}
+
+// rows_out[r][c] = leaves[bitrev(first + r * step)][c] for c < ncols: PolynomialBatch::
+// get_lde_values(first + r * step, 1) for a block of LDE indices, salt columns dropped.
+__global__ void __launch_bounds__(128)
+gather_lde_rows(const u64* __restrict__ leaves, u32 width, u32 ncols, unsigned log_m, u64 first,
+                u64 step, u64 count, u64* __restrict__ rows_out) {
+  const u64 r = blockIdx.x;
+  if (r >= count) return;
+  const u64 idx = first + r * step;
+  const u64 leaf = log_m ? (__brevll(idx) >> (64 - log_m)) : 0;
+  const u64* src = leaves + leaf * width;
+  for (u32 c = threadIdx.x; c < ncols; c += blockDim.x) rows_out[r * ncols + c] = src[c];
+}
+
+}  // namespace perm

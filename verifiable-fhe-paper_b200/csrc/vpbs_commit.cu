@@ -23,6 +23,7 @@
 #include "../../include/vpbs_commit.h"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "permutation.cuh"
 
 using gl::u32;
 using gl::u64;
@@ -69,6 +70,8 @@ struct vpbs_ctx {
   // Live resident batches of this context: vpbs_ctx_destroy frees their device buffers and orphans
   // the handles (a batch outliving its context is then inert instead of a use-after-free).
   std::set<struct vpbs_batch*> batches;
+  std::set<struct vpbs_sigmas*> sigma_sets;
+  std::set<struct vpbs_fri*> fri_chains;
 };
 
 // A commit kept in HBM (vpbs_batch_*): owns its device buffers, reads go through the context.
@@ -78,6 +81,31 @@ struct vpbs_batch {
   bool coeff_inputs = false;
   u64 *coeffs = nullptr, *leaves = nullptr, *digests = nullptr, *cap = nullptr;
   size_t coeffs_bytes = 0, leaves_bytes = 0, digests_bytes = 0, cap_bytes = 0;
+};
+
+// Sigma polynomials' values + coset shifts of one circuit, resident in HBM (vpbs_sigmas_upload).
+struct vpbs_sigmas {
+  vpbs_ctx* ctx = nullptr;
+  u32 num_routed = 0, log_n = 0;
+  u64 *sigmas = nullptr, *k_is = nullptr;  // num_routed x n column-major; num_routed
+};
+
+// FRI commit phase kept in HBM (vpbs_fri_*): the current polynomial (coefficients and coset
+// evaluations over the quadratic extension, (re, im) pairs) and the Merkle tree of every layer.
+struct vpbs_fri {
+  vpbs_ctx* ctx = nullptr;
+  u64 len = 0;             // current number of extension elements (power of two)
+  u64 shift = 0;           // current coset shift
+  u32 pending_arity_bits = 0;
+  bool layer_open = false;  // a layer has been committed and not folded yet
+  u64 *coeffs = nullptr, *values = nullptr, *scratch = nullptr;  // 2 * cap_len u64 each (+ scratch 4x)
+  u64 cap_len = 0;         // allocated extension elements
+  struct Layer {
+    u64 nleaves = 0;
+    u32 leaf_len = 0, cap_height = 0;
+    u64 *leaves = nullptr, *digests = nullptr, *cap = nullptr;
+  };
+  std::vector<Layer> layers;
 };
 
 namespace {
@@ -99,6 +127,8 @@ int fail(vpbs_ctx* ctx, int code, const std::string& msg) {
   } while (0)
 
 constexpr size_t POOL_LIMIT_BYTES = 8ULL << 30;  // at most 8 GiB parked in the pool
+int batch_alloc(vpbs_ctx* ctx, u32 ncols, u32 log_n, u32 rate_bits, u32 cap_height, bool salted,
+                bool coeff_inputs, vpbs_batch** out);
 
 cudaError_t pool_alloc(vpbs_ctx* ctx, size_t bytes, u64** out) {
   auto it = ctx->pool.find(bytes);
@@ -633,6 +663,27 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (vpbs_fri* f : ctx->fri_chains) {  // orphan, like the batches below
+    cudaFree(f->coeffs);
+    cudaFree(f->values);
+    cudaFree(f->scratch);
+    for (auto& l : f->layers) {
+      cudaFree(l.leaves);
+      cudaFree(l.digests);
+      cudaFree(l.cap);
+    }
+    f->layers.clear();
+    f->coeffs = f->values = f->scratch = nullptr;
+    f->ctx = nullptr;
+  }
+  ctx->fri_chains.clear();
+  for (vpbs_sigmas* sg : ctx->sigma_sets) {  // orphan, like the batches below
+    cudaFree(sg->sigmas);
+    cudaFree(sg->k_is);
+    sg->sigmas = sg->k_is = nullptr;
+    sg->ctx = nullptr;
+  }
+  ctx->sigma_sets.clear();
   for (vpbs_batch* b : ctx->batches) {  // orphan: the handle stays valid but holds nothing
     cudaFree(b->coeffs);
     cudaFree(b->leaves);
@@ -1289,6 +1340,208 @@ int vpbs_fri_fold(vpbs_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len, uint3
   return VPBS_OK;
 }
 
+
+// ---- FRI commit phase as one device-resident chain ------------------------------------------------------
+void vpbs_fri_destroy(vpbs_fri* f) {
+  if (!f) return;
+  if (f->ctx) {
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    f->ctx->fri_chains.erase(f);
+    cudaFree(f->coeffs);
+    cudaFree(f->values);
+    cudaFree(f->scratch);
+    for (auto& l : f->layers) {
+      cudaFree(l.leaves);
+      cudaFree(l.digests);
+      cudaFree(l.cap);
+    }
+  }
+  delete f;
+}
+
+}  // extern "C"
+
+namespace {
+// values = coeffs.coset_fft(shift) for `len` extension elements held interleaved in f->coeffs
+// (natural order in and out), through the planar two-column transform.
+int fri_evaluate(vpbs_fri* f) {
+  vpbs_ctx* ctx = f->ctx;
+  const int lg = log2_strict(f->len);
+  int rc;
+  if ((rc = ensure_roots(ctx, (unsigned)lg))) return rc;
+  const u64* scale = nullptr;
+  if ((rc = get_coset_table(ctx, (unsigned)lg, 0, f->shift, &scale))) return rc;
+  u64* planar = f->scratch;                 // 2 * len
+  u64* work = f->scratch + 2 * f->cap_len;  // 2 * len
+  u64* outp = f->scratch + 4 * f->cap_len;  // 2 * len
+  ntt::deinterleave2_pad<<<(unsigned)((f->len + 255) / 256), 256, 0, ctx->stream>>>(
+      (const ulonglong2*)f->coeffs, f->len, f->len, planar);
+  ctx->launches++;
+  if ((rc = run_transform<false>(ctx, planar, f->len, 2, (unsigned)lg, work, Out::Natural, outp, f->len, 0,
+                                 scale, 1)))
+    return rc;
+  ntt::interleave2<<<(unsigned)((f->len + 255) / 256), 256, 0, ctx->stream>>>(outp, f->len,
+                                                                            (ulonglong2*)f->values);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  return VPBS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int vpbs_fri_begin(vpbs_ctx* ctx, const uint64_t* final_poly_coeffs_ext, uint64_t ncoeffs,
+                   uint32_t rate_bits, vpbs_fri** out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!final_poly_coeffs_ext || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  *out = nullptr;
+  const int lg = log2_strict(ncoeffs);
+  if (lg < 0 || lg + (int)rate_bits > 30)
+    return fail(ctx, VPBS_ERR_ARG, "coeffs.len() must be a power of two with len << rate_bits <= 2^30");
+  vpbs_fri* f = new (std::nothrow) vpbs_fri();
+  if (!f) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
+  f->ctx = ctx;
+  f->len = f->cap_len = ncoeffs << rate_bits;
+  f->shift = gl::COSET_SHIFT;
+  cudaError_t e = cudaMalloc(&f->coeffs, f->cap_len * 16);
+  if (e == cudaSuccess) e = cudaMalloc(&f->values, f->cap_len * 16);
+  if (e == cudaSuccess) e = cudaMalloc(&f->scratch, f->cap_len * 16 * 3);
+  // [P2] PolynomialCoeffs::lde: the coefficient vector zero-padded to len << rate_bits
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->coeffs, 0, f->cap_len * 16, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(f->coeffs, final_poly_coeffs_ext, ncoeffs * 16, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(f->coeffs);
+    cudaFree(f->values);
+    cudaFree(f->scratch);
+    delete f;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? VPBS_ERR_OOM : VPBS_ERR_CUDA,
+                std::string("fri begin: ") + cudaGetErrorString(e));
+  }
+  ctx->fri_chains.insert(f);
+  if ((rc = fri_evaluate(f))) {  // lde_final_values = lde_final_poly.coset_fft(F::coset_shift())
+    vpbs_fri_destroy(f);
+    return rc;
+  }
+  *out = f;
+  return VPBS_OK;
+}
+
+int vpbs_fri_commit_layer(vpbs_fri* f, uint32_t arity_bits, uint32_t cap_height, uint64_t* cap_out) {
+  if (!f) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = f->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!cap_out) return fail(ctx, VPBS_ERR_ARG, "cap_out == NULL");
+  if (f->layer_open) return fail(ctx, VPBS_ERR_STATE, "the previous layer has not been folded yet");
+  const int lg = log2_strict(f->len);
+  if ((int)arity_bits > lg) return fail(ctx, VPBS_ERR_ARG, "arity larger than the vector");
+  const unsigned log_leaves = (unsigned)lg - arity_bits;
+  if (cap_height > log_leaves)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  vpbs_fri::Layer L;
+  L.nleaves = f->len >> arity_bits;
+  L.leaf_len = 2u << arity_bits;
+  L.cap_height = cap_height;
+  const u64 ncap = 1ULL << cap_height, ndig = 2 * (L.nleaves - ncap);
+  cudaError_t e = cudaMalloc(&L.leaves, f->len * 16);
+  if (e == cudaSuccess) e = cudaMalloc(&L.digests, ndig ? ndig * 32 : 32);
+  if (e == cudaSuccess) e = cudaMalloc(&L.cap, ncap * 32);
+  if (e != cudaSuccess) {
+    cudaFree(L.leaves);
+    cudaFree(L.digests);
+    cudaFree(L.cap);
+    return fail(ctx, VPBS_ERR_OOM, std::string("fri layer allocation: ") + cudaGetErrorString(e));
+  }
+  f->layers.push_back(L);
+  // reverse_index_bits_in_place(values) + chunking = a pure re-indexing (ntt::fri_gather_leaves)
+  ntt::fri_gather_leaves<<<(unsigned)((f->len + 255) / 256), 256, 0, ctx->stream>>>(
+      (const ulonglong2*)f->values, (unsigned)lg, (ulonglong2*)L.leaves);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  if ((rc = merkle_build(ctx, L.leaves, L.nleaves, L.leaf_len, log_leaves - cap_height, L.digests, L.cap)))
+    return rc;
+  CU(ctx, cudaMemcpyAsync(cap_out, L.cap, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));  // the challenger needs the cap before beta exists
+  f->pending_arity_bits = arity_bits;
+  f->layer_open = true;
+  return VPBS_OK;
+}
+
+int vpbs_fri_fold_layer(vpbs_fri* f, const uint64_t beta[2]) {
+  if (!f) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = f->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!beta) return fail(ctx, VPBS_ERR_ARG, "beta == NULL");
+  if (!f->layer_open) return fail(ctx, VPBS_ERR_STATE, "no committed layer to fold");
+  const u32 ab = f->pending_arity_bits;
+  const u64 out_len = f->len >> ab;
+  // coeffs' = chunks_exact(arity).map(|c| reduce_with_powers(c, beta)); written to the value buffer
+  // (free until the next evaluation) and swapped in
+  ntt::fri_fold<<<(unsigned)((out_len + 127) / 128), 128, 0, ctx->stream>>>(
+      (const ulonglong2*)f->coeffs, out_len, ab, gl::canon(beta[0]), gl::canon(beta[1]),
+      (ulonglong2*)f->values, f->scratch /* planar copy, unused here */);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  std::swap(f->coeffs, f->values);
+  f->len = out_len;
+  f->shift = gl::pow(f->shift, 1ULL << ab);  // shift = shift.exp_u64(arity)
+  f->layer_open = false;
+  return fri_evaluate(f);                    // values = coeffs.coset_fft(shift)
+}
+
+int vpbs_fri_final_poly(vpbs_fri* f, uint32_t rate_bits, uint64_t* coeffs_out) {
+  if (!f) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = f->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!coeffs_out) return fail(ctx, VPBS_ERR_ARG, "coeffs_out == NULL");
+  if (f->layer_open) return fail(ctx, VPBS_ERR_STATE, "the last layer has not been folded yet");
+  const u64 keep = f->len >> rate_bits;  // coeffs.truncate(len >> rate_bits)
+  if (keep == 0) return fail(ctx, VPBS_ERR_ARG, "rate_bits exceeds the polynomial's length");
+  CU(ctx, cudaMemcpyAsync(coeffs_out, f->coeffs, keep * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_fri_query_layer(vpbs_fri* f, uint32_t layer, const uint64_t* leaf_indices, uint64_t count,
+                         uint64_t* rows_out, uint64_t* siblings_out) {
+  if (!f) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = f->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (layer >= f->layers.size()) return fail(ctx, VPBS_ERR_ARG, "no such layer");
+  if (count == 0) return VPBS_OK;
+  if (!leaf_indices || !rows_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  const vpbs_fri::Layer& L = f->layers[layer];
+  for (uint64_t i = 0; i < count; i++)
+    if (leaf_indices[i] >= L.nleaves) return fail(ctx, VPBS_ERR_ARG, "leaf index out of range");
+  const int lg = log2_strict(L.nleaves);
+  const unsigned num_layers = (unsigned)lg - L.cap_height;
+  u64 *d_idx = nullptr, *d_rows = nullptr, *d_sib = nullptr;
+  if ((rc = arena_get(ctx, "idx", count * 8, (void**)&d_idx))) return rc;
+  if ((rc = arena_get(ctx, "rows", count * (size_t)L.leaf_len * 8, (void**)&d_rows))) return rc;
+  CU(ctx, cudaMemcpyAsync(d_idx, leaf_indices, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  merkle::gather_rows<<<(unsigned)count, 128, 0, ctx->stream>>>(L.leaves, L.leaf_len, d_idx, count, d_rows);
+  ctx->launches++;
+  CU(ctx, cudaMemcpyAsync(rows_out, d_rows, count * (size_t)L.leaf_len * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (num_layers && siblings_out) {
+    if ((rc = arena_get(ctx, "sibs", count * (size_t)num_layers * 32, (void**)&d_sib))) return rc;
+    const u64 total = count * num_layers;
+    merkle::gather_siblings<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
+        L.digests, d_idx, count, num_layers, 2 * (1ULL << num_layers) - 2, d_sib);
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(siblings_out, d_sib, count * (size_t)num_layers * 32, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  }
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
 // ---- FRI proof of work -----------------------------------------------------------------------------
 int vpbs_pow_grind(vpbs_ctx* ctx, const uint64_t state[12], uint32_t witness_pos,
                    uint32_t response_lane, uint32_t min_leading_zeros, uint64_t first_candidate,
@@ -1355,26 +1608,11 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
   if (cap_height > log_m)
     return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
   const u64 n = 1ULL << log_n, m = n << rate_bits;
-  const u32 width = ncols + (salt_cols ? VPBS_SALT_SIZE : 0);
-  const u64 ncap = 1ULL << cap_height, ndig = 2 * (m - ncap);
-  vpbs_batch* b = new (std::nothrow) vpbs_batch();
-  if (!b) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
-  b->ctx = ctx;
-  b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
-  b->width = width;
-  b->coeff_inputs = inputs_are_coeffs != 0;
-  b->coeffs_bytes = (size_t)ncols * n * 8;
-  b->leaves_bytes = (size_t)m * width * 8;
-  b->digests_bytes = ndig ? ndig * 32 : 32;
-  b->cap_bytes = ncap * 32;
-  cudaError_t e = pool_alloc(ctx, b->coeffs_bytes, &b->coeffs);
-  if (e == cudaSuccess) e = pool_alloc(ctx, b->leaves_bytes, &b->leaves);
-  if (e == cudaSuccess) e = pool_alloc(ctx, b->digests_bytes, &b->digests);
-  if (e == cudaSuccess) e = pool_alloc(ctx, b->cap_bytes, &b->cap);
-  if (e != cudaSuccess) {
-    vpbs_batch_destroy(b);
-    return fail(ctx, VPBS_ERR_OOM, std::string("batch allocation: ") + cudaGetErrorString(e));
-  }
+  const u64 ncap = 1ULL << cap_height;
+  vpbs_batch* b = nullptr;
+  if ((rc = batch_alloc(ctx, ncols, log_n, rate_bits, cap_height, salt_cols != nullptr,
+                        inputs_are_coeffs != 0, &b)))
+    return rc;
   u64 *din = nullptr, *dsa = nullptr;
   if ((rc = arena_get(ctx, "in", (size_t)ncols * n * 8, (void**)&din)) ||
       (salt_cols && (rc = arena_get(ctx, "salt", (size_t)4 * m * 8, (void**)&dsa)))) {
@@ -1450,8 +1688,316 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
     cudaEventElapsedTime(&stats->d2h_ms, e2, e3);
     cudaEventElapsedTime(&stats->total_ms, e0, e3);
   }
-  ctx->batches.insert(b);
   *out = b;
+  return VPBS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// A new batch handle with its four device buffers (from the context's pool).
+int batch_alloc(vpbs_ctx* ctx, u32 ncols, u32 log_n, u32 rate_bits, u32 cap_height, bool salted,
+                bool coeff_inputs, vpbs_batch** out) {
+  const u64 n = 1ULL << log_n, m = n << rate_bits;
+  const u32 width = ncols + (salted ? VPBS_SALT_SIZE : 0);
+  const u64 ncap = 1ULL << cap_height, ndig = 2 * (m - ncap);
+  vpbs_batch* b = new (std::nothrow) vpbs_batch();
+  if (!b) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
+  b->ctx = ctx;
+  b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+  b->width = width;
+  b->coeff_inputs = coeff_inputs;
+  b->coeffs_bytes = (size_t)ncols * n * 8;
+  b->leaves_bytes = (size_t)m * width * 8;
+  b->digests_bytes = ndig ? ndig * 32 : 32;
+  b->cap_bytes = ncap * 32;
+  ctx->batches.insert(b);
+  cudaError_t e = pool_alloc(ctx, b->coeffs_bytes, &b->coeffs);
+  if (e == cudaSuccess) e = pool_alloc(ctx, b->leaves_bytes, &b->leaves);
+  if (e == cudaSuccess) e = pool_alloc(ctx, b->digests_bytes, &b->digests);
+  if (e == cudaSuccess) e = pool_alloc(ctx, b->cap_bytes, &b->cap);
+  if (e != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, VPBS_ERR_OOM, std::string("batch allocation: ") + cudaGetErrorString(e));
+  }
+  *out = b;
+  return VPBS_OK;
+}
+
+// Inclusive prefix product of data[0..count) in place (perm::scan_blocks recursion).
+int prefix_product(vpbs_ctx* ctx, u64* data, u64 count, u64* scratch) {
+  const u64 nblocks = (count + perm::SCAN_THREADS - 1) / perm::SCAN_THREADS;
+  perm::scan_blocks<<<(unsigned)nblocks, perm::SCAN_THREADS, 0, ctx->stream>>>(
+      data, count, nblocks > 1 ? scratch : nullptr);
+  ctx->launches++;
+  if (nblocks > 1) {
+    int rc = prefix_product(ctx, scratch, nblocks, scratch + nblocks);
+    if (rc) return rc;
+    perm::scan_apply<<<(unsigned)nblocks, perm::SCAN_THREADS, 0, ctx->stream>>>(data, count, scratch);
+    ctx->launches++;
+  }
+  CU(ctx, cudaGetLastError());
+  return VPBS_OK;
+}
+
+// Z and partial products of every challenge on device data, written in commit order into d_out
+// (num_challenges * K columns of n): Z_0 .. Z_{c-1}, then the K - 1 partial products of each
+// challenge.  d_wires / d_sigmas column-major with the given strides.
+int zs_core(vpbs_ctx* ctx, const u64* d_wires, u64 wires_stride, const u64* d_sigmas, const u64* d_kis,
+            u32 num_routed, u32 log_n, u32 max_degree, const uint64_t* betas, const uint64_t* gammas,
+            u32 num_challenges, u64* d_out) {
+  const u64 n = 1ULL << log_n;
+  const u32 K = (num_routed + max_degree - 1) / max_degree;
+  int rc;
+  u64 *quot = nullptr, *rowprod = nullptr;
+  int* flag = nullptr;
+  if ((rc = arena_get(ctx, "zs_quot", (size_t)K * n * 8, (void**)&quot))) return rc;
+  // row products + the scan's block totals of every level (n/256 + n/256^2 + ... < n/128)
+  if ((rc = arena_get(ctx, "zs_rows", (size_t)(n + n / 128 + 512) * 8, (void**)&rowprod))) return rc;
+  if ((rc = arena_get(ctx, "zs_flag", sizeof(int), (void**)&flag))) return rc;
+  if ((rc = ensure_roots(ctx, log_n))) return rc;
+  const ntt::Roots R{ctx->roots, ctx->roots_log};
+  CU(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  for (u32 c = 0; c < num_challenges; c++) {
+    perm::chunk_quotients<<<grid, 128, 0, ctx->stream>>>(
+        d_wires, wires_stride, d_sigmas, n, d_kis, num_routed, max_degree, log_n,
+        gl::canon(betas[c]), gl::canon(gammas[c]), R, quot, rowprod, flag);
+    ctx->launches++;
+    if ((rc = prefix_product(ctx, rowprod, n, rowprod + n))) return rc;
+    perm::finish_rows<<<grid, 128, 0, ctx->stream>>>(
+        quot, rowprod, log_n, K, d_out + (u64)c * n,
+        d_out + ((u64)num_challenges + (u64)c * (K - 1)) * n);
+    ctx->launches++;
+  }
+  CU(ctx, cudaGetLastError());
+  int h_flag = 0;
+  CU(ctx, cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_flag)
+    return fail(ctx, VPBS_ERR_ARG,
+                "a permutation denominator is zero (plonky2's batch_multiplicative_inverse panics)");
+  return VPBS_OK;
+}
+
+int check_zs_args(vpbs_ctx* ctx, u32 num_routed, u32 log_n, u32 max_degree, u32 num_challenges,
+                  const void* betas, const void* gammas) {
+  if (!betas || !gammas || num_routed == 0 || num_challenges == 0)
+    return fail(ctx, VPBS_ERR_ARG, "null pointer, num_routed == 0 or num_challenges == 0");
+  if (max_degree < 2) return fail(ctx, VPBS_ERR_ARG, "max_degree must be at least 2");
+  if (log_n > 30) return fail(ctx, VPBS_ERR_ARG, "log_n > 30");
+  if ((num_routed + max_degree - 1) / max_degree > (u32)perm::MAX_CHUNKS)
+    return fail(ctx, VPBS_ERR_ARG, "more than 32 chunks of routed wires per row");
+  return VPBS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// ---- permutation argument: Z and partial products ------------------------------------------------------
+int vpbs_sigmas_upload(vpbs_ctx* ctx, const uint64_t* const* sigma_cols, const uint64_t* k_is,
+                       uint32_t num_routed, uint32_t log_n, vpbs_sigmas** out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!sigma_cols || !k_is || !out || num_routed == 0)
+    return fail(ctx, VPBS_ERR_ARG, "null pointer or num_routed == 0");
+  if (log_n > 30) return fail(ctx, VPBS_ERR_ARG, "log_n > 30");
+  *out = nullptr;
+  const u64 n = 1ULL << log_n;
+  vpbs_sigmas* sg = new (std::nothrow) vpbs_sigmas();
+  if (!sg) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
+  sg->ctx = ctx;
+  sg->num_routed = num_routed;
+  sg->log_n = log_n;
+  cudaError_t e = cudaMalloc(&sg->sigmas, (size_t)num_routed * n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&sg->k_is, (size_t)num_routed * 8);
+  std::vector<u64> kc(num_routed);
+  for (u32 j = 0; j < num_routed; j++) kc[j] = gl::canon(k_is[j]);
+  for (u32 j = 0; j < num_routed && e == cudaSuccess; j++) {
+    if (!sigma_cols[j]) e = cudaErrorInvalidValue;
+    else e = cudaMemcpyAsync(sg->sigmas + (u64)j * n, sigma_cols[j], n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(sg->k_is, kc.data(), (size_t)num_routed * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(sg->sigmas);
+    cudaFree(sg->k_is);
+    delete sg;
+    return fail(ctx, e == cudaErrorInvalidValue ? VPBS_ERR_ARG : e == cudaErrorMemoryAllocation ? VPBS_ERR_OOM : VPBS_ERR_CUDA,
+                std::string("sigmas upload: ") + cudaGetErrorString(e));
+  }
+  ctx->sigma_sets.insert(sg);
+  *out = sg;
+  return VPBS_OK;
+}
+
+void vpbs_sigmas_destroy(vpbs_sigmas* sg) {
+  if (!sg) return;
+  if (sg->ctx) {
+    cudaSetDevice(sg->ctx->device);
+    cudaStreamSynchronize(sg->ctx->stream);
+    sg->ctx->sigma_sets.erase(sg);
+    cudaFree(sg->sigmas);
+    cudaFree(sg->k_is);
+  }
+  delete sg;
+}
+
+int vpbs_zs_partial_products(vpbs_ctx* ctx, const uint64_t* const* wire_cols,
+                             const vpbs_sigmas* sigmas, uint32_t max_degree, const uint64_t* betas,
+                             const uint64_t* gammas, uint32_t num_challenges,
+                             uint64_t* const* cols_out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!sigmas || sigmas->ctx != ctx) return fail(ctx, VPBS_ERR_STATE, "sigmas handle does not belong to this context");
+  if (!wire_cols || !cols_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  const u32 nr = sigmas->num_routed, log_n = sigmas->log_n;
+  if ((rc = check_zs_args(ctx, nr, log_n, max_degree, num_challenges, betas, gammas))) return rc;
+  const u64 n = 1ULL << log_n;
+  const u32 K = (nr + max_degree - 1) / max_degree, ncols_out = num_challenges * K;
+  u64 *dw = nullptr, *dout = nullptr;
+  if ((rc = arena_get(ctx, "in", (size_t)nr * n * 8, (void**)&dw))) return rc;
+  if ((rc = arena_get(ctx, "zs_out", (size_t)ncols_out * n * 8, (void**)&dout))) return rc;
+  for (u32 j = 0; j < nr; j++) {
+    if (!wire_cols[j]) return fail(ctx, VPBS_ERR_ARG, "wire_cols[j] == NULL");
+    CU(ctx, cudaMemcpyAsync(dw + (u64)j * n, wire_cols[j], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if ((rc = zs_core(ctx, dw, n, sigmas->sigmas, sigmas->k_is, nr, log_n, max_degree, betas, gammas,
+                    num_challenges, dout)))
+    return rc;
+  for (u32 c = 0; c < ncols_out; c++)
+    if (cols_out[c])
+      CU(ctx, cudaMemcpyAsync(cols_out[c], dout + (u64)c * n, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas, uint32_t max_degree,
+                                   const uint64_t* betas, const uint64_t* gammas,
+                                   uint32_t num_challenges, uint32_t rate_bits, uint32_t cap_height,
+                                   uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {
+  if (!wires) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = wires->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!sigmas || sigmas->ctx != ctx) return fail(ctx, VPBS_ERR_STATE, "sigmas handle does not belong to this context");
+  if (!cap_out || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  *out = nullptr;
+  const u32 nr = sigmas->num_routed, log_n = sigmas->log_n;
+  if (wires->log_n != log_n || wires->ncols < nr)
+    return fail(ctx, VPBS_ERR_ARG, "wires batch does not match the sigmas (degree or routed wires)");
+  if ((rc = check_zs_args(ctx, nr, log_n, max_degree, num_challenges, betas, gammas))) return rc;
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  if (cap_height > log_n + rate_bits)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  const u64 n = 1ULL << log_n;
+  const u32 K = (nr + max_degree - 1) / max_degree, ncols_out = num_challenges * K;
+  const uint64_t l0 = ctx->launches;
+  cudaEvent_t e0 = ctx->ev[4], e3 = ctx->ev[7];
+  if (stats) cudaEventRecord(e0, ctx->stream);
+  // routed wire VALUES over the subgroup = forward transform of the batch's coefficients (exact)
+  u64 *dvals = nullptr, *dwork = nullptr, *dout = nullptr;
+  if ((rc = arena_get(ctx, "in", (size_t)nr * n * 8, (void**)&dvals))) return rc;
+  if ((rc = arena_get(ctx, "work", (size_t)nr * n * 8, (void**)&dwork))) return rc;
+  if ((rc = arena_get(ctx, "zs_out", (size_t)ncols_out * n * 8, (void**)&dout))) return rc;
+  if ((rc = ensure_roots(ctx, log_n + rate_bits))) return rc;
+  if ((rc = run_transform<false>(ctx, wires->coeffs, n, nr, log_n, dwork, Out::Natural, dvals, n, 0,
+                                 nullptr, 1)))
+    return rc;
+  if ((rc = zs_core(ctx, dvals, n, sigmas->sigmas, sigmas->k_is, nr, log_n, max_degree, betas, gammas,
+                    num_challenges, dout)))
+    return rc;
+  vpbs_batch* b = nullptr;
+  if ((rc = batch_alloc(ctx, ncols_out, log_n, rate_bits, cap_height, false, false, &b))) return rc;
+  Timer tm{ctx, stats != nullptr};
+  rc = commit_core(ctx, dout, ncols_out, log_n, rate_bits, cap_height, 0, nullptr, 0, n << rate_bits,
+                   b->coeffs, b->leaves, b->digests, b->cap, &tm);
+  if (rc) {
+    vpbs_batch_destroy(b);
+    return rc;
+  }
+  cudaError_t ce = cudaMemcpyAsync(cap_out, b->cap, b->cap_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (stats) cudaEventRecord(e3, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, VPBS_ERR_CUDA, std::string("zs batch commit: ") + cudaGetErrorString(ce));
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    fill_stats(stats, tm, ctx->launches - l0);
+    cudaEventElapsedTime(&stats->total_ms, e0, e3);
+  }
+  *out = b;
+  return VPBS_OK;
+}
+
+int vpbs_batch_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
+                          uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
+                          uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!d_cols || ncols == 0 || !cap_out || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer or ncols == 0");
+  *out = nullptr;
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  if (cap_height > log_n + rate_bits)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  vpbs_batch* b = nullptr;
+  if ((rc = batch_alloc(ctx, ncols, log_n, rate_bits, cap_height, false, inputs_are_coeffs != 0, &b)))
+    return rc;
+  const uint64_t l0 = ctx->launches;
+  Timer tm{ctx, stats != nullptr};
+  rc = commit_core(ctx, d_cols, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, nullptr, 0,
+                   1ULL << (log_n + rate_bits), b->coeffs, b->leaves, b->digests, b->cap, &tm);
+  if (rc) {
+    vpbs_batch_destroy(b);
+    return rc;
+  }
+  cudaError_t ce = cudaMemcpyAsync(cap_out, b->cap, b->cap_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, VPBS_ERR_CUDA, std::string("batch commit: ") + cudaGetErrorString(ce));
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    fill_stats(stats, tm, ctx->launches - l0);
+    stats->total_ms = tm.ms(0, 3);
+  }
+  *out = b;
+  return VPBS_OK;
+}
+
+int vpbs_batch_get_lde_rows(vpbs_batch* b, uint64_t first_index, uint64_t step, uint64_t count,
+                            uint64_t* rows_out) {
+  if (!b) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = b->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (count == 0) return VPBS_OK;
+  if (!rows_out) return fail(ctx, VPBS_ERR_ARG, "rows_out == NULL");
+  const unsigned log_m = b->log_n + b->rate_bits;
+  const u64 m = 1ULL << log_m;
+  if (step == 0 || first_index >= m || (count - 1) > (m - 1 - first_index) / step)
+    return fail(ctx, VPBS_ERR_ARG, "LDE index range out of bounds");
+  u64* d_rows = nullptr;
+  const size_t bytes = count * (size_t)b->ncols * 8;
+  // pulled in pieces of at most 64 Ki rows through the context's staging buffer
+  const u64 piece = 1ULL << 16;
+  if ((rc = arena_get(ctx, "rows", (size_t)(count < piece ? count : piece) * b->ncols * 8, (void**)&d_rows)))
+    return rc;
+  (void)bytes;
+  for (u64 off = 0; off < count; off += piece) {
+    const u64 cnt = count - off < piece ? count - off : piece;
+    perm::gather_lde_rows<<<(unsigned)cnt, 128, 0, ctx->stream>>>(
+        b->leaves, b->width, b->ncols, log_m, first_index + off * step, step, cnt, d_rows);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(rows_out + off * b->ncols, d_rows, (size_t)cnt * b->ncols * 8,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return VPBS_OK;
 }
 

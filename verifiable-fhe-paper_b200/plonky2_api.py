@@ -251,6 +251,59 @@ def fri_fold(coeffs_ext, arity_bits: int, beta, shift_next: int, ctx: Optional[C
     return co, vo
 
 
+class FriCommitPhase:
+    """[P2] fri/prover.rs fri_committed_trees as one device-resident chain (vpbs_fri_*): the
+    polynomial and every layer's tree stay in HBM; the caller (the challenger) sees caps and supplies
+    betas.  final_poly_coeffs: (ncoeffs, 2) extension coefficients, not yet padded."""
+
+    def __init__(self, final_poly_coeffs, rate_bits: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        c = _as_u64(final_poly_coeffs).reshape(-1, 2)
+        log2_strict(c.shape[0])
+        self.rate_bits = rate_bits
+        self.len = c.shape[0] << rate_bits
+        self.layers = []  # (nleaves, arity_bits, cap_height)
+        self.handle = ctypes.c_void_p()
+        self.ctx.check(self.ctx.lib.vpbs_fri_begin(self.ctx.handle, _ptr(c), c.shape[0], rate_bits,
+                                                   ctypes.byref(self.handle)))
+
+    def commit_layer(self, arity_bits: int, cap_height: int) -> np.ndarray:
+        cap = np.empty((1 << cap_height, 4), np.uint64)
+        self.ctx.check(self.ctx.lib.vpbs_fri_commit_layer(self.handle, arity_bits, cap_height, _ptr(cap)))
+        self.layers.append((self.len >> arity_bits, arity_bits, cap_height))
+        return cap
+
+    def fold(self, beta):
+        self.ctx.check(self.ctx.lib.vpbs_fri_fold_layer(self.handle, _ptr(_as_u64(beta).reshape(2))))
+        self.len >>= self.layers[-1][1]
+
+    def final_poly(self) -> np.ndarray:
+        out = np.empty((self.len >> self.rate_bits, 2), np.uint64)
+        self.ctx.check(self.ctx.lib.vpbs_fri_final_poly(self.handle, self.rate_bits, _ptr(out)))
+        return out
+
+    def query(self, layer: int, leaf_indices):
+        """(rows (count, 2 << arity_bits), siblings (count, layers, 4)) of one layer's tree."""
+        nleaves, arity_bits, cap_height = self.layers[layer]
+        idx = _as_u64(leaf_indices).reshape(-1)
+        rows = np.empty((idx.size, 2 << arity_bits), np.uint64)
+        sib = np.empty((idx.size, log2_strict(nleaves) - cap_height, 4), np.uint64)
+        self.ctx.check(self.ctx.lib.vpbs_fri_query_layer(self.handle, layer, _ptr(idx), idx.size, _ptr(rows),
+                                                         _ptr(sib) if sib.size else None))
+        return rows, sib
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.vpbs_fri_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def fri_proof_of_work(state, witness_pos: int, min_leading_zeros: int, first_candidate: int = 0,
                       count: int = 1 << 32, response_lane: int = 7, ctx: Optional[Context] = None):
     """[P2] fri/prover.rs fri_proof_of_work on a duplex state: smallest witness in
@@ -495,6 +548,14 @@ class ResidentPolynomialBatch:
         self.ctx.check(self.ctx.lib.vpbs_batch_eval_ext2(self.handle, _ptr(pts), pts.shape[0], _ptr(out)))
         return out
 
+    def get_lde_rows(self, first: int, step: int, count: int) -> np.ndarray:
+        """get_lde_values(first + i * step, 1) for i < count as a (count, ncols) block — what
+        [P2] plonk/prover.rs compute_quotient_polys reads (get_lde_values_packed), pulled lazily."""
+        out = np.empty((count, self.ncols), np.uint64)
+        self.ctx.check(self.ctx.lib.vpbs_batch_get_lde_rows(self.handle, first, step, count,
+                                                            _ptr(out) if count else None))
+        return out
+
     def download(self) -> "PolynomialBatch":
         """Materialise the eager form (polynomials, leaves, digests) on the host."""
         n, m = 1 << self.degree_log, 1 << (self.degree_log + self.rate_bits)
@@ -540,6 +601,98 @@ def commit_resident(cols, rate_bits: int, blinding: bool, cap_height: int,
                                         int(inputs_are_coeffs), saltp, _ptr(cap),
                                         ctypes.byref(handle), ctypes.byref(st)))
     return ResidentPolynomialBatch(ctx, handle, cap, ncols, log_n, rate_bits, blinding, st.as_dict())
+
+
+def commit_resident_device(ctx: Context, d_cols: int, ncols: int, log_n: int, rate_bits: int,
+                           cap_height: int, inputs_are_coeffs: bool = False) -> ResidentPolynomialBatch:
+    """vpbs_batch_commit_dev: a resident batch from columns that are already in HBM."""
+    cap = np.empty((1 << cap_height, 4), np.uint64)
+    handle = ctypes.c_void_p()
+    st = VpbsStats()
+    ctx.check(ctx.lib.vpbs_batch_commit_dev(ctx.handle, d_cols, ncols, log_n, rate_bits, cap_height,
+                                            int(inputs_are_coeffs), _ptr(cap), ctypes.byref(handle),
+                                            ctypes.byref(st)))
+    return ResidentPolynomialBatch(ctx, handle, cap, ncols, log_n, rate_bits, False, st.as_dict())
+
+
+# ----------------------------------------------------------------------------- plonk/prover.rs
+def get_unique_coset_shifts(subgroup_size: int, num_shifts: int) -> np.ndarray:
+    """[P2] plonky2_field/src/cosets.rs get_unique_coset_shifts: g^0 .. g^(num_shifts-1), g = 7
+    (CommonCircuitData.k_is)."""
+    log2_strict(subgroup_size)
+    out, x = [], 1
+    for _ in range(num_shifts):
+        out.append(x)
+        x = x * COSET_SHIFT % P
+    return np.array(out, dtype=np.uint64)
+
+
+class Sigmas:
+    """The sigma polynomials' values and the coset shifts k_is of one circuit, resident in HBM
+    (vpbs_sigmas_upload): constant per circuit, uploaded once."""
+
+    def __init__(self, sigma_cols, k_is, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        a, k = _as_u64(sigma_cols), _as_u64(k_is).reshape(-1)
+        if a.ndim != 2 or a.shape[0] != k.size or a.shape[0] == 0:
+            raise ValueError("sigma_cols must be (num_routed, n) with one k_i per routed wire")
+        self.num_routed, n = a.shape
+        self.degree_bits = log2_strict(n)
+        colp = (u64p * self.num_routed)(*[_ptr(a[j]) for j in range(self.num_routed)])
+        self.handle = ctypes.c_void_p()
+        self.ctx.check(self.ctx.lib.vpbs_sigmas_upload(self.ctx.handle, colp, _ptr(k), self.num_routed,
+                                                       self.degree_bits, ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.vpbs_sigmas_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def all_wires_permutation_partial_products(wire_cols, sigmas: Sigmas, betas, gammas,
+                                           max_degree: int) -> np.ndarray:
+    """[P2] plonk/prover.rs all_wires_permutation_partial_products, returned in the order prove()
+    commits the columns: (num_challenges * K, n) = [Z_0 .. Z_{C-1}, partial products of challenge 0,
+    of challenge 1, ...].  wire_cols: (num_routed, n) with wire_cols[j][i] = witness.get_wire(i, j)."""
+    ctx = sigmas.ctx
+    w = _as_u64(wire_cols)
+    b, g = _as_u64(betas).reshape(-1), _as_u64(gammas).reshape(-1)
+    if w.shape != (sigmas.num_routed, 1 << sigmas.degree_bits) or b.size != g.size or b.size == 0:
+        raise ValueError("wire_cols must be (num_routed, n); one gamma per beta")
+    if max_degree < 2:
+        raise ValueError("max_degree must be at least 2")
+    K = -(-sigmas.num_routed // max_degree)
+    out = np.empty((b.size * K, w.shape[1]), np.uint64)
+    wp = (u64p * w.shape[0])(*[_ptr(w[j]) for j in range(w.shape[0])])
+    op = (u64p * out.shape[0])(*[_ptr(out[c]) for c in range(out.shape[0])])
+    ctx.check(ctx.lib.vpbs_zs_partial_products(ctx.handle, wp, sigmas.handle, max_degree, _ptr(b),
+                                               _ptr(g), b.size, op))
+    return out
+
+
+def commit_zs_partial_products(wires: ResidentPolynomialBatch, sigmas: Sigmas, betas, gammas,
+                               max_degree: int, rate_bits: int, cap_height: int) -> ResidentPolynomialBatch:
+    """prove() steps 4-5 on the device: Z and partial products from the resident wires batch,
+    committed at once as a new resident batch (vpbs_batch_zs_partial_products)."""
+    ctx = wires.ctx
+    b, g = _as_u64(betas).reshape(-1), _as_u64(gammas).reshape(-1)
+    if b.size != g.size or b.size == 0:
+        raise ValueError("one gamma per beta")
+    K = -(-sigmas.num_routed // max_degree)
+    cap = np.empty((1 << cap_height, 4), np.uint64)
+    handle = ctypes.c_void_p()
+    st = VpbsStats()
+    ctx.check(ctx.lib.vpbs_batch_zs_partial_products(wires.handle, sigmas.handle, max_degree, _ptr(b),
+                                                     _ptr(g), b.size, rate_bits, cap_height, _ptr(cap),
+                                                     ctypes.byref(handle), ctypes.byref(st)))
+    return ResidentPolynomialBatch(ctx, handle, cap, b.size * K, wires.degree_log, rate_bits, False,
+                                   st.as_dict())
 
 
 # ----------------------------------------------------------------------------- device-resident

@@ -1,3 +1,9 @@
+// MEASURED ALTERNATIVES — not part of the product.  Round-1 form of csrc/gl64.cuh with every compile-time
+// variant DESIGN.md quotes a measurement for (Goldilocks arithmetic): -DVPBS_MUL_C, -DVPBS_ADDSUB_C, -DVPBS_CANON_C,
+// -DVPBS_MDS_INT32, -DVPBS_MDS_FP64_DENSE, -DVPBS_SBOX_REDUCED, -DVPBS_SBOX_OUTLINE, -DVPBS_SBOX_CALL4,
+// -DVPBS_NO_PIPE_INTERLEAVE, -DVPBS_HALF_I2F.  Build a tool against them with
+//   nvcc ... -I tools/variants -I csrc tools/selftest.cu   (this directory first)
+// tests/test_abi_and_host.py keeps them compiling; tools/selftest.cu checks them bit for bit on a GPU.
 // gl64.cuh — Goldilocks field (p = 2^64 - 2^32 + 1) on 32-bit integer lanes, sm_100a.
 //
 // Replaces [P2] plonky2_field 0.2.0 src/goldilocks_field.rs (GoldilocksField add/sub/mul/
@@ -19,7 +25,7 @@ constexpr u64 EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 // wrapped sum is x - p: on the device that is IADD3 + IADD3.X + 2 SEL on the carry predicate (the
 // compare-based C form costs 6 instructions).
 __host__ __device__ __forceinline__ u64 canon(u64 x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(VPBS_CANON_C)
   u32 r0, r1;
   asm("{\n\t"
       ".reg .u32 x0, x1, t0, t1, c;\n\t"
@@ -43,6 +49,7 @@ __host__ __device__ __forceinline__ u64 canon(u64 x) {
 // a + b, a any u64, b canonical.  Result any u64 (not necessarily canonical).
 // One wrap only: b < p bounds the wrapped sum below p - 1, so adding 2^64 mod p = 2^32 - 1 fits.
 __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
+#if !defined(VPBS_ADDSUB_C)
   u32 r0, r1;
   asm("{\n\t"
       ".reg .u32 a0, a1, b0, b1, l, h, c, h2;\n\t"
@@ -58,10 +65,15 @@ __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) {
       : "=r"(r0), "=r"(r1)
       : "l"(a), "l"(b));
   return ((u64)r1 << 32) | r0;
+#else
+  u64 s = a + b;
+  return s < a ? s + EPS : s;
+#endif
 }
 // a - b, a any u64, b canonical.  Result any u64.
 // One wrap only: b < p keeps the wrapped difference >= 2^32 - 1.
 __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) {
+#if !defined(VPBS_ADDSUB_C)
   u32 r0, r1;
   asm("{\n\t"
       ".reg .u32 a0, a1, b0, b1, l, h, bm;\n\t"
@@ -76,6 +88,10 @@ __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) {
       : "=r"(r0), "=r"(r1)
       : "l"(a), "l"(b));
   return ((u64)r1 << 32) | r0;
+#else
+  u64 d = a - b;
+  return a < b ? d - EPS : d;
+#endif
 }
 // a + b, both canonical, canonical result.
 __host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {
@@ -117,26 +133,39 @@ __host__ __device__ __forceinline__ void sqr_wide(u64 a, u64& lo, u64& hi) {
 }
 // Products of arbitrary u64 operands; result arbitrary u64.
 //
-// Device sequence (16 SASS instructions; the first version, a chain of mad.wide with carry fix-ups
-// after each reduce128 step, needed 26, the second — four mul.wide.u32 summed carry-save in PTX — 18):
-//   * the 128-bit product is written as `unsigned __int128` arithmetic: ptxas then uses the 64-bit
-//     addend, the carry-out predicate and the carry-in (.X) form of IMAD.WIDE.U32, which PTX cannot
-//     express — 4 IMAD.WIDE.U32 + IMAD.X + IMAD.MOV + IADD3 = 7 instructions for (p0, s1, u, h1),
-//     only one of them on the ALU pipe (the PTX carry-save form: 4 + 6, all six on the ALU pipe,
-//     the pipe that bounds Poseidon's full rounds and the NTT butterflies);
-//   * product = p0 + s1 2^32 + u 2^64 + h1 2^96 == p0 + s1 2^32 + u (2^32 - 1) - h1     (mod p)
-//             = p0 - (u + h1) + (s1 + u) 2^32
-//     (v, cv) = s1 + u; the carry is worth 2^64 == 2^32 - 1: v' = v + cv (cannot wrap: cv = 1 means
-//               v <= 2^32 - 2) and w = u + h1 + cv (33 bits: w, cw)
-//     r = (p0, v') - (w, cw); on borrow the wrapped value is >= 2^64 - 2^33, and r - (2^32 - 1)
-//     is the representative.  One carry flag feeds two consumers (addc without .cc leaves CC.CF
-//     alone); 9 SASS instructions.
-__device__ __forceinline__ u64 reduce_words(u64 lo, u64 hi) {
+// Device sequence (4 IMAD.WIDE.U32 + 14 integer instructions in SASS; the first version, a chain
+// of mad.wide with carry fix-ups after each reduce128 step, needed 4 + 22):
+//   p = a0 b0, x = a0 b1, y = a1 b0, z = a1 b1                     (32x32 -> 64 each)
+//   (t0, t1, t2) = x + y                                           65-bit sum of the cross terms
+//   (s1, u, h1)  = (t0, t1, t2) + (p1, z0, z1)                     product = (p0, s1, u, h1)
+//   product = p0 + s1 2^32 + u 2^64 + h1 2^96 == p0 + s1 2^32 + u (2^32 - 1) - h1     (mod p)
+//           = p0 - (u + h1) + (s1 + u) 2^32
+//   (v, cv) = s1 + u; the carry is worth 2^64 == 2^32 - 1: v' = v + cv (cannot wrap: cv = 1 means
+//             v <= 2^32 - 2) and w = u + h1 + cv (33 bits: w, cw)
+//   r = (p0, v') - (w, cw); on borrow the wrapped value is >= 2^64 - 2^33, and r - (2^32 - 1)
+//   is the representative.
+// One carry flag feeds two consumers below (addc without .cc leaves CC.CF alone).
+__host__ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__) && !defined(VPBS_MUL_C)
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
   u32 r0, r1;
   asm("{\n\t"
-      ".reg .u32 p0, s1, u, h1, v, vv, w, cw, lo, hi, bm;\n\t"
-      "mov.b64 {p0, s1}, %2;\n\t"
-      "mov.b64 {u, h1}, %3;\n\t"
+      ".reg .u32 p0, p1, x0, x1, y0, y1, z0, z1, t0, t1, t2, s1, u, h1, v, vv, w, cw, lo, hi, bm;\n\t"
+      ".reg .u64 q;\n\t"
+      "mul.wide.u32 q, %2, %4;\n\t"
+      "mov.b64 {p0, p1}, q;\n\t"
+      "mul.wide.u32 q, %2, %5;\n\t"
+      "mov.b64 {x0, x1}, q;\n\t"
+      "mul.wide.u32 q, %3, %4;\n\t"
+      "mov.b64 {y0, y1}, q;\n\t"
+      "mul.wide.u32 q, %3, %5;\n\t"
+      "mov.b64 {z0, z1}, q;\n\t"
+      "add.cc.u32 t0, x0, y0;\n\t"
+      "addc.cc.u32 t1, x1, y1;\n\t"
+      "addc.u32 t2, z1, 0;\n\t"      // z1 + carry of the cross sum
+      "add.cc.u32 s1, t0, p1;\n\t"
+      "addc.cc.u32 u, t1, z0;\n\t"
+      "addc.u32 h1, t2, 0;\n\t"
       "add.cc.u32 v, s1, u;\n\t"
       "addc.u32 vv, v, 0;\n\t"       // v' = v + cv
       "addc.cc.u32 w, u, h1;\n\t"    // w = u + h1 + cv (same flag)
@@ -148,13 +177,8 @@ __device__ __forceinline__ u64 reduce_words(u64 lo, u64 hi) {
       "subc.u32 %1, hi, 0;\n\t"
       "}"
       : "=r"(r0), "=r"(r1)
-      : "l"(lo), "l"(hi));
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return ((u64)r1 << 32) | r0;
-}
-__host__ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
-#if defined(__CUDA_ARCH__)
-  const unsigned __int128 r = (unsigned __int128)a * b;
-  return reduce_words((u64)r, (u64)(r >> 64));
 #else
   u64 lo, hi;
   mul_wide(a, b, lo, hi);
@@ -168,11 +192,67 @@ struct Words128 {
   u32 p0, s1, u, h1;
 };
 __device__ __forceinline__ Words128 mul_words(u64 a, u64 b) {
-  const unsigned __int128 r = (unsigned __int128)a * b;
-  const u64 lo = (u64)r, hi = (u64)(r >> 64);
-  return Words128{(u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32)};
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  Words128 w;
+  asm("{\n\t"
+      ".reg .u32 p1, x0, x1, y0, y1, z0, z1, t0, t1, t2;\n\t"
+      ".reg .u64 q;\n\t"
+      "mul.wide.u32 q, %4, %6;\n\t"
+      "mov.b64 {%0, p1}, q;\n\t"
+      "mul.wide.u32 q, %4, %7;\n\t"
+      "mov.b64 {x0, x1}, q;\n\t"
+      "mul.wide.u32 q, %5, %6;\n\t"
+      "mov.b64 {y0, y1}, q;\n\t"
+      "mul.wide.u32 q, %5, %7;\n\t"
+      "mov.b64 {z0, z1}, q;\n\t"
+      "add.cc.u32 t0, x0, y0;\n\t"
+      "addc.cc.u32 t1, x1, y1;\n\t"
+      "addc.u32 t2, z1, 0;\n\t"
+      "add.cc.u32 %1, t0, p1;\n\t"
+      "addc.cc.u32 %2, t1, z0;\n\t"
+      "addc.u32 %3, t2, 0;\n\t"
+      "}"
+      : "=r"(w.p0), "=r"(w.s1), "=r"(w.u), "=r"(w.h1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return w;
 }
-__host__ __device__ __forceinline__ u64 sqr_lazy(u64 a) { return mul_lazy(a, a); }
+// a * a: the cross product a0 a1 is formed once (3 IMAD.WIDE.U32), (t0, t1, t2) = 2 x.
+__host__ __device__ __forceinline__ u64 sqr_lazy(u64 a) {
+#if defined(__CUDA_ARCH__) && !defined(VPBS_MUL_C)
+  const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+  u32 r0, r1;
+  asm("{\n\t"
+      ".reg .u32 p0, p1, x0, x1, z0, z1, t0, t1, t2, s1, u, h1, v, vv, w, cw, lo, hi, bm;\n\t"
+      ".reg .u64 q;\n\t"
+      "mul.wide.u32 q, %2, %2;\n\t"
+      "mov.b64 {p0, p1}, q;\n\t"
+      "mul.wide.u32 q, %2, %3;\n\t"
+      "mov.b64 {x0, x1}, q;\n\t"
+      "mul.wide.u32 q, %3, %3;\n\t"
+      "mov.b64 {z0, z1}, q;\n\t"
+      "add.cc.u32 t0, x0, x0;\n\t"
+      "addc.cc.u32 t1, x1, x1;\n\t"
+      "addc.u32 t2, z1, 0;\n\t"
+      "add.cc.u32 s1, t0, p1;\n\t"
+      "addc.cc.u32 u, t1, z0;\n\t"
+      "addc.u32 h1, t2, 0;\n\t"
+      "add.cc.u32 v, s1, u;\n\t"
+      "addc.u32 vv, v, 0;\n\t"
+      "addc.cc.u32 w, u, h1;\n\t"
+      "addc.u32 cw, 0, 0;\n\t"
+      "sub.cc.u32 lo, p0, w;\n\t"
+      "subc.cc.u32 hi, vv, cw;\n\t"
+      "subc.u32 bm, 0, 0;\n\t"
+      "sub.cc.u32 %0, lo, bm;\n\t"
+      "subc.u32 %1, hi, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1));
+  return ((u64)r1 << 32) | r0;
+#else
+  return mul_lazy(a, a);
+#endif
+}
 __host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) { return canon(mul_lazy(a, b)); }
 
 __host__ __device__ inline u64 pow(u64 a, u64 e) {

@@ -1,3 +1,9 @@
+// MEASURED ALTERNATIVES — not part of the product.  Round-1 form of csrc/poseidon.cuh with every compile-time
+// variant DESIGN.md quotes a measurement for (Poseidon permutation): -DVPBS_MUL_C, -DVPBS_ADDSUB_C, -DVPBS_CANON_C,
+// -DVPBS_MDS_INT32, -DVPBS_MDS_FP64_DENSE, -DVPBS_SBOX_REDUCED, -DVPBS_SBOX_OUTLINE, -DVPBS_SBOX_CALL4,
+// -DVPBS_NO_PIPE_INTERLEAVE, -DVPBS_HALF_I2F.  Build a tool against them with
+//   nvcc ... -I tools/variants -I csrc tools/selftest.cu   (this directory first)
+// tests/test_abi_and_host.py keeps them compiling; tools/selftest.cu checks them bit for bit on a GPU.
 // poseidon.cuh — width-12 Poseidon permutation over Goldilocks, state held in registers.
 //
 // Replaces [P2] plonky2 0.2.0 src/hash/poseidon.rs (Poseidon::poseidon: 4 full + 22 partial + 4
@@ -7,14 +13,13 @@
 // natively at /root/reference/src/vtfhe/ivc_based_vpbs.rs:73.
 //
 // Design (one permutation per thread):
-//  * the 12 state words live in 24 32-bit registers; the MDS layer works on the 32-bit halves:
-//    out_r = sum_i c_i * lo(s_{i+r}) + 2^32 * sum_i c_i * hi(s_{i+r}); every sum stays below 2^42
-//    (c_i <= 41), i.e. exact in a double, so the layer is DFMA work on the FP64 pipe while the
-//    S-boxes keep the integer pipes busy.  No 64x64 multiply is spent on the linear layer.
-//  * the next round's constants are the initial value of the accumulators, so the constant layer
-//    costs no extra instructions.
-//  * S-box x^7 = (x^2 * x) * (x^2)^2: four 64x64 -> 128 products (gl64.cuh), the last one left
-//    unreduced in the full rounds.
+//  * the 12 state words live in 24 32-bit registers; the MDS layer works on the 32-bit halves
+//    directly: out_r = sum_i c_i * lo(s_{i+r}) + 2^32 * sum_i c_i * hi(s_{i+r}), each sum an
+//    IMAD.WIDE.U32 chain (c_i <= 41, so twelve terms stay below 2^42), recombined with one
+//    96-bit reduction.  No 64x64 multiply is spent on the linear layer.
+//  * the next round's constants are the initial value of those accumulators, so the constant
+//    layer costs no extra instructions.
+//  * S-box x^7 = (x^2 * x) * (x^2)^2: two squarings (3 wide products) and two multiplies (4).
 //  * state words are kept as arbitrary u64 (lazy reduction); canonicalise once on output.
 #pragma once
 #include "gl64.cuh"
@@ -104,10 +109,23 @@ __device__ __forceinline__ u64 combine_biased(double dlo, double dhi) {
 }
 
 // ---- MDS layer --------------------------------------------------------------------------------
-// The linear layer runs on the FP64 pipe as a split convolution with pair-merged partial rounds
-// (below).  What was measured against it on B200 (tools/variants/): a dense FP64
-// form (288 DFMA per layer) and a pure 32-bit integer form on 22/21/21-bit limbs, both bit-exact
-// and both slower (7.80 and 8.21 ms against 5.32 ms for 8.39 M permutations in round 1).
+// Three implementations, selected at compile time and all bit-exact (tools/selftest.cu): the
+// split-convolution FP64 form with pair-merged partial rounds (default: 5.32 ms for 8.39 M
+// permutations on B200), the dense FP64 form (-DVPBS_MDS_FP64_DENSE, 7.80 ms) and a pure 32-bit
+// integer form (-DVPBS_MDS_INT32, 8.21 ms), the last two with one linear layer per round.
+//
+// What the integer pipes cost here (tools/microbench.cu + ncu, profiles/): IMAD.WIDE.U32 runs at
+// half rate and ptxas never uses its 64-bit addend, so a 64-bit multiply-accumulate is
+// IMAD.WIDE + IADD3 + IADD3.X; every IMAD-class instruction (incl. the IMAD.X / IMAD.MOV ptxas
+// likes to emit for adds and moves) goes to the fmaheavy half of the FMA pipe, which ends up the
+// busiest unit.  The MDS constants are tiny (<= 41).  The integer form:
+//   * split every state word into limbs of 22/21/21 bits; sum_i c_i * limb_i < 2^31 fits a 32-bit
+//     accumulator and each MAC is ONE IMAD;
+//   * the matrix is circulant (+ one diagonal entry), i.e. a length-12 cyclic convolution.
+//     x^12 - 1 = (x^6 - 1)(x^6 + 1) splits it into a cyclic and a negacyclic length-6 convolution
+//     on p_t = s_t + s_{t+6} and m_t = s_t - s_{t+6}:  2 y_r = Z+_r + Z-_r, 2 y_{r+6} = Z+_r - Z-_r
+//     (72 MACs per limb instead of 144; all arithmetic is exact mod 2^32, results < 2^32);
+//   * the doubled outputs are recombined and reduced once per lane (reduce96).
 // Round constants pre-split for the accumulators: RCD[2*(12*r+i)] = 2^52 + lo32(RC),
 // RCD[2*(12*r+i)+1] = 2^52 + hi32(RC) (exact doubles; row 30 is the all-zero "no next round").
 __constant__ double RCD[2 * (ROUNDS + 1) * WIDTH] = {
@@ -119,6 +137,77 @@ __device__ const double RCD_G[2 * (ROUNDS + 1) * WIDTH] = {
 #include "poseidon_rcd.inc"
 };
 
+#ifdef VPBS_MDS_INT32
+
+// {sum, difference} of the limbs of RC[r'], RC[r'+6]: [round][limb][r'][2]; row 30 = zeros.
+__constant__ u32 RCL[(ROUNDS + 1) * 36] = {
+#include "poseidon_rcl.inc"
+};
+
+namespace mds_detail {
+constexpr int CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+__host__ __device__ constexpr int cplus(int j) { return CIRC[j] + CIRC[j + 6]; }   // 30 28 80 34 36 48
+__host__ __device__ constexpr int cminus(int j) { return CIRC[j] - CIRC[j + 6]; }  //  4  2  2 -2 -32  8
+
+// Z+_r = init + sum_j c+_j p[(j + r) mod 6];  Z-_r = init + sum_j (+-)c-_j m[(j + r) mod 6]
+template <int R, int J>
+__device__ __forceinline__ void conv(const u32 (&p)[6], const u32 (&m)[6], u32& zp, u32& zm) {
+  constexpr int T = J + R;
+  constexpr u32 CP = (u32)cplus(J);
+  constexpr u32 CM = (u32)(T < 6 ? cminus(J) : -cminus(J));
+  zp += CP * p[T % 6];
+  zm += CM * m[T % 6];
+  if constexpr (J + 1 < 6) conv<R, J + 1>(p, m, zp, zm);
+}
+template <int R>
+__device__ __forceinline__ void rows(const u32 (&p)[6], const u32 (&m)[6], const u32 (&l)[WIDTH],
+                                     const u32* __restrict__ rcl, u32 (&y2)[WIDTH]) {
+  u32 zp = rcl[2 * R], zm = rcl[2 * R + 1];
+  conv<R, 0>(p, m, zp, zm);
+  y2[R] = zp + zm;
+  y2[R + 6] = zp - zm;
+  if constexpr (R == 0) y2[0] += 16u * l[0];  // MDS_MATRIX_DIAG = [8, 0, ..., 0], doubled
+  if constexpr (R + 1 < 6) rows<R + 1>(p, m, l, rcl, y2);
+}
+// One limb plane: y2[r] = 2 * (RC_limb[r] + sum_i CIRC[i] * l[(i + r) % 12] + DIAG[r] * l[r])
+__device__ __forceinline__ void plane(const u32 (&l)[WIDTH], const u32* __restrict__ rcl,
+                                      u32 (&y2)[WIDTH]) {
+  u32 p[6], m[6];
+#pragma unroll
+  for (int t = 0; t < 6; t++) {
+    p[t] = l[t] + l[t + 6];
+    m[t] = l[t] - l[t + 6];
+  }
+  rows<0>(p, m, l, rcl, y2);
+}
+}  // namespace mds_detail
+
+// MDS layer fused with the following constant layer:
+//   s'_r = RC_next[r] + sum_i CIRC[i] * s_{(i+r) mod 12} + DIAG[r] * s_r
+// `next_round` indexes the constants added after the MDS (ROUNDS = none).
+__device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
+  u32 l0[WIDTH], l1[WIDTH], l2[WIDTH], a[WIDTH], b[WIDTH], c[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) {
+    const u32 w0 = (u32)s[i], w1 = (u32)(s[i] >> 32);
+    l0[i] = w0 & 0x3FFFFFu;                              // bits  0..21
+    l1[i] = __funnelshift_r(w0, w1, 22) & 0x1FFFFFu;     // bits 22..42
+    l2[i] = w1 >> 11;                                    // bits 43..63
+  }
+  const u32* __restrict__ rcl = RCL + 36 * next_round;
+  mds_detail::plane(l0, rcl, a);
+  mds_detail::plane(l1, rcl + 12, b);
+  mds_detail::plane(l2, rcl + 24, c);
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) {
+    // value = a/2 + (b/2) * 2^22 + (c/2) * 2^43  with a, b, c even and < 2^32
+    const u64 lo = (u64)(a[r] >> 1) + ((u64)b[r] << 21);  // < 2^54
+    const u64 hi = (u64)c[r] << 10;                       // (c/2) * 2^43 = hi * 2^32, hi < 2^42
+    s[r] = reduce96(lo, hi);
+  }
+}
+
+#else  // FP64 MDS (default)
 
 // ---- MDS layer on the FP64 pipe ---------------------------------------------------------------
 // On B200 a 64-bit integer multiply-accumulate costs three issue slots (IMAD.WIDE.U32 runs at half
@@ -132,6 +221,52 @@ __device__ const double RCD_G[2 * (ROUNDS + 1) * WIDTH] = {
 __device__ __forceinline__ double half_to_f64(u32 x) {
   return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
 }
+#ifdef VPBS_MDS_FP64_DENSE
+// Input-stationary order: for each state word (converted to doubles on the fly) update all twelve
+// output accumulators.  Consecutive DFMAs then share their multiplicand, which the register reuse
+// cache serves without a second register-file read (a DFMA with three distinct 64-bit register
+// operands needs two dispatch cycles on this part), and only one converted pair is live at a time.
+template <int J, int R>
+struct MdsCol {
+  static constexpr u32 CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  // out[R] takes in[J] with coefficient CIRC[(J - R) mod 12]; MDS_MATRIX_DIAG = [8, 0, ..., 0]
+  // only touches (row 0, lane 0) and is folded into that coefficient.
+  static constexpr double COEF =
+      (double)(CIRC[(J - R + WIDTH) % WIDTH] + ((R == 0 && J == 0) ? 8u : 0u));
+  __device__ __forceinline__ static void run(double xl, double xh, double (&al)[WIDTH],
+                                             double (&ah)[WIDTH]) {
+    al[R] = fma(xl, COEF, al[R]);
+    ah[R] = fma(xh, COEF, ah[R]);
+    if constexpr (R + 1 < WIDTH) MdsCol<J, R + 1>::run(xl, xh, al, ah);
+  }
+};
+
+template <int J>
+__device__ __forceinline__ void mds_cols(const u64 (&s)[WIDTH], double (&al)[WIDTH],
+                                         double (&ah)[WIDTH]) {
+  MdsCol<J, 0>::run(half_to_f64((u32)s[J]), half_to_f64((u32)(s[J] >> 32)), al, ah);
+  if constexpr (J + 1 < WIDTH) mds_cols<J + 1>(s, al, ah);
+}
+
+// MDS layer fused with the following constant layer:
+//   s'_r = RC_next[r] + sum_i CIRC[i] * s_{(i+r) mod 12} + DIAG[r] * s_r
+// `next_round` indexes the constants added after the MDS (ROUNDS = none).
+__device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
+  double al[WIDTH], ah[WIDTH];
+  const double* __restrict__ rcd = RCD + 2 * WIDTH * next_round;
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++) {
+    al[r] = rcd[2 * r];
+    ah[r] = rcd[2 * r + 1];
+  }
+  mds_cols<0>(s, al, ah);
+  const u64 MANT = 0x000FFFFFFFFFFFFFULL;
+#pragma unroll
+  for (int r = 0; r < WIDTH; r++)
+    s[r] = reduce96((u64)__double_as_longlong(al[r]) & MANT, (u64)__double_as_longlong(ah[r]) & MANT);
+}
+
+#else  // split-convolution FP64 MDS (default)
 
 // The MDS matrix is circulant (plus one diagonal entry), i.e. y = c (*) s is a length-12 cyclic
 // convolution.  x^12 - 1 = (x^6 - 1)(x^6 + 1) splits it into a cyclic and a negacyclic length-6
@@ -210,6 +345,16 @@ template <int T>
 __device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
   // p = x_T + x_{T+6}, m = x_T - x_{T+6} straight from the biased views: (2^52 + a) - (2^52 + b)
   // is a - b, and (2^52 + a) + ((2^52 + b) - 2^53) is a + b; every step is exact (|.| < 2^53).
+#ifdef VPBS_HALF_I2F
+  // conversion unit variant: I2F.F64.U32 issues beside the FP64 pipe (26 lanes/clk/SM measured)
+  const double al = __uint2double_rn((u32)s[T]), ah = __uint2double_rn((u32)(s[T] >> 32));
+  const double bl = __uint2double_rn((u32)s[T + 6]), bh = __uint2double_rn((u32)(s[T + 6] >> 32));
+  if constexpr (T == 0) {
+    a.x0l = al;
+    a.x0h = ah;
+  }
+  mds_split::col<T, 0>(al + bl, ah + bh, al - bl, ah - bh, a.zpl, a.zph, a.zml, a.zmh);
+#else
   const double TWO53 = 9007199254740992.0;
   const double cal = half_biased((u32)s[T]), cah = half_biased((u32)(s[T] >> 32));
   const double cbl = half_biased((u32)s[T + 6]), cbh = half_biased((u32)(s[T + 6] >> 32));
@@ -219,6 +364,7 @@ __device__ __forceinline__ void mds_absorb(MdsAcc& a, const u64 (&s)[WIDTH]) {
   }
   mds_split::col<T, 0>(cal + (cbl - TWO53), cah + (cbh - TWO53), cal - cbl, cah - cbh, a.zpl, a.zph,
                        a.zml, a.zmh);
+#endif
 }
 // The same for two state words given as unreduced 128-bit products (p0, s1, u, h1):
 //   p0 + s1 2^32 + u 2^64 + h1 2^96 == L + H 2^32 (mod p),  L = p0 - u - h1,  H = s1 + u,
@@ -294,6 +440,15 @@ __device__ __forceinline__ void col(double pl, double ph, double ml, double mh, 
 // words T and T + 6 of u into the C^2 accumulators and into row 0 of C u (xl, xh)
 template <int T>
 __device__ __forceinline__ void absorb(MdsAcc& a, const u64 (&s)[WIDTH], double& xl, double& xh) {
+#ifdef VPBS_HALF_I2F
+  const double al = __uint2double_rn((u32)s[T]), ah = __uint2double_rn((u32)(s[T] >> 32));
+  const double bl = __uint2double_rn((u32)s[T + 6]), bh = __uint2double_rn((u32)(s[T + 6] >> 32));
+  const double pl = al + bl, ph = ah + bh, ml = al - bl, mh = ah - bh;
+  if constexpr (T == 0) {
+    a.x0l = al;
+    a.x0h = ah;
+  }
+#else
   const double TWO53 = 9007199254740992.0;
   const double cal = half_biased((u32)s[T]), cah = half_biased((u32)(s[T] >> 32));
   const double cbl = half_biased((u32)s[T + 6]), cbh = half_biased((u32)(s[T + 6] >> 32));
@@ -302,6 +457,7 @@ __device__ __forceinline__ void absorb(MdsAcc& a, const u64 (&s)[WIDTH], double&
     a.x0l = cal - 4503599627370496.0;
     a.x0h = cah - 4503599627370496.0;
   }
+#endif
   constexpr double HP = mds_split::cplus(T), HM = mds_split::cminus(T);  // already halved
   xl = fma(pl, HP, fma(ml, HM, xl));
   xh = fma(ph, HP, fma(mh, HM, xh));
@@ -322,9 +478,13 @@ __device__ __forceinline__ void tie_to(u64& x, double positive) {
   asm("lop3.b32 %0, %0, %1, 0x80000000, 0xf8;" : "+r"(lo) : "r"((u32)__double2hiint(positive)));
   x = ((u64)hi << 32) | lo;
 }
+#ifndef VPBS_NO_PIPE_INTERLEAVE
 #define VPBS_TIE(x, y, acc) \
   tie_to(x, (acc).zpl[5]);  \
   tie_to(y, (acc).zph[5]);
+#else
+#define VPBS_TIE(x, y, acc)
+#endif
 
 // Partial rounds r = 4 + 2 * pair and r + 1.  In: state with RC_r added; out: state with RC_{r+2}.
 __device__ __forceinline__ void partial_pair(u64 (&s)[WIDTH], int pair) {
@@ -374,7 +534,17 @@ __device__ __forceinline__ void partial_pair(u64 (&s)[WIDTH], int pair) {
     s[r + 6] = combine_biased(d2l, d2h);
   }
 }
-// The whole layer in one call (tools/selftest.cu).
+#define VPBS_PARTIAL_PAIRS 1
+// S-boxes inline by default.  With the first modular multiply (26 SASS instructions) the inlined
+// round loop overflowed the 32 KB instruction cache and an out-of-line two-lane S-box was faster
+// (6.79 vs 7.48 ms at 2^19 x 128 leaves); with the 18-instruction multiply the inlined loop fits:
+// 5.70 ms inline, 5.79 ms with -DVPBS_SBOX_OUTLINE (calls), 5.73 ms with -DVPBS_SBOX_CALL4.
+#ifdef VPBS_SBOX_OUTLINE
+#define VPBS_SBOX_CALL 1
+#endif
+
+#define VPBS_MDS_INTERLEAVED 1
+// The whole layer in one call (tests, tools/selftest.cu).
 __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
   MdsAcc acc;
   mds_begin(acc, next_round);
@@ -387,14 +557,70 @@ __device__ __forceinline__ void mds_add_rc(u64 (&s)[WIDTH], int next_round) {
   mds_finish(acc, s);
 }
 
+#endif  // VPBS_MDS_FP64_DENSE
+#endif  // VPBS_MDS_INT32
 
-// ---- the permutation -----------------------------------------------------------------------------
-// In-place; input words arbitrary u64, output words arbitrary u64 (lazy).  The four full rounds of
-// each half share one loop body and the eleven partial-round pairs another (~27 KB of code in all),
-// which fits the 32 KB instruction cache; unrolled round bodies did not (ncu: 13 % icache misses,
-// stall_no_instruction 1.3 per issue).  Measured alternatives (out-of-line S-boxes, integer and
-// dense FP64 linear layers, reduced S-box outputs) live in tools/variants/, not here.
+// In-place permutation; input words arbitrary u64, output words arbitrary u64 (lazy).
+// One loop over the 30 rounds with a warp-uniform "full round" branch keeps a single copy of the
+// S-box and MDS code (~27 KB), which fits the 32 KB instruction cache; two unrolled round bodies
+// did not (ncu: 13 % icache misses, stall_no_instruction 1.3 per issue).
+// Two S-boxes as ONE out-of-line function: the eight full rounds call it six times each instead of
+// inlining twelve ~100-instruction S-boxes, which keeps the whole permutation (full-round loop +
+// partial-pair loop) inside the 32 KB instruction cache.  Two independent chains per call keep the
+// integer pipes fed.
+__device__ __noinline__ ulonglong2 sbox7_x2(u64 a, u64 b) {
+  return make_ulonglong2(sbox7(a), sbox7(b));
+}
+#define VPBS_SBOX2(i, j)                        \
+  {                                             \
+    const ulonglong2 v_ = sbox7_x2(s[i], s[j]); \
+    s[i] = v_.x;                                \
+    s[j] = v_.y;                                \
+  }
+
+struct Sbox4 {
+  u64 a, b, c, d;
+};
+__device__ __noinline__ Sbox4 sbox7_x4(u64 a, u64 b, u64 c, u64 d) {
+  return Sbox4{sbox7(a), sbox7(b), sbox7(c), sbox7(d)};
+}
+#define VPBS_SBOX4(i, j, k, l)                              \
+  {                                                         \
+    const Sbox4 v_ = sbox7_x4(s[i], s[j], s[k], s[l]);      \
+    s[i] = v_.a; s[j] = v_.b; s[k] = v_.c; s[l] = v_.d;     \
+  }
+
 __device__ __forceinline__ void full_round(u64 (&s)[WIDTH], int r) {
+#ifdef VPBS_SBOX_CALL4
+  MdsAcc acc;
+  mds_begin(acc, r + 1);
+  VPBS_SBOX4(0, 6, 1, 7)
+  mds_absorb<0>(acc, s);
+  mds_absorb<1>(acc, s);
+  VPBS_SBOX4(2, 8, 3, 9)
+  mds_absorb<2>(acc, s);
+  mds_absorb<3>(acc, s);
+  VPBS_SBOX4(4, 10, 5, 11)
+  mds_absorb<4>(acc, s);
+  mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+#elif defined(VPBS_SBOX_CALL)
+  MdsAcc acc;
+  mds_begin(acc, r + 1);
+  VPBS_SBOX2(0, 6)
+  mds_absorb<0>(acc, s);
+  VPBS_SBOX2(1, 7)
+  mds_absorb<1>(acc, s);
+  VPBS_SBOX2(2, 8)
+  mds_absorb<2>(acc, s);
+  VPBS_SBOX2(3, 9)
+  mds_absorb<3>(acc, s);
+  VPBS_SBOX2(4, 10)
+  mds_absorb<4>(acc, s);
+  VPBS_SBOX2(5, 11)
+  mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+#elif defined(VPBS_MDS_INTERLEAVED) && !defined(VPBS_SBOX_REDUCED)
   // S-boxes (integer pipes) and MDS accumulation (FP64 pipe) interleaved pair by pair; the last
   // product of every S-box stays unreduced (sbox7_words / mds_absorb_words).
   MdsAcc acc;
@@ -418,11 +644,35 @@ __device__ __forceinline__ void full_round(u64 (&s)[WIDTH], int r) {
     mds_absorb_words<5>(acc, a5, b5);
   }
   mds_finish(acc, s);
+#elif defined(VPBS_MDS_INTERLEAVED)
+  // S-boxes (integer pipes) and MDS accumulation (FP64 pipe) interleaved pair by pair: as soon as
+  // words t and t + 6 are final they are fed to the accumulators.
+  MdsAcc acc;
+  mds_begin(acc, r + 1);
+  s[0] = sbox7(s[0]); s[6] = sbox7(s[6]);
+  mds_absorb<0>(acc, s);
+  s[1] = sbox7(s[1]); s[7] = sbox7(s[7]);
+  mds_absorb<1>(acc, s);
+  s[2] = sbox7(s[2]); s[8] = sbox7(s[8]);
+  mds_absorb<2>(acc, s);
+  s[3] = sbox7(s[3]); s[9] = sbox7(s[9]);
+  mds_absorb<3>(acc, s);
+  s[4] = sbox7(s[4]); s[10] = sbox7(s[10]);
+  mds_absorb<4>(acc, s);
+  s[5] = sbox7(s[5]); s[11] = sbox7(s[11]);
+  mds_absorb<5>(acc, s);
+  mds_finish(acc, s);
+#else
+#pragma unroll
+  for (int i = 0; i < WIDTH; i++) s[i] = sbox7(s[i]);
+  mds_add_rc(s, r + 1);
+#endif
 }
 
 __device__ __forceinline__ void permute_lazy(u64 (&s)[WIDTH]) {
 #pragma unroll
   for (int i = 0; i < WIDTH; i++) s[i] = gl::add_lazy(s[i], RC[i]);
+#ifdef VPBS_PARTIAL_PAIRS
   // 4 full rounds, 11 pairs of partial rounds, 4 full rounds; one copy of each loop body.
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
@@ -434,6 +684,17 @@ __device__ __forceinline__ void permute_lazy(u64 (&s)[WIDTH]) {
       for (int p = 0; p < PARTIAL_ROUNDS / 2; p++) partial_pair(s, p);
     }
   }
+#else
+#pragma unroll 1
+  for (int r = 0; r < ROUNDS; r++) {
+    if (r < FULL_ROUNDS_HALF || r >= FULL_ROUNDS_HALF + PARTIAL_ROUNDS) {
+      full_round(s, r);
+    } else {
+      s[0] = sbox7(s[0]);
+      mds_add_rc(s, r + 1);
+    }
+  }
+#endif
 }
 
 // ---- latency-optimised permutation: 12 threads of a 16-thread group share one state -----------
