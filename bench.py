@@ -160,15 +160,16 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / timed
     value = n / dt
     sample = ("%d of %d steps timed (bounded to ~%ds); each step = one full 2^16x128 commit by the C "
-              "restatement of plonky2 0.2.0's CPU path (oracle/liboracle.so, OpenMP, %d threads)"
-              % (timed, args.steps, int(budget), cores))
+              "restatement of plonky2 0.2.0's CPU path (oracle/liboracle.so: OpenMP, %d threads, %d-lane "
+              "SIMD Poseidon and FFT layers)" % (timed, args.steps, int(budget), cores, B.get_simd()))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "simd_lanes": B.get_simd(),
+                         "us_per_permutation_per_core": cpu_perm_rate(B, np)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -765,8 +766,11 @@ def main():
         check("cpu_baseline.digests_match_gpu", np.array_equal(ref["digests"], h_digests))
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "one full 2^16x128 commit (%.2f s) by the C restatement of plonky2 "
-                                  "0.2.0's CPU path (oracle/liboracle.so, OpenMP); plonky2 itself "
-                                  "cannot be built here (no Rust toolchain)" % dt}
+                                  "0.2.0's CPU path (oracle/liboracle.so: OpenMP over %d threads, %d-lane "
+                                  "SIMD Poseidon and FFT layers, zero-padding layers skipped); plonky2 "
+                                  "itself cannot be built here (no Rust toolchain)" % (dt, cores, B.get_simd()),
+                        "simd_lanes": B.get_simd(),
+                        "us_per_permutation_per_core": cpu_perm_rate(B, np)}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -807,6 +811,15 @@ def main():
     if fail_checks:
         sys.stderr.write("bench.py: self-check(s) failed: %s\n" % "; ".join(fail_checks))
         sys.exit(3)
+
+
+def cpu_perm_rate(B, np):
+    """Poseidon permutations of the CPU arm on ONE core (microseconds each), for context."""
+    st = np.random.default_rng(1).integers(0, P_GL, size=(100000, 12), dtype=np.uint64)
+    B.poseidon_batch(st[:800])
+    t0 = time.perf_counter()
+    B.poseidon_batch(st)
+    return (time.perf_counter() - t0) / st.shape[0] * 1e6
 
 
 def int_peak_gimad(clocks):

@@ -21,7 +21,7 @@ _u64pp = ctypes.POINTER(_u64p)
 
 def build(force: bool = False) -> str:
     """Compile oracle.c -> liboracle.so with the recipe in oracle/Makefile."""
-    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "poseidon_simd.inc", "Makefile")]
     if force or not os.path.exists(_SO) or any(
             os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
@@ -75,6 +75,9 @@ def lib() -> ctypes.CDLL:
         L.orc_fri_fold.argtypes = [_u64p, u64, u32, _u64p, u64, _u64p, _u64p]
         L.orc_zs_partial_products.restype = ctypes.c_int
         L.orc_zs_partial_products.argtypes = [_u64pp, _u64pp, _u64p, u32, u32, u32, u64, u64, _u64p]
+        L.orc_set_simd.argtypes = [ctypes.c_int]
+        L.orc_get_simd.restype = ctypes.c_int
+        L.orc_poseidon_batch.argtypes = [_u64p, u64]
         L.orc_set_threads.argtypes = [ctypes.c_int]
         L.orc_get_threads.restype = ctypes.c_int
         _lib = L
@@ -244,3 +247,14 @@ def zs_partial_products(wires, sigmas, k_is, max_degree, beta, gamma):
     if rc != 0:
         raise ValueError("bad arguments")
     return out
+
+
+def set_simd(width): lib().orc_set_simd(int(width))
+def get_simd(): return lib().orc_get_simd()
+
+
+def poseidon_batch(states):
+    """count x 12 states through the SIMD path (4 / 8 permutations per call)."""
+    a = _arr(states).reshape(-1, 12).copy()
+    lib().orc_poseidon_batch(_p(a), a.shape[0])
+    return a

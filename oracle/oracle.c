@@ -8,6 +8,7 @@
  */
 #include "oracle.h"
 
+#include <immintrin.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -126,16 +127,88 @@ static void fft_classic(uint64_t* v, unsigned log_n, const uint64_t* roots) {
       }
   }
 }
+/* The same transform at the speed class of plonky2's packed-field fft_classic_simd: per-layer
+ * contiguous twiddles ([P2] fft_root_table), SIMD butterflies (poseidon_simd.inc fft_layer), and
+ * the first `zero_factor` layers as copies when the upper (2^zero_factor - 1)/2^zero_factor of the
+ * input is zero padding ([P2] fft_classic's r parameter).  Used when orc_get_simd() > 1; the plain
+ * loop above is its checker (tests/test_oracle_golden.py). */
+static void fft_layer_x4(uint64_t* v, uint64_t n, uint64_t half_m, const uint64_t* tw);
+static void fft_layer_x8(uint64_t* v, uint64_t n, uint64_t half_m, const uint64_t* tw);
+int orc_get_simd(void);
+static inline uint64_t brev64(uint64_t x) {
+  x = __builtin_bswap64(x);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+  x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+  return x;
+}
+/* layer_tw[lg][j] = w_{2^(lg+1)}^j, j < 2^lg, all layers in one allocation */
+static uint64_t** make_layer_roots(unsigned log_n, const uint64_t* roots) {
+  uint64_t n = 1ULL << log_n;
+  uint64_t** t = (uint64_t**)malloc(sizeof(uint64_t*) * (log_n + 1) + sizeof(uint64_t) * (n + 8));
+  uint64_t* data = (uint64_t*)(t + log_n + 1);
+  for (unsigned lg = 0; lg < log_n; lg++) {
+    t[lg] = data;
+    uint64_t half_m = 1ULL << lg, stride = n / (2 * half_m);
+    for (uint64_t j = 0; j < half_m; j++) data[j] = roots[j * stride];
+    data += half_m;
+  }
+  return t;
+}
+static void fft_fast(uint64_t* v, unsigned log_n, uint64_t* const* layer_tw, unsigned zero_factor) {
+  const uint64_t n = 1ULL << log_n;
+  const int w = orc_get_simd();
+  for (uint64_t i = 0; i < n; i++) { /* reverse_index_bits_in_place, canonicalising on the way */
+    uint64_t j = log_n ? (brev64(i) >> (64 - log_n)) : 0;
+    if (i < j) {
+      uint64_t a = canon(v[i]), b = canon(v[j]);
+      v[i] = b;
+      v[j] = a;
+    } else if (i == j) {
+      v[i] = canon(v[i]);
+    }
+  }
+  for (unsigned lg = 0; lg < log_n; lg++) {
+    const uint64_t half_m = 1ULL << lg, m = half_m << 1;
+    if (lg < zero_factor) { /* the second operand of every butterfly is zero padding */
+      for (uint64_t k = 0; k < n; k += m)
+        for (uint64_t j = 0; j < half_m; j++) v[k + half_m + j] = v[k + j];
+    } else if (w == 8 && half_m >= 8) {
+      fft_layer_x8(v, n, half_m, layer_tw[lg]);
+    } else if (w >= 4 && half_m >= 4) {
+      fft_layer_x4(v, n, half_m, layer_tw[lg]);
+    } else {
+      const uint64_t* tw = layer_tw[lg];
+      for (uint64_t k = 0; k < n; k += m)
+        for (uint64_t j = 0; j < half_m; j++) {
+          uint64_t t = mul_(tw[j], v[k + half_m + j]);
+          uint64_t u = v[k + j];
+          v[k + j] = add_(u, t);
+          v[k + half_m + j] = sub_(u, t);
+        }
+    }
+  }
+}
 void orc_fft(uint64_t* v, unsigned log_n) {
   uint64_t* roots = make_roots(log_n);
-  fft_classic(v, log_n, roots);
+  if (orc_get_simd() > 1) {
+    uint64_t** lt = make_layer_roots(log_n, roots);
+    fft_fast(v, log_n, lt, 0);
+    free(lt);
+  } else {
+    fft_classic(v, log_n, roots);
+  }
   free(roots);
 }
 /* [P2] fft.rs ifft_with_options: forward FFT, then reverse all values except the first and
  * scale by n^-1 (= F::inverse_2exp(lg n)). */
+static void ifft_finish(uint64_t* v, unsigned log_n);
 static void ifft_with_roots(uint64_t* v, unsigned log_n, const uint64_t* roots) {
-  uint64_t n = 1ULL << log_n;
   fft_classic(v, log_n, roots);
+  ifft_finish(v, log_n);
+}
+static void ifft_finish(uint64_t* v, unsigned log_n) {
+  uint64_t n = 1ULL << log_n;
   uint64_t n_inv = orc_gl_inv(n % P);
   v[0] = mul_(v[0], n_inv);
   if (n > 1) v[n / 2] = mul_(v[n / 2], n_inv);
@@ -344,6 +417,66 @@ void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
 }
 
 /* ------------------------------------------------------------------------------------------
+ * SIMD evaluation of the same permutation on 4 (AVX2) or 8 (AVX-512) states at once: the speed
+ * of the CPU arm (bench.py cpu_baseline / --impl reference); the scalar code above stays the
+ * checker.  See poseidon_simd.inc.
+ * ---------------------------------------------------------------------------------------- */
+#define VSUF4_(name) name##_x4
+#define VSUF8_(name) name##_x8
+typedef uint64_t v4u __attribute__((vector_size(32)));
+typedef uint64_t v8u __attribute__((vector_size(64)));
+#define VW 4
+#define VT v4u
+#define VMU(a, b) ((v4u)_mm256_mul_epu32((__m256i)(a), (__m256i)(b)))
+#define VSUF(name) VSUF4_(name)
+#define VTARGET __attribute__((target("avx2")))
+#include "poseidon_simd.inc"
+#undef VW
+#undef VT
+#undef VMU
+#undef VSUF
+#undef VTARGET
+#define VW 8
+#define VT v8u
+#define VMU(a, b) ((v8u)_mm512_mul_epu32((__m512i)(a), (__m512i)(b)))
+#define VSUF(name) VSUF8_(name)
+#define VTARGET __attribute__((target("avx512f,avx512dq,avx512bw,avx512vl")))
+#include "poseidon_simd.inc"
+#undef VW
+#undef VT
+#undef VMU
+#undef VSUF
+#undef VTARGET
+
+static void fft_layer_x4(uint64_t* v, uint64_t n, uint64_t half_m, const uint64_t* tw) {
+  fft_layer_impl_x4(v, n, half_m, tw);
+}
+static void fft_layer_x8(uint64_t* v, uint64_t n, uint64_t half_m, const uint64_t* tw) {
+  fft_layer_impl_x8(v, n, half_m, tw);
+}
+
+static int g_simd = 0; /* 0 = widest the CPU supports, 1 = scalar (naive checker), 4, 8 */
+void orc_set_simd(int width) { g_simd = width; }
+int orc_get_simd(void) {
+  int w = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") ? 8
+          : __builtin_cpu_supports("avx2")                                          ? 4
+                                                                                    : 1;
+  if (g_simd == 1 || (g_simd == 4 && w >= 4) || (g_simd == 8 && w >= 8)) w = g_simd;
+  return w;
+}
+/* count independent permutations (count x 12 words) through the SIMD path */
+void orc_poseidon_batch(uint64_t* states, uint64_t count) {
+  ensure_rc();
+  const int w = orc_get_simd();
+  uint64_t k = 0;
+  if (w == 8)
+    for (; k + 8 <= count; k += 8) permute_states_x8(states + 12 * k);
+  if (w >= 4)
+    for (; k + 4 <= count; k += 4) permute_states_x4(states + 12 * k);
+  for (; k < count; k++) orc_poseidon(states + 12 * k);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Merkle tree.  [P2] plonky2/src/hash/merkle_tree.rs
  * ---------------------------------------------------------------------------------------- */
 static int log2_strict(uint64_t n) {
@@ -388,6 +521,17 @@ int orc_merkle_new(const uint64_t* leaves, uint64_t nleaves, uint32_t leaf_len, 
   if (lg < 0 || (int)cap_height > lg) return -1;
   uint64_t ncap = 1ULL << cap_height;
   uint64_t num_digests = 2 * (nleaves - ncap);
+  { /* SIMD path (level by level, same digests layout); the recursion below is the checker */
+    const int w = orc_get_simd();
+    if (w == 8 && nleaves >= 8) {
+      merkle_new_x8(leaves, nleaves, leaf_len, (unsigned)lg - cap_height, digests, cap, orc_get_threads());
+      return 0;
+    }
+    if (w >= 4 && nleaves >= 4) {
+      merkle_new_x4(leaves, nleaves, leaf_len, (unsigned)lg - cap_height, digests, cap, orc_get_threads());
+      return 0;
+    }
+  }
   if (num_digests == 0) { /* tree is all cap */
 #pragma omp parallel for num_threads(orc_get_threads()) schedule(static)
     for (uint64_t k = 0; k < nleaves; k++) hash_or_noop_(leaves + k * leaf_len, leaf_len, cap + 4 * k);
@@ -459,6 +603,18 @@ int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint
   int nt = orc_get_threads();
   uint64_t* roots_n = make_roots(log_n);
   uint64_t* roots_m = make_roots(log_m);
+  const int fast = orc_get_simd() > 1;
+  uint64_t** lt_n = fast ? make_layer_roots(log_n, roots_n) : NULL;
+  uint64_t** lt_m = fast ? make_layer_roots(log_m, roots_m) : NULL;
+  uint64_t* shift_pow = NULL; /* 7^j, shared by all columns */
+  if (fast) {
+    shift_pow = (uint64_t*)malloc(sizeof(uint64_t) * n);
+    uint64_t sp = 1;
+    for (uint64_t j = 0; j < n; j++) {
+      shift_pow[j] = sp;
+      sp = mul_(sp, COSET_SHIFT);
+    }
+  }
   uint64_t* coeffs = coeffs_out ? coeffs_out : (uint64_t*)malloc(sizeof(uint64_t) * ncols * n);
   uint64_t* lde = lde_cols_out ? lde_cols_out : (uint64_t*)malloc(sizeof(uint64_t) * (uint64_t)ncols * m);
   if (!coeffs || !lde) return -2;
@@ -468,15 +624,28 @@ int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint
   for (uint32_t c = 0; c < ncols; c++) {
     uint64_t* dst = coeffs + (uint64_t)c * n;
     for (uint64_t i = 0; i < n; i++) dst[i] = canon(cols[c][i]);
-    if (!inputs_are_coeffs) ifft_with_roots(dst, log_n, roots_n);
+    if (!inputs_are_coeffs) {
+      if (fast) {
+        fft_fast(dst, log_n, lt_n, 0);
+        ifft_finish(dst, log_n);
+      } else {
+        ifft_with_roots(dst, log_n, roots_n);
+      }
+    }
   }
   /* "FFT + blinding": polynomials.par_iter().map(|p| p.lde(r).coset_fft_with_options(7, ..)) */
 #pragma omp parallel for num_threads(nt) schedule(dynamic)
   for (uint32_t c = 0; c < ncols; c++) {
     uint64_t* dst = lde + (uint64_t)c * m;
-    memcpy(dst, coeffs + (uint64_t)c * n, n * sizeof(uint64_t));
     memset(dst + n, 0, (m - n) * sizeof(uint64_t));
-    coset_fft_with_roots(dst, log_m, COSET_SHIFT, roots_m);
+    if (fast) { /* c_j * 7^j on the n non-zero coefficients, then the transform minus its copy layers */
+      const uint64_t* src = coeffs + (uint64_t)c * n;
+      for (uint64_t j = 0; j < n; j++) dst[j] = mul_(src[j], shift_pow[j]);
+      fft_fast(dst, log_m, lt_m, rate_bits);
+    } else {
+      memcpy(dst, coeffs + (uint64_t)c * n, n * sizeof(uint64_t));
+      coset_fft_with_roots(dst, log_m, COSET_SHIFT, roots_m);
+    }
   }
   /* "transpose LDEs" + reverse_index_bits_in_place: leaf k = natural row bitrev(k); the salt
    * columns are further entries of lde_values and are transposed/reordered with the rest. */
@@ -497,6 +666,9 @@ int orc_commit(const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, uint
   if (!lde_cols_out) free(lde);
   free(roots_n);
   free(roots_m);
+  free(lt_n);
+  free(lt_m);
+  free(shift_pow);
   return rc;
 }
 

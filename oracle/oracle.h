@@ -117,6 +117,15 @@ int orc_zs_partial_products(const uint64_t* const* wires, const uint64_t* const*
                             const uint64_t* k_is, uint32_t num_routed, uint32_t log_n,
                             uint32_t max_degree, uint64_t beta, uint64_t gamma, uint64_t* out);
 
+/* SIMD width of the hashing path: 0 = widest the CPU supports (default), 1 = scalar — the naive
+ * restatement, which is the checker for the other two — 4 = AVX2, 8 = AVX-512.  The SIMD paths
+ * evaluate the SAME permutation on 4 / 8 independent leaves or tree nodes per call
+ * (poseidon_simd.inc) so that the CPU arm of bench.py runs at a speed comparable with plonky2's
+ * hand-vectorised x86 Poseidon; results are bit-identical (tests/test_oracle_golden.py). */
+void orc_set_simd(int width);
+int orc_get_simd(void);
+void orc_poseidon_batch(uint64_t* states, uint64_t count);
+
 /* Threads used by the parallel regions (mirrors rayon's pool). */
 void orc_set_threads(int n);
 int orc_get_threads(void);

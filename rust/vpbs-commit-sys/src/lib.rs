@@ -18,6 +18,16 @@ pub struct vpbs_batch {
 }
 
 #[repr(C)]
+pub struct vpbs_sigmas {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct vpbs_fri {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
 #[derive(Default, Debug, Clone, Copy)]
 pub struct vpbs_stats {
     pub h2d_ms: f32,
@@ -56,6 +66,9 @@ extern "C" {
     pub fn vpbs_merkle_new(ctx: *mut vpbs_ctx, leaves_rowmajor: *const u64, nleaves: u64,
                            leaf_len: u32, cap_height: u32, digests_out: *mut u64,
                            cap_out: *mut u64) -> c_int;
+    pub fn vpbs_merkle_new_dev(ctx: *mut vpbs_ctx, d_leaves: *const u64, nleaves: u64, leaf_len: u32,
+                               cap_height: u32, d_digests_out: *mut u64, d_cap_out: *mut u64,
+                               stats: *mut vpbs_stats) -> c_int;
     pub fn vpbs_lde_batch(ctx: *mut vpbs_ctx, cols: *const *const u64, ncols: u32, log_n: u32,
                           rate_bits: u32, inputs_are_coeffs: c_int, coeffs_out: *const *mut u64,
                           lde_cols_out: *mut u64) -> c_int;
@@ -90,6 +103,16 @@ extern "C" {
     pub fn vpbs_fri_fold(ctx: *mut vpbs_ctx, coeffs_ext: *const u64, len: u64, arity_bits: u32,
                          beta: *const u64, shift_next: u64, coeffs_out: *mut u64,
                          values_out: *mut u64) -> c_int;
+    // FRI commit phase as one device-resident chain
+    pub fn vpbs_fri_begin(ctx: *mut vpbs_ctx, final_poly_coeffs_ext: *const u64, ncoeffs: u64,
+                          rate_bits: u32, out: *mut *mut vpbs_fri) -> c_int;
+    pub fn vpbs_fri_commit_layer(fri: *mut vpbs_fri, arity_bits: u32, cap_height: u32,
+                                 cap_out: *mut u64) -> c_int;
+    pub fn vpbs_fri_fold_layer(fri: *mut vpbs_fri, beta: *const u64) -> c_int;
+    pub fn vpbs_fri_final_poly(fri: *mut vpbs_fri, rate_bits: u32, coeffs_out: *mut u64) -> c_int;
+    pub fn vpbs_fri_query_layer(fri: *mut vpbs_fri, layer: u32, leaf_indices: *const u64, count: u64,
+                                rows_out: *mut u64, siblings_out: *mut u64) -> c_int;
+    pub fn vpbs_fri_destroy(fri: *mut vpbs_fri);
     pub fn vpbs_pow_grind(ctx: *mut vpbs_ctx, state: *const u64, witness_pos: u32, response_lane: u32,
                           min_leading_zeros: u32, first_candidate: u64, count: u64,
                           witness_out: *mut u64, found: *mut c_int) -> c_int;
@@ -105,6 +128,25 @@ extern "C" {
                             siblings_out: *mut u64) -> c_int;
     pub fn vpbs_batch_download(batch: *mut vpbs_batch, coeffs_out: *const *mut u64,
                                leaves_out: *mut u64, digests_out: *mut u64) -> c_int;
+    pub fn vpbs_batch_commit_dev(ctx: *mut vpbs_ctx, d_cols: *const u64, ncols: u32, log_n: u32,
+                                 rate_bits: u32, cap_height: u32, inputs_are_coeffs: c_int,
+                                 cap_out: *mut u64, out: *mut *mut vpbs_batch,
+                                 stats: *mut vpbs_stats) -> c_int;
+    pub fn vpbs_batch_get_lde_rows(batch: *mut vpbs_batch, first_index: u64, step: u64, count: u64,
+                                   rows_out: *mut u64) -> c_int;
+    // permutation argument (prove() steps 4-5) on the device
+    pub fn vpbs_sigmas_upload(ctx: *mut vpbs_ctx, sigma_cols: *const *const u64, k_is: *const u64,
+                              num_routed: u32, log_n: u32, out: *mut *mut vpbs_sigmas) -> c_int;
+    pub fn vpbs_sigmas_destroy(sigmas: *mut vpbs_sigmas);
+    pub fn vpbs_zs_partial_products(ctx: *mut vpbs_ctx, wire_cols: *const *const u64,
+                                    sigmas: *const vpbs_sigmas, max_degree: u32, betas: *const u64,
+                                    gammas: *const u64, num_challenges: u32,
+                                    cols_out: *const *mut u64) -> c_int;
+    pub fn vpbs_batch_zs_partial_products(wires: *mut vpbs_batch, sigmas: *const vpbs_sigmas,
+                                          max_degree: u32, betas: *const u64, gammas: *const u64,
+                                          num_challenges: u32, rate_bits: u32, cap_height: u32,
+                                          cap_out: *mut u64, out: *mut *mut vpbs_batch,
+                                          stats: *mut vpbs_stats) -> c_int;
     pub fn vpbs_batch_shape(batch: *mut vpbs_batch, ncols: *mut u32, log_n: *mut u32,
                             rate_bits: *mut u32, cap_height: *mut u32, width: *mut u32) -> c_int;
 }
@@ -137,14 +179,120 @@ impl Drop for Ctx {
     }
 }
 
-/// Outputs of one commit in the flat layout of include/vpbs_commit.h.
+/// A page-locked host buffer (vpbs_host_alloc): device copies into it run at full PCIe speed and
+/// overlap with kernels; an ordinary `Vec` is pageable, so the driver stages every copy through its
+/// own bounce buffers and nothing overlaps (bench.py `e2e_pageable` vs `e2e_eager`).  Derefs to
+/// `[u64]`, which is what the patched `MerkleTree { leaves: PinnedBuf, .. }` hands out from
+/// `get(i) -> &[F]` (flat leaves).
+pub struct PinnedBuf {
+    ptr: *mut u64,
+    len: usize,
+}
+unsafe impl Send for PinnedBuf {}
+unsafe impl Sync for PinnedBuf {}
+impl PinnedBuf {
+    pub fn new(len: usize) -> Self {
+        let ptr = unsafe { vpbs_host_alloc(len.max(1) * 8) } as *mut u64;
+        assert!(!ptr.is_null(), "vpbs_host_alloc({}) failed", len * 8);
+        PinnedBuf { ptr, len }
+    }
+}
+impl std::ops::Deref for PinnedBuf {
+    type Target = [u64];
+    fn deref(&self) -> &[u64] {
+        unsafe { std::slice::from_raw_parts(self.ptr, self.len) }
+    }
+}
+impl std::ops::DerefMut for PinnedBuf {
+    fn deref_mut(&mut self) -> &mut [u64] {
+        unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) }
+    }
+}
+impl Drop for PinnedBuf {
+    fn drop(&mut self) {
+        unsafe { vpbs_host_free(self.ptr as *mut c_void) }
+    }
+}
+
+/// Outputs of one commit in the flat layout of include/vpbs_commit.h, in pinned host memory.
 pub struct Commit {
-    pub coeffs: Vec<Vec<u64>>, // PolynomialBatch.polynomials
-    pub leaves: Vec<u64>,      // m x width, row-major, leaf k = natural LDE row bitrev(k)
+    pub coeffs: PinnedBuf,  // ncols x n, column c at [c * n, (c + 1) * n): PolynomialBatch.polynomials
+    pub n: usize,
+    pub leaves: PinnedBuf,  // m x width, row-major, leaf k = natural LDE row bitrev(k)
     pub width: usize,
-    pub digests: Vec<u64>,     // 2(m - 2^h) x 4, plonky2 layout
-    pub cap: Vec<u64>,         // 2^h x 4
+    pub digests: PinnedBuf, // 2(m - 2^h) x 4, plonky2 layout
+    pub cap: Vec<u64>,      // 2^h x 4
     pub stats: vpbs_stats,
+}
+
+/// A PolynomialBatch that stays in HBM (vpbs_batch_*): the cap is on the host, rows / Merkle paths /
+/// openings / LDE row blocks are fetched on demand.
+pub struct ResidentBatch {
+    h: *mut vpbs_batch,
+    pub cap: Vec<u64>,
+    pub ncols: usize,
+    pub degree_log: usize,
+    pub rate_bits: usize,
+    pub cap_height: usize,
+}
+unsafe impl Send for ResidentBatch {}
+impl Drop for ResidentBatch {
+    fn drop(&mut self) {
+        unsafe { vpbs_batch_destroy(self.h) }
+    }
+}
+impl ResidentBatch {
+    /// PolynomialBatch::from_values / from_coeffs with the result left on the device.
+    pub fn commit(ctx: &Ctx, cols: &[&[u64]], rate_bits: usize, cap_height: usize,
+                  inputs_are_coeffs: bool) -> Self {
+        let n = cols[0].len();
+        assert!(n.is_power_of_two());
+        let ptrs: Vec<*const u64> = cols.iter().map(|c| c.as_ptr()).collect();
+        let mut cap = vec![0u64; 4 << cap_height];
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe {
+            vpbs_batch_commit(ctx.0, ptrs.as_ptr(), cols.len() as u32, n.trailing_zeros(),
+                              rate_bits as u32, cap_height as u32, inputs_are_coeffs as c_int,
+                              std::ptr::null(), cap.as_mut_ptr(), &mut h, std::ptr::null_mut())
+        };
+        ctx.check(rc);
+        ResidentBatch { h, cap, ncols: cols.len(), degree_log: n.trailing_zeros() as usize, rate_bits,
+                        cap_height }
+    }
+    /// MerkleTree::get(i) + MerkleTree::prove(i) for a set of leaf indices (one FRI query round).
+    pub fn open(&self, ctx: &Ctx, leaf_indices: &[u64]) -> (Vec<u64>, Vec<u64>) {
+        let layers = self.degree_log + self.rate_bits - self.cap_height;
+        let mut rows = vec![0u64; leaf_indices.len() * self.ncols];
+        let mut sibs = vec![0u64; leaf_indices.len() * layers * 4];
+        ctx.check(unsafe { vpbs_batch_get_leaves(self.h, leaf_indices.as_ptr(), leaf_indices.len() as u64,
+                                                 rows.as_mut_ptr()) });
+        ctx.check(unsafe { vpbs_batch_prove(self.h, leaf_indices.as_ptr(), leaf_indices.len() as u64,
+                                            sibs.as_mut_ptr()) });
+        (rows, sibs)
+    }
+    /// get_lde_values(first + i * step, 1) for i < count: the block compute_quotient_polys reads.
+    pub fn lde_rows(&self, ctx: &Ctx, first: u64, step: u64, count: usize, out: &mut [u64]) {
+        assert!(out.len() >= count * self.ncols);
+        ctx.check(unsafe { vpbs_batch_get_lde_rows(self.h, first, step, count as u64, out.as_mut_ptr()) });
+    }
+    /// prove() steps 4-5: Z and partial products computed from this (wires) batch on the device and
+    /// committed as a new resident batch.
+    pub fn commit_zs_partial_products(&self, ctx: &Ctx, sigmas: *const vpbs_sigmas, max_degree: usize,
+                                      betas: &[u64], gammas: &[u64], num_routed: usize) -> ResidentBatch {
+        assert_eq!(betas.len(), gammas.len());
+        let mut cap = vec![0u64; 4 << self.cap_height];
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe {
+            vpbs_batch_zs_partial_products(self.h, sigmas, max_degree as u32, betas.as_ptr(),
+                                           gammas.as_ptr(), betas.len() as u32, self.rate_bits as u32,
+                                           self.cap_height as u32, cap.as_mut_ptr(), &mut h,
+                                           std::ptr::null_mut())
+        };
+        ctx.check(rc);
+        let chunks = (num_routed + max_degree - 1) / max_degree;
+        ResidentBatch { h, cap, ncols: betas.len() * chunks, degree_log: self.degree_log,
+                        rate_bits: self.rate_bits, cap_height: self.cap_height }
+    }
 }
 
 /// `cols[c]` is one polynomial's values (or coefficients): GoldilocksField is
@@ -159,10 +307,11 @@ pub fn commit(ctx: &Ctx, cols: &[&[u64]], rate_bits: usize, cap_height: usize,
     let width = ncols + if salt.is_some() { VPBS_SALT_SIZE } else { 0 };
     let col_ptrs: Vec<*const u64> = cols.iter().map(|c| c.as_ptr()).collect();
     let salt_ptrs: Option<Vec<*const u64>> = salt.map(|s| s.iter().map(|c| c.as_ptr()).collect());
-    let mut coeffs = vec![vec![0u64; n]; ncols];
-    let coeff_ptrs: Vec<*mut u64> = coeffs.iter_mut().map(|c| c.as_mut_ptr()).collect();
-    let mut leaves = vec![0u64; m * width];
-    let mut digests = vec![0u64; 8 * (m - (1 << cap_height))];
+    // outputs in pinned memory: the call then costs the PCIe time of its outputs and no more
+    let mut coeffs = PinnedBuf::new(ncols * n);
+    let coeff_ptrs: Vec<*mut u64> = (0..ncols).map(|c| unsafe { coeffs.as_mut_ptr().add(c * n) }).collect();
+    let mut leaves = PinnedBuf::new(m * width);
+    let mut digests = PinnedBuf::new(8 * (m - (1 << cap_height)));
     let mut cap = vec![0u64; 4 << cap_height];
     let mut stats = vpbs_stats::default();
     let rc = unsafe {
@@ -174,5 +323,5 @@ pub fn commit(ctx: &Ctx, cols: &[&[u64]], rate_bits: usize, cap_height: usize,
                     cap.as_mut_ptr(), &mut stats)
     };
     ctx.check(rc);
-    Commit { coeffs, leaves, width, digests, cap, stats }
+    Commit { coeffs, n, leaves, width, digests, cap, stats }
 }
