@@ -407,6 +407,219 @@ pass_final_r16p(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
   cp_async_wait<0>();
 }
 
+// ---- the same passes with TMA tile loads ------------------------------------------------------------
+// The tile of a strided pass is a box of a strided tensor — 16 consecutive elements (128 B) x 256
+// rows of pitch 2^log_sigma — and the tile of the leaf-order final pass a box of 256 elements x 16
+// columns: ONE cp.async.bulk.tensor per tile, issued by one thread and completed on an mbarrier,
+// replaces 16 cp.async + their address arithmetic per thread (4096 LDGSTS per tile), and columns
+// beyond ncols arrive as zeros (out-of-bounds fill) instead of through a branch.  The tensor maps
+// are encoded on the host per launch (vpbs_commit.cu, make_tile_map) and passed as __grid_constant__.
+// Hazards: the staging buffer is also the exchange buffer (generic-proxy stores), so every thread
+// executes fence.proxy.async before the barrier that precedes the next bulk copy into it.
+namespace tma {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void load_4d(void* dst, const void* map, u64* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void load_2d(void* dst, const void* map, u64* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+struct alignas(64) TileMap {  // same size and alignment as the driver's CUtensorMap
+  unsigned long long opaque[16];
+};
+constexpr unsigned TILE_BYTES = 256 * 16 * sizeof(u64);
+}  // namespace tma
+
+constexpr size_t R16T_STRIDED_SMEM = 2 * tma::TILE_BYTES + (128 + 256 + 2) * sizeof(u64) + 128;
+constexpr size_t R16T_FINAL_SMEM = 2 * tma::TILE_BYTES + (128 + 2 * 256 + 2) * sizeof(u64) + 128;
+
+// pass_strided_r16p with the tile fetched by TMA.  map: rank-4 tensor over the source,
+// (low < 2^log_sigma, q < 256, block < 2^(log_n - log_B), column < ncols), box 16 x 256 x 1 x 1.
+template <bool INVERSE, bool OUT_TW>
+__global__ void __launch_bounds__(THREADS, R16P_MIN_BLOCKS)
+pass_strided_r16t(const __grid_constant__ tma::TileMap map, u64* __restrict__ dst, u64 dst_col_stride,
+                  unsigned log_B, const u64* __restrict__ in_scale, Roots R, unsigned tiles_x,
+                  unsigned ntiles) {
+  extern __shared__ u64 dyn_raw[];
+  u64* dyn = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(dyn_raw) + 127) & ~(uintptr_t)127);
+  u64* buf = dyn;                  // [2][256 * 16], dense [q][low]: what the box lands as
+  u64* tw = dyn + 2 * 256 * 16;    // [128]
+  u64* sq = tw + 128;              // [256]
+  u64* bar = sq + 256;             // [2]
+  const unsigned log_sigma = log_B - 8;
+  const unsigned tiles_per_block_log = log_sigma - 4;
+  const unsigned t = threadIdx.x & 15, qa = threadIdx.x >> 4;
+  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  unsigned tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  if (threadIdx.x == 0) {
+    tma::mbar_init(bar, 1);
+    tma::mbar_init(bar + 1, 1);
+    tma::fence_mbar_init();
+  }
+  auto issue = [&](unsigned tl, unsigned b) {  // one thread
+    const unsigned bx = tl % tiles_x, by = tl / tiles_x;
+    tma::mbar_expect_tx(bar + b, tma::TILE_BYTES);
+    tma::load_4d(buf + b * (256 * 16), &map, bar + b, (int)((bx & ((1u << tiles_per_block_log) - 1)) << 4), 0,
+                 (int)(bx >> tiles_per_block_log), (int)by);
+  };
+  if (!OUT_TW && in_scale) sq[threadIdx.x] = __ldg(in_scale + ((u64)threadIdx.x << log_sigma));
+  __syncthreads();  // barriers initialised; tw, sq ready
+  if (threadIdx.x == 0) issue(tile, 0);
+  for (unsigned it = 0;; it++) {
+    u64* cur = buf + (it & 1) * (256 * 16);
+    const unsigned next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < ntiles) issue(next, (it & 1) ^ 1);
+    tma::mbar_wait(bar + (it & 1), (it >> 1) & 1);
+    const unsigned bx = tile % tiles_x, by = tile / tiles_x;
+    const u64 blk = bx >> tiles_per_block_log;
+    const u64 low0 = (u64)(bx & ((1u << tiles_per_block_log) - 1)) << 4;
+    const u64 base = blk << log_B;
+    u64 x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = cur[(16 * j + qa) * 16 + t];
+    if (in_scale) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        if (OUT_TW) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + base + ((u64)(16 * j + qa) << log_sigma) + low0 + t));
+        else x[j] = gl::mul_lazy(x[j], sq[16 * j + qa]);
+      }
+    }
+    dif16<true>(x, tw, 16, qa, 0);
+#pragma unroll
+    for (int j = 0; j < 16; j++) cur[(16 * j + qa) * 16 + t] = x[j];  // own slots only
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = cur[(16 * qa + j) * 16 + t];
+    tma::fence_proxy_async();  // our stores to `cur` are ordered before the bulk copy that refills it
+    __syncthreads();
+    dif16<false>(x, tw, 1, 0, 4);
+    u64* out = dst + (u64)by * dst_col_stride + base + low0 + t;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const unsigned q = 16 * qa + j;
+      if (OUT_TW) {
+        const u64 e = (low0 + t) * (u64)brev(q, 8);
+        out[(u64)q << log_sigma] = e ? gl::mul_lazy(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
+      } else {
+        out[(u64)q << log_sigma] = x[j];
+      }
+    }
+    if (next >= ntiles) break;
+    tile = next;
+  }
+}
+
+// pass_final_r16p<., STORE_LEAF> with the tile fetched by TMA.  map: rank-2 tensor (position < n,
+// column < ncols), box 256 x 16: the tile lands dense as [lane][q] (no padding possible), so the
+// register exchange swizzles the low four bits of q with the lane (slot = lane * 256 + (q ^ lane)):
+// the stage-1 stores then touch slots read by threads of the same half-warp (a __syncwarp orders
+// them) and both exchange accesses are bank-conflict free (the padded cp.async form had 7.7e5
+// conflicts per launch).
+template <bool INVERSE>
+__global__ void __launch_bounds__(THREADS, R16P_MIN_BLOCKS)
+pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* __restrict__ dst,
+                u64 dst_stride, u64 row0, u64 out_scale, Roots R, unsigned in_tw_log_B,
+                const u64* __restrict__ in_tw_scale, unsigned tiles_x, unsigned ntiles) {
+  extern __shared__ u64 dyn_raw[];
+  u64* dyn = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(dyn_raw) + 127) & ~(uintptr_t)127);
+  u64* buf = dyn;                  // [2][16 * 256], dense [lane][q]
+  u64* tw = dyn + 2 * 256 * 16;    // [128]
+  u64* tws = tw + 128;             // [2][256]
+  u64* bar = tws + 2 * 256;        // [2]
+  const bool in_tw = in_tw_log_B != 0;
+  const unsigned q_lo = threadIdx.x & 15, lane_a = threadIdx.x >> 4;
+  const unsigned lane_b = threadIdx.x & 15, q_hi = threadIdx.x >> 4;
+  if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
+  unsigned tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  if (threadIdx.x == 0) {
+    tma::mbar_init(bar, 1);
+    tma::mbar_init(bar + 1, 1);
+    tma::fence_mbar_init();
+  }
+  auto issue = [&](unsigned tl, unsigned b) {  // one thread
+    tma::mbar_expect_tx(bar + b, tma::TILE_BYTES);
+    tma::load_2d(buf + b * (256 * 16), &map, bar + b, (int)((tl % tiles_x) << 8), (int)((tl / tiles_x) << 4));
+  };
+  auto twiddle = [&](unsigned tl) -> u64 {  // pending four-step twiddle (times the g^low scaling)
+    return root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev((tl % tiles_x) & 255u, 8));
+  };
+  const u64 tw_scale = (in_tw && in_tw_scale) ? __ldg(in_tw_scale + threadIdx.x) : 1;
+  if (in_tw) tws[threadIdx.x] = gl::mul_lazy(twiddle(tile), tw_scale);
+  __syncthreads();  // barriers initialised; tw and the first tws visible
+  if (threadIdx.x == 0) issue(tile, 0);
+  for (unsigned it = 0;; it++) {
+    u64* cur = buf + (it & 1) * (256 * 16);
+    const u64* twc = tws + (it & 1) * 256;
+    const unsigned next = tile + gridDim.x;
+    u64 w_next = 0;
+    if (next < ntiles) {
+      if (threadIdx.x == 0) issue(next, (it & 1) ^ 1);
+      if (in_tw) w_next = twiddle(next);  // the load completes behind this tile's arithmetic
+    }
+    tma::mbar_wait(bar + (it & 1), (it >> 1) & 1);
+    u64 x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = cur[lane_a * 256 + 16 * j + q_lo];
+    if (in_tw) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], twc[16 * j + q_lo]);
+    }
+    dif16<true>(x, tw, 16, q_lo, 0);
+    __syncwarp();  // the slots written next were read by threads of this half-warp
+#pragma unroll
+    for (int j = 0; j < 16; j++) cur[lane_a * 256 + 16 * j + (q_lo ^ lane_a)] = x[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = cur[lane_b * 256 + 16 * q_hi + (j ^ lane_b)];
+    if (in_tw && next < ntiles) tws[((it & 1) ^ 1) * 256 + threadIdx.x] = gl::mul_lazy(w_next, tw_scale);
+    tma::fence_proxy_async();
+    __syncthreads();  // everyone is done with `cur` before the next bulk copy refills it
+    dif16<false>(x, tw, 1, 0, 4);
+    const unsigned bx = tile % tiles_x, by = tile / tiles_x;
+    const unsigned col = by * 16 + lane_b;
+    if (col < ncols) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const u64 pos = ((u64)bx << 8) + 16 * q_hi + j;
+        const u64 v = (out_scale != 1) ? gl::mul(x[j], out_scale) : gl::canon(x[j]);
+        dst[(row0 + pos) * dst_stride + col] = v;
+      }
+    }
+    if (next >= ntiles) break;
+    tile = next;
+  }
+}
+
 // ---- polynomial evaluation at quadratic-extension points --------------------------------------------
 // F[X]/(X^2 - 7): (a0 + a1 X)(b0 + b1 X) = (a0 b0 + 7 a1 b1) + (a0 b1 + a1 b0) X.
 struct Ext2 {

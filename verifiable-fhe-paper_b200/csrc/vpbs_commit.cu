@@ -8,6 +8,7 @@
 //   leaves   m x W   row-major      W = C (+4 salt); leaf k = natural LDE row bitrev(k)
 //   digests  2(m - 2^h) x 4, plonky2 layout;  cap 2^h x 4
 // There is no CPU fallback anywhere in this file: every path ends in a kernel launch or an error.
+#include <cuda.h>  // CUtensorMap and its enums only: the encoder is fetched through the runtime
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -239,6 +240,47 @@ Plan make_plan(unsigned L) {
 
 enum class Out { Leaf, Natural };
 
+// ---- TMA tile maps for the 256-point passes (ntt::pass_*_r16t) ------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+static_assert(sizeof(CUtensorMap) == sizeof(ntt::tma::TileMap) && alignof(CUtensorMap) <= alignof(ntt::tma::TileMap),
+              "ntt::tma::TileMap must mirror CUtensorMap");
+EncodeTiledFn tile_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// A u64 tensor of `rank` dimensions (dims[0] contiguous; strides in elements for dims 1..) with the
+// given box.  false: this source cannot be described (alignment) and the caller uses the cp.async pass.
+bool make_tile_map(ntt::tma::TileMap* out, const u64* base, unsigned rank, const u64* dims,
+                   const u64* strides_elems, const unsigned* box) {
+  EncodeTiledFn enc = tile_map_encoder();
+  if (!enc || ((uintptr_t)base & 15)) return false;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (unsigned i = 0; i < rank; i++) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i) {
+      gstr[i - 1] = strides_elems[i - 1] * sizeof(u64);
+      if (gstr[i - 1] & 15) return false;
+    }
+  }
+  return enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT64, rank, const_cast<u64*>(base),
+             gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // One size-2^log_n transform of `ncols` columns.
 //   src (column-major, stride src_stride) -> dst.  work: scratch ncols x n (needed if npass > 1).
 //   Out::Leaf   : dst = row-major matrix, row stride dst_stride, rows row0.. in bit-reversed order
@@ -267,7 +309,21 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
     dim3 grid((unsigned)(n >> (s + log_T)), ncols);
     const unsigned ntiles = grid.x * grid.y;
     const unsigned pgrid = ntiles < ctx->sms * ntt::R16P_MIN_BLOCKS ? ntiles : ctx->sms * ntt::R16P_MIN_BLOCKS;
-    if (s == 8 && log_T == 4 && tw_at_load)  // 256-point pass: persistent radix-16 register kernel
+    ntt::tma::TileMap map;
+    bool tiled = false;
+    if (s == 8 && log_T == 4) {  // the tile is a 16 x 256 box of (low, q, block, column)
+      const u64 dims[4] = {1ULL << log_sigma, 256, n >> log_B, ncols};
+      const u64 strides[3] = {1ULL << log_sigma, 1ULL << log_B, cur_stride};
+      const unsigned box[4] = {16, 256, 1, 1};
+      tiled = make_tile_map(&map, cur, 4, dims, strides, box);
+    }
+    if (tiled && tw_at_load)  // 256-point pass: persistent radix-16 register kernel, TMA tile loads
+      ntt::pass_strided_r16t<INVERSE, false><<<pgrid, ntt::THREADS, ntt::R16T_STRIDED_SMEM, stream>>>(
+          map, work, n, log_B, p == 0 ? in_scale : nullptr, R, grid.x, ntiles);
+    else if (tiled)
+      ntt::pass_strided_r16t<INVERSE, true><<<pgrid, ntt::THREADS, ntt::R16T_STRIDED_SMEM, stream>>>(
+          map, work, n, log_B, p == 0 ? in_scale : nullptr, R, grid.x, ntiles);
+    else if (s == 8 && log_T == 4 && tw_at_load)  // sources TMA cannot describe: cp.async tile loads
       ntt::pass_strided_r16p<INVERSE, false><<<pgrid, ntt::THREADS, ntt::R16P_STRIDED_SMEM, stream>>>(
           cur, cur_stride, work, n, log_B, p == 0 ? in_scale : nullptr, R, grid.x, ntiles);
     else if (s == 8 && log_T == 4)
@@ -290,7 +346,19 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
       dim3 grid((unsigned)(n >> s), (ncols + (1u << log_T) - 1) >> log_T);
       const unsigned ntiles = grid.x * grid.y;
       const unsigned pgrid = ntiles < ctx->sms * ntt::R16P_MIN_BLOCKS ? ntiles : ctx->sms * ntt::R16P_MIN_BLOCKS;
-      if (s == 8)
+      ntt::tma::TileMap map;
+      bool tiled = false;
+      if (s == 8 && !scale && ncols >= 16) {  // the tile is a 256 x 16 box of (position, column)
+        const u64 dims[2] = {n, ncols};
+        const u64 strides[1] = {cur_stride};
+        const unsigned box[2] = {256, 16};
+        tiled = make_tile_map(&map, cur, 2, dims, strides, box);
+      }
+      if (tiled)
+        ntt::pass_final_r16t<INVERSE><<<pgrid, ntt::THREADS, ntt::R16T_FINAL_SMEM, stream>>>(
+            map, ncols, dst, dst_stride, row0, out_scale, R, tw_at_load ? log_n : 0u,
+            tw_at_load ? in_scale : nullptr, grid.x, ntiles);
+      else if (s == 8)
         ntt::pass_final_r16p<INVERSE, ntt::STORE_LEAF><<<pgrid, ntt::THREADS, ntt::R16P_FINAL_SMEM, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R,
             tw_at_load ? log_n : 0u, tw_at_load ? in_scale : nullptr, grid.x, ntiles);
@@ -576,6 +644,12 @@ cudaError_t allow_large_smem() {
   set((const void*)ntt::pass_final_r16p<false, ntt::STORE_NATURAL>, ntt::R16P_FINAL_SMEM);
   set((const void*)ntt::pass_final_r16p<true, ntt::STORE_LEAF>, ntt::R16P_FINAL_SMEM);
   set((const void*)ntt::pass_final_r16p<true, ntt::STORE_NATURAL>, ntt::R16P_FINAL_SMEM);
+  set((const void*)ntt::pass_strided_r16t<false, false>, ntt::R16T_STRIDED_SMEM);
+  set((const void*)ntt::pass_strided_r16t<false, true>, ntt::R16T_STRIDED_SMEM);
+  set((const void*)ntt::pass_strided_r16t<true, false>, ntt::R16T_STRIDED_SMEM);
+  set((const void*)ntt::pass_strided_r16t<true, true>, ntt::R16T_STRIDED_SMEM);
+  set((const void*)ntt::pass_final_r16t<false>, ntt::R16T_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16t<true>, ntt::R16T_FINAL_SMEM);
   return e;
 }
 
