@@ -238,6 +238,22 @@ int vpbs_fri_fold(vpbs_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len, uint3
 typedef struct vpbs_fri vpbs_fri;
 int vpbs_fri_begin(vpbs_ctx* ctx, const uint64_t* final_poly_coeffs_ext, uint64_t ncoeffs,
                    uint32_t rate_bits, vpbs_fri** out);
+/* The chain started from the committed batches themselves: [P2] fri/oracle.rs prove_openings from its
+ * first line to lde_final_values, on the device.  oracles: the resident batches (FRI_ORACLES order is
+ * the caller's); the FRI instance ([P2] FriInstanceInfo) is nbatches batches of batch_sizes[b]
+ * polynomials each, poly_refs holding their (oracle_index, polynomial_index) pairs back to back
+ * ([P2] FriPolynomialInfo), opened at the extension points points[2b], points[2b+1].  Per batch:
+ *   F_b = sum_j alpha^j f_bj (ReducingFactor::reduce_polys_base),
+ *   Q_b = (F_b(X) - F_b(z_b)) / (X - z_b) padded with a zero (divide_by_linear),
+ *   final_poly = final_poly * alpha^(batch_sizes[b]) + Q_b (shift_poly, +=);
+ * then final_poly.lde(rate_bits).coset_fft(F::coset_shift()) as vpbs_fri_begin.  Only alpha and
+ * the points cross PCIe.  vpbs_fri_final_poly(fri, rate_bits, ..) right after this call returns
+ * final_poly itself (n coefficients). */
+struct vpbs_batch; /* resident batches: declared below */
+int vpbs_fri_begin_openings(vpbs_ctx* ctx, struct vpbs_batch* const* oracles, uint32_t noracles,
+                            const uint32_t* batch_sizes, uint32_t nbatches, const uint32_t* poly_refs,
+                            const uint64_t* points, const uint64_t alpha[2], uint32_t rate_bits,
+                            vpbs_fri** out);
 int vpbs_fri_commit_layer(vpbs_fri* fri, uint32_t arity_bits, uint32_t cap_height, uint64_t* cap_out);
 int vpbs_fri_fold_layer(vpbs_fri* fri, const uint64_t beta[2]);
 int vpbs_fri_final_poly(vpbs_fri* fri, uint32_t rate_bits, uint64_t* coeffs_out);

@@ -73,6 +73,8 @@ def lib() -> ctypes.CDLL:
         L.orc_fri_layer_commit.argtypes = [_u64p, u64, u32, u32, _u64p, _u64p, _u64p]
         L.orc_fri_fold.restype = None
         L.orc_fri_fold.argtypes = [_u64p, u64, u32, _u64p, u64, _u64p, _u64p]
+        L.orc_fri_final_poly.restype = ctypes.c_int
+        L.orc_fri_final_poly.argtypes = [_u64pp, ctypes.POINTER(u32), u32, u64, _u64p, _u64p, _u64p]
         L.orc_zs_partial_products.restype = ctypes.c_int
         L.orc_zs_partial_products.argtypes = [_u64pp, _u64pp, _u64p, u32, u32, u32, u64, u64, _u64p]
         L.orc_set_simd.argtypes = [ctypes.c_int]
@@ -229,6 +231,22 @@ def fri_fold(coeffs_ext, arity_bits, beta, shift_next):
     co = np.empty((ol, 2), np.uint64); vo = np.empty((ol, 2), np.uint64)
     lib().orc_fri_fold(_p(c), ln, arity_bits, _p(_arr(beta)), int(shift_next), _p(co), _p(vo))
     return co, vo
+
+
+def fri_final_poly(batches, points, alpha):
+    """[P2] prove_openings up to final_poly.  batches: list of (len_b, n) coefficient arrays;
+    points: (nbatches, 2); alpha: (2,) -> (n, 2)."""
+    arrs = [_arr(b) for b in batches]
+    n = arrs[0].shape[1]
+    sizes = np.array([a.shape[0] for a in arrs], np.uint32)
+    ptrs = [_p(a[j]) for a in arrs for j in range(a.shape[0])]
+    pp = (_u64p * len(ptrs))(*ptrs)
+    out = np.empty((n, 2), np.uint64)
+    rc = lib().orc_fri_final_poly(pp, sizes.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(arrs), n,
+                                  _p(_arr(points).reshape(-1)), _p(_arr(alpha).reshape(2)), _p(out))
+    if rc != 0:
+        raise ValueError("orc_fri_final_poly: bad arguments")
+    return out
 
 
 def zs_partial_products(wires, sigmas, k_is, max_degree, beta, gamma):

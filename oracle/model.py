@@ -263,6 +263,34 @@ def fri_fold(coeffs, arity_bits, beta, shift_next):
     return out, list(zip(re, im))
 
 
+def fri_final_poly(batches, points, alpha):
+    """[P2] fri/oracle.rs prove_openings up to final_poly, from the definitions (no Horner scan):
+    batches: per FRI batch a list of coefficient lists; points / alpha: extension elements.
+    F_b = sum_j alpha^j f_bj;  Q_b = (F_b(X) - F_b(z)) / (X - z) has coefficients
+    q_i = sum_{j > i} F_b[j] z^(j - i - 1)  (padded with q_{n-1} = 0);
+    final = final * alpha^len(batch) + Q_b."""
+    n = len(batches[0][0])
+    final = [(0, 0)] * n
+    for polys, z in zip(batches, points):
+        comp, pw = [(0, 0)] * n, (1, 0)
+        for f in polys:
+            comp = [((c[0] + x % P * pw[0]) % P, (c[1] + x % P * pw[1]) % P) for c, x in zip(comp, f)]
+            pw = ext_mul(pw, alpha)
+        zp = [(1, 0)]
+        for _ in range(n):
+            zp.append(ext_mul(zp[-1], z))
+        quot = []
+        for i in range(n):
+            acc = (0, 0)
+            for j in range(i + 1, n):
+                t = ext_mul(comp[j], zp[j - i - 1])
+                acc = ((acc[0] + t[0]) % P, (acc[1] + t[1]) % P)
+            quot.append(acc)
+        shifted = [ext_mul(f, pw) for f in final]  # pw = alpha^len(polys)
+        final = [((a[0] + b[0]) % P, (a[1] + b[1]) % P) for a, b in zip(shifted, quot)]
+    return final
+
+
 # --------------------------------------------------------------------------- permutation argument
 def zs_partial_products(wires, sigmas, k_is, max_degree, beta, gamma):
     """[P2] plonk/prover.rs wires_permutation_partial_products_and_zs for one (beta, gamma), from the

@@ -738,6 +738,61 @@ void orc_fri_fold(const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
   free(tmp);
 }
 
+/* ---- [P2] fri/oracle.rs PolynomialBatch::prove_openings, up to final_poly ------------------------ */
+/* ReducingFactor (util/reducing.rs): reduce_polys_base multiplies the j-th polynomial of the call by
+ * base^j (powers restart at 1 in every call) and counts the polynomials; shift_poly multiplies by
+ * base^count and resets the count.  divide_by_linear (polynomial/division.rs): bs = scan from the top
+ * of acc = acc * z + c; drop bs of the constant term; quotient = the rest, lowest first. */
+int orc_fri_final_poly(const uint64_t* const* polys, const uint32_t* batch_sizes, uint32_t nbatches,
+                       uint64_t n, const uint64_t* points, const uint64_t alpha[2], uint64_t* out) {
+  if (!polys || !batch_sizes || !points || !alpha || !out || n == 0 || nbatches == 0) return -1;
+  const uint64_t a0 = canon(alpha[0]), a1 = canon(alpha[1]);
+  uint64_t* comp = (uint64_t*)malloc(sizeof(uint64_t) * 2 * n);
+  if (!comp) return -1;
+  memset(out, 0, sizeof(uint64_t) * 2 * n); /* final_poly = PolynomialCoeffs::empty() */
+  size_t off = 0;
+  for (uint32_t b = 0; b < nbatches; b++) {
+    const uint32_t len = batch_sizes[b];
+    if (len == 0) {
+      free(comp);
+      return -1;
+    }
+    /* composition_poly = alpha.reduce_polys_base(polys_coeff) */
+    memset(comp, 0, sizeof(uint64_t) * 2 * n);
+    uint64_t p0 = 1, p1 = 0; /* alpha^j */
+    for (uint32_t j = 0; j < len; j++) {
+      const uint64_t* f = polys[off + j];
+      for (uint64_t i = 0; i < n; i++) {
+        const uint64_t c = canon(f[i]);
+        comp[2 * i] = add_(comp[2 * i], mul_(c, p0));
+        comp[2 * i + 1] = add_(comp[2 * i + 1], mul_(c, p1));
+      }
+      const uint64_t n0 = add_(mul_(p0, a0), mul_(EXT_W, mul_(p1, a1)));
+      const uint64_t n1 = add_(mul_(p0, a1), mul_(p1, a0));
+      p0 = n0;
+      p1 = n1;
+    }
+    /* after the loop (p0, p1) = alpha^len = the factor shift_poly applies */
+    /* quotient = composition_poly.divide_by_linear(point); quotient.coeffs.push(ZERO) */
+    const uint64_t z0 = canon(points[2 * b]), z1 = canon(points[2 * b + 1]);
+    uint64_t acc0 = 0, acc1 = 0; /* b_{i+1} while visiting i from the top */
+    for (uint64_t i = n; i-- > 0;) {
+      const uint64_t q0 = acc0, q1 = acc1; /* quotient coefficient i (q_{n-1} = 0: the pushed zero) */
+      const uint64_t m0 = add_(mul_(acc0, z0), mul_(EXT_W, mul_(acc1, z1)));
+      const uint64_t m1 = add_(mul_(acc0, z1), mul_(acc1, z0));
+      acc0 = add_(m0, comp[2 * i]);
+      acc1 = add_(m1, comp[2 * i + 1]);
+      /* alpha.shift_poly(&mut final_poly); final_poly += quotient */
+      const uint64_t f0 = out[2 * i], f1 = out[2 * i + 1];
+      out[2 * i] = add_(add_(mul_(f0, p0), mul_(EXT_W, mul_(f1, p1))), q0);
+      out[2 * i + 1] = add_(add_(mul_(f0, p1), mul_(f1, p0)), q1);
+    }
+    off += len;
+  }
+  free(comp);
+  return 0;
+}
+
 /* ---- [P2] plonk/prover.rs wires_permutation_partial_products_and_zs -------------------------- */
 int orc_zs_partial_products(const uint64_t* const* wires, const uint64_t* const* sigmas,
                             const uint64_t* k_is, uint32_t num_routed, uint32_t log_n,

@@ -101,6 +101,17 @@ void orc_fri_fold(const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
                   const uint64_t beta[2], uint64_t shift_next, uint64_t* coeffs_out,
                   uint64_t* values_out);
 
+/* [P2] plonky2/src/fri/oracle.rs PolynomialBatch::prove_openings from its first line to final_poly
+ * (the polynomial FRI is run on), with util/reducing.rs ReducingFactor::{reduce_polys_base,
+ * shift_poly} and polynomial/division.rs divide_by_linear; reached from prove(),
+ * /root/reference/src/vtfhe/ivc_based_vpbs.rs:302.  polys: the coefficient polynomials of all FRI
+ * batches back to back (batch_sizes[b] pointers to n base-field coefficients each); points: the
+ * opening point of every batch (2 words each); alpha: the extension challenge.  out: n x 2.
+ *   F_b = sum_j alpha^j f_bj;  Q_b = (F_b(X) - F_b(z_b)) / (X - z_b), padded with a zero;
+ *   final_poly = final_poly * alpha^(batch_sizes[b]) + Q_b. */
+int orc_fri_final_poly(const uint64_t* const* polys, const uint32_t* batch_sizes, uint32_t nbatches,
+                       uint64_t n, const uint64_t* points, const uint64_t alpha[2], uint64_t* out);
+
 /* [P2] plonky2/src/plonk/prover.rs wires_permutation_partial_products_and_zs with
  * util/partial_products.rs quotient_chunk_products / partial_products_and_z_gx, for ONE challenge
  * pair (beta, gamma) — step 4 of prove() ("compute partial products"), reached from

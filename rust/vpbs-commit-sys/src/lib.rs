@@ -106,6 +106,10 @@ extern "C" {
     // FRI commit phase as one device-resident chain
     pub fn vpbs_fri_begin(ctx: *mut vpbs_ctx, final_poly_coeffs_ext: *const u64, ncoeffs: u64,
                           rate_bits: u32, out: *mut *mut vpbs_fri) -> c_int;
+    pub fn vpbs_fri_begin_openings(ctx: *mut vpbs_ctx, oracles: *const *mut vpbs_batch, noracles: u32,
+                                   batch_sizes: *const u32, nbatches: u32, poly_refs: *const u32,
+                                   points: *const u64, alpha: *const u64, rate_bits: u32,
+                                   out: *mut *mut vpbs_fri) -> c_int;
     pub fn vpbs_fri_commit_layer(fri: *mut vpbs_fri, arity_bits: u32, cap_height: u32,
                                  cap_out: *mut u64) -> c_int;
     pub fn vpbs_fri_fold_layer(fri: *mut vpbs_fri, beta: *const u64) -> c_int;

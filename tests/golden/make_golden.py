@@ -125,6 +125,13 @@ def model_anchors():
     ka = [pow(7, j, P) for j in range(5)]
     out["zs_partial_products"] = dict(beta=beta, gamma=gamma, max_degree=2,
                                       columns=[hx(c) for c in M.zs_partial_products(wa, sa, ka, 2, beta, gamma)])
+    # [P2] fri/oracle.rs prove_openings up to final_poly on a fixed case: two FRI batches (5 and 2
+    # polynomials of 8 coefficients), points and alpha in the quadratic extension
+    fb = [[[((11 * b + 5 * j + 3) * (i + 1) ** 2 + 7 * i) % P for i in range(8)] for j in range(nb)]
+          for b, nb in enumerate((5, 2))]
+    fpts, falpha = [(0x1111111111111111, 0x2222222222222222), (3, 5)], (0x0123456789ABCDEF % P, 0x0FEDCBA987654321 % P)
+    out["fri_final_poly"] = dict(batches=[[hx(f) for f in b] for b in fb], points=[hx(z) for z in fpts],
+                                 alpha=hx(falpha), final_poly=[hx(c) for c in M.fri_final_poly(fb, fpts, falpha)])
     json.dump(out, open(os.path.join(HERE, "model_anchors.json"), "w"))
 
 

@@ -850,3 +850,52 @@ def test_fri_commit_phase_resident_chain(V, ctx, oracle, log_n, rate_bits, ariti
     with pytest.raises(V.VpbsError):
         fri.fold([1, 2])  # nothing committed to fold
     fri.close()
+
+
+@pytest.mark.parametrize("log_n,widths,sizes", [
+    (0, (3,), ((0, 0), (0, 2))), (3, (5, 2), None), (8, (9, 4, 3), None), (12, (20, 16), None),
+    (13, (7,), None), (16, (135, 20, 16), None)])
+def test_prove_openings_final_poly_from_resident_batches(V, ctx, oracle, log_n, widths, sizes):
+    """[P2] fri/oracle.rs prove_openings from its first line to the committed first FRI layer, with the
+    batches resident (vpbs_fri_begin_openings): alpha-combination of the coefficient polynomials,
+    division by (X - z), shift / accumulate over two FRI batches (all polynomials at zeta; the
+    first oracle's leading polynomials at g zeta, as plonky2 opens Z), then LDE + first layer cap.
+    The last case has the N=1024 step's shapes (135 + 20 + 16 polynomials of 2^16 coefficients)."""
+    rng = np.random.default_rng(log_n * 31 + len(widths))
+    n = 1 << log_n
+    cols = [rand_u64(rng, (w, n)) for w in widths]
+    obs = [V.commit_resident(c, 3, False, min(4, log_n + 3), True, ctx=ctx) for c in cols]
+    all_refs = [(o, j) for o, w in enumerate(widths) for j in range(w)]
+    next_refs = [(len(widths) - 1, j) for j in range(min(2, widths[-1]))]
+    if sizes is not None:
+        all_refs, next_refs = [sizes[0]], [sizes[1]]
+    batches = [all_refs, next_refs]
+    pts = rand_u64(rng, (2, 2), edge_frac=0)
+    alpha = rand_u64(rng, 2, edge_frac=0)
+    fri = V.FriCommitPhase.from_openings(obs, batches, pts, alpha, 3)
+    got = fri.final_poly()  # before any fold: final_poly itself
+    want = oracle.fri_final_poly([np.stack([cols[o][j] for (o, j) in b]) for b in batches], pts, alpha)
+    assert np.array_equal(got, want)
+    if log_n + 3 >= 4:  # the chain goes on exactly as from host coefficients
+        ref = V.FriCommitPhase(want, 3, ctx)
+        h = min(4, log_n + 3 - 4)
+        assert np.array_equal(fri.commit_layer(4, h), ref.commit_layer(4, h))
+        ref.close()
+    fri.close()
+    for o in obs:
+        o.close()
+
+
+def test_prove_openings_rejects_bad_instances(V, ctx):
+    rng = np.random.default_rng(3)
+    a = V.commit_resident(rand_u64(rng, (3, 16)), 1, False, 0, True, ctx=ctx)
+    b = V.commit_resident(rand_u64(rng, (2, 32)), 1, False, 0, True, ctx=ctx)
+    pt, al = np.array([[1, 2]], np.uint64), np.array([3, 4], np.uint64)
+    with pytest.raises(ValueError):  # FriPolynomialInfo out of range
+        V.FriCommitPhase.from_openings([a], [[(0, 3)]], pt, al, 1)
+    with pytest.raises(ValueError):  # oracles of different degree
+        V.FriCommitPhase.from_openings([a, b], [[(0, 0), (1, 0)]], pt, al, 1)
+    with pytest.raises(ValueError):  # empty batch
+        V.FriCommitPhase.from_openings([a], [[]], pt, al, 1)
+    a.close()
+    b.close()

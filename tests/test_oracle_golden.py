@@ -177,6 +177,43 @@ def test_fri_layer_against_model(oracle):
         assert co.tolist() == [list(x) for x in mco] and vo.tolist() == [list(x) for x in mvo]
 
 
+def test_fri_final_poly_oracle_vs_model(oracle, model_anchors):
+    """[P2] prove_openings up to final_poly: the C restatement (Horner scan from the top) against the
+    model's explicit sums, the committed anchor, and the defining identity
+    (X - z) Q(X) = F(X) - F(z) checked at a random point for one batch."""
+    from oracle import model as M
+    rnd = random.Random(9)
+    for (n, sizes) in [(1, (1,)), (2, (3,)), (8, (5, 2)), (16, (1, 1, 4)), (32, (7, 3))]:
+        batches = [[[rnd.getrandbits(64) for _ in range(n)] for _ in range(k)] for k in sizes]
+        pts = [(rnd.getrandbits(64) % P, rnd.getrandbits(64) % P) for _ in sizes]
+        alpha = (rnd.getrandbits(64) % P, rnd.getrandbits(64) % P)
+        got = oracle.fri_final_poly([np.array(b, dtype=np.uint64) for b in batches], np.array(pts, dtype=np.uint64),
+                                    np.array(alpha, dtype=np.uint64))
+        want = M.fri_final_poly(batches, pts, alpha)
+        assert got.tolist() == [list(c) for c in want], (n, sizes)
+    g = model_anchors["fri_final_poly"]
+    gb = [unhex(b) for b in g["batches"]]
+    got = oracle.fri_final_poly(gb, unhex(g["points"]), unhex([g["alpha"]])[0])
+    assert np.array_equal(got, unhex(g["final_poly"]))
+    # one batch of one polynomial: final = Q, and (x - z) Q(x) + F(z) = F(x)
+    n = 64
+    f = [rnd.getrandbits(64) % P for _ in range(n)]
+    z, x = (rnd.getrandbits(64) % P, rnd.getrandbits(64) % P), (rnd.getrandbits(64) % P, rnd.getrandbits(64) % P)
+    q = oracle.fri_final_poly([np.array([f], dtype=np.uint64)], np.array([z], dtype=np.uint64),
+                              np.array([5, 6], dtype=np.uint64))
+
+    def ev(coeffs, at):
+        acc = (0, 0)
+        for c in reversed(coeffs):
+            acc = M.ext_mul(acc, at)
+            acc = ((acc[0] + c[0]) % P, (acc[1] + c[1]) % P)
+        return acc
+    fx, fz, qx = ev([(c, 0) for c in f], x), ev([(c, 0) for c in f], z), ev([tuple(int(v) for v in c) for c in q], x)
+    lhs = M.ext_mul(((x[0] - z[0]) % P, (x[1] - z[1]) % P), qx)
+    assert ((lhs[0] + fz[0]) % P, (lhs[1] + fz[1]) % P) == fx
+    assert q[n - 1].tolist() == [0, 0]  # "pad back to power of two"
+
+
 # ------------------------------------------------------------------------------ permutation argument
 def test_zs_partial_products_oracle_vs_model(oracle):
     """[P2] wires_permutation_partial_products_and_zs: the C restatement against the big-integer

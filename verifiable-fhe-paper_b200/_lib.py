@@ -77,6 +77,9 @@ SIGNATURES = {
     "vpbs_fri_layer_commit": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, _c.c_uint32, u64p, u64p, u64p]),
     "vpbs_fri_fold": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, u64p, _c.c_uint64, u64p, u64p]),
     "vpbs_fri_begin": (_c.c_int, [_ctx, u64p, _c.c_uint64, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
+    "vpbs_fri_begin_openings": (_c.c_int, [_ctx, _c.POINTER(_c.c_void_p), _c.c_uint32,
+                                           _c.POINTER(_c.c_uint32), _c.c_uint32, _c.POINTER(_c.c_uint32),
+                                           u64p, u64p, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
     "vpbs_fri_commit_layer": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, u64p]),
     "vpbs_fri_fold_layer": (_c.c_int, [_c.c_void_p, u64p]),
     "vpbs_fri_final_poly": (_c.c_int, [_c.c_void_p, _c.c_uint32, u64p]),

@@ -24,6 +24,7 @@
 #include "../../include/vpbs_commit.h"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "openings.cuh"
 #include "permutation.cuh"
 
 using gl::u32;
@@ -1502,6 +1503,109 @@ int vpbs_fri_begin(vpbs_ctx* ctx, const uint64_t* final_poly_coeffs_ext, uint64_
     vpbs_fri_destroy(f);
     return rc;
   }
+  *out = f;
+  return VPBS_OK;
+}
+
+// [P2] fri/oracle.rs prove_openings up to lde_final_values, from resident batches (openings.cuh).
+int vpbs_fri_begin_openings(vpbs_ctx* ctx, vpbs_batch* const* oracles, uint32_t noracles,
+                            const uint32_t* batch_sizes, uint32_t nbatches, const uint32_t* poly_refs,
+                            const uint64_t* points, const uint64_t alpha[2], uint32_t rate_bits,
+                            vpbs_fri** out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!oracles || !batch_sizes || !poly_refs || !points || !alpha || !out || noracles == 0 || nbatches == 0)
+    return fail(ctx, VPBS_ERR_ARG, "null pointer, no oracles or no batches");
+  *out = nullptr;
+  for (u32 o = 0; o < noracles; o++) {
+    if (!oracles[o] || oracles[o]->ctx != ctx)
+      return fail(ctx, VPBS_ERR_STATE, "oracle batch is NULL or belongs to another context");
+    if (oracles[o]->log_n != oracles[0]->log_n)
+      return fail(ctx, VPBS_ERR_ARG, "all oracles must have the same degree");
+  }
+  const u32 log_n = oracles[0]->log_n;
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  const u64 n = 1ULL << log_n;
+  u64 total = 0;
+  u32 longest = 0;
+  for (u32 b = 0; b < nbatches; b++) {
+    if (batch_sizes[b] == 0) return fail(ctx, VPBS_ERR_ARG, "empty FRI batch");
+    total += batch_sizes[b];
+    if (batch_sizes[b] > longest) longest = batch_sizes[b];
+  }
+  std::vector<const u64*> ptrs(total);
+  for (u64 k = 0; k < total; k++) {
+    const u32 o = poly_refs[2 * k], pi = poly_refs[2 * k + 1];
+    if (o >= noracles || pi >= oracles[o]->ncols)
+      return fail(ctx, VPBS_ERR_ARG, "FriPolynomialInfo out of range");
+    ptrs[k] = oracles[o]->coeffs + (u64)pi * n;
+  }
+  // alpha^j, j <= longest (alpha^len_b is the shift of batch b), on the host
+  auto emul = [](const u64 a[2], const u64 b[2], u64 r[2]) {
+    const u64 t = gl::mul(a[1], b[1]);
+    const u64 re = gl::add(gl::mul(a[0], b[0]), gl::mul(7, t));
+    const u64 im = gl::add(gl::mul(a[0], b[1]), gl::mul(a[1], b[0]));
+    r[0] = re;
+    r[1] = im;
+  };
+  const u64 al[2] = {gl::canon(alpha[0]), gl::canon(alpha[1])};
+  std::vector<u64> pows(2 * ((size_t)longest + 1));
+  pows[0] = 1;
+  pows[1] = 0;
+  for (u32 j = 1; j <= longest; j++) emul(&pows[2 * (j - 1)], al, &pows[2 * j]);
+
+  vpbs_fri* f = new (std::nothrow) vpbs_fri();
+  if (!f) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
+  f->ctx = ctx;
+  f->len = f->cap_len = n << rate_bits;
+  f->shift = gl::COSET_SHIFT;
+  cudaError_t e = pool_alloc(ctx, f->cap_len * 16, &f->coeffs);
+  if (e == cudaSuccess) e = pool_alloc(ctx, f->cap_len * 16, &f->values);
+  if (e == cudaSuccess) e = pool_alloc(ctx, f->cap_len * 16 * 3, &f->scratch);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->coeffs, 0, f->cap_len * 16, ctx->stream);  // lde(): zero padding
+  if (e != cudaSuccess) {
+    pool_free(ctx, f->coeffs, f->cap_len * 16);
+    pool_free(ctx, f->values, f->cap_len * 16);
+    pool_free(ctx, f->scratch, f->cap_len * 16 * 3);
+    delete f;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? VPBS_ERR_OOM : VPBS_ERR_CUDA,
+                std::string("fri begin: ") + cudaGetErrorString(e));
+  }
+  ctx->fri_chains.insert(f);
+  auto bail = [&](int code) {
+    vpbs_fri_destroy(f);
+    return code;
+  };
+  const u64 nblocks = (n + openings::DIV_BLOCK - 1) / openings::DIV_BLOCK;
+  u64 *d_ptrs = nullptr, *d_pows = nullptr, *d_tot = nullptr;
+  if ((rc = arena_get(ctx, "open_ptrs", total * 8, (void**)&d_ptrs))) return bail(rc);
+  if ((rc = arena_get(ctx, "open_pows", pows.size() * 8, (void**)&d_pows))) return bail(rc);
+  if ((rc = arena_get(ctx, "open_tot", nblocks * 32, (void**)&d_tot))) return bail(rc);
+  ulonglong2* comp = (ulonglong2*)f->scratch;  // n extension elements; free until fri_evaluate
+  ulonglong2* totals = (ulonglong2*)d_tot;
+  ulonglong2* carries = totals + nblocks;
+  if (cudaMemcpyAsync(d_ptrs, ptrs.data(), total * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaMemcpyAsync(d_pows, pows.data(), pows.size() * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    return bail(fail(ctx, VPBS_ERR_CUDA, "openings: upload failed"));
+  u64 off = 0;
+  for (u32 b = 0; b < nbatches; b++) {
+    const u32 len = batch_sizes[b];
+    const u64 z0 = gl::canon(points[2 * b]), z1 = gl::canon(points[2 * b + 1]);
+    openings::reduce_polys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        (const u64* const*)d_ptrs + off, len, (const ulonglong2*)d_pows, n, comp);
+    openings::divide_pass1<<<(unsigned)nblocks, openings::DIV_THREADS, 0, ctx->stream>>>(comp, n, z0, z1, totals);
+    openings::divide_carries<<<1, 32, 0, ctx->stream>>>(totals, nblocks, z0, z1, carries);
+    openings::divide_pass2<<<(unsigned)nblocks, openings::DIV_THREADS, 0, ctx->stream>>>(
+        comp, n, z0, z1, carries, pows[2 * (size_t)len], pows[2 * (size_t)len + 1], b == 0,
+        (ulonglong2*)f->coeffs);
+    ctx->launches += 4;
+    off += len;
+  }
+  if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, VPBS_ERR_CUDA, "openings: launch failed"));
+  if ((rc = fri_evaluate(f))) return bail(rc);  // lde_final_values ("perform final FFT")
+  // the pointer / power tables above are host vectors: make sure the copies have left them
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    return bail(fail(ctx, VPBS_ERR_CUDA, "openings: synchronize failed"));
   *out = f;
   return VPBS_OK;
 }

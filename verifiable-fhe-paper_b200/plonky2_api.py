@@ -267,6 +267,31 @@ class FriCommitPhase:
         self.ctx.check(self.ctx.lib.vpbs_fri_begin(self.ctx.handle, _ptr(c), c.shape[0], rate_bits,
                                                    ctypes.byref(self.handle)))
 
+    @classmethod
+    def from_openings(cls, oracles, batches, points, alpha, rate_bits: int) -> "FriCommitPhase":
+        """[P2] fri/oracle.rs PolynomialBatch::prove_openings up to lde_final_values, on the device
+        (vpbs_fri_begin_openings).  oracles: ResidentPolynomialBatch list; batches: per FRI batch the
+        list of (oracle_index, polynomial_index) ([P2] FriBatchInfo.polynomials); points: one extension
+        point (re, im) per batch; alpha: the extension challenge."""
+        self = cls.__new__(cls)
+        self.ctx = oracles[0].ctx
+        sizes = np.array([len(b) for b in batches], np.uint32)
+        refs = np.array([r for b in batches for r in b], np.uint32).reshape(-1, 2)
+        pts = _as_u64(points).reshape(-1, 2)
+        if pts.shape[0] != len(batches) or sizes.size == 0 or (sizes == 0).any():
+            raise ValueError("one opening point per non-empty FRI batch")
+        hs = (ctypes.c_void_p * len(oracles))(*[o.handle for o in oracles])
+        self.rate_bits = rate_bits
+        self.len = (1 << oracles[0].degree_log) << rate_bits
+        self.layers = []
+        self.handle = ctypes.c_void_p()
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        self.ctx.check(self.ctx.lib.vpbs_fri_begin_openings(
+            self.ctx.handle, hs, len(oracles), sizes.ctypes.data_as(u32p), sizes.size,
+            np.ascontiguousarray(refs).ctypes.data_as(u32p), _ptr(pts), _ptr(_as_u64(alpha).reshape(2)),
+            rate_bits, ctypes.byref(self.handle)))
+        return self
+
     def commit_layer(self, arity_bits: int, cap_height: int) -> np.ndarray:
         cap = np.empty((1 << cap_height, 4), np.uint64)
         self.ctx.check(self.ctx.lib.vpbs_fri_commit_layer(self.handle, arity_bits, cap_height, _ptr(cap)))
