@@ -387,6 +387,12 @@ def main():
     ap.add_argument("--chain-steps", type=int, default=0,
                     help="BASELINE configs[3] stand-in: that many sequentially dependent N=1024 IVC "
                          "step stand-ins (3 commits each) through the host C ABI; prints its own line")
+    ap.add_argument("--chain-log-n", type=int, default=LOG_N,
+                    help="rows of the chained step stand-in (16: N=1024, BASELINE configs[2-4]; 13: the "
+                         "N=8 test circuit's size, configs[0])")
+    ap.add_argument("--chain-eager", action="store_true",
+                    help="with --chain-steps: also time round 1's eager form of the step (all outputs "
+                         "of the first two commits downloaded)")
     ap.add_argument("--shard-commit", action="store_true",
                     help="strong scaling of ONE commit: every rank computes its row range "
                          "(vpbs_commit_shard_dev) and the subtree roots are all-gathered over NCCL")
@@ -857,6 +863,14 @@ def run_step_standin(V, ctx, dev, n, m, ncap, d_digests, d_cap, pinned, colptrs,
     del bufs
     perms = sum(permutations(c, n, RATE_BITS, CAP_HEIGHT) for c, _ in shapes)
     kernels_ms = min(tot[1:])
+    # build()'s one-off constants/sigmas commit (~85 columns x 2^16, ivc_based_vpbs.rs:275)
+    cs = torch.from_numpy(V.synthetic_columns(85, n, 0x5EED0000 + 85).view(np.int64)).to(dev)
+    cs_co = torch.empty((85, n), dtype=torch.int64, device=dev)
+    cs_le = torch.empty((m, 85), dtype=torch.int64, device=dev)
+    cs_ms = min(V.commit_device(ctx, cs.data_ptr(), 85, LOG_N, RATE_BITS, CAP_HEIGHT, False, cs_co.data_ptr(),
+                                cs_le.data_ptr(), d_digests.data_ptr(), d_cap.data_ptr(),
+                                want_stats=True)["total_ms"] for _ in range(4))
+    del cs, cs_co, cs_le
 
     # (b) resident pipeline
     num_routed, max_degree = 80, 8
@@ -912,6 +926,8 @@ def run_step_standin(V, ctx, dev, n, m, ncap, d_digests, d_cap, pinned, colptrs,
     return {"what": "three commits of one N=1024 IVC step (135 wire + 20 Z/partial-product value "
                     "columns, 16 quotient coefficient columns, 2^16 rows)",
             "kernels_ms": kernels_ms, "permutations": perms,
+            "constants_sigmas_commit_ms": cs_ms,
+            "constants_sigmas_note": "build()'s one-off commit, 85 value columns x 2^16 rows, kernels only",
             "int_frac": perms * IMAD_PER_PERMUTATION / (kernels_ms * 1e-3) / 1e9 / int_peak,
             "resident_pipeline_ms": res_ms, "resident_h2d_bytes": h2d, "resident_d2h_bytes": d2h,
             "resident_api": "vpbs_batch_commit(wires) -> vpbs_batch_zs_partial_products (Z computed and "
@@ -990,71 +1006,170 @@ def run_shard_commit_record(V, ctx, rank, world, dev, barrier, max_over_ranks, c
 
 
 def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
-    """BASELINE.json configs[3]/[4] stand-in: a chain of sequentially dependent IVC-step stand-ins,
-    one chain per GPU.  Each step = the three commits of one N=1024 step proof through the HOST C
-    ABI: wires (135 value columns) and Z/partial products (20) with full outputs (the CPU prover
-    reads their LDE), quotient chunks (16 coefficient columns) as a resident batch opened at 28
-    query positions.  Step k+1's inputs depend on step k's caps (as the real chain's witness
-    contains the previous proof, ivc_based_vpbs.rs:329), so nothing can be pipelined across steps.
-    The real step proof (witness generation, quotient, FRI) needs plonky2 and cannot run here."""
+    """BASELINE.json configs[3]/[4] stand-in (configs[0] with --chain-log-n 13): a chain of
+    sequentially dependent IVC-step stand-ins, one chain per GPU.  Step k+1's inputs depend on step
+    k's caps (as the real chain's witness contains the previous proof, ivc_based_vpbs.rs:329), so
+    nothing can be pipelined across steps.  Two forms of the step are timed:
+      resident (the product path): everything of prove() this repository puts on the device —
+        wires commit (135 value columns from the host) -> Z / partial products computed and committed
+        on the device (20) -> quotient-chunk commit (16 coefficient columns from the host) ->
+        openings of all 171 polynomials at zeta / g zeta -> prove_openings (alpha-combination,
+        division by X - z, final-polynomial LDE) -> FRI commit phase (3 arity-16 layers: tree, cap to
+        the host, beta back, fold) -> final polynomial -> 16-bit proof-of-work grind -> 28 query rounds
+        served from the three resident batches and the FRI layers;
+      eager (round 1's form): the three commits with every output downloaded.
+    The challenges are derived from the caps by plain mixing (a stand-in for the Poseidon
+    challenger, which stays on the CPU); witness generation and the gate constraints of the quotient
+    need plonky2 and are not part of either number."""
     import numpy as np
     lib, u64p = ctx.lib, V._lib.u64p
-    n, m, ncap = 1 << LOG_N, (1 << LOG_N) << RATE_BITS, 1 << CAP_HEIGHT
+    log_n = args.chain_log_n
+    n, m, ncap = 1 << log_n, (1 << log_n) << RATE_BITS, 1 << CAP_HEIGHT
+    nlayers = log_n + RATE_BITS - CAP_HEIGHT
 
     def pinned(shape):
         p = lib.vpbs_host_alloc(int(np.prod(shape)) * 8)
         buf = (ctypes.c_uint64 * int(np.prod(shape))).from_address(p)
         return np.ctypeslib.as_array(buf).reshape(shape)
 
-    shapes = [(135, False), (20, False), (16, True)]
-    ins, coeffs, leaves, digests, caps = [], [], [], [], []
-    for i, (c, _) in enumerate(shapes):
-        a = pinned((c, n)); a[:] = V.synthetic_columns(c, n, 0x5EED0000 + 1000 * rank + c)
-        ins.append(a); coeffs.append(pinned((c, n))); caps.append(pinned((ncap, 4)))
-        if i < 2:
-            leaves.append(pinned((m, c))); digests.append(pinned((2 * (m - ncap), 4)))
-    qidx = np.random.default_rng(1).integers(0, m, size=28, dtype=np.uint64)
-    qrows = np.empty((28, 16), np.uint64)
-    qsib = np.empty((28, LOG_N + RATE_BITS - CAP_HEIGHT, 4), np.uint64)
-
     def ptrs(a):
         return (u64p * a.shape[0])(*[a[c].ctypes.data_as(u64p) for c in range(a.shape[0])])
 
-    pin, pco = [ptrs(a) for a in ins], [ptrs(a) for a in coeffs]
+    shapes = [(135, False), (20, False), (16, True)]
+    ins, caps = [], []
+    for i, (c, _) in enumerate(shapes):
+        a = pinned((c, n)); a[:] = V.synthetic_columns(c, n, 0x5EED0000 + 1000 * rank + c)
+        ins.append(a); caps.append(pinned((ncap, 4)))
+    pin = [ptrs(a) for a in ins]
+    num_routed, max_degree = 80, 8
+    sig = V.Sigmas(V.synthetic_columns(num_routed, n, 0x51630000), V.get_unique_coset_shifts(n, num_routed), ctx)
+    g_n = pow(7, (P_GL - 1) >> log_n, P_GL)  # generator of the trace subgroup
 
-    def step():
-        for i in range(2):
-            ctx.check(lib.vpbs_commit(ctx.handle, pin[i], shapes[i][0], LOG_N, RATE_BITS, CAP_HEIGHT, 0,
-                                      None, pco[i], leaves[i].ctypes.data_as(u64p),
-                                      digests[i].ctypes.data_as(u64p), caps[i].ctypes.data_as(u64p), None))
-            ins[i + 1][:, 0] ^= caps[i].reshape(-1)[: shapes[i + 1][0]] >> np.uint64(1)  # Fiat-Shamir-like dependency
-        h = ctypes.c_void_p()
-        ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, LOG_N, RATE_BITS, CAP_HEIGHT, 1, None,
-                                        caps[2].ctypes.data_as(u64p), ctypes.byref(h), None))
-        ctx.check(lib.vpbs_batch_get_leaves(h, qidx.ctypes.data_as(u64p), 28, qrows.ctypes.data_as(u64p)))
-        ctx.check(lib.vpbs_batch_prove(h, qidx.ctypes.data_as(u64p), 28, qsib.ctypes.data_as(u64p)))
-        lib.vpbs_batch_destroy(h)
-        ins[0][:, 0] ^= np.resize(caps[2].reshape(-1), 135) >> np.uint64(1)  # next step depends on this one
+    def challenge(cap, k, count):  # stand-in for challenger.get_n_challenges (see docstring)
+        x = cap.reshape(-1).astype(np.uint64)
+        seed = int(np.bitwise_xor.reduce(x * np.uint64(2 * k + 1))) ^ (k * 0x9E3779B97F4A7C15)
+        return np.random.default_rng(seed % (1 << 63)).integers(1, P_GL, size=count, dtype=np.uint64)
+
+    opens = [np.empty((2, c, 2), np.uint64) for c, _ in shapes]
+    rows = [np.empty((28, c), np.uint64) for c, _ in shapes]
+    sibs = [np.empty((28, nlayers, 4), np.uint64) for _ in shapes]
+    fri_batches = [[(o, j) for o, (c, _) in enumerate(shapes) for j in range(c)], [(1, 0), (1, 1)]]
+    stats = {"fri_layers": 0}
+
+    def resident_step():
+        hs = [ctypes.c_void_p() for _ in range(3)]
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[0], 135, log_n, RATE_BITS, CAP_HEIGHT, 0, None,
+                                        caps[0].ctypes.data_as(u64p), ctypes.byref(hs[0]), None))
+        bg = challenge(caps[0], 1, 4)
+        ctx.check(lib.vpbs_batch_zs_partial_products(hs[0], sig.handle, max_degree, bg[:2].ctypes.data_as(u64p),
+                                                     bg[2:].ctypes.data_as(u64p), 2, RATE_BITS, CAP_HEIGHT,
+                                                     caps[1].ctypes.data_as(u64p), ctypes.byref(hs[1]), None))
+        ins[2][:, 0] ^= caps[1].reshape(-1)[:16] >> np.uint64(1)  # the quotient depends on alpha <- cap 1
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, log_n, RATE_BITS, CAP_HEIGHT, 1, None,
+                                        caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
+        zeta = challenge(caps[2], 2, 2)
+        gz = np.array([int(zeta[0]) * g_n % P_GL, int(zeta[1]) * g_n % P_GL], np.uint64)
+        pts = np.stack([zeta, gz])
+        for k in range(3):  # OpeningSet::new
+            ctx.check(lib.vpbs_batch_eval_ext2(hs[k], pts.ctypes.data_as(u64p), 2, opens[k].ctypes.data_as(u64p)))
+        alpha = challenge(opens[2][0, :4].copy(), 3, 2)
+        obs = [_Resident(ctx, h, log_n) for h in hs]
+        fri = V.FriCommitPhase.from_openings(obs, fri_batches, pts, alpha, RATE_BITS)
+        lg, k, cap = log_n + RATE_BITS, 0, caps[2]
+        while lg - RATE_BITS > 5 and lg - 4 >= CAP_HEIGHT:  # ConstantArityBits(4, 5)
+            cap = fri.commit_layer(4, min(CAP_HEIGHT, lg - 4))
+            fri.fold(challenge(cap, 4 + k, 2))
+            lg -= 4
+            k += 1
+        stats["fri_layers"] = k
+        final = fri.final_poly()
+        pow_state = challenge(final[: min(4, final.shape[0])].copy(), 9, 12)
+        w = V.fri_proof_of_work(pow_state, 5, 16, ctx=ctx)
+        qidx = np.random.default_rng(int(w or 0) + 1).integers(0, m, size=28, dtype=np.uint64)
+        for b in range(3):
+            ctx.check(lib.vpbs_batch_get_leaves(hs[b], qidx.ctypes.data_as(u64p), 28, rows[b].ctypes.data_as(u64p)))
+            ctx.check(lib.vpbs_batch_prove(hs[b], qidx.ctypes.data_as(u64p), 28, sibs[b].ctypes.data_as(u64p)))
+        qi = qidx.copy()
+        for layer in range(k):
+            qi = qi >> np.uint64(4)
+            fri.query(layer, qi)
+        fri.close()
+        for h in reversed(hs):
+            lib.vpbs_batch_destroy(h)
+        ins[0][:, 0] ^= np.resize(caps[2].reshape(-1) ^ cap.reshape(-1)[:1], 135) >> np.uint64(1)  # next step
+
+    class _Resident:  # the two attributes FriCommitPhase.from_openings reads
+        def __init__(self, c, h, lg):
+            self.ctx, self.handle, self.degree_log = c, h, lg
+
+    out_eager = None
+    if args.chain_eager:
+        coeffs = [pinned((c, n)) for c, _ in shapes]
+        leaves = [pinned((m, c)) for c, _ in shapes[:2]]
+        digests = [pinned((2 * (m - ncap), 4)) for _ in shapes[:2]]
+        pco = [ptrs(a) for a in coeffs]
+        qidx0 = np.random.default_rng(1).integers(0, m, size=28, dtype=np.uint64)
+
+        def eager_step():
+            for i in range(2):
+                ctx.check(lib.vpbs_commit(ctx.handle, pin[i], shapes[i][0], log_n, RATE_BITS, CAP_HEIGHT, 0,
+                                          None, pco[i], leaves[i].ctypes.data_as(u64p),
+                                          digests[i].ctypes.data_as(u64p), caps[i].ctypes.data_as(u64p), None))
+                ins[i + 1][:, 0] ^= caps[i].reshape(-1)[: shapes[i + 1][0]] >> np.uint64(1)
+            h = ctypes.c_void_p()
+            ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, log_n, RATE_BITS, CAP_HEIGHT, 1, None,
+                                            caps[2].ctypes.data_as(u64p), ctypes.byref(h), None))
+            ctx.check(lib.vpbs_batch_get_leaves(h, qidx0.ctypes.data_as(u64p), 28, rows[2].ctypes.data_as(u64p)))
+            ctx.check(lib.vpbs_batch_prove(h, qidx0.ctypes.data_as(u64p), 28, sibs[2].ctypes.data_as(u64p)))
+            lib.vpbs_batch_destroy(h)
+            ins[0][:, 0] ^= np.resize(caps[2].reshape(-1), 135) >> np.uint64(1)
+
+        for _ in range(3):
+            eager_step()
+        barrier()
+        k_e = min(args.chain_steps, 64)
+        t0 = time.perf_counter()
+        for _ in range(k_e):
+            eager_step()
+        out_eager = max_over_ranks(time.perf_counter() - t0) / k_e * 1e3
 
     for _ in range(3):
-        step()
+        resident_step()
     barrier()
+    l0 = ctx.kernel_launches
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.chain_steps):
-        step()
+        resident_step()
     dt = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (ctx.kernel_launches - l0) // args.chain_steps
     barrier()
+    sig.close()
     if rank == 0:
+        h2d = 8 * n * (135 + 16) + 16 * 8
+        d2h = (3 * 32 * ncap + 171 * 2 * 16 + stats["fri_layers"] * 32 * ncap +
+               28 * sum(8 * c + 32 * nlayers for c, _ in shapes))
         emit(({
-            "metric": "N=1024 vPBS IVC step stand-in (3 commits: 135 + 20 value columns, 16 coefficient "
-                      "columns, 2^16 rows) through the host C ABI, sequentially dependent chain",
-            "value": dt / args.chain_steps * 1e3, "unit": "ms per step (commit part only)",
+            "metric": "N=%d-class vPBS IVC step stand-in (2^%d rows): wires / Z / quotient commits, openings, "
+                      "prove_openings and the FRI commit phase device-resident through the host C ABI, "
+                      "sequentially dependent chain" % (1024 if log_n == 16 else 8 if log_n == 13 else 0, log_n),
+            "value": dt / args.chain_steps * 1e3, "unit": "ms per step (device-side scope of prove())",
             "higher_is_better": False, "n_gpus": world, "steps": args.chain_steps,
             "chains": world, "steps_per_s_all_gpus": world * args.chain_steps / dt,
             "full_pbs_730_steps_s": 730 * dt / args.chain_steps, "scaling": "weak", "dtype": "u64",
-            "data": "synthetic", "vs_baseline": None,
-            "note": "commit path only: witness generation, quotient polynomials and FRI of the real "
-                    "step proof run in plonky2 on the CPU and are not part of this number"}))
+            "data": "synthetic", "vs_baseline": None, "log_n": log_n,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step_approx": d2h,
+            "gpu_launches_per_step": int(launches), "fri_layers": stats["fri_layers"],
+            "eager_commits_ms_per_step": out_eager,
+            "eager_note": "round 1's form of the step: the three commits with coefficients, LDE rows and "
+                          "digests of the first two downloaded to pinned host memory (--chain-eager)",
+            "clocks": clocks,
+            "note": "witness generation, the gate constraints of the quotient and the Poseidon challenger "
+                    "run in plonky2 on the CPU and are not part of this number; challenges are derived from "
+                    "the caps by plain mixing"}))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

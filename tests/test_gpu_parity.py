@@ -266,8 +266,10 @@ def test_microbench_config_full_size(V, ctx, oracle):
 
 
 def test_step_shapes_full_size(V, ctx, oracle):
-    """BASELINE.json configs[2] stand-in: the three commits of one N=1024 IVC step."""
-    for (ncols, coeffs, seed) in ((135, False, 0x5EED0000), (20, False, 0x5EED1000), (16, True, 0x5EED2000)):
+    """BASELINE.json configs[2] stand-in: the three commits of one N=1024 IVC step, and build()'s
+    one-off constants/sigmas commit (~85 columns, ivc_based_vpbs.rs:275)."""
+    for (ncols, coeffs, seed) in ((135, False, 0x5EED0000), (20, False, 0x5EED1000), (16, True, 0x5EED2000),
+                                  (85, False, 0x5EED3000)):
         cols = V.synthetic_columns(ncols, 1 << 16, seed)
         f = V.PolynomialBatch.from_coeffs if coeffs else V.PolynomialBatch.from_values
         b = f(cols, 3, False, 4, ctx=ctx)
