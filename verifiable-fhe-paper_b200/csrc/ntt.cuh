@@ -612,7 +612,7 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
       for (int j = 0; j < 16; j++) {
         const u64 pos = ((u64)bx << 8) + 16 * q_hi + j;
         const u64 v = (out_scale != 1) ? gl::mul(x[j], out_scale) : gl::canon(x[j]);
-        dst[(row0 + pos) * dst_stride + col] = v;
+        __stcs(reinterpret_cast<unsigned long long*>(dst + (row0 + pos) * dst_stride + col), v);  // streaming: leaf rows are not re-read before the whole LDE is done
       }
     }
     if (next >= ntiles) break;
