@@ -901,3 +901,24 @@ def test_prove_openings_rejects_bad_instances(V, ctx):
         V.FriCommitPhase.from_openings([a], [[]], pt, al, 1)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("log_n,ncols,rate_bits,cap_height,coeffs", [
+    (12, 64, 3, 4, False), (12, 70, 3, 4, False), (13, 135, 3, 4, False), (12, 100, 2, 0, True),
+    (12, 65, 1, 13, False), (14, 128, 3, 4, False)])
+def test_resident_commit_of_wide_host_batches(V, ctx, oracle, log_n, ncols, rate_bits, cap_height, coeffs):
+    """vpbs_batch_commit on batches wide enough to travel in column chunks (>= 64 columns, >= 2^12
+    rows: chunk k's IFFT and its columns of every LDE block run while chunk k+1 is on the bus), incl.
+    a ragged last chunk, a last chunk of one column, widths that are not multiples of 8, the all-cap
+    tree and from_coeffs.  Everything equals the oracle's commit."""
+    rng = np.random.default_rng(log_n * 1000 + ncols)
+    cols = rand_u64(rng, (ncols, 1 << log_n))
+    rb = V.commit_resident(cols, rate_bits, False, cap_height, coeffs, ctx=ctx)
+    ref = oracle.commit(cols, rate_bits, cap_height, coeffs)
+    assert np.array_equal(rb.merkle_tree.cap, ref["cap"])
+    eager = rb.download()
+    assert np.array_equal(eager.merkle_tree.leaves, ref["leaves"])
+    assert np.array_equal(eager.merkle_tree.digests, ref["digests"])
+    if not coeffs:
+        assert np.array_equal(eager.polynomials, ref["coeffs"])
+    rb.close()
