@@ -469,7 +469,9 @@ pass_strided_r16t(const __grid_constant__ tma::TileMap map, u64* __restrict__ ds
                   unsigned log_B, const u64* __restrict__ in_scale, Roots R, unsigned tiles_x,
                   unsigned ntiles) {
   extern __shared__ u64 dyn_raw[];
-  u64* dyn = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(dyn_raw) + 127) & ~(uintptr_t)127);
+  // 128-byte aligned start, by pointer arithmetic ON the shared array (a round trip through an integer
+  // would turn every access below into a generic LD / ST instead of LDS / STS)
+  u64* dyn = dyn_raw + (((128u - (tma::smem_u32(dyn_raw) & 127u)) & 127u) >> 3);
   u64* buf = dyn;                  // [2][256 * 16], dense [q][low]: what the box lands as
   u64* tw = dyn + 2 * 256 * 16;    // [128]
   u64* sq = tw + 128;              // [256]
@@ -550,7 +552,9 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
                 u64 dst_stride, u64 row0, u64 out_scale, Roots R, unsigned in_tw_log_B,
                 const u64* __restrict__ in_tw_scale, unsigned tiles_x, unsigned ntiles) {
   extern __shared__ u64 dyn_raw[];
-  u64* dyn = reinterpret_cast<u64*>((reinterpret_cast<uintptr_t>(dyn_raw) + 127) & ~(uintptr_t)127);
+  // 128-byte aligned start, by pointer arithmetic ON the shared array (a round trip through an integer
+  // would turn every access below into a generic LD / ST instead of LDS / STS)
+  u64* dyn = dyn_raw + (((128u - (tma::smem_u32(dyn_raw) & 127u)) & 127u) >> 3);
   u64* buf = dyn;                  // [2][16 * 256], dense [lane][q]
   u64* tw = dyn + 2 * 256 * 16;    // [128]
   u64* tws = tw + 128;             // [2][256]
