@@ -540,16 +540,20 @@ pass_strided_r16t(const __grid_constant__ tma::TileMap map, u64* __restrict__ ds
   }
 }
 
-// pass_final_r16p<., STORE_LEAF> with the tile fetched by TMA.  map: rank-2 tensor (position < n,
-// column < ncols), box 256 x 16: the tile lands dense as [lane][q] (no padding possible), so the
-// register exchange swizzles the low four bits of q with the lane (slot = lane * 256 + (q ^ lane)):
-// the stage-1 stores then touch slots read by threads of the same half-warp (a __syncwarp orders
-// them) and both exchange accesses are bank-conflict free (the padded cp.async form had 7.7e5
-// conflicts per launch).
-template <bool INVERSE>
+// pass_final_r16p with the tile fetched by TMA.
+//   STORE_LEAF:    map = rank-2 tensor (position < n, column < ncols), box 256 x 16.
+//   STORE_NATURAL: map = rank-4 tensor (position < 256, block_lo < 2^(log_nb - 4), block_hi < 16,
+//                  column), box 256 x 1 x 16 x 1 at block_lo = bitrev(tile_x): the 16 blocks whose
+//                  bit-reversed ids are consecutive lie 2^(log_nb - 4) blocks apart; row i of the tile
+//                  is block_hi = i, i.e. the block the cp.async form calls lane bitrev4(i).
+// The tile lands dense as [lane][q] (no padding possible), so the register exchange swizzles the low
+// four bits of q with the lane (slot = lane * 256 + (q ^ lane)): the stage-1 stores then touch slots
+// read by threads of the same half-warp (a __syncwarp orders them) and both exchange accesses are
+// bank-conflict free (the padded cp.async form had 7.7e5 conflicts per launch).
+template <bool INVERSE, int MODE>
 __global__ void __launch_bounds__(THREADS, R16P_MIN_BLOCKS)
 pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* __restrict__ dst,
-                u64 dst_stride, u64 row0, u64 out_scale, Roots R, unsigned in_tw_log_B,
+                u64 dst_stride, u64 row0, unsigned log_n, u64 out_scale, Roots R, unsigned in_tw_log_B,
                 const u64* __restrict__ in_tw_scale, unsigned tiles_x, unsigned ntiles) {
   extern __shared__ u64 dyn_raw[];
   // 128-byte aligned start, by pointer arithmetic ON the shared array (a round trip through an integer
@@ -559,7 +563,8 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
   u64* tw = dyn + 2 * 256 * 16;    // [128]
   u64* tws = tw + 128;             // [2][256]
   u64* bar = tws + 2 * 256;        // [2]
-  const bool in_tw = in_tw_log_B != 0;
+  const unsigned log_nb = log_n - 8;
+  const bool in_tw = MODE == STORE_LEAF && in_tw_log_B != 0;
   const unsigned q_lo = threadIdx.x & 15, lane_a = threadIdx.x >> 4;
   const unsigned lane_b = threadIdx.x & 15, q_hi = threadIdx.x >> 4;
   if (threadIdx.x < 128) tw[threadIdx.x] = root_of<INVERSE>(R, 8, threadIdx.x);
@@ -572,7 +577,11 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
   }
   auto issue = [&](unsigned tl, unsigned b) {  // one thread
     tma::mbar_expect_tx(bar + b, tma::TILE_BYTES);
-    tma::load_2d(buf + b * (256 * 16), &map, bar + b, (int)((tl % tiles_x) << 8), (int)((tl / tiles_x) << 4));
+    if (MODE == STORE_LEAF)
+      tma::load_2d(buf + b * (256 * 16), &map, bar + b, (int)((tl % tiles_x) << 8), (int)((tl / tiles_x) << 4));
+    else
+      tma::load_4d(buf + b * (256 * 16), &map, bar + b, 0, (int)brev(tl % tiles_x, log_nb - 4), 0,
+                   (int)(tl / tiles_x));
   };
   auto twiddle = [&](unsigned tl) -> u64 {  // pending four-step twiddle (times the g^low scaling)
     return root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev((tl % tiles_x) & 255u, 8));
@@ -610,13 +619,23 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
     __syncthreads();  // everyone is done with `cur` before the next bulk copy refills it
     dif16<false>(x, tw, 1, 0, 4);
     const unsigned bx = tile % tiles_x, by = tile / tiles_x;
-    const unsigned col = by * 16 + lane_b;
-    if (col < ncols) {
+    if (MODE == STORE_LEAF) {
+      const unsigned col = by * 16 + lane_b;
+      if (col < ncols) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const u64 pos = ((u64)bx << 8) + 16 * q_hi + j;
+          const u64 v = (out_scale != 1) ? gl::mul(x[j], out_scale) : gl::canon(x[j]);
+          // streaming: leaf rows are not re-read before the whole LDE is done
+          __stcs(reinterpret_cast<unsigned long long*>(dst + (row0 + pos) * dst_stride + col), v);
+        }
+      }
+    } else {
+      u64* out = dst + (u64)by * dst_stride + (u64)bx * 16 + brev(lane_b, 4);
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        const u64 pos = ((u64)bx << 8) + 16 * q_hi + j;
         const u64 v = (out_scale != 1) ? gl::mul(x[j], out_scale) : gl::canon(x[j]);
-        __stcs(reinterpret_cast<unsigned long long*>(dst + (row0 + pos) * dst_stride + col), v);  // streaming: leaf rows are not re-read before the whole LDE is done
+        out[(u64)brev(16 * q_hi + j, 8) << log_nb] = v;
       }
     }
     if (next >= ntiles) break;

@@ -356,8 +356,8 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
         tiled = make_tile_map(&map, cur, 2, dims, strides, box);
       }
       if (tiled)
-        ntt::pass_final_r16t<INVERSE><<<pgrid, ntt::THREADS, ntt::R16T_FINAL_SMEM, stream>>>(
-            map, ncols, dst, dst_stride, row0, out_scale, R, tw_at_load ? log_n : 0u,
+        ntt::pass_final_r16t<INVERSE, ntt::STORE_LEAF><<<pgrid, ntt::THREADS, ntt::R16T_FINAL_SMEM, stream>>>(
+            map, ncols, dst, dst_stride, row0, log_n, out_scale, R, tw_at_load ? log_n : 0u,
             tw_at_load ? in_scale : nullptr, grid.x, ntiles);
       else if (s == 8)
         ntt::pass_final_r16p<INVERSE, ntt::STORE_LEAF><<<pgrid, ntt::THREADS, ntt::R16P_FINAL_SMEM, stream>>>(
@@ -373,7 +373,19 @@ int run_transform(vpbs_ctx* ctx, const u64* src, u64 src_stride, unsigned ncols,
       dim3 grid((unsigned)(n >> (s + log_T)), ncols);
       const unsigned ntiles = grid.x * grid.y;
       const unsigned pgrid = ntiles < ctx->sms * ntt::R16P_MIN_BLOCKS ? ntiles : ctx->sms * ntt::R16P_MIN_BLOCKS;
-      if (s == 8 && log_T == 4)
+      ntt::tma::TileMap map;
+      bool tiled = false;
+      if (s == 8 && log_T == 4 && !scale) {  // 16 blocks 2^(log_nb - 4) apart, 256 positions each
+        const unsigned log_nb = log_n - 8;
+        const u64 dims[4] = {256, 1ULL << (log_nb - 4), 16, ncols};
+        const u64 strides[3] = {256, 256ULL << (log_nb - 4), cur_stride};
+        const unsigned box[4] = {256, 1, 16, 1};
+        tiled = make_tile_map(&map, cur, 4, dims, strides, box);
+      }
+      if (tiled)
+        ntt::pass_final_r16t<INVERSE, ntt::STORE_NATURAL><<<pgrid, ntt::THREADS, ntt::R16T_FINAL_SMEM, stream>>>(
+            map, ncols, dst, dst_stride, row0, log_n, out_scale, R, 0u, nullptr, grid.x, ntiles);
+      else if (s == 8 && log_T == 4)
         ntt::pass_final_r16p<INVERSE, ntt::STORE_NATURAL><<<pgrid, ntt::THREADS, ntt::R16P_FINAL_SMEM, stream>>>(
             cur, cur_stride, ncols, dst, dst_stride, row0, log_n, scale, out_scale, R, 0u, nullptr,
             grid.x, ntiles);
@@ -649,8 +661,10 @@ cudaError_t allow_large_smem() {
   set((const void*)ntt::pass_strided_r16t<false, true>, ntt::R16T_STRIDED_SMEM);
   set((const void*)ntt::pass_strided_r16t<true, false>, ntt::R16T_STRIDED_SMEM);
   set((const void*)ntt::pass_strided_r16t<true, true>, ntt::R16T_STRIDED_SMEM);
-  set((const void*)ntt::pass_final_r16t<false>, ntt::R16T_FINAL_SMEM);
-  set((const void*)ntt::pass_final_r16t<true>, ntt::R16T_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16t<false, ntt::STORE_LEAF>, ntt::R16T_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16t<true, ntt::STORE_LEAF>, ntt::R16T_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16t<false, ntt::STORE_NATURAL>, ntt::R16T_FINAL_SMEM);
+  set((const void*)ntt::pass_final_r16t<true, ntt::STORE_NATURAL>, ntt::R16T_FINAL_SMEM);
   return e;
 }
 
