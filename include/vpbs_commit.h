@@ -149,11 +149,13 @@ int vpbs_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols, uint
                 uint64_t* digests_out, uint64_t* cap_out, vpbs_stats* stats);
 
 /* The same commit spread over nctx GPUs of this process (SURVEY.md §8(b) vpbs_commit_multi, §8(e)
- * partitioning B).  Every GPU receives all input columns; GPU g transforms and hashes only leaf rows
- * [g*m/nctx, (g+1)*m/nctx) — whole LDE blocks, already in leaf order — and copies those rows, the
- * digests and the cap entries of the cap subtrees above them straight into the caller's buffers
- * over its own host link; coefficient column c comes from GPU c*nctx/ncols.  There is no
- * GPU-to-GPU traffic and the outputs are bit-identical to vpbs_commit's.
+ * partitioning B).  Every GPU needs all input columns: each column chunk crosses PCIe once, into
+ * the GPU that owns it (chunks round-robin over the GPUs, all host links in parallel), and reaches
+ * the others by peer copies (NVLink where peer access exists); GPU g transforms and hashes only leaf
+ * rows [g*m/nctx, (g+1)*m/nctx) — whole LDE blocks, already in leaf order — and copies those rows,
+ * the digests and the cap entries of the cap subtrees above them straight into the caller's buffers
+ * over its own host link; coefficient column c comes from GPU c*nctx/ncols.  The outputs are
+ * bit-identical to vpbs_commit's.
  *  ctxs   nctx contexts on distinct devices; nctx a power of two, <= 2^rate_bits and <= 2^cap_height.
  * The call starts every device before it waits for any.  stats: the slowest device's breakdown,
  * kernel_launches summed.  On error vpbs_last_error(ctxs[0]) explains. */

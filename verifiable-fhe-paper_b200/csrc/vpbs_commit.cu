@@ -63,6 +63,12 @@ struct vpbs_ctx {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
 
+  // vpbs_commit_multi: events of the chunk uploads this context performs for all contexts, and the
+  // event that marks the tail of this context's compute stream when such an upload starts
+  std::vector<cudaEvent_t> peer_ev;
+  cudaEvent_t peer_tail = nullptr;
+  std::set<int> peers_enabled;
+
   unsigned sms = 148;  // persistent NTT passes launch sms * ntt::R16P_MIN_BLOCKS CTAs
   std::vector<cudaEvent_t> ov;  // coeffs ready, one per LDE block, commit done
   // Buffers of destroyed resident batches, kept for the next batch of the same shape (a prover
@@ -791,6 +797,8 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (auto& kv : ctx->pool) cudaFree(kv.second);
   for (cudaEvent_t e : ctx->ov) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->peer_ev) cudaEventDestroy(e);
+  if (ctx->peer_tail) cudaEventDestroy(ctx->peer_tail);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -1076,6 +1084,9 @@ int vpbs_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint3
 
 namespace {
 
+// Width of the column chunks wide host batches travel in (0: one piece).
+u32 host_chunk_cols(u32 ncols, u32 log_n) { return (ncols >= 64 && log_n >= 12) ? 32u : 0u; }
+
 // State between commit_host_enqueue and commit_host_finish.
 struct HostRun {
   Timer tm{nullptr, false};
@@ -1092,7 +1103,8 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
                         uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
                         const uint64_t* const* salt_cols, u64 first_leaf, u64 nleaves_shard,
                         uint64_t* const* coeffs_out, u32 cc0, u32 cc1, uint64_t* leaves_out,
-                        uint64_t* digests_out, uint64_t* roots_out, bool want_stats, HostRun* run) {
+                        uint64_t* digests_out, uint64_t* roots_out, bool want_stats, HostRun* run,
+                        const std::vector<cudaEvent_t>* delivered = nullptr) {
   int rc;
   const unsigned log_m = log_n + rate_bits;
   const u64 n = 1ULL << log_n, m = n << rate_bits;
@@ -1116,8 +1128,7 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
   // chunk k-1 is already being transformed.
   // chunk width swept with tools/e2e_sweep.py (2^16 x 128, e2e ms): 8 -> 12.21, 16 -> 12.19,
   // 32 -> 12.08, 64 -> 12.35
-  constexpr u32 host_chunk = 32;
-  const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? host_chunk : 0;
+  const u32 chunk_cols = host_chunk_cols(ncols, log_n);
   const u32 nchunks = chunk_cols ? (ncols + chunk_cols - 1) / chunk_cols : 0;
   const u64 nblocks = nleaves_shard >> log_n;
   while (ctx->ov.size() < nblocks + 2 * (u64)nchunks + 4) {
@@ -1139,6 +1150,10 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
     evi += nchunks;
     ovl.coeffs_chunk_ready.assign(ctx->ov.begin() + evi, ctx->ov.begin() + evi + nchunks);
   }
+  // vpbs_commit_multi: the columns are being delivered into `din` by other streams (one upload per
+  // chunk by its owner GPU, then peer copies); `delivered` holds one event per chunk (or a single
+  // one) in place of this context's own uploads
+  if (delivered) ovl.h2d_ready = *delivered;
   run->chunked = nchunks != 0;
   cudaStream_t hs = nchunks ? ctx->h2d_stream : ctx->stream;
   if (want_stats) cudaEventRecord(e0, ctx->stream);
@@ -1152,7 +1167,7 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
       CU(ctx, cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice,
                               ctx->stream));
     }
-  for (u32 c0 = 0, k = 0; c0 < ncols; k++) {
+  for (u32 c0 = 0, k = 0; c0 < ncols && !delivered; k++) {
     const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
     CU(ctx, copy_columns(din, cols, c0, c1, n, true, hs));
     if (nchunks) CU(ctx, cudaEventRecord(ovl.h2d_ready[k], hs));
@@ -1273,6 +1288,60 @@ int vpbs_commit_multi(vpbs_ctx* const* ctxs, int nctx, const uint64_t* const* co
   const u64 shard = m / (u64)nctx, cap_per = ncap / (u64)nctx, dig_per = 2 * (shard - cap_per);
   std::vector<HostRun> runs((size_t)nctx);
   std::vector<vpbs_stats> st((size_t)nctx);
+  // Inputs: every column chunk crosses PCIe ONCE, into the GPU that owns it (chunk k -> GPU k mod
+  // nctx, all host links in parallel), and reaches the other GPUs by peer copies over NVLink.
+  std::vector<cudaEvent_t> delivered;
+  if (nctx > 1) {
+    for (u32 c = 0; c < ncols; c++)
+      if (!cols[c]) return fail(c0, VPBS_ERR_ARG, "cols[c] == NULL");
+    std::vector<u64*> din((size_t)nctx, nullptr);
+    for (int g = 0; g < nctx; g++) {  // buffers, peer access, and where each compute stream stands now
+      vpbs_ctx* ctx = ctxs[g];
+      if ((rc = bind(ctx))) return rc;
+      if ((rc = arena_get(ctx, "in", (size_t)ncols * n * 8, (void**)&din[g]))) return rc;
+      if (!ctx->peer_tail) CU(ctx, cudaEventCreateWithFlags(&ctx->peer_tail, cudaEventDisableTiming));
+      CU(ctx, cudaEventRecord(ctx->peer_tail, ctx->stream));
+      for (int o = 0; o < nctx; o++) {
+        if (o == g || ctx->peers_enabled.count(ctxs[o]->device)) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[o]->device) == cudaSuccess && can) {
+          cudaError_t pe = cudaDeviceEnablePeerAccess(ctxs[o]->device, 0);
+          if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(ctx, VPBS_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+        }
+        cudaGetLastError();
+        ctx->peers_enabled.insert(ctxs[o]->device);
+      }
+    }
+    const u32 chunk_cols = host_chunk_cols(ncols, log_n);
+    const u32 step = chunk_cols ? chunk_cols : ncols;
+    const u32 nchunks = (ncols + step - 1) / step;
+    delivered.resize(nchunks);
+    std::vector<bool> started((size_t)nctx, false);
+    for (u32 k = 0, col0 = 0; k < nchunks; k++, col0 += step) {
+      const u32 col1 = col0 + step < ncols ? col0 + step : ncols;
+      const int owner = (int)(k % (u32)nctx);
+      vpbs_ctx* oc = ctxs[owner];
+      if ((rc = bind(oc))) return rc;
+      while (oc->peer_ev.size() < nchunks) {
+        cudaEvent_t e;
+        CU(oc, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        oc->peer_ev.push_back(e);
+      }
+      if (!started[owner]) {  // nobody's `in` buffer is overwritten while its previous commit reads it
+        for (int g = 0; g < nctx; g++) CU(oc, cudaStreamWaitEvent(oc->h2d_stream, ctxs[g]->peer_tail, 0));
+        started[owner] = true;
+      }
+      CU(oc, copy_columns(din[owner], cols, col0, col1, n, true, oc->h2d_stream));
+      const size_t off = (size_t)col0 * n, bytes = (size_t)(col1 - col0) * n * sizeof(u64);
+      for (int g = 0; g < nctx; g++)
+        if (g != owner)
+          CU(oc, cudaMemcpyPeerAsync(din[g] + off, ctxs[g]->device, din[owner] + off, oc->device, bytes,
+                                     oc->h2d_stream));
+      CU(oc, cudaEventRecord(oc->peer_ev[k], oc->h2d_stream));
+      delivered[k] = oc->peer_ev[k];
+    }
+  }
   int enq = 0;
   for (; enq < nctx; enq++) {  // start every device ...
     vpbs_ctx* ctx = ctxs[enq];
@@ -1282,7 +1351,8 @@ int vpbs_commit_multi(vpbs_ctx* const* ctxs, int nctx, const uint64_t* const* co
                              salt_cols, shard * enq, shard, coeffs_out, cc0, cc1,
                              leaves_out ? leaves_out + shard * enq * width : nullptr,
                              digests_out ? digests_out + dig_per * enq * 4 : nullptr,
-                             cap_out + cap_per * enq * 4, stats != nullptr, &runs[enq]);
+                             cap_out + cap_per * enq * 4, stats != nullptr, &runs[enq],
+                             nctx > 1 ? &delivered : nullptr);
     if (rc) break;
   }
   int first_err = rc;
@@ -1290,6 +1360,8 @@ int vpbs_commit_multi(vpbs_ctx* const* ctxs, int nctx, const uint64_t* const* co
   for (int g = 0; g < enq; g++) {  // ... then wait for all of them
     vpbs_ctx* ctx = ctxs[g];
     int r2 = bind(ctx);
+    if (!r2 && nctx > 1 && cudaStreamSynchronize(ctx->h2d_stream) != cudaSuccess)
+      r2 = fail(ctx, VPBS_ERR_CUDA, "input delivery failed");
     if (!r2) r2 = commit_host_finish(ctx, &runs[g], stats ? &st[g] : nullptr);
     if (r2 && !first_err) {
       first_err = r2;
