@@ -652,27 +652,33 @@ __device__ __forceinline__ Ext2 ext_mul(Ext2 a, Ext2 b) {
   const u64 t = gl::mul(a.im, b.im);
   return Ext2{gl::add(gl::mul(a.re, b.re), gl::mul(7, t)), gl::add(gl::mul(a.re, b.im), gl::mul(a.im, b.re))};
 }
-// One CTA per (polynomial, point).  Thread t sums the coefficients j = t (mod 256) by Horner in
-// y = x^256 (coalesced reads), scales by x^t and the CTA adds the 256 partial values.
-__global__ void __launch_bounds__(256)
+// One CTA of EVAL_THREADS threads per (polynomial, point).  Thread t sums the coefficients
+// j = t (mod T) by Horner in y = x^T (coalesced reads), scales by x^t and the CTA adds the partial
+// values.  T = 1024 for long polynomials: the Horner chain of a thread is a serial run of extension
+// multiplies (2^16 coefficients: 64 steps instead of 256 with T = 256, and four times the warps to
+// hide them behind; 170 -> see DESIGN.md §9.2 for the measured effect), T = 256 below 2^14.
+template <int T>
+__global__ void __launch_bounds__(T)
 eval_ext2(const u64* __restrict__ coeffs, u64 col_stride, unsigned log_n,
           const u64* __restrict__ points, u64* __restrict__ out, unsigned ncols) {
-  __shared__ u64 sre[256], sim[256];
+  constexpr int LOG_T = T == 1024 ? 10 : 8;
+  static_assert(T == 1024 || T == 256, "eval_ext2: 256 or 1024 threads");
+  __shared__ u64 sre[T], sim[T];
   const unsigned col = blockIdx.x, pt = blockIdx.y, t = threadIdx.x;
   const u64 n = 1ULL << log_n;
   const Ext2 x{gl::canon(points[2 * pt]), gl::canon(points[2 * pt + 1])};
-  Ext2 y = x;  // x^256
+  Ext2 y = x;  // x^T
 #pragma unroll
-  for (int i = 0; i < 8; i++) y = ext_mul(y, y);
+  for (int i = 0; i < LOG_T; i++) y = ext_mul(y, y);
   const u64* c = coeffs + (u64)col * col_stride;
   Ext2 acc{0, 0};
   if (t < n) {
-    const u64 k_hi = (n - 1 - t) >> 8;  // largest k with 256 k + t < n
+    const u64 k_hi = (n - 1 - t) >> LOG_T;  // largest k with T k + t < n
     for (u64 k = k_hi + 1; k-- > 0;) {
       acc = ext_mul(acc, y);
-      acc.re = gl::add(acc.re, gl::canon(__ldg(c + (k << 8) + t)));
+      acc.re = gl::add(acc.re, gl::canon(__ldg(c + (k << LOG_T) + t)));
     }
-    Ext2 p{1, 0}, b = x;  // x^t by binary exponentiation (t < 256)
+    Ext2 p{1, 0}, b = x;  // x^t by binary exponentiation (t < T)
     for (unsigned e = t; e; e >>= 1) {
       if (e & 1) p = ext_mul(p, b);
       b = ext_mul(b, b);
@@ -682,7 +688,7 @@ eval_ext2(const u64* __restrict__ coeffs, u64 col_stride, unsigned log_n,
   sre[t] = acc.re;
   sim[t] = acc.im;
   __syncthreads();
-  for (unsigned s = 128; s > 0; s >>= 1) {
+  for (unsigned s = T / 2; s > 0; s >>= 1) {
     if (t < s) {
       sre[t] = gl::add(sre[t], sre[t + s]);
       sim[t] = gl::add(sim[t], sim[t + s]);

@@ -1394,7 +1394,11 @@ static int eval_ext2_device(vpbs_ctx* ctx, const u64* d_coeffs, u32 ncols, u32 l
   if ((rc = arena_get(ctx, "idx", (size_t)npoints * 16, (void**)&d_pts))) return rc;
   if ((rc = arena_get(ctx, "rows", (size_t)npoints * ncols * 16, (void**)&d_out))) return rc;
   CU(ctx, cudaMemcpyAsync(d_pts, points, (size_t)npoints * 16, cudaMemcpyHostToDevice, ctx->stream));
-  ntt::eval_ext2<<<dim3(ncols, npoints), 256, 0, ctx->stream>>>(d_coeffs, 1ULL << log_n, log_n, d_pts,
+  if (log_n >= 14)
+    ntt::eval_ext2<1024><<<dim3(ncols, npoints), 1024, 0, ctx->stream>>>(d_coeffs, 1ULL << log_n, log_n, d_pts,
+                                                               d_out, ncols);
+  else
+    ntt::eval_ext2<256><<<dim3(ncols, npoints), 256, 0, ctx->stream>>>(d_coeffs, 1ULL << log_n, log_n, d_pts,
                                                                d_out, ncols);
   ctx->launches++;
   CU(ctx, cudaGetLastError());
@@ -1827,7 +1831,12 @@ int vpbs_pow_grind(vpbs_ctx* ctx, const uint64_t state[12], uint32_t witness_pos
   const unsigned long long none = ~0ULL;
   CU(ctx, cudaMemcpyAsync(d, state, 12 * 8, cudaMemcpyHostToDevice, ctx->stream));
   CU(ctx, cudaMemcpyAsync(d + 12, &none, 8, cudaMemcpyHostToDevice, ctx->stream));
-  const u64 chunk = 1ULL << 22;  // candidates per launch; stop at the first chunk with a hit
+  // candidates per launch; stop at the first chunk with a hit.  A witness is expected after
+  // 2^min_leading_zeros candidates: four times that per launch finds it in the first one with
+  // probability 1 - e^-4 without hashing millions of candidates beyond it (a 2^22 chunk cost the
+  // 16-bit grind of the N=1024 step 0.52 ms; 2^18: see DESIGN.md §9.2)
+  u64 chunk = min_leading_zeros < 20 ? (4ULL << min_leading_zeros) : (1ULL << 22);
+  if (chunk < (1ULL << 17)) chunk = 1ULL << 17;
   for (u64 off = 0; off < count; off += chunk) {
     const u64 cnt = count - off < chunk ? count - off : chunk;
     merkle::pow_grind<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(
