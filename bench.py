@@ -1014,10 +1014,11 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
       resident (the product path): everything of prove() this repository puts on the device —
         wires commit (135 value columns from the host) -> Z / partial products computed and committed
         on the device (20) -> quotient-chunk commit (16 coefficient columns from the host) ->
-        openings of all 171 polynomials at zeta / g zeta -> prove_openings (alpha-combination,
-        division by X - z, final-polynomial LDE) -> FRI commit phase (3 arity-16 layers: tree, cap to
+        openings of all 256 polynomials of the four FRI oracles (the circuit's constants/sigmas batch,
+        85 columns, is committed once and stays resident) at zeta / g zeta -> prove_openings
+        (alpha-combination of the 256 + 2 polynomials, division by X - z, final-polynomial LDE) -> FRI commit phase (3 arity-16 layers: tree, cap to
         the host, beta back, fold) -> final polynomial -> 16-bit proof-of-work grind -> 28 query rounds
-        served from the three resident batches and the FRI layers;
+        served from the four resident batches and the FRI layers;
       eager (round 1's form): the three commits with every output downloaded.
     The challenges are derived from the caps by plain mixing (a stand-in for the Poseidon
     challenger, which stays on the CPU); witness generation and the gate constraints of the quotient
@@ -1051,10 +1052,19 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         seed = int(np.bitwise_xor.reduce(x * np.uint64(2 * k + 1))) ^ (k * 0x9E3779B97F4A7C15)
         return np.random.default_rng(seed % (1 << 63)).integers(1, P_GL, size=count, dtype=np.uint64)
 
-    opens = [np.empty((2, c, 2), np.uint64) for c, _ in shapes]
-    rows = [np.empty((28, c), np.uint64) for c, _ in shapes]
-    sibs = [np.empty((28, nlayers, 4), np.uint64) for _ in shapes]
-    fri_batches = [[(o, j) for o, (c, _) in enumerate(shapes) for j in range(c)], [(1, 0), (1, 1)]]
+    # the circuit's constants/sigmas batch (85 columns, committed once in build(), ivc_based_vpbs.rs:275)
+    # is the fourth FRI oracle: resident for the whole chain, opened and queried in every step
+    CS = 85
+    cs_cols = pinned((CS, n)); cs_cols[:] = V.synthetic_columns(CS, n, 0x5EED0000 + 85)
+    cs_cap = np.empty((ncap, 4), np.uint64)
+    h_cs = ctypes.c_void_p()
+    ctx.check(lib.vpbs_batch_commit(ctx.handle, ptrs(cs_cols), CS, log_n, RATE_BITS, CAP_HEIGHT, 0, None,
+                                    cs_cap.ctypes.data_as(u64p), ctypes.byref(h_cs), None))
+    widths = [CS] + [c for c, _ in shapes]  # FRI_ORACLES order: constants_sigmas, wires, zs, quotient
+    opens = [np.empty((2, c, 2), np.uint64) for c in widths]
+    rows = [np.empty((28, c), np.uint64) for c in widths]
+    sibs = [np.empty((28, nlayers, 4), np.uint64) for _ in widths]
+    fri_batches = [[(o, j) for o, c in enumerate(widths) for j in range(c)], [(2, 0), (2, 1)]]
     stats = {"fri_layers": 0}
 
     def resident_step():
@@ -1071,10 +1081,11 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         zeta = challenge(caps[2], 2, 2)
         gz = np.array([int(zeta[0]) * g_n % P_GL, int(zeta[1]) * g_n % P_GL], np.uint64)
         pts = np.stack([zeta, gz])
-        for k in range(3):  # OpeningSet::new
-            ctx.check(lib.vpbs_batch_eval_ext2(hs[k], pts.ctypes.data_as(u64p), 2, opens[k].ctypes.data_as(u64p)))
-        alpha = challenge(opens[2][0, :4].copy(), 3, 2)
-        obs = [_Resident(ctx, h, log_n) for h in hs]
+        allh = [h_cs] + hs
+        for k in range(4):  # OpeningSet::new
+            ctx.check(lib.vpbs_batch_eval_ext2(allh[k], pts.ctypes.data_as(u64p), 2, opens[k].ctypes.data_as(u64p)))
+        alpha = challenge(opens[3][0, :4].copy(), 3, 2)
+        obs = [_Resident(ctx, h, log_n) for h in allh]
         fri = V.FriCommitPhase.from_openings(obs, fri_batches, pts, alpha, RATE_BITS)
         lg, k, cap = log_n + RATE_BITS, 0, caps[2]
         while lg - RATE_BITS > 5 and lg - 4 >= CAP_HEIGHT:  # ConstantArityBits(4, 5)
@@ -1087,9 +1098,9 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         pow_state = challenge(final[: min(4, final.shape[0])].copy(), 9, 12)
         w = V.fri_proof_of_work(pow_state, 5, 16, ctx=ctx)
         qidx = np.random.default_rng(int(w or 0) + 1).integers(0, m, size=28, dtype=np.uint64)
-        for b in range(3):
-            ctx.check(lib.vpbs_batch_get_leaves(hs[b], qidx.ctypes.data_as(u64p), 28, rows[b].ctypes.data_as(u64p)))
-            ctx.check(lib.vpbs_batch_prove(hs[b], qidx.ctypes.data_as(u64p), 28, sibs[b].ctypes.data_as(u64p)))
+        for b in range(4):
+            ctx.check(lib.vpbs_batch_get_leaves(allh[b], qidx.ctypes.data_as(u64p), 28, rows[b].ctypes.data_as(u64p)))
+            ctx.check(lib.vpbs_batch_prove(allh[b], qidx.ctypes.data_as(u64p), 28, sibs[b].ctypes.data_as(u64p)))
         qi = qidx.copy()
         for layer in range(k):
             qi = qi >> np.uint64(4)
@@ -1149,10 +1160,11 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     launches = (ctx.kernel_launches - l0) // args.chain_steps
     barrier()
     sig.close()
+    lib.vpbs_batch_destroy(h_cs)
     if rank == 0:
         h2d = 8 * n * (135 + 16) + 16 * 8
-        d2h = (3 * 32 * ncap + 171 * 2 * 16 + stats["fri_layers"] * 32 * ncap +
-               28 * sum(8 * c + 32 * nlayers for c, _ in shapes))
+        d2h = (3 * 32 * ncap + sum(widths) * 2 * 16 + stats["fri_layers"] * 32 * ncap +
+               28 * sum(8 * c + 32 * nlayers for c in widths))
         emit(({
             "metric": "N=%d-class vPBS IVC step stand-in (2^%d rows): wires / Z / quotient commits, openings, "
                       "prove_openings and the FRI commit phase device-resident through the host C ABI, "
