@@ -298,10 +298,78 @@ class ResidentBatch {
     ctx_.check(vpbs_batch_eval_ext2(h_, point, 1, out.data()));
     return out;
   }
+  // get_lde_values(first + k * step) for k < count, salt dropped: count x ncols, row-major
+  std::vector<F> get_lde_rows(std::size_t first, std::size_t step, std::size_t count) const {
+    std::vector<F> out(count * ncols);
+    ctx_.check(vpbs_batch_get_lde_rows(h_, first, step, count, out.data()));
+    return out;
+  }
+  vpbs_batch* handle() const { return h_; }
+  const Context& context() const { return ctx_; }
+
+ private:
+  friend class Sigmas;
+  ResidentBatch(const Context& ctx, vpbs_batch* h, std::vector<HashOut> cap_, unsigned degree_log_,
+                unsigned rate_bits_, std::size_t ncols_)
+      : cap(std::move(cap_)), degree_log(degree_log_), rate_bits(rate_bits_), ncols(ncols_), width(ncols_),
+        ctx_(ctx), h_(h) {}
+  const Context& ctx_;
+  vpbs_batch* h_ = nullptr;
+};
+
+// ---- plonk/prover.rs, step 4-5: Z and partial products of the permutation argument ----------------
+// The sigma polynomials' values and the coset shifts k_is of one circuit, resident in HBM.
+class Sigmas {
+ public:
+  Sigmas(const Context& ctx, const std::vector<std::vector<F>>& sigma_cols, const std::vector<F>& k_is)
+      : ctx_(ctx), num_routed_(sigma_cols.size()) {
+    if (sigma_cols.empty() || k_is.size() != sigma_cols.size())
+      throw std::invalid_argument("one k_i per routed wire");
+    std::vector<const F*> in(sigma_cols.size());
+    for (std::size_t j = 0; j < in.size(); j++) in[j] = sigma_cols[j].data();
+    degree_log_ = log2_strict(sigma_cols[0].size());
+    ctx.check(vpbs_sigmas_upload(ctx.get(), in.data(), k_is.data(), (uint32_t)in.size(), degree_log_, &h_));
+  }
+  ~Sigmas() { vpbs_sigmas_destroy(h_); }
+  Sigmas(const Sigmas&) = delete;
+  Sigmas& operator=(const Sigmas&) = delete;
+
+  // all_wires_permutation_partial_products on host wire columns: num_challenges * K columns in commit
+  // order (the Zs first), K = ceil(num_routed / max_degree)
+  std::vector<std::vector<F>> partial_products(const std::vector<std::vector<F>>& wire_cols,
+                                               const std::vector<F>& betas, const std::vector<F>& gammas,
+                                               unsigned max_degree) const {
+    if (wire_cols.size() != num_routed_ || betas.size() != gammas.size() || betas.empty())
+      throw std::invalid_argument("wire_cols must be num_routed columns; one gamma per beta");
+    const std::size_t n = std::size_t(1) << degree_log_, K = (num_routed_ + max_degree - 1) / max_degree;
+    std::vector<std::vector<F>> out(betas.size() * K, std::vector<F>(n));
+    std::vector<const F*> in(num_routed_);
+    std::vector<F*> op(out.size());
+    for (std::size_t j = 0; j < num_routed_; j++) in[j] = wire_cols[j].data();
+    for (std::size_t c = 0; c < out.size(); c++) op[c] = out[c].data();
+    ctx_.check(vpbs_zs_partial_products(ctx_.get(), in.data(), h_, max_degree, betas.data(), gammas.data(),
+                                        (uint32_t)betas.size(), op.data()));
+    return out;
+  }
+  // the same from a resident wires batch, committed at once as a new resident batch (steps 4-5)
+  ResidentBatch commit_partial_products(const ResidentBatch& wires, const std::vector<F>& betas,
+                                        const std::vector<F>& gammas, unsigned max_degree, unsigned rate_bits,
+                                        unsigned cap_height) const {
+    if (betas.size() != gammas.size() || betas.empty()) throw std::invalid_argument("one gamma per beta");
+    const std::size_t K = (num_routed_ + max_degree - 1) / max_degree;
+    std::vector<HashOut> cap(std::size_t(1) << cap_height);
+    vpbs_batch* h = nullptr;
+    ctx_.check(vpbs_batch_zs_partial_products(wires.handle(), h_, max_degree, betas.data(), gammas.data(),
+                                              (uint32_t)betas.size(), rate_bits, cap_height, cap[0].elements,
+                                              &h, nullptr));
+    return ResidentBatch(ctx_, h, std::move(cap), degree_log_, rate_bits, betas.size() * K);
+  }
 
  private:
   const Context& ctx_;
-  vpbs_batch* h_ = nullptr;
+  vpbs_sigmas* h_ = nullptr;
+  std::size_t num_routed_ = 0;
+  unsigned degree_log_ = 0;
 };
 
 // ---- fri/prover.rs ------------------------------------------------------------------------------
@@ -345,5 +413,68 @@ inline long long fri_proof_of_work(const Context& ctx, const F (&state)[12], uns
   ctx.check(vpbs_pow_grind(ctx.get(), state, witness_pos, 7, min_leading_zeros, first, count, &w, &found));
   return found ? (long long)w : -1;
 }
+
+// fri_committed_trees as one device-resident chain (vpbs_fri_*): started either from the final
+// polynomial's coefficients or, as fri/oracle.rs prove_openings does, from the committed batches.
+struct FriPolynomialInfo {
+  uint32_t oracle_index, polynomial_index;
+};
+class FriChain {
+ public:
+  FriChain(const Context& ctx, const std::vector<F>& final_poly_coeffs_ext, unsigned rate_bits)
+      : ctx_(ctx), rate_bits_(rate_bits) {
+    log2_strict(final_poly_coeffs_ext.size() / 2);
+    ctx.check(vpbs_fri_begin(ctx.get(), final_poly_coeffs_ext.data(), final_poly_coeffs_ext.size() / 2,
+                             rate_bits, &h_));
+    len_ = (final_poly_coeffs_ext.size() / 2) << rate_bits;
+  }
+  // batches[b]: the polynomials opened at points[2b], points[2b+1]  ([P2] FriInstanceInfo)
+  FriChain(const std::vector<const ResidentBatch*>& oracles,
+           const std::vector<std::vector<FriPolynomialInfo>>& batches, const std::vector<F>& points,
+           const F (&alpha)[2], unsigned rate_bits)
+      : ctx_(oracles.at(0)->context()), rate_bits_(rate_bits) {
+    if (points.size() != 2 * batches.size() || batches.empty())
+      throw std::invalid_argument("one opening point per FRI batch");
+    std::vector<vpbs_batch*> hs;
+    for (const ResidentBatch* o : oracles) hs.push_back(o->handle());
+    std::vector<uint32_t> sizes, refs;
+    for (const auto& b : batches) {
+      sizes.push_back((uint32_t)b.size());
+      for (const auto& r : b) {
+        refs.push_back(r.oracle_index);
+        refs.push_back(r.polynomial_index);
+      }
+    }
+    ctx_.check(vpbs_fri_begin_openings(ctx_.get(), hs.data(), (uint32_t)hs.size(), sizes.data(),
+                                       (uint32_t)sizes.size(), refs.data(), points.data(), alpha, rate_bits,
+                                       &h_));
+    len_ = (std::size_t(1) << oracles[0]->degree_log) << rate_bits;
+  }
+  ~FriChain() { vpbs_fri_destroy(h_); }
+  FriChain(const FriChain&) = delete;
+  FriChain& operator=(const FriChain&) = delete;
+
+  std::vector<HashOut> commit_layer(unsigned arity_bits, unsigned cap_height) {
+    std::vector<HashOut> cap(std::size_t(1) << cap_height);
+    ctx_.check(vpbs_fri_commit_layer(h_, arity_bits, cap_height, cap[0].elements));
+    pending_ = arity_bits;
+    return cap;
+  }
+  void fold(const F (&beta)[2]) {
+    ctx_.check(vpbs_fri_fold_layer(h_, beta));
+    len_ >>= pending_;
+  }
+  std::vector<F> final_poly() const {  // (len >> rate_bits) extension coefficients
+    std::vector<F> out(2 * (len_ >> rate_bits_));
+    ctx_.check(vpbs_fri_final_poly(h_, rate_bits_, out.data()));
+    return out;
+  }
+
+ private:
+  const Context& ctx_;
+  vpbs_fri* h_ = nullptr;
+  unsigned rate_bits_ = 0, pending_ = 0;
+  std::size_t len_ = 0;
+};
 
 }  // namespace vpbs

@@ -299,6 +299,98 @@ impl ResidentBatch {
     }
 }
 
+impl ResidentBatch {
+    /// OpeningSet::new for this batch: every polynomial at each extension point (npoints x ncols x 2).
+    pub fn eval_ext2(&self, ctx: &Ctx, points: &[[u64; 2]]) -> Vec<u64> {
+        let mut out = vec![0u64; points.len() * self.ncols * 2];
+        ctx.check(unsafe { vpbs_batch_eval_ext2(self.h, points.as_ptr() as *const u64, points.len() as u32,
+                                                out.as_mut_ptr()) });
+        out
+    }
+}
+
+/// Sigma polynomials' values + coset shifts of one circuit in HBM (uploaded once per circuit).
+pub struct Sigmas(*mut vpbs_sigmas);
+unsafe impl Send for Sigmas {}
+impl Drop for Sigmas {
+    fn drop(&mut self) {
+        unsafe { vpbs_sigmas_destroy(self.0) }
+    }
+}
+impl Sigmas {
+    pub fn upload(ctx: &Ctx, sigma_cols: &[&[u64]], k_is: &[u64]) -> Self {
+        assert_eq!(sigma_cols.len(), k_is.len());
+        let n = sigma_cols[0].len();
+        assert!(n.is_power_of_two());
+        let ptrs: Vec<*const u64> = sigma_cols.iter().map(|c| c.as_ptr()).collect();
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe { vpbs_sigmas_upload(ctx.0, ptrs.as_ptr(), k_is.as_ptr(), k_is.len() as u32,
+                                              n.trailing_zeros(), &mut h) });
+        Sigmas(h)
+    }
+    pub fn as_ptr(&self) -> *const vpbs_sigmas {
+        self.0
+    }
+}
+
+/// fri/prover.rs fri_committed_trees as one device-resident chain, started the way
+/// fri/oracle.rs prove_openings starts it: from the committed batches (FRI_ORACLES order), the
+/// FriInstanceInfo (per batch: opening point + (oracle_index, polynomial_index) pairs) and alpha.
+pub struct Fri {
+    h: *mut vpbs_fri,
+    len: usize,
+    rate_bits: usize,
+    pending_arity_bits: usize,
+}
+unsafe impl Send for Fri {}
+impl Drop for Fri {
+    fn drop(&mut self) {
+        unsafe { vpbs_fri_destroy(self.h) }
+    }
+}
+impl Fri {
+    pub fn begin_openings(ctx: &Ctx, oracles: &[&ResidentBatch], batches: &[(&[(u32, u32)], [u64; 2])],
+                          alpha: [u64; 2], rate_bits: usize) -> Self {
+        let hs: Vec<*mut vpbs_batch> = oracles.iter().map(|o| o.h).collect();
+        let sizes: Vec<u32> = batches.iter().map(|(polys, _)| polys.len() as u32).collect();
+        let refs: Vec<u32> = batches.iter().flat_map(|(polys, _)| polys.iter().flat_map(|&(o, p)| [o, p])).collect();
+        let points: Vec<u64> = batches.iter().flat_map(|(_, z)| *z).collect();
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe {
+            vpbs_fri_begin_openings(ctx.0, hs.as_ptr(), hs.len() as u32, sizes.as_ptr(), sizes.len() as u32,
+                                    refs.as_ptr(), points.as_ptr(), alpha.as_ptr(), rate_bits as u32, &mut h)
+        });
+        Fri { h, len: (1usize << oracles[0].degree_log) << rate_bits, rate_bits, pending_arity_bits: 0 }
+    }
+    /// One reduction layer's tree; the cap goes to the challenger.
+    pub fn commit_layer(&mut self, ctx: &Ctx, arity_bits: usize, cap_height: usize) -> Vec<u64> {
+        let mut cap = vec![0u64; 4 << cap_height];
+        ctx.check(unsafe { vpbs_fri_commit_layer(self.h, arity_bits as u32, cap_height as u32, cap.as_mut_ptr()) });
+        self.pending_arity_bits = arity_bits;
+        cap
+    }
+    /// reduce_with_powers with the challenger's beta, then the next coset evaluations.
+    pub fn fold(&mut self, ctx: &Ctx, beta: [u64; 2]) {
+        ctx.check(unsafe { vpbs_fri_fold_layer(self.h, beta.as_ptr()) });
+        self.len >>= self.pending_arity_bits;
+    }
+    pub fn final_poly(&self, ctx: &Ctx) -> Vec<u64> {
+        let mut out = vec![0u64; 2 * (self.len >> self.rate_bits)];
+        ctx.check(unsafe { vpbs_fri_final_poly(self.h, self.rate_bits as u32, out.as_mut_ptr()) });
+        out
+    }
+    /// fri_prover_query_round on one layer's tree: (rows, siblings).
+    pub fn query(&self, ctx: &Ctx, layer: usize, leaf_indices: &[u64], leaf_len: usize, layers: usize)
+                 -> (Vec<u64>, Vec<u64>) {
+        let mut rows = vec![0u64; leaf_indices.len() * leaf_len];
+        let mut sibs = vec![0u64; leaf_indices.len() * layers * 4];
+        ctx.check(unsafe { vpbs_fri_query_layer(self.h, layer as u32, leaf_indices.as_ptr(),
+                                                leaf_indices.len() as u64, rows.as_mut_ptr(),
+                                                if sibs.is_empty() { std::ptr::null_mut() } else { sibs.as_mut_ptr() }) });
+        (rows, sibs)
+    }
+}
+
 /// `cols[c]` is one polynomial's values (or coefficients): GoldilocksField is
 /// `#[repr(transparent)]` over u64, so `&[GoldilocksField]` reinterprets as `&[u64]`.
 pub fn commit(ctx: &Ctx, cols: &[&[u64]], rate_bits: usize, cap_height: usize,

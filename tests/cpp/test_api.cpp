@@ -119,6 +119,70 @@ int main() {
     orc_poseidon(chk);
     CHECK((chk[7] >> 54) == 0);
   }
+  // steps 4-5 and 9 of prove() through the mirror: Z / partial products (host and resident forms), then
+  // prove_openings + one FRI layer from the resident batches
+  {
+    const unsigned log_n = 8, num_routed = 12, ncols = 15, max_degree = 5, rate_bits = 3, cap_height = 2;
+    const std::size_t n = std::size_t(1) << log_n, K = (num_routed + max_degree - 1) / max_degree;
+    std::vector<std::vector<F>> wires(ncols, std::vector<F>(n)), sig(num_routed, std::vector<F>(n));
+    for (auto& col : wires)
+      for (auto& x : col) x = rng();
+    for (auto& col : sig)
+      for (auto& x : col) x = rng();
+    std::vector<F> k_is(num_routed), betas = {rng() % ORC_P, rng() % ORC_P}, gammas = {rng() % ORC_P, rng() % ORC_P};
+    for (unsigned j = 0; j < num_routed; j++) k_is[j] = j ? orc_gl_mul(k_is[j - 1], 7) : 1;
+    vpbs::Sigmas sigmas(ctx, sig, k_is);
+    std::vector<std::vector<F>> routed(wires.begin(), wires.begin() + num_routed);
+    auto zs = sigmas.partial_products(routed, betas, gammas, max_degree);
+    CHECK(zs.size() == 2 * K);
+    std::vector<const uint64_t*> wp(num_routed), sp(num_routed);
+    for (unsigned j = 0; j < num_routed; j++) {
+      wp[j] = wires[j].data();
+      sp[j] = sig[j].data();
+    }
+    for (unsigned c = 0; c < 2; c++) {
+      std::vector<uint64_t> want(K * n);
+      CHECK(orc_zs_partial_products(wp.data(), sp.data(), k_is.data(), num_routed, log_n, max_degree, betas[c],
+                                    gammas[c], want.data()) == 0);
+      CHECK(std::memcmp(zs[c].data(), want.data(), n * 8) == 0);
+      for (std::size_t k = 0; k + 1 < K; k++)
+        CHECK(std::memcmp(zs[2 + c * (K - 1) + k].data(), want.data() + (1 + k) * n, n * 8) == 0);
+    }
+    vpbs::ResidentBatch wb(ctx, wires, rate_bits, cap_height, false);
+    auto zb = sigmas.commit_partial_products(wb, betas, gammas, max_degree, rate_bits, cap_height);
+    auto zref = vpbs::PolynomialBatch::from_values(ctx, zs, rate_bits, false, cap_height);
+    CHECK(std::memcmp(zb.cap.data(), zref.merkle_tree.cap.data(), zb.cap.size() * 32) == 0);
+    auto rows = zb.get_lde_rows(3, 2, 4);
+    for (std::size_t k = 0; k < 4; k++)
+      CHECK(std::memcmp(rows.data() + k * zb.ncols, zref.get_lde_values(3 + 2 * k).data(), zb.ncols * 8) == 0);
+
+    // prove_openings: every polynomial of both batches at zeta, the two Zs at g zeta
+    std::vector<std::vector<vpbs::FriPolynomialInfo>> fb(2);
+    for (uint32_t j = 0; j < ncols; j++) fb[0].push_back({0, j});
+    for (uint32_t j = 0; j < zb.ncols; j++) fb[0].push_back({1, j});
+    fb[1] = {{1, 0}, {1, 1}};
+    const std::vector<F> pts = {rng() % ORC_P, rng() % ORC_P, rng() % ORC_P, rng() % ORC_P};
+    const F alpha[2] = {rng() % ORC_P, rng() % ORC_P};
+    vpbs::FriChain fri({&wb, &zb}, fb, pts, alpha, rate_bits);
+    auto fp = fri.final_poly();
+    auto wco = vpbs::PolynomialBatch::from_values(ctx, wires, rate_bits, false, cap_height);  // coefficients
+    std::vector<const uint64_t*> polys;
+    for (unsigned j = 0; j < ncols; j++) polys.push_back(wco.polynomials[j].data());
+    for (std::size_t j = 0; j < zb.ncols; j++) polys.push_back(zref.polynomials[j].data());
+    polys.push_back(zref.polynomials[0].data());
+    polys.push_back(zref.polynomials[1].data());
+    const uint32_t sizes[2] = {(uint32_t)(ncols + zb.ncols), 2};
+    std::vector<uint64_t> want(2 * n);
+    CHECK(orc_fri_final_poly(polys.data(), sizes, 2, n, pts.data(), alpha, want.data()) == 0);
+    CHECK(fp == want);
+    vpbs::FriChain ref(ctx, want, rate_bits);
+    auto c1 = fri.commit_layer(4, 2), c2 = ref.commit_layer(4, 2);
+    CHECK(std::memcmp(c1.data(), c2.data(), c1.size() * 32) == 0);
+    const F beta[2] = {rng() % ORC_P, rng() % ORC_P};
+    fri.fold(beta);
+    ref.fold(beta);
+    CHECK(fri.final_poly() == ref.final_poly());
+  }
   // failure behaviour: what plonky2 asserts on
   bool threw = false;
   try {
