@@ -922,3 +922,28 @@ def test_resident_commit_of_wide_host_batches(V, ctx, oracle, log_n, ncols, rate
     if not coeffs:
         assert np.array_equal(eager.polynomials, ref["coeffs"])
     rb.close()
+
+
+def test_prove_openings_random_instances(V, ctx, oracle):
+    """Random FRI instances (1-3 batches, polynomials drawn with repetition from 1-3 oracles of
+    different widths, sizes 2^0..2^11, non-canonical points / alpha) against the oracle."""
+    rnd = random.Random(77)
+    rng = np.random.default_rng(77)
+    for _ in range(24):
+        log_n = rnd.randint(0, 11)
+        n = 1 << log_n
+        widths = [rnd.choice([1, 2, 5, 9, 20]) for _ in range(rnd.randint(1, 3))]
+        cols = [rand_u64(rng, (w, n)) for w in widths]
+        obs = [V.commit_resident(c, 1, False, 0, True, ctx=ctx) for c in cols]
+        batches = []
+        for _b in range(rnd.randint(1, 3)):
+            k = rnd.randint(1, 12)
+            batches.append([(o, rnd.randrange(widths[o])) for o in (rnd.randrange(len(widths)) for _ in range(k))])
+        pts = rand_u64(rng, (len(batches), 2))
+        alpha = rand_u64(rng, 2)
+        fri = V.FriCommitPhase.from_openings(obs, batches, pts, alpha, 1)
+        want = oracle.fri_final_poly([np.stack([cols[o][j] for (o, j) in b]) for b in batches], pts, alpha)
+        assert np.array_equal(fri.final_poly(), want), (log_n, widths, batches)
+        fri.close()
+        for o in obs:
+            o.close()
