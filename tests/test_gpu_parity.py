@@ -947,3 +947,16 @@ def test_prove_openings_random_instances(V, ctx, oracle):
         fri.close()
         for o in obs:
             o.close()
+
+
+def test_fft_of_2p24_points_three_256_point_passes(V, ctx, oracle):
+    """log_n = 24 = 8 + 8 + 8: the only size whose strided radix-16 passes work on more than one
+    block per column (TMA box coordinate `block` > 0) and apply the four-step twiddle at their
+    store; forward, inverse (round trip) and coset transforms against the oracle."""
+    rng = np.random.default_rng(24)
+    v = rand_u64(rng, 1 << 24, 0.01)
+    want = oracle.fft(v.copy())
+    got = V.fft(v.copy(), ctx)
+    assert np.array_equal(got, want)
+    assert np.array_equal(V.ifft(got.copy(), ctx), v % np.uint64(P))
+    assert np.array_equal(V.coset_fft(v.copy(), 7, ctx), oracle.coset_fft(v.copy(), 7))
