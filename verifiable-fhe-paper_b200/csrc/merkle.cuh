@@ -65,7 +65,7 @@ __device__ __forceinline__ u64 leaf_digest_pos(u64 l) { return 4 * (l >> 1) + (l
 // Occupancy does not matter any more (the kernel is bound by the ALU pipe in the full rounds and
 // the FP64 pipe in the pair steps): 3 / 4 / 5 / 6 CTAs per SM measure 5.55 / 5.54 / 5.52 / 5.59 ms,
 // 64- and 256-thread CTAs the same.
-#define VPBS_HASH_MIN_BLOCKS 4
+#define VPBS_HASH_MIN_BLOCKS 5  // round 2: with the 3-product squaring ptxas takes 102 registers unless held to 96
 #endif
 // One thread per leaf.  all_cap: the tree has no digests, leaf hashes are the cap.
 __global__ void __launch_bounds__(VPBS_HASH_THREADS, VPBS_HASH_MIN_BLOCKS)
