@@ -622,7 +622,46 @@ def main():
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": eager_d2h,
                     "api": "vpbs_commit, pageable host buffers (numpy.empty): the driver stages every "
                            "copy through its own pinned bounce buffers and nothing overlaps"}
-        del g_cols, g_coeffs, g_leaves, g_digests
+        del g_coeffs, g_leaves, g_digests
+
+        # (3b) e2e_pageable_inputs — the product path (resident batch) as a patched plonky2 calls it:
+        # the value columns are the prover's own Vec<PolynomialValues<F>> — pageable, one allocation per
+        # column — and reach the GPU through the context's pinned staging ring (host_stage.h); the same
+        # with the ring switched off (the CUDA driver stages every copy on the calling thread)
+        vec_cols = [g_cols[c].copy() for c in range(NCOLS)]
+        vcolp = (u64p * NCOLS)(*[a.ctypes.data_as(u64p) for a in vec_cols])
+        pg_cap = np.empty((ncap, 4), np.uint64)
+
+        def pageable_resident_step():
+            h = ctypes.c_void_p()
+            ctx.check(lib.vpbs_batch_commit(ctx.handle, vcolp, NCOLS, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None,
+                                            pg_cap.ctypes.data_as(u64p), ctypes.byref(h), None))
+            ctx.check(lib.vpbs_batch_eval_ext2(h, zeta.ctypes.data_as(u64p), 2, res_open.ctypes.data_as(u64p)))
+            ctx.check(lib.vpbs_batch_get_leaves(h, query_idx.ctypes.data_as(u64p), 28,
+                                                res_rows.ctypes.data_as(u64p)))
+            ctx.check(lib.vpbs_batch_prove(h, query_idx.ctypes.data_as(u64p), 28,
+                                           res_sib.ctypes.data_as(u64p)))
+            lib.vpbs_batch_destroy(h)
+
+        pg_in = {}
+        for threads in (4, 0):
+            ctx.set_host_threads(threads)
+            for _ in range(2):
+                pageable_resident_step()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                pageable_resident_step()
+            pg_in[threads] = (time.perf_counter() - t0) / args.e2e_steps
+            check("e2e_pageable_inputs.cap_matches_pinned_path_threads%d" % threads, np.array_equal(pg_cap, h_cap))
+        ctx.set_host_threads(4)
+        pageable["inputs_only"] = {
+            "value": n / pg_in[4], "unit": UNIT, "ms_per_step": pg_in[4] * 1e3,
+            "ms_per_step_driver_staging": pg_in[0] * 1e3, "copy_threads": 4,
+            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": res_d2h,
+            "api": "vpbs_batch_commit + openings + 28 rows/paths, value columns in pageable memory (one "
+                   "allocation per column, as plonky2's Vec<PolynomialValues<F>>) through the library's "
+                   "pinned staging ring; *_driver_staging: ring off (vpbs_ctx_set_host_threads(0))"}
+        del g_cols, vec_cols
 
     # (4) what the host link of this box can do (explains e2e_eager): H2D alone, D2H alone, both
     pcie = None

@@ -77,6 +77,16 @@ const char* vpbs_last_error(vpbs_ctx* ctx); /* ctx may be NULL: last create/glob
 /* Total kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t vpbs_ctx_kernel_launches(vpbs_ctx* ctx);
 
+/* Host columns handed to vpbs_commit / vpbs_batch_commit in ORDINARY (pageable) memory — what
+ * plonky2's prover passes to PolynomialBatch::from_values: Vec<PolynomialValues<F>> it allocated
+ * itself, [P2] plonk/prover.rs — are staged by the library through a pinned ring of the context:
+ * `threads` copy threads fill 4 MiB slots in parallel and an uploader thread sends them on the
+ * H2D stream while the kernels of the previous column chunk already run.
+ * Default 4; 0 leaves such copies to the CUDA driver's own staging (serial, on the calling
+ * thread, before any kernel is enqueued).  Page-locked inputs (vpbs_host_alloc) never take
+ * this path. */
+int vpbs_ctx_set_host_threads(vpbs_ctx* ctx, unsigned threads);
+
 /* Pinned host memory for callers that want full-speed PCIe copies. */
 void* vpbs_host_alloc(size_t bytes);
 void vpbs_host_free(void* p);

@@ -57,6 +57,8 @@ class Context {
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   vpbs_ctx* get() const { return h_; }
+  // copy threads of the pinned staging ring for pageable host columns (0: driver staging)
+  void set_host_threads(unsigned threads) { check(vpbs_ctx_set_host_threads(h_, threads)); }
   void check(int rc) const {
     if (rc == VPBS_OK) return;
     std::string msg = vpbs_last_error(h_);

@@ -5,7 +5,7 @@
 //!
 //! NOT compiled in this repository's environment (no Rust toolchain there).
 #![allow(non_camel_case_types)]
-use std::ffi::{c_char, c_int, c_void, CStr};
+use std::ffi::{c_char, c_int, c_uint, c_void, CStr};
 
 #[repr(C)]
 pub struct vpbs_ctx {
@@ -53,6 +53,7 @@ extern "C" {
     pub fn vpbs_ctx_sync(ctx: *mut vpbs_ctx) -> c_int;
     pub fn vpbs_last_error(ctx: *mut vpbs_ctx) -> *const c_char;
     pub fn vpbs_ctx_kernel_launches(ctx: *mut vpbs_ctx) -> u64;
+    pub fn vpbs_ctx_set_host_threads(ctx: *mut vpbs_ctx, threads: c_uint) -> c_int;
     pub fn vpbs_host_alloc(bytes: usize) -> *mut c_void;
     pub fn vpbs_host_free(p: *mut c_void);
     pub fn vpbs_fft(ctx: *mut vpbs_ctx, inout: *mut u64, log_n: u32) -> c_int;

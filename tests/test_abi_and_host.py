@@ -33,6 +33,16 @@ def test_library_contains_sm100a_code_only(V):
     assert not re.search(r"sm_(?!100a)\d+", out)
 
 
+def test_host_stage_copy_pool(tmp_path):
+    """The copy threads behind the pinned staging ring (csrc/host_stage.h) against plain memcpy."""
+    import subprocess
+    exe = str(tmp_path / "test_host_stage")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-pthread", "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "tests", "cpp", "test_host_stage.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "host stage copy pool ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_product_does_not_touch_the_oracle():
     """Nothing under the package may import, link or execute oracle/ (it is test infrastructure)."""
     pkg = os.path.join(ROOT, "verifiable-fhe-paper_b200")

@@ -557,6 +557,50 @@ def test_resident_batch_lazy_openings(V, ctx, oracle, log_n, ncols, rate_bits, c
     rb.close()
 
 
+@pytest.mark.parametrize("log_n,ncols,coeffs", [(13, 128, False), (14, 20, False), (13, 16, True),
+                                               (12, 70, False), (20, 3, False)])
+@pytest.mark.parametrize("threads", [0, 1, 4])
+def test_pageable_host_columns_through_the_pinned_ring(V, oracle, log_n, ncols, coeffs, threads):
+    """Host columns in ordinary (pageable) memory — what plonky2's prover passes to from_values —
+    travel through the context's pinned staging ring (csrc/host_stage.h): column-chunked wide
+    batches, narrow single-chunk batches and columns longer than a ring slot, with 0 (driver
+    staging), 1 and 4 copy threads, and columns that are separate allocations.  The resident and
+    the eager commit must equal the commit from pinned columns and, at the smaller sizes, the oracle."""
+    import ctypes
+    rng = np.random.default_rng(1000 * log_n + ncols)
+    n = 1 << log_n
+    cols = [rand_u64(rng, (n,)) for _ in range(ncols)]          # one allocation per column
+    mat = np.stack(cols)
+    with V.Context(0) as c:
+        c.set_host_threads(threads)
+        u64p, lib = V._lib.u64p, c.lib
+        pin = lib.vpbs_host_alloc(mat.nbytes)
+        pinned = np.ctypeslib.as_array((ctypes.c_uint64 * mat.size).from_address(pin)).reshape(mat.shape)
+        pinned[:] = mat
+        want = V.commit_resident(pinned, 3, False, 4, coeffs, ctx=c)
+        colp = (u64p * ncols)(*[a.ctypes.data_as(u64p) for a in cols])
+        cap = np.empty((16, 4), np.uint64)
+        for _ in range(3):                                       # ring slots are reused across calls
+            h = ctypes.c_void_p()
+            c.check(lib.vpbs_batch_commit(c.handle, colp, ncols, log_n, 3, 4, int(coeffs), None,
+                                          cap.ctypes.data_as(u64p), ctypes.byref(h), None))
+            assert np.array_equal(cap, want.merkle_tree.cap)
+            idx = rng.integers(0, n << 3, size=8, dtype=np.uint64)
+            rows = np.empty((8, ncols), np.uint64)
+            c.check(lib.vpbs_batch_get_leaves(h, idx.ctypes.data_as(u64p), 8, rows.ctypes.data_as(u64p)))
+            assert np.array_equal(rows, want.merkle_tree.get_many(idx))
+            lib.vpbs_batch_destroy(h)
+        if log_n <= 14:
+            eager = V.PolynomialBatch._commit(mat, 3, False, 4, coeffs, c, None, None)
+            assert np.array_equal(eager.merkle_tree.cap, want.merkle_tree.cap)
+            ref = oracle.commit(mat, 3, 4, coeffs, None)
+            assert np.array_equal(cap, ref["cap"])
+            assert np.array_equal(eager.merkle_tree.leaves, ref["leaves"])
+            assert np.array_equal(eager.merkle_tree.digests, ref["digests"])
+        want.close()
+        lib.vpbs_host_free(pin)
+
+
 def test_fri_proof_of_work_grind(V, ctx, oracle):
     """vpbs_pow_grind: the smallest witness found on the GPU is exactly the first one the oracle's
     permutation accepts, for the reference's proof_of_work_bits = 16 (plus the 0 extra bits of a

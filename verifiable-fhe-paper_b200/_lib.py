@@ -47,6 +47,7 @@ SIGNATURES = {
     "vpbs_ctx_sync": (_c.c_int, [_ctx]),
     "vpbs_last_error": (_c.c_char_p, [_ctx]),
     "vpbs_ctx_kernel_launches": (_c.c_uint64, [_ctx]),
+    "vpbs_ctx_set_host_threads": (_c.c_int, [_ctx, _c.c_uint]),
     "vpbs_host_alloc": (_c.c_void_p, [_c.c_size_t]),
     "vpbs_host_free": (None, [_c.c_void_p]),
     "vpbs_fft": (_c.c_int, [_ctx, u64p, _c.c_uint32]),

@@ -9,9 +9,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvpbs_commit.so")
 SOURCES = ["vpbs_commit.cu"]
-HEADERS = ["gl64.cuh", "poseidon.cuh", "poseidon_rc.inc", "poseidon_rcd.inc", "poseidon_rcs.inc", "poseidon_rcp.inc", "ntt.cuh", "merkle.cuh"]
+HEADERS = ["gl64.cuh", "poseidon.cuh", "poseidon_rc.inc", "poseidon_rcd.inc", "poseidon_rcs.inc", "poseidon_rcp.inc", "ntt.cuh", "merkle.cuh",
+           "permutation.cuh", "openings.cuh", "host_stage.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 
 def nvcc() -> str:

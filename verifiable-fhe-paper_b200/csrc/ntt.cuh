@@ -181,11 +181,13 @@ __device__ __forceinline__ void dif16(u64 (&x)[16], const u64* __restrict__ tw, 
     for (int j = 0; j < 16; j++) {
       if ((j & dd) == 0) {
         const u64 a = x[j], c = gl::canon(x[j + dd]);
-        x[j] = gl::add_lazy(a, c);
+        // the _fma forms materialise their carries on the FMA pipe (IMAD.X instead of SEL): these
+        // passes are bound by the ALU pipe (65-69 % against 36 % FMA-heavy), LDE 1.05 -> 1.00 ms
+        x[j] = gl::add_lazy_fma(a, c);
         const u64 d = gl::sub_lazy(a, c);
         const int jm = j & (dd - 1);
         if (!HAS_OFF && jm == 0) x[j + dd] = d;
-        else x[j + dd] = gl::mul_lazy(d, tw[((unsigned)jm * jstride + off) << (l0 + l)]);
+        else x[j + dd] = gl::mul_lazy_fma(d, tw[((unsigned)jm * jstride + off) << (l0 + l)]);
       }
     }
   }
@@ -280,8 +282,8 @@ pass_strided_r16p(const u64* __restrict__ src, u64 src_col_stride, u64* __restri
     if (in_scale) {
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        if (OUT_TW) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + base + ((u64)(16 * j + qa) << log_sigma) + low0 + t));
-        else x[j] = gl::mul_lazy(x[j], sq[16 * j + qa]);
+        if (OUT_TW) x[j] = gl::mul_lazy_fma(x[j], __ldg(in_scale + base + ((u64)(16 * j + qa) << log_sigma) + low0 + t));
+        else x[j] = gl::mul_lazy_fma(x[j], sq[16 * j + qa]);
       }
     }
     dif16<true>(x, tw, 16, qa, 0);
@@ -298,7 +300,7 @@ pass_strided_r16p(const u64* __restrict__ src, u64 src_col_stride, u64* __restri
       const unsigned q = 16 * qa + j;
       if (OUT_TW) {
         const u64 e = (low0 + t) * (u64)brev(q, 8);
-        out[(u64)q << log_sigma] = e ? gl::mul_lazy(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
+        out[(u64)q << log_sigma] = e ? gl::mul_lazy_fma(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
       } else {
         out[(u64)q << log_sigma] = x[j];
       }
@@ -350,7 +352,7 @@ pass_final_r16p(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
   const u64 tw_scale = (in_tw && in_tw_scale) ? __ldg(in_tw_scale + threadIdx.x) : 1;
   issue(tile, buf);
   cp_async_commit();
-  if (in_tw) tws[threadIdx.x] = gl::mul_lazy(twiddle(tile), tw_scale);
+  if (in_tw) tws[threadIdx.x] = gl::mul_lazy_fma(twiddle(tile), tw_scale);
   for (unsigned it = 0;; it++) {
     u64* cur = buf + (it & 1) * (256 * 17);
     const u64* twc = tws + (it & 1) * 256;
@@ -371,11 +373,11 @@ pass_final_r16p(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
       const unsigned bx = tile % tiles_x;
       const u64 pos0 = MODE == STORE_LEAF ? ((u64)bx << 8) : ((u64)brev(bx * 16 + lane_a, log_nb) << 8);
 #pragma unroll
-      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + pos0 + 16 * j + q_lo));
+      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy_fma(x[j], __ldg(in_scale + pos0 + 16 * j + q_lo));
     }
     if (in_tw) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], twc[16 * j + q_lo]);
+      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy_fma(x[j], twc[16 * j + q_lo]);
     }
     dif16<true>(x, tw, 16, q_lo, 0);
 #pragma unroll
@@ -383,7 +385,7 @@ pass_final_r16p(const u64* __restrict__ src, u64 src_col_stride, unsigned ncols,
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 16; j++) x[j] = cur[(16 * q_hi + j) * 17 + lane_b];
-    if (in_tw && next < ntiles) tws[((it & 1) ^ 1) * 256 + threadIdx.x] = gl::mul_lazy(w_next, tw_scale);
+    if (in_tw && next < ntiles) tws[((it & 1) ^ 1) * 256 + threadIdx.x] = gl::mul_lazy_fma(w_next, tw_scale);
     __syncthreads();  // everyone is done with `cur` before the next iteration refills it
     dif16<false>(x, tw, 1, 0, 4);
     const unsigned bx = tile % tiles_x, by = tile / tiles_x;
@@ -511,8 +513,8 @@ pass_strided_r16t(const __grid_constant__ tma::TileMap map, u64* __restrict__ ds
     if (in_scale) {
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        if (OUT_TW) x[j] = gl::mul_lazy(x[j], __ldg(in_scale + base + ((u64)(16 * j + qa) << log_sigma) + low0 + t));
-        else x[j] = gl::mul_lazy(x[j], sq[16 * j + qa]);
+        if (OUT_TW) x[j] = gl::mul_lazy_fma(x[j], __ldg(in_scale + base + ((u64)(16 * j + qa) << log_sigma) + low0 + t));
+        else x[j] = gl::mul_lazy_fma(x[j], sq[16 * j + qa]);
       }
     }
     dif16<true>(x, tw, 16, qa, 0);
@@ -530,7 +532,7 @@ pass_strided_r16t(const __grid_constant__ tma::TileMap map, u64* __restrict__ ds
       const unsigned q = 16 * qa + j;
       if (OUT_TW) {
         const u64 e = (low0 + t) * (u64)brev(q, 8);
-        out[(u64)q << log_sigma] = e ? gl::mul_lazy(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
+        out[(u64)q << log_sigma] = e ? gl::mul_lazy_fma(x[j], root_of<INVERSE>(R, log_B, e)) : x[j];
       } else {
         out[(u64)q << log_sigma] = x[j];
       }
@@ -587,7 +589,7 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
     return root_of<INVERSE>(R, in_tw_log_B, (u64)threadIdx.x * brev((tl % tiles_x) & 255u, 8));
   };
   const u64 tw_scale = (in_tw && in_tw_scale) ? __ldg(in_tw_scale + threadIdx.x) : 1;
-  if (in_tw) tws[threadIdx.x] = gl::mul_lazy(twiddle(tile), tw_scale);
+  if (in_tw) tws[threadIdx.x] = gl::mul_lazy_fma(twiddle(tile), tw_scale);
   __syncthreads();  // barriers initialised; tw and the first tws visible
   if (threadIdx.x == 0) issue(tile, 0);
   for (unsigned it = 0;; it++) {
@@ -605,7 +607,7 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
     for (int j = 0; j < 16; j++) x[j] = cur[lane_a * 256 + 16 * j + q_lo];
     if (in_tw) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy(x[j], twc[16 * j + q_lo]);
+      for (int j = 0; j < 16; j++) x[j] = gl::mul_lazy_fma(x[j], twc[16 * j + q_lo]);
     }
     dif16<true>(x, tw, 16, q_lo, 0);
     __syncwarp();  // the slots written next were read by threads of this half-warp
@@ -614,7 +616,7 @@ pass_final_r16t(const __grid_constant__ tma::TileMap map, unsigned ncols, u64* _
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 16; j++) x[j] = cur[lane_b * 256 + 16 * q_hi + (j ^ lane_b)];
-    if (in_tw && next < ntiles) tws[((it & 1) ^ 1) * 256 + threadIdx.x] = gl::mul_lazy(w_next, tw_scale);
+    if (in_tw && next < ntiles) tws[((it & 1) ^ 1) * 256 + threadIdx.x] = gl::mul_lazy_fma(w_next, tw_scale);
     tma::fence_proxy_async();
     __syncthreads();  // everyone is done with `cur` before the next bulk copy refills it
     dif16<false>(x, tw, 1, 0, 4);

@@ -16,12 +16,14 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <string>
 #include <vector>
 
 #include "../../include/vpbs_commit.h"
+#include "host_stage.h"
 #include "merkle.cuh"
 #include "ntt.cuh"
 #include "openings.cuh"
@@ -80,6 +82,10 @@ struct vpbs_ctx {
   std::set<struct vpbs_batch*> batches;
   std::set<struct vpbs_sigmas*> sigma_sets;
   std::set<struct vpbs_fri*> fri_chains;
+  // Host columns that are not page-locked travel through this pinned ring, filled by host_threads
+  // copy threads (host_stage.h); 0 threads: leave such copies to the driver's own staging.
+  hoststage::Ring ring;
+  unsigned host_threads = 4;
 };
 
 // A commit kept in HBM (vpbs_batch_*): owns its device buffers, reads go through the context.
@@ -490,6 +496,10 @@ struct Overlap {
   bool lde_by_block = false;  // chunked inputs, but LDE over all columns block by block (see commit_core)
   std::vector<cudaEvent_t> h2d_ready, coeffs_chunk_ready;
   cudaEvent_t lde_done = nullptr;
+  // Staged upload in flight (pageable host columns): h2d_ready[k] is recorded by the uploader thread,
+  // and a stream wait enqueued before the record would wait for nothing — so the enqueueing thread
+  // first waits on the host until the record has happened.
+  hoststage::Upload* upload = nullptr;
 };
 
 struct Timer {
@@ -588,8 +598,10 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   for (u32 c0 = 0, k = 0; c0 < ncols; c0 += chunk, k++) {
     const u32 nc = ncols - c0 < chunk ? ncols - c0 : chunk;
     if (chunked && k < ov->h2d_ready.size()) {
+      if (ov->upload) ov->upload->wait_recorded(k);
       CU(ctx, cudaStreamWaitEvent(ctx->stream, ov->h2d_ready[k], 0));
     } else if (!chunked && ov) {  // uploads on the H2D stream but a single compute chunk: wait for all
+      if (ov->upload && !ov->h2d_ready.empty()) ov->upload->wait_recorded((unsigned)ov->h2d_ready.size() - 1);
       for (cudaEvent_t e : ov->h2d_ready) CU(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
     }
     // "IFFT": values -> coefficients (natural order), scaled by n^-1.
@@ -805,6 +817,7 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
   if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
   if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
 
+  ctx->ring.release();
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -812,6 +825,13 @@ void vpbs_ctx_destroy(vpbs_ctx* ctx) {
 int vpbs_ctx_set_stream(vpbs_ctx* ctx, void* cuda_stream) {
   if (!usable(ctx)) return VPBS_ERR_STATE;
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return VPBS_OK;
+}
+
+int vpbs_ctx_set_host_threads(vpbs_ctx* ctx, unsigned threads) {
+  if (!usable(ctx)) return VPBS_ERR_STATE;
+  if (threads > 64) return fail(ctx, VPBS_ERR_ARG, "host_threads > 64");
+  ctx->host_threads = threads;
   return VPBS_OK;
 }
 
@@ -1087,11 +1107,43 @@ namespace {
 // Width of the column chunks wide host batches travel in (0: one piece).
 u32 host_chunk_cols(u32 ncols, u32 log_n) { return (ncols >= 64 && log_n >= 12) ? 32u : 0u; }
 
+// Host columns in ordinary (pageable) memory, and enough of them to matter: the library stages them
+// through its own pinned ring (host_stage.h) instead of leaving it to the driver.
+bool want_staging(vpbs_ctx* ctx, const uint64_t* const* cols, u32 ncols, u64 n) {
+  if (ctx->host_threads == 0 || (u64)ncols * n * sizeof(u64) < (1u << 20)) return false;
+  return hoststage::is_pageable(cols[0]) && hoststage::is_pageable(cols[ncols - 1]);
+}
+// Starts the uploader thread for columns [0, ncols) in chunks of chunk_cols (0: one chunk); chunk k's
+// event is ready[k].
+int start_staged_upload(vpbs_ctx* ctx, u64* din, const uint64_t* const* cols, u32 ncols, u64 n,
+                        u32 chunk_cols, const std::vector<cudaEvent_t>& ready, cudaStream_t hs,
+                        cudaEvent_t done_ev, std::unique_ptr<hoststage::Upload>* out) {
+  CU(ctx, ctx->ring.ensure(ctx->host_threads));
+  std::unique_ptr<hoststage::Upload> up(new hoststage::Upload());
+  up->device = ctx->device;
+  up->ring = &ctx->ring;
+  up->stream = hs;
+  up->dev = din;
+  up->cols = cols;
+  up->n = n;
+  up->ready = ready;
+  up->done_ev = done_ev;
+  for (u32 c0 = 0; c0 < ncols;) {
+    const u32 c1 = (chunk_cols && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
+    up->chunks.push_back({c0, c1});
+    c0 = c1;
+  }
+  up->start();
+  *out = std::move(up);
+  return VPBS_OK;
+}
+
 // State between commit_host_enqueue and commit_host_finish.
 struct HostRun {
   Timer tm{nullptr, false};
   bool chunked = false;
   uint64_t l0 = 0;
+  std::unique_ptr<hoststage::Upload> upload;  // staged upload in flight (joined by commit_host_finish)
 };
 
 // One commit — or the row-range shard [first_leaf, first_leaf + nleaves_shard) of one — from host
@@ -1154,10 +1206,12 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
   // chunk by its owner GPU, then peer copies); `delivered` holds one event per chunk (or a single
   // one) in place of this context's own uploads
   if (delivered) ovl.h2d_ready = *delivered;
-  run->chunked = nchunks != 0;
-  cudaStream_t hs = nchunks ? ctx->h2d_stream : ctx->stream;
+  const bool staged = !delivered && want_staging(ctx, cols, ncols, n);
+  if (staged && !nchunks) ovl.h2d_ready.assign(1, ctx->ov[evi]);  // one upload event, one compute chunk
+  run->chunked = nchunks != 0 || staged;
+  cudaStream_t hs = run->chunked ? ctx->h2d_stream : ctx->stream;
   if (want_stats) cudaEventRecord(e0, ctx->stream);
-  if (nchunks) {  // the H2D stream starts after whatever the caller queued on the compute stream
+  if (run->chunked) {  // the H2D stream starts after whatever the caller queued on the compute stream
     CU(ctx, cudaEventRecord(all_done, ctx->stream));
     CU(ctx, cudaStreamWaitEvent(hs, all_done, 0));
   }
@@ -1167,13 +1221,19 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
       CU(ctx, cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice,
                               ctx->stream));
     }
-  for (u32 c0 = 0, k = 0; c0 < ncols && !delivered; k++) {
+  if (staged) {
+    if ((rc = start_staged_upload(ctx, din, cols, ncols, n, chunk_cols, ovl.h2d_ready, hs,
+                                  want_stats ? e1 : nullptr, &run->upload)))
+      return rc;
+    ovl.upload = run->upload.get();
+  }
+  for (u32 c0 = 0, k = 0; c0 < ncols && !delivered && !staged; k++) {
     const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
     CU(ctx, copy_columns(din, cols, c0, c1, n, true, hs));
     if (nchunks) CU(ctx, cudaEventRecord(ovl.h2d_ready[k], hs));
     c0 = c1;
   }
-  if (want_stats) cudaEventRecord(e1, hs);
+  if (want_stats && !staged) cudaEventRecord(e1, hs);
   // Output copies run on the copy stream as soon as their data is final: coefficients after the
   // IFFT, leaf rows after their last NTT pass, digests and cap after the tree.  All kernels are
   // enqueued first, so the copies overlap the remaining NTT passes and the hashing.
@@ -1183,6 +1243,7 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
                    nleaves_shard, inputs_are_coeffs ? nullptr : dco, dle, ddi, dca, &run->tm);
   run->tm.overlap = nullptr;
   if (rc) {
+    if (run->upload) run->upload->join();
     cudaStreamSynchronize(hs);
     return rc;
   }
@@ -1222,6 +1283,13 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
 }
 
 int commit_host_finish(vpbs_ctx* ctx, HostRun* run, vpbs_stats* stats) {
+  if (run->upload) {
+    const cudaError_t ue = run->upload->join();
+    if (ue != cudaSuccess) {
+      cudaStreamSynchronize(ctx->stream);
+      return fail(ctx, VPBS_ERR_CUDA, std::string("staged upload: ") + cudaGetErrorString(ue));
+    }
+  }
   CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   if (run->chunked) CU(ctx, cudaStreamSynchronize(ctx->h2d_stream));
@@ -1904,27 +1972,43 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
   cudaError_t ce = cudaSuccess;
   // Wide batches: inputs travel in column chunks on the H2D stream and chunk k is transformed
   // (IFFT + its columns of every LDE block) while chunk k+1 is still on the bus.
-  const u32 chunk_cols = (ncols >= 64 && log_n >= 12) ? 32 : 0;
+  const u32 chunk_cols = host_chunk_cols(ncols, log_n);
   const u32 nchunks = chunk_cols ? (ncols + chunk_cols - 1) / chunk_cols : 0;
+  for (u32 c = 0; c < ncols; c++)
+    if (!cols[c]) {
+      vpbs_batch_destroy(b);
+      return fail(ctx, VPBS_ERR_ARG, "cols[c] == NULL");
+    }
+  // Pageable host columns go through the context's pinned ring (host_stage.h), also when the batch
+  // is too narrow for chunked compute (one upload event then).
+  const bool staged = want_staging(ctx, cols, ncols, n);
+  const u32 nup = nchunks ? nchunks : (staged ? 1u : 0u);  // upload events
   Overlap ovl;
-  cudaStream_t hs = nchunks ? ctx->h2d_stream : ctx->stream;
-  if (nchunks) {
-    while (ctx->ov.size() < (size_t)nchunks + 1 && ce == cudaSuccess) {
+  std::unique_ptr<hoststage::Upload> upload;
+  cudaStream_t hs = nup ? ctx->h2d_stream : ctx->stream;
+  if (nup) {
+    while (ctx->ov.size() < (size_t)nup + 1 && ce == cudaSuccess) {
       cudaEvent_t e;
       ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
       if (ce == cudaSuccess) ctx->ov.push_back(e);
     }
     if (ce == cudaSuccess) {
       ovl.chunk_cols = chunk_cols;
-      ovl.h2d_ready.assign(ctx->ov.begin() + 1, ctx->ov.begin() + 1 + nchunks);
+      ovl.h2d_ready.assign(ctx->ov.begin() + 1, ctx->ov.begin() + 1 + nup);
       // the H2D stream starts after whatever the caller queued on the compute stream
       ce = cudaEventRecord(ctx->ov[0], ctx->stream);
       if (ce == cudaSuccess) ce = cudaStreamWaitEvent(hs, ctx->ov[0], 0);
     }
   }
-  for (u32 c = 0; c < ncols && ce == cudaSuccess; c++)
-    if (!cols[c]) ce = cudaErrorInvalidValue;
-  for (u32 c0 = 0, k = 0; c0 < ncols && ce == cudaSuccess; k++) {
+  if (staged && ce == cudaSuccess) {
+    if ((rc = start_staged_upload(ctx, din, cols, ncols, n, chunk_cols, ovl.h2d_ready, hs,
+                                  stats ? e1 : nullptr, &upload))) {
+      vpbs_batch_destroy(b);
+      return rc;
+    }
+    ovl.upload = upload.get();
+  }
+  for (u32 c0 = 0, k = 0; c0 < ncols && ce == cudaSuccess && !staged; k++) {
     const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
     ce = copy_columns(din, cols, c0, c1, n, true, hs);
     if (ce == cudaSuccess && nchunks) ce = cudaEventRecord(ovl.h2d_ready[k], hs);
@@ -1936,19 +2020,24 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
       ce = cudaMemcpyAsync(dsa + (u64)s * m, salt_cols[s], m * 8, cudaMemcpyHostToDevice, ctx->stream);
     }
   if (ce != cudaSuccess) {
-    if (nchunks) cudaStreamSynchronize(hs);
+    if (upload) upload->join();
+    if (nup) cudaStreamSynchronize(hs);
     vpbs_batch_destroy(b);
     return fail(ctx, ce == cudaErrorInvalidValue ? VPBS_ERR_ARG : VPBS_ERR_CUDA,
                 std::string("batch input copy: ") + cudaGetErrorString(ce));
   }
-  if (stats) cudaEventRecord(e1, hs);
+  if (stats && !staged) cudaEventRecord(e1, hs);
   Timer tm{ctx, stats != nullptr};
-  if (nchunks) tm.overlap = &ovl;
+  if (nup) tm.overlap = &ovl;
   // coefficients always end up in the batch (from_coeffs: a device copy of the inputs)
   rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
                    b->coeffs, b->leaves, b->digests, b->cap, &tm);
+  const cudaError_t ue = upload ? upload->join() : cudaSuccess;
+  if (rc == VPBS_OK && ue != cudaSuccess)
+    rc = fail(ctx, VPBS_ERR_CUDA, std::string("staged upload: ") + cudaGetErrorString(ue));
   if (rc) {
-    if (nchunks) cudaStreamSynchronize(hs);
+    if (nup) cudaStreamSynchronize(hs);
+    cudaStreamSynchronize(ctx->stream);
     vpbs_batch_destroy(b);
     return rc;
   }

@@ -120,6 +120,11 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._L.vpbs_ctx_kernel_launches(self._h))
 
+    def set_host_threads(self, threads: int):
+        """Copy threads of the pinned staging ring that pageable host columns travel through
+        (vpbs_ctx_set_host_threads; 0: leave such copies to the driver)."""
+        self.check(self._L.vpbs_ctx_set_host_threads(self._h, int(threads)))
+
 
 _default_ctx: Optional[Context] = None
 
