@@ -394,6 +394,11 @@ def main():
     ap.add_argument("--chain-eager", action="store_true",
                     help="with --chain-steps: also time round 1's eager form of the step (all outputs "
                          "of the first two commits downloaded)")
+    ap.add_argument("--chain-shard", action="store_true",
+                    help="with --chain-steps under torchrun: ONE chain for all ranks — every resident "
+                         "batch of a step is sharded by row range over the GPUs (vpbs_ctx_set_shard), "
+                         "the caps are completed by an NCCL all-gather and the query openings "
+                         "collected from the owners; strong scaling of the step latency")
     ap.add_argument("--shard-commit", action="store_true",
                     help="strong scaling of ONE commit: every rank computes its row range "
                          "(vpbs_commit_shard_dev) and the subtree roots are all-gathered over NCCL")
@@ -1076,12 +1081,22 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     def ptrs(a):
         return (u64p * a.shape[0])(*[a[c].ctypes.data_as(u64p) for c in range(a.shape[0])])
 
+    import torch
+    shard = bool(args.chain_shard) and world > 1   # ONE chain, every batch sharded over the ranks
+    sp = V.ShardedProof(rank, world, torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    sharded_now = [False]
+
+    def set_sharding(on):
+        sharded_now[0] = bool(on)
+        ctx.set_shard(rank if on else 0, world if on else 1)
+
     shapes = [(135, False), (20, False), (16, True)]
     ins, caps = [], []
     for i, (c, _) in enumerate(shapes):
-        a = pinned((c, n)); a[:] = V.synthetic_columns(c, n, 0x5EED0000 + 1000 * rank + c)
+        a = pinned((c, n)); a[:] = V.synthetic_columns(c, n, 0x5EED0000 + (0 if shard else 1000 * rank) + c)
         ins.append(a); caps.append(pinned((ncap, 4)))
     pin = [ptrs(a) for a in ins]
+    ins0 = [a.copy() for a in ins] if shard else None
     num_routed, max_degree = 80, 8
     sig = V.Sigmas(V.synthetic_columns(num_routed, n, 0x51630000), V.get_unique_coset_shifts(n, num_routed), ctx)
     g_n = pow(7, (P_GL - 1) >> log_n, P_GL)  # generator of the trace subgroup
@@ -1096,9 +1111,22 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     CS = 85
     cs_cols = pinned((CS, n)); cs_cols[:] = V.synthetic_columns(CS, n, 0x5EED0000 + 85)
     cs_cap = np.empty((ncap, 4), np.uint64)
-    h_cs = ctypes.c_void_p()
-    ctx.check(lib.vpbs_batch_commit(ctx.handle, ptrs(cs_cols), CS, log_n, RATE_BITS, CAP_HEIGHT, 0, None,
-                                    cs_cap.ctypes.data_as(u64p), ctypes.byref(h_cs), None))
+    cs_ptrs = ptrs(cs_cols)
+    cs = {"h": None}
+
+    def commit_cs():  # (re)commit the constants/sigmas batch under the current sharding
+        if cs["h"] is not None:
+            lib.vpbs_batch_destroy(cs["h"])
+        if sharded_now[0]:
+            cs["h"], full = sp.commit_from_host(ctx, cs_cols, RATE_BITS, CAP_HEIGHT)
+            cs_cap[:] = full
+            return
+        cs["h"] = ctypes.c_void_p()
+        ctx.check(lib.vpbs_batch_commit(ctx.handle, cs_ptrs, CS, log_n, RATE_BITS, CAP_HEIGHT, 0, None,
+                                        cs_cap.ctypes.data_as(u64p), ctypes.byref(cs["h"]), None))
+
+    set_sharding(shard)
+    commit_cs()
     widths = [CS] + [c for c, _ in shapes]  # FRI_ORACLES order: constants_sigmas, wires, zs, quotient
     opens = [np.empty((2, c, 2), np.uint64) for c in widths]
     rows = [np.empty((28, c), np.uint64) for c in widths]
@@ -1106,26 +1134,50 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     fri_batches = [[(o, j) for o, c in enumerate(widths) for j in range(c)], [(2, 0), (2, 1)]]
     stats = {"fri_layers": 0}
 
+    phase = {}
+
+    def lap(name, t0):  # host-side time of one section of the step (every section ends synchronised)
+        t1 = time.perf_counter()
+        phase[name] = phase.get(name, 0.0) + (t1 - t0)
+        return t1
+
     def resident_step():
         hs = [ctypes.c_void_p() for _ in range(3)]
-        ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[0], 135, log_n, RATE_BITS, CAP_HEIGHT, 0, None,
-                                        caps[0].ctypes.data_as(u64p), ctypes.byref(hs[0]), None))
+        t = time.perf_counter()
+        if sharded_now[0]:  # every column crosses PCIe once (1 / world per rank), then NVLink all-gather
+            hs[0], full = sp.commit_from_host(ctx, ins[0], RATE_BITS, CAP_HEIGHT)
+            caps[0][:] = full
+        else:
+            ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[0], 135, log_n, RATE_BITS, CAP_HEIGHT, 0, None,
+                                            caps[0].ctypes.data_as(u64p), ctypes.byref(hs[0]), None))
+        t = lap("wires_commit", t)
         bg = challenge(caps[0], 1, 4)
         ctx.check(lib.vpbs_batch_zs_partial_products(hs[0], sig.handle, max_degree, bg[:2].ctypes.data_as(u64p),
                                                      bg[2:].ctypes.data_as(u64p), 2, RATE_BITS, CAP_HEIGHT,
                                                      caps[1].ctypes.data_as(u64p), ctypes.byref(hs[1]), None))
+        t = lap("zs_commit", t)
+        if sharded_now[0]:
+            sp.complete_cap(caps[1])
+            t = lap("cap_gather", t)
         ins[2][:, 0] ^= caps[1].reshape(-1)[:16] >> np.uint64(1)  # the quotient depends on alpha <- cap 1
-        ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, log_n, RATE_BITS, CAP_HEIGHT, 1, None,
-                                        caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
+        if sharded_now[0]:
+            hs[2], full = sp.commit_from_host(ctx, ins[2], RATE_BITS, CAP_HEIGHT, True)
+            caps[2][:] = full
+        else:
+            ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, log_n, RATE_BITS, CAP_HEIGHT, 1, None,
+                                            caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
+        t = lap("quotient_commit", t)
         zeta = challenge(caps[2], 2, 2)
         gz = np.array([int(zeta[0]) * g_n % P_GL, int(zeta[1]) * g_n % P_GL], np.uint64)
         pts = np.stack([zeta, gz])
-        allh = [h_cs] + hs
+        allh = [cs["h"]] + hs
         for k in range(4):  # OpeningSet::new
             ctx.check(lib.vpbs_batch_eval_ext2(allh[k], pts.ctypes.data_as(u64p), 2, opens[k].ctypes.data_as(u64p)))
+        t = lap("openings", t)
         alpha = challenge(opens[3][0, :4].copy(), 3, 2)
         obs = [_Resident(ctx, h, log_n) for h in allh]
         fri = V.FriCommitPhase.from_openings(obs, fri_batches, pts, alpha, RATE_BITS)
+        t = lap("prove_openings", t)
         lg, k, cap = log_n + RATE_BITS, 0, caps[2]
         while lg - RATE_BITS > 5 and lg - 4 >= CAP_HEIGHT:  # ConstantArityBits(4, 5)
             cap = fri.commit_layer(4, min(CAP_HEIGHT, lg - 4))
@@ -1134,20 +1186,39 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
             k += 1
         stats["fri_layers"] = k
         final = fri.final_poly()
+        t = lap("fri_commit_phase", t)
         pow_state = challenge(final[: min(4, final.shape[0])].copy(), 9, 12)
         w = V.fri_proof_of_work(pow_state, 5, 16, ctx=ctx)
+        t = lap("pow", t)
         qidx = np.random.default_rng(int(w or 0) + 1).integers(0, m, size=28, dtype=np.uint64)
-        for b in range(4):
-            ctx.check(lib.vpbs_batch_get_leaves(allh[b], qidx.ctypes.data_as(u64p), 28, rows[b].ctypes.data_as(u64p)))
-            ctx.check(lib.vpbs_batch_prove(allh[b], qidx.ctypes.data_as(u64p), 28, sibs[b].ctypes.data_as(u64p)))
+        if not sharded_now[0]:
+            for b in range(4):
+                ctx.check(lib.vpbs_batch_get_leaves(allh[b], qidx.ctypes.data_as(u64p), 28, rows[b].ctypes.data_as(u64p)))
+                ctx.check(lib.vpbs_batch_prove(allh[b], qidx.ctypes.data_as(u64p), 28, sibs[b].ctypes.data_as(u64p)))
+        else:  # every rank opens the rows its shard holds; one all-reduce hands all of them to everyone
+            own = sp.owned(qidx, m)
+            q_own = np.ascontiguousarray(qidx[own])
+            for b in range(4):
+                rows[b][:] = 0
+                sibs[b][:] = 0
+                if len(q_own):
+                    r = np.empty((len(q_own), widths[b]), np.uint64)
+                    sb = np.empty((len(q_own), nlayers, 4), np.uint64)
+                    ctx.check(lib.vpbs_batch_get_leaves(allh[b], q_own.ctypes.data_as(u64p), len(q_own), r.ctypes.data_as(u64p)))
+                    ctx.check(lib.vpbs_batch_prove(allh[b], q_own.ctypes.data_as(u64p), len(q_own), sb.ctypes.data_as(u64p)))
+                    rows[b][own] = r
+                    sibs[b][own] = sb
+            sp.collect(rows + sibs)
         qi = qidx.copy()
         for layer in range(k):
             qi = qi >> np.uint64(4)
             fri.query(layer, qi)
+        t = lap("queries", t)
         fri.close()
         for h in reversed(hs):
             lib.vpbs_batch_destroy(h)
         ins[0][:, 0] ^= np.resize(caps[2].reshape(-1) ^ cap.reshape(-1)[:1], 135) >> np.uint64(1)  # next step
+        lap("teardown", t)
 
     class _Resident:  # the two attributes FriCommitPhase.from_openings reads
         def __init__(self, c, h, lg):
@@ -1184,9 +1255,29 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
             eager_step()
         out_eager = max_over_ranks(time.perf_counter() - t0) / k_e * 1e3
 
+    shard_check = None
+    if shard:
+        # the sharded step must reproduce the unsharded one bit for bit: caps of the three commits, the
+        # opened rows and the Merkle paths of all four batches, over two dependent steps from the same start
+        def trace(on):
+            set_sharding(on)
+            commit_cs()
+            for a, a0 in zip(ins, ins0):
+                a[:] = a0
+            out = []
+            for _ in range(2):
+                resident_step()
+                out.append([c.copy() for c in caps] + [cs_cap.copy()] + [r.copy() for r in rows] +
+                           [x.copy() for x in sibs])
+            return out
+        ta, tb = trace(False), trace(True)
+        shard_check = all(np.array_equal(x, y) for sa, sb_ in zip(ta, tb) for x, y in zip(sa, sb_))
+        for a, a0 in zip(ins, ins0):
+            a[:] = a0
     for _ in range(3):
         resident_step()
     barrier()
+    phase.clear()
     l0 = ctx.kernel_launches
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
@@ -1199,7 +1290,12 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     launches = (ctx.kernel_launches - l0) // args.chain_steps
     barrier()
     sig.close()
-    lib.vpbs_batch_destroy(h_cs)
+    lib.vpbs_batch_destroy(cs["h"])
+    if shard:
+        ok = [None] * world
+        import torch.distributed as dist
+        dist.all_gather_object(ok, bool(shard_check))
+        shard_check = all(ok)
     if rank == 0:
         h2d = 8 * n * (135 + 16) + 16 * 8
         d2h = (3 * 32 * ncap + sum(widths) * 2 * 16 + stats["fri_layers"] * 32 * ncap +
@@ -1210,11 +1306,23 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
                       "sequentially dependent chain" % (1024 if log_n == 16 else 8 if log_n == 13 else 0, log_n),
             "value": dt / args.chain_steps * 1e3, "unit": "ms per step (device-side scope of prove())",
             "higher_is_better": False, "n_gpus": world, "steps": args.chain_steps,
-            "chains": world, "steps_per_s_all_gpus": world * args.chain_steps / dt,
-            "full_pbs_730_steps_s": 730 * dt / args.chain_steps, "scaling": "weak", "dtype": "u64",
+            "chains": 1 if shard else world,
+            "steps_per_s_all_gpus": (1 if shard else world) * args.chain_steps / dt,
+            "full_pbs_730_steps_s": 730 * dt / args.chain_steps, "scaling": "strong" if shard else "weak",
+            "sharded_step": None if not shard else {
+                "ranks": world, "matches_unsharded_step": shard_check,
+                "what": "ONE chain: every resident batch of a step (constants/sigmas, wires, Z, quotient) "
+                        "holds the rows of its rank only (vpbs_ctx_set_shard); host columns cross PCIe "
+                        "once (1 / ranks of them per rank) and reach the other GPUs by an NCCL "
+                        "all-gather over NVLink; per commit the cap is "
+                        "completed by an NCCL all-gather of 32 B per entry, per step the 28 x 4 opened "
+                        "rows + paths are collected by one all-reduce; IFFTs, Z, openings and the FRI "
+                        "commit phase are computed by every rank (they need all coefficients)"},
+            "dtype": "u64",
             "data": "synthetic", "vs_baseline": None, "log_n": log_n,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step_approx": d2h,
             "gpu_launches_per_step": int(launches), "fri_layers": stats["fri_layers"],
+            "phase_ms_rank0": {k: round(v / args.chain_steps * 1e3, 4) for k, v in phase.items()},
             "eager_commits_ms_per_step": out_eager,
             "eager_note": "round 1's form of the step: the three commits with coefficients, LDE rows and "
                           "digests of the first two downloaded to pinned host memory (--chain-eager)",
@@ -1225,6 +1333,8 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    if shard and not shard_check:
+        sys.exit(3)
 
 
 def run_shard_commit(args, V, ctx, rank, world, dev, barrier, max_over_ranks, emit):

@@ -87,6 +87,22 @@ uint64_t vpbs_ctx_kernel_launches(vpbs_ctx* ctx);
  * this path. */
 int vpbs_ctx_set_host_threads(vpbs_ctx* ctx, unsigned threads);
 
+/* Row-range sharding of ONE proof over several GPUs (partitioning B): after
+ * vpbs_ctx_set_shard(ctx, index, count) every resident batch this context creates
+ * (vpbs_batch_commit / _commit_dev / vpbs_batch_zs_partial_products) keeps ALL coefficient columns
+ * but transforms, hashes and holds only leaves [index * m / count, (index + 1) * m / count) and the
+ * digests / cap entries of the cap subtrees under them.  count: a power of two; m / count must be
+ * whole n-row LDE blocks and whole cap subtrees (count <= 2^rate_bits and <= 2^cap_height), else
+ * the commit returns VPBS_ERR_ARG.  cap_out of such a commit has all 2^cap_height entries, the ones
+ * of other shards ZERO: the caller fills them by gathering the other shards' entries (NCCL
+ * all-gather of 32 B per entry — the only cross-GPU traffic of a sharded commit); the union is
+ * bit-identical to the unsharded commit.  vpbs_batch_get_leaves / _prove / _get_lde_rows of a
+ * sharded batch serve the rows of its own range (global leaf indices; others: VPBS_ERR_ARG),
+ * vpbs_batch_download copies the shard's rows and digests.  Everything that reads coefficients
+ * (vpbs_batch_eval_ext2, vpbs_batch_zs_partial_products, vpbs_fri_begin_openings) is unaffected.
+ * count == 1 (the default) switches sharding off. */
+int vpbs_ctx_set_shard(vpbs_ctx* ctx, uint32_t index, uint32_t count);
+
 /* Pinned host memory for callers that want full-speed PCIe copies. */
 void* vpbs_host_alloc(size_t bytes);
 void vpbs_host_free(void* p);
@@ -325,6 +341,8 @@ int vpbs_batch_get_lde_rows(vpbs_batch* batch, uint64_t first_index, uint64_t st
 /* Shape of the batch: m = 2^(log_n + rate_bits) leaves of `width` elements. */
 int vpbs_batch_shape(vpbs_batch* batch, uint32_t* ncols, uint32_t* log_n, uint32_t* rate_bits,
                      uint32_t* cap_height, uint32_t* width);
+/* Leaves the batch holds: [first_leaf, first_leaf + nleaves) (0 and m unless its context shards). */
+int vpbs_batch_shard(vpbs_batch* batch, uint64_t* first_leaf, uint64_t* nleaves);
 
 /* ---- permutation argument: Z and partial products (first device consumer) ---
  * [P2] plonky2/src/plonk/prover.rs wires_permutation_partial_products_and_zs /

@@ -59,6 +59,8 @@ class Context {
   vpbs_ctx* get() const { return h_; }
   // copy threads of the pinned staging ring for pageable host columns (0: driver staging)
   void set_host_threads(unsigned threads) { check(vpbs_ctx_set_host_threads(h_, threads)); }
+  // row-range shard of the resident batches created afterwards (one proof over `count` GPUs)
+  void set_shard(uint32_t index, uint32_t count) { check(vpbs_ctx_set_shard(h_, index, count)); }
   void check(int rc) const {
     if (rc == VPBS_OK) return;
     std::string msg = vpbs_last_error(h_);

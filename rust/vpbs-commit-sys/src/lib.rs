@@ -54,6 +54,7 @@ extern "C" {
     pub fn vpbs_last_error(ctx: *mut vpbs_ctx) -> *const c_char;
     pub fn vpbs_ctx_kernel_launches(ctx: *mut vpbs_ctx) -> u64;
     pub fn vpbs_ctx_set_host_threads(ctx: *mut vpbs_ctx, threads: c_uint) -> c_int;
+    pub fn vpbs_ctx_set_shard(ctx: *mut vpbs_ctx, index: u32, count: u32) -> c_int;
     pub fn vpbs_host_alloc(bytes: usize) -> *mut c_void;
     pub fn vpbs_host_free(p: *mut c_void);
     pub fn vpbs_fft(ctx: *mut vpbs_ctx, inout: *mut u64, log_n: u32) -> c_int;
@@ -154,6 +155,7 @@ extern "C" {
                                           stats: *mut vpbs_stats) -> c_int;
     pub fn vpbs_batch_shape(batch: *mut vpbs_batch, ncols: *mut u32, log_n: *mut u32,
                             rate_bits: *mut u32, cap_height: *mut u32, width: *mut u32) -> c_int;
+    pub fn vpbs_batch_shard(batch: *mut vpbs_batch, first_leaf: *mut u64, nleaves: *mut u64) -> c_int;
 }
 
 /// One device context (device arena + stream), reused across the 730 step proofs of a PBS.
@@ -176,6 +178,17 @@ impl Ctx {
             let msg = unsafe { CStr::from_ptr(vpbs_last_error(self.0)) };
             panic!("vpbs error {rc}: {}", msg.to_string_lossy());
         }
+    }
+    /// Copy threads of the pinned staging ring that pageable columns (plonky2's own
+    /// `Vec<PolynomialValues<F>>`) travel through; 0 leaves such copies to the CUDA driver.
+    pub fn set_host_threads(&self, threads: u32) {
+        self.check(unsafe { vpbs_ctx_set_host_threads(self.0, threads) })
+    }
+    /// Row-range sharding of one proof over `count` GPUs: resident batches created afterwards hold
+    /// leaves [index * m / count, (index + 1) * m / count); their caps carry only the own entries
+    /// (the rest zero) and are completed by an all-gather across the shards.
+    pub fn set_shard(&self, index: u32, count: u32) {
+        self.check(unsafe { vpbs_ctx_set_shard(self.0, index, count) })
     }
 }
 impl Drop for Ctx {

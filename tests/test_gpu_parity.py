@@ -495,6 +495,74 @@ def test_sharded_commit_over_nccl(V):
     assert q.get(timeout=5) is True
 
 
+def _nccl_proof_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import vfhe_b200 as V
+    from oracle import binding as B
+    c = V.Context(rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    c.set_stream(stream.cuda_stream)
+    c.set_shard(rank, world)
+    sp = V.ShardedProof(rank, world, torch.device("cuda", rank))
+    log_n, r, h = 12, 3, 4
+    m = (1 << log_n) << r
+    ok = True
+    for ncols, coeffs in [(21, False), (16, True), (3, False)]:     # 21 and 3: not multiples of the world size
+        cols = V.synthetic_columns(ncols, 1 << log_n, seed=50 + ncols)
+        handle, cap = sp.commit_from_host(c, cols, r, h, coeffs)
+        ref = B.commit(cols, r, h, coeffs)
+        ok = ok and np.array_equal(cap, ref["cap"])
+        qidx = np.random.default_rng(3).integers(0, m, size=28, dtype=np.uint64)
+        qidx[:world] = np.arange(world, dtype=np.uint64) * np.uint64(m // world)   # every rank serves some
+        own = sp.owned(qidx, m)
+        rows = np.zeros((28, ncols), np.uint64)
+        sibs = np.zeros((28, log_n + r - h, 4), np.uint64)
+        rb = V.ResidentPolynomialBatch(c, handle, cap, ncols, log_n, r, False, None)
+        rows[own] = rb.merkle_tree.get_many(qidx[own])
+        sibs[own] = np.stack([p.siblings for p in rb.merkle_tree.prove_many(qidx[own])])
+        sp.collect([rows, sibs])
+        for k, i in enumerate(qidx):
+            ok = ok and np.array_equal(rows[k], ref["leaves"][int(i)])
+            ok = ok and B.merkle_verify(rows[k], int(i), sibs[k], ref["cap"])
+        rb.close()
+    res = [None] * world
+    dist.all_gather_object(res, bool(ok))
+    if rank == 0:
+        q.put(all(res))
+    dist.destroy_process_group()
+
+
+def test_sharded_proof_over_nccl(V):
+    """One proof's resident batches sharded over all visible GPUs (needs >= 2): host columns cross
+    PCIe once and travel on by NVLink all-gather, every rank commits its row range, caps are completed
+    and query openings collected over NCCL; everything equals the oracle's unsharded commit."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 1 << (min(world, 8).bit_length() - 1)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    procs = [mpctx.Process(target=_nccl_proof_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def test_randomized_shapes_against_oracle(V, ctx, oracle):
     """SURVEY.md §4 test plan (iii): random (log_n, cols, rate_bits, cap_height, from_values/coeffs)
     with seeded inputs incl. non-canonical words, sizes bounded so the oracle stays fast."""
@@ -805,6 +873,102 @@ def test_resident_zs_commit_matches_host_pipeline(V, ctx, oracle, log_n, ncols, 
     assert np.array_equal(eager.polynomials, ref["coeffs"])
     assert np.array_equal(eager.merkle_tree.digests, ref["digests"])
     zb.close(); wb.close(); sg.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("log_n,ncols,num_routed,coeffs", [(10, 135, 80, False), (13, 20, 20, False), (6, 16, 8, True)])
+def test_sharded_resident_batches_one_proof_over_several_ranks(V, oracle, world, log_n, ncols, num_routed, coeffs):
+    """vpbs_ctx_set_shard: `world` contexts (here all on one GPU) each hold the row range of their
+    rank of the SAME commit — wires batch from host columns, Z / partial products computed and
+    committed from it — and together reproduce the unsharded commit exactly: the union of the caps,
+    opened rows, Merkle paths (verified against the full cap), LDE row blocks, downloaded shard rows
+    and digests; rows of another shard are refused; a shard count the commit cannot be split into is
+    an argument error."""
+    rng = np.random.default_rng(100 * world + log_n)
+    n, m = 1 << log_n, (1 << log_n) << 3
+    cols = rand_u64(rng, (ncols, n))
+    sigmas = rand_u64(rng, (num_routed, n))
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    betas, gammas = rand_u64(rng, 2, edge_frac=0), rand_u64(rng, 2, edge_frac=0)
+    ref = oracle.commit(cols, 3, 4, coeffs, None)
+    zref = None
+    if not coeffs:
+        per = [oracle.zs_partial_products(cols[:num_routed], sigmas, k_is, 8, betas[c], gammas[c]) for c in range(2)]
+        zcols = np.concatenate([np.stack([per[0][0], per[1][0]]), per[0][1:], per[1][1:]])
+        zref = oracle.commit(zcols, 3, 4)
+    cap_union = np.zeros((16, 4), np.uint64)
+    zcap_union = np.zeros((16, 4), np.uint64)
+    sub_dig = 2 * (m >> 4) - 2
+    for rank in range(world):
+        with V.Context(0) as c:
+            c.set_shard(rank, world)
+            rb = V.commit_resident(cols, 3, False, 4, coeffs, ctx=c)
+            first, nl = rb.shard
+            assert (first, nl) == (rank * m // world, m // world)
+            cap = rb.merkle_tree.cap
+            own = slice(rank * 16 // world, (rank + 1) * 16 // world)
+            assert np.array_equal(cap[own], ref["cap"][own])
+            mask = np.ones(16, bool); mask[own] = False
+            assert not cap[mask].any()
+            cap_union[own] = cap[own]
+            idx = rng.integers(first, first + nl, size=12, dtype=np.uint64)
+            idx[0], idx[1] = first, first + nl - 1
+            rows = rb.merkle_tree.get_many(idx)
+            proofs = rb.merkle_tree.prove_many(idx)
+            for k, i in enumerate(idx):
+                i = int(i)
+                assert np.array_equal(rows[k], ref["leaves"][i])
+                assert np.array_equal(proofs[k].siblings, oracle.merkle_prove(ref["digests"], m, 4, i))
+                assert oracle.merkle_verify(rows[k], i, proofs[k].siblings, ref["cap"])
+            other = (first + nl) % m
+            with pytest.raises(ValueError):
+                rb.merkle_tree.get_many(np.array([other], np.uint64))
+            with pytest.raises(ValueError):
+                rb.merkle_tree.prove_many(np.array([other], np.uint64))
+            # natural rows i with bitrev(i) inside the shard: i = bitrev(first) + j * world
+            i0 = V.reverse_bits(first, log_n + 3)
+            got = rb.get_lde_rows(i0, world, 9)
+            want = np.array([ref["leaves"][V.reverse_bits(i0 + j * world, log_n + 3)][:ncols] for j in range(9)], np.uint64)
+            assert np.array_equal(got, want)
+            if world > 1:
+                with pytest.raises(ValueError):
+                    rb.get_lde_rows(i0, 1, 2)
+            eager = rb.download()
+            assert np.array_equal(eager.merkle_tree.leaves, ref["leaves"][first:first + nl])
+            assert np.array_equal(eager.merkle_tree.digests,
+                                  ref["digests"][own.start * sub_dig:own.stop * sub_dig])
+            if not coeffs:
+                assert np.array_equal(eager.polynomials, ref["coeffs"])
+                sg = V.Sigmas(sigmas, k_is, c)
+                zb = V.commit_zs_partial_products(rb, sg, betas, gammas, 8, 3, 4)
+                assert zb.shard == (first, nl)
+                zcap_union[own] = zb.merkle_tree.cap[own]
+                zrows = zb.merkle_tree.get_many(idx)
+                for k, i in enumerate(idx):
+                    assert np.array_equal(zrows[k], zref["leaves"][int(i)])
+                opens = rb.eval_ext2(np.array([[3, 5]], np.uint64))   # coefficient consumers are unaffected
+                c.set_shard(0, 1)
+                full = V.commit_resident(cols, 3, False, 4, coeffs, ctx=c)
+                assert np.array_equal(opens, full.eval_ext2(np.array([[3, 5]], np.uint64)))
+                full.close(); zb.close(); sg.close()
+            rb.close()
+    assert np.array_equal(cap_union, ref["cap"])
+    if zref is not None:
+        assert np.array_equal(zcap_union, zref["cap"])
+
+
+def test_shard_count_the_commit_cannot_be_split_into(V):
+    with V.Context(0) as c:
+        with pytest.raises(ValueError):
+            c.set_shard(0, 3)
+        with pytest.raises(ValueError):
+            c.set_shard(2, 2)
+        c.set_shard(1, 16)          # more shards than LDE blocks (2^rate_bits = 8)
+        with pytest.raises(ValueError):
+            V.commit_resident(np.ones((5, 64), np.uint64), 3, False, 4, ctx=c)
+        c.set_shard(1, 4)           # more shards than cap subtrees (cap_height = 1)
+        with pytest.raises(ValueError):
+            V.commit_resident(np.ones((5, 64), np.uint64), 3, False, 1, ctx=c)
 
 
 @pytest.mark.parametrize("log_n,ncols,rate_bits,salted", [(8, 9, 3, False), (10, 135, 3, False), (5, 6, 2, True), (0, 3, 3, False)])

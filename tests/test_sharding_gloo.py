@@ -80,3 +80,49 @@ def test_shard_plan_arithmetic():
             V.shard_plan(16, 3, 4, bad["rank"], bad["world"])
     with pytest.raises(ValueError):
         V.shard_plan(16, 3, 1, 0, 4)     # more shards than cap subtrees
+
+
+def _proof_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vfhe_b200 as V
+    sp = V.ShardedProof(rank, world)                      # CPU tensors: gloo
+    rng = np.random.default_rng(5)
+    ncap, m, width, layers = 16, 1 << 10, 7, 6
+    full_cap = rng.integers(0, 2**64, size=(ncap, 4), dtype=np.uint64)
+    own = ncap // world
+    cap = np.zeros_like(full_cap)
+    cap[rank * own:(rank + 1) * own] = full_cap[rank * own:(rank + 1) * own]
+    ok = np.array_equal(sp.complete_cap(cap), full_cap)
+    qidx = rng.integers(0, m, size=28, dtype=np.uint64)
+    all_rows = rng.integers(0, 2**64, size=(28, width), dtype=np.uint64)
+    all_sibs = rng.integers(0, 2**64, size=(28, layers, 4), dtype=np.uint64)
+    mine = sp.owned(qidx, m)
+    ok = ok and np.array_equal(mine, (qidx // np.uint64(m // world)) == rank)
+    rows, sibs = np.zeros_like(all_rows), np.zeros_like(all_sibs)
+    rows[mine], sibs[mine] = all_rows[mine], all_sibs[mine]
+    sp.collect([rows, sibs])
+    ok = ok and np.array_equal(rows, all_rows) and np.array_equal(sibs, all_sibs)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bool(ok))
+    if rank == 0:
+        q.put(all(gathered))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_proof_host_glue(world):
+    """ShardedProof over gloo: caps completed from the per-rank entries, query openings collected
+    from their owners — the host side of a step proof whose batches are sharded by row range."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_proof_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

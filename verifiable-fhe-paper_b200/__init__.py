@@ -15,4 +15,4 @@ from .plonky2_api import (  # noqa: F401
     fri_proof_of_work, hash_or_noop, ifft, lde_values,
     log2_strict, poseidon, reverse_bits, synthetic_columns, two_to_one,
     verify_merkle_proof_to_cap)
-from .sharding import ShardPlan, commit_sharded, gather_cap, shard_plan  # noqa: F401,E402
+from .sharding import ShardPlan, ShardedProof, commit_sharded, gather_cap, shard_plan  # noqa: F401,E402

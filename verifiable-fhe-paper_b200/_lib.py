@@ -48,6 +48,7 @@ SIGNATURES = {
     "vpbs_last_error": (_c.c_char_p, [_ctx]),
     "vpbs_ctx_kernel_launches": (_c.c_uint64, [_ctx]),
     "vpbs_ctx_set_host_threads": (_c.c_int, [_ctx, _c.c_uint]),
+    "vpbs_ctx_set_shard": (_c.c_int, [_ctx, _c.c_uint32, _c.c_uint32]),
     "vpbs_host_alloc": (_c.c_void_p, [_c.c_size_t]),
     "vpbs_host_free": (None, [_c.c_void_p]),
     "vpbs_fft": (_c.c_int, [_ctx, u64p, _c.c_uint32]),
@@ -108,6 +109,7 @@ SIGNATURES = {
                                                   _c.c_uint32, _c.c_uint32, _c.c_uint32, u64p,
                                                   _c.POINTER(_c.c_void_p), _c.POINTER(VpbsStats)]),
     "vpbs_batch_shape": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint32)] * 5),
+    "vpbs_batch_shard": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint64)] * 2),
 }
 
 _lib = None

@@ -182,11 +182,11 @@ finish_rows(const u64* __restrict__ quot, const u64* __restrict__ rowscan, unsig
 // get_lde_values(first + r * step, 1) for a block of LDE indices, salt columns dropped.
 __global__ void __launch_bounds__(128)
 gather_lde_rows(const u64* __restrict__ leaves, u32 width, u32 ncols, unsigned log_m, u64 first,
-                u64 step, u64 count, u64* __restrict__ rows_out) {
+                u64 step, u64 count, u64 leaf_off, u64* __restrict__ rows_out) {
   const u64 r = blockIdx.x;
   if (r >= count) return;
   const u64 idx = first + r * step;
-  const u64 leaf = log_m ? (__brevll(idx) >> (64 - log_m)) : 0;
+  const u64 leaf = (log_m ? (__brevll(idx) >> (64 - log_m)) : 0) - leaf_off;  // leaf_off: first leaf of a shard
   const u64* src = leaves + leaf * width;
   for (u32 c = threadIdx.x; c < ncols; c += blockDim.x) rows_out[r * ncols + c] = src[c];
 }

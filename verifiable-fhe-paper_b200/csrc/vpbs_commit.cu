@@ -86,6 +86,9 @@ struct vpbs_ctx {
   // copy threads (host_stage.h); 0 threads: leave such copies to the driver's own staging.
   hoststage::Ring ring;
   unsigned host_threads = 4;
+  // Row-range sharding of the resident batches this context creates (vpbs_ctx_set_shard): batch
+  // leaves / digests cover leaves [index * m / count, (index + 1) * m / count) only.
+  u32 shard_index = 0, shard_count = 1;
 };
 
 // A commit kept in HBM (vpbs_batch_*): owns its device buffers, reads go through the context.
@@ -95,6 +98,11 @@ struct vpbs_batch {
   bool coeff_inputs = false;
   u64 *coeffs = nullptr, *leaves = nullptr, *digests = nullptr, *cap = nullptr;
   size_t coeffs_bytes = 0, leaves_bytes = 0, digests_bytes = 0, cap_bytes = 0;
+  // rows held: leaves [first_leaf, first_leaf + nleaves) (all m of them unless the context shards);
+  // `cap` always has all 2^cap_height entries, the ones of other shards zero
+  u64 first_leaf = 0, nleaves = 0;
+  u64* own_roots() const { return cap + 4 * (first_leaf >> (log_n + rate_bits - cap_height)); }
+  bool sharded() const { return nleaves != (1ULL << (log_n + rate_bits)); }
 };
 
 // Sigma polynomials' values + coset shifts of one circuit, resident in HBM (vpbs_sigmas_upload).
@@ -659,6 +667,12 @@ void fill_stats(vpbs_stats* st, Timer& tm, uint64_t launches) {
 
 bool usable(vpbs_ctx* ctx) { return ctx != nullptr; }
 
+u64 reverse_bits64(u64 x, unsigned bits) {
+  u64 r = 0;
+  for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1ULL) << (bits - 1 - i);
+  return r;
+}
+
 // The persistent NTT passes use two tile buffers (64-68 KB of dynamic shared memory): opt in, on
 // the current device, for every instantiation run_transform launches.
 cudaError_t allow_large_smem() {
@@ -832,6 +846,15 @@ int vpbs_ctx_set_host_threads(vpbs_ctx* ctx, unsigned threads) {
   if (!usable(ctx)) return VPBS_ERR_STATE;
   if (threads > 64) return fail(ctx, VPBS_ERR_ARG, "host_threads > 64");
   ctx->host_threads = threads;
+  return VPBS_OK;
+}
+
+int vpbs_ctx_set_shard(vpbs_ctx* ctx, uint32_t index, uint32_t count) {
+  if (!usable(ctx)) return VPBS_ERR_STATE;
+  if (count == 0 || (count & (count - 1)) || index >= count)
+    return fail(ctx, VPBS_ERR_ARG, "shard count must be a power of two and index < count");
+  ctx->shard_index = index;
+  ctx->shard_count = count;
   return VPBS_OK;
 }
 
@@ -2030,8 +2053,8 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
   Timer tm{ctx, stats != nullptr};
   if (nup) tm.overlap = &ovl;
   // coefficients always end up in the batch (from_coeffs: a device copy of the inputs)
-  rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, 0, m,
-                   b->coeffs, b->leaves, b->digests, b->cap, &tm);
+  rc = commit_core(ctx, din, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, dsa, b->first_leaf,
+                   b->nleaves, b->coeffs, b->leaves, b->digests, b->own_roots(), &tm);
   const cudaError_t ue = upload ? upload->join() : cudaSuccess;
   if (rc == VPBS_OK && ue != cudaSuccess)
     rc = fail(ctx, VPBS_ERR_CUDA, std::string("staged upload: ") + cudaGetErrorString(ue));
@@ -2068,15 +2091,27 @@ int batch_alloc(vpbs_ctx* ctx, u32 ncols, u32 log_n, u32 rate_bits, u32 cap_heig
                 bool coeff_inputs, vpbs_batch** out) {
   const u64 n = 1ULL << log_n, m = n << rate_bits;
   const u32 width = ncols + (salted ? VPBS_SALT_SIZE : 0);
-  const u64 ncap = 1ULL << cap_height, ndig = 2 * (m - ncap);
+  const u64 ncap = 1ULL << cap_height;
+  // the shard of this context: whole n-row LDE blocks covering whole cap subtrees
+  u64 first = 0, nl = m;
+  if (ctx->shard_count > 1) {
+    nl = m / ctx->shard_count;
+    if (nl < n || nl < (m >> cap_height) || nl * ctx->shard_count != m)
+      return fail(ctx, VPBS_ERR_ARG,
+                  "shard count too large for this commit (a shard is whole LDE blocks and whole cap subtrees)");
+    first = nl * ctx->shard_index;
+  }
+  const u64 nroots = nl >> (log_n + rate_bits - cap_height), ndig = 2 * (nl - nroots);
   vpbs_batch* b = new (std::nothrow) vpbs_batch();
   if (!b) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
   b->ctx = ctx;
   b->ncols = ncols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
   b->width = width;
   b->coeff_inputs = coeff_inputs;
+  b->first_leaf = first;
+  b->nleaves = nl;
   b->coeffs_bytes = (size_t)ncols * n * 8;
-  b->leaves_bytes = (size_t)m * width * 8;
+  b->leaves_bytes = (size_t)nl * width * 8;
   b->digests_bytes = ndig ? ndig * 32 : 32;
   b->cap_bytes = ncap * 32;
   ctx->batches.insert(b);
@@ -2087,6 +2122,10 @@ int batch_alloc(vpbs_ctx* ctx, u32 ncols, u32 log_n, u32 rate_bits, u32 cap_heig
   if (e != cudaSuccess) {
     vpbs_batch_destroy(b);
     return fail(ctx, VPBS_ERR_OOM, std::string("batch allocation: ") + cudaGetErrorString(e));
+  }
+  if (b->sharded() && (e = cudaMemsetAsync(b->cap, 0, b->cap_bytes, ctx->stream)) != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, VPBS_ERR_CUDA, std::string("batch allocation: ") + cudaGetErrorString(e));
   }
   *out = b;
   return VPBS_OK;
@@ -2279,8 +2318,8 @@ int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas,
   vpbs_batch* b = nullptr;
   if ((rc = batch_alloc(ctx, ncols_out, log_n, rate_bits, cap_height, false, false, &b))) return rc;
   Timer tm{ctx, stats != nullptr};
-  rc = commit_core(ctx, dout, ncols_out, log_n, rate_bits, cap_height, 0, nullptr, 0, n << rate_bits,
-                   b->coeffs, b->leaves, b->digests, b->cap, &tm);
+  rc = commit_core(ctx, dout, ncols_out, log_n, rate_bits, cap_height, 0, nullptr, b->first_leaf,
+                   b->nleaves, b->coeffs, b->leaves, b->digests, b->own_roots(), &tm);
   if (rc) {
     vpbs_batch_destroy(b);
     return rc;
@@ -2316,8 +2355,8 @@ int vpbs_batch_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols,
     return rc;
   const uint64_t l0 = ctx->launches;
   Timer tm{ctx, stats != nullptr};
-  rc = commit_core(ctx, d_cols, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, nullptr, 0,
-                   1ULL << (log_n + rate_bits), b->coeffs, b->leaves, b->digests, b->cap, &tm);
+  rc = commit_core(ctx, d_cols, ncols, log_n, rate_bits, cap_height, inputs_are_coeffs, nullptr,
+                   b->first_leaf, b->nleaves, b->coeffs, b->leaves, b->digests, b->own_roots(), &tm);
   if (rc) {
     vpbs_batch_destroy(b);
     return rc;
@@ -2349,6 +2388,12 @@ int vpbs_batch_get_lde_rows(vpbs_batch* b, uint64_t first_index, uint64_t step, 
   const u64 m = 1ULL << log_m;
   if (step == 0 || first_index >= m || (count - 1) > (m - 1 - first_index) / step)
     return fail(ctx, VPBS_ERR_ARG, "LDE index range out of bounds");
+  if (b->sharded())  // every requested row must live in this shard
+    for (u64 r = 0; r < count; r++) {
+      const u64 leaf = reverse_bits64(first_index + r * step, log_m);
+      if (leaf < b->first_leaf || leaf >= b->first_leaf + b->nleaves)
+        return fail(ctx, VPBS_ERR_ARG, "LDE row outside this shard");
+    }
   u64* d_rows = nullptr;
   const size_t bytes = count * (size_t)b->ncols * 8;
   // pulled in pieces of at most 64 Ki rows through the context's staging buffer
@@ -2359,7 +2404,7 @@ int vpbs_batch_get_lde_rows(vpbs_batch* b, uint64_t first_index, uint64_t step, 
   for (u64 off = 0; off < count; off += piece) {
     const u64 cnt = count - off < piece ? count - off : piece;
     perm::gather_lde_rows<<<(unsigned)cnt, 128, 0, ctx->stream>>>(
-        b->leaves, b->width, b->ncols, log_m, first_index + off * step, step, cnt, d_rows);
+        b->leaves, b->width, b->ncols, log_m, first_index + off * step, step, cnt, b->first_leaf, d_rows);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(rows_out + off * b->ncols, d_rows, (size_t)cnt * b->ncols * 8,
@@ -2380,14 +2425,32 @@ int vpbs_batch_shape(vpbs_batch* b, uint32_t* ncols, uint32_t* log_n, uint32_t* 
   return VPBS_OK;
 }
 
+int vpbs_batch_shard(vpbs_batch* b, uint64_t* first_leaf, uint64_t* nleaves) {
+  if (!b) return VPBS_ERR_STATE;
+  if (first_leaf) *first_leaf = b->first_leaf;
+  if (nleaves) *nleaves = b->nleaves;
+  return VPBS_OK;
+}
+
 static int batch_indices(vpbs_batch* b, const uint64_t* idx, uint64_t count, u64** d_idx) {
   vpbs_ctx* ctx = b->ctx;
   const u64 m = 1ULL << (b->log_n + b->rate_bits);
-  for (uint64_t i = 0; i < count; i++)
+  for (uint64_t i = 0; i < count; i++) {
     if (idx[i] >= m) return fail(ctx, VPBS_ERR_ARG, "leaf index out of range");
+    if (idx[i] < b->first_leaf || idx[i] >= b->first_leaf + b->nleaves)
+      return fail(ctx, VPBS_ERR_ARG, "leaf index outside this shard");
+  }
   int rc;
   if ((rc = arena_get(ctx, "idx", count * 8, (void**)d_idx))) return rc;
-  CU(ctx, cudaMemcpyAsync(*d_idx, idx, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (!b->sharded()) {
+    CU(ctx, cudaMemcpyAsync(*d_idx, idx, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return VPBS_OK;
+  }
+  // the kernels index the shard's own buffers: leaf - first_leaf (the shard starts at a subtree boundary)
+  std::vector<u64> local(idx, idx + count);
+  for (u64& v : local) v -= b->first_leaf;
+  CU(ctx, cudaMemcpyAsync(*d_idx, local.data(), count * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));  // `local` dies with this frame
   return VPBS_OK;
 }
 
@@ -2441,8 +2504,8 @@ int vpbs_batch_download(vpbs_batch* b, uint64_t* const* coeffs_out, uint64_t* le
   vpbs_ctx* ctx = b->ctx;
   int rc = bind(ctx);
   if (rc) return rc;
-  const u64 n = 1ULL << b->log_n, m = n << b->rate_bits;
-  const u64 ndig = 2 * (m - (1ULL << b->cap_height));
+  const u64 n = 1ULL << b->log_n, m = b->nleaves;  // a sharded batch downloads its own rows / digests
+  const u64 ndig = 2 * (m - (m >> (b->log_n + b->rate_bits - b->cap_height)));
   if (coeffs_out)
     for (u32 c = 0; c < b->ncols; c++)
       if (coeffs_out[c])

@@ -120,6 +120,12 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._L.vpbs_ctx_kernel_launches(self._h))
 
+    def set_shard(self, index: int, count: int):
+        """Row-range sharding of one proof over `count` GPUs (vpbs_ctx_set_shard): resident batches
+        created afterwards hold leaves [index * m / count, (index + 1) * m / count); their caps carry
+        only the own entries (others zero) until gathered across the shards."""
+        self.check(self._L.vpbs_ctx_set_shard(self._h, int(index), int(count)))
+
     def set_host_threads(self, threads: int):
         """Copy threads of the pinned staging ring that pageable host columns travel through
         (vpbs_ctx_set_host_threads; 0: leave such copies to the driver)."""
@@ -566,6 +572,14 @@ class ResidentPolynomialBatch:
         except Exception:
             pass
 
+    @property
+    def shard(self):
+        """(first_leaf, nleaves): the rows this batch holds — (0, m) unless its context shards
+        (Context.set_shard)."""
+        first, nl = ctypes.c_uint64(), ctypes.c_uint64()
+        self.ctx.check(self.ctx.lib.vpbs_batch_shard(self.handle, ctypes.byref(first), ctypes.byref(nl)))
+        return int(first.value), int(nl.value)
+
     def get_lde_values(self, index: int, step: int = 1) -> np.ndarray:
         k = reverse_bits(index * step, self.degree_log + self.rate_bits)
         row = self.merkle_tree.get(k)
@@ -587,13 +601,15 @@ class ResidentPolynomialBatch:
         return out
 
     def download(self) -> "PolynomialBatch":
-        """Materialise the eager form (polynomials, leaves, digests) on the host."""
-        n, m = 1 << self.degree_log, 1 << (self.degree_log + self.rate_bits)
+        """Materialise the eager form (polynomials, leaves, digests) on the host; of a sharded batch:
+        all polynomials, the shard's own rows and the digests of its own cap subtrees."""
+        n, m_all = 1 << self.degree_log, 1 << (self.degree_log + self.rate_bits)
         cap = self.merkle_tree.cap
+        m = self.shard[1]
         coeffs = np.empty((self.ncols, n), np.uint64)
         cop = (u64p * self.ncols)(*[_ptr(coeffs[c]) for c in range(self.ncols)])
         leaves = np.empty((m, self.merkle_tree.width), np.uint64)
-        digests = np.empty((2 * (m - cap.shape[0]), 4), np.uint64)
+        digests = np.empty((2 * (m - cap.shape[0] * m // m_all), 4), np.uint64)
         self.ctx.check(self.ctx.lib.vpbs_batch_download(self.handle, cop, _ptr(leaves),
                                                         _ptr(digests) if digests.size else None))
         return PolynomialBatch(coeffs, MerkleTree(leaves, digests, cap), self.degree_log,

@@ -61,6 +61,107 @@ def gather_cap(local_roots, world: int):
     return out
 
 
+class ShardedProof:
+    """Host-side glue for ONE proof whose resident batches are sharded by row range over the ranks
+    of a torch.distributed group (Context.set_shard; NCCL when `device` is a CUDA device, gloo on
+    the CPU): completes the caps the shards return, and collects the query openings each rank serves
+    from its own rows.  The exchanged data is 32 bytes per cap entry per commit and the opened rows +
+    Merkle paths (a few tens of KB per proof)."""
+
+    def __init__(self, rank: int, world: int, device=None):
+        import torch
+        self.rank, self.world = rank, world
+        self.device = device if device is not None else torch.device("cpu")
+        self._buf = {}
+
+    def _tensor(self, key, numel):
+        import torch
+        t = self._buf.get(key)
+        if t is None or t.numel() != numel:
+            t = self._buf[key] = torch.empty(numel, dtype=torch.int64, device=self.device)
+        return t
+
+    def complete_cap(self, cap):
+        """cap: (ncap, 4) uint64 numpy array as a sharded commit returns it (own entries filled, the
+        rest zero), completed IN PLACE with the other shards' entries (all-gather).  ncap must be a
+        multiple of the world size (a shard is whole cap subtrees)."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return cap
+        ncap = cap.shape[0]
+        if ncap % self.world:
+            raise ValueError("cap entries (%d) must be a multiple of the world size" % ncap)
+        own = ncap // self.world
+        mine = torch.from_numpy(cap[self.rank * own:(self.rank + 1) * own].view(np.int64).reshape(-1))
+        full = self._tensor(("cap", ncap), ncap * 4)
+        dist.all_gather_into_tensor(full, mine.to(self.device, non_blocking=False))
+        cap[:] = full.cpu().numpy().view(np.uint64).reshape(ncap, 4)
+        return cap
+
+    def commit_from_host(self, ctx, host_cols, rate_bits: int, cap_height: int,
+                         inputs_are_coeffs: bool = False):
+        """PolynomialBatch::from_values / from_coeffs of one proof sharded over the ranks, from host
+        columns every rank can read (host_cols: (ncols, n) uint64, ideally page-locked).  Every shard
+        needs ALL columns, but they cross PCIe only once: rank r uploads columns
+        [r * C' / world, (r + 1) * C' / world) and the ranks exchange them GPU to GPU (NCCL
+        all-gather over NVLink), then each commits its own row range from device memory
+        (vpbs_batch_commit_dev under Context.set_shard) and the cap is completed by the all-gather of
+        the subtree roots.  Returns (batch handle, full cap).  The context must have been switched to
+        torch's current stream (Context.set_stream) so that the copies, the collective and the
+        kernels are ordered."""
+        import ctypes
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        ncols, n = host_cols.shape
+        log_n = n.bit_length() - 1
+        per = -(-ncols // self.world)                       # columns per rank, last ranks may be short
+        d_all = self._tensor(("cols", per * self.world, n), per * self.world * n).view(per * self.world, n)
+        c0, c1 = min(self.rank * per, ncols), min((self.rank + 1) * per, ncols)
+        mine = d_all[self.rank * per:(self.rank + 1) * per]
+        if c1 > c0:
+            mine[:c1 - c0].copy_(torch.from_numpy(host_cols[c0:c1].view(np.int64)), non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(d_all.view(-1), mine.reshape(-1))
+        cap = np.empty((1 << cap_height, 4), np.uint64)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.vpbs_batch_commit_dev(ctx.handle, d_all.data_ptr(), ncols, log_n, rate_bits,
+                                                cap_height, int(inputs_are_coeffs),
+                                                cap.ctypes.data_as(_lib.u64p), ctypes.byref(h), None))
+        return h, self.complete_cap(cap)
+
+    def owned(self, leaf_indices, nleaves_total: int):
+        """Boolean mask of the leaf indices this rank's shard holds."""
+        import numpy as np
+        per = nleaves_total // self.world
+        idx = np.asarray(leaf_indices, dtype=np.uint64)
+        return (idx // np.uint64(per)) == np.uint64(self.rank)
+
+    def collect(self, arrays):
+        """arrays: uint64 numpy arrays in which every rank has filled the entries it owns and left
+        the others ZERO.  Sums them across the ranks in place (all-reduce; integer addition of a
+        value and zeros is exact), so that afterwards every rank holds every entry."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return arrays
+        total = sum(a.size for a in arrays)
+        t = self._tensor(("collect", total), total)
+        flat = np.concatenate([a.reshape(-1).view(np.int64) for a in arrays])
+        t.copy_(torch.from_numpy(flat))
+        dist.all_reduce(t)
+        out = t.cpu().numpy().view(np.uint64)
+        off = 0
+        for a in arrays:
+            a[...] = out[off:off + a.size].reshape(a.shape)
+            off += a.size
+        return arrays
+
+
 def commit_sharded(ctx, d_cols, ncols: int, log_n: int, rate_bits: int, cap_height: int,
                    inputs_are_coeffs: bool, rank: int, world: int, want_stats: bool = False):
     """One rank's part of a sharded commit on device tensors.  d_cols: torch int64 (ncols, n) on this
