@@ -1133,6 +1133,9 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     sibs = [np.empty((28, nlayers, 4), np.uint64) for _ in widths]
     fri_batches = [[(o, j) for o, c in enumerate(widths) for j in range(c)], [(2, 0), (2, 1)]]
     stats = {"fri_layers": 0}
+    open_ptrs = (u64p * 4)(*[a.ctypes.data_as(u64p) for a in opens])
+    row_ptrs = (u64p * 4)(*[a.ctypes.data_as(u64p) for a in rows])
+    sib_ptrs = (u64p * 4)(*[a.ctypes.data_as(u64p) for a in sibs])
 
     phase = {}
 
@@ -1171,8 +1174,9 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         gz = np.array([int(zeta[0]) * g_n % P_GL, int(zeta[1]) * g_n % P_GL], np.uint64)
         pts = np.stack([zeta, gz])
         allh = [cs["h"]] + hs
-        for k in range(4):  # OpeningSet::new
-            ctx.check(lib.vpbs_batch_eval_ext2(allh[k], pts.ctypes.data_as(u64p), 2, opens[k].ctypes.data_as(u64p)))
+        # OpeningSet::new: all four oracles at zeta / g zeta in one round trip
+        hp = (ctypes.c_void_p * 4)(*allh)
+        ctx.check(lib.vpbs_batches_eval_ext2(hp, 4, pts.ctypes.data_as(u64p), 2, open_ptrs))
         t = lap("openings", t)
         alpha = challenge(opens[3][0, :4].copy(), 3, 2)
         obs = [_Resident(ctx, h, log_n) for h in allh]
@@ -1191,23 +1195,23 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         w = V.fri_proof_of_work(pow_state, 5, 16, ctx=ctx)
         t = lap("pow", t)
         qidx = np.random.default_rng(int(w or 0) + 1).integers(0, m, size=28, dtype=np.uint64)
-        if not sharded_now[0]:
-            for b in range(4):
-                ctx.check(lib.vpbs_batch_get_leaves(allh[b], qidx.ctypes.data_as(u64p), 28, rows[b].ctypes.data_as(u64p)))
-                ctx.check(lib.vpbs_batch_prove(allh[b], qidx.ctypes.data_as(u64p), 28, sibs[b].ctypes.data_as(u64p)))
+        if not sharded_now[0]:  # initial_trees_proof of the 28 query rounds: one round trip for all oracles
+            ctx.check(lib.vpbs_batches_open(hp, 4, qidx.ctypes.data_as(u64p), 28, row_ptrs, sib_ptrs))
         else:  # every rank opens the rows its shard holds; one all-reduce hands all of them to everyone
             own = sp.owned(qidx, m)
             q_own = np.ascontiguousarray(qidx[own])
             for b in range(4):
                 rows[b][:] = 0
                 sibs[b][:] = 0
-                if len(q_own):
-                    r = np.empty((len(q_own), widths[b]), np.uint64)
-                    sb = np.empty((len(q_own), nlayers, 4), np.uint64)
-                    ctx.check(lib.vpbs_batch_get_leaves(allh[b], q_own.ctypes.data_as(u64p), len(q_own), r.ctypes.data_as(u64p)))
-                    ctx.check(lib.vpbs_batch_prove(allh[b], q_own.ctypes.data_as(u64p), len(q_own), sb.ctypes.data_as(u64p)))
-                    rows[b][own] = r
-                    sibs[b][own] = sb
+            if len(q_own):
+                r = [np.empty((len(q_own), widths[b]), np.uint64) for b in range(4)]
+                sb = [np.empty((len(q_own), nlayers, 4), np.uint64) for b in range(4)]
+                ctx.check(lib.vpbs_batches_open(hp, 4, q_own.ctypes.data_as(u64p), len(q_own),
+                                                (u64p * 4)(*[a.ctypes.data_as(u64p) for a in r]),
+                                                (u64p * 4)(*[a.ctypes.data_as(u64p) for a in sb])))
+                for b in range(4):
+                    rows[b][own] = r[b]
+                    sibs[b][own] = sb[b]
             sp.collect(rows + sibs)
         qi = qidx.copy()
         for layer in range(k):

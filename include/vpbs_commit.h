@@ -338,6 +338,15 @@ int vpbs_batch_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols,
  * instead of receiving the whole m x width matrix at commit time. */
 int vpbs_batch_get_lde_rows(vpbs_batch* batch, uint64_t first_index, uint64_t step, uint64_t count,
                             uint64_t* rows_out);
+/* [P2] plonk/proof.rs OpeningSet::new in one round trip: outs[k] = (npoints x ncols_k x 2) openings
+ * of batch k, all batches at the same points (one upload, one kernel per batch, one wait). */
+int vpbs_batches_eval_ext2(vpbs_batch* const* batches, uint32_t nbatches, const uint64_t* points,
+                           uint32_t npoints, uint64_t* const* outs);
+/* [P2] fri/prover.rs fri_prover_query_round (initial_trees_proof) in one round trip: for every batch
+ * the leaf rows (count x width_k) and Merkle paths (count x (log2 m - cap_height) x 4) at the same
+ * leaf indices.  The batches must share the tree shape (and the shard, if their context shards). */
+int vpbs_batches_open(vpbs_batch* const* batches, uint32_t nbatches, const uint64_t* leaf_indices,
+                      uint64_t count, uint64_t* const* rows_out, uint64_t* const* siblings_out);
 /* Shape of the batch: m = 2^(log_n + rate_bits) leaves of `width` elements. */
 int vpbs_batch_shape(vpbs_batch* batch, uint32_t* ncols, uint32_t* log_n, uint32_t* rate_bits,
                      uint32_t* cap_height, uint32_t* width);

@@ -321,6 +321,47 @@ class ResidentBatch {
   vpbs_batch* h_ = nullptr;
 };
 
+// plonk/proof.rs OpeningSet::new over all FRI oracles in one round trip: per batch ncols x (re, im)
+inline std::vector<std::vector<F>> open_all_at_point(const std::vector<const ResidentBatch*>& batches,
+                                                     const F (&point)[2]) {
+  std::vector<vpbs_batch*> hs;
+  std::vector<std::vector<F>> outs;
+  std::vector<F*> ptrs;
+  for (const ResidentBatch* b : batches) {
+    hs.push_back(b->handle());
+    outs.emplace_back(2 * b->ncols);
+  }
+  for (auto& o : outs) ptrs.push_back(o.data());
+  batches.at(0)->context().check(vpbs_batches_eval_ext2(hs.data(), (uint32_t)hs.size(), point, 1, ptrs.data()));
+  return outs;
+}
+// fri/prover.rs fri_prover_query_round (initial_trees_proof): (row, Merkle path) of every oracle at
+// one leaf index, one round trip for all of them
+inline std::vector<std::pair<std::vector<F>, MerkleProof>> open_all_at_leaf(
+    const std::vector<const ResidentBatch*>& batches, std::size_t leaf_index) {
+  const ResidentBatch* b0 = batches.at(0);
+  const std::size_t layers = b0->degree_log + b0->rate_bits - log2_strict(b0->cap.size());
+  std::vector<vpbs_batch*> hs;
+  std::vector<std::pair<std::vector<F>, MerkleProof>> out;
+  for (const ResidentBatch* b : batches) {
+    hs.push_back(b->handle());
+    out.emplace_back(std::vector<F>(b->width), MerkleProof{std::vector<HashOut>(layers)});
+  }
+  std::vector<F*> rows, sibs;
+  for (auto& o : out) {
+    rows.push_back(o.first.data());
+    sibs.push_back(layers ? o.second.siblings[0].elements : nullptr);
+  }
+  if (!layers) {  // all-cap trees have no paths: rows only
+    uint64_t idx = leaf_index;
+    for (std::size_t k = 0; k < hs.size(); k++) b0->context().check(vpbs_batch_get_leaves(hs[k], &idx, 1, rows[k]));
+    return out;
+  }
+  uint64_t idx = leaf_index;
+  b0->context().check(vpbs_batches_open(hs.data(), (uint32_t)hs.size(), &idx, 1, rows.data(), sibs.data()));
+  return out;
+}
+
 // ---- plonk/prover.rs, step 4-5: Z and partial products of the permutation argument ----------------
 // The sigma polynomials' values and the coset shifts k_is of one circuit, resident in HBM.
 class Sigmas {

@@ -156,6 +156,10 @@ extern "C" {
     pub fn vpbs_batch_shape(batch: *mut vpbs_batch, ncols: *mut u32, log_n: *mut u32,
                             rate_bits: *mut u32, cap_height: *mut u32, width: *mut u32) -> c_int;
     pub fn vpbs_batch_shard(batch: *mut vpbs_batch, first_leaf: *mut u64, nleaves: *mut u64) -> c_int;
+    pub fn vpbs_batches_eval_ext2(batches: *const *mut vpbs_batch, nbatches: u32, points: *const u64,
+                                  npoints: u32, outs: *const *mut u64) -> c_int;
+    pub fn vpbs_batches_open(batches: *const *mut vpbs_batch, nbatches: u32, leaf_indices: *const u64,
+                             count: u64, rows_out: *const *mut u64, siblings_out: *const *mut u64) -> c_int;
 }
 
 /// One device context (device arena + stream), reused across the 730 step proofs of a PBS.
@@ -321,6 +325,30 @@ impl ResidentBatch {
                                                 out.as_mut_ptr()) });
         out
     }
+}
+
+/// OpeningSet::new over all FRI oracles in one round trip: per batch (npoints x ncols x 2).
+pub fn eval_ext2_all(ctx: &Ctx, batches: &[&ResidentBatch], points: &[[u64; 2]]) -> Vec<Vec<u64>> {
+    let hs: Vec<*mut vpbs_batch> = batches.iter().map(|b| b.h).collect();
+    let mut outs: Vec<Vec<u64>> = batches.iter().map(|b| vec![0u64; points.len() * b.ncols * 2]).collect();
+    let ptrs: Vec<*mut u64> = outs.iter_mut().map(|o| o.as_mut_ptr()).collect();
+    ctx.check(unsafe { vpbs_batches_eval_ext2(hs.as_ptr(), hs.len() as u32, points.as_ptr() as *const u64,
+                                              points.len() as u32, ptrs.as_ptr()) });
+    outs
+}
+/// fri_prover_query_round's initial_trees_proof over all oracles in one round trip: per batch
+/// (rows, siblings) at the same leaf indices.
+pub fn open_all(ctx: &Ctx, batches: &[&ResidentBatch], leaf_indices: &[u64]) -> Vec<(Vec<u64>, Vec<u64>)> {
+    let hs: Vec<*mut vpbs_batch> = batches.iter().map(|b| b.h).collect();
+    let layers = batches[0].degree_log + batches[0].rate_bits - batches[0].cap_height;
+    let mut out: Vec<(Vec<u64>, Vec<u64>)> = batches.iter()
+        .map(|b| (vec![0u64; leaf_indices.len() * b.ncols], vec![0u64; leaf_indices.len() * layers * 4]))
+        .collect();
+    let rows: Vec<*mut u64> = out.iter_mut().map(|o| o.0.as_mut_ptr()).collect();
+    let sibs: Vec<*mut u64> = out.iter_mut().map(|o| o.1.as_mut_ptr()).collect();
+    ctx.check(unsafe { vpbs_batches_open(hs.as_ptr(), hs.len() as u32, leaf_indices.as_ptr(),
+                                         leaf_indices.len() as u64, rows.as_ptr(), sibs.as_ptr()) });
+    out
 }
 
 /// Sigma polynomials' values + coset shifts of one circuit in HBM (uploaded once per circuit).

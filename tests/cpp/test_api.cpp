@@ -96,6 +96,16 @@ int main() {
     std::vector<uint64_t> want(2 * ncols);
     orc_eval_ext2(cp.data(), ncols, n, zeta, want.data());
     CHECK(op == want);
+    {  // the same through the all-oracles-at-once forms (OpeningSet::new / initial_trees_proof)
+      vpbs::ResidentBatch rb2(ctx, values, rate_bits, cap_height, true);
+      auto all = vpbs::open_all_at_point({&rb, &rb2}, zeta);
+      CHECK(all.size() == 2 && all[0] == want && all[1] == rb2.eval_ext2(zeta));
+      auto opened = vpbs::open_all_at_leaf({&rb, &rb2}, m / 2 + 3);
+      CHECK(opened[0].first == rb.get(m / 2 + 3) && opened[1].first == rb2.get(m / 2 + 3));
+      auto q1 = rb.prove(m / 2 + 3), q2 = rb2.prove(m / 2 + 3);
+      CHECK(std::memcmp(opened[0].second.siblings.data(), q1.siblings.data(), q1.siblings.size() * 32) == 0);
+      CHECK(std::memcmp(opened[1].second.siblings.data(), q2.siblings.data(), q2.siblings.size() * 32) == 0);
+    }
 
     std::vector<F> ext(2 * 4096);
     for (auto& x : ext) x = rng() % ORC_P;

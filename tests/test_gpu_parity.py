@@ -957,6 +957,34 @@ def test_sharded_resident_batches_one_proof_over_several_ranks(V, oracle, world,
         assert np.array_equal(zcap_union, zref["cap"])
 
 
+def test_all_oracles_opened_in_one_round_trip(V, ctx, oracle):
+    """vpbs_batches_eval_ext2 / vpbs_batches_open (OpeningSet::new and initial_trees_proof over all
+    FRI oracles at once) equal the per-batch calls and the oracle."""
+    rng = np.random.default_rng(77)
+    log_n, widths = 9, [85, 135, 20, 16]
+    m = (1 << log_n) << 3
+    mats = [rand_u64(rng, (w, 1 << log_n)) for w in widths]
+    batches = [V.commit_resident(a, 3, False, 4, k == 3, ctx=ctx) for k, a in enumerate(mats)]
+    pts = rand_u64(rng, (2, 2))
+    got = V.open_all_at_points(batches, pts)
+    for b, g in zip(batches, got):
+        assert np.array_equal(g, b.eval_ext2(pts))
+    idx = rng.integers(0, m, size=28, dtype=np.uint64)
+    opened = V.open_all_at_leaves(batches, idx)
+    for k, (b, (rows, sibs)) in enumerate(zip(batches, opened)):
+        ref = oracle.commit(mats[k], 3, 4, k == 3, None)
+        for q, i in enumerate(idx):
+            assert np.array_equal(rows[q], ref["leaves"][int(i)])
+            assert np.array_equal(sibs[q], oracle.merkle_prove(ref["digests"], m, 4, int(i)))
+    other = V.commit_resident(mats[0], 2, False, 4, ctx=ctx)      # different tree shape
+    with pytest.raises(ValueError):
+        V.open_all_at_leaves([batches[0], other], idx[:2])
+    with pytest.raises(ValueError):
+        V.open_all_at_leaves(batches, np.array([m], np.uint64))
+    for b in batches + [other]:
+        b.close()
+
+
 def test_shard_count_the_commit_cannot_be_split_into(V):
     with V.Context(0) as c:
         with pytest.raises(ValueError):

@@ -13,6 +13,6 @@ from .plonky2_api import (  # noqa: F401
     get_unique_coset_shifts,
     commit_device, commit_shard_device, default_context, eval_ext2, fft, fri_fold, fri_layer_commit,
     fri_proof_of_work, hash_or_noop, ifft, lde_values,
-    log2_strict, poseidon, reverse_bits, synthetic_columns, two_to_one,
+    log2_strict, open_all_at_leaves, open_all_at_points, poseidon, reverse_bits, synthetic_columns, two_to_one,
     verify_merkle_proof_to_cap)
 from .sharding import ShardPlan, ShardedProof, commit_sharded, gather_cap, shard_plan  # noqa: F401,E402

@@ -1526,6 +1526,48 @@ int vpbs_batch_eval_ext2(vpbs_batch* b, const uint64_t* points, uint32_t npoints
   return eval_ext2_device(ctx, b->coeffs, b->ncols, b->log_n, points, npoints, out);
 }
 
+// [P2] plonk/proof.rs OpeningSet::new evaluates the polynomials of all four oracles at the same points:
+// one upload of the points, one kernel per batch, one synchronisation (four separate
+// vpbs_batch_eval_ext2 calls cost the N=1024 step 0.69 ms, almost all of it round trips).
+int vpbs_batches_eval_ext2(vpbs_batch* const* batches, uint32_t nbatches, const uint64_t* points,
+                           uint32_t npoints, uint64_t* const* outs) {
+  if (!batches || nbatches == 0 || !batches[0]) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = batches[0]->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (npoints == 0) return VPBS_OK;
+  if (!points || !outs) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  if (npoints > 65535) return fail(ctx, VPBS_ERR_ARG, "too many points");
+  size_t total = 0;
+  for (u32 k = 0; k < nbatches; k++) {
+    if (!batches[k] || batches[k]->ctx != ctx) return fail(ctx, VPBS_ERR_STATE, "batches of different contexts");
+    if (!outs[k]) return fail(ctx, VPBS_ERR_ARG, "outs[k] == NULL");
+    total += (size_t)npoints * batches[k]->ncols * 16;
+  }
+  u64 *d_pts = nullptr, *d_out = nullptr;
+  if ((rc = arena_get(ctx, "idx", (size_t)npoints * 16, (void**)&d_pts))) return rc;
+  if ((rc = arena_get(ctx, "rows", total, (void**)&d_out))) return rc;
+  CU(ctx, cudaMemcpyAsync(d_pts, points, (size_t)npoints * 16, cudaMemcpyHostToDevice, ctx->stream));
+  size_t off = 0;
+  for (u32 k = 0; k < nbatches; k++) {
+    const vpbs_batch* b = batches[k];
+    u64* o = d_out + off / 8;
+    if (b->log_n >= 14)
+      ntt::eval_ext2<1024><<<dim3(b->ncols, npoints), 1024, 0, ctx->stream>>>(b->coeffs, 1ULL << b->log_n,
+                                                                            b->log_n, d_pts, o, b->ncols);
+    else
+      ntt::eval_ext2<256><<<dim3(b->ncols, npoints), 256, 0, ctx->stream>>>(b->coeffs, 1ULL << b->log_n,
+                                                                          b->log_n, d_pts, o, b->ncols);
+    ctx->launches++;
+    const size_t bytes = (size_t)npoints * b->ncols * 16;
+    CU(ctx, cudaMemcpyAsync(outs[k], o, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    off += bytes;
+  }
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
 // ---- FRI commit phase --------------------------------------------------------------------------------
 int vpbs_fri_layer_commit(vpbs_ctx* ctx, const uint64_t* values_ext, uint64_t len,
                           uint32_t arity_bits, uint32_t cap_height, uint64_t* leaves_out,
@@ -2494,6 +2536,57 @@ int vpbs_batch_prove(vpbs_batch* b, const uint64_t* leaf_indices, uint64_t count
   ctx->launches++;
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(siblings_out, d_sib, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+// [P2] fri/prover.rs fri_prover_query_round -> initial_trees_proof: for every oracle the leaf row and
+// the Merkle path at the same query indices.  One index upload, two gathers per batch, one
+// synchronisation for all batches (eight separate get_leaves / prove calls cost the step 0.4 ms).
+int vpbs_batches_open(vpbs_batch* const* batches, uint32_t nbatches, const uint64_t* leaf_indices,
+                      uint64_t count, uint64_t* const* rows_out, uint64_t* const* siblings_out) {
+  if (!batches || nbatches == 0 || !batches[0]) return VPBS_ERR_STATE;
+  vpbs_batch* b0 = batches[0];
+  vpbs_ctx* ctx = b0->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (count == 0) return VPBS_OK;
+  if (!leaf_indices || !rows_out || !siblings_out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  const unsigned num_layers = b0->log_n + b0->rate_bits - b0->cap_height;
+  size_t total = 0;
+  for (u32 k = 0; k < nbatches; k++) {
+    const vpbs_batch* b = batches[k];
+    if (!b || b->ctx != ctx) return fail(ctx, VPBS_ERR_STATE, "batches of different contexts");
+    if (b->log_n != b0->log_n || b->rate_bits != b0->rate_bits || b->cap_height != b0->cap_height ||
+        b->first_leaf != b0->first_leaf || b->nleaves != b0->nleaves)
+      return fail(ctx, VPBS_ERR_ARG, "batches opened together must have the same tree shape and shard");
+    if (!rows_out[k] || (num_layers && !siblings_out[k])) return fail(ctx, VPBS_ERR_ARG, "null output pointer");
+    total += count * ((size_t)b->width * 8 + (size_t)num_layers * 32);
+  }
+  u64 *d_idx = nullptr, *d_buf = nullptr;
+  if ((rc = batch_indices(b0, leaf_indices, count, &d_idx))) return rc;
+  if ((rc = arena_get(ctx, "rows", total, (void**)&d_buf))) return rc;
+  const u64 sub_digests = 2 * (1ULL << num_layers) - 2;
+  size_t off = 0;
+  for (u32 k = 0; k < nbatches; k++) {
+    const vpbs_batch* b = batches[k];
+    u64* d_rows = d_buf + off / 8;
+    const size_t row_bytes = count * (size_t)b->width * 8, sib_bytes = count * (size_t)num_layers * 32;
+    merkle::gather_rows<<<(unsigned)count, 128, 0, ctx->stream>>>(b->leaves, b->width, d_idx, count, d_rows);
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(rows_out[k], d_rows, row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    off += row_bytes;
+    if (num_layers) {
+      u64* d_sib = d_buf + off / 8;
+      const u64 tot = count * num_layers;
+      merkle::gather_siblings<<<(unsigned)((tot + 127) / 128), 128, 0, ctx->stream>>>(
+          b->digests, d_idx, count, num_layers, sub_digests, d_sib);
+      ctx->launches++;
+      CU(ctx, cudaMemcpyAsync(siblings_out[k], d_sib, sib_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      off += sib_bytes;
+    }
+  }
+  CU(ctx, cudaGetLastError());
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return VPBS_OK;
 }

@@ -616,6 +616,34 @@ class ResidentPolynomialBatch:
                                self.rate_bits, self.blinding, self.stats)
 
 
+def open_all_at_points(batches: Sequence["ResidentPolynomialBatch"], points) -> List[np.ndarray]:
+    """[P2] plonk/proof.rs OpeningSet::new over all oracles in one round trip
+    (vpbs_batches_eval_ext2): per batch the (npoints, ncols, 2) openings at the same points."""
+    ctx = batches[0].ctx
+    pts = _as_u64(points).reshape(-1, 2)
+    outs = [np.empty((pts.shape[0], b.ncols, 2), np.uint64) for b in batches]
+    hs = (ctypes.c_void_p * len(batches))(*[b.handle for b in batches])
+    ops = (u64p * len(batches))(*[_ptr(o) for o in outs])
+    ctx.check(ctx.lib.vpbs_batches_eval_ext2(hs, len(batches), _ptr(pts), pts.shape[0], ops))
+    return outs
+
+
+def open_all_at_leaves(batches: Sequence["ResidentPolynomialBatch"], leaf_indices):
+    """[P2] fri/prover.rs fri_prover_query_round (initial_trees_proof) over all oracles in one round
+    trip (vpbs_batches_open): per batch (rows (count, width), siblings (count, layers, 4))."""
+    ctx = batches[0].ctx
+    idx = _as_u64(leaf_indices).reshape(-1)
+    t0 = batches[0].merkle_tree
+    layers = log2_strict(t0.nleaves) - log2_strict(t0.cap.shape[0])
+    rows = [np.empty((idx.size, b.merkle_tree.width), np.uint64) for b in batches]
+    sibs = [np.empty((idx.size, layers, 4), np.uint64) for _ in batches]
+    hs = (ctypes.c_void_p * len(batches))(*[b.handle for b in batches])
+    rp = (u64p * len(batches))(*[_ptr(r) for r in rows])
+    sp = (u64p * len(batches))(*[_ptr(x) for x in sibs])
+    ctx.check(ctx.lib.vpbs_batches_open(hs, len(batches), _ptr(idx), idx.size, rp, sp))
+    return list(zip(rows, sibs))
+
+
 def commit_resident(cols, rate_bits: int, blinding: bool, cap_height: int,
                     inputs_are_coeffs: bool = False, *, ctx: Optional[Context] = None, salt=None,
                     rng: Optional[np.random.Generator] = None) -> ResidentPolynomialBatch:
