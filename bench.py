@@ -649,7 +649,7 @@ def main():
             lib.vpbs_batch_destroy(h)
 
         pg_in = {}
-        for threads in (4, 0):
+        for threads in (1, 2, 8, 4, 0):
             ctx.set_host_threads(threads)
             for _ in range(2):
                 pageable_resident_step()
@@ -662,6 +662,7 @@ def main():
         pageable["inputs_only"] = {
             "value": n / pg_in[4], "unit": UNIT, "ms_per_step": pg_in[4] * 1e3,
             "ms_per_step_driver_staging": pg_in[0] * 1e3, "copy_threads": 4,
+            "ms_per_step_by_copy_threads": {str(k): round(v * 1e3, 3) for k, v in pg_in.items() if k},
             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": res_d2h,
             "api": "vpbs_batch_commit + openings + 28 rows/paths, value columns in pageable memory (one "
                    "allocation per column, as plonky2's Vec<PolynomialValues<F>>) through the library's "

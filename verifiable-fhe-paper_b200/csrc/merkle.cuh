@@ -81,6 +81,41 @@ hash_leaves(const u64* __restrict__ leaves, u64 nleaves, u32 width, u64* __restr
   hash_row(leaves + k * width, width, out + 4 * pos);
 }
 
+// The same sponge in pieces: columns [c0, c1) of every row absorbed on top of the state the previous
+// piece left (c0 a multiple of the rate; `state` holds the 12 words of every leaf, word-major so
+// that a warp's accesses coalesce).  The sponge state after the first c columns depends on those
+// columns only, so a wide batch whose columns arrive chunk by chunk from a slow source (pageable host
+// memory through the staging ring) can be hashed while the later chunks are still on their way.
+// first: start from the zero state; last: write the digest instead of the state.
+__global__ void __launch_bounds__(VPBS_HASH_THREADS, VPBS_HASH_MIN_BLOCKS)
+hash_leaves_part(const u64* __restrict__ leaves, u64 nleaves, u32 width, u32 c0, u32 c1,
+                 u64* __restrict__ state, int first, int last, u64* __restrict__ out, unsigned log_sub,
+                 u64 sub_digests, int all_cap) {
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nleaves) return;
+  u64 s[poseidon::WIDTH];
+#pragma unroll
+  for (int i = 0; i < poseidon::WIDTH; i++) s[i] = first ? 0 : state[(u64)i * nleaves + k];
+  const u64* row = leaves + k * width;
+  for (u32 off = c0; off < c1; off += poseidon::RATE) {
+#pragma unroll
+    for (int i = 0; i < poseidon::RATE; i++)
+      if (off + i < c1) s[i] = __ldg(row + off + i);
+    poseidon::permute_lazy(s);
+  }
+  if (!last) {
+#pragma unroll
+    for (int i = 0; i < poseidon::WIDTH; i++) state[(u64)i * nleaves + k] = s[i];
+    return;
+  }
+  u64 pos = k;
+  if (!all_cap) {
+    const u64 sub = k >> log_sub, l = k & ((1ULL << log_sub) - 1);
+    pos = sub * sub_digests + leaf_digest_pos(l);
+  }
+  store_hash(out + 4 * pos, s);
+}
+
 // Layer `level` (>= 1) of every cap subtree: node jj = two_to_one(children pair jj of level-1).
 // level == log_sub writes the subtree roots into `cap`.
 __global__ void __launch_bounds__(128)

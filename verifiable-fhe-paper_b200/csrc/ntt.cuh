@@ -659,6 +659,13 @@ __device__ __forceinline__ Ext2 ext_mul(Ext2 a, Ext2 b) {
 // values.  T = 1024 for long polynomials: the Horner chain of a thread is a serial run of extension
 // multiplies (2^16 coefficients: 64 steps instead of 256 with T = 256, and four times the warps to
 // hide them behind; 170 -> see DESIGN.md §9.2 for the measured effect), T = 256 below 2^14.
+// a b + c + d formed in 128 bits (it fits: (2^64-1)^2 + 2 (2^64-1) = 2^128 - 1) and reduced once:
+// the Horner step acc <- acc y + c_k costs two of these and two plain products (~66 instructions)
+// instead of five canonical multiplies and three canonical adds (~124).
+__device__ __forceinline__ u64 mul_add2_lazy(u64 a, u64 b, u64 c, u64 d) {
+  const unsigned __int128 r = (unsigned __int128)a * b + c + d;
+  return gl::reduce_words((u64)r, (u64)(r >> 64));
+}
 template <int T>
 __global__ void __launch_bounds__(T)
 eval_ext2(const u64* __restrict__ coeffs, u64 col_stride, unsigned log_n,
@@ -666,26 +673,50 @@ eval_ext2(const u64* __restrict__ coeffs, u64 col_stride, unsigned log_n,
   constexpr int LOG_T = T == 1024 ? 10 : 8;
   static_assert(T == 1024 || T == 256, "eval_ext2: 256 or 1024 threads");
   __shared__ u64 sre[T], sim[T];
+  __shared__ u64 plo[2][32], phi[2][32];  // x^i and x^(32 i), i < 32 (re, im)
   const unsigned col = blockIdx.x, pt = blockIdx.y, t = threadIdx.x;
   const u64 n = 1ULL << log_n;
   const Ext2 x{gl::canon(points[2 * pt]), gl::canon(points[2 * pt + 1])};
   Ext2 y = x;  // x^T
 #pragma unroll
   for (int i = 0; i < LOG_T; i++) y = ext_mul(y, y);
-  const u64* c = coeffs + (u64)col * col_stride;
-  Ext2 acc{0, 0};
-  if (t < n) {
-    const u64 k_hi = (n - 1 - t) >> LOG_T;  // largest k with T k + t < n
-    for (u64 k = k_hi + 1; k-- > 0;) {
-      acc = ext_mul(acc, y);
-      acc.re = gl::add(acc.re, gl::canon(__ldg(c + (k << LOG_T) + t)));
+  // x^t = x^(t mod 32) * x^(32 (t / 32)): two 32-entry tables built by the first two warps (a
+  // per-thread binary exponentiation cost a quarter of the kernel)
+  if (t < 64) {
+    Ext2 b = x;
+    if (t >= 32) {
+#pragma unroll
+      for (int i = 0; i < 5; i++) b = ext_mul(b, b);  // x^32
     }
-    Ext2 p{1, 0}, b = x;  // x^t by binary exponentiation (t < T)
-    for (unsigned e = t; e; e >>= 1) {
+    Ext2 p{1, 0};
+    for (unsigned e = t & 31; e; e >>= 1) {
       if (e & 1) p = ext_mul(p, b);
       b = ext_mul(b, b);
     }
-    acc = ext_mul(acc, p);
+    if (t < 32) {
+      plo[0][t] = p.re;
+      plo[1][t] = p.im;
+    } else {
+      phi[0][t - 32] = p.re;
+      phi[1][t - 32] = p.im;
+    }
+  }
+  __syncthreads();
+  const u64* c = coeffs + (u64)col * col_stride;
+  Ext2 acc{0, 0};
+  if (t < n) {
+    const u64 y7 = gl::mul(7, y.im);
+    const u64 k_hi = (n - 1 - t) >> LOG_T;  // largest k with T k + t < n
+    u64 are = 0, aim = 0;                   // arbitrary u64 representatives inside the chain
+    for (u64 k = k_hi + 1; k-- > 0;) {
+      const u64 ck = __ldg(c + (k << LOG_T) + t);
+      const u64 t1 = gl::mul_lazy_fma(are, y.re), t2 = gl::mul_lazy_fma(are, y.im);
+      are = mul_add2_lazy(aim, y7, t1, ck);   // re: a.re y.re + 7 a.im y.im + c_k
+      aim = mul_add2_lazy(aim, y.re, t2, 0);  // im: a.re y.im + a.im y.re
+    }
+    acc = Ext2{gl::canon(are), gl::canon(aim)};
+    const Ext2 lo{plo[0][t & 31], plo[1][t & 31]}, hi{phi[0][(t >> 5) & 31], phi[1][(t >> 5) & 31]};
+    acc = ext_mul(acc, ext_mul(lo, hi));
   }
   sre[t] = acc.re;
   sim[t] = acc.im;

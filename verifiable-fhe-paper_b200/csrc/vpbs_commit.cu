@@ -508,6 +508,10 @@ struct Overlap {
   // and a stream wait enqueued before the record would wait for nothing — so the enqueueing thread
   // first waits on the host until the record has happened.
   hoststage::Upload* upload = nullptr;
+  // Hash every column chunk into the leaf sponges right after its LDE (merkle::hash_leaves_part)
+  // instead of hashing whole rows at the end: only worth it when the chunks arrive slowly (staged
+  // uploads from pageable memory) — with pinned inputs it measured 0.1 ms slower.
+  bool absorb_chunks = false;
 };
 
 struct Timer {
@@ -580,6 +584,9 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   // block by block over all columns, so that finished leaf rows can stream out while later
   // blocks are still being transformed (best when the leaf matrix is copied to the host).
   const bool by_block = chunked && ov->lde_by_block;
+  // chunk-wise hashing needs whole permutations per chunk (chunk a multiple of the rate) and rows
+  // without salt columns
+  const bool absorb = chunked && !by_block && ov->absorb_chunks && !d_salt && chunk % poseidon::RATE == 0;
   // "FFT + blinding" + "transpose LDEs": one size-n coset transform per LDE block, written as
   // leaf rows (columns c0 .. c0 + nc of the row-major matrix).
   auto lde_blocks = [&](const u64* coeffs, u32 c0, u32 nc, bool block_events) -> int {
@@ -630,6 +637,17 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
       cudaEventRecord(ov->coeffs_chunk_ready[k], ctx->stream);
     }
     if (!by_block && (rc = lde_blocks(coeffs, c0, nc, !chunked)) != VPBS_OK) return rc;
+    if (absorb) {  // this chunk's columns of every leaf row into the sponges
+      u64* sponge = nullptr;
+      if ((rc = arena_get(ctx, "sponge", (size_t)nleaves_shard * poseidon::WIDTH * sizeof(u64), (void**)&sponge)))
+        return rc;
+      const bool last = c0 + nc == ncols;
+      const u64 sub_digests = 2 * (1ULL << log_sub) - 2;
+      merkle::hash_leaves_part<<<(unsigned)((nleaves_shard + 127) / 128), 128, 0, ctx->stream>>>(
+          d_leaves, nleaves_shard, width, c0, c0 + nc, sponge, c0 == 0, last,
+          log_sub == 0 ? d_roots : d_digests, log_sub, sub_digests, log_sub == 0);
+      ctx->launches++;
+    }
   }
   if (by_block &&
       (rc = lde_blocks(inputs_are_coeffs ? d_cols : cbuf, 0, ncols, true)) != VPBS_OK)
@@ -647,8 +665,11 @@ int commit_core(vpbs_ctx* ctx, const u64* d_cols, u32 ncols, u32 log_n, u32 rate
   // this phase-by-phase order at 2^16 x 128 — a 65,536-leaf launch is less than one wave of 128-thread
   // CTAs, each of which lives ~1 ms (16 sequential permutations), so the per-block kernels fragment
   // the machine)
-  if ((rc = merkle_build(ctx, d_leaves, nleaves_shard, width, log_sub, d_digests, d_roots,
-                         tm->on ? ctx->ev[8] : nullptr)) != VPBS_OK)
+  if (absorb) {  // leaf digests are final: only the levels above them remain
+    if (tm->on) cudaEventRecord(ctx->ev[8], ctx->stream);
+    if ((rc = merkle_levels(ctx, nleaves_shard, log_sub, d_digests, d_roots, ctx->stream)) != VPBS_OK) return rc;
+  } else if ((rc = merkle_build(ctx, d_leaves, nleaves_shard, width, log_sub, d_digests, d_roots,
+                                tm->on ? ctx->ev[8] : nullptr)) != VPBS_OK)
     return rc;
   tm->leaf_event = tm->on;
   tm->mark();  // 3
@@ -1249,6 +1270,7 @@ int commit_host_enqueue(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t nco
                                   want_stats ? e1 : nullptr, &run->upload)))
       return rc;
     ovl.upload = run->upload.get();
+    ovl.absorb_chunks = !ovl.lde_by_block;
   }
   for (u32 c0 = 0, k = 0; c0 < ncols && !delivered && !staged; k++) {
     const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
@@ -2072,6 +2094,7 @@ int vpbs_batch_commit(vpbs_ctx* ctx, const uint64_t* const* cols, uint32_t ncols
       return rc;
     }
     ovl.upload = upload.get();
+    ovl.absorb_chunks = true;  // slow arrivals: hash chunk k while chunk k + 1 is still being staged
   }
   for (u32 c0 = 0, k = 0; c0 < ncols && ce == cudaSuccess && !staged; k++) {
     const u32 c1 = (nchunks && c0 + chunk_cols < ncols) ? c0 + chunk_cols : ncols;
