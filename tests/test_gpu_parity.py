@@ -265,6 +265,30 @@ def test_microbench_config_full_size(V, ctx, oracle):
         assert int(b.merkle_tree.leaves[k, 3]) == acc
 
 
+def test_microbench_config_full_size_adversarial(V, ctx, oracle):
+    """the configs[1] shape with raw (non-canonical) u64 inputs and constant columns —
+    all zeros, all p - 1, all 2^64 - 1, all p — through the eager and the resident commit."""
+    rng = np.random.default_rng(2024)
+    cols = rng.integers(0, 2**64, size=(128, 1 << 16), dtype=np.uint64)
+    cols[0] = 0
+    cols[1] = P - 1
+    cols[2] = 2**64 - 1
+    cols[3] = P
+    cols[127, ::2] = P - 1
+    ref = oracle.commit(cols, 3, 4, False)
+    b = V.PolynomialBatch.from_values(cols, 3, False, 4, ctx=ctx)
+    assert np.array_equal(b.merkle_tree.cap, ref["cap"])
+    assert np.array_equal(b.polynomials, ref["coeffs"])
+    assert np.array_equal(b.merkle_tree.digests, ref["digests"])
+    assert np.array_equal(b.merkle_tree.leaves, ref["leaves"])
+    assert (b.merkle_tree.leaves < np.uint64(P)).all() and (b.polynomials < np.uint64(P)).all()
+    assert not b.polynomials[0].any() and not b.polynomials[3].any()          # 0 and p are the zero polynomial
+    assert int(b.polynomials[1][0]) == P - 1 and not b.polynomials[1][1:].any()  # constants have degree 0
+    rb = V.commit_resident(cols, 3, False, 4, ctx=ctx)
+    assert np.array_equal(rb.merkle_tree.cap, ref["cap"])
+    rb.close()
+
+
 def test_step_shapes_full_size(V, ctx, oracle):
     """BASELINE.json configs[2] stand-in: the three commits of one N=1024 IVC step, and build()'s
     one-off constants/sigmas commit (~85 columns, ivc_based_vpbs.rs:275)."""
