@@ -388,6 +388,37 @@ int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas,
                                    uint32_t num_challenges, uint32_t rate_bits, uint32_t cap_height,
                                    uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats);
 
+/* ---- quotient polynomials: the gate-independent part + the tail --------------
+ * [P2] plonky2/src/plonk/prover.rs compute_quotient_polys with plonk/vanishing_poly.rs
+ * eval_vanishing_poly_base_batch restricted to the terms that do not depend on the gate set (step 6
+ * of prove(), /root/reference/src/vtfhe/ivc_based_vpbs.rs:302, :333, :364).  On the quotient domain
+ * (n << quotient_degree_bits points of the coset 7<w>, read from the resident batches' LDE rows):
+ *   L_0(x) (Z_c(x) - 1)   and   the partial-product checks of every challenge
+ *   (check_partial_products with max_degree = quotient_degree_factor), in upstream's order, reduced
+ *   with the powers of every alpha (reduce_with_powers_multi), divided by Z_H(x) = x^n - 1
+ *   (ZeroPolyOnCoset), then per challenge coset_ifft(7), split into 2^quotient_degree_bits chunks of
+ *   n coefficients and committed from coefficients as a new resident batch (prove() step 7:
+ *   num_challenges * 2^quotient_degree_bits columns, challenge-major).
+ * The gate constraints (every gate's eval_unfiltered_base_batch with its selector filter; the gate
+ * definitions are plonky2 source that is not restated here) enter as ALREADY alpha-reduced values:
+ *   gate_terms[c][i] = sum_j alpha_c^j gate_constraint_j(7 w_q^i),  i < n << quotient_degree_bits,
+ * natural order, host memory, NULL = no gate constraints; they are added times
+ * alpha_c^(number of permutation terms), which is where upstream's term order puts them.
+ *   constants_sigmas: the circuit's batch; its sigma polynomials are columns
+ *                     [sigmas_first_col, sigmas_first_col + num_routed)
+ *   wires:            routed wires are its first num_routed columns
+ *   zs_pp:            the batch vpbs_batch_zs_partial_products returned (Z_0 .. Z_{nc-1}, then the
+ *                     partial products of challenge 0, 1, ..)
+ *   k_is:             num_routed coset shifts (host)
+ * All three batches must be unsharded and have rate_bits >= quotient_degree_bits; at most 4
+ * challenges. */
+int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
+                              vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
+                              uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
+                              const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
+                              const uint64_t* const* gate_terms, uint32_t rate_bits, uint32_t cap_height,
+                              uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

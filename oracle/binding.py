@@ -77,6 +77,9 @@ def lib() -> ctypes.CDLL:
         L.orc_fri_final_poly.argtypes = [_u64pp, ctypes.POINTER(u32), u32, u64, _u64p, _u64p, _u64p]
         L.orc_zs_partial_products.restype = ctypes.c_int
         L.orc_zs_partial_products.argtypes = [_u64pp, _u64pp, _u64p, u32, u32, u32, u64, u64, _u64p]
+        L.orc_quotient_polys.restype = ctypes.c_int
+        L.orc_quotient_polys.argtypes = [_u64pp, _u64pp, _u64pp, _u64p, u32, u32, u32, u32, _u64p, _u64p,
+                                         _u64p, u32, _u64pp, _u64p]
         L.orc_set_simd.argtypes = [ctypes.c_int]
         L.orc_get_simd.restype = ctypes.c_int
         L.orc_poseidon_batch.argtypes = [_u64p, u64]
@@ -262,6 +265,28 @@ def zs_partial_products(wires, sigmas, k_is, max_degree, beta, gamma):
     rc = lib().orc_zs_partial_products(wp, sp, _p(k), nr, _log2(n), max_degree, int(beta), int(gamma), _p(out))
     if rc == -2:
         raise ZeroDivisionError("a permutation denominator is zero (plonky2 panics here)")
+    if rc != 0:
+        raise ValueError("bad arguments")
+    return out
+
+
+def quotient_polys(wire_coeffs, sigma_coeffs, zs_pp_coeffs, k_is, max_degree, qdb, betas, gammas, alphas,
+                   gate_terms=None):
+    """[P2] compute_quotient_polys (gate-independent terms + optional alpha-reduced gate terms).
+    Coefficient columns in: wires (num_routed, n), sigmas (num_routed, n), zs_pp (nc * K, n) in commit
+    order; gate_terms: (nc, n << qdb) or None.  Returns (nc * 2^qdb, n) quotient chunks."""
+    w, s, z, k = _arr(wire_coeffs), _arr(sigma_coeffs), _arr(zs_pp_coeffs), _arr(k_is)
+    b, g, a = _arr(betas).reshape(-1), _arr(gammas).reshape(-1), _arr(alphas).reshape(-1)
+    nr, n = w.shape
+    nc = b.size
+    out = np.zeros((nc << qdb, n), np.uint64)
+    ptrs = lambda m: (_u64p * m.shape[0])(*[_p(m[j]) for j in range(m.shape[0])])
+    gt = None
+    if gate_terms is not None:
+        gt_arr = _arr(gate_terms)
+        gt = ptrs(gt_arr)
+    rc = lib().orc_quotient_polys(ptrs(w), ptrs(s), ptrs(z), _p(k), nr, _log2(n), max_degree, qdb,
+                                  _p(b), _p(g), _p(a), nc, gt, _p(out))
     if rc != 0:
         raise ValueError("bad arguments")
     return out

@@ -314,3 +314,53 @@ def zs_partial_products(wires, sigmas, k_is, max_degree, beta, gamma):
                 cols[1 + k][i] = acc
         z = acc
     return cols
+
+
+def quotient_polys(wire_coeffs, sigma_coeffs, zs_pp_coeffs, k_is, max_degree, qdb, betas, gammas, alphas,
+                   gate_terms=None):
+    """[P2] plonk/prover.rs compute_quotient_polys restricted to the gate-independent vanishing terms
+    (plonk/vanishing_poly.rs eval_vanishing_poly_base_batch: the Z(1) = 1 terms, then the
+    partial-product checks of every challenge, reduced with powers of each alpha), straight from the
+    definitions: every polynomial is evaluated by Horner at x = 7 w_q^i, the vanishing value divided
+    by x^n - 1, the quotient interpolated on the coset by the defining sum and cut into chunks of n.
+    gate_terms[c][i] (optional) = alpha-reduced gate constraints at point i; they follow the nc + nc K
+    permutation terms in upstream's order, i.e. enter times alpha_c^(nc + nc K).
+    Returns nc * 2^qdb coefficient lists of length n."""
+    num_routed, n = len(wire_coeffs), len(wire_coeffs[0])
+    nc = len(betas)
+    K = -(-num_routed // max_degree)
+    q = n << qdb
+    wq = primitive_root_of_unity(q.bit_length() - 1)
+    g = primitive_root_of_unity(n.bit_length() - 1)
+    n_inv_mod = lambda v: pow(v, P - 2, P)
+    vals = [[0] * q for _ in range(nc)]
+    for i in range(q):
+        x = 7 * pow(wq, i, P) % P
+        gx = g * x % P
+        wv = [evaluate(c, x) for c in wire_coeffs]
+        sv = [evaluate(c, x) for c in sigma_coeffs]
+        zv = [evaluate(c, x) for c in zs_pp_coeffs]
+        zg = [evaluate(zs_pp_coeffs[c], gx) for c in range(nc)]
+        zh = (pow(x, n, P) - 1) % P
+        l0 = zh * n_inv_mod(n * (x - 1) % P) % P
+        terms = [l0 * (zv[c] - 1) % P for c in range(nc)]
+        for c in range(nc):
+            accs = [zv[c]] + [zv[nc + c * (K - 1) + t] for t in range(K - 1)] + [zg[c]]
+            for t in range(K):
+                num = den = 1
+                for j in range(t * max_degree, min((t + 1) * max_degree, num_routed)):
+                    num = num * (wv[j] + betas[c] * k_is[j] * x + gammas[c]) % P
+                    den = den * (wv[j] + betas[c] * sv[j] + gammas[c]) % P
+                terms.append((accs[t] * num - accs[t + 1] * den) % P)
+        for c in range(nc):
+            res = sum(t * pow(alphas[c], j, P) for j, t in enumerate(terms)) % P
+            if gate_terms is not None:
+                res = (res + pow(alphas[c], len(terms), P) * gate_terms[c][i]) % P
+            vals[c][i] = res * n_inv_mod(zh) % P
+    out = []
+    w_inv, q_inv, s_inv = n_inv_mod(wq), n_inv_mod(q), n_inv_mod(7)
+    for c in range(nc):
+        coeffs = [sum(v * pow(w_inv, i * j, P) for i, v in enumerate(vals[c])) % P * q_inv % P * pow(s_inv, j, P) % P
+                  for j in range(q)]
+        out += [coeffs[t * n:(t + 1) * n] for t in range(1 << qdb)]
+    return out

@@ -847,3 +847,96 @@ int orc_zs_partial_products(const uint64_t* const* wires, const uint64_t* const*
   free(subgroup);
   return zero_den ? -2 : 0;
 }
+
+/* ---- [P2] plonk/prover.rs compute_quotient_polys + plonk/vanishing_poly.rs
+ * eval_vanishing_poly_base_batch, the terms that do not depend on the gate set ------------------------
+ * (reached from prove(), /root/reference/src/vtfhe/ivc_based_vpbs.rs:302, :333, :364).
+ * Quotient domain: lde_q = n << qdb points x_i = 7 w_q^i (natural order), qdb =
+ * log2_ceil(quotient_degree_factor).  Per point and challenge c, with K = ceil(num_routed / max_degree)
+ * chunks (max_degree = quotient_degree_factor):
+ *   Z(1) = 1 term:          L_0(x) (Z_c(x) - 1),  L_0(x) = (x^n - 1) / (n (x - 1))     [ZeroPolyOnCoset::eval_l_0]
+ *   partial-product checks: accs = [Z_c(x), pp_c,0(x) .. pp_c,K-2(x), Z_c(g x)] (g = w_n, i.e. the point
+ *                           i + 2^qdb); check_t = accs[t] prod_{j in chunk t} (w_j + beta_c k_j x + gamma_c)
+ *                                              - accs[t+1] prod_{j in chunk t} (w_j + beta_c sigma_j(x) + gamma_c)
+ *   vanishing terms, in upstream's order: Z(1) terms of all challenges, then the checks of challenge
+ *   0, 1, .., then (lookups: none in this reference) the gate constraints.  reduce_with_powers_multi:
+ *   res_c = sum_j term_j alpha_c^j.  The gate constraints enter through gate_terms[c][i] =
+ *   sum_j alpha_c^j gate_constraint_j(x_i) (NULL: none), shifted by alpha_c^(nc + nc K).
+ *   quotient value = res_c / (x^n - 1); then per challenge coset_ifft(7) and chunks of n coefficients.
+ * Inputs are COEFFICIENT columns of length n (the batches' `polynomials`): wires[j] (j < num_routed),
+ * sigmas[j], zs_pp[..] in commit order (Z_0 .. Z_{nc-1}, then the K - 1 partial products of challenge 0,
+ * of challenge 1, ..).  out: nc * 2^qdb columns of n coefficients (challenge-major, chunk-minor). */
+int orc_quotient_polys(const uint64_t* const* wires, const uint64_t* const* sigmas,
+                       const uint64_t* const* zs_pp, const uint64_t* k_is, uint32_t num_routed,
+                       uint32_t log_n, uint32_t max_degree, uint32_t qdb, const uint64_t* betas,
+                       const uint64_t* gammas, const uint64_t* alphas, uint32_t nc,
+                       const uint64_t* const* gate_terms, uint64_t* out) {
+  if (!wires || !sigmas || !zs_pp || !k_is || !betas || !gammas || !alphas || !out || num_routed == 0 ||
+      max_degree < 2 || nc == 0 || log_n + qdb > 30)
+    return -1;
+  const uint64_t n = 1ULL << log_n, q = n << qdb, next_step = 1ULL << qdb;
+  const uint32_t K = (num_routed + max_degree - 1) / max_degree;
+  const uint32_t nzp = nc * K; /* columns of the Z / partial-products batch */
+  const uint32_t nterms = nc + nc * K;
+  uint64_t** lw = malloc(sizeof(uint64_t*) * (2 * num_routed + nzp));
+  if (!lw) return -1;
+  for (uint32_t j = 0; j < 2 * num_routed + nzp; j++) {
+    lw[j] = malloc(q * sizeof(uint64_t));
+    const uint64_t* src = j < num_routed ? wires[j] : j < 2 * num_routed ? sigmas[j - num_routed] : zs_pp[j - 2 * num_routed];
+    orc_lde(src, log_n, qdb, lw[j]);
+  }
+  uint64_t** ls = lw + num_routed;
+  uint64_t** lz = lw + 2 * num_routed;
+  /* ZeroPolyOnCoset: x^n - 1 takes 2^qdb values on the coset */
+  uint64_t zh[1 << 10], zh_inv[1 << 10];
+  const uint64_t g_pow_n = orc_gl_pow(7, n), wr = orc_primitive_root_of_unity(qdb);
+  for (uint64_t k = 0, x = 1; k < next_step; k++, x = mul_(x, wr)) {
+    zh[k] = sub_(mul_(g_pow_n, x), 1);
+    zh_inv[k] = orc_gl_inv(zh[k]);
+  }
+  uint64_t* vals = malloc((size_t)nc * q * sizeof(uint64_t));
+  uint64_t* xs = malloc(q * sizeof(uint64_t));
+  const uint64_t wq = orc_primitive_root_of_unity(log_n + qdb);
+  xs[0] = 7;
+  for (uint64_t i = 1; i < q; i++) xs[i] = mul_(xs[i - 1], wq);
+#pragma omp parallel for schedule(static) num_threads(orc_get_threads())
+  for (uint64_t i = 0; i < q; i++) {
+    const uint64_t x = xs[i], i_next = (i + next_step) % q;
+    uint64_t terms[2 + 2 * 64];
+    const uint64_t l0 = mul_(zh[i % next_step], orc_gl_inv(mul_(canon(n), sub_(x, 1))));
+    for (uint32_t c = 0; c < nc; c++) terms[c] = mul_(l0, sub_(lz[c][i], 1));
+    for (uint32_t c = 0; c < nc; c++) {
+      const uint64_t beta = canon(betas[c]), gamma = canon(gammas[c]);
+      for (uint32_t t = 0; t < K; t++) {
+        uint64_t num = 1, den = 1;
+        for (uint32_t j = t * max_degree; j < (t + 1) * max_degree && j < num_routed; j++) {
+          const uint64_t wv = lw[j][i];
+          num = mul_(num, add_(add_(wv, mul_(beta, mul_(canon(k_is[j]), x))), gamma));
+          den = mul_(den, add_(add_(wv, mul_(beta, ls[j][i])), gamma));
+        }
+        const uint64_t prev = t == 0 ? lz[c][i] : lz[nc + c * (K - 1) + (t - 1)][i];
+        const uint64_t next = t == K - 1 ? lz[c][i_next] : lz[nc + c * (K - 1) + t][i];
+        terms[nc + c * K + t] = sub_(mul_(prev, num), mul_(next, den));
+      }
+    }
+    for (uint32_t c = 0; c < nc; c++) {
+      const uint64_t alpha = canon(alphas[c]);
+      uint64_t acc = gate_terms && gate_terms[c] ? canon(gate_terms[c][i]) : 0;
+      for (uint32_t j = nterms; j-- > 0;) acc = add_(mul_(acc, alpha), terms[j]);
+      vals[(uint64_t)c * q + i] = mul_(acc, zh_inv[i % next_step]);
+    }
+  }
+  /* coset_ifft(7): ifft, then coefficient j times 7^-j; chunks of n are contiguous */
+  const uint64_t inv7 = orc_gl_inv(7);
+  for (uint32_t c = 0; c < nc; c++) {
+    uint64_t* v = vals + (uint64_t)c * q;
+    orc_ifft(v, log_n + qdb);
+    uint64_t s = 1;
+    for (uint64_t j = 0; j < q; j++, s = mul_(s, inv7)) out[(uint64_t)c * q + j] = mul_(v[j], s);
+  }
+  for (uint32_t j = 0; j < 2 * num_routed + nzp; j++) free(lw[j]);
+  free(lw);
+  free(vals);
+  free(xs);
+  return 0;
+}

@@ -128,6 +128,17 @@ int orc_zs_partial_products(const uint64_t* const* wires, const uint64_t* const*
                             const uint64_t* k_is, uint32_t num_routed, uint32_t log_n,
                             uint32_t max_degree, uint64_t beta, uint64_t gamma, uint64_t* out);
 
+/* [P2] plonk/prover.rs compute_quotient_polys with plonk/vanishing_poly.rs
+ * eval_vanishing_poly_base_batch restricted to the gate-independent terms (Z(1) = 1 and the
+ * partial-product checks of the permutation argument), reduce_with_powers_multi over alphas, division
+ * by Z_H on the coset, coset_ifft and the split into chunks of n coefficients; the gate constraints
+ * enter as already alpha-reduced values gate_terms[c][i] (NULL: none).  Layouts: see oracle.c. */
+int orc_quotient_polys(const uint64_t* const* wires, const uint64_t* const* sigmas,
+                       const uint64_t* const* zs_pp, const uint64_t* k_is, uint32_t num_routed,
+                       uint32_t log_n, uint32_t max_degree, uint32_t qdb, const uint64_t* betas,
+                       const uint64_t* gammas, const uint64_t* alphas, uint32_t nc,
+                       const uint64_t* const* gate_terms, uint64_t* out);
+
 /* SIMD width of the hashing path: 0 = widest the CPU supports (default), 1 = scalar — the naive
  * restatement, which is the checker for the other two — 4 = AVX2, 8 = AVX-512.  The SIMD paths
  * evaluate the SAME permutation on 4 / 8 independent leaves or tree nodes per call

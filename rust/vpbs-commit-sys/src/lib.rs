@@ -155,6 +155,13 @@ extern "C" {
                                           stats: *mut vpbs_stats) -> c_int;
     pub fn vpbs_batch_shape(batch: *mut vpbs_batch, ncols: *mut u32, log_n: *mut u32,
                             rate_bits: *mut u32, cap_height: *mut u32, width: *mut u32) -> c_int;
+    pub fn vpbs_batch_quotient_polys(constants_sigmas: *mut vpbs_batch, sigmas_first_col: u32,
+                                     wires: *mut vpbs_batch, zs_pp: *mut vpbs_batch, k_is: *const u64,
+                                     num_routed: u32, max_degree: u32, quotient_degree_bits: u32,
+                                     betas: *const u64, gammas: *const u64, alphas: *const u64,
+                                     num_challenges: u32, gate_terms: *const *const u64, rate_bits: u32,
+                                     cap_height: u32, cap_out: *mut u64, out: *mut *mut vpbs_batch,
+                                     stats: *mut vpbs_stats) -> c_int;
     pub fn vpbs_batch_shard(batch: *mut vpbs_batch, first_leaf: *mut u64, nleaves: *mut u64) -> c_int;
     pub fn vpbs_batches_eval_ext2(batches: *const *mut vpbs_batch, nbatches: u32, points: *const u64,
                                   npoints: u32, outs: *const *mut u64) -> c_int;

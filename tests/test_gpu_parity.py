@@ -1023,6 +1023,122 @@ def test_shard_count_the_commit_cannot_be_split_into(V):
             V.commit_resident(np.ones((5, 64), np.uint64), 3, False, 1, ctx=c)
 
 
+@pytest.mark.parametrize("log_n,ncols,num_routed,deg,qdb,first_sigma", [(6, 12, 8, 4, 2, 3), (10, 135, 80, 8, 3, 5),
+                                                                         (5, 9, 7, 2, 3, 0), (13, 20, 16, 8, 1, 2)])
+def test_quotient_polys_against_oracle(V, ctx, oracle, log_n, ncols, num_routed, deg, qdb, first_sigma):
+    """prove() steps 6-7, gate-independent part (vpbs_batch_quotient_polys): from the resident wires,
+    constants/sigmas and Z batches to the committed quotient chunks, with and without alpha-reduced
+    gate terms; coefficients, cap and opened rows equal the oracle's compute_quotient_polys + from_coeffs."""
+    rng = np.random.default_rng(17 * log_n + ncols)
+    n = 1 << log_n
+    wires = rand_u64(rng, (ncols, n))
+    cs = rand_u64(rng, (first_sigma + num_routed + 1, n))
+    sigma_vals = cs[first_sigma:first_sigma + num_routed]
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    betas, gammas, alphas = (rand_u64(rng, 2, edge_frac=0) for _ in range(3))
+    wb = V.commit_resident(wires, 3, False, 4, ctx=ctx)
+    cb = V.commit_resident(cs, 3, False, 4, ctx=ctx)
+    sg = V.Sigmas(sigma_vals, k_is, ctx)
+    zb = V.commit_zs_partial_products(wb, sg, betas, gammas, deg, 3, 4)
+    wc, cc, zc = wb.download().polynomials, cb.download().polynomials, zb.download().polynomials
+    gate = rand_u64(rng, (2, n << qdb))
+    for gt in (None, gate):
+        qb = V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4, gt)
+        want = oracle.quotient_polys(wc[:num_routed], cc[first_sigma:first_sigma + num_routed], zc, k_is, deg,
+                                     qdb, betas, gammas, alphas, gt)
+        assert qb.ncols == 2 << qdb == want.shape[0]
+        ref = oracle.commit(want, 3, 4, True)
+        assert np.array_equal(qb.merkle_tree.cap, ref["cap"])
+        got = qb.download()
+        assert np.array_equal(got.polynomials, want)
+        assert np.array_equal(got.merkle_tree.leaves, ref["leaves"])
+        qb.close()
+    with pytest.raises(ValueError):
+        V.commit_quotient_polys(cb, first_sigma + 2, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4)
+    with pytest.raises(ValueError):
+        V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, 4, betas, gammas, alphas, 3, 4)
+    for b in (wb, cb, zb):
+        b.close()
+    sg.close()
+
+
+def test_quotient_polys_plonk_identity(V, ctx):
+    """The property the quotient exists for, on a VALID instance: routed wires that satisfy a
+    copy-constraint permutation and an arithmetic gate w3 = c0 w0 w1 + c1 w2 on four further columns.
+    Then every vanishing term is zero on the subgroup, the device's quotient chunks t_k are a true
+    polynomial quotient, and at a random point zeta outside the domain
+        sum_j alpha^j term_j(zeta) = (zeta^n - 1) * sum_k zeta^(n k) t_k(zeta)
+    with the terms recomputed from openings in Python integers (no oracle involved)."""
+    from oracle import model as M
+    rng = np.random.default_rng(9)
+    log_n, num_routed, deg, qdb = 8, 16, 8, 3
+    n, K = 1 << log_n, 2
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    w = pow(7, (P - 1) >> log_n, P)
+    sub = [pow(w, i, P) for i in range(n)]
+    ncell = num_routed * n
+    perm = rng.permutation(ncell)
+    label = np.full(ncell, -1, dtype=np.int64)
+    vals = rng.integers(0, P, size=ncell, dtype=np.uint64)
+    for c0 in range(ncell):
+        c = c0
+        while label[c] < 0:
+            label[c] = c0
+            c = perm[c]
+    routed = vals[label].reshape(num_routed, n)
+    tj, ti = np.divmod(perm, n)
+    sig = np.array([int(k_is[j]) * sub[i] % P for j, i in zip(tj, ti)], dtype=np.uint64).reshape(num_routed, n)
+    consts = rng.integers(0, P, size=(2, n), dtype=np.uint64)            # c0, c1 per row
+    g = rng.integers(0, P, size=(3, n), dtype=np.uint64)                 # w0, w1, w2
+    w3 = np.array([(int(consts[0, i]) * int(g[0, i]) * int(g[1, i]) + int(consts[1, i]) * int(g[2, i])) % P
+                   for i in range(n)], dtype=np.uint64)
+    wires = np.concatenate([routed, g, w3[None]])
+    cs = np.concatenate([consts, sig])
+    betas, gammas, alphas = (rng.integers(1, P, size=2, dtype=np.uint64) for _ in range(3))
+    wb = V.commit_resident(wires, 3, False, 4, ctx=ctx)
+    cb = V.commit_resident(cs, 3, False, 4, ctx=ctx)
+    sg = V.Sigmas(sig, k_is, ctx)
+    zb = V.commit_zs_partial_products(wb, sg, betas, gammas, deg, 3, 4)
+    # the gate's constraint on the quotient domain, alpha-reduced (one constraint: alpha^0)
+    q = n << qdb
+    wl, cl = wb.get_lde_rows(0, 1, q), cb.get_lde_rows(0, 1, q)          # natural order (rate_bits == qdb)
+    gate = np.array([(int(r[19]) - (int(c[0]) * int(r[16]) * int(r[17]) + int(c[1]) * int(r[18]))) % P
+                     for r, c in zip(wl, cl)], dtype=np.uint64)
+    qb = V.commit_quotient_polys(cb, 2, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4,
+                                 np.stack([gate, gate]))
+    t = qb.download().polynomials
+    wc, cc, zc = wb.download().polynomials, cb.download().polynomials, zb.download().polynomials
+    ints = lambda a: [int(x) for x in a]
+    zeta = int(rng.integers(2, P, dtype=np.uint64))
+    ev = lambda coeffs, x: M.evaluate(ints(coeffs), x)
+    gz = w * zeta % P
+    wz, cz, zz = [ev(c, zeta) for c in wc], [ev(c, zeta) for c in cc], [ev(c, zeta) for c in zc]
+    zg = [ev(zc[c], gz) for c in range(2)]
+    zh = (pow(zeta, n, P) - 1) % P
+    l0 = zh * pow(n * (zeta - 1) % P, P - 2, P) % P
+    terms = [l0 * (zz[c] - 1) % P for c in range(2)]
+    for c in range(2):
+        accs = [zz[c]] + [zz[2 + c * (K - 1) + k] for k in range(K - 1)] + [zg[c]]
+        for k in range(K):
+            num = den = 1
+            for j in range(k * deg, (k + 1) * deg):
+                num = num * (wz[j] + int(betas[c]) * int(k_is[j]) * zeta + int(gammas[c])) % P
+                den = den * (wz[j] + int(betas[c]) * cz[2 + j] + int(gammas[c])) % P
+            terms.append((accs[k] * num - accs[k + 1] * den) % P)
+    terms.append((wz[19] - (cz[0] * wz[16] * wz[17] + cz[1] * wz[18])) % P)   # the gate constraint, last
+    for c in range(2):
+        lhs = sum(tm * pow(int(alphas[c]), j, P) for j, tm in enumerate(terms)) % P
+        rhs = zh * sum(pow(zeta, n * k, P) * ev(t[(c << qdb) + k], zeta) for k in range(1 << qdb)) % P
+        assert lhs == rhs
+    # deg(vanishing) <= 9 (n - 1), so the true quotient has degree <= 8 n - 9: the top 8 coefficients of
+    # the last chunk vanish only because the instance is valid (a random instance fills them)
+    for c in range(2):
+        assert not t[(c << qdb) + (1 << qdb) - 1][n - 8:].any()
+    for b in (wb, cb, zb, qb):
+        b.close()
+    sg.close()
+
+
 @pytest.mark.parametrize("log_n,ncols,rate_bits,salted", [(8, 9, 3, False), (10, 135, 3, False), (5, 6, 2, True), (0, 3, 3, False)])
 def test_batch_get_lde_rows(V, ctx, oracle, log_n, ncols, rate_bits, salted):
     """vpbs_batch_get_lde_rows == [get_lde_values(first + i * step) for i] (what the quotient reads)."""

@@ -364,3 +364,26 @@ def test_plonky2_dump(oracle, V):
         for k in ("cap", "sha256_coeffs", "sha256_leaves", "sha256_digests", "lde_row_5"):
             assert t[k] == c[k], (c["name"], k)
     assert theirs["fri_layer"] == mine["fri_layer"]
+
+
+@pytest.mark.parametrize("log_n,nr,deg,qdb,nc", [(3, 5, 2, 2, 2), (2, 4, 4, 1, 1), (3, 3, 2, 3, 2)])
+def test_quotient_polys_oracle_equals_model(oracle, log_n, nr, deg, qdb, nc):
+    """[P2] compute_quotient_polys (gate-independent terms, optional alpha-reduced gate terms): the C
+    restatement (LDE + IFFT based) against the big-integer model (Horner evaluation and the defining
+    interpolation sum)."""
+    from oracle import model as M
+    rng = np.random.default_rng(100 * log_n + nr)
+    n, K = 1 << log_n, -(-nr // deg)
+    P = M.P
+    wires, sig = (rng.integers(0, P, size=(nr, n), dtype=np.uint64) for _ in range(2))
+    zs = rng.integers(0, P, size=(nc * K, n), dtype=np.uint64)
+    k_is = np.array([pow(7, j, P) for j in range(nr)], dtype=np.uint64)
+    b, g, a = (rng.integers(0, P, size=nc, dtype=np.uint64) for _ in range(3))
+    gt = rng.integers(0, P, size=(nc, n << qdb), dtype=np.uint64)
+    ints = lambda m: [[int(x) for x in r] for r in m]
+    for gate in (None, gt):
+        got = oracle.quotient_polys(wires, sig, zs, k_is, deg, qdb, b, g, a, gate)
+        want = M.quotient_polys(ints(wires), ints(sig), ints(zs), [int(x) for x in k_is], deg, qdb,
+                                [int(x) for x in b], [int(x) for x in g], [int(x) for x in a],
+                                None if gate is None else ints(gate))
+        assert np.array_equal(got, np.array(want, dtype=np.uint64))

@@ -9,7 +9,7 @@ from ._lib import VpbsError, VpbsStats  # noqa: F401
 from .plonky2_api import (  # noqa: F401
     COSET_SHIFT, P, SALT_SIZE, Context, FriCommitPhase, MerkleProof, MerkleTree, PolynomialBatch,
     ResidentMerkleTree, ResidentPolynomialBatch, Sigmas, all_wires_permutation_partial_products,
-    commit_resident, commit_resident_device, commit_zs_partial_products, coset_fft,
+    commit_quotient_polys, commit_resident, commit_resident_device, commit_zs_partial_products, coset_fft,
     get_unique_coset_shifts,
     commit_device, commit_shard_device, default_context, eval_ext2, fft, fri_fold, fri_layer_commit,
     fri_proof_of_work, hash_or_noop, ifft, lde_values,

@@ -109,6 +109,10 @@ SIGNATURES = {
                                                   _c.c_uint32, _c.c_uint32, _c.c_uint32, u64p,
                                                   _c.POINTER(_c.c_void_p), _c.POINTER(VpbsStats)]),
     "vpbs_batch_shape": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint32)] * 5),
+    "vpbs_batch_quotient_polys": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, u64p,
+                                             _c.c_uint32, _c.c_uint32, _c.c_uint32, u64p, u64p, u64p,
+                                             _c.c_uint32, _c.POINTER(u64p), _c.c_uint32, _c.c_uint32, u64p,
+                                             _c.POINTER(_c.c_void_p), _c.POINTER(VpbsStats)]),
     "vpbs_batch_shard": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint64)] * 2),
     "vpbs_batches_eval_ext2": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_uint32, u64p, _c.c_uint32,
                                           _c.POINTER(u64p)]),

@@ -191,4 +191,88 @@ gather_lde_rows(const u64* __restrict__ leaves, u32 width, u32 ncols, unsigned l
   for (u32 c = threadIdx.x; c < ncols; c += blockDim.x) rows_out[r * ncols + c] = src[c];
 }
 
+// ---- quotient polynomial: the gate-independent vanishing terms -------------------------------------------
+// [P2] plonk/prover.rs compute_quotient_polys + plonk/vanishing_poly.rs eval_vanishing_poly_base_batch
+// (step 6 of prove(), reached from /root/reference/src/vtfhe/ivc_based_vpbs.rs:302, :333, :364): on
+// the quotient domain x_i = 7 w_q^i, q = n << qdb, per challenge c
+//   Z(1) = 1 term      L_0(x) (Z_c(x) - 1),  L_0(x) = (x^n - 1) / (n (x - 1))
+//   partial products   accs = [Z_c(x), pp_c,0 .. pp_c,K-2, Z_c(g x)];
+//                      check_t = accs[t] prod_chunk (w_j + beta_c k_j x + gamma_c)
+//                              - accs[t+1] prod_chunk (w_j + beta_c sigma_j(x) + gamma_c)
+//   res_c = sum_j term_j alpha_c^j over [Z(1) terms of all challenges, checks of challenge 0, 1, ..]
+//           (+ alpha_c^(nc + nc K) times the alpha-reduced gate constraints, if the caller supplies them)
+//   value_c(i) = res_c / (x^n - 1).
+// The LDE rows come straight from the resident batches: the points of the quotient domain are the
+// first q leaves of the (bit-reversed) leaf matrices, leaf k <-> natural index bitrev_q(k), so thread
+// k reads row k of each matrix (a warp reads 32 consecutive rows) and the "next" row i + 2^qdb.
+struct QuotientParams {
+  u64 zh[32], zh_inv[32];           // x^n - 1 on the coset takes 2^qdb values; and their inverses
+  u64 beta[4], gamma[4];            // per challenge (at most 4)
+  u64 apow[4][4 + 4 * MAX_CHUNKS];  // alpha_c^j for j < nc + nc K
+  u64 agate[4];                     // alpha_c^(nc + nc K)
+  u64 n_canon;                      // n mod p
+};
+__global__ void __launch_bounds__(128)
+quotient_permutation_terms(const u64* __restrict__ wires, u32 wires_width, const u64* __restrict__ cs,
+                           u32 cs_width, u32 sigmas_first, const u64* __restrict__ zs, u32 zs_width,
+                           const u64* __restrict__ k_is, u32 num_routed, u32 max_degree, u32 K, u32 nc,
+                           unsigned log_q, unsigned qdb, const __grid_constant__ QuotientParams qp,
+                           ntt::Roots R, const u64* __restrict__ gate_terms, u64* __restrict__ vals) {
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 q = 1ULL << log_q;
+  if (k >= q) return;
+  const u64 i = log_q ? (__brevll(k) >> (64 - log_q)) : 0;
+  const u64 i_next = (i + (1ULL << qdb)) & (q - 1);
+  const u64 k_next = log_q ? (__brevll(i_next) >> (64 - log_q)) : 0;
+  const u64 x = gl::mul(gl::COSET_SHIFT, ntt::root_of<false>(R, log_q, i));
+  const u64* wrow = wires + k * wires_width;
+  const u64* srow = cs + k * cs_width + sigmas_first;
+  const u64* zrow = zs + k * zs_width;
+  const u64* znext = zs + k_next * zs_width;
+  const unsigned cosetk = (unsigned)(i & ((1u << qdb) - 1));
+  u64 res[4] = {0, 0, 0, 0};
+  // Z(1) = 1 terms
+  const u64 l0 = gl::mul(qp.zh[cosetk], inv_nonzero(gl::mul(qp.n_canon, gl::sub(x, 1))));
+  for (u32 c = 0; c < nc; c++) {
+    const u64 term = gl::mul(l0, gl::sub(__ldg(zrow + c), 1));
+    for (u32 d = 0; d < nc; d++) res[d] = gl::add(res[d], gl::mul(term, qp.apow[d][c]));
+  }
+  // partial-product checks, chunk by chunk (the wire / sigma values of a chunk serve every challenge)
+  for (u32 t = 0; t < K; t++) {
+    u64 num[4] = {1, 1, 1, 1}, den[4] = {1, 1, 1, 1};
+    const u32 j1 = (t + 1) * max_degree < num_routed ? (t + 1) * max_degree : num_routed;
+    for (u32 j = t * max_degree; j < j1; j++) {
+      const u64 wv = __ldg(wrow + j), sv = __ldg(srow + j);
+      const u64 kx = gl::mul(__ldg(k_is + j), x);
+      for (u32 c = 0; c < nc; c++) {
+        num[c] = gl::mul(num[c], gl::add(gl::add(wv, gl::mul(qp.beta[c], kx)), qp.gamma[c]));
+        den[c] = gl::mul(den[c], gl::add(gl::add(wv, gl::mul(qp.beta[c], sv)), qp.gamma[c]));
+      }
+    }
+    for (u32 c = 0; c < nc; c++) {
+      const u64 prev = t == 0 ? __ldg(zrow + c) : __ldg(zrow + nc + c * (K - 1) + (t - 1));
+      const u64 next = t == K - 1 ? __ldg(znext + c) : __ldg(zrow + nc + c * (K - 1) + t);
+      const u64 term = gl::sub(gl::mul(prev, num[c]), gl::mul(next, den[c]));
+      const u32 idx = nc + c * K + t;
+      for (u32 d = 0; d < nc; d++) res[d] = gl::add(res[d], gl::mul(term, qp.apow[d][idx]));
+    }
+  }
+  for (u32 c = 0; c < nc; c++) {
+    u64 r = res[c];
+    if (gate_terms) r = gl::add(r, gl::mul(qp.agate[c], gl::canon(__ldg(gate_terms + (u64)c * q + i))));
+    vals[(u64)c * q + i] = gl::mul(r, qp.zh_inv[cosetk]);
+  }
+}
+// coset_ifft's tail: coefficient j of every column times shift^-j
+__global__ void coset_unscale(u64* __restrict__ coeffs, u64 len, u32 ncols, u64 shift_inv) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len) return;
+  u64 s = 1, b = shift_inv;
+  for (u64 e = t; e; e >>= 1) {
+    if (e & 1) s = gl::mul(s, b);
+    b = gl::mul(b, b);
+  }
+  for (u32 c = 0; c < ncols; c++) coeffs[(u64)c * len + t] = gl::mul(coeffs[(u64)c * len + t], s);
+}
+
 }  // namespace perm

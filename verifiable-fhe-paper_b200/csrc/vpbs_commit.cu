@@ -2405,6 +2405,122 @@ int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas,
   return VPBS_OK;
 }
 
+// [P2] plonk/prover.rs compute_quotient_polys, gate-independent part (see perm::quotient_permutation_terms),
+// then per challenge coset_ifft + chunks of n, committed from coefficients as the quotient batch.
+int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
+                              vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
+                              uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
+                              const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
+                              const uint64_t* const* gate_terms, uint32_t rate_bits, uint32_t cap_height,
+                              uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {
+  if (!wires || !constants_sigmas || !zs_pp) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = wires->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (constants_sigmas->ctx != ctx || zs_pp->ctx != ctx)
+    return fail(ctx, VPBS_ERR_STATE, "batches of different contexts");
+  if (!k_is || !betas || !gammas || !alphas || !cap_out || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  *out = nullptr;
+  const u32 nc = num_challenges, log_n = wires->log_n, qdb = quotient_degree_bits;
+  if (nc == 0 || nc > 4) return fail(ctx, VPBS_ERR_ARG, "num_challenges must be 1..4");
+  if (num_routed == 0 || max_degree < 2) return fail(ctx, VPBS_ERR_ARG, "num_routed == 0 or max_degree < 2");
+  const u32 K = (num_routed + max_degree - 1) / max_degree;
+  if (K > (u32)perm::MAX_CHUNKS) return fail(ctx, VPBS_ERR_ARG, "too many partial-product chunks");
+  if (wires->ncols < num_routed || constants_sigmas->ncols < sigmas_first_col + num_routed || zs_pp->ncols != nc * K)
+    return fail(ctx, VPBS_ERR_ARG, "batch widths do not match num_routed / the chunk count");
+  if (constants_sigmas->log_n != log_n || zs_pp->log_n != log_n)
+    return fail(ctx, VPBS_ERR_ARG, "batches of different degree");
+  for (const vpbs_batch* b : {wires, constants_sigmas, zs_pp}) {
+    if (b->sharded()) return fail(ctx, VPBS_ERR_ARG, "the quotient needs unsharded batches");
+    if (qdb > b->rate_bits || qdb >= 5)
+      return fail(ctx, VPBS_ERR_ARG, "quotient_degree_bits exceeds the batches' rate_bits");
+  }
+  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  if (cap_height > log_n + rate_bits)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  const unsigned log_q = log_n + qdb;
+  const u64 n = 1ULL << log_n, q = 1ULL << log_q;
+  const uint64_t l0 = ctx->launches;
+  cudaEvent_t e0 = ctx->ev[4], e3 = ctx->ev[7];
+  if (stats) cudaEventRecord(e0, ctx->stream);
+
+  perm::QuotientParams qp;
+  memset(&qp, 0, sizeof qp);
+  const u64 g_pow_n = gl::pow(gl::COSET_SHIFT, n), wr = gl::primitive_root_of_unity(qdb);
+  u64 xr = 1;
+  for (u32 k = 0; k < (1u << qdb); k++, xr = gl::mul(xr, wr)) {
+    qp.zh[k] = gl::sub(gl::mul(g_pow_n, xr), 1);
+    qp.zh_inv[k] = gl::inv(qp.zh[k]);
+  }
+  const u32 nterms = nc + nc * K;
+  for (u32 c = 0; c < nc; c++) {
+    qp.beta[c] = gl::canon(betas[c]);
+    qp.gamma[c] = gl::canon(gammas[c]);
+    const u64 a = gl::canon(alphas[c]);
+    u64 pw = 1;
+    for (u32 j = 0; j < nterms; j++, pw = gl::mul(pw, a)) qp.apow[c][j] = pw;
+    qp.agate[c] = pw;
+  }
+  qp.n_canon = n % gl::P;
+
+  u64 *d_k = nullptr, *d_vals = nullptr, *d_gate = nullptr, *d_work = nullptr, *d_coef = nullptr;
+  if ((rc = arena_get(ctx, "idx", (size_t)num_routed * 8, (void**)&d_k))) return rc;
+  if ((rc = arena_get(ctx, "in", (size_t)nc * q * 8, (void**)&d_vals))) return rc;
+  if ((rc = arena_get(ctx, "work", (size_t)nc * q * 8, (void**)&d_work))) return rc;
+  if ((rc = arena_get(ctx, "zs_out", (size_t)nc * q * 8, (void**)&d_coef))) return rc;
+  if ((rc = ensure_roots(ctx, log_n + (rate_bits > qdb ? rate_bits : qdb)))) return rc;
+  std::vector<u64> kc(k_is, k_is + num_routed);
+  for (u64& v : kc) v = gl::canon(v);
+  CU(ctx, cudaMemcpyAsync(d_k, kc.data(), (size_t)num_routed * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (gate_terms) {
+    if ((rc = arena_get(ctx, "gate_terms", (size_t)nc * q * 8, (void**)&d_gate))) return rc;
+    for (u32 c = 0; c < nc; c++) {
+      if (!gate_terms[c]) return fail(ctx, VPBS_ERR_ARG, "gate_terms[c] == NULL");
+      CU(ctx, cudaMemcpyAsync(d_gate + (u64)c * q, gate_terms[c], q * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  const ntt::Roots R{ctx->roots, ctx->roots_log};
+  perm::quotient_permutation_terms<<<(unsigned)((q + 127) / 128), 128, 0, ctx->stream>>>(
+      wires->leaves, wires->width, constants_sigmas->leaves, constants_sigmas->width, sigmas_first_col,
+      zs_pp->leaves, zs_pp->width, d_k, num_routed, max_degree, K, nc, log_q, qdb, qp, R, d_gate, d_vals);
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  // `kc` must outlive its copy; the kernel above is ordered after it on the same stream
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  // coset_ifft(7): inverse transform (natural order in and out, scaled by 1/q), then 7^-j
+  if ((rc = run_transform<true>(ctx, d_vals, q, nc, log_q, d_work, Out::Natural, d_coef, q, 0, nullptr,
+                                gl::inv(q % gl::P))))
+    return rc;
+  perm::coset_unscale<<<(unsigned)((q + 255) / 256), 256, 0, ctx->stream>>>(d_coef, q, nc, gl::inv(gl::COSET_SHIFT));
+  ctx->launches++;
+  CU(ctx, cudaGetLastError());
+  // chunks of n coefficients are contiguous: nc * 2^qdb columns, committed from coefficients
+  const u32 ncols_out = nc << qdb;
+  vpbs_batch* b = nullptr;
+  if ((rc = batch_alloc(ctx, ncols_out, log_n, rate_bits, cap_height, false, true, &b))) return rc;
+  Timer tm{ctx, stats != nullptr};
+  rc = commit_core(ctx, d_coef, ncols_out, log_n, rate_bits, cap_height, 1, nullptr, b->first_leaf,
+                   b->nleaves, b->coeffs, b->leaves, b->digests, b->own_roots(), &tm);
+  if (rc) {
+    vpbs_batch_destroy(b);
+    return rc;
+  }
+  cudaError_t ce = cudaMemcpyAsync(cap_out, b->cap, b->cap_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (stats) cudaEventRecord(e3, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    vpbs_batch_destroy(b);
+    return fail(ctx, VPBS_ERR_CUDA, std::string("quotient batch commit: ") + cudaGetErrorString(ce));
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    fill_stats(stats, tm, ctx->launches - l0);
+    cudaEventElapsedTime(&stats->total_ms, e0, e3);
+  }
+  *out = b;
+  return VPBS_OK;
+}
+
 int vpbs_batch_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
                           uint32_t rate_bits, uint32_t cap_height, int inputs_are_coeffs,
                           uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {

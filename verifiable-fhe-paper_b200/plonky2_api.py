@@ -769,6 +769,38 @@ def commit_zs_partial_products(wires: ResidentPolynomialBatch, sigmas: Sigmas, b
                                    st.as_dict())
 
 
+def commit_quotient_polys(constants_sigmas: "ResidentPolynomialBatch", sigmas_first_col: int,
+                          wires: "ResidentPolynomialBatch", zs_pp: "ResidentPolynomialBatch", k_is,
+                          max_degree: int, quotient_degree_bits: int, betas, gammas, alphas,
+                          rate_bits: int, cap_height: int, gate_terms=None) -> "ResidentPolynomialBatch":
+    """prove() steps 6-7 on the device, gate-independent part ([P2] plonk/prover.rs
+    compute_quotient_polys / plonk/vanishing_poly.rs): the Z(1) = 1 terms and the partial-product
+    checks over the quotient domain, reduced with the alphas, divided by Z_H, coset_ifft, chunked and
+    committed (vpbs_batch_quotient_polys).  gate_terms: (num_challenges, n << quotient_degree_bits)
+    alpha-reduced gate constraints in natural order, or None."""
+    ctx = wires.ctx
+    k = _as_u64(k_is).reshape(-1)
+    b, g, a = (_as_u64(v).reshape(-1) for v in (betas, gammas, alphas))
+    if not (b.size == g.size == a.size) or b.size == 0:
+        raise ValueError("one beta, gamma and alpha per challenge")
+    gt_arr, gtp = None, None
+    if gate_terms is not None:
+        gt_arr = _as_u64(gate_terms)
+        if gt_arr.shape != (b.size, (1 << wires.degree_log) << quotient_degree_bits):
+            raise ValueError("gate_terms must be (num_challenges, n << quotient_degree_bits)")
+        gtp = (u64p * b.size)(*[_ptr(gt_arr[c]) for c in range(b.size)])
+    cap = np.empty((1 << cap_height, 4), np.uint64)
+    handle = ctypes.c_void_p()
+    st = VpbsStats()
+    ctx.check(ctx.lib.vpbs_batch_quotient_polys(constants_sigmas.handle, sigmas_first_col, wires.handle,
+                                                zs_pp.handle, _ptr(k), k.size, max_degree,
+                                                quotient_degree_bits, _ptr(b), _ptr(g), _ptr(a), b.size, gtp,
+                                                rate_bits, cap_height, _ptr(cap), ctypes.byref(handle),
+                                                ctypes.byref(st)))
+    return ResidentPolynomialBatch(ctx, handle, cap, b.size << quotient_degree_bits, wires.degree_log,
+                                   rate_bits, False, st.as_dict())
+
+
 # ----------------------------------------------------------------------------- device-resident
 def commit_device(ctx: Context, d_cols: int, ncols: int, log_n: int, rate_bits: int,
                   cap_height: int, inputs_are_coeffs: bool, d_coeffs: int, d_leaves: int,
