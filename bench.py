@@ -394,6 +394,10 @@ def main():
     ap.add_argument("--chain-eager", action="store_true",
                     help="with --chain-steps: also time round 1's eager form of the step (all outputs "
                          "of the first two commits downloaded)")
+    ap.add_argument("--chain-host-quotient", action="store_true",
+                    help="with --chain-steps: the quotient chunks arrive as 16 coefficient columns from the "
+                         "host (the form of the first half of round 2) instead of being computed on the "
+                         "device from the resident batches (vpbs_batch_quotient_polys)")
     ap.add_argument("--chain-shard", action="store_true",
                     help="with --chain-steps under torchrun: ONE chain for all ranks — every resident "
                          "batch of a step is sharded by row range over the GPUs (vpbs_ctx_set_shard), "
@@ -1058,7 +1062,10 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     nothing can be pipelined across steps.  Two forms of the step are timed:
       resident (the product path): everything of prove() this repository puts on the device —
         wires commit (135 value columns from the host) -> Z / partial products computed and committed
-        on the device (20) -> quotient-chunk commit (16 coefficient columns from the host) ->
+        on the device (20) -> quotient polynomials: permutation-argument terms on the device from the
+        resident batches' LDE rows + alpha-reduced gate constraints from the host, Z_H division, coset
+        IFFT, 16 chunks committed (--chain-host-quotient and the sharded chain: 16 coefficient columns
+        from the host instead) ->
         openings of all 256 polynomials of the four FRI oracles (the circuit's constants/sigmas batch,
         85 columns, is committed once and stays resident) at zeta / g zeta -> prove_openings
         (alpha-combination of the 256 + 2 polynomials, division by X - z, final-polynomial LDE) -> FRI commit phase (3 arity-16 layers: tree, cap to
@@ -1101,6 +1108,9 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     num_routed, max_degree = 80, 8
     sig = V.Sigmas(V.synthetic_columns(num_routed, n, 0x51630000), V.get_unique_coset_shifts(n, num_routed), ctx)
     g_n = pow(7, (P_GL - 1) >> log_n, P_GL)  # generator of the trace subgroup
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    gate_view = ins[2].reshape(2, 8 * n)      # alpha-reduced gate constraints on the quotient domain
+    gate_ptrs = (u64p * 2)(gate_view[0].ctypes.data_as(u64p), gate_view[1].ctypes.data_as(u64p))
 
     def challenge(cap, k, count):  # stand-in for challenger.get_n_challenges (see docstring)
         x = cap.reshape(-1).astype(np.uint64)
@@ -1111,6 +1121,7 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     # is the fourth FRI oracle: resident for the whole chain, opened and queried in every step
     CS = 85
     cs_cols = pinned((CS, n)); cs_cols[:] = V.synthetic_columns(CS, n, 0x5EED0000 + 85)
+    cs_cols[CS - num_routed:] = V.synthetic_columns(num_routed, n, 0x51630000)  # the sigma polynomials' values
     cs_cap = np.empty((ncap, 4), np.uint64)
     cs_ptrs = ptrs(cs_cols)
     cs = {"h": None}
@@ -1167,9 +1178,18 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         if sharded_now[0]:
             hs[2], full = sp.commit_from_host(ctx, ins[2], RATE_BITS, CAP_HEIGHT, True)
             caps[2][:] = full
-        else:
+        elif args.chain_host_quotient:
             ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, log_n, RATE_BITS, CAP_HEIGHT, 1, None,
                                             caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
+        else:
+            # compute_quotient_polys on the device: the permutation argument's vanishing terms from the
+            # resident batches' LDE rows, the gate constraints as alpha-reduced values from the host
+            # (the same 8 MiB the 16 coefficient columns were), Z_H division, coset IFFT, chunks, commit
+            al = challenge(caps[1], 7, 2)
+            ctx.check(lib.vpbs_batch_quotient_polys(
+                cs["h"], CS - num_routed, hs[0], hs[1], k_is.ctypes.data_as(u64p), num_routed, max_degree,
+                RATE_BITS, bg[:2].ctypes.data_as(u64p), bg[2:].ctypes.data_as(u64p), al.ctypes.data_as(u64p), 2,
+                gate_ptrs, None, None, RATE_BITS, CAP_HEIGHT, caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
         t = lap("quotient_commit", t)
         zeta = challenge(caps[2], 2, 2)
         gz = np.array([int(zeta[0]) * g_n % P_GL, int(zeta[1]) * g_n % P_GL], np.uint64)

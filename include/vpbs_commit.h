@@ -411,12 +411,34 @@ int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas,
  *                     partial products of challenge 0, 1, ..)
  *   k_is:             num_routed coset shifts (host)
  * All three batches must be unsharded and have rate_bits >= quotient_degree_bits; at most 4
- * challenges. */
+ * challenges.
+ *
+ * Instead of gate_terms the gate constraints can be evaluated ON THE DEVICE from a program
+ * ([P2] plonk/vanishing_poly.rs evaluate_gate_constraints_base_batch as data): the host compiles,
+ * once per circuit, every gate's eval_unfiltered_base and its selector filter into straight-line
+ * code over the local wires, the local constants (columns of the constants/sigmas batch) and
+ * public_inputs_hash; the device runs it at every point of the quotient domain, so no LDE row
+ * crosses PCIe.  One 64-bit word per instruction:
+ *     bits 0-7 op | 8-15 dst register | 16-19 kind(a) | 20-23 kind(b) | 24-39 index(a) | 40-55 index(b)
+ *     op   0 ADD, 1 SUB, 2 MUL: dst <- a op b;  3 EMIT: constraint number index(b) of the current
+ *          gate has value a;  4 ENDGATE: the current gate's constraints, times the filter value a,
+ *          are added to the totals (constraint j counts alpha_c^j, as reduce_with_powers does)
+ *     kind 0 register, 1 wire column, 2 column of the constants/sigmas batch, 3 immediate table
+ *          entry, 4 public_inputs_hash element
+ * nregs <= 224 registers (shared memory), num_constraints = the circuit's num_gate_constraints. */
+typedef struct vpbs_gate_program vpbs_gate_program;
+int vpbs_gate_program_upload(vpbs_ctx* ctx, const uint64_t* code, uint32_t ncode, const uint64_t* imms,
+                             uint32_t nimm, uint32_t nregs, uint32_t num_constraints,
+                             vpbs_gate_program** out);
+void vpbs_gate_program_destroy(vpbs_gate_program* program);
+/* gate_terms and program are mutually exclusive (either or both NULL); public_inputs_hash: 4
+ * elements (NULL: zeros), read by programs only. */
 int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
                               vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
                               uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
                               const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
-                              const uint64_t* const* gate_terms, uint32_t rate_bits, uint32_t cap_height,
+                              const uint64_t* const* gate_terms, const vpbs_gate_program* program,
+                              const uint64_t* public_inputs_hash, uint32_t rate_bits, uint32_t cap_height,
                               uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats);
 
 #ifdef __cplusplus

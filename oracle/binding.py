@@ -80,6 +80,9 @@ def lib() -> ctypes.CDLL:
         L.orc_quotient_polys.restype = ctypes.c_int
         L.orc_quotient_polys.argtypes = [_u64pp, _u64pp, _u64pp, _u64p, u32, u32, u32, u32, _u64p, _u64p,
                                          _u64p, u32, _u64pp, _u64p]
+        L.orc_gate_program_eval.restype = ctypes.c_int
+        L.orc_gate_program_eval.argtypes = [_u64p, u32, _u64p, u32, u32, u32, _u64pp, u32, _u64pp, u32, u32, u32,
+                                            _u64p, _u64p, u32, _u64pp]
         L.orc_set_simd.argtypes = [ctypes.c_int]
         L.orc_get_simd.restype = ctypes.c_int
         L.orc_poseidon_batch.argtypes = [_u64p, u64]
@@ -289,6 +292,23 @@ def quotient_polys(wire_coeffs, sigma_coeffs, zs_pp_coeffs, k_is, max_degree, qd
                                   _p(b), _p(g), _p(a), nc, gt, _p(out))
     if rc != 0:
         raise ValueError("bad arguments")
+    return out
+
+
+def gate_program_eval(code, imms, nregs, num_constraints, wire_coeffs, cs_coeffs, qdb, pih, alphas):
+    """[P2] evaluate_gate_constraints_base_batch for gates given as a program: (nc, n << qdb)
+    alpha-reduced gate constraints over the quotient domain (natural order)."""
+    c, im = _arr(code).reshape(-1), _arr(imms).reshape(-1)
+    w, s, a = _arr(wire_coeffs), _arr(cs_coeffs), _arr(alphas).reshape(-1)
+    ph = _arr(pih if pih is not None else [0, 0, 0, 0]).reshape(4)
+    n = w.shape[1]
+    out = np.zeros((a.size, n << qdb), np.uint64)
+    ptrs = lambda m: (_u64p * m.shape[0])(*[_p(m[j]) for j in range(m.shape[0])])
+    rc = lib().orc_gate_program_eval(_p(c) if c.size else None, c.size, _p(im) if im.size else None, im.size,
+                                     nregs, num_constraints, ptrs(w), w.shape[0], ptrs(s), s.shape[0],
+                                     _log2(n), qdb, _p(ph), _p(a), a.size, ptrs(out))
+    if rc != 0:
+        raise ValueError("bad program")
     return out
 
 

@@ -364,3 +364,36 @@ def quotient_polys(wire_coeffs, sigma_coeffs, zs_pp_coeffs, k_is, max_degree, qd
                   for j in range(q)]
         out += [coeffs[t * n:(t + 1) * n] for t in range(1 << qdb)]
     return out
+
+
+def gate_program_eval(code, imms, num_constraints, wire_coeffs, cs_coeffs, qdb, pih, alphas):
+    """The gate-constraint program (format: include/vpbs_commit.h) interpreted from its definition: every
+    wire / constant operand is the polynomial evaluated by Horner at x = 7 w_q^i.  Returns
+    [[alpha_c-reduced gate constraints at point i] for c]."""
+    n = len(wire_coeffs[0])
+    q = n << qdb
+    wq = primitive_root_of_unity(q.bit_length() - 1)
+    out = [[0] * q for _ in alphas]
+    for i in range(q):
+        x = 7 * pow(wq, i, P) % P
+        regs, total, gacc = {}, [0] * len(alphas), [0] * len(alphas)
+
+        def val(kind, idx):
+            return (regs[idx] if kind == 0 else evaluate(wire_coeffs[idx], x) if kind == 1 else
+                    evaluate(cs_coeffs[idx], x) if kind == 2 else imms[idx] % P if kind == 3 else pih[idx] % P)
+        for ins in code:
+            op, dst = ins & 0xff, (ins >> 8) & 0xff
+            a = val((ins >> 16) & 0xf, (ins >> 24) & 0xffff)
+            if op <= 2:
+                b = val((ins >> 20) & 0xf, (ins >> 40) & 0xffff)
+                regs[dst] = (a + b) % P if op == 0 else (a - b) % P if op == 1 else a * b % P
+            elif op == 3:
+                j = (ins >> 40) & 0xffff
+                assert j < num_constraints
+                gacc = [(g + a * pow(al, j, P)) % P for g, al in zip(gacc, alphas)]
+            else:
+                total = [(t + g * a) % P for t, g in zip(total, gacc)]
+                gacc = [0] * len(alphas)
+        for c in range(len(alphas)):
+            out[c][i] = total[c]
+    return out

@@ -940,3 +940,69 @@ int orc_quotient_polys(const uint64_t* const* wires, const uint64_t* const* sigm
   free(xs);
   return 0;
 }
+
+/* ---- [P2] plonk/vanishing_poly.rs evaluate_gate_constraints_base_batch as a program ------------------
+ * The gate constraints of a circuit given as straight-line code (instruction format: include/
+ * vpbs_commit.h, vpbs_gate_program_upload), interpreted at every point x_i = 7 w_q^i of the quotient
+ * domain over the LDE values of ALL wire columns and ALL columns of the constants/sigmas batch
+ * (coefficient columns in).  out[c][i] = sum_j alpha_c^j sum_gates filter_g c_{g,j}: the gate_terms
+ * argument of orc_quotient_polys. */
+int orc_gate_program_eval(const uint64_t* code, uint32_t ncode, const uint64_t* imms, uint32_t nimm,
+                          uint32_t nregs, uint32_t num_constraints, const uint64_t* const* wires,
+                          uint32_t nwires, const uint64_t* const* cs, uint32_t ncs, uint32_t log_n,
+                          uint32_t qdb, const uint64_t pih[4], const uint64_t* alphas, uint32_t nc,
+                          uint64_t* const* out) {
+  if ((!code && ncode) || !wires || !cs || !alphas || !out || nregs == 0 || nc == 0 || nc > 4 || log_n + qdb > 30)
+    return -1;
+  const uint64_t n = 1ULL << log_n, q = n << qdb;
+  uint64_t** lw = malloc(sizeof(uint64_t*) * (nwires + ncs));
+  for (uint32_t j = 0; j < nwires + ncs; j++) {
+    lw[j] = malloc(q * sizeof(uint64_t));
+    orc_lde(j < nwires ? wires[j] : cs[j - nwires], log_n, qdb, lw[j]);
+  }
+  uint64_t* apow = malloc((size_t)nc * num_constraints * sizeof(uint64_t));
+  for (uint32_t c = 0; c < nc; c++) {
+    uint64_t pw = 1;
+    for (uint32_t j = 0; j < num_constraints; j++, pw = mul_(pw, canon(alphas[c]))) apow[(size_t)c * num_constraints + j] = pw;
+  }
+  int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(orc_get_threads()) reduction(| : bad)
+  for (uint64_t i = 0; i < q; i++) {
+    uint64_t regs[256];
+    uint64_t total[4] = {0, 0, 0, 0}, gacc[4] = {0, 0, 0, 0};
+    for (uint32_t pc = 0; pc < ncode; pc++) {
+      const uint64_t ins = code[pc];
+      const unsigned op = ins & 0xff, dst = (ins >> 8) & 0xff;
+      const unsigned kind[2] = {(unsigned)((ins >> 16) & 0xf), (unsigned)((ins >> 20) & 0xf)};
+      const unsigned idx[2] = {(unsigned)((ins >> 24) & 0xffff), (unsigned)((ins >> 40) & 0xffff)};
+      uint64_t v[2] = {0, 0};
+      for (int o = 0; o < (op <= 2 ? 2 : 1); o++) {
+        switch (kind[o]) {
+          case 0: v[o] = idx[o] < 256 ? regs[idx[o]] : (bad |= 1, 0); break;
+          case 1: v[o] = idx[o] < nwires ? lw[idx[o]][i] : (bad |= 1, 0); break;
+          case 2: v[o] = idx[o] < ncs ? lw[nwires + idx[o]][i] : (bad |= 1, 0); break;
+          case 3: v[o] = idx[o] < nimm ? canon(imms[idx[o]]) : (bad |= 1, 0); break;
+          case 4: v[o] = pih ? canon(pih[idx[o] & 3]) : 0; break;
+          default: bad |= 1;
+        }
+      }
+      if (op == 0) regs[dst] = add_(v[0], v[1]);
+      else if (op == 1) regs[dst] = sub_(v[0], v[1]);
+      else if (op == 2) regs[dst] = mul_(v[0], v[1]);
+      else if (op == 3) {
+        if (idx[1] >= num_constraints) { bad |= 1; continue; }
+        for (uint32_t c = 0; c < nc; c++) gacc[c] = add_(gacc[c], mul_(v[0], apow[(size_t)c * num_constraints + idx[1]]));
+      } else if (op == 4) {
+        for (uint32_t c = 0; c < nc; c++) {
+          total[c] = add_(total[c], mul_(gacc[c], v[0]));
+          gacc[c] = 0;
+        }
+      } else bad |= 1;
+    }
+    for (uint32_t c = 0; c < nc; c++) out[c][i] = total[c];
+  }
+  for (uint32_t j = 0; j < nwires + ncs; j++) free(lw[j]);
+  free(lw);
+  free(apow);
+  return bad ? -1 : 0;
+}

@@ -139,6 +139,15 @@ int orc_quotient_polys(const uint64_t* const* wires, const uint64_t* const* sigm
                        const uint64_t* gammas, const uint64_t* alphas, uint32_t nc,
                        const uint64_t* const* gate_terms, uint64_t* out);
 
+/* [P2] evaluate_gate_constraints_base_batch with the gates given as a program (format:
+ * include/vpbs_commit.h): out[c][i] = alpha_c-reduced gate constraints at point i of the quotient
+ * domain, from the coefficient columns of all wires and of the constants/sigmas batch. */
+int orc_gate_program_eval(const uint64_t* code, uint32_t ncode, const uint64_t* imms, uint32_t nimm,
+                          uint32_t nregs, uint32_t num_constraints, const uint64_t* const* wires,
+                          uint32_t nwires, const uint64_t* const* cs, uint32_t ncs, uint32_t log_n,
+                          uint32_t qdb, const uint64_t pih[4], const uint64_t* alphas, uint32_t nc,
+                          uint64_t* const* out);
+
 /* SIMD width of the hashing path: 0 = widest the CPU supports (default), 1 = scalar — the naive
  * restatement, which is the checker for the other two — 4 = AVX2, 8 = AVX-512.  The SIMD paths
  * evaluate the SAME permutation on 4 / 8 independent leaves or tree nodes per call

@@ -28,6 +28,11 @@ pub struct vpbs_fri {
 }
 
 #[repr(C)]
+pub struct vpbs_gate_program {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
 #[derive(Default, Debug, Clone, Copy)]
 pub struct vpbs_stats {
     pub h2d_ms: f32,
@@ -159,9 +164,14 @@ extern "C" {
                                      wires: *mut vpbs_batch, zs_pp: *mut vpbs_batch, k_is: *const u64,
                                      num_routed: u32, max_degree: u32, quotient_degree_bits: u32,
                                      betas: *const u64, gammas: *const u64, alphas: *const u64,
-                                     num_challenges: u32, gate_terms: *const *const u64, rate_bits: u32,
-                                     cap_height: u32, cap_out: *mut u64, out: *mut *mut vpbs_batch,
-                                     stats: *mut vpbs_stats) -> c_int;
+                                     num_challenges: u32, gate_terms: *const *const u64,
+                                     program: *const vpbs_gate_program, public_inputs_hash: *const u64,
+                                     rate_bits: u32, cap_height: u32, cap_out: *mut u64,
+                                     out: *mut *mut vpbs_batch, stats: *mut vpbs_stats) -> c_int;
+    pub fn vpbs_gate_program_upload(ctx: *mut vpbs_ctx, code: *const u64, ncode: u32, imms: *const u64,
+                                    nimm: u32, nregs: u32, num_constraints: u32,
+                                    out: *mut *mut vpbs_gate_program) -> c_int;
+    pub fn vpbs_gate_program_destroy(program: *mut vpbs_gate_program);
     pub fn vpbs_batch_shard(batch: *mut vpbs_batch, first_leaf: *mut u64, nleaves: *mut u64) -> c_int;
     pub fn vpbs_batches_eval_ext2(batches: *const *mut vpbs_batch, nbatches: u32, points: *const u64,
                                   npoints: u32, outs: *const *mut u64) -> c_int;

@@ -1062,6 +1062,144 @@ def test_quotient_polys_against_oracle(V, ctx, oracle, log_n, ncols, num_routed,
     sg.close()
 
 
+@pytest.mark.parametrize("log_n,ncols,ncs,qdb", [(6, 12, 12, 2), (10, 40, 30, 3)])
+def test_gate_program_against_oracle(V, ctx, oracle, log_n, ncols, ncs, qdb):
+    """Gate constraints as a program evaluated on the device (vpbs_gate_program_upload +
+    vpbs_batch_quotient_polys): random straight-line programs over wires, constants, immediates and
+    public_inputs_hash; the committed quotient chunks equal the oracle's, whose gate terms come from the
+    oracle's own interpreter."""
+    from test_oracle_golden import _random_gate_program
+    rng = np.random.default_rng(5 * log_n + ncols)
+    n, num_routed, deg = 1 << log_n, 8, 4
+    wires, cs = rand_u64(rng, (ncols, n)), rand_u64(rng, (ncs, n))
+    first_sigma = ncs - num_routed
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    betas, gammas, alphas = (rand_u64(rng, 2, edge_frac=0) for _ in range(3))
+    pih = rand_u64(rng, 4)
+    wb = V.commit_resident(wires, 3, False, 4, ctx=ctx)
+    cb = V.commit_resident(cs, 3, False, 4, ctx=ctx)
+    sg = V.Sigmas(cs[first_sigma:], k_is, ctx)
+    zb = V.commit_zs_partial_products(wb, sg, betas, gammas, deg, 3, 4)
+    wc, cc, zc = wb.download().polynomials, cb.download().polynomials, zb.download().polynomials
+    bld = _random_gate_program(V, rng, ncols, ncs, ngates=4, nops=60, nconstraints=9)
+    prog = bld.build(ctx)
+    qb = V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4,
+                                 program=prog, public_inputs_hash=pih)
+    gt = oracle.gate_program_eval(bld.code, bld.imms, bld.nregs, bld.num_constraints, wc, cc, qdb, pih, alphas)
+    want = oracle.quotient_polys(wc[:num_routed], cc[first_sigma:], zc, k_is, deg, qdb, betas, gammas, alphas, gt)
+    assert np.array_equal(qb.download().polynomials, want)
+    assert np.array_equal(qb.merkle_tree.cap, oracle.commit(want, 3, 4, True)["cap"])
+    with pytest.raises(ValueError):          # gate_terms and a program at once
+        V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4,
+                                gate_terms=gt, program=prog)
+    bad = V.GateProgramBuilder()
+    bad.emit(0, bad.wire(ncols))             # a wire column the batch does not have
+    bad.end_gate(bad.imm(1))
+    bp = bad.build(ctx)
+    with pytest.raises(ValueError):
+        V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4, program=bp)
+    with pytest.raises(ValueError):          # register index beyond nregs
+        V.GateProgram(np.array([0 | 5 << 8], np.uint64), np.zeros(0, np.uint64), 2, 1, ctx)
+    for b in (wb, cb, zb, qb):
+        b.close()
+    sg.close(); prog.close(); bp.close()
+
+
+def test_quotient_polys_plonk_identity_with_gate_program(V, ctx):
+    """A valid mini-circuit proved end to end on the device side: three gate types selected per row by a
+    selector polynomial (arithmetic: out = c0 m0 m1 + c1 add, twice per row; constant: wire_k = const_k;
+    public input: wires 0..3 = public_inputs_hash) with plonky2's filter prod_{i != g}(i - s), copy
+    constraints among equal cells, Z / partial products, and the quotient computed from the gate
+    program + the permutation terms.  At a random zeta:
+        sum_j alpha^j term_j(zeta) = (zeta^n - 1) sum_k zeta^(n k) t_k(zeta)."""
+    from oracle import model as M
+    rng = np.random.default_rng(11)
+    log_n, num_routed, deg, qdb = 7, 8, 4, 3
+    n, K = 1 << log_n, 2
+    ri = lambda: int(rng.integers(0, P, dtype=np.uint64))
+    pih = [ri() for _ in range(4)]
+    sel = rng.integers(0, 3, size=n)
+    c0, c1 = [ri() for _ in range(n)], [ri() for _ in range(n)]
+    wires = [[ri() for _ in range(n)] for _ in range(num_routed)]
+    for i in range(n):
+        if sel[i] == 0:                                   # ArithmeticGate, 2 operations
+            for o in range(2):
+                m0, m1, ad = wires[4 * o][i], wires[4 * o + 1][i], wires[4 * o + 2][i]
+                wires[4 * o + 3][i] = (c0[i] * m0 * m1 + c1[i] * ad) % P
+        elif sel[i] == 1:                                 # ConstantGate, 2 constants
+            c0[i] = 5
+            wires[0][i], wires[1][i] = c0[i], c1[i]
+        else:                                             # PublicInputGate
+            for k in range(4):
+                wires[k][i] = pih[k]
+    # copy constraints: all wire-0 cells of the constant rows hold 5 -> one cycle; the public-input
+    # cells of column 2 hold pih[2] -> another; everything else is a fixed point
+    w = pow(7, (P - 1) >> log_n, P)
+    sub = [pow(w, i, P) for i in range(n)]
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    sig = [[int(k_is[j]) * sub[i] % P for i in range(n)] for j in range(num_routed)]
+    for col, rows in ((0, [i for i in range(n) if sel[i] == 1]), (2, [i for i in range(n) if sel[i] == 2])):
+        for a, b_ in zip(rows, rows[1:] + rows[:1]):
+            sig[col][a] = int(k_is[col]) * sub[b_] % P
+    wires_np = np.array(wires, dtype=np.uint64)
+    cs_np = np.array([list(map(int, sel)), c0, c1] + sig, dtype=np.uint64)
+    betas, gammas, alphas = (rng.integers(1, P, size=2, dtype=np.uint64) for _ in range(3))
+    wb = V.commit_resident(wires_np, 3, False, 4, ctx=ctx)
+    cb = V.commit_resident(cs_np, 3, False, 4, ctx=ctx)
+    sg = V.Sigmas(cs_np[3:], k_is, ctx)
+    zb = V.commit_zs_partial_products(wb, sg, betas, gammas, deg, 3, 4)
+    b = V.GateProgramBuilder()
+    for o in range(2):                                    # gate 0
+        prod = b.mul(b.mul(b.wire(4 * o), b.wire(4 * o + 1)), b.const(1))
+        b.emit(o, b.sub(b.wire(4 * o + 3), b.add(prod, b.mul(b.wire(4 * o + 2), b.const(2)))))
+    b.end_gate(b.selector_filter(0, 0, range(3), False))
+    for k in range(2):                                    # gate 1
+        b.emit(k, b.sub(b.wire(k), b.const(1 + k)))
+    b.end_gate(b.selector_filter(0, 1, range(3), False))
+    for k in range(4):                                    # gate 2
+        b.emit(k, b.sub(b.wire(k), b.pih(k)))
+    b.end_gate(b.selector_filter(0, 2, range(3), False))
+    prog = b.build(ctx)
+    qb = V.commit_quotient_polys(cb, 3, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4, program=prog,
+                                 public_inputs_hash=np.array(pih, dtype=np.uint64))
+    t = qb.download().polynomials
+    wc, cc, zc = wb.download().polynomials, cb.download().polynomials, zb.download().polynomials
+    assert int(zc[0][0]) != 1 or zc[0][1:].any()          # Z is not the constant 1: the cycles are real
+    ev = lambda coeffs, x: M.evaluate([int(v) for v in coeffs], x)
+    zeta = int(rng.integers(2, P, dtype=np.uint64))
+    gz = w * zeta % P
+    wz, cz, zz = [ev(c, zeta) for c in wc], [ev(c, zeta) for c in cc], [ev(c, zeta) for c in zc]
+    zg = [ev(zc[c], gz) for c in range(2)]
+    zh = (pow(zeta, n, P) - 1) % P
+    l0 = zh * pow(n * (zeta - 1) % P, P - 2, P) % P
+    terms = [l0 * (zz[c] - 1) % P for c in range(2)]
+    for c in range(2):
+        accs = [zz[c]] + [zz[2 + c * (K - 1) + k] for k in range(K - 1)] + [zg[c]]
+        for k in range(K):
+            num = den = 1
+            for j in range(k * deg, (k + 1) * deg):
+                num = num * (wz[j] + int(betas[c]) * int(k_is[j]) * zeta + int(gammas[c])) % P
+                den = den * (wz[j] + int(betas[c]) * cz[3 + j] + int(gammas[c])) % P
+            terms.append((accs[k] * num - accs[k + 1] * den) % P)
+    s = cz[0]
+    filt = [(1 - s) * (2 - s) % P, (0 - s) * (2 - s) % P, (0 - s) * (1 - s) % P]
+    gate_c = [0] * 4
+    for o in range(2):
+        gate_c[o] += filt[0] * (wz[4 * o + 3] - (cz[1] * wz[4 * o] * wz[4 * o + 1] + cz[2] * wz[4 * o + 2]))
+    for k in range(2):
+        gate_c[k] += filt[1] * (wz[k] - cz[1 + k])
+    for k in range(4):
+        gate_c[k] += filt[2] * (wz[k] - pih[k])
+    terms += [g % P for g in gate_c]
+    for c in range(2):
+        lhs = sum(tm * pow(int(alphas[c]), j, P) for j, tm in enumerate(terms)) % P
+        rhs = zh * sum(pow(zeta, n * k, P) * ev(t[(c << qdb) + k], zeta) for k in range(1 << qdb)) % P
+        assert lhs == rhs
+    for x in (wb, cb, zb, qb):
+        x.close()
+    sg.close(); prog.close()
+
+
 def test_quotient_polys_plonk_identity(V, ctx):
     """The property the quotient exists for, on a VALID instance: routed wires that satisfy a
     copy-constraint permutation and an arithmetic gate w3 = c0 w0 w1 + c1 w2 on four further columns.

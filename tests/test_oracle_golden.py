@@ -387,3 +387,37 @@ def test_quotient_polys_oracle_equals_model(oracle, log_n, nr, deg, qdb, nc):
                                 [int(x) for x in b], [int(x) for x in g], [int(x) for x in a],
                                 None if gate is None else ints(gate))
         assert np.array_equal(got, np.array(want, dtype=np.uint64))
+
+
+def _random_gate_program(V, rng, nwires, ncs, ngates=3, nops=25, nconstraints=5):
+    b = V.GateProgramBuilder()
+    for _ in range(ngates):
+        pool = [b.wire(int(rng.integers(nwires))) for _ in range(4)] + [b.const(int(rng.integers(ncs))),
+                b.imm(int(rng.integers(0, 2**63))), b.pih(int(rng.integers(4)))]
+        for _ in range(nops):
+            x, y = (pool[int(rng.integers(len(pool)))] for _ in range(2))
+            pool.append([b.add, b.sub, b.mul][int(rng.integers(3))](x, y))
+        for j in rng.permutation(nconstraints)[: int(rng.integers(1, nconstraints + 1))]:
+            b.emit(int(j), pool[int(rng.integers(len(pool)))])
+        b.end_gate(pool[int(rng.integers(len(pool)))])
+    return b
+
+
+def test_gate_program_oracle_equals_model(oracle, V):
+    """The gate-constraint program interpreter: C restatement (LDE based) against the big-integer model
+    (Horner evaluation of every operand), on random programs — no device involved (the builder is pure
+    host code)."""
+    from oracle import model as M
+    rng = np.random.default_rng(3)
+    log_n, qdb, nwires, ncs = 3, 2, 6, 3
+    n = 1 << log_n
+    wires = rng.integers(0, M.P, size=(nwires, n), dtype=np.uint64)
+    cs = rng.integers(0, M.P, size=(ncs, n), dtype=np.uint64)
+    pih = rng.integers(0, M.P, size=4, dtype=np.uint64)
+    alphas = rng.integers(0, M.P, size=2, dtype=np.uint64)
+    b = _random_gate_program(V, rng, nwires, ncs)
+    got = oracle.gate_program_eval(b.code, b.imms, b.nregs, b.num_constraints, wires, cs, qdb, pih, alphas)
+    ints = lambda m: [[int(x) for x in r] for r in m]
+    want = M.gate_program_eval(b.code, b.imms, b.num_constraints, ints(wires), ints(cs), qdb,
+                               [int(x) for x in pih], [int(x) for x in alphas])
+    assert np.array_equal(got, np.array(want, dtype=np.uint64))

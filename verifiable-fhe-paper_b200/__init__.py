@@ -7,7 +7,7 @@ The directory name is not a Python identifier; import it through the root module
 from . import _lib, build, sharding  # noqa: F401
 from ._lib import VpbsError, VpbsStats  # noqa: F401
 from .plonky2_api import (  # noqa: F401
-    COSET_SHIFT, P, SALT_SIZE, Context, FriCommitPhase, MerkleProof, MerkleTree, PolynomialBatch,
+    COSET_SHIFT, P, SALT_SIZE, Context, FriCommitPhase, GateProgram, GateProgramBuilder, MerkleProof, MerkleTree, PolynomialBatch,
     ResidentMerkleTree, ResidentPolynomialBatch, Sigmas, all_wires_permutation_partial_products,
     commit_quotient_polys, commit_resident, commit_resident_device, commit_zs_partial_products, coset_fft,
     get_unique_coset_shifts,

@@ -111,8 +111,12 @@ SIGNATURES = {
     "vpbs_batch_shape": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint32)] * 5),
     "vpbs_batch_quotient_polys": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, u64p,
                                              _c.c_uint32, _c.c_uint32, _c.c_uint32, u64p, u64p, u64p,
-                                             _c.c_uint32, _c.POINTER(u64p), _c.c_uint32, _c.c_uint32, u64p,
-                                             _c.POINTER(_c.c_void_p), _c.POINTER(VpbsStats)]),
+                                             _c.c_uint32, _c.POINTER(u64p), _c.c_void_p, u64p, _c.c_uint32,
+                                             _c.c_uint32, u64p, _c.POINTER(_c.c_void_p),
+                                             _c.POINTER(VpbsStats)]),
+    "vpbs_gate_program_upload": (_c.c_int, [_ctx, u64p, _c.c_uint32, u64p, _c.c_uint32, _c.c_uint32,
+                                            _c.c_uint32, _c.POINTER(_c.c_void_p)]),
+    "vpbs_gate_program_destroy": (None, [_c.c_void_p]),
     "vpbs_batch_shard": (_c.c_int, [_c.c_void_p] + [_c.POINTER(_c.c_uint64)] * 2),
     "vpbs_batches_eval_ext2": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_uint32, u64p, _c.c_uint32,
                                           _c.POINTER(u64p)]),

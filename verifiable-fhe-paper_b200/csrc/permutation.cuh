@@ -245,8 +245,10 @@ quotient_permutation_terms(const u64* __restrict__ wires, u32 wires_width, const
       const u64 wv = __ldg(wrow + j), sv = __ldg(srow + j);
       const u64 kx = gl::mul(__ldg(k_is + j), x);
       for (u32 c = 0; c < nc; c++) {
-        num[c] = gl::mul(num[c], gl::add(gl::add(wv, gl::mul(qp.beta[c], kx)), qp.gamma[c]));
-        den[c] = gl::mul(den[c], gl::add(gl::add(wv, gl::mul(qp.beta[c], sv)), qp.gamma[c]));
+        // wire + beta s + gamma in one 128-bit multiply-add (exact, reduced once); the running
+        // products stay arbitrary u64 representatives until the chunk is complete
+        num[c] = gl::mul_lazy(num[c], ntt::mul_add2_lazy(qp.beta[c], kx, wv, qp.gamma[c]));
+        den[c] = gl::mul_lazy(den[c], ntt::mul_add2_lazy(qp.beta[c], sv, wv, qp.gamma[c]));
       }
     }
     for (u32 c = 0; c < nc; c++) {
@@ -263,6 +265,76 @@ quotient_permutation_terms(const u64* __restrict__ wires, u32 wires_width, const
     vals[(u64)c * q + i] = gl::mul(r, qp.zh_inv[cosetk]);
   }
 }
+// ---- gate constraints as a straight-line program -----------------------------------------------------------
+// [P2] plonk/vanishing_poly.rs evaluate_gate_constraints_base_batch: constraint_j(x) = sum over the
+// gates of filter_g(selectors(x)) * gate_g.eval_unfiltered_base(local_constants(x), local_wires(x),
+// public_inputs_hash)_j.  The gates' constraint polynomials are plonky2 source (gates/*.rs) that this
+// repository does not restate; they reach the device as DATA: a program the host compiles once per
+// circuit from the gates' own evaluation code, executed here at every point of the
+// quotient domain.  One 64-bit word per instruction:
+//     bits 0-7 op | 8-15 dst register | 16-19 kind of a | 20-23 kind of b | 24-39 index of a | 40-55 index of b
+//     op:   0 ADD  1 SUB  2 MUL   dst <- a op b
+//           3 EMIT     the current gate's constraint number (index of b) has value a
+//           4 ENDGATE  the gate's constraints, times the filter value a, are added to the totals
+//     kind: 0 register  1 wire column  2 column of the constants/sigmas batch (selectors and
+//           constants)  3 entry of the immediate table  4 public_inputs_hash element
+// Constraint j enters the total of challenge c times alpha_c^j (reduce_with_powers), so per gate the
+// kernel keeps sum_j alpha_c^j c_j and multiplies it by the filter at ENDGATE: exactly
+// sum_j alpha_c^j sum_g filter_g c_{g,j}.  Registers live in shared memory ([register][thread]).
+constexpr int PROG_THREADS = 128;
+enum : unsigned { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_EMIT = 3, OP_ENDGATE = 4 };
+enum : unsigned { K_REG = 0, K_WIRE = 1, K_CONST = 2, K_IMM = 3, K_PIH = 4 };
+struct PihAlphas {
+  u64 pih[4];
+};
+__global__ void __launch_bounds__(PROG_THREADS)
+gate_program_eval(const u64* __restrict__ code, u32 ncode, const u64* __restrict__ imm,
+                  const u64* __restrict__ apow /* nc x num_constraints: alpha_c^j */, u32 num_constraints,
+                  const u64* __restrict__ wires, u32 wires_width, const u64* __restrict__ cs, u32 cs_width,
+                  u32 nc, unsigned log_q, const __grid_constant__ PihAlphas pa, u64* __restrict__ out) {
+  extern __shared__ u64 regs[];  // [register][thread]
+  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 q = 1ULL << log_q;
+  const bool live = k < q;
+  const u64 kk = live ? k : 0;
+  const u64 i = log_q ? (__brevll(kk) >> (64 - log_q)) : 0;
+  const u64* wrow = wires + kk * wires_width;
+  const u64* crow = cs + kk * cs_width;
+  const unsigned tid = threadIdx.x;
+  u64 total[4] = {0, 0, 0, 0}, gacc[4] = {0, 0, 0, 0};
+  auto fetch = [&](unsigned kind, unsigned idx) -> u64 {
+    switch (kind) {
+      case K_REG: return regs[idx * PROG_THREADS + tid];
+      case K_WIRE: return __ldg(wrow + idx);
+      case K_CONST: return __ldg(crow + idx);
+      case K_IMM: return __ldg(imm + idx);
+      default: return pa.pih[idx & 3];
+    }
+  };
+  for (u32 pc = 0; pc < ncode; pc++) {
+    const u64 ins = __ldg(code + pc);
+    const unsigned op = (unsigned)(ins & 0xff), dst = (unsigned)((ins >> 8) & 0xff);
+    const unsigned ka = (unsigned)((ins >> 16) & 0xf), kb = (unsigned)((ins >> 20) & 0xf);
+    const unsigned ia = (unsigned)((ins >> 24) & 0xffff), ib = (unsigned)((ins >> 40) & 0xffff);
+    const u64 a = fetch(ka, ia);
+    if (op <= OP_MUL) {
+      const u64 b = fetch(kb, ib);
+      const u64 r = op == OP_ADD ? gl::add(a, b) : op == OP_SUB ? gl::sub(a, b) : gl::mul(a, b);
+      regs[dst * PROG_THREADS + tid] = r;
+    } else if (op == OP_EMIT) {
+      for (u32 c = 0; c < nc; c++)
+        gacc[c] = gl::add(gacc[c], gl::mul(a, __ldg(apow + (u64)c * num_constraints + ib)));
+    } else {  // OP_ENDGATE
+      for (u32 c = 0; c < nc; c++) {
+        total[c] = gl::add(total[c], gl::mul(gacc[c], a));
+        gacc[c] = 0;
+      }
+    }
+  }
+  if (live)
+    for (u32 c = 0; c < nc; c++) out[(u64)c * q + i] = total[c];
+}
+
 // coset_ifft's tail: coefficient j of every column times shift^-j
 __global__ void coset_unscale(u64* __restrict__ coeffs, u64 len, u32 ncols, u64 shift_inv) {
   const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;

@@ -112,6 +112,15 @@ struct vpbs_sigmas {
   u64 *sigmas = nullptr, *k_is = nullptr;  // num_routed x n column-major; num_routed
 };
 
+// The gate constraints of one circuit as a straight-line program in HBM (vpbs_gate_program_upload;
+// perm::gate_program_eval).  Owns plain device allocations on `device`.
+struct vpbs_gate_program {
+  int device = 0;
+  u64 *code = nullptr, *imm = nullptr;
+  u32 ncode = 0, nimm = 0, nregs = 0, num_constraints = 0;
+  u32 max_wire = 0, max_const = 0;   // highest column indices the program reads (+ 1)
+};
+
 // FRI commit phase kept in HBM (vpbs_fri_*): the current polynomial (coefficients and coset
 // evaluations over the quadratic extension, (re, im) pairs) and the Merkle tree of every layer.
 struct vpbs_fri {
@@ -2405,13 +2414,76 @@ int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas,
   return VPBS_OK;
 }
 
+// The gate constraints of a circuit as a program (perm::gate_program_eval): validated here, once.
+int vpbs_gate_program_upload(vpbs_ctx* ctx, const uint64_t* code, uint32_t ncode, const uint64_t* imms,
+                             uint32_t nimm, uint32_t nregs, uint32_t num_constraints,
+                             vpbs_gate_program** out) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!out || (!code && ncode) || (!imms && nimm)) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  *out = nullptr;
+  if (nregs == 0 || nregs > 224 || num_constraints == 0 || num_constraints > 4096)
+    return fail(ctx, VPBS_ERR_ARG, "gate program: 1..224 registers, 1..4096 constraints");
+  u32 max_wire = 0, max_const = 0;
+  for (u32 pc = 0; pc < ncode; pc++) {
+    const u64 ins = code[pc];
+    const unsigned op = (unsigned)(ins & 0xff), dst = (unsigned)((ins >> 8) & 0xff);
+    const unsigned kind[2] = {(unsigned)((ins >> 16) & 0xf), (unsigned)((ins >> 20) & 0xf)};
+    const unsigned idx[2] = {(unsigned)((ins >> 24) & 0xffff), (unsigned)((ins >> 40) & 0xffff)};
+    if (op > perm::OP_ENDGATE || (ins >> 56)) return fail(ctx, VPBS_ERR_ARG, "gate program: bad opcode");
+    if (op <= perm::OP_MUL && dst >= nregs) return fail(ctx, VPBS_ERR_ARG, "gate program: bad destination register");
+    if (op == perm::OP_EMIT && idx[1] >= num_constraints)
+      return fail(ctx, VPBS_ERR_ARG, "gate program: constraint index out of range");
+    const int nops = op <= perm::OP_MUL ? 2 : 1;
+    for (int o = 0; o < nops; o++) {
+      switch (kind[o]) {
+        case perm::K_REG: if (idx[o] >= nregs) return fail(ctx, VPBS_ERR_ARG, "gate program: bad register"); break;
+        case perm::K_WIRE: if (idx[o] + 1 > max_wire) max_wire = idx[o] + 1; break;
+        case perm::K_CONST: if (idx[o] + 1 > max_const) max_const = idx[o] + 1; break;
+        case perm::K_IMM: if (idx[o] >= nimm) return fail(ctx, VPBS_ERR_ARG, "gate program: bad immediate"); break;
+        case perm::K_PIH: if (idx[o] >= 4) return fail(ctx, VPBS_ERR_ARG, "gate program: bad public-input index"); break;
+        default: return fail(ctx, VPBS_ERR_ARG, "gate program: bad operand kind");
+      }
+    }
+  }
+  vpbs_gate_program* g = new (std::nothrow) vpbs_gate_program();
+  if (!g) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
+  g->device = ctx->device;
+  g->ncode = ncode; g->nimm = nimm; g->nregs = nregs; g->num_constraints = num_constraints;
+  g->max_wire = max_wire; g->max_const = max_const;
+  std::vector<u64> ic(imms, imms + nimm);
+  for (u64& v : ic) v = gl::canon(v);
+  cudaError_t e = cudaMalloc((void**)&g->code, (size_t)(ncode ? ncode : 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&g->imm, (size_t)(nimm ? nimm : 1) * 8);
+  if (e == cudaSuccess && ncode) e = cudaMemcpy(g->code, code, (size_t)ncode * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nimm) e = cudaMemcpy(g->imm, ic.data(), (size_t)nimm * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(g->code);
+    cudaFree(g->imm);
+    delete g;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? VPBS_ERR_OOM : VPBS_ERR_CUDA,
+                std::string("gate program upload: ") + cudaGetErrorString(e));
+  }
+  *out = g;
+  return VPBS_OK;
+}
+
+void vpbs_gate_program_destroy(vpbs_gate_program* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaFree(g->code);
+  cudaFree(g->imm);
+  delete g;
+}
+
 // [P2] plonk/prover.rs compute_quotient_polys, gate-independent part (see perm::quotient_permutation_terms),
 // then per challenge coset_ifft + chunks of n, committed from coefficients as the quotient batch.
 int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
                               vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
                               uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
                               const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
-                              const uint64_t* const* gate_terms, uint32_t rate_bits, uint32_t cap_height,
+                              const uint64_t* const* gate_terms, const vpbs_gate_program* program,
+                              const uint64_t* public_inputs_hash, uint32_t rate_bits, uint32_t cap_height,
                               uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {
   if (!wires || !constants_sigmas || !zs_pp) return VPBS_ERR_STATE;
   vpbs_ctx* ctx = wires->ctx;
@@ -2438,6 +2510,12 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
   if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
   if (cap_height > log_n + rate_bits)
     return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  if (program) {
+    if (gate_terms) return fail(ctx, VPBS_ERR_ARG, "gate_terms and a gate program are mutually exclusive");
+    if (program->device != ctx->device) return fail(ctx, VPBS_ERR_STATE, "gate program lives on another device");
+    if (program->max_wire > wires->width || program->max_const > constants_sigmas->width)
+      return fail(ctx, VPBS_ERR_ARG, "gate program reads columns the batches do not have");
+  }
   const unsigned log_q = log_n + qdb;
   const u64 n = 1ULL << log_n, q = 1ULL << log_q;
   const uint64_t l0 = ctx->launches;
@@ -2478,6 +2556,31 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
       if (!gate_terms[c]) return fail(ctx, VPBS_ERR_ARG, "gate_terms[c] == NULL");
       CU(ctx, cudaMemcpyAsync(d_gate + (u64)c * q, gate_terms[c], q * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
+  }
+  if (program) {  // evaluate_gate_constraints_base_batch, alpha-reduced, at every point of the quotient domain
+    const u32 ng = program->num_constraints;
+    std::vector<u64> ap((size_t)nc * ng);
+    for (u32 c = 0; c < nc; c++) {
+      const u64 a = gl::canon(alphas[c]);
+      u64 pw = 1;
+      for (u32 j = 0; j < ng; j++, pw = gl::mul(pw, a)) ap[(size_t)c * ng + j] = pw;
+    }
+    u64* d_ap = nullptr;
+    if ((rc = arena_get(ctx, "gate_apow", ap.size() * 8 + 8, (void**)&d_ap))) return rc;
+    if ((rc = arena_get(ctx, "gate_terms", (size_t)nc * q * 8, (void**)&d_gate))) return rc;
+    CU(ctx, cudaMemcpyAsync(d_ap, ap.data(), ap.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    perm::PihAlphas pa;
+    for (int k = 0; k < 4; k++) pa.pih[k] = public_inputs_hash ? gl::canon(public_inputs_hash[k]) : 0;
+    const size_t smem = (size_t)program->nregs * perm::PROG_THREADS * sizeof(u64);
+    CU(ctx, cudaFuncSetAttribute((const void*)perm::gate_program_eval,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    perm::gate_program_eval<<<(unsigned)((q + perm::PROG_THREADS - 1) / perm::PROG_THREADS), perm::PROG_THREADS,
+                              smem, ctx->stream>>>(program->code, program->ncode, program->imm, d_ap, ng,
+                                                   wires->leaves, wires->width, constants_sigmas->leaves,
+                                                   constants_sigmas->width, nc, log_q, pa, d_gate);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // `ap` dies with this scope
   }
   const ntt::Roots R{ctx->roots, ctx->roots_log};
   perm::quotient_permutation_terms<<<(unsigned)((q + 127) / 128), 128, 0, ctx->stream>>>(

@@ -769,15 +769,116 @@ def commit_zs_partial_products(wires: ResidentPolynomialBatch, sigmas: Sigmas, b
                                    st.as_dict())
 
 
+class GateProgram:
+    """The gate constraints of a circuit as a straight-line program on the device
+    (vpbs_gate_program_upload; instruction format in include/vpbs_commit.h).  Built with
+    GateProgramBuilder; constant per circuit, uploaded once."""
+
+    def __init__(self, code, imms, nregs: int, num_constraints: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        c, im = _as_u64(code).reshape(-1), _as_u64(imms).reshape(-1)
+        self.code, self.imms, self.nregs, self.num_constraints = c, im, nregs, num_constraints
+        self.handle = ctypes.c_void_p()
+        self.ctx.check(self.ctx.lib.vpbs_gate_program_upload(
+            self.ctx.handle, _ptr(c) if c.size else None, c.size, _ptr(im) if im.size else None, im.size,
+            nregs, num_constraints, ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.vpbs_gate_program_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GateProgramBuilder:
+    """Assembler for gate programs: what a host-side compiler of plonky2's gates emits.  Operands are
+    tuples (kind, index): reg(i), wire(col), const(col), imm(value), pih(i); add / sub / mul return a
+    fresh register; emit(j, v) states constraint j of the current gate; end_gate(filter) closes it.
+    Registers are recycled at end_gate (a gate's temporaries die with it)."""
+    ADD, SUB, MUL, EMIT, ENDGATE = 0, 1, 2, 3, 4
+
+    def __init__(self):
+        self.code: List[int] = []
+        self.imms: List[int] = []
+        self._imm_index = {}
+        self._next = 0
+        self.nregs = 1
+        self.num_constraints = 1
+
+    @staticmethod
+    def wire(col): return (1, col)
+
+    @staticmethod
+    def const(col): return (2, col)
+
+    @staticmethod
+    def pih(i): return (4, i)
+
+    def imm(self, value):
+        v = int(value) % P
+        if v not in self._imm_index:
+            self._imm_index[v] = len(self.imms)
+            self.imms.append(v)
+        return (3, self._imm_index[v])
+
+    def _ins(self, op, dst, a, b=(0, 0)):
+        self.code.append(op | dst << 8 | a[0] << 16 | b[0] << 20 | a[1] << 24 | b[1] << 40)
+
+    def _binary(self, op, a, b):
+        dst = self._next
+        self._next += 1
+        if self._next > 224:
+            raise ValueError("gate needs more than 224 live registers")
+        self.nregs = max(self.nregs, self._next)
+        self._ins(op, dst, a, b)
+        return (0, dst)
+
+    def add(self, a, b): return self._binary(self.ADD, a, b)
+    def sub(self, a, b): return self._binary(self.SUB, a, b)
+    def mul(self, a, b): return self._binary(self.MUL, a, b)
+
+    def emit(self, j: int, value):
+        self.num_constraints = max(self.num_constraints, j + 1)
+        self._ins(self.EMIT, 0, value, (0, j))
+
+    def end_gate(self, filter_value):
+        self._ins(self.ENDGATE, 0, filter_value)
+        self._next = 0
+
+    def selector_filter(self, selector_col: int, row: int, group, many_selectors: bool):
+        """[P2] gates/gate.rs compute_filter: prod over the group's other gate indices i of (i - s),
+        times (UNUSED_SELECTOR - s) when the circuit has several selector polynomials; s = the
+        selector constant of this row."""
+        s = self.const(selector_col)
+        f = self.imm(1)
+        for i in group:
+            if i != row:
+                f = self.mul(f, self.sub(self.imm(i), s))
+        if many_selectors:
+            f = self.mul(f, self.sub(self.imm(2**32 - 1), s))
+        return f
+
+    def build(self, ctx: Optional[Context] = None, num_constraints: Optional[int] = None) -> GateProgram:
+        return GateProgram(np.array(self.code, dtype=np.uint64), np.array(self.imms, dtype=np.uint64),
+                           self.nregs, num_constraints or self.num_constraints, ctx)
+
+
 def commit_quotient_polys(constants_sigmas: "ResidentPolynomialBatch", sigmas_first_col: int,
                           wires: "ResidentPolynomialBatch", zs_pp: "ResidentPolynomialBatch", k_is,
                           max_degree: int, quotient_degree_bits: int, betas, gammas, alphas,
-                          rate_bits: int, cap_height: int, gate_terms=None) -> "ResidentPolynomialBatch":
+                          rate_bits: int, cap_height: int, gate_terms=None, program: "GateProgram" = None,
+                          public_inputs_hash=None) -> "ResidentPolynomialBatch":
     """prove() steps 6-7 on the device, gate-independent part ([P2] plonk/prover.rs
     compute_quotient_polys / plonk/vanishing_poly.rs): the Z(1) = 1 terms and the partial-product
     checks over the quotient domain, reduced with the alphas, divided by Z_H, coset_ifft, chunked and
-    committed (vpbs_batch_quotient_polys).  gate_terms: (num_challenges, n << quotient_degree_bits)
-    alpha-reduced gate constraints in natural order, or None."""
+    committed (vpbs_batch_quotient_polys).  The gate constraints come either as gate_terms —
+    (num_challenges, n << quotient_degree_bits) alpha-reduced values in natural order — or as a
+    GateProgram the device evaluates at every point (with public_inputs_hash), or not at all."""
     ctx = wires.ctx
     k = _as_u64(k_is).reshape(-1)
     b, g, a = (_as_u64(v).reshape(-1) for v in (betas, gammas, alphas))
@@ -795,6 +896,9 @@ def commit_quotient_polys(constants_sigmas: "ResidentPolynomialBatch", sigmas_fi
     ctx.check(ctx.lib.vpbs_batch_quotient_polys(constants_sigmas.handle, sigmas_first_col, wires.handle,
                                                 zs_pp.handle, _ptr(k), k.size, max_degree,
                                                 quotient_degree_bits, _ptr(b), _ptr(g), _ptr(a), b.size, gtp,
+                                                program.handle if program is not None else None,
+                                                _ptr(_as_u64(public_inputs_hash).reshape(4))
+                                                if public_inputs_hash is not None else None,
                                                 rate_bits, cap_height, _ptr(cap), ctypes.byref(handle),
                                                 ctypes.byref(st)))
     return ResidentPolynomialBatch(ctx, handle, cap, b.size << quotient_degree_bits, wires.degree_log,
