@@ -398,6 +398,11 @@ def main():
                     help="with --chain-steps: the quotient chunks arrive as 16 coefficient columns from the "
                          "host (the form of the first half of round 2) instead of being computed on the "
                          "device from the resident batches (vpbs_batch_quotient_polys)")
+    ap.add_argument("--chain-gate-ops", type=int, default=0, metavar="N",
+                    help="with --chain-steps: evaluate the gate constraints ON THE DEVICE from a synthetic "
+                         "program of about N field operations per point of the quotient domain (Poseidon-gate-"
+                         "like rounds: x^7 S-boxes and 12 x 12 linear layers; plonky2's PoseidonGate is a few "
+                         "thousand) instead of taking their alpha-reduced values from the host")
     ap.add_argument("--chain-shard", action="store_true",
                     help="with --chain-steps under torchrun: ONE chain for all ranks — every resident "
                          "batch of a step is sharded by row range over the GPUs (vpbs_ctx_set_shard), "
@@ -1112,6 +1117,39 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     gate_view = ins[2].reshape(2, 8 * n)      # alpha-reduced gate constraints on the quotient domain
     gate_ptrs = (u64p * 2)(gate_view[0].ctypes.data_as(u64p), gate_view[1].ctypes.data_as(u64p))
 
+    gate_prog = None
+    if args.chain_gate_ops and not shard:
+        # stand-in for the circuit's compiled gate program (the real one comes from plonky2's gates through
+        # a host-side compiler): Poseidon-gate-like rounds on 12 wires — every round
+        # constrains its 12 S-box inputs against 12 further wires, raises them to the 7th power and mixes
+        # them with a dense 12 x 12 constant layer — until about N operations are reached
+        B = V.GateProgramBuilder()
+        rng_p = np.random.default_rng(1)
+        # registers managed by hand: 0..11 state, 12..23 S-box outputs, 24..25 temporaries, 26..37 mixed
+        R = lambda i: (0, i)
+        for i in range(12):
+            B.into(i, B.ADD, B.wire(i), B.imm(0))
+        j = 0
+        while len(B.code) < args.chain_gate_ops:
+            for i in range(12):
+                if j < 123:
+                    B.emit(j, B.into(24, B.SUB, R(i), B.wire(12 + j % 120)))
+                    j += 1
+                B.into(24, B.MUL, R(i), R(i))              # x^2
+                B.into(25, B.MUL, R(24), R(24))            # x^4
+                B.into(25, B.MUL, R(25), R(24))            # x^6
+                B.into(12 + i, B.MUL, R(25), R(i))         # x^7
+            for r in range(12):
+                B.into(26 + r, B.MUL, R(12), B.imm(int(rng_p.integers(1, 64))))
+                for i in range(1, 12):
+                    B.mad(R(26 + r), R(12 + i), B.imm(int(rng_p.integers(1, 64))))
+            for r in range(12):
+                B.into(r, B.ADD, R(26 + r), B.imm(int(rng_p.integers(1, 2**62))))   # + round constant
+        B.into(24, B.SUB, B.imm(0), B.const(0))
+        B.into(25, B.SUB, B.imm(2), B.const(0))
+        B.end_gate(B.into(24, B.MUL, R(24), R(25)))         # filter of gate 1 in a group of three
+        gate_prog = B.build(ctx, 123)
+
     def challenge(cap, k, count):  # stand-in for challenger.get_n_challenges (see docstring)
         x = cap.reshape(-1).astype(np.uint64)
         seed = int(np.bitwise_xor.reduce(x * np.uint64(2 * k + 1))) ^ (k * 0x9E3779B97F4A7C15)
@@ -1189,7 +1227,8 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
             ctx.check(lib.vpbs_batch_quotient_polys(
                 cs["h"], CS - num_routed, hs[0], hs[1], k_is.ctypes.data_as(u64p), num_routed, max_degree,
                 RATE_BITS, bg[:2].ctypes.data_as(u64p), bg[2:].ctypes.data_as(u64p), al.ctypes.data_as(u64p), 2,
-                gate_ptrs, None, None, RATE_BITS, CAP_HEIGHT, caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
+                None if gate_prog else gate_ptrs, gate_prog.handle if gate_prog else None, None,
+                RATE_BITS, CAP_HEIGHT, caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
         t = lap("quotient_commit", t)
         zeta = challenge(caps[2], 2, 2)
         gz = np.array([int(zeta[0]) * g_n % P_GL, int(zeta[1]) * g_n % P_GL], np.uint64)
@@ -1347,6 +1386,11 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
             "data": "synthetic", "vs_baseline": None, "log_n": log_n,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step_approx": d2h,
             "gpu_launches_per_step": int(launches), "fri_layers": stats["fri_layers"],
+            "quotient": ("16 coefficient columns from the host" if (shard or args.chain_host_quotient) else
+                         "device: permutation terms + tail; gate constraints %s" %
+                         ("evaluated on the device from a synthetic %d-instruction program (%d registers)"
+                          % (len(gate_prog.code), gate_prog.nregs) if gate_prog else
+                          "as alpha-reduced values from the host (8 MiB)")),
             "phase_ms_rank0": {k: round(v / args.chain_steps * 1e3, 4) for k, v in phase.items()},
             "eager_commits_ms_per_step": out_eager,
             "eager_note": "round 1's form of the step: the three commits with coefficients, LDE rows and "

@@ -420,9 +420,10 @@ int vpbs_batch_zs_partial_products(vpbs_batch* wires, const vpbs_sigmas* sigmas,
  * public_inputs_hash; the device runs it at every point of the quotient domain, so no LDE row
  * crosses PCIe.  One 64-bit word per instruction:
  *     bits 0-7 op | 8-15 dst register | 16-19 kind(a) | 20-23 kind(b) | 24-39 index(a) | 40-55 index(b)
- *     op   0 ADD, 1 SUB, 2 MUL: dst <- a op b;  3 EMIT: constraint number index(b) of the current
- *          gate has value a;  4 ENDGATE: the current gate's constraints, times the filter value a,
- *          are added to the totals (constraint j counts alpha_c^j, as reduce_with_powers does)
+ *     op   0 ADD, 1 SUB, 2 MUL: dst <- a op b;  5 MAD: dst <- dst + a b;  3 EMIT: constraint number
+ *          index(b) of the current gate has value a;  4 ENDGATE: the current gate's constraints,
+ *          times the filter value a, are added to the totals (constraint j counts alpha_c^j, as
+ *          reduce_with_powers does)
  *     kind 0 register, 1 wire column, 2 column of the constants/sigmas batch, 3 immediate table
  *          entry, 4 public_inputs_hash element
  * nregs <= 224 registers (shared memory), num_constraints = the circuit's num_gate_constraints. */

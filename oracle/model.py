@@ -384,9 +384,10 @@ def gate_program_eval(code, imms, num_constraints, wire_coeffs, cs_coeffs, qdb, 
         for ins in code:
             op, dst = ins & 0xff, (ins >> 8) & 0xff
             a = val((ins >> 16) & 0xf, (ins >> 24) & 0xffff)
-            if op <= 2:
+            if op <= 2 or op == 5:
                 b = val((ins >> 20) & 0xf, (ins >> 40) & 0xffff)
-                regs[dst] = (a + b) % P if op == 0 else (a - b) % P if op == 1 else a * b % P
+                regs[dst] = ((a + b) % P if op == 0 else (a - b) % P if op == 1 else a * b % P if op == 2
+                             else (regs[dst] + a * b) % P)
             elif op == 3:
                 j = (ins >> 40) & 0xffff
                 assert j < num_constraints

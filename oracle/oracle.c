@@ -976,7 +976,7 @@ int orc_gate_program_eval(const uint64_t* code, uint32_t ncode, const uint64_t* 
       const unsigned kind[2] = {(unsigned)((ins >> 16) & 0xf), (unsigned)((ins >> 20) & 0xf)};
       const unsigned idx[2] = {(unsigned)((ins >> 24) & 0xffff), (unsigned)((ins >> 40) & 0xffff)};
       uint64_t v[2] = {0, 0};
-      for (int o = 0; o < (op <= 2 ? 2 : 1); o++) {
+      for (int o = 0; o < ((op <= 2 || op == 5) ? 2 : 1); o++) {
         switch (kind[o]) {
           case 0: v[o] = idx[o] < 256 ? regs[idx[o]] : (bad |= 1, 0); break;
           case 1: v[o] = idx[o] < nwires ? lw[idx[o]][i] : (bad |= 1, 0); break;
@@ -989,6 +989,7 @@ int orc_gate_program_eval(const uint64_t* code, uint32_t ncode, const uint64_t* 
       if (op == 0) regs[dst] = add_(v[0], v[1]);
       else if (op == 1) regs[dst] = sub_(v[0], v[1]);
       else if (op == 2) regs[dst] = mul_(v[0], v[1]);
+      else if (op == 5) regs[dst] = add_(regs[dst], mul_(v[0], v[1]));
       else if (op == 3) {
         if (idx[1] >= num_constraints) { bad |= 1; continue; }
         for (uint32_t c = 0; c < nc; c++) gacc[c] = add_(gacc[c], mul_(v[0], apow[(size_t)c * num_constraints + idx[1]]));

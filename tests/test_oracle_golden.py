@@ -396,7 +396,10 @@ def _random_gate_program(V, rng, nwires, ncs, ngates=3, nops=25, nconstraints=5)
                 b.imm(int(rng.integers(0, 2**63))), b.pih(int(rng.integers(4)))]
         for _ in range(nops):
             x, y = (pool[int(rng.integers(len(pool)))] for _ in range(2))
-            pool.append([b.add, b.sub, b.mul][int(rng.integers(3))](x, y))
+            if rng.random() < 0.25 and pool[-1][0] == 0:
+                b.mad(pool[-1], x, y)
+            else:
+                pool.append([b.add, b.sub, b.mul][int(rng.integers(3))](x, y))
         for j in rng.permutation(nconstraints)[: int(rng.integers(1, nconstraints + 1))]:
             b.emit(int(j), pool[int(rng.integers(len(pool)))])
         b.end_gate(pool[int(rng.integers(len(pool)))])

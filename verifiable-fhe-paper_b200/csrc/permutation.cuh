@@ -276,22 +276,21 @@ quotient_permutation_terms(const u64* __restrict__ wires, u32 wires_width, const
 //     op:   0 ADD  1 SUB  2 MUL   dst <- a op b
 //           3 EMIT     the current gate's constraint number (index of b) has value a
 //           4 ENDGATE  the gate's constraints, times the filter value a, are added to the totals
+//           5 MAD      dst <- dst + a b   (linear layers: one instruction and one reduction per term)
 //     kind: 0 register  1 wire column  2 column of the constants/sigmas batch (selectors and
 //           constants)  3 entry of the immediate table  4 public_inputs_hash element
 // Constraint j enters the total of challenge c times alpha_c^j (reduce_with_powers), so per gate the
 // kernel keeps sum_j alpha_c^j c_j and multiplies it by the filter at ENDGATE: exactly
 // sum_j alpha_c^j sum_g filter_g c_{g,j}.  Registers live in shared memory ([register][thread]).
 constexpr int PROG_THREADS = 128;
-enum : unsigned { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_EMIT = 3, OP_ENDGATE = 4 };
+enum : unsigned { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_EMIT = 3, OP_ENDGATE = 4, OP_MAD = 5 };
 enum : unsigned { K_REG = 0, K_WIRE = 1, K_CONST = 2, K_IMM = 3, K_PIH = 4 };
-struct PihAlphas {
-  u64 pih[4];
-};
 __global__ void __launch_bounds__(PROG_THREADS)
 gate_program_eval(const u64* __restrict__ code, u32 ncode, const u64* __restrict__ imm,
-                  const u64* __restrict__ apow /* nc x num_constraints: alpha_c^j */, u32 num_constraints,
+                  const u64* __restrict__ apow /* nc x num_constraints: alpha_c^j, then public_inputs_hash[4] */,
+                  u32 num_constraints,
                   const u64* __restrict__ wires, u32 wires_width, const u64* __restrict__ cs, u32 cs_width,
-                  u32 nc, unsigned log_q, const __grid_constant__ PihAlphas pa, u64* __restrict__ out) {
+                  u32 nc, unsigned log_q, u64* __restrict__ out) {
   extern __shared__ u64 regs[];  // [register][thread]
   const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const u64 q = 1ULL << log_q;
@@ -301,38 +300,60 @@ gate_program_eval(const u64* __restrict__ code, u32 ncode, const u64* __restrict
   const u64* wrow = wires + kk * wires_width;
   const u64* crow = cs + kk * cs_width;
   const unsigned tid = threadIdx.x;
-  u64 total[4] = {0, 0, 0, 0}, gacc[4] = {0, 0, 0, 0};
-  auto fetch = [&](unsigned kind, unsigned idx) -> u64 {
-    switch (kind) {
-      case K_REG: return regs[idx * PROG_THREADS + tid];
-      case K_WIRE: return __ldg(wrow + idx);
-      case K_CONST: return __ldg(crow + idx);
-      case K_IMM: return __ldg(imm + idx);
-      default: return pa.pih[idx & 3];
-    }
+  u64 total[4] = {0, 0, 0, 0}, gacc[4] = {0, 0, 0, 0};  // fully unrolled below: registers
+  // register file: plain 32-bit shared-memory addresses (LDS / STS; the generic-pointer form re-derives
+  // the shared window base at every access) — register r of this thread lives at rbase + r * 1024
+  const unsigned rbase = (unsigned)__cvta_generic_to_shared(regs) + tid * 8u;
+  auto lds = [&](unsigned r) -> u64 {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(rbase + (r << 10)));
+    return v;
   };
+  // operand of a kind other than "register": every such source is a global-memory table, so the kind
+  // only SELECTS a base pointer (a switch / if-chain becomes an indirect branch through a
+  // constant-memory jump table, the top stall of the first version of this kernel)
+  const u64* pihp = apow + (u64)nc * num_constraints;  // the caller appends public_inputs_hash there
+  auto fetch_slow = [&](unsigned kind, unsigned idx) -> u64 {
+    const u64* p = kind == K_IMM ? imm : kind == K_WIRE ? wrow : kind == K_CONST ? crow : pihp;
+    return __ldg(p + idx);
+  };
+  // the instruction stream is the same for every thread: the next word is fetched while the current
+  // one executes, and register operands (the common case) skip the operand-kind dispatch
+  u64 ins = ncode ? __ldg(code) : 0;
   for (u32 pc = 0; pc < ncode; pc++) {
-    const u64 ins = __ldg(code + pc);
-    const unsigned op = (unsigned)(ins & 0xff), dst = (unsigned)((ins >> 8) & 0xff);
-    const unsigned ka = (unsigned)((ins >> 16) & 0xf), kb = (unsigned)((ins >> 20) & 0xf);
-    const unsigned ia = (unsigned)((ins >> 24) & 0xffff), ib = (unsigned)((ins >> 40) & 0xffff);
-    const u64 a = fetch(ka, ia);
-    if (op <= OP_MUL) {
-      const u64 b = fetch(kb, ib);
-      const u64 r = op == OP_ADD ? gl::add(a, b) : op == OP_SUB ? gl::sub(a, b) : gl::mul(a, b);
-      regs[dst * PROG_THREADS + tid] = r;
+    const u64 next = pc + 1 < ncode ? __ldg(code + pc + 1) : 0;
+    const unsigned lo = (unsigned)ins, hi = (unsigned)(ins >> 32);
+    const unsigned op = lo & 0xff, dst = (lo >> 8) & 0xff;
+    const unsigned ka = (lo >> 16) & 0xf, kb = (lo >> 20) & 0xf;
+    const unsigned ia = (lo >> 24) | ((hi & 0xff) << 8), ib = (hi >> 8) & 0xffff;
+    const u64 a = ka == K_REG ? lds(ia) : fetch_slow(ka, ia);
+    if (op <= OP_MUL || op == OP_MAD) {
+      const u64 b = kb == K_REG ? lds(ib) : fetch_slow(kb, ib);
+      u64 r;
+      if (op == OP_MAD) r = gl::canon(ntt::mul_add2_lazy(a, b, lds(dst), 0));
+      else if (op == OP_MUL) r = gl::mul(a, b);
+      else if (op == OP_ADD) r = gl::add(a, b);
+      else r = gl::sub(a, b);
+      asm volatile("st.shared.u64 [%0], %1;" ::"r"(rbase + (dst << 10)), "l"(r) : "memory");
     } else if (op == OP_EMIT) {
-      for (u32 c = 0; c < nc; c++)
-        gacc[c] = gl::add(gacc[c], gl::mul(a, __ldg(apow + (u64)c * num_constraints + ib)));
+#pragma unroll
+      for (u32 c = 0; c < 4; c++)
+        if (c < nc) gacc[c] = gl::add(gacc[c], gl::mul(a, __ldg(apow + (u64)c * num_constraints + ib)));
     } else {  // OP_ENDGATE
-      for (u32 c = 0; c < nc; c++) {
-        total[c] = gl::add(total[c], gl::mul(gacc[c], a));
-        gacc[c] = 0;
-      }
+#pragma unroll
+      for (u32 c = 0; c < 4; c++)
+        if (c < nc) {
+          total[c] = gl::add(total[c], gl::mul(gacc[c], a));
+          gacc[c] = 0;
+        }
     }
+    ins = next;
   }
-  if (live)
-    for (u32 c = 0; c < nc; c++) out[(u64)c * q + i] = total[c];
+  if (live) {
+#pragma unroll
+    for (u32 c = 0; c < 4; c++)
+      if (c < nc) out[(u64)c * q + i] = total[c];
+  }
 }
 
 // coset_ifft's tail: coefficient j of every column times shift^-j

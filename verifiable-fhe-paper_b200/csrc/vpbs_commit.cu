@@ -2430,11 +2430,12 @@ int vpbs_gate_program_upload(vpbs_ctx* ctx, const uint64_t* code, uint32_t ncode
     const unsigned op = (unsigned)(ins & 0xff), dst = (unsigned)((ins >> 8) & 0xff);
     const unsigned kind[2] = {(unsigned)((ins >> 16) & 0xf), (unsigned)((ins >> 20) & 0xf)};
     const unsigned idx[2] = {(unsigned)((ins >> 24) & 0xffff), (unsigned)((ins >> 40) & 0xffff)};
-    if (op > perm::OP_ENDGATE || (ins >> 56)) return fail(ctx, VPBS_ERR_ARG, "gate program: bad opcode");
-    if (op <= perm::OP_MUL && dst >= nregs) return fail(ctx, VPBS_ERR_ARG, "gate program: bad destination register");
+    if (op > perm::OP_MAD || (ins >> 56)) return fail(ctx, VPBS_ERR_ARG, "gate program: bad opcode");
+    const bool binary = op <= perm::OP_MUL || op == perm::OP_MAD;
+    if (binary && dst >= nregs) return fail(ctx, VPBS_ERR_ARG, "gate program: bad destination register");
     if (op == perm::OP_EMIT && idx[1] >= num_constraints)
       return fail(ctx, VPBS_ERR_ARG, "gate program: constraint index out of range");
-    const int nops = op <= perm::OP_MUL ? 2 : 1;
+    const int nops = binary ? 2 : 1;
     for (int o = 0; o < nops; o++) {
       switch (kind[o]) {
         case perm::K_REG: if (idx[o] >= nregs) return fail(ctx, VPBS_ERR_ARG, "gate program: bad register"); break;
@@ -2559,25 +2560,26 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
   }
   if (program) {  // evaluate_gate_constraints_base_batch, alpha-reduced, at every point of the quotient domain
     const u32 ng = program->num_constraints;
-    std::vector<u64> ap((size_t)nc * ng);
+    std::vector<u64> ap((size_t)nc * ng + 4);  // alpha powers, then public_inputs_hash
     for (u32 c = 0; c < nc; c++) {
       const u64 a = gl::canon(alphas[c]);
       u64 pw = 1;
       for (u32 j = 0; j < ng; j++, pw = gl::mul(pw, a)) ap[(size_t)c * ng + j] = pw;
     }
+    for (int k = 0; k < 4; k++) ap[(size_t)nc * ng + k] = public_inputs_hash ? gl::canon(public_inputs_hash[k]) : 0;
     u64* d_ap = nullptr;
-    if ((rc = arena_get(ctx, "gate_apow", ap.size() * 8 + 8, (void**)&d_ap))) return rc;
+    if ((rc = arena_get(ctx, "gate_apow", ap.size() * 8, (void**)&d_ap))) return rc;
     if ((rc = arena_get(ctx, "gate_terms", (size_t)nc * q * 8, (void**)&d_gate))) return rc;
     CU(ctx, cudaMemcpyAsync(d_ap, ap.data(), ap.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    perm::PihAlphas pa;
-    for (int k = 0; k < 4; k++) pa.pih[k] = public_inputs_hash ? gl::canon(public_inputs_hash[k]) : 0;
     const size_t smem = (size_t)program->nregs * perm::PROG_THREADS * sizeof(u64);
     CU(ctx, cudaFuncSetAttribute((const void*)perm::gate_program_eval,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(ctx, cudaFuncSetAttribute((const void*)perm::gate_program_eval,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     perm::gate_program_eval<<<(unsigned)((q + perm::PROG_THREADS - 1) / perm::PROG_THREADS), perm::PROG_THREADS,
                               smem, ctx->stream>>>(program->code, program->ncode, program->imm, d_ap, ng,
                                                    wires->leaves, wires->width, constants_sigmas->leaves,
-                                                   constants_sigmas->width, nc, log_q, pa, d_gate);
+                                                   constants_sigmas->width, nc, log_q, d_gate);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // `ap` dies with this scope

@@ -800,7 +800,7 @@ class GateProgramBuilder:
     tuples (kind, index): reg(i), wire(col), const(col), imm(value), pih(i); add / sub / mul return a
     fresh register; emit(j, v) states constraint j of the current gate; end_gate(filter) closes it.
     Registers are recycled at end_gate (a gate's temporaries die with it)."""
-    ADD, SUB, MUL, EMIT, ENDGATE = 0, 1, 2, 3, 4
+    ADD, SUB, MUL, EMIT, ENDGATE, MAD = 0, 1, 2, 3, 4, 5
 
     def __init__(self):
         self.code: List[int] = []
@@ -837,6 +837,23 @@ class GateProgramBuilder:
         self.nregs = max(self.nregs, self._next)
         self._ins(op, dst, a, b)
         return (0, dst)
+
+    def into(self, dst: int, op: int, a, b):
+        """dst <- a op b into a register the caller manages (long gates reuse registers; add / sub / mul
+        hand out a fresh one per result and recycle only at end_gate)."""
+        if not 0 <= dst < 224:
+            raise ValueError("register index out of range")
+        self.nregs = max(self.nregs, dst + 1)
+        self._next = max(self._next, dst + 1)
+        self._ins(op, dst, a, b)
+        return (0, dst)
+
+    def mad(self, acc, a, b):
+        """acc <- acc + a b in place (acc: a register operand); returns acc."""
+        if acc[0] != 0:
+            raise ValueError("mad accumulates into a register")
+        self._ins(self.MAD, acc[1], a, b)
+        return acc
 
     def add(self, a, b): return self._binary(self.ADD, a, b)
     def sub(self, a, b): return self._binary(self.SUB, a, b)
