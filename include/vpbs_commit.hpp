@@ -308,11 +308,20 @@ class ResidentBatch {
     ctx_.check(vpbs_batch_get_lde_rows(h_, first, step, count, out.data()));
     return out;
   }
+  // PolynomialBatch.polynomials of the resident batch (coefficient columns), copied to the host
+  std::vector<std::vector<F>> coefficients() const {
+    std::vector<std::vector<F>> out(ncols, std::vector<F>(std::size_t(1) << degree_log));
+    std::vector<F*> ptrs(ncols);
+    for (std::size_t c = 0; c < ncols; c++) ptrs[c] = out[c].data();
+    ctx_.check(vpbs_batch_download(h_, ptrs.data(), nullptr, nullptr));
+    return out;
+  }
   vpbs_batch* handle() const { return h_; }
   const Context& context() const { return ctx_; }
 
  private:
   friend class Sigmas;
+  friend class GateProgram;
   ResidentBatch(const Context& ctx, vpbs_batch* h, std::vector<HashOut> cap_, unsigned degree_log_,
                 unsigned rate_bits_, std::size_t ncols_)
       : cap(std::move(cap_)), degree_log(degree_log_), rate_bits(rate_bits_), ncols(ncols_), width(ncols_),
@@ -415,6 +424,57 @@ class Sigmas {
   vpbs_sigmas* h_ = nullptr;
   std::size_t num_routed_ = 0;
   unsigned degree_log_ = 0;
+};
+
+// ---- plonk/prover.rs, steps 6-7: compute_quotient_polys + the quotient commit ----------------------
+// The circuit's gate constraints as a straight-line program on the device (format: vpbs_commit.h).
+class GateProgram {
+ public:
+  GateProgram(const Context& ctx, const std::vector<uint64_t>& code, const std::vector<F>& imms,
+              unsigned nregs, unsigned num_constraints)
+      : ctx_(ctx) {
+    ctx.check(vpbs_gate_program_upload(ctx.get(), code.data(), (uint32_t)code.size(), imms.data(),
+                                       (uint32_t)imms.size(), nregs, num_constraints, &h_));
+  }
+  ~GateProgram() { vpbs_gate_program_destroy(h_); }
+  GateProgram(const GateProgram&) = delete;
+  GateProgram& operator=(const GateProgram&) = delete;
+  const vpbs_gate_program* handle() const { return h_; }
+
+  // vanishing terms of the permutation argument + gate constraints (from `program`, or as alpha-reduced
+  // values gate_terms[c][i] over the quotient domain, or none), reduced with the alphas, divided by
+  // Z_H, coset_ifft, chunks of n, committed: the quotient batch (num_challenges << quotient_degree_bits
+  // columns)
+  static ResidentBatch quotient_polys(const ResidentBatch& constants_sigmas, unsigned sigmas_first_col,
+                                      const ResidentBatch& wires, const ResidentBatch& zs_pp,
+                                      const std::vector<F>& k_is, unsigned max_degree,
+                                      unsigned quotient_degree_bits, const std::vector<F>& betas,
+                                      const std::vector<F>& gammas, const std::vector<F>& alphas,
+                                      unsigned rate_bits, unsigned cap_height,
+                                      const GateProgram* program = nullptr,
+                                      const F* public_inputs_hash = nullptr,
+                                      const std::vector<std::vector<F>>* gate_terms = nullptr) {
+    if (betas.size() != gammas.size() || betas.size() != alphas.size() || betas.empty())
+      throw std::invalid_argument("one beta, gamma and alpha per challenge");
+    std::vector<const F*> gt;
+    if (gate_terms)
+      for (const auto& v : *gate_terms) gt.push_back(v.data());
+    std::vector<HashOut> cap(std::size_t(1) << cap_height);
+    vpbs_batch* h = nullptr;
+    const Context& ctx = wires.context();
+    ctx.check(vpbs_batch_quotient_polys(constants_sigmas.handle(), sigmas_first_col, wires.handle(),
+                                        zs_pp.handle(), k_is.data(), (uint32_t)k_is.size(), max_degree,
+                                        quotient_degree_bits, betas.data(), gammas.data(), alphas.data(),
+                                        (uint32_t)betas.size(), gate_terms ? gt.data() : nullptr,
+                                        program ? program->handle() : nullptr, public_inputs_hash, rate_bits,
+                                        cap_height, cap[0].elements, &h, nullptr));
+    return ResidentBatch(ctx, h, std::move(cap), wires.degree_log, rate_bits,
+                         betas.size() << quotient_degree_bits);
+  }
+
+ private:
+  const Context& ctx_;
+  vpbs_gate_program* h_ = nullptr;
 };
 
 // ---- fri/prover.rs ------------------------------------------------------------------------------

@@ -344,6 +344,50 @@ impl ResidentBatch {
     }
 }
 
+/// The circuit's gate constraints as a straight-line program on the device (vpbs_gate_program_upload;
+/// instruction format in include/vpbs_commit.h).  `CircuitBuilder::build` compiles it once per circuit
+/// by running every gate's `eval_unfiltered_base_one` on a recording field type.
+pub struct GateProgram(*mut vpbs_gate_program);
+unsafe impl Send for GateProgram {}
+impl GateProgram {
+    pub fn upload(ctx: &Ctx, code: &[u64], imms: &[u64], nregs: u32, num_constraints: u32) -> Self {
+        let mut h = std::ptr::null_mut();
+        ctx.check(unsafe { vpbs_gate_program_upload(ctx.0, code.as_ptr(), code.len() as u32, imms.as_ptr(),
+                                                    imms.len() as u32, nregs, num_constraints, &mut h) });
+        GateProgram(h)
+    }
+}
+impl Drop for GateProgram {
+    fn drop(&mut self) {
+        unsafe { vpbs_gate_program_destroy(self.0) }
+    }
+}
+
+/// prove() steps 6-7 on the device: compute_quotient_polys (permutation terms from the resident
+/// batches, gate constraints from `program` or as alpha-reduced `gate_terms`), then the quotient commit.
+#[allow(clippy::too_many_arguments)]
+pub fn quotient_polys(ctx: &Ctx, constants_sigmas: &ResidentBatch, sigmas_first_col: usize,
+                      wires: &ResidentBatch, zs_pp: &ResidentBatch, k_is: &[u64], max_degree: usize,
+                      quotient_degree_bits: usize, betas: &[u64], gammas: &[u64], alphas: &[u64],
+                      program: Option<&GateProgram>, public_inputs_hash: &[u64; 4],
+                      gate_terms: Option<&[&[u64]]>) -> ResidentBatch {
+    assert!(betas.len() == gammas.len() && betas.len() == alphas.len());
+    let gt: Vec<*const u64> = gate_terms.map(|g| g.iter().map(|v| v.as_ptr()).collect()).unwrap_or_default();
+    let mut cap = vec![0u64; 4 << wires.cap_height];
+    let mut h = std::ptr::null_mut();
+    ctx.check(unsafe {
+        vpbs_batch_quotient_polys(constants_sigmas.h, sigmas_first_col as u32, wires.h, zs_pp.h, k_is.as_ptr(),
+                                  k_is.len() as u32, max_degree as u32, quotient_degree_bits as u32,
+                                  betas.as_ptr(), gammas.as_ptr(), alphas.as_ptr(), betas.len() as u32,
+                                  if gt.is_empty() { std::ptr::null() } else { gt.as_ptr() },
+                                  program.map_or(std::ptr::null(), |p| p.0 as *const _),
+                                  public_inputs_hash.as_ptr(), wires.rate_bits as u32,
+                                  wires.cap_height as u32, cap.as_mut_ptr(), &mut h, std::ptr::null_mut())
+    });
+    ResidentBatch { h, cap, ncols: betas.len() << quotient_degree_bits, degree_log: wires.degree_log,
+                    rate_bits: wires.rate_bits, cap_height: wires.cap_height }
+}
+
 /// OpeningSet::new over all FRI oracles in one round trip: per batch (npoints x ncols x 2).
 pub fn eval_ext2_all(ctx: &Ctx, batches: &[&ResidentBatch], points: &[[u64; 2]]) -> Vec<Vec<u64>> {
     let hs: Vec<*mut vpbs_batch> = batches.iter().map(|b| b.h).collect();

@@ -166,6 +166,40 @@ int main() {
     for (std::size_t k = 0; k < 4; k++)
       CHECK(std::memcmp(rows.data() + k * zb.ncols, zref.get_lde_values(3 + 2 * k).data(), zb.ncols * 8) == 0);
 
+    // steps 6-7: the quotient from the resident batches, gate constraints from a program
+    // (constraint 0: wire0 * wire1 - wire2 + public_inputs_hash[1], filter: the first sigma column)
+    {
+      const unsigned qdb = 2;
+      vpbs::ResidentBatch cb(ctx, sig, rate_bits, cap_height, false);
+      const std::vector<F> alphas = {rng() % ORC_P, rng() % ORC_P};
+      const F pih[4] = {rng() % ORC_P, rng() % ORC_P, rng() % ORC_P, rng() % ORC_P};
+      auto ins = [](unsigned op, unsigned dst, unsigned ka, unsigned ia, unsigned kb, unsigned ib) {
+        return uint64_t(op) | uint64_t(dst) << 8 | uint64_t(ka) << 16 | uint64_t(kb) << 20 | uint64_t(ia) << 24 |
+               uint64_t(ib) << 40;
+      };
+      const std::vector<uint64_t> code = {ins(2, 0, 1, 0, 1, 1), ins(1, 0, 0, 0, 1, 2), ins(0, 0, 0, 0, 4, 1),
+                                          ins(3, 0, 0, 0, 0, 0), ins(4, 0, 2, 0, 0, 0)};
+      vpbs::GateProgram prog(ctx, code, {}, 1, 1);
+      auto qb = vpbs::GateProgram::quotient_polys(cb, 0, wb, zb, k_is, max_degree, qdb, betas, gammas, alphas,
+                                                  rate_bits, cap_height, &prog, pih);
+      auto wcoef = wb.coefficients(), scoef = cb.coefficients(), zcoef = zb.coefficients();
+      std::vector<const uint64_t*> wq, sq, zq;
+      for (auto& c : wcoef) wq.push_back(c.data());
+      for (auto& c : scoef) sq.push_back(c.data());
+      for (auto& c : zcoef) zq.push_back(c.data());
+      const std::size_t q = n << qdb;
+      std::vector<uint64_t> g0(q), g1(q), want((2u << qdb) * n);
+      uint64_t* gout[2] = {g0.data(), g1.data()};
+      CHECK(orc_gate_program_eval(code.data(), (uint32_t)code.size(), nullptr, 0, 1, 1, wq.data(), ncols, sq.data(),
+                                  num_routed, log_n, qdb, pih, alphas.data(), 2, gout) == 0);
+      const uint64_t* gin[2] = {g0.data(), g1.data()};
+      CHECK(orc_quotient_polys(wq.data(), sq.data(), zq.data(), k_is.data(), num_routed, log_n, max_degree, qdb,
+                               betas.data(), gammas.data(), alphas.data(), 2, gin, want.data()) == 0);
+      auto got = qb.coefficients();
+      CHECK(got.size() == (2u << qdb));
+      for (std::size_t c = 0; c < got.size(); c++) CHECK(std::memcmp(got[c].data(), want.data() + c * n, n * 8) == 0);
+    }
+
     // prove_openings: every polynomial of both batches at zeta, the two Zs at g zeta
     std::vector<std::vector<vpbs::FriPolynomialInfo>> fb(2);
     for (uint32_t j = 0; j < ncols; j++) fb[0].push_back({0, j});
