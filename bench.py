@@ -975,6 +975,36 @@ def run_step_standin(V, ctx, dev, n, m, ncap, d_digests, d_cap, pinned, colptrs,
     ref = V.PolynomialBatch.from_values(zcols, RATE_BITS, False, CAP_HEIGHT, ctx=ctx)
     check("step_standin.resident_z_batch_matches_host_pipeline",
           np.array_equal(ref.merkle_tree.cap, caps[1]) and np.array_equal(ref.merkle_tree.leaves[qidx], rows[1]))
+    # (c) the quotient of the same step computed on the device from the resident batches
+    # (vpbs_batch_quotient_polys: permutation terms, Z_H division, coset IFFT, 16 chunks committed), the
+    # gate constraints as alpha-reduced values from pinned host memory (8 MiB, what the 16 columns were)
+    h_cs = pinned((85, n)); h_cs[:] = V.synthetic_columns(85, n, 0x5EED0000 + 85)
+    h_cs[5:] = V.synthetic_columns(num_routed, n, 0x51630000)
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    alphas = rng.integers(0, P_GL, size=2, dtype=np.uint64)
+    gate = h_q.reshape(2, 8 * n)
+    gp = (u64p * 2)(gate[0].ctypes.data_as(u64p), gate[1].ctypes.data_as(u64p))
+    hcs, hw, hz = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    cap_tmp = np.empty((ncap, 4), np.uint64)
+    ctx.check(lib.vpbs_batch_commit(ctx.handle, colptrs(h_cs), 85, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None,
+                                    cap_tmp.ctypes.data_as(u64p), ctypes.byref(hcs), None))
+    ctx.check(lib.vpbs_batch_commit(ctx.handle, wp, 135, LOG_N, RATE_BITS, CAP_HEIGHT, 0, None,
+                                    cap_tmp.ctypes.data_as(u64p), ctypes.byref(hw), None))
+    ctx.check(lib.vpbs_batch_zs_partial_products(hw, sig.handle, max_degree, betas.ctypes.data_as(u64p),
+                                                 gammas.ctypes.data_as(u64p), 2, RATE_BITS, CAP_HEIGHT,
+                                                 cap_tmp.ctypes.data_as(u64p), ctypes.byref(hz), None))
+    q_ms = []
+    for _ in range(5):
+        hq = ctypes.c_void_p()
+        t0 = time.perf_counter()
+        ctx.check(lib.vpbs_batch_quotient_polys(hcs, 5, hw, hz, k_is.ctypes.data_as(u64p), num_routed, max_degree,
+                                                RATE_BITS, betas.ctypes.data_as(u64p), gammas.ctypes.data_as(u64p),
+                                                alphas.ctypes.data_as(u64p), 2, gp, None, None, RATE_BITS,
+                                                CAP_HEIGHT, cap_tmp.ctypes.data_as(u64p), ctypes.byref(hq), None))
+        q_ms.append((time.perf_counter() - t0) * 1e3)
+        lib.vpbs_batch_destroy(hq)
+    for h in (hz, hw, hcs):
+        lib.vpbs_batch_destroy(h)
     sig.close()
     h2d = 8 * n * (135 + 16)
     d2h = sum(32 * ncap + 2 * c * 16 + 28 * (8 * c + 32 * nlayers) for c in (135, 20, 16))
@@ -988,6 +1018,12 @@ def run_step_standin(V, ctx, dev, n, m, ncap, d_digests, d_cap, pinned, colptrs,
             "resident_api": "vpbs_batch_commit(wires) -> vpbs_batch_zs_partial_products (Z computed and "
                             "committed on the device) -> vpbs_batch_commit(quotient, from coefficients); "
                             "per batch: cap + openings at 2 points + 28 rows and Merkle paths",
+            "device_quotient_ms": min(q_ms[1:]),
+            "device_quotient_note": "vpbs_batch_quotient_polys on the resident batches of the step: the "
+                                    "permutation argument's vanishing terms over 2^19 points, alpha-reduced "
+                                    "gate values from the host (8 MiB), Z_H division, coset IFFT, the 16 "
+                                    "chunks committed; replaces the from-coefficients commit of the pipeline "
+                                    "above (bench.py --chain-steps times the step with it)",
             "full_pbs_730_steps_s_commit_part": 730 * res_ms * 1e-3}
 
 
@@ -1216,7 +1252,7 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         if sharded_now[0]:
             hs[2], full = sp.commit_from_host(ctx, ins[2], RATE_BITS, CAP_HEIGHT, True)
             caps[2][:] = full
-        elif args.chain_host_quotient:
+        elif args.chain_host_quotient or shard:  # (the sharded chain's reference trace takes the same form)
             ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, log_n, RATE_BITS, CAP_HEIGHT, 1, None,
                                             caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
         else:

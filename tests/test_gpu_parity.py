@@ -1099,7 +1099,9 @@ def test_gate_program_against_oracle(V, ctx, oracle, log_n, ncols, ncs, qdb):
     with pytest.raises(ValueError):
         V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4, program=bp)
     with pytest.raises(ValueError):          # register index beyond nregs
-        V.GateProgram(np.array([0 | 5 << 8], np.uint64), np.zeros(0, np.uint64), 2, 1, ctx)
+        V.GateProgram(np.array([0 | 5 << 8 | 3 << 16 | 3 << 20], np.uint64), np.zeros(1, np.uint64), 2, 1, ctx)
+    with pytest.raises(ValueError):          # a register read before anything wrote it
+        V.GateProgram(np.array([3 | 0 << 16 | 1 << 24], np.uint64), np.zeros(0, np.uint64), 2, 1, ctx)
     for b in (wb, cb, zb, qb):
         b.close()
     sg.close(); prog.close(); bp.close()

@@ -2425,6 +2425,7 @@ int vpbs_gate_program_upload(vpbs_ctx* ctx, const uint64_t* code, uint32_t ncode
   if (nregs == 0 || nregs > 224 || num_constraints == 0 || num_constraints > 4096)
     return fail(ctx, VPBS_ERR_ARG, "gate program: 1..224 registers, 1..4096 constraints");
   u32 max_wire = 0, max_const = 0;
+  std::vector<bool> written(nregs, false);  // straight-line code: a register must be written before it is read
   for (u32 pc = 0; pc < ncode; pc++) {
     const u64 ins = code[pc];
     const unsigned op = (unsigned)(ins & 0xff), dst = (unsigned)((ins >> 8) & 0xff);
@@ -2438,7 +2439,10 @@ int vpbs_gate_program_upload(vpbs_ctx* ctx, const uint64_t* code, uint32_t ncode
     const int nops = binary ? 2 : 1;
     for (int o = 0; o < nops; o++) {
       switch (kind[o]) {
-        case perm::K_REG: if (idx[o] >= nregs) return fail(ctx, VPBS_ERR_ARG, "gate program: bad register"); break;
+        case perm::K_REG:
+          if (idx[o] >= nregs) return fail(ctx, VPBS_ERR_ARG, "gate program: bad register");
+          if (!written[idx[o]]) return fail(ctx, VPBS_ERR_ARG, "gate program: register read before it is written");
+          break;
         case perm::K_WIRE: if (idx[o] + 1 > max_wire) max_wire = idx[o] + 1; break;
         case perm::K_CONST: if (idx[o] + 1 > max_const) max_const = idx[o] + 1; break;
         case perm::K_IMM: if (idx[o] >= nimm) return fail(ctx, VPBS_ERR_ARG, "gate program: bad immediate"); break;
@@ -2446,6 +2450,9 @@ int vpbs_gate_program_upload(vpbs_ctx* ctx, const uint64_t* code, uint32_t ncode
         default: return fail(ctx, VPBS_ERR_ARG, "gate program: bad operand kind");
       }
     }
+    if (op == perm::OP_MAD && !written[dst])
+      return fail(ctx, VPBS_ERR_ARG, "gate program: MAD accumulates into a register that was never written");
+    if (binary) written[dst] = true;
   }
   vpbs_gate_program* g = new (std::nothrow) vpbs_gate_program();
   if (!g) return fail(ctx, VPBS_ERR_OOM, "host allocation failed");
