@@ -1105,8 +1105,8 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         wires commit (135 value columns from the host) -> Z / partial products computed and committed
         on the device (20) -> quotient polynomials: permutation-argument terms on the device from the
         resident batches' LDE rows + alpha-reduced gate constraints from the host, Z_H division, coset
-        IFFT, 16 chunks committed (--chain-host-quotient and the sharded chain: 16 coefficient columns
-        from the host instead) ->
+        IFFT, 16 chunks committed (--chain-host-quotient: 16 coefficient columns from the host instead;
+        sharded chain: values of the own rows per rank, one all-reduce, then every rank's shard) ->
         openings of all 256 polynomials of the four FRI oracles (the circuit's constants/sigmas batch,
         85 columns, is committed once and stays resident) at zeta / g zeta -> prove_openings
         (alpha-combination of the 256 + 2 polynomials, division by X - z, final-polynomial LDE) -> FRI commit phase (3 arity-16 layers: tree, cap to
@@ -1154,7 +1154,7 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
     gate_ptrs = (u64p * 2)(gate_view[0].ctypes.data_as(u64p), gate_view[1].ctypes.data_as(u64p))
 
     gate_prog = None
-    if args.chain_gate_ops and not shard:
+    if args.chain_gate_ops:
         # stand-in for the circuit's compiled gate program (the real one comes from plonky2's gates through
         # a host-side compiler): Poseidon-gate-like rounds on 12 wires — every round
         # constrains its 12 S-box inputs against 12 further wires, raises them to the 7th power and mixes
@@ -1249,10 +1249,18 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
             sp.complete_cap(caps[1])
             t = lap("cap_gather", t)
         ins[2][:, 0] ^= caps[1].reshape(-1)[:16] >> np.uint64(1)  # the quotient depends on alpha <- cap 1
-        if sharded_now[0]:
+        if sharded_now[0] and args.chain_host_quotient:
             hs[2], full = sp.commit_from_host(ctx, ins[2], RATE_BITS, CAP_HEIGHT, True)
             caps[2][:] = full
-        elif args.chain_host_quotient or shard:  # (the sharded chain's reference trace takes the same form)
+        elif sharded_now[0]:
+            # the device quotient on sharded batches: every rank computes the values of its own rows, one
+            # all-reduce over NVLink completes them (2 x 2^19 x 8 B), every rank commits its shard
+            al = challenge(caps[1], 7, 2)
+            hs[2], full = sp.quotient_polys(ctx, cs["h"], CS - num_routed, hs[0], hs[1], k_is, max_degree, RATE_BITS,
+                                            bg[:2], bg[2:], al, RATE_BITS, CAP_HEIGHT, log_n,
+                                            gate_terms=None if gate_prog else gate_view, program=gate_prog)
+            caps[2][:] = full
+        elif args.chain_host_quotient:
             ctx.check(lib.vpbs_batch_commit(ctx.handle, pin[2], 16, log_n, RATE_BITS, CAP_HEIGHT, 1, None,
                                             caps[2].ctypes.data_as(u64p), ctypes.byref(hs[2]), None))
         else:
@@ -1416,13 +1424,14 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
                         "once (1 / ranks of them per rank) and reach the other GPUs by an NCCL "
                         "all-gather over NVLink; per commit the cap is "
                         "completed by an NCCL all-gather of 32 B per entry, per step the 28 x 4 opened "
-                        "rows + paths are collected by one all-reduce; IFFTs, Z, openings and the FRI "
+                        "rows + paths are collected by one all-reduce; the quotient values of a rank's rows "
+                        "are completed by one all-reduce (8 MiB); IFFTs, Z, openings and the FRI "
                         "commit phase are computed by every rank (they need all coefficients)"},
             "dtype": "u64",
             "data": "synthetic", "vs_baseline": None, "log_n": log_n,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step_approx": d2h,
             "gpu_launches_per_step": int(launches), "fri_layers": stats["fri_layers"],
-            "quotient": ("16 coefficient columns from the host" if (shard or args.chain_host_quotient) else
+            "quotient": ("16 coefficient columns from the host" if args.chain_host_quotient else
                          "device: permutation terms + tail; gate constraints %s" %
                          ("evaluated on the device from a synthetic %d-instruction program (%d registers)"
                           % (len(gate_prog.code), gate_prog.nregs) if gate_prog else

@@ -442,6 +442,24 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
                               const uint64_t* public_inputs_hash, uint32_t rate_bits, uint32_t cap_height,
                               uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats);
 
+/* The two halves of vpbs_batch_quotient_polys, for a proof whose resident batches are sharded by row
+ * range (vpbs_ctx_set_shard; needs rate_bits == quotient_degree_bits, i.e. the quotient domain is the
+ * whole LDE): vpbs_batch_quotient_values writes the quotient VALUES of the rank's own leaves into
+ * d_vals_out (DEVICE memory, num_challenges x (n << quotient_degree_bits), natural order; the entries of
+ * other shards are zeroed), the ranks add their buffers up (an all-reduce over NVLink: a value and
+ * zeros), and vpbs_quotient_commit_values turns the complete values into the rank's shard of the
+ * quotient batch (coset_ifft, chunks, from_coeffs).  On unsharded batches the pair equals
+ * vpbs_batch_quotient_polys. */
+int vpbs_batch_quotient_values(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
+                               vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
+                               uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
+                               const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
+                               const uint64_t* const* gate_terms, const vpbs_gate_program* program,
+                               const uint64_t* public_inputs_hash, uint64_t* d_vals_out);
+int vpbs_quotient_commit_values(vpbs_ctx* ctx, const uint64_t* d_vals, uint32_t num_challenges, uint32_t log_n,
+                                uint32_t quotient_degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                                uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

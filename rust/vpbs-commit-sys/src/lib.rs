@@ -168,6 +168,17 @@ extern "C" {
                                      program: *const vpbs_gate_program, public_inputs_hash: *const u64,
                                      rate_bits: u32, cap_height: u32, cap_out: *mut u64,
                                      out: *mut *mut vpbs_batch, stats: *mut vpbs_stats) -> c_int;
+    pub fn vpbs_batch_quotient_values(constants_sigmas: *mut vpbs_batch, sigmas_first_col: u32,
+                                      wires: *mut vpbs_batch, zs_pp: *mut vpbs_batch, k_is: *const u64,
+                                      num_routed: u32, max_degree: u32, quotient_degree_bits: u32,
+                                      betas: *const u64, gammas: *const u64, alphas: *const u64,
+                                      num_challenges: u32, gate_terms: *const *const u64,
+                                      program: *const vpbs_gate_program, public_inputs_hash: *const u64,
+                                      d_vals_out: *mut u64) -> c_int;
+    pub fn vpbs_quotient_commit_values(ctx: *mut vpbs_ctx, d_vals: *const u64, num_challenges: u32,
+                                       log_n: u32, quotient_degree_bits: u32, rate_bits: u32,
+                                       cap_height: u32, cap_out: *mut u64, out: *mut *mut vpbs_batch,
+                                       stats: *mut vpbs_stats) -> c_int;
     pub fn vpbs_gate_program_upload(ctx: *mut vpbs_ctx, code: *const u64, ncode: u32, imms: *const u64,
                                     nimm: u32, nregs: u32, num_constraints: u32,
                                     out: *mut *mut vpbs_gate_program) -> c_int;

@@ -993,13 +993,14 @@ def test_all_oracles_opened_in_one_round_trip(V, ctx, oracle):
     got = V.open_all_at_points(batches, pts)
     for b, g in zip(batches, got):
         assert np.array_equal(g, b.eval_ext2(pts))
-    idx = rng.integers(0, m, size=28, dtype=np.uint64)
-    opened = V.open_all_at_leaves(batches, idx)
-    for k, (b, (rows, sibs)) in enumerate(zip(batches, opened)):
-        ref = oracle.commit(mats[k], 3, 4, k == 3, None)
-        for q, i in enumerate(idx):
-            assert np.array_equal(rows[q], ref["leaves"][int(i)])
-            assert np.array_equal(sibs[q], oracle.merkle_prove(ref["digests"], m, 4, int(i)))
+    refs = [oracle.commit(mats[k], 3, 4, k == 3, None) for k in range(4)]
+    for count in (28, 13, 1):          # odd counts x odd widths: every region stays 16-byte aligned
+        idx = rng.integers(0, m, size=count, dtype=np.uint64)
+        opened = V.open_all_at_leaves(batches, idx)
+        for k, (b, (rows, sibs)) in enumerate(zip(batches, opened)):
+            for q, i in enumerate(idx):
+                assert np.array_equal(rows[q], refs[k]["leaves"][int(i)])
+                assert np.array_equal(sibs[q], oracle.merkle_prove(refs[k]["digests"], m, 4, int(i)))
     other = V.commit_resident(mats[0], 2, False, 4, ctx=ctx)      # different tree shape
     with pytest.raises(ValueError):
         V.open_all_at_leaves([batches[0], other], idx[:2])
@@ -1105,6 +1106,83 @@ def test_gate_program_against_oracle(V, ctx, oracle, log_n, ncols, ncs, qdb):
     for b in (wb, cb, zb, qb):
         b.close()
     sg.close(); prog.close(); bp.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_quotient_values_and_commit(V, oracle, world):
+    """The two halves of the device quotient on sharded batches (vpbs_batch_quotient_values ->
+    sum over the ranks -> vpbs_quotient_commit_values), `world` contexts on one GPU standing in for the
+    ranks: the summed values, the union of the caps and every rank's rows equal the unsharded
+    vpbs_batch_quotient_polys — with a gate program and with host gate terms."""
+    import ctypes
+    import torch
+    from test_oracle_golden import _random_gate_program
+    rng = np.random.default_rng(world)
+    log_n, ncols, ncs, num_routed, deg, qdb = 9, 20, 14, 8, 4, 3
+    n, q = 1 << log_n, (1 << log_n) << qdb
+    wires, cs = rand_u64(rng, (ncols, n)), rand_u64(rng, (ncs, n))
+    first_sigma = ncs - num_routed
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    betas, gammas, alphas = (rand_u64(rng, 2, edge_frac=0) for _ in range(3))
+    pih = rand_u64(rng, 4)
+    gate_host = rand_u64(rng, (2, q))
+    bld = _random_gate_program(V, rng, ncols, ncs, ngates=2, nops=30, nconstraints=6)
+    u64p = V._lib.u64p
+    ptr = lambda a: a.ctypes.data_as(u64p)
+    for use_program in (True, False):
+        with V.Context(0) as c0:
+            wb, cb = V.commit_resident(wires, 3, False, 4, ctx=c0), V.commit_resident(cs, 3, False, 4, ctx=c0)
+            sg = V.Sigmas(cs[first_sigma:], k_is, c0)
+            zb = V.commit_zs_partial_products(wb, sg, betas, gammas, deg, 3, 4)
+            prog0 = bld.build(c0) if use_program else None
+            ref = V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4,
+                                          gate_terms=None if use_program else gate_host, program=prog0,
+                                          public_inputs_hash=pih)
+            ref_cap = ref.merkle_tree.cap.copy()
+            ref_rows = ref.download().merkle_tree.leaves
+            for b in (wb, cb, zb, ref):
+                b.close()
+            sg.close()
+            if prog0:
+                prog0.close()
+        ranks, total = [], torch.zeros(2 * q, dtype=torch.int64, device="cuda")
+        for rank in range(world):
+            c = V.Context(0)
+            c.set_shard(rank, world)
+            wb, cb = V.commit_resident(wires, 3, False, 4, ctx=c), V.commit_resident(cs, 3, False, 4, ctx=c)
+            sg = V.Sigmas(cs[first_sigma:], k_is, c)
+            zb = V.commit_zs_partial_products(wb, sg, betas, gammas, deg, 3, 4)
+            prog = bld.build(c) if use_program else None
+            with pytest.raises(ValueError):      # the one-call form refuses sharded batches
+                V.commit_quotient_polys(cb, first_sigma, wb, zb, k_is, deg, qdb, betas, gammas, alphas, 3, 4)
+            vals = torch.empty(2 * q, dtype=torch.int64, device="cuda")
+            gtp = None if use_program else (u64p * 2)(ptr(gate_host[0]), ptr(gate_host[1]))
+            c.check(c.lib.vpbs_batch_quotient_values(cb.handle, first_sigma, wb.handle, zb.handle, ptr(k_is),
+                                                     num_routed, deg, qdb, ptr(betas), ptr(gammas), ptr(alphas), 2,
+                                                     gtp, prog.handle if prog else None, ptr(pih), vals.data_ptr()))
+            torch.cuda.synchronize()
+            total += vals
+            ranks.append((c, wb, cb, zb, sg, prog))
+        torch.cuda.synchronize()
+        cap_union = np.zeros((16, 4), np.uint64)
+        for rank, (c, wb, cb, zb, sg, prog) in enumerate(ranks):
+            cap = np.empty((16, 4), np.uint64)
+            h = ctypes.c_void_p()
+            c.check(c.lib.vpbs_quotient_commit_values(c.handle, total.data_ptr(), 2, log_n, qdb, 3, 4, ptr(cap),
+                                                      ctypes.byref(h), None))
+            own = slice(rank * 16 // world, (rank + 1) * 16 // world)
+            cap_union[own] = cap[own]
+            qb = V.ResidentPolynomialBatch(c, h, cap, 2 << qdb, log_n, 3, False, None)
+            first, nl = qb.shard
+            idx = rng.integers(first, first + nl, size=6, dtype=np.uint64)
+            assert np.array_equal(qb.merkle_tree.get_many(idx), ref_rows[idx])
+            for b in (qb, wb, cb, zb):
+                b.close()
+            sg.close()
+            if prog:
+                prog.close()
+            c.close()
+        assert np.array_equal(cap_union, ref_cap)
 
 
 def test_quotient_polys_plonk_identity_with_gate_program(V, ctx):

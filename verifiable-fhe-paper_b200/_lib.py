@@ -114,6 +114,12 @@ SIGNATURES = {
                                              _c.c_uint32, _c.POINTER(u64p), _c.c_void_p, u64p, _c.c_uint32,
                                              _c.c_uint32, u64p, _c.POINTER(_c.c_void_p),
                                              _c.POINTER(VpbsStats)]),
+    "vpbs_batch_quotient_values": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, u64p,
+                                              _c.c_uint32, _c.c_uint32, _c.c_uint32, u64p, u64p, u64p,
+                                              _c.c_uint32, _c.POINTER(u64p), _c.c_void_p, u64p, _c.c_void_p]),
+    "vpbs_quotient_commit_values": (_c.c_int, [_ctx, _c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_uint32,
+                                               _c.c_uint32, _c.c_uint32, u64p, _c.POINTER(_c.c_void_p),
+                                               _c.POINTER(VpbsStats)]),
     "vpbs_gate_program_upload": (_c.c_int, [_ctx, u64p, _c.c_uint32, u64p, _c.c_uint32, _c.c_uint32,
                                             _c.c_uint32, _c.POINTER(_c.c_void_p)]),
     "vpbs_gate_program_destroy": (None, [_c.c_void_p]),

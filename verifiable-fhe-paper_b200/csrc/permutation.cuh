@@ -217,18 +217,22 @@ quotient_permutation_terms(const u64* __restrict__ wires, u32 wires_width, const
                            u32 cs_width, u32 sigmas_first, const u64* __restrict__ zs, u32 zs_width,
                            const u64* __restrict__ k_is, u32 num_routed, u32 max_degree, u32 K, u32 nc,
                            unsigned log_q, unsigned qdb, const __grid_constant__ QuotientParams qp,
-                           ntt::Roots R, const u64* __restrict__ gate_terms, u64* __restrict__ vals) {
-  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+                           ntt::Roots R, const u64* __restrict__ gate_terms, u64 k0, u64 kcount,
+                           u64* __restrict__ vals) {
+  // leaves [k0, k0 + kcount) of the quotient domain: all of it, or the shard whose rows the batches hold
+  // (row r of the matrices is leaf k0 + r; the "next" point lies in the same LDE block, hence the same shard)
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const u64 q = 1ULL << log_q;
-  if (k >= q) return;
+  if (t >= kcount) return;
+  const u64 k = k0 + t;
   const u64 i = log_q ? (__brevll(k) >> (64 - log_q)) : 0;
   const u64 i_next = (i + (1ULL << qdb)) & (q - 1);
   const u64 k_next = log_q ? (__brevll(i_next) >> (64 - log_q)) : 0;
   const u64 x = gl::mul(gl::COSET_SHIFT, ntt::root_of<false>(R, log_q, i));
-  const u64* wrow = wires + k * wires_width;
-  const u64* srow = cs + k * cs_width + sigmas_first;
-  const u64* zrow = zs + k * zs_width;
-  const u64* znext = zs + k_next * zs_width;
+  const u64* wrow = wires + t * wires_width;
+  const u64* srow = cs + t * cs_width + sigmas_first;
+  const u64* zrow = zs + t * zs_width;
+  const u64* znext = zs + (k_next - k0) * zs_width;
   const unsigned cosetk = (unsigned)(i & ((1u << qdb) - 1));
   u64 res[4] = {0, 0, 0, 0};
   // Z(1) = 1 terms
@@ -290,15 +294,15 @@ gate_program_eval(const u64* __restrict__ code, u32 ncode, const u64* __restrict
                   const u64* __restrict__ apow /* nc x num_constraints: alpha_c^j, then public_inputs_hash[4] */,
                   u32 num_constraints,
                   const u64* __restrict__ wires, u32 wires_width, const u64* __restrict__ cs, u32 cs_width,
-                  u32 nc, unsigned log_q, u64* __restrict__ out) {
+                  u32 nc, unsigned log_q, u64 k0, u64 kcount, u64* __restrict__ out) {
   extern __shared__ u64 regs[];  // [register][thread]
-  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const u64 q = 1ULL << log_q;
-  const bool live = k < q;
-  const u64 kk = live ? k : 0;
-  const u64 i = log_q ? (__brevll(kk) >> (64 - log_q)) : 0;
-  const u64* wrow = wires + kk * wires_width;
-  const u64* crow = cs + kk * cs_width;
+  const bool live = t0 < kcount;
+  const u64 tt = live ? t0 : 0;  // row of the (possibly sharded) leaf matrices; leaf k0 + tt
+  const u64 i = log_q ? (__brevll(k0 + tt) >> (64 - log_q)) : 0;
+  const u64* wrow = wires + tt * wires_width;
+  const u64* crow = cs + tt * cs_width;
   const unsigned tid = threadIdx.x;
   u64 total[4] = {0, 0, 0, 0}, gacc[4] = {0, 0, 0, 0};  // fully unrolled below: registers
   // register file: plain 32-bit shared-memory addresses (LDS / STS; the generic-pointer form re-derives

@@ -2484,24 +2484,22 @@ void vpbs_gate_program_destroy(vpbs_gate_program* g) {
   delete g;
 }
 
-// [P2] plonk/prover.rs compute_quotient_polys, gate-independent part (see perm::quotient_permutation_terms),
-// then per challenge coset_ifft + chunks of n, committed from coefficients as the quotient batch.
-int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
-                              vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
-                              uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
-                              const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
-                              const uint64_t* const* gate_terms, const vpbs_gate_program* program,
-                              const uint64_t* public_inputs_hash, uint32_t rate_bits, uint32_t cap_height,
-                              uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {
-  if (!wires || !constants_sigmas || !zs_pp) return VPBS_ERR_STATE;
+}  // extern "C"
+
+namespace {
+// compute_quotient_polys up to the quotient VALUES: d_vals[c * q + i] for the leaves the batches hold
+// (all of the quotient domain, or — sharded batches — the rank's row range, the rest zeroed).
+int quotient_values_core(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
+                         vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed, uint32_t max_degree,
+                         uint32_t qdb, const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas,
+                         uint32_t nc, const uint64_t* const* gate_terms, const vpbs_gate_program* program,
+                         const uint64_t* public_inputs_hash, u64* d_vals) {
   vpbs_ctx* ctx = wires->ctx;
-  int rc = bind(ctx);
-  if (rc) return rc;
+  int rc;
   if (constants_sigmas->ctx != ctx || zs_pp->ctx != ctx)
     return fail(ctx, VPBS_ERR_STATE, "batches of different contexts");
-  if (!k_is || !betas || !gammas || !alphas || !cap_out || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
-  *out = nullptr;
-  const u32 nc = num_challenges, log_n = wires->log_n, qdb = quotient_degree_bits;
+  if (!k_is || !betas || !gammas || !alphas || !d_vals) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  const u32 log_n = wires->log_n;
   if (nc == 0 || nc > 4) return fail(ctx, VPBS_ERR_ARG, "num_challenges must be 1..4");
   if (num_routed == 0 || max_degree < 2) return fail(ctx, VPBS_ERR_ARG, "num_routed == 0 or max_degree < 2");
   const u32 K = (num_routed + max_degree - 1) / max_degree;
@@ -2510,14 +2508,15 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
     return fail(ctx, VPBS_ERR_ARG, "batch widths do not match num_routed / the chunk count");
   if (constants_sigmas->log_n != log_n || zs_pp->log_n != log_n)
     return fail(ctx, VPBS_ERR_ARG, "batches of different degree");
+  const bool sharded = wires->sharded();
   for (const vpbs_batch* b : {wires, constants_sigmas, zs_pp}) {
-    if (b->sharded()) return fail(ctx, VPBS_ERR_ARG, "the quotient needs unsharded batches");
     if (qdb > b->rate_bits || qdb >= 5)
       return fail(ctx, VPBS_ERR_ARG, "quotient_degree_bits exceeds the batches' rate_bits");
+    if (b->sharded() != sharded || b->first_leaf != wires->first_leaf || b->nleaves != wires->nleaves)
+      return fail(ctx, VPBS_ERR_ARG, "the three batches must hold the same rows");
+    if (sharded && b->rate_bits != qdb)
+      return fail(ctx, VPBS_ERR_ARG, "sharded batches: the quotient domain must be the whole LDE (rate_bits == quotient_degree_bits)");
   }
-  if (log_n + rate_bits > 30) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
-  if (cap_height > log_n + rate_bits)
-    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
   if (program) {
     if (gate_terms) return fail(ctx, VPBS_ERR_ARG, "gate_terms and a gate program are mutually exclusive");
     if (program->device != ctx->device) return fail(ctx, VPBS_ERR_STATE, "gate program lives on another device");
@@ -2526,9 +2525,7 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
   }
   const unsigned log_q = log_n + qdb;
   const u64 n = 1ULL << log_n, q = 1ULL << log_q;
-  const uint64_t l0 = ctx->launches;
-  cudaEvent_t e0 = ctx->ev[4], e3 = ctx->ev[7];
-  if (stats) cudaEventRecord(e0, ctx->stream);
+  const u64 k0 = sharded ? wires->first_leaf : 0, kcount = sharded ? wires->nleaves : q;
 
   perm::QuotientParams qp;
   memset(&qp, 0, sizeof qp);
@@ -2549,15 +2546,13 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
   }
   qp.n_canon = n % gl::P;
 
-  u64 *d_k = nullptr, *d_vals = nullptr, *d_gate = nullptr, *d_work = nullptr, *d_coef = nullptr;
+  u64 *d_k = nullptr, *d_gate = nullptr;
   if ((rc = arena_get(ctx, "idx", (size_t)num_routed * 8, (void**)&d_k))) return rc;
-  if ((rc = arena_get(ctx, "in", (size_t)nc * q * 8, (void**)&d_vals))) return rc;
-  if ((rc = arena_get(ctx, "work", (size_t)nc * q * 8, (void**)&d_work))) return rc;
-  if ((rc = arena_get(ctx, "zs_out", (size_t)nc * q * 8, (void**)&d_coef))) return rc;
-  if ((rc = ensure_roots(ctx, log_n + (rate_bits > qdb ? rate_bits : qdb)))) return rc;
+  if ((rc = ensure_roots(ctx, log_q))) return rc;
   std::vector<u64> kc(k_is, k_is + num_routed);
   for (u64& v : kc) v = gl::canon(v);
   CU(ctx, cudaMemcpyAsync(d_k, kc.data(), (size_t)num_routed * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (sharded) CU(ctx, cudaMemsetAsync(d_vals, 0, (size_t)nc * q * 8, ctx->stream));
   if (gate_terms) {
     if ((rc = arena_get(ctx, "gate_terms", (size_t)nc * q * 8, (void**)&d_gate))) return rc;
     for (u32 c = 0; c < nc; c++) {
@@ -2583,22 +2578,42 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(ctx, cudaFuncSetAttribute((const void*)perm::gate_program_eval,
                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    perm::gate_program_eval<<<(unsigned)((q + perm::PROG_THREADS - 1) / perm::PROG_THREADS), perm::PROG_THREADS,
-                              smem, ctx->stream>>>(program->code, program->ncode, program->imm, d_ap, ng,
-                                                   wires->leaves, wires->width, constants_sigmas->leaves,
-                                                   constants_sigmas->width, nc, log_q, d_gate);
+    perm::gate_program_eval<<<(unsigned)((kcount + perm::PROG_THREADS - 1) / perm::PROG_THREADS),
+                              perm::PROG_THREADS, smem, ctx->stream>>>(
+        program->code, program->ncode, program->imm, d_ap, ng, wires->leaves, wires->width,
+        constants_sigmas->leaves, constants_sigmas->width, nc, log_q, k0, kcount, d_gate);
     ctx->launches++;
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // `ap` dies with this scope
   }
   const ntt::Roots R{ctx->roots, ctx->roots_log};
-  perm::quotient_permutation_terms<<<(unsigned)((q + 127) / 128), 128, 0, ctx->stream>>>(
+  perm::quotient_permutation_terms<<<(unsigned)((kcount + 127) / 128), 128, 0, ctx->stream>>>(
       wires->leaves, wires->width, constants_sigmas->leaves, constants_sigmas->width, sigmas_first_col,
-      zs_pp->leaves, zs_pp->width, d_k, num_routed, max_degree, K, nc, log_q, qdb, qp, R, d_gate, d_vals);
+      zs_pp->leaves, zs_pp->width, d_k, num_routed, max_degree, K, nc, log_q, qdb, qp, R, d_gate, k0, kcount,
+      d_vals);
   ctx->launches++;
   CU(ctx, cudaGetLastError());
   // `kc` must outlive its copy; the kernel above is ordered after it on the same stream
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return VPBS_OK;
+}
+
+// The tail of compute_quotient_polys + prove() step 7: coset_ifft(7) of the complete quotient values,
+// chunks of n coefficients, committed from coefficients (the context's shard of the rows, if it shards).
+int quotient_commit_core(vpbs_ctx* ctx, const u64* d_vals, u32 nc, u32 log_n, u32 qdb, u32 rate_bits,
+                         u32 cap_height, uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats, uint64_t l0) {
+  int rc;
+  if (log_n + rate_bits > 30 || qdb >= 5) return fail(ctx, VPBS_ERR_ARG, "log_n + rate_bits > 30");
+  if (cap_height > log_n + rate_bits)
+    return fail(ctx, VPBS_ERR_ARG, "cap_height should be at most log2(leaves.len())");
+  const unsigned log_q = log_n + qdb;
+  const u64 q = 1ULL << log_q;
+  cudaEvent_t e0 = ctx->ev[4], e3 = ctx->ev[7];
+  if (stats) cudaEventRecord(e0, ctx->stream);
+  u64 *d_work = nullptr, *d_coef = nullptr;
+  if ((rc = arena_get(ctx, "work", (size_t)nc * q * 8, (void**)&d_work))) return rc;
+  if ((rc = arena_get(ctx, "zs_out", (size_t)nc * q * 8, (void**)&d_coef))) return rc;
+  if ((rc = ensure_roots(ctx, log_n + (rate_bits > qdb ? rate_bits : qdb)))) return rc;
   // coset_ifft(7): inverse transform (natural order in and out, scaled by 1/q), then 7^-j
   if ((rc = run_transform<true>(ctx, d_vals, q, nc, log_q, d_work, Out::Natural, d_coef, q, 0, nullptr,
                                 gl::inv(q % gl::P))))
@@ -2631,6 +2646,71 @@ int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_firs
   }
   *out = b;
   return VPBS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// [P2] plonk/prover.rs compute_quotient_polys (see perm::quotient_permutation_terms) + step 7's commit.
+int vpbs_batch_quotient_polys(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
+                              vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
+                              uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
+                              const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
+                              const uint64_t* const* gate_terms, const vpbs_gate_program* program,
+                              const uint64_t* public_inputs_hash, uint32_t rate_bits, uint32_t cap_height,
+                              uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {
+  if (!wires || !constants_sigmas || !zs_pp) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = wires->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!cap_out || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  *out = nullptr;
+  if (wires->sharded())
+    return fail(ctx, VPBS_ERR_ARG, "sharded batches: use vpbs_batch_quotient_values, exchange the values, "
+                                   "then vpbs_quotient_commit_values");
+  if (num_challenges == 0 || num_challenges > 4) return fail(ctx, VPBS_ERR_ARG, "num_challenges must be 1..4");
+  const uint64_t l0 = ctx->launches;
+  const u64 q = 1ULL << (wires->log_n + quotient_degree_bits);
+  if (quotient_degree_bits >= 5 || wires->log_n + quotient_degree_bits > 30)
+    return fail(ctx, VPBS_ERR_ARG, "quotient_degree_bits exceeds the batches' rate_bits");
+  u64* d_vals = nullptr;
+  if ((rc = arena_get(ctx, "in", (size_t)num_challenges * q * 8, (void**)&d_vals))) return rc;
+  if ((rc = quotient_values_core(constants_sigmas, sigmas_first_col, wires, zs_pp, k_is, num_routed, max_degree,
+                                 quotient_degree_bits, betas, gammas, alphas, num_challenges, gate_terms,
+                                 program, public_inputs_hash, d_vals)))
+    return rc;
+  return quotient_commit_core(ctx, d_vals, num_challenges, wires->log_n, quotient_degree_bits, rate_bits,
+                              cap_height, cap_out, out, stats, l0);
+}
+
+// The two halves of the call above for a proof whose batches are sharded by row range: every rank
+// computes the quotient values of ITS leaves (the rest of d_vals_out is zeroed), the ranks add their
+// buffers up (an all-reduce: a value and zeros), and every rank commits its shard of the quotient batch.
+int vpbs_batch_quotient_values(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col, vpbs_batch* wires,
+                               vpbs_batch* zs_pp, const uint64_t* k_is, uint32_t num_routed,
+                               uint32_t max_degree, uint32_t quotient_degree_bits, const uint64_t* betas,
+                               const uint64_t* gammas, const uint64_t* alphas, uint32_t num_challenges,
+                               const uint64_t* const* gate_terms, const vpbs_gate_program* program,
+                               const uint64_t* public_inputs_hash, uint64_t* d_vals_out) {
+  if (!wires || !constants_sigmas || !zs_pp) return VPBS_ERR_STATE;
+  vpbs_ctx* ctx = wires->ctx;
+  int rc = bind(ctx);
+  if (rc) return rc;
+  return quotient_values_core(constants_sigmas, sigmas_first_col, wires, zs_pp, k_is, num_routed, max_degree,
+                              quotient_degree_bits, betas, gammas, alphas, num_challenges, gate_terms, program,
+                              public_inputs_hash, d_vals_out);
+}
+
+int vpbs_quotient_commit_values(vpbs_ctx* ctx, const uint64_t* d_vals, uint32_t num_challenges, uint32_t log_n,
+                                uint32_t quotient_degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                                uint64_t* cap_out, vpbs_batch** out, vpbs_stats* stats) {
+  int rc = bind(ctx);
+  if (rc) return rc;
+  if (!d_vals || !cap_out || !out) return fail(ctx, VPBS_ERR_ARG, "null pointer");
+  *out = nullptr;
+  if (num_challenges == 0 || num_challenges > 4) return fail(ctx, VPBS_ERR_ARG, "num_challenges must be 1..4");
+  return quotient_commit_core(ctx, d_vals, num_challenges, log_n, quotient_degree_bits, rate_bits, cap_height,
+                              cap_out, out, stats, ctx->launches);
 }
 
 int vpbs_batch_commit_dev(vpbs_ctx* ctx, const uint64_t* d_cols, uint32_t ncols, uint32_t log_n,
@@ -2812,7 +2892,7 @@ int vpbs_batches_open(vpbs_batch* const* batches, uint32_t nbatches, const uint6
         b->first_leaf != b0->first_leaf || b->nleaves != b0->nleaves)
       return fail(ctx, VPBS_ERR_ARG, "batches opened together must have the same tree shape and shard");
     if (!rows_out[k] || (num_layers && !siblings_out[k])) return fail(ctx, VPBS_ERR_ARG, "null output pointer");
-    total += count * ((size_t)b->width * 8 + (size_t)num_layers * 32);
+    total += count * ((size_t)b->width * 8 + (size_t)num_layers * 32) + 32;  // + alignment slack per region
   }
   u64 *d_idx = nullptr, *d_buf = nullptr;
   if ((rc = batch_indices(b0, leaf_indices, count, &d_idx))) return rc;
@@ -2826,7 +2906,7 @@ int vpbs_batches_open(vpbs_batch* const* batches, uint32_t nbatches, const uint6
     merkle::gather_rows<<<(unsigned)count, 128, 0, ctx->stream>>>(b->leaves, b->width, d_idx, count, d_rows);
     ctx->launches++;
     CU(ctx, cudaMemcpyAsync(rows_out[k], d_rows, row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    off += row_bytes;
+    off += (row_bytes + 15) & ~(size_t)15;  // gather_siblings moves hashes as 16-byte halves
     if (num_layers) {
       u64* d_sib = d_buf + off / 8;
       const u64 tot = count * num_layers;
@@ -2834,7 +2914,7 @@ int vpbs_batches_open(vpbs_batch* const* batches, uint32_t nbatches, const uint6
           b->digests, d_idx, count, num_layers, sub_digests, d_sib);
       ctx->launches++;
       CU(ctx, cudaMemcpyAsync(siblings_out[k], d_sib, sib_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-      off += sib_bytes;
+      off += (sib_bytes + 15) & ~(size_t)15;
     }
   }
   CU(ctx, cudaGetLastError());

@@ -133,6 +133,44 @@ class ShardedProof:
                                                 cap.ctypes.data_as(_lib.u64p), ctypes.byref(h), None))
         return h, self.complete_cap(cap)
 
+    def quotient_polys(self, ctx, constants_sigmas, sigmas_first_col: int, wires, zs_pp, k_is,
+                       max_degree: int, quotient_degree_bits: int, betas, gammas, alphas, rate_bits: int,
+                       cap_height: int, log_n: int, gate_terms=None, program=None, public_inputs_hash=None):
+        """prove() steps 6-7 with sharded batches (handles as vpbs_batch_commit* returned them): every
+        rank computes the quotient values of its own rows (vpbs_batch_quotient_values), the buffers are
+        added up across the ranks (all-reduce over NCCL / NVLink: 8 bytes per challenge and point), and
+        every rank commits its shard of the quotient batch (vpbs_quotient_commit_values); the cap is
+        completed like every sharded commit's.  Returns (batch handle, full cap)."""
+        import ctypes
+        import numpy as np
+        import torch.distributed as dist
+        from . import _lib
+        from .plonky2_api import _as_u64, _ptr
+        u64p = _lib.u64p
+        k = _as_u64(k_is).reshape(-1)
+        b, g, a = (_as_u64(v).reshape(-1) for v in (betas, gammas, alphas))
+        nc, q = b.size, (1 << log_n) << quotient_degree_bits
+        d_vals = self._tensor(("qvals", nc, q), nc * q)
+        gt_arr, gtp = None, None
+        if gate_terms is not None:
+            gt_arr = _as_u64(gate_terms)
+            gtp = (u64p * nc)(*[_ptr(gt_arr[c]) for c in range(nc)])
+        h = lambda x: x.handle if hasattr(x, "handle") else x
+        ctx.check(ctx.lib.vpbs_batch_quotient_values(
+            h(constants_sigmas), sigmas_first_col, h(wires), h(zs_pp), _ptr(k), k.size, max_degree,
+            quotient_degree_bits, _ptr(b), _ptr(g), _ptr(a), nc, gtp,
+            program.handle if program is not None else None,
+            _ptr(_as_u64(public_inputs_hash).reshape(4)) if public_inputs_hash is not None else None,
+            d_vals.data_ptr()))
+        if self.world > 1:
+            dist.all_reduce(d_vals)     # int64 wrap-around addition of a value and zeros: exact
+        cap = np.empty((1 << cap_height, 4), np.uint64)
+        out = ctypes.c_void_p()
+        ctx.check(ctx.lib.vpbs_quotient_commit_values(ctx.handle, d_vals.data_ptr(), nc, log_n,
+                                                      quotient_degree_bits, rate_bits, cap_height,
+                                                      cap.ctypes.data_as(u64p), ctypes.byref(out), None))
+        return out, self.complete_cap(cap)
+
     def owned(self, leaf_indices, nleaves_total: int):
         """Boolean mask of the leaf indices this rank's shard holds."""
         import numpy as np
