@@ -51,3 +51,36 @@ for rank in range(4):
     rb.get_lde_rows(V.reverse_bits(first, 16), 4, 5)
     rb.download(); rb.close(); rb2.close(); c.close()
 print("sanitizer workload (second half) done")
+# the device quotient: permutation terms + tail, gate terms from the host and from a program, and the
+# two-halves form on sharded batches
+n13 = 1 << 10
+wires = rng.integers(0, 2**64, size=(20, n13), dtype=np.uint64)
+cs = rng.integers(0, 2**64, size=(14, n13), dtype=np.uint64)
+k_is = V.get_unique_coset_shifts(n13, 8)
+bb, gg, aa = (rng.integers(1, V.P, size=2, dtype=np.uint64) for _ in range(3))
+Bd = V.GateProgramBuilder()
+acc = Bd.mul(Bd.wire(0), Bd.const(1))
+acc = Bd.mad(acc, Bd.wire(19), Bd.imm(12345))
+Bd.emit(0, Bd.sub(acc, Bd.pih(2)))
+Bd.emit(3, Bd.add(Bd.wire(7), Bd.const(0)))
+Bd.end_gate(Bd.selector_filter(0, 1, range(3), True))
+for shard in ((0, 1), (1, 2)):
+    c = V.Context(0)
+    c.set_shard(*shard)
+    wb, cb = V.commit_resident(wires, 3, False, 4, ctx=c), V.commit_resident(cs, 3, False, 4, ctx=c)
+    sg = V.Sigmas(cs[6:], k_is, c)
+    zb = V.commit_zs_partial_products(wb, sg, bb, gg, 4, 3, 4)
+    prog = Bd.build(c)
+    if shard[1] == 1:
+        V.commit_quotient_polys(cb, 6, wb, zb, k_is, 4, 3, bb, gg, aa, 3, 4, program=prog, public_inputs_hash=bb.repeat(2)).close()
+        V.commit_quotient_polys(cb, 6, wb, zb, k_is, 4, 2, bb, gg, aa, 3, 4,
+                                gate_terms=rng.integers(0, 2**64, size=(2, n13 << 2), dtype=np.uint64)).close()
+    else:
+        import torch
+        sp = V.ShardedProof(0, 1, torch.device("cuda", 0))
+        h, cap = sp.quotient_polys(c, cb, 6, wb, zb, k_is, 4, 3, bb, gg, aa, 3, 4, 10, program=prog)
+        c.lib.vpbs_batch_destroy(h)
+    for x in (wb, cb, zb):
+        x.close()
+    sg.close(); prog.close(); c.close()
+print("sanitizer workload (quotient) done")
