@@ -17,15 +17,31 @@ def step():
     f.commit_layer(4, 4); f.fold([7, 8]); f.commit_layer(4, 4); f.fold([9, 10]); f.final_poly(); f.query(0, [1, 2, 3]); f.close()
     b.merkle_tree.get_many(np.arange(5, dtype=np.uint64)); b.eval_ext2(np.array([[1, 2]], np.uint64))
     V.PolynomialBatch.from_values(cols, 3, False, 4, ctx=ctx)
+    # second half of round 2: sigma-carrying constants batch, device quotient from a freshly uploaded gate
+    # program, all-oracle openings, staged (pageable) upload with chunk-wise sponge hashing
+    cb = V.commit_resident(sig, 3, False, 4, ctx=ctx)
+    B = V.GateProgramBuilder()
+    B.emit(0, B.mad(B.mul(B.wire(0), B.wire(1)), B.wire(2), B.imm(7)))
+    B.end_gate(B.selector_filter(0, 1, range(3), False))
+    prog = B.build(ctx)
+    q = V.commit_quotient_polys(cb, 0, b, z, k, 8, 3, [3, 4], [5, 6], [7, 8], 3, 4, program=prog)
+    V.open_all_at_points([b, z, q], np.array([[1, 2], [3, 4]], np.uint64))
+    V.open_all_at_leaves([b, z, q], np.arange(7, dtype=np.uint64))
+    prog.close(); q.close(); cb.close()
     s.close(); z.close(); b.close()
+import psutil
 for _ in range(5):
     step()
 torch.cuda.synchronize()
+rss0 = psutil.Process().memory_info().rss
 free0 = torch.cuda.mem_get_info()[0]
 for _ in range(300):
     step()
 torch.cuda.synchronize()
 free1 = torch.cuda.mem_get_info()[0]
 print("free before %.1f MiB, after %.1f MiB, delta %.1f MiB" % (free0 / 2**20, free1 / 2**20, (free0 - free1) / 2**20))
+rss1 = psutil.Process().memory_info().rss
+print("host RSS before %.1f MiB, after %.1f MiB, threads %d" % (rss0 / 2**20, rss1 / 2**20, psutil.Process().num_threads()))
 assert free0 - free1 < 64 * 2**20, "device memory grows"
+assert rss1 - rss0 < 256 * 2**20, "host memory grows"
 print("leak check ok")
