@@ -237,36 +237,67 @@ quotient_permutation_terms(const u64* __restrict__ wires, u32 wires_width, const
   u64 res[4] = {0, 0, 0, 0};
   // Z(1) = 1 terms
   const u64 l0 = gl::mul(qp.zh[cosetk], inv_nonzero(gl::mul(qp.n_canon, gl::sub(x, 1))));
-  for (u32 c = 0; c < nc; c++) {
-    const u64 term = gl::mul(l0, gl::sub(__ldg(zrow + c), 1));
-    for (u32 d = 0; d < nc; d++) res[d] = gl::add(res[d], gl::mul(term, qp.apow[d][c]));
+  // (loops over the challenges are unrolled to 4 with a guard so that res / num / den stay in registers)
+#pragma unroll
+  for (u32 c = 0; c < 4; c++) {
+    if (c < nc) {
+      const u64 term = gl::mul(l0, gl::sub(__ldg(zrow + c), 1));
+#pragma unroll
+      for (u32 d = 0; d < 4; d++)
+        if (d < nc) res[d] = gl::add(res[d], gl::mul(term, qp.apow[d][c]));
+    }
   }
   // partial-product checks, chunk by chunk (the wire / sigma values of a chunk serve every challenge)
   for (u32 t = 0; t < K; t++) {
     u64 num[4] = {1, 1, 1, 1}, den[4] = {1, 1, 1, 1};
     const u32 j1 = (t + 1) * max_degree < num_routed ? (t + 1) * max_degree : num_routed;
-    for (u32 j = t * max_degree; j < j1; j++) {
-      const u64 wv = __ldg(wrow + j), sv = __ldg(srow + j);
-      const u64 kx = gl::mul(__ldg(k_is + j), x);
-      for (u32 c = 0; c < nc; c++) {
-        // wire + beta s + gamma in one 128-bit multiply-add (exact, reduced once); the running
-        // products stay arbitrary u64 representatives until the chunk is complete
-        num[c] = gl::mul_lazy(num[c], ntt::mul_add2_lazy(qp.beta[c], kx, wv, qp.gamma[c]));
-        den[c] = gl::mul_lazy(den[c], ntt::mul_add2_lazy(qp.beta[c], sv, wv, qp.gamma[c]));
+    for (u32 j0 = t * max_degree; j0 < j1; j0 += 8) {
+      // eight wires' values and sigmas are requested before any of them is used: a thread's loads hit one
+      // or two cache lines of its own rows, and issued one by one between dependent multiplies they made
+      // the kernel latency-bound (ncu: 10 long-scoreboard stalls per issue, 1.75x the algorithmic DRAM bytes)
+      u64 wv[8], sv[8];
+#pragma unroll
+      for (u32 u = 0; u < 8; u++) {
+        const u32 j = j0 + u < j1 ? j0 + u : j1 - 1;
+        wv[u] = __ldg(wrow + j);
+        sv[u] = __ldg(srow + j);
+      }
+#pragma unroll
+      for (u32 u = 0; u < 8; u++) {
+        if (j0 + u < j1) {
+          const u64 kx = gl::mul(__ldg(k_is + j0 + u), x);
+#pragma unroll
+          for (u32 c = 0; c < 4; c++) {
+            if (c < nc) {
+              // wire + beta s + gamma in one 128-bit multiply-add (exact, reduced once); the running
+              // products stay arbitrary u64 representatives until the chunk is complete
+              num[c] = gl::mul_lazy(num[c], ntt::mul_add2_lazy(qp.beta[c], kx, wv[u], qp.gamma[c]));
+              den[c] = gl::mul_lazy(den[c], ntt::mul_add2_lazy(qp.beta[c], sv[u], wv[u], qp.gamma[c]));
+            }
+          }
+        }
       }
     }
-    for (u32 c = 0; c < nc; c++) {
-      const u64 prev = t == 0 ? __ldg(zrow + c) : __ldg(zrow + nc + c * (K - 1) + (t - 1));
-      const u64 next = t == K - 1 ? __ldg(znext + c) : __ldg(zrow + nc + c * (K - 1) + t);
-      const u64 term = gl::sub(gl::mul(prev, num[c]), gl::mul(next, den[c]));
-      const u32 idx = nc + c * K + t;
-      for (u32 d = 0; d < nc; d++) res[d] = gl::add(res[d], gl::mul(term, qp.apow[d][idx]));
+#pragma unroll
+    for (u32 c = 0; c < 4; c++) {
+      if (c < nc) {
+        const u64 prev = t == 0 ? __ldg(zrow + c) : __ldg(zrow + nc + c * (K - 1) + (t - 1));
+        const u64 next = t == K - 1 ? __ldg(znext + c) : __ldg(zrow + nc + c * (K - 1) + t);
+        const u64 term = gl::sub(gl::mul(prev, num[c]), gl::mul(next, den[c]));
+        const u32 idx = nc + c * K + t;
+#pragma unroll
+        for (u32 d = 0; d < 4; d++)
+          if (d < nc) res[d] = gl::add(res[d], gl::mul(term, qp.apow[d][idx]));
+      }
     }
   }
-  for (u32 c = 0; c < nc; c++) {
-    u64 r = res[c];
-    if (gate_terms) r = gl::add(r, gl::mul(qp.agate[c], gl::canon(__ldg(gate_terms + (u64)c * q + i))));
-    vals[(u64)c * q + i] = gl::mul(r, qp.zh_inv[cosetk]);
+#pragma unroll
+  for (u32 c = 0; c < 4; c++) {
+    if (c < nc) {
+      u64 r = res[c];
+      if (gate_terms) r = gl::add(r, gl::mul(qp.agate[c], gl::canon(__ldg(gate_terms + (u64)c * q + i))));
+      vals[(u64)c * q + i] = gl::mul(r, qp.zh_inv[cosetk]);
+    }
   }
 }
 // ---- gate constraints as a straight-line program -----------------------------------------------------------
