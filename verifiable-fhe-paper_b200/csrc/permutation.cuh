@@ -317,40 +317,64 @@ quotient_permutation_terms(const u64* __restrict__ wires, u32 wires_width, const
 // Constraint j enters the total of challenge c times alpha_c^j (reduce_with_powers), so per gate the
 // kernel keeps sum_j alpha_c^j c_j and multiplies it by the filter at ENDGATE: exactly
 // sum_j alpha_c^j sum_g filter_g c_{g,j}.  Registers live in shared memory ([register][thread]).
-constexpr int PROG_THREADS = 128;
+#ifndef VPBS_PROG_THREADS
+#define VPBS_PROG_THREADS 128
+#endif
+constexpr int PROG_THREADS = VPBS_PROG_THREADS;
 enum : unsigned { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_EMIT = 3, OP_ENDGATE = 4, OP_MAD = 5 };
 enum : unsigned { K_REG = 0, K_WIRE = 1, K_CONST = 2, K_IMM = 3, K_PIH = 4 };
+// PROG_POINTS points per thread share one decode of every instruction (the decode, dispatch and loop
+// bookkeeping are about 40 % of the per-instruction cost with one point per thread); a CTA covers
+// PROG_THREADS * PROG_POINTS consecutive leaves, point p of thread t being leaf base + p * PROG_THREADS + t
+// so that a warp still reads consecutive rows.
+#ifndef VPBS_PROG_POINTS
+#define VPBS_PROG_POINTS 1
+#endif
+constexpr int PROG_POINTS = VPBS_PROG_POINTS;
+constexpr unsigned MAX_PROG_REGS = 224u * 128u / (PROG_THREADS * PROG_POINTS);  // 224 KB of shared memory
 __global__ void __launch_bounds__(PROG_THREADS)
 gate_program_eval(const u64* __restrict__ code, u32 ncode, const u64* __restrict__ imm,
                   const u64* __restrict__ apow /* nc x num_constraints: alpha_c^j, then public_inputs_hash[4] */,
                   u32 num_constraints,
                   const u64* __restrict__ wires, u32 wires_width, const u64* __restrict__ cs, u32 cs_width,
                   u32 nc, unsigned log_q, u64 k0, u64 kcount, u64* __restrict__ out) {
-  extern __shared__ u64 regs[];  // [register][thread]
-  const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ u64 regs[];  // [register][point][thread]
+  constexpr int PP = PROG_POINTS;
   const u64 q = 1ULL << log_q;
-  const bool live = t0 < kcount;
-  const u64 tt = live ? t0 : 0;  // row of the (possibly sharded) leaf matrices; leaf k0 + tt
-  const u64 i = log_q ? (__brevll(k0 + tt) >> (64 - log_q)) : 0;
-  const u64* wrow = wires + tt * wires_width;
-  const u64* crow = cs + tt * cs_width;
   const unsigned tid = threadIdx.x;
-  u64 total[4] = {0, 0, 0, 0}, gacc[4] = {0, 0, 0, 0};  // fully unrolled below: registers
+  const u64 base = (u64)blockIdx.x * (PROG_THREADS * PP);
+  bool live[PP];
+  const u64 *wrow[PP], *crow[PP];
+#pragma unroll
+  for (int p = 0; p < PP; p++) {
+    const u64 t0 = base + (u64)p * PROG_THREADS + tid;
+    live[p] = t0 < kcount;
+    const u64 tt = live[p] ? t0 : 0;  // row of the (possibly sharded) leaf matrices; leaf k0 + tt
+    wrow[p] = wires + tt * wires_width;
+    crow[p] = cs + tt * cs_width;
+  }
+  u64 total[PP][4], gacc[PP][4];  // fully unrolled below: registers
+#pragma unroll
+  for (int p = 0; p < PP; p++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) total[p][c] = gacc[p][c] = 0;
   // register file: plain 32-bit shared-memory addresses (LDS / STS; the generic-pointer form re-derives
-  // the shared window base at every access) — register r of this thread lives at rbase + r * 1024
+  // the shared window base at every access) — register r, point p of this thread lives at
+  // rbase + (r * PP + p) * PROG_THREADS * 8
   const unsigned rbase = (unsigned)__cvta_generic_to_shared(regs) + tid * 8u;
-  auto lds = [&](unsigned r) -> u64 {
+  constexpr unsigned RSTRIDE = PROG_THREADS * 8u;
+  auto lds = [&](unsigned r, int p) -> u64 {
     u64 v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(rbase + (r << 10)));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(rbase + (r * PP + p) * RSTRIDE));
     return v;
   };
   // operand of a kind other than "register": every such source is a global-memory table, so the kind
   // only SELECTS a base pointer (a switch / if-chain becomes an indirect branch through a
   // constant-memory jump table, the top stall of the first version of this kernel)
   const u64* pihp = apow + (u64)nc * num_constraints;  // the caller appends public_inputs_hash there
-  auto fetch_slow = [&](unsigned kind, unsigned idx) -> u64 {
-    const u64* p = kind == K_IMM ? imm : kind == K_WIRE ? wrow : kind == K_CONST ? crow : pihp;
-    return __ldg(p + idx);
+  auto fetch_slow = [&](unsigned kind, unsigned idx, int p) -> u64 {
+    const u64* ptr = kind == K_IMM ? imm : kind == K_WIRE ? wrow[p] : kind == K_CONST ? crow[p] : pihp;
+    return __ldg(ptr + idx);
   };
   // the instruction stream is the same for every thread: the next word is fetched while the current
   // one executes, and register operands (the common case) skip the operand-kind dispatch
@@ -361,33 +385,69 @@ gate_program_eval(const u64* __restrict__ code, u32 ncode, const u64* __restrict
     const unsigned op = lo & 0xff, dst = (lo >> 8) & 0xff;
     const unsigned ka = (lo >> 16) & 0xf, kb = (lo >> 20) & 0xf;
     const unsigned ia = (lo >> 24) | ((hi & 0xff) << 8), ib = (hi >> 8) & 0xffff;
-    const u64 a = ka == K_REG ? lds(ia) : fetch_slow(ka, ia);
+    u64 a[PP];
+    if (ka == K_REG) {
+#pragma unroll
+      for (int p = 0; p < PP; p++) a[p] = lds(ia, p);
+    } else {
+#pragma unroll
+      for (int p = 0; p < PP; p++) a[p] = fetch_slow(ka, ia, p);
+    }
     if (op <= OP_MUL || op == OP_MAD) {
-      const u64 b = kb == K_REG ? lds(ib) : fetch_slow(kb, ib);
-      u64 r;
-      if (op == OP_MAD) r = gl::canon(ntt::mul_add2_lazy(a, b, lds(dst), 0));
-      else if (op == OP_MUL) r = gl::mul(a, b);
-      else if (op == OP_ADD) r = gl::add(a, b);
-      else r = gl::sub(a, b);
-      asm volatile("st.shared.u64 [%0], %1;" ::"r"(rbase + (dst << 10)), "l"(r) : "memory");
+      u64 b[PP], r[PP];
+      if (kb == K_REG) {
+#pragma unroll
+        for (int p = 0; p < PP; p++) b[p] = lds(ib, p);
+      } else {
+#pragma unroll
+        for (int p = 0; p < PP; p++) b[p] = fetch_slow(kb, ib, p);
+      }
+      if (op == OP_MAD) {
+#pragma unroll
+        for (int p = 0; p < PP; p++) r[p] = gl::canon(ntt::mul_add2_lazy(a[p], b[p], lds(dst, p), 0));
+      } else if (op == OP_MUL) {
+#pragma unroll
+        for (int p = 0; p < PP; p++) r[p] = gl::mul(a[p], b[p]);
+      } else if (op == OP_ADD) {
+#pragma unroll
+        for (int p = 0; p < PP; p++) r[p] = gl::add(a[p], b[p]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < PP; p++) r[p] = gl::sub(a[p], b[p]);
+      }
+#pragma unroll
+      for (int p = 0; p < PP; p++)
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(rbase + (dst * PP + p) * RSTRIDE), "l"(r[p]) : "memory");
     } else if (op == OP_EMIT) {
 #pragma unroll
       for (u32 c = 0; c < 4; c++)
-        if (c < nc) gacc[c] = gl::add(gacc[c], gl::mul(a, __ldg(apow + (u64)c * num_constraints + ib)));
+        if (c < nc) {
+          const u64 w = __ldg(apow + (u64)c * num_constraints + ib);
+#pragma unroll
+          for (int p = 0; p < PP; p++) gacc[p][c] = gl::add(gacc[p][c], gl::mul(a[p], w));
+        }
     } else {  // OP_ENDGATE
 #pragma unroll
       for (u32 c = 0; c < 4; c++)
         if (c < nc) {
-          total[c] = gl::add(total[c], gl::mul(gacc[c], a));
-          gacc[c] = 0;
+#pragma unroll
+          for (int p = 0; p < PP; p++) {
+            total[p][c] = gl::add(total[p][c], gl::mul(gacc[p][c], a[p]));
+            gacc[p][c] = 0;
+          }
         }
     }
     ins = next;
   }
-  if (live) {
 #pragma unroll
-    for (u32 c = 0; c < 4; c++)
-      if (c < nc) out[(u64)c * q + i] = total[c];
+  for (int p = 0; p < PP; p++) {
+    if (live[p]) {
+      const u64 k = k0 + base + (u64)p * PROG_THREADS + tid;
+      const u64 i = log_q ? (__brevll(k) >> (64 - log_q)) : 0;
+#pragma unroll
+      for (u32 c = 0; c < 4; c++)
+        if (c < nc) out[(u64)c * q + i] = total[p][c];
+    }
   }
 }
 

@@ -2422,8 +2422,8 @@ int vpbs_gate_program_upload(vpbs_ctx* ctx, const uint64_t* code, uint32_t ncode
   if (rc) return rc;
   if (!out || (!code && ncode) || (!imms && nimm)) return fail(ctx, VPBS_ERR_ARG, "null pointer");
   *out = nullptr;
-  if (nregs == 0 || nregs > 224 || num_constraints == 0 || num_constraints > 4096)
-    return fail(ctx, VPBS_ERR_ARG, "gate program: 1..224 registers, 1..4096 constraints");
+  if (nregs == 0 || nregs > perm::MAX_PROG_REGS || num_constraints == 0 || num_constraints > 4096)
+    return fail(ctx, VPBS_ERR_ARG, "gate program: too many registers (shared-memory register file) or constraints");
   u32 max_wire = 0, max_const = 0;
   std::vector<bool> written(nregs, false);  // straight-line code: a register must be written before it is read
   for (u32 pc = 0; pc < ncode; pc++) {
@@ -2573,12 +2573,13 @@ int quotient_values_core(vpbs_batch* constants_sigmas, uint32_t sigmas_first_col
     if ((rc = arena_get(ctx, "gate_apow", ap.size() * 8, (void**)&d_ap))) return rc;
     if ((rc = arena_get(ctx, "gate_terms", (size_t)nc * q * 8, (void**)&d_gate))) return rc;
     CU(ctx, cudaMemcpyAsync(d_ap, ap.data(), ap.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const size_t smem = (size_t)program->nregs * perm::PROG_THREADS * sizeof(u64);
+    const size_t smem = (size_t)program->nregs * perm::PROG_THREADS * perm::PROG_POINTS * sizeof(u64);
     CU(ctx, cudaFuncSetAttribute((const void*)perm::gate_program_eval,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(ctx, cudaFuncSetAttribute((const void*)perm::gate_program_eval,
                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    perm::gate_program_eval<<<(unsigned)((kcount + perm::PROG_THREADS - 1) / perm::PROG_THREADS),
+    const u64 per_cta = (u64)perm::PROG_THREADS * perm::PROG_POINTS;
+    perm::gate_program_eval<<<(unsigned)((kcount + per_cta - 1) / per_cta),
                               perm::PROG_THREADS, smem, ctx->stream>>>(
         program->code, program->ncode, program->imm, d_ap, ng, wires->leaves, wires->width,
         constants_sigmas->leaves, constants_sigmas->width, nc, log_q, k0, kcount, d_gate);

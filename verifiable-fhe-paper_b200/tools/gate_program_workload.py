@@ -1,6 +1,8 @@
 import sys; sys.path.insert(0, '.')
 import numpy as np, time
 import vfhe_b200 as V
+if len(sys.argv) > 2:  # A/B of interpreter variants: a library built with other -DVPBS_PROG_THREADS / _POINTS
+    V._lib.LIB_PATH = sys.argv[2]
 ctx = V.Context(0)
 rng = np.random.default_rng(1)
 log_n = 16; n = 1 << log_n
