@@ -16,7 +16,7 @@ def load_bench():
 
 
 def test_recorded_bench_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r2_final.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r2_final3.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
               "scaling", "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e",
               "gpu_launches", "clocks"):
@@ -32,8 +32,10 @@ def test_recorded_bench_line_has_the_contract_keys():
     assert d["e2e"]["h2d_bytes_per_step"] == 8 * 128 * (1 << 16)
     assert d["gpu_launches"] > 0 and d["vs_baseline"] is None and d["dtype"] == "u64"
     assert d["self_checks"]["failed"] == []
+    assert d["e2e_pageable"]["inputs_only"]["ms_per_step"] < d["e2e_pageable"]["inputs_only"]["ms_per_step_driver_staging"]
+    assert d["step_standin"]["device_quotient_ms"] > 0
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    ref = json.load(open(os.path.join(ROOT, "profiles", "bench_r2_reference_arm.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "bench_r2_reference_arm3.json")))
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert ref["config"]["workload"] == d["config"]["workload"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
