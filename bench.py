@@ -1114,8 +1114,10 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
         served from the four resident batches and the FRI layers;
       eager (round 1's form): the three commits with every output downloaded.
     The challenges are derived from the caps by plain mixing (a stand-in for the Poseidon
-    challenger, which stays on the CPU); witness generation and the gate constraints of the quotient
-    need plonky2 and are not part of either number."""
+    challenger, which stays on the CPU); witness generation needs plonky2 and is not part of either
+    number; the gate constraints of the quotient are either supplied by the host as alpha-reduced values
+    (default: their evaluation is then not part of the number) or evaluated on the device from a
+    synthetic gate program (--chain-gate-ops N)."""
     import numpy as np
     lib, u64p = ctx.lib, V._lib.u64p
     log_n = args.chain_log_n
@@ -1441,9 +1443,10 @@ def run_chain(args, V, ctx, rank, world, barrier, max_over_ranks, emit):
             "eager_note": "round 1's form of the step: the three commits with coefficients, LDE rows and "
                           "digests of the first two downloaded to pinned host memory (--chain-eager)",
             "clocks": clocks,
-            "note": "witness generation, the gate constraints of the quotient and the Poseidon challenger "
-                    "run in plonky2 on the CPU and are not part of this number; challenges are derived from "
-                    "the caps by plain mixing"}))
+            "note": "witness generation and the Poseidon challenger run in plonky2 on the CPU and are not part "
+                    "of this number; the gate constraints of the quotient: see `quotient` (as values from "
+                    "the host their evaluation is not part of it either); challenges are derived from the "
+                    "caps by plain mixing"}))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
