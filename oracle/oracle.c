@@ -880,6 +880,7 @@ int orc_quotient_polys(const uint64_t* const* wires, const uint64_t* const* sigm
   const uint32_t nterms = nc + nc * K;
   uint64_t** lw = malloc(sizeof(uint64_t*) * (2 * num_routed + nzp));
   if (!lw) return -1;
+#pragma omp parallel for schedule(dynamic) num_threads(orc_get_threads())
   for (uint32_t j = 0; j < 2 * num_routed + nzp; j++) {
     lw[j] = malloc(q * sizeof(uint64_t));
     const uint64_t* src = j < num_routed ? wires[j] : j < 2 * num_routed ? sigmas[j - num_routed] : zs_pp[j - 2 * num_routed];
@@ -956,6 +957,7 @@ int orc_gate_program_eval(const uint64_t* code, uint32_t ncode, const uint64_t* 
     return -1;
   const uint64_t n = 1ULL << log_n, q = n << qdb;
   uint64_t** lw = malloc(sizeof(uint64_t*) * (nwires + ncs));
+#pragma omp parallel for schedule(dynamic) num_threads(orc_get_threads())
   for (uint32_t j = 0; j < nwires + ncs; j++) {
     lw[j] = malloc(q * sizeof(uint64_t));
     orc_lde(j < nwires ? wires[j] : cs[j - nwires], log_n, qdb, lw[j]);

@@ -1108,6 +1108,30 @@ def test_gate_program_against_oracle(V, ctx, oracle, log_n, ncols, ncs, qdb):
     sg.close(); prog.close(); bp.close()
 
 
+def test_quotient_polys_step_shapes_full_size(V, ctx, oracle):
+    """BASELINE.json configs[2] stand-in, steps 4-7 at full size: 135 wire columns (80 routed), the 85-column
+    constants/sigmas batch, Z / partial products on the device, then the quotient (2^19 points, alpha-reduced
+    gate values from the host): the 16 committed chunks and their cap equal the oracle's."""
+    n, num_routed = 1 << 16, 80
+    wires = V.synthetic_columns(135, n, 0x5EED0000 + 135)
+    cs = V.synthetic_columns(85, n, 0x5EED0000 + 85)
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    rng = np.random.default_rng(8)
+    betas, gammas, alphas = (rng.integers(1, P, size=2, dtype=np.uint64) for _ in range(3))
+    gate = rng.integers(0, 2**64, size=(2, n << 3), dtype=np.uint64)
+    wb, cb = V.commit_resident(wires, 3, False, 4, ctx=ctx), V.commit_resident(cs, 3, False, 4, ctx=ctx)
+    sg = V.Sigmas(cs[5:], k_is, ctx)
+    zb = V.commit_zs_partial_products(wb, sg, betas, gammas, 8, 3, 4)
+    qb = V.commit_quotient_polys(cb, 5, wb, zb, k_is, 8, 3, betas, gammas, alphas, 3, 4, gate_terms=gate)
+    want = oracle.quotient_polys(wb.coefficients()[:num_routed], cb.coefficients()[5:], zb.coefficients(), k_is,
+                                 8, 3, betas, gammas, alphas, gate)
+    assert np.array_equal(qb.coefficients(), want)
+    assert np.array_equal(qb.merkle_tree.cap, oracle.commit(want, 3, 4, True)["cap"])
+    for b in (wb, cb, zb, qb):
+        b.close()
+    sg.close()
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_sharded_quotient_values_and_commit(V, oracle, world):
     """The two halves of the device quotient on sharded batches (vpbs_batch_quotient_values ->

@@ -600,6 +600,15 @@ class ResidentPolynomialBatch:
                                                             _ptr(out) if count else None))
         return out
 
+    def coefficients(self) -> np.ndarray:
+        """PolynomialBatch.polynomials of the resident batch: (ncols, n) coefficient columns, copied to
+        the host (leaves and digests stay on the device)."""
+        n = 1 << self.degree_log
+        coeffs = np.empty((self.ncols, n), np.uint64)
+        cop = (u64p * self.ncols)(*[_ptr(coeffs[c]) for c in range(self.ncols)])
+        self.ctx.check(self.ctx.lib.vpbs_batch_download(self.handle, cop, None, None))
+        return coeffs
+
     def download(self) -> "PolynomialBatch":
         """Materialise the eager form (polynomials, leaves, digests) on the host; of a sharded batch:
         all polynomials, the shard's own rows and the digests of its own cap subtrees."""
