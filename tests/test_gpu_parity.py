@@ -1132,6 +1132,34 @@ def test_quotient_polys_step_shapes_full_size(V, ctx, oracle):
     sg.close()
 
 
+def test_gate_program_step_shapes_full_size(V, ctx, oracle):
+    """The gate-program interpreter at the N=1024 step's shapes (2^19 points, 135 wire and 85 constant
+    columns, a 400-instruction random program with MADs over every operand kind): quotient chunks equal the
+    oracle's, whose gate terms come from its own interpreter."""
+    from test_oracle_golden import _random_gate_program
+    n, num_routed = 1 << 16, 80
+    wires = V.synthetic_columns(135, n, 0x5EED0000 + 135)
+    cs = V.synthetic_columns(85, n, 0x5EED0000 + 85)
+    k_is = V.get_unique_coset_shifts(n, num_routed)
+    rng = np.random.default_rng(18)
+    betas, gammas, alphas = (rng.integers(1, P, size=2, dtype=np.uint64) for _ in range(3))
+    pih = rng.integers(0, P, size=4, dtype=np.uint64)
+    bld = _random_gate_program(V, rng, 135, 85, ngates=6, nops=60, nconstraints=20)
+    prog = bld.build(ctx)
+    wb, cb = V.commit_resident(wires, 3, False, 4, ctx=ctx), V.commit_resident(cs, 3, False, 4, ctx=ctx)
+    sg = V.Sigmas(cs[5:], k_is, ctx)
+    zb = V.commit_zs_partial_products(wb, sg, betas, gammas, 8, 3, 4)
+    qb = V.commit_quotient_polys(cb, 5, wb, zb, k_is, 8, 3, betas, gammas, alphas, 3, 4, program=prog,
+                                 public_inputs_hash=pih)
+    wc, cc = wb.coefficients(), cb.coefficients()
+    gt = oracle.gate_program_eval(bld.code, bld.imms, bld.nregs, bld.num_constraints, wc, cc, 3, pih, alphas)
+    want = oracle.quotient_polys(wc[:num_routed], cc[5:], zb.coefficients(), k_is, 8, 3, betas, gammas, alphas, gt)
+    assert np.array_equal(qb.coefficients(), want)
+    for b in (wb, cb, zb, qb):
+        b.close()
+    sg.close(); prog.close()
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_sharded_quotient_values_and_commit(V, oracle, world):
     """The two halves of the device quotient on sharded batches (vpbs_batch_quotient_values ->
