@@ -81,6 +81,18 @@ class ShardedProof:
             t = self._buf[key] = torch.empty(numel, dtype=torch.int64, device=self.device)
         return t
 
+    def _before_library_call(self, ctx):
+        """torch / NCCL work is ordered on torch's current stream; the library runs on the context's.
+        When they differ, what torch enqueued must be finished before the library reads it (library
+        calls themselves return synchronised)."""
+        import torch
+        if self.device.type != "cuda":
+            return
+        cur = torch.cuda.current_stream(self.device)
+        # ctx.stream == 0 means "the context's own stream" (never torch's, whose legacy stream is also 0)
+        if ctx.stream == 0 or cur.cuda_stream != ctx.stream:
+            cur.synchronize()
+
     def complete_cap(self, cap):
         """cap: (ncap, 4) uint64 numpy array as a sharded commit returns it (own entries filled, the
         rest zero), completed IN PLACE with the other shards' entries (all-gather).  ncap must be a
@@ -108,9 +120,9 @@ class ShardedProof:
         [r * C' / world, (r + 1) * C' / world) and the ranks exchange them GPU to GPU (NCCL
         all-gather over NVLink), then each commits its own row range from device memory
         (vpbs_batch_commit_dev under Context.set_shard) and the cap is completed by the all-gather of
-        the subtree roots.  Returns (batch handle, full cap).  The context must have been switched to
-        torch's current stream (Context.set_stream) so that the copies, the collective and the
-        kernels are ordered."""
+        the subtree roots.  Returns (batch handle, full cap).  Fastest when the context runs on torch's
+        current stream (Context.set_stream): copies, collective and kernels are then ordered on one
+        stream; otherwise the torch side is synchronised before the library reads its results."""
         import ctypes
         import numpy as np
         import torch
@@ -128,6 +140,7 @@ class ShardedProof:
             dist.all_gather_into_tensor(d_all.view(-1), mine.reshape(-1))
         cap = np.empty((1 << cap_height, 4), np.uint64)
         h = ctypes.c_void_p()
+        self._before_library_call(ctx)
         ctx.check(ctx.lib.vpbs_batch_commit_dev(ctx.handle, d_all.data_ptr(), ncols, log_n, rate_bits,
                                                 cap_height, int(inputs_are_coeffs),
                                                 cap.ctypes.data_as(_lib.u64p), ctypes.byref(h), None))
@@ -166,6 +179,7 @@ class ShardedProof:
             dist.all_reduce(d_vals)     # int64 wrap-around addition of a value and zeros: exact
         cap = np.empty((1 << cap_height, 4), np.uint64)
         out = ctypes.c_void_p()
+        self._before_library_call(ctx)
         ctx.check(ctx.lib.vpbs_quotient_commit_values(ctx.handle, d_vals.data_ptr(), nc, log_n,
                                                       quotient_degree_bits, rate_bits, cap_height,
                                                       cap.ctypes.data_as(u64p), ctypes.byref(out), None))
