@@ -33,7 +33,10 @@
 extern "C" {
 #endif
 
-#define VPBS_ABI_VERSION 2
+/* 3: additions only (second half of round 2): vpbs_ctx_set_host_threads, vpbs_ctx_set_shard,
+ * vpbs_batch_shard, vpbs_batches_eval_ext2, vpbs_batches_open, vpbs_batch_quotient_polys / _values,
+ * vpbs_quotient_commit_values, vpbs_gate_program_upload / _destroy; every version-2 entry is unchanged. */
+#define VPBS_ABI_VERSION 3
 #define VPBS_SALT_SIZE 4 /* [P2] fri/oracle.rs SALT_SIZE */
 
 typedef enum vpbs_status {

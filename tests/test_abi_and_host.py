@@ -23,7 +23,7 @@ def test_library_builds_and_exports_every_declared_symbol(V):
     for s in syms:
         assert hasattr(lib, s), "libvpbs_commit.so does not export %s" % s
     assert sorted(V._lib.SIGNATURES) == syms, "binding and header disagree"
-    assert lib.vpbs_abi_version() == 2
+    assert lib.vpbs_abi_version() == 3
 
 
 def test_library_contains_sm100a_code_only(V):
