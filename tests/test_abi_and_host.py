@@ -180,3 +180,38 @@ def test_documented_kernel_variants_still_compile(flag, tmp_path):
                         "-D" + flag, "-c", "-o", str(tmp_path / "v.o"),
                         os.path.join(pkg, "tools", "selftest.cu")], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_gate_program_builder_host_logic(V, oracle):
+    """The gate-program assembler (pure host code): instruction packing, immediate dedup, register
+    recycling at end_gate, and plonky2's selector filter prod_{i != row}(i - s) [* (UNUSED - s)] — checked
+    by running the assembled program through the oracle's interpreter on constant polynomials."""
+    P = 2**64 - 2**32 + 1
+    b = V.GateProgramBuilder()
+    assert b.imm(5) == b.imm(5 + P) and b.imm(7) != b.imm(5) and b.imms == [5, 7]
+    r0 = b.add(b.wire(3), b.const(2))
+    r1 = b.mad(r0, b.wire(1), b.imm(7))
+    assert r0 == r1 == (0, 0) and b.nregs == 1
+    op, dst, ka, kb, ia, ib = (b.code[0] & 0xff, (b.code[0] >> 8) & 0xff, (b.code[0] >> 16) & 0xf,
+                               (b.code[0] >> 20) & 0xf, (b.code[0] >> 24) & 0xffff, (b.code[0] >> 40) & 0xffff)
+    assert (op, dst, ka, kb, ia, ib) == (0, 0, 1, 2, 3, 2)
+    assert b.code[1] & 0xff == 5 and (b.code[1] >> 8) & 0xff == 0
+    b.emit(4, r1)
+    assert b.num_constraints == 5
+    f = b.selector_filter(0, 1, range(3), True)
+    b.end_gate(f)
+    assert b._next == 0                      # registers recycled
+    with pytest.raises(ValueError):
+        b.mad(b.wire(0), b.wire(1), b.wire(2))   # accumulator must be a register
+    with pytest.raises(ValueError):
+        b.into(224, b.ADD, b.wire(0), b.wire(1))
+    # evaluate on constant polynomials: every wire / constant column is a constant function
+    n, qdb = 4, 1
+    wires = np.zeros((4, n), np.uint64); wires[:, 0] = [11, 13, 17, 19]      # coefficient form: constants
+    cs = np.zeros((3, n), np.uint64); cs[:, 0] = [5, 23, 29]                 # selector s = 5
+    alphas = np.array([3], np.uint64)
+    got = oracle.gate_program_eval(b.code, b.imms, b.nregs, b.num_constraints, wires, cs, qdb, None, alphas)
+    s = 5
+    filt = (0 - s) * (2 - s) * (2**32 - 1 - s)
+    want = (((19 + 29) + 13 * 7) * pow(3, 4, P) * filt) % P
+    assert want != 0 and (got == np.uint64(want)).all()
